@@ -1,0 +1,215 @@
+/*
+ * lmcu.h — C ABI of liblmcu.so, the B200 (sm_100a) ray-tracing hot path for Lightmetrica v3.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, POD structs, int status codes, no
+ * exceptions and no C++/torch types across the line.  The Lightmetrica plugin (plugin/lm_cuda.cpp:
+ * accel::cuda_bvh, renderer::{raycast,ao,pt}_cuda) and the Python host (lmcu/) both bind exactly
+ * these entry points.  Every entry cites the reference interface it replaces, relative to
+ * /root/reference.
+ *
+ * Conventions shared with the reference:
+ *   - all host-side scalars are FP64 (lm::Float is double, include/lm/common.h:279-287);
+ *   - Inf = 1e10 is a finite sentinel and the default tmax, Eps = 1e-3 the default tmin
+ *     (include/lm/math.h:54-55);
+ *   - matrices are column-major 4x4 (glm), vectors xyz;
+ *   - film buffers are row-major, row 0 = bottom row (raster y grows upward,
+ *     src/film/film_bitmap.cpp:212-218,256-260), 3 channels.
+ */
+#ifndef LMCU_H
+#define LMCU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LMCU_INF 1e10
+#define LMCU_EPS 1e-3
+
+/* status codes (0 = ok); lmcu_last_error() has the message for the calling thread */
+enum {
+    LMCU_OK = 0,
+    LMCU_ERR_INVALID_ARGUMENT = 1,   /* lm::Error::InvalidArgument */
+    LMCU_ERR_UNSUPPORTED = 2,        /* lm::Error::Unsupported */
+    LMCU_ERR_CUDA = 3,               /* a CUDA runtime call or kernel failed */
+    LMCU_ERR_NO_DEVICE = 4           /* no CUDA device: there is NO CPU fallback */
+};
+
+/* ---------------------------------------------------------------------------------------------
+ * Ray / hit records.  Replace lm::Ray (include/lm/math.h:67-79) + the (tmin,tmax) arguments of
+ * lm::Accel::intersect (include/lm/accel.h:70) and lm::Accel::Hit (include/lm/accel.h:49-55).
+ * The 208-byte Hit::global_transform is NOT copied per ray: `primitive` identifies the instance
+ * and the caller looks the transform up in its own table.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct LmcuRay {
+    double o[3];
+    double d[3];
+    double tmin;
+    double tmax;
+} LmcuRay;                                   /* 64 bytes */
+
+typedef struct LmcuHit {
+    double t;                                /* hit distance; tmin <= t <= tmax (inclusive) */
+    double u, v;                             /* barycentrics: p = p1(1-u-v) + p2 u + p3 v */
+    int32_t primitive;                       /* LmcuPrimitive::node_index of the instance; -1 = miss */
+    int32_t face;                            /* mesh-local face index */
+} LmcuHit;                                   /* 32 bytes */
+
+/* ---------------------------------------------------------------------------------------------
+ * Scene description = what a Lightmetrica Accel/Renderer pulls out of lm::Scene:
+ *   meshes      <- Mesh::foreach_triangle (include/lm/mesh.h:64-100), un-indexed triangle soup
+ *   primitives  <- Scene::traverse_primitive_nodes (include/lm/scene.h:163-177): one entry per
+ *                  primitive node that has a mesh, with its GLOBAL transform (instance groups are
+ *                  flattened, src/scene.cpp:216-230), in traversal order
+ *   materials   <- material::{diffuse,glossy,glass,mirror} parameters
+ *   lights      <- Scene light table order (src/scene.cpp:281-286)
+ *   camera      <- camera::pinhole (src/camera/camera_pinhole.cpp:66-97)
+ * ------------------------------------------------------------------------------------------- */
+typedef struct LmcuMesh {
+    int32_t num_faces;
+    const double* p;                         /* [num_faces][3][3] local-space positions */
+    const double* n;                         /* [num_faces][3][3] vertex normals, or NULL (use geometric normal) */
+} LmcuMesh;
+
+typedef struct LmcuPrimitive {
+    int32_t node_index;                      /* value reported back in LmcuHit::primitive (SceneNode::index) */
+    int32_t mesh;                            /* index into meshes[] */
+    int32_t material;                        /* index into materials[] */
+    int32_t light;                           /* index into lights[] if this primitive is an area light, else -1 */
+    double M[16];                            /* global transform, column-major */
+} LmcuPrimitive;
+
+enum { LMCU_MAT_DIFFUSE = 0, LMCU_MAT_GLOSSY = 1, LMCU_MAT_GLASS = 2, LMCU_MAT_MIRROR = 3 };
+
+typedef struct LmcuMaterial {
+    int32_t type;
+    int32_t pad_;
+    double color[3];                         /* diffuse: Kd; glossy: Ks */
+    double ax, ay;                           /* glossy: anisotropic GGX roughness */
+    double Ni;                               /* glass: index of refraction */
+} LmcuMaterial;
+
+enum { LMCU_LIGHT_AREA = 0, LMCU_LIGHT_ENVCONST = 1, LMCU_LIGHT_ENV = 2 };
+
+typedef struct LmcuLight {
+    int32_t type;
+    int32_t primitive;                       /* area: index into primitives[] (emitter geometry); env: -1 */
+    int32_t node_index;                      /* scene node index of the light primitive */
+    int32_t env_w, env_h;                    /* env: image size */
+    int32_t pad_;
+    double Ke[3];                            /* area: Ke; envconst: Le */
+    double env_rot;                          /* env: rotation about +y in DEGREES (light_env.cpp:63) */
+    double env_scale;                        /* env: luminance scale */
+    const float* env_rgb;                    /* env: [env_h][env_w][3], row order as texture::bitmap holds it */
+    const char* env_path;                    /* env: image path (only the reference harness reads files) */
+} LmcuLight;
+
+typedef struct LmcuCamera {
+    double position[3];
+    double center[3];
+    double up[3];
+    double vfov;                             /* degrees */
+    double aspect;                           /* width / height */
+} LmcuCamera;
+
+typedef struct LmcuSceneDesc {
+    int32_t num_meshes;
+    int32_t num_primitives;
+    int32_t num_materials;
+    int32_t num_lights;
+    const LmcuMesh* meshes;
+    const LmcuPrimitive* primitives;
+    const LmcuMaterial* materials;
+    const LmcuLight* lights;
+    const LmcuCamera* camera;                /* may be NULL for accel-only use */
+} LmcuSceneDesc;
+
+/* ---------------------------------------------------------------------------------------------
+ * Renderer parameters = the JSON keys of renderer::raycast (src/renderer/renderer_raycast.cpp:48-60),
+ * renderer::ao (functest/renderer_ao.cpp:18-22) and renderer::pt (src/renderer/renderer_pt.cpp:51-77).
+ * ------------------------------------------------------------------------------------------- */
+enum { LMCU_SAMPLING_NAIVE = 0, LMCU_SAMPLING_NEE = 1, LMCU_SAMPLING_MIS = 2 };
+
+typedef struct LmcuRenderParams {
+    int32_t width, height;                   /* film size */
+    int32_t max_verts;                       /* pt: max path vertices */
+    int32_t sampling_mode;                   /* pt: LMCU_SAMPLING_* (default mis) */
+    int64_t spp;                             /* pt/ao: samples per pixel rendered by THIS call */
+    int64_t sample_offset;                   /* pt/ao: global index of this call's first sample (sample split) */
+    uint32_t seed;                           /* pt/ao: RNG seed */
+    int32_t rescale;                         /* pt: 1 = divide by spp at the end (renderer_pt.cpp:307-309); 0 = leave sums */
+    int32_t use_constant_color;              /* raycast */
+    int32_t visualize_normal;                /* raycast */
+    int32_t has_color;                       /* raycast: `color` override present */
+    int32_t pad_;
+    double bg_color[3];                      /* raycast */
+    double color[3];                         /* raycast */
+    double ao_distance;                      /* ao: occlusion ray tmax (0.2 in the reference) */
+} LmcuRenderParams;
+
+typedef struct LmcuRenderStats {
+    double elapsed;                          /* seconds, device time of the render (the "elapsed" Json key) */
+    int64_t processed;                       /* the "processed" Json key: spp rendered by this call */
+    int64_t paths;                           /* width*height*spp */
+    int64_t rays;                            /* closest-hit + shadow queries issued (device counter) */
+    int64_t kernel_launches;                 /* kernels launched by this call */
+    double bvh_nodes_per_ray;                /* mean wide nodes fetched per ray (counters build only, else 0) */
+    double bvh_tris_per_ray;                 /* mean triangles fetched per ray (counters build only, else 0) */
+} LmcuRenderStats;
+
+typedef struct LmcuBuildOptions {
+    int32_t max_leaf_tris;                   /* 1..3 triangles per leaf slot (default 3) */
+    int32_t reserved_[7];
+} LmcuBuildOptions;
+
+typedef struct LmcuBuildStats {
+    double elapsed;                          /* seconds, device time of flatten + build */
+    int64_t num_triangles;
+    int64_t num_wide_nodes;
+    int64_t node_bytes;
+    int64_t triangle_bytes;
+    int32_t triangles_fp32;                  /* 1 if every world-space vertex is float-representable (48 B triangles) */
+    int32_t pad_;
+    double sah_cost;                         /* SAH cost of the wide tree */
+} LmcuBuildStats;
+
+typedef struct LmcuScene LmcuScene;
+
+/* -- library ---------------------------------------------------------------------------------- */
+const char* lmcu_last_error(void);
+int lmcu_device_count(void);
+const char* lmcu_version(void);
+
+/* -- scene + accel: replaces lm::Accel::build / intersect (include/lm/accel.h:38,70) ---------- */
+int lmcu_scene_create(int device, LmcuScene** out);
+void lmcu_scene_destroy(LmcuScene* scene);
+/* Upload + flatten (accel_sahbvh.cpp:132-151: world p = M * (p,1) in FP64, glm operation order). */
+int lmcu_scene_upload(LmcuScene* scene, const LmcuSceneDesc* desc);
+/* Build the wide BVH (replaces accel_sahbvh.cpp:156-266). */
+int lmcu_accel_build(LmcuScene* scene, const LmcuBuildOptions* opts, LmcuBuildStats* stats);
+/* Closest hit for a batch of rays in HOST memory (replaces accel_sahbvh.cpp:269-299 per ray). */
+int lmcu_accel_intersect(LmcuScene* scene, const LmcuRay* rays, int64_t n, LmcuHit* hits);
+/* Same with DEVICE buffers on `stream` (a cudaStream_t, may be NULL); asynchronous. */
+int lmcu_accel_intersect_device(LmcuScene* scene, const void* d_rays, int64_t n, void* d_hits, void* stream);
+/* Mean wide nodes / triangles fetched per ray by the last counted batch (counters variant of the kernel). */
+int lmcu_accel_intersect_counted(LmcuScene* scene, const LmcuRay* rays, int64_t n, LmcuHit* hits,
+                                 double* nodes_per_ray, double* tris_per_ray);
+
+/* -- renderers: replace lm::Renderer::render (include/lm/renderer.h:25) ------------------------ */
+/* film_rgb: HOST buffer of width*height*3 floats, or NULL to keep the result only in the device film. */
+int lmcu_render_raycast(LmcuScene* scene, const LmcuRenderParams* p, float* film_rgb, LmcuRenderStats* stats);
+int lmcu_render_ao(LmcuScene* scene, const LmcuRenderParams* p, float* film_rgb, LmcuRenderStats* stats);
+int lmcu_render_pt(LmcuScene* scene, const LmcuRenderParams* p, float* film_rgb, LmcuRenderStats* stats);
+/* Device film of the last render (width*height*3 floats) for the multi-GPU film reduce
+ * (sample split: every rank renders with rescale=0, NCCL-reduces this buffer, then scales). */
+int lmcu_film_device_ptr(LmcuScene* scene, void** d_film, int64_t* num_floats);
+/* film *= s on the device (film::bitmap::rescale, src/film/film_bitmap.cpp:244-248). */
+int lmcu_film_rescale(LmcuScene* scene, double s);
+/* Copy the device film to a host buffer. */
+int lmcu_film_download(LmcuScene* scene, float* film_rgb);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LMCU_H */

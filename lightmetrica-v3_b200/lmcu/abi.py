@@ -1,0 +1,96 @@
+"""ctypes mirror of include/lmcu.h (POD structs only; no logic).
+
+Shared by the product binding (lmcu.api -> liblmcu.so) and by the test-only checkers under
+oracle/ (reference harness, C port), which consume the same scene description.
+"""
+import ctypes as C
+
+c_double3 = C.c_double * 3
+
+
+class LmcuRay(C.Structure):
+    _fields_ = [("o", c_double3), ("d", c_double3), ("tmin", C.c_double), ("tmax", C.c_double)]
+
+
+class LmcuHit(C.Structure):
+    _fields_ = [("t", C.c_double), ("u", C.c_double), ("v", C.c_double),
+                ("primitive", C.c_int32), ("face", C.c_int32)]
+
+
+class LmcuMesh(C.Structure):
+    _fields_ = [("num_faces", C.c_int32), ("p", C.POINTER(C.c_double)), ("n", C.POINTER(C.c_double))]
+
+
+class LmcuPrimitive(C.Structure):
+    _fields_ = [("node_index", C.c_int32), ("mesh", C.c_int32), ("material", C.c_int32),
+                ("light", C.c_int32), ("M", C.c_double * 16)]
+
+
+MAT_DIFFUSE, MAT_GLOSSY, MAT_GLASS, MAT_MIRROR = 0, 1, 2, 3
+LIGHT_AREA, LIGHT_ENVCONST, LIGHT_ENV = 0, 1, 2
+SAMPLING_NAIVE, SAMPLING_NEE, SAMPLING_MIS = 0, 1, 2
+
+
+class LmcuMaterial(C.Structure):
+    _fields_ = [("type", C.c_int32), ("pad_", C.c_int32), ("color", c_double3),
+                ("ax", C.c_double), ("ay", C.c_double), ("Ni", C.c_double)]
+
+
+class LmcuLight(C.Structure):
+    _fields_ = [("type", C.c_int32), ("primitive", C.c_int32), ("node_index", C.c_int32),
+                ("env_w", C.c_int32), ("env_h", C.c_int32), ("pad_", C.c_int32),
+                ("Ke", c_double3), ("env_rot", C.c_double), ("env_scale", C.c_double),
+                ("env_rgb", C.POINTER(C.c_float)), ("env_path", C.c_char_p)]
+
+
+class LmcuCamera(C.Structure):
+    _fields_ = [("position", c_double3), ("center", c_double3), ("up", c_double3),
+                ("vfov", C.c_double), ("aspect", C.c_double)]
+
+
+class LmcuSceneDesc(C.Structure):
+    _fields_ = [("num_meshes", C.c_int32), ("num_primitives", C.c_int32),
+                ("num_materials", C.c_int32), ("num_lights", C.c_int32),
+                ("meshes", C.POINTER(LmcuMesh)), ("primitives", C.POINTER(LmcuPrimitive)),
+                ("materials", C.POINTER(LmcuMaterial)), ("lights", C.POINTER(LmcuLight)),
+                ("camera", C.POINTER(LmcuCamera))]
+
+
+class LmcuRenderParams(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("max_verts", C.c_int32),
+                ("sampling_mode", C.c_int32), ("spp", C.c_int64), ("sample_offset", C.c_int64),
+                ("seed", C.c_uint32), ("rescale", C.c_int32), ("use_constant_color", C.c_int32),
+                ("visualize_normal", C.c_int32), ("has_color", C.c_int32), ("pad_", C.c_int32),
+                ("bg_color", c_double3), ("color", c_double3), ("ao_distance", C.c_double)]
+
+
+class LmcuRenderStats(C.Structure):
+    _fields_ = [("elapsed", C.c_double), ("processed", C.c_int64), ("paths", C.c_int64),
+                ("rays", C.c_int64), ("kernel_launches", C.c_int64),
+                ("bvh_nodes_per_ray", C.c_double), ("bvh_tris_per_ray", C.c_double)]
+
+
+class LmcuBuildOptions(C.Structure):
+    _fields_ = [("max_leaf_tris", C.c_int32), ("reserved_", C.c_int32 * 7)]
+
+
+class LmcuBuildStats(C.Structure):
+    _fields_ = [("elapsed", C.c_double), ("num_triangles", C.c_int64), ("num_wide_nodes", C.c_int64),
+                ("node_bytes", C.c_int64), ("triangle_bytes", C.c_int64),
+                ("triangles_fp32", C.c_int32), ("pad_", C.c_int32), ("sah_cost", C.c_double)]
+
+
+def render_params(width, height, spp=1, max_verts=20, seed=42, sampling_mode=SAMPLING_MIS,
+                  sample_offset=0, rescale=1, bg_color=(0, 0, 0), use_constant_color=False,
+                  visualize_normal=False, color=None, ao_distance=0.2):
+    """Defaults follow the reference renderers' JSON defaults (renderer_pt.cpp:51-77,
+    renderer_raycast.cpp:48-60, functest/renderer_ao.cpp:36-40)."""
+    p = LmcuRenderParams()
+    p.width, p.height, p.max_verts, p.sampling_mode = width, height, max_verts, sampling_mode
+    p.spp, p.sample_offset, p.seed, p.rescale = spp, sample_offset, seed, rescale
+    p.use_constant_color, p.visualize_normal = int(use_constant_color), int(visualize_normal)
+    p.has_color = int(color is not None)
+    p.bg_color = c_double3(*bg_color)
+    p.color = c_double3(*(color if color is not None else (0, 0, 0)))
+    p.ao_distance = ao_distance
+    return p

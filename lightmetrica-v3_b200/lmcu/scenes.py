@@ -1,0 +1,400 @@
+"""Procedural scenes of BASELINE.json's configs as plain arrays.
+
+A SceneBuilder mirrors the calls a Lightmetrica user makes (load mesh/material/light, add a
+(transformed) primitive: /root/reference/include/lm/scene.h:120-140) and produces the
+LmcuSceneDesc that liblmcu.so, the reference harness and the C port all consume.  All coordinates
+are snapped to float32-representable doubles unless stated, so device triangles can be stored as
+float without changing a single bit of the FP64 geometry the reference sees.
+"""
+import ctypes as C
+import numpy as np
+
+from . import abi
+
+
+def _f32(a):
+    return np.asarray(a, dtype=np.float64).astype(np.float32).astype(np.float64)
+
+
+def translate(v):
+    M = np.eye(4)
+    M[:3, 3] = v
+    return M
+
+
+def scale(v):
+    return np.diag([v[0], v[1], v[2], 1.0])
+
+
+def rotate(angle_deg, axis):
+    a = np.asarray(axis, dtype=np.float64)
+    a = a / np.linalg.norm(a)
+    t = np.radians(angle_deg)
+    K = np.array([[0, -a[2], a[1]], [a[2], 0, -a[0]], [-a[1], a[0], 0]])
+    R = np.eye(3) + np.sin(t) * K + (1 - np.cos(t)) * (K @ K)
+    M = np.eye(4)
+    M[:3, :3] = R
+    return M
+
+
+class SceneBuilder:
+    def __init__(self):
+        self.meshes = []        # (p[nf,3,3], n[nf,3,3] or None)
+        self.materials = []     # dict
+        self.lights = []        # dict
+        self.primitives = []    # dict
+        self.camera = None
+        self._keep = []
+
+    # -- assets -------------------------------------------------------------------------------
+    def add_mesh(self, p, n=None):
+        p = np.ascontiguousarray(p, dtype=np.float64).reshape(-1, 3, 3)
+        if n is not None:
+            n = np.ascontiguousarray(n, dtype=np.float64).reshape(-1, 3, 3)
+            assert n.shape == p.shape
+        self.meshes.append((p, n))
+        return len(self.meshes) - 1
+
+    def add_material(self, type, color=(1, 1, 1), ax=0.0, ay=0.0, Ni=1.0):
+        self.materials.append(dict(type=type, color=tuple(color), ax=ax, ay=ay, Ni=Ni))
+        return len(self.materials) - 1
+
+    def diffuse(self, Kd):
+        return self.add_material(abi.MAT_DIFFUSE, Kd)
+
+    def glossy(self, Ks, ax, ay):
+        return self.add_material(abi.MAT_GLOSSY, Ks, ax, ay)
+
+    def glass(self, Ni):
+        return self.add_material(abi.MAT_GLASS, (0, 0, 0), Ni=Ni)
+
+    def mirror(self):
+        return self.add_material(abi.MAT_MIRROR, (0, 0, 0))
+
+    # -- scene graph (flattened: one entry per primitive node with a mesh) -----------------------
+    def add_primitive(self, mesh, material, Ke=None, M=None):
+        """Ke != None attaches a light::area to the primitive (light_area.cpp:68-73)."""
+        light = -1
+        if Ke is not None:
+            assert all(l["type"] == abi.LIGHT_AREA for l in self.lights), "env light must come last"
+            self.lights.append(dict(type=abi.LIGHT_AREA, primitive=len(self.primitives), Ke=tuple(Ke)))
+            light = len(self.lights) - 1
+        M = np.eye(4) if M is None else np.asarray(M, dtype=np.float64)
+        self.primitives.append(dict(node_index=len(self.primitives), mesh=mesh, material=material,
+                                    light=light, M=M))
+        return len(self.primitives) - 1
+
+    def set_envconst(self, Le):
+        self.lights.append(dict(type=abi.LIGHT_ENVCONST, primitive=-1, Ke=tuple(Le)))
+
+    def set_env(self, rgb, rot=0.0, scale=1.0, path=None):
+        rgb = np.ascontiguousarray(rgb, dtype=np.float32)
+        self.lights.append(dict(type=abi.LIGHT_ENV, primitive=-1, Ke=(0, 0, 0), rgb=rgb, rot=rot,
+                                scale=scale, path=path))
+
+    def set_camera(self, position, center, up, vfov, aspect):
+        self.camera = dict(position=tuple(position), center=tuple(center), up=tuple(up),
+                           vfov=float(vfov), aspect=float(aspect))
+
+    # -- statistics ---------------------------------------------------------------------------
+    def num_triangles(self):
+        return sum(self.meshes[p["mesh"]][0].shape[0] for p in self.primitives)
+
+    # -- ctypes view --------------------------------------------------------------------------
+    def desc(self):
+        """Returns an LmcuSceneDesc whose pointers stay valid while this builder is alive."""
+        dp = C.POINTER(C.c_double)
+        meshes = (abi.LmcuMesh * max(1, len(self.meshes)))()
+        for i, (p, n) in enumerate(self.meshes):
+            meshes[i].num_faces = p.shape[0]
+            meshes[i].p = p.ctypes.data_as(dp)
+            meshes[i].n = n.ctypes.data_as(dp) if n is not None else None
+        prims = (abi.LmcuPrimitive * max(1, len(self.primitives)))()
+        for i, q in enumerate(self.primitives):
+            prims[i].node_index, prims[i].mesh = q["node_index"], q["mesh"]
+            prims[i].material, prims[i].light = q["material"], q["light"]
+            prims[i].M = (C.c_double * 16)(*np.asarray(q["M"]).T.reshape(-1))   # column-major
+        mats = (abi.LmcuMaterial * max(1, len(self.materials)))()
+        for i, m in enumerate(self.materials):
+            mats[i].type, mats[i].color = m["type"], abi.c_double3(*m["color"])
+            mats[i].ax, mats[i].ay, mats[i].Ni = m["ax"], m["ay"], m["Ni"]
+        lights = (abi.LmcuLight * max(1, len(self.lights)))()
+        for i, l in enumerate(self.lights):
+            lights[i].type, lights[i].primitive = l["type"], l["primitive"]
+            lights[i].node_index = l["primitive"] if l["primitive"] >= 0 else len(self.primitives)
+            lights[i].Ke = abi.c_double3(*l["Ke"])
+            if l["type"] == abi.LIGHT_ENV:
+                lights[i].env_h, lights[i].env_w = l["rgb"].shape[:2]
+                lights[i].env_rgb = l["rgb"].ctypes.data_as(C.POINTER(C.c_float))
+                lights[i].env_rot, lights[i].env_scale = l["rot"], l["scale"]
+                lights[i].env_path = l["path"].encode() if l["path"] else None
+        d = abi.LmcuSceneDesc()
+        d.num_meshes, d.num_primitives = len(self.meshes), len(self.primitives)
+        d.num_materials, d.num_lights = len(self.materials), len(self.lights)
+        d.meshes, d.primitives, d.materials, d.lights = meshes, prims, mats, lights
+        if self.camera is not None:
+            cam = abi.LmcuCamera()
+            cam.position = abi.c_double3(*self.camera["position"])
+            cam.center = abi.c_double3(*self.camera["center"])
+            cam.up = abi.c_double3(*self.camera["up"])
+            cam.vfov, cam.aspect = self.camera["vfov"], self.camera["aspect"]
+            d.camera = C.pointer(cam)
+            self._keep.append(cam)
+        self._keep.append((meshes, prims, mats, lights))
+        return d
+
+
+# ------------------------------------------------------------------------------------------------
+# Geometry generators
+# ------------------------------------------------------------------------------------------------
+def quad(a, b, c, d):
+    """Two CCW triangles (a,b,c), (a,c,d); the normal is (b-a)x(c-a)."""
+    a, b, c, d = (np.asarray(v, dtype=np.float64) for v in (a, b, c, d))
+    return np.stack([np.stack([a, b, c]), np.stack([a, c, d])])
+
+
+def flat_normals(p):
+    p = p.reshape(-1, 3, 3)
+    gn = np.cross(p[:, 1] - p[:, 0], p[:, 2] - p[:, 0])
+    gn /= np.linalg.norm(gn, axis=1, keepdims=True)
+    return np.repeat(gn[:, None, :], 3, axis=1)
+
+
+def box(lo, hi):
+    """Axis-aligned box, 12 outward-facing triangles."""
+    x0, y0, z0 = lo
+    x1, y1, z1 = hi
+    q = [
+        quad((x0, y0, z1), (x1, y0, z1), (x1, y1, z1), (x0, y1, z1)),   # +z
+        quad((x1, y0, z0), (x0, y0, z0), (x0, y1, z0), (x1, y1, z0)),   # -z
+        quad((x1, y0, z1), (x1, y0, z0), (x1, y1, z0), (x1, y1, z1)),   # +x
+        quad((x0, y0, z0), (x0, y0, z1), (x0, y1, z1), (x0, y1, z0)),   # -x
+        quad((x0, y1, z1), (x1, y1, z1), (x1, y1, z0), (x0, y1, z0)),   # +y
+        quad((x0, y0, z0), (x1, y0, z0), (x1, y0, z1), (x0, y0, z1)),   # -y
+    ]
+    return np.concatenate(q)
+
+
+def uv_sphere(num_theta, num_phi=None, r=1.0):
+    """The UV sphere of /root/reference/functest/func_render_instancing.py:60-92 (same vertex
+    formula and face order), returned as soup positions + smooth normals, outward winding."""
+    num_phi = 2 * num_theta if num_phi is None else num_phi
+    i, j = np.meshgrid(np.arange(num_theta + 1), np.arange(num_phi), indexing="ij")
+    theta = i * np.pi / num_theta
+    phi = j * 2 * np.pi / num_phi
+    ns = np.stack([np.sin(theta) * np.sin(phi), np.cos(theta), np.sin(theta) * np.cos(phi)], -1).reshape(-1, 3)
+    vs = r * ns
+    fs = []
+    for ii in range(1, num_theta + 1):
+        jj = np.arange(1, num_phi + 1)
+        p00 = (ii - 1) * num_phi + jj - 1
+        p01 = (ii - 1) * num_phi + jj % num_phi
+        p10 = ii * num_phi + jj - 1
+        p11 = ii * num_phi + jj % num_phi
+        rows = []
+        if ii > 1:
+            rows.append(np.stack([p10, p01, p00], -1))
+        if ii < num_theta:
+            rows.append(np.stack([p11, p01, p10], -1))
+        # interleave exactly like the reference loop (per j: first the i>1 face, then the i<n face)
+        fs.append(np.stack(rows, 1).reshape(-1, 3))
+    fs = np.concatenate(fs)
+    p = vs[fs]
+    n = ns[fs]
+    # make the winding outward (geometric normal on the same side as the shading normals)
+    gn = np.cross(p[:, 1] - p[:, 0], p[:, 2] - p[:, 0])
+    flip = np.einsum("ij,ij->i", gn, n.mean(1)) < 0
+    p[flip] = p[flip][:, [0, 2, 1]]
+    n[flip] = n[flip][:, [0, 2, 1]]
+    return p, n
+
+
+def _fbm(x, z, octaves=6, seed=1):
+    """Value-noise fBm on a lattice hashed from (seed, octave): deterministic, numpy only."""
+    rng = np.random.RandomState(seed)
+    y = np.zeros_like(x)
+    amp, freq = 1.0, 2.0
+    for _ in range(octaves):
+        n = int(freq) + 2
+        lattice = rng.rand(n, n)
+        fx, fz = (x * 0.5 + 0.5) * freq, (z * 0.5 + 0.5) * freq
+        ix, iz = np.clip(fx.astype(np.int64), 0, n - 2), np.clip(fz.astype(np.int64), 0, n - 2)
+        tx, tz = fx - ix, fz - iz
+        tx, tz = tx * tx * (3 - 2 * tx), tz * tz * (3 - 2 * tz)
+        v = (lattice[ix, iz] * (1 - tx) * (1 - tz) + lattice[ix + 1, iz] * tx * (1 - tz)
+             + lattice[ix, iz + 1] * (1 - tx) * tz + lattice[ix + 1, iz + 1] * tx * tz)
+        y += amp * (v - 0.5)
+        amp *= 0.5
+        freq *= 2.0
+    return y
+
+
+def heightfield(n, height=0.15, seed=1):
+    """(n+1)^2 grid over [-1,1]^2 -> 2 n^2 triangles (C3: n=2236 -> 9 999 392)."""
+    g = np.linspace(-1.0, 1.0, n + 1)
+    x, z = np.meshgrid(g, g, indexing="ij")
+    y = height * _fbm(x, z, 6, seed)
+    v = _f32(np.stack([x, y, z], -1))
+    a, b, c, d = v[:-1, :-1], v[1:, :-1], v[1:, 1:], v[:-1, 1:]
+    t1 = np.stack([a, c, b], -2)      # normal +y
+    t2 = np.stack([a, d, c], -2)
+    return np.stack([t1, t2], 2).reshape(-1, 3, 3)
+
+
+# ------------------------------------------------------------------------------------------------
+# Configs
+# ------------------------------------------------------------------------------------------------
+CORNELL_CAMERA = dict(position=(0, 1, 5), center=(0, 1, 0), up=(0, 1, 0), vfov=30, aspect=16 / 9)
+
+
+def _cornell_shell(sb):
+    white = sb.diffuse((.725, .725, .725))
+    red = sb.diffuse((.63, .065, .05))
+    green = sb.diffuse((.14, .45, .091))
+    black = sb.diffuse((0, 0, 0))
+    floor = quad((-1, 0, 1), (1, 0, 1), (1, 0, -1), (-1, 0, -1))         # +y
+    ceil_ = quad((-1, 2, -1), (1, 2, -1), (1, 2, 1), (-1, 2, 1))         # -y
+    back = quad((-1, 0, -1), (1, 0, -1), (1, 2, -1), (-1, 2, -1))        # +z
+    left = quad((-1, 0, 1), (-1, 0, -1), (-1, 2, -1), (-1, 2, 1))        # +x
+    right = quad((1, 0, -1), (1, 0, 1), (1, 2, 1), (1, 2, -1))           # -x
+    lq = quad((-.25, 1.9921875, -.25), (.25, 1.9921875, -.25), (.25, 1.9921875, .25), (-.25, 1.9921875, .25))  # -y
+    for geo, mat in ((np.concatenate([floor, ceil_, back]), white), (left, red), (right, green)):
+        geo = _f32(geo)
+        sb.add_primitive(sb.add_mesh(geo, flat_normals(geo)), mat)
+    lq = _f32(lq)
+    sb.add_primitive(sb.add_mesh(lq, flat_normals(lq)), black, Ke=(17, 12, 4))
+    sb.set_camera(**CORNELL_CAMERA)
+    return white
+
+
+def cornell_box(transformed_boxes=False):
+    """C1: 18 quads = 36 triangles in [-1,1]x[0,2]x[-1,1]."""
+    sb = SceneBuilder()
+    white = _cornell_shell(sb)
+    tall = translate((-.35, 0, -.3)) @ rotate(17, (0, 1, 0)) @ scale((.3, .6, .3)) @ translate((0, 1, 0))
+    short = translate((.35, 0, .3)) @ rotate(-17, (0, 1, 0)) @ scale((.3, .3, .3)) @ translate((0, 1, 0))
+    unit = box((-1, -1, -1), (1, 1, 1))
+    for M in (tall, short):
+        if transformed_boxes:
+            sb.add_primitive(sb.add_mesh(unit, flat_normals(unit)), white, M=M)
+        else:
+            w = _f32(unit.reshape(-1, 3) @ M[:3, :3].T + M[:3, 3]).reshape(-1, 3, 3)
+            sb.add_primitive(sb.add_mesh(w, flat_normals(w)), white)
+    return sb
+
+
+def cornell_spheres(num_theta=64):
+    """C2/C5: Cornell shell + diffuse and glass UV spheres (2 x 16 128 tris at num_theta=64)."""
+    sb = SceneBuilder()
+    _cornell_shell(sb)
+    p, n = uv_sphere(num_theta, 2 * num_theta, 1.0)
+    for centre, mat in (((-.4, .35, -.3), sb.diffuse((.8, .8, .8))), ((.45, .35, .3), sb.glass(1.5))):
+        w = _f32(p * .35 + np.asarray(centre))
+        sb.add_primitive(sb.add_mesh(w, n), mat)
+    return sb
+
+
+def heightfield_scene(n=2236):
+    """C3: n x n heightfield, single diffuse material; camera of the coherent batch."""
+    sb = SceneBuilder()
+    geo = heightfield(n)
+    sb.add_primitive(sb.add_mesh(geo, flat_normals(geo)), sb.diffuse((.7, .7, .7)))
+    sb.set_camera(position=(0, 1.2, 2.2), center=(0, 0, 0), up=(0, 1, 0), vfov=40, aspect=1.0)
+    return sb
+
+
+def instanced_spheres(grid=10, num_theta=112, seed=3, env=None):
+    """C4: grid^3 transformed instances of one UV sphere (num_theta=112 -> 49 728 tris each),
+    materials cycling glossy/glass/mirror/diffuse, ground quad, constant (or image) env light."""
+    sb = SceneBuilder()
+    p, n = uv_sphere(num_theta, 2 * num_theta, 0.4)
+    mesh = sb.add_mesh(_f32(p), n)
+    mats = [sb.glossy((.8, .6, .3), .15, .15), sb.glass(1.5), sb.mirror(), sb.diffuse((.7, .7, .7))]
+    rng = np.random.RandomState(seed)
+    k = 0
+    half = (grid - 1) / 2
+    for ix in range(grid):
+        for iy in range(grid):
+            for iz in range(grid):
+                axis = rng.randn(3)
+                M = (translate((ix - half, iy + .5, iz - half)) @ rotate(rng.rand() * 360, axis)
+                     @ scale([.7 + .3 * rng.rand()] * 3))
+                sb.add_primitive(mesh, mats[k % 4], M=M)
+                k += 1
+    g = grid
+    ground = _f32(quad((-g, 0, g), (g, 0, g), (g, 0, -g), (-g, 0, -g)))
+    sb.add_primitive(sb.add_mesh(ground, flat_normals(ground)), sb.diffuse((.5, .5, .5)))
+    if env is None:
+        sb.set_envconst((1, 1, 1))
+    else:
+        sb.set_env(**env)
+    sb.set_camera(position=(grid * 1.1, grid * .9, grid * 1.6), center=(0, grid * .45, 0), up=(0, 1, 0),
+                  vfov=35, aspect=16 / 9)
+    return sb
+
+
+# ------------------------------------------------------------------------------------------------
+# Ray batches (host, FP64, float-representable origins) — SURVEY.md §8d C1/C3
+# ------------------------------------------------------------------------------------------------
+def camera_rays(camera, width, height):
+    """Pixel-centre primary rays, the arithmetic of camera_pinhole.cpp:90-95,128-132."""
+    pos, center, up = (np.asarray(camera[k], dtype=np.float64) for k in ("position", "center", "up"))
+    w = pos - center
+    w /= np.sqrt(np.dot(w, w))
+    u = np.cross(up, w)
+    u /= np.sqrt(np.dot(u, u))
+    v = np.cross(w, u)
+    tf = np.tan(camera["vfov"] * np.pi / 180 * .5)
+    x = (np.arange(width) + .5) / width
+    y = (np.arange(height) + .5) / height
+    rx, ry = np.meshgrid(2 * x - 1, 2 * y - 1, indexing="xy")
+    d = np.stack([camera["aspect"] * tf * rx, tf * ry, -np.ones_like(rx)], -1)
+    d /= np.sqrt((d * d).sum(-1, keepdims=True))
+    dirs = d[..., 0:1] * u + d[..., 1:2] * v + d[..., 2:3] * w
+    rays = np.zeros(width * height, dtype=RAY_DTYPE)
+    rays["o"] = pos
+    rays["d"] = dirs.reshape(-1, 3)
+    rays["tmin"] = 1e-3
+    rays["tmax"] = 1e10
+    return rays
+
+
+RAY_DTYPE = np.dtype([("o", "<f8", 3), ("d", "<f8", 3), ("tmin", "<f8"), ("tmax", "<f8")])
+HIT_DTYPE = np.dtype([("t", "<f8"), ("u", "<f8"), ("v", "<f8"), ("primitive", "<i4"), ("face", "<i4")])
+
+
+def random_rays(n, lo, hi, seed=7):
+    """Incoherent rays: origins uniform in the box [lo,hi], uniform directions."""
+    rng = np.random.RandomState(seed)
+    rays = np.zeros(n, dtype=RAY_DTYPE)
+    rays["o"] = _f32(lo + (np.asarray(hi) - np.asarray(lo)) * rng.rand(n, 3))
+    d = rng.randn(n, 3)
+    rays["d"] = d / np.sqrt((d * d).sum(-1, keepdims=True))
+    rays["tmin"] = 1e-3
+    rays["tmax"] = 1e10
+    return rays
+
+
+def bounce_rays(rays, hits, tri_normal_fn, seed=7):
+    """C3 (ii): one cosine-weighted bounce ray per hit of a primary batch."""
+    ok = hits["primitive"] >= 0
+    o = rays["o"][ok] + rays["d"][ok] * hits["t"][ok, None]
+    n = tri_normal_fn(hits[ok])
+    flip = (n * rays["d"][ok]).sum(-1) > 0
+    n[flip] = -n[flip]
+    rng = np.random.RandomState(seed)
+    u0, u1 = rng.rand(len(o)), rng.rand(len(o))
+    r, phi = np.sqrt(u0), 2 * np.pi * u1
+    lx, ly = r * np.cos(phi), r * np.sin(phi)
+    lz = np.sqrt(np.maximum(0, 1 - lx * lx - ly * ly))
+    a = np.where(np.abs(n[:, 0:1]) > .9, np.array([[0., 1, 0]]), np.array([[1., 0, 0]]))
+    t = np.cross(a, n)
+    t /= np.linalg.norm(t, axis=1, keepdims=True)
+    b = np.cross(n, t)
+    d = lx[:, None] * t + ly[:, None] * b + lz[:, None] * n
+    out = np.zeros(len(o), dtype=RAY_DTYPE)
+    out["o"] = _f32(o)
+    out["d"] = d
+    out["tmin"] = 1e-3
+    out["tmax"] = 1e10
+    return out
