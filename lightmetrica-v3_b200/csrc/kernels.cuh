@@ -1,0 +1,362 @@
+// kernels.cuh — device-side scene view and the per-item bodies of the render kernels
+// (raycast, ao, wavefront pt: generate / extend / shade / shadow).  The __global__ wrappers with
+// persistent-thread work fetch and warp-ballot queue compaction live in lmcu.cu.
+#pragma once
+#include "bvh.cuh"
+#include "build.cuh"
+#include "shade.cuh"
+
+namespace lmcu {
+
+struct DevScene {
+    const WideNode* nodes;
+    const TriF32* t32;          // exactly one of t32 / t64 is non-null
+    const TriF64* t64;
+    const TriShade* shade;
+    const PrimDev* prims;
+    const MaterialDev* mats;
+    const LightDev* lights;
+    const EmitTri* emit;
+    const float* cdf;
+    const float4* env_tex;
+    int32_t num_prims, num_lights, env_light, pad_;
+    uint32_t num_tris, pad2_;
+    CameraDev cam;
+};
+
+template <typename TriT> LMCU_HD const TriT* scene_tris(const DevScene& s);
+template <> LMCU_HD const TriF32* scene_tris<TriF32>(const DevScene& s) { return s.t32; }
+template <> LMCU_HD const TriF64* scene_tris<TriF64>(const DevScene& s) { return s.t64; }
+
+// -- surface point at a hit (src/scene.cpp:333-344, src/mesh/mesh_raw.cpp:87-97), FP32 ------------------
+struct SurfPoint {
+    F3 p, n, gn;
+    int32_t prim;      // primitive ordinal
+    int32_t face;
+};
+
+LMCU_HD void tri_fetch(const DevScene& s, uint32_t tri, F3& p1, F3& p2, F3& p3, int32_t& prim, int32_t& face) {
+    if (s.t32) {
+        const float4 a = s.t32[tri].a, b = s.t32[tri].b, c = s.t32[tri].c;
+        p1 = f3(a.x, a.y, a.z); p2 = f3(b.x, b.y, b.z); p3 = f3(c.x, c.y, c.z);
+        prim = (int32_t)f2u(a.w); face = (int32_t)f2u(b.w);
+    } else {
+        const TriF64& t = s.t64[tri];
+        p1 = f3((float)t.p[0], (float)t.p[1], (float)t.p[2]);
+        p2 = f3((float)t.p[3], (float)t.p[4], (float)t.p[5]);
+        p3 = f3((float)t.p[6], (float)t.p[7], (float)t.p[8]);
+        prim = t.prim; face = t.face;
+    }
+}
+
+LMCU_HD SurfPoint surface_point(const DevScene& s, uint32_t tri, float u, float v) {
+    SurfPoint sp;
+    F3 p1, p2, p3;
+    tri_fetch(s, tri, p1, p2, p3, sp.prim, sp.face);
+    const float w = 1.0f - u - v;
+    sp.p = p1 * w + p2 * u + p3 * v;
+    const float4 n1 = s.shade[tri].n1, n2 = s.shade[tri].n2, n3 = s.shade[tri].n3;
+    sp.n = normalize(f3(n1.x, n1.y, n1.z) * w + f3(n2.x, n2.y, n2.z) * u + f3(n3.x, n3.y, n3.z) * v);
+    sp.gn = normalize(cross(p2 - p1, p3 - p1)) * n1.w;
+    return sp;
+}
+
+// -- raycast (src/renderer/renderer_raycast.cpp:70-98) -----------------------------------------------------
+struct RaycastParams {
+    int32_t width, height;
+    int32_t use_constant_color, visualize_normal, has_color, pad_;
+    float bg[3], color[3];
+};
+
+template <typename TriT>
+LMCU_HD void raycast_pixel(const DevScene& s, const RaycastParams& p, int x, int y, float* film, uint2* stack) {
+    RayD r;
+    camera_primary_ray_d(s.cam, divrn(addrn((double)x, 0.5), (double)p.width), divrn(addrn((double)y, 0.5), (double)p.height), r.o, r.d);
+    r.tmin = kEps; r.tmax = kInf;
+    HitD h; h.t = r.tmax; h.tri = -1; h.u = h.v = 0;
+    traverse<false, false, TriT>(s.nodes, scene_tris<TriT>(s), r, h, stack, nullptr);
+    F3 c;
+    if (h.tri < 0) {
+        if (s.env_light >= 0) {
+            // miss with tmax = Inf and an environment light -> light endpoint (src/scene.cpp:321-331)
+            const LightDev& l = s.lights[s.env_light];
+            c = p.visualize_normal ? f3s(0.f) : f3(l.Ke[0], l.Ke[1], l.Ke[2]);
+        } else {
+            c = f3(p.bg[0], p.bg[1], p.bg[2]);
+        }
+    } else {
+        const SurfPoint sp = surface_point(s, (uint32_t)h.tri, (float)h.u, (float)h.v);
+        if (p.visualize_normal) {
+            c = f3(fabsf(sp.n.x), fabsf(sp.n.y), fabsf(sp.n.z));
+        } else {
+            c = p.has_color ? f3(p.color[0], p.color[1], p.color[2]) : mat_reflectance(s.mats[s.prims[sp.prim].material]);
+            if (!p.use_constant_color) {
+                const F3 d = f3((float)r.d.x, (float)r.d.y, (float)r.d.z);
+                c = c * (0.2f + 0.8f * fabsf(dot(sp.n, -d)));
+            }
+        }
+    }
+    float* px = film + ((size_t)y * p.width + x) * 3;
+    px[0] = c.x; px[1] = c.y; px[2] = c.z;
+}
+
+// -- ambient occlusion (functest/renderer_ao.cpp:26-43) ----------------------------------------------------
+template <typename TriT>
+LMCU_HD void ao_pixel(const DevScene& s, int width, int height, int x, int y, int64_t spp, uint64_t sample_offset,
+                      uint32_t seed, double ao_distance, float* film, uint2* stack, uint32_t* ray_count) {
+    RayD r;
+    camera_primary_ray_d(s.cam, divrn(addrn((double)x, 0.5), (double)width), divrn(addrn((double)y, 0.5), (double)height), r.o, r.d);
+    r.tmin = kEps; r.tmax = kInf;
+    HitD h; h.t = r.tmax; h.tri = -1; h.u = h.v = 0;
+    traverse<false, false, TriT>(s.nodes, scene_tris<TriT>(s), r, h, stack, nullptr);
+    *ray_count += 1;
+    if (h.tri < 0) return;   // the reference leaves the pixel untouched on a miss
+    const SurfPoint sp = surface_point(s, (uint32_t)h.tri, (float)h.u, (float)h.v);
+    const F3 wi = -f3((float)r.d.x, (float)r.d.y, (float)r.d.z);
+    const Frame f = frame_twosided(sp.n, wi);
+    float V = 0.f;
+    const uint32_t pixel = (uint32_t)(y * width + x);
+    for (int64_t i = 0; i < spp; i++) {
+        const R4 u = rand4(seed, pixel, sample_offset + (uint64_t)i, 0);
+        const F3 d = sample_cosine_weighted(u.x, u.y);
+        const F3 wo = f.u * d.x + f.v * d.y + f.n * d.z;
+        RayD q;
+        q.o = d3(sp.p.x, sp.p.y, sp.p.z); q.d = d3(wo.x, wo.y, wo.z);
+        q.tmin = kEps; q.tmax = ao_distance;
+        HitD hq; hq.t = q.tmax; hq.tri = -1; hq.u = hq.v = 0;
+        traverse<true, false, TriT>(s.nodes, scene_tris<TriT>(s), q, hq, stack, nullptr);
+        V += hq.tri < 0 ? 1.f : 0.f;
+    }
+    *ray_count += (uint32_t)spp;
+    V /= (float)spp;
+    float* px = film + ((size_t)y * width + x) * 3;
+    px[0] = V; px[1] = V; px[2] = V;
+}
+
+// -- wavefront path tracer (src/renderer/renderer_pt.cpp:89-302, pixel mode) --------------------------------
+// Path state, SoA, one entry per queue slot.
+struct PathQueue {
+    float4* ray_o;      // o.xyz, tmin
+    float4* ray_d;      // d.xyz, tmax
+    float4* thr_pix;    // throughput.rgb, pixel (uint bits)
+    float4* aux;        // pdf_bsdf (projected SA) of the sampled direction, shading normal at the previous vertex
+    uint2* info;        // x: sample index of the pixel, y: num_verts | prev_nee<<8
+};
+
+struct ShadowQueue {
+    float4* ray_o;      // o.xyz, tmin
+    float4* ray_d;      // d.xyz, tmax
+    float4* contrib;    // C.rgb, pixel (uint bits)
+};
+
+struct PtParams {
+    int32_t width, height;
+    int32_t max_verts, sampling_mode;
+    uint32_t seed, tiled;
+    uint64_t sample_offset;
+    uint64_t total_paths;
+    uint32_t capacity, pad_;
+};
+
+struct PtCounters {
+    uint32_t count[2];          // entries in path queue A / B
+    uint32_t shadow_count;
+    uint32_t fetch_extend;      // persistent-thread work fetch cursors
+    uint32_t fetch_shadow;
+    uint32_t overflow;          // traversal stack overflow flag
+    unsigned long long next_path;
+    unsigned long long rays;
+    unsigned long long iterations;
+};
+
+LMCU_HD void path_pixel(const PtParams& p, uint64_t g, uint32_t& pixel, uint32_t& sample, int& x, int& y) {
+    const uint64_t npix = (uint64_t)p.width * p.height;
+    sample = (uint32_t)(g / npix);
+    const uint32_t lin = (uint32_t)(g % npix);
+    if (p.tiled) {                       // 8x4 pixel tiles: one warp = one tile of coherent primary rays
+        const uint32_t tiles_x = (uint32_t)p.width / 8u;
+        const uint32_t tile = lin >> 5, idx = lin & 31u;
+        x = (int)((tile % tiles_x) * 8u + (idx & 7u));
+        y = (int)((tile / tiles_x) * 4u + (idx >> 3));
+    } else {
+        x = (int)(lin % (uint32_t)p.width);
+        y = (int)(lin / (uint32_t)p.width);
+    }
+    pixel = (uint32_t)y * (uint32_t)p.width + (uint32_t)x;
+}
+
+// First path vertex: camera endpoint + direction through the pixel window (renderer_pt.cpp:96-113,197-206)
+LMCU_HD void pt_generate_body(const DevScene& s, const PtParams& p, uint64_t g, const PathQueue& q, uint32_t slot) {
+    uint32_t pixel, sample; int x, y;
+    path_pixel(p, g, pixel, sample, x, y);
+    const R4 u = rand4(p.seed, pixel, p.sample_offset + sample, 0);
+    const float rpx = ((float)x + u.x) / (float)p.width, rpy = ((float)y + u.y) / (float)p.height;
+    const float rx = 2.0f * rpx - 1.0f, ry = 2.0f * rpy - 1.0f;
+    const CameraDev& c = s.cam;
+    const F3 dl = normalize(f3((float)(c.aspect * c.tf) * rx, (float)c.tf * ry, -1.0f));
+    const F3 d = f3((float)c.u[0], (float)c.u[1], (float)c.u[2]) * dl.x + f3((float)c.v[0], (float)c.v[1], (float)c.v[2]) * dl.y
+               + f3((float)c.w[0], (float)c.w[1], (float)c.w[2]) * dl.z;
+    q.ray_o[slot] = make_float4((float)c.pos[0], (float)c.pos[1], (float)c.pos[2], (float)kEps);
+    q.ray_d[slot] = make_float4(d.x, d.y, d.z, (float)kInf);
+    q.thr_pix[slot] = make_float4(1.f, 1.f, 1.f, u2f(pixel));
+    q.aux[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+    q.info[slot] = make_uint2(sample, 1u);   // num_verts = 1, prev_nee = 0
+}
+
+template <bool ANY, typename TriT>
+LMCU_HD bool pt_trace(const DevScene& s, float4 o, float4 d, HitD& h, uint2* stack) {
+    RayD r;
+    r.o = d3(o.x, o.y, o.z); r.d = d3(d.x, d.y, d.z);
+    r.tmin = o.w; r.tmax = d.w;
+    h.t = r.tmax; h.tri = -1; h.u = h.v = 0;
+    return traverse<ANY, false, TriT>(s.nodes, scene_tris<TriT>(s), r, h, stack, nullptr);
+}
+
+struct ShadeOut {
+    bool alive;             // path continues: next ray in (o, d), state below
+    bool shadow;            // a shadow ray was generated
+    float4 o, d, thr_pix, aux;
+    uint2 info;
+    float4 sh_o, sh_d, sh_c;
+    F3 emit;                // direct-hit contribution to add to the film now
+};
+
+// Geometry term between a surface vertex (normal n1) and a light point (normal n2): surface.h:329-348
+LMCU_HD float geometry_term(F3 p1, F3 n1, F3 p2, F3 n2) {
+    F3 d = p2 - p1;
+    const float L2 = dot(d, d);
+    d = d * (1.0f / sqrtf(L2));
+    return fabsf(dot(n1, d)) * fabsf(dot(n2, -d)) / L2;
+}
+
+// One path vertex: everything the reference does between Scene::intersect returning `hit` and the next
+// Scene::intersect (renderer_pt.cpp:229-300 for the hit, then :127-209 of the next loop iteration).
+LMCU_HD ShadeOut pt_shade_body(const DevScene& s, const PtParams& p, float4 ro, float4 rd, float4 thr_pix, float4 aux,
+                               uint2 info, float4 hit) {
+    ShadeOut out;
+    out.alive = false; out.shadow = false; out.emit = f3s(0.f);
+    const uint32_t pixel = f2u(thr_pix.w);
+    const uint32_t sample = info.x;
+    uint32_t num_verts = info.y & 0xffu;
+    const bool prev_nee = (info.y >> 8) & 1u;
+    F3 thr = f3(thr_pix.x, thr_pix.y, thr_pix.z);
+    const F3 rdir = f3(rd.x, rd.y, rd.z);
+    const F3 wi = -rdir;
+    const int32_t tri = (int32_t)f2u(hit.w);
+    const float inv_nl = 1.0f / (float)(s.num_lights > 0 ? s.num_lights : 1);
+    const bool direct_ok = p.sampling_mode != 1 /*NEE*/ || !prev_nee;       // renderer_pt.cpp:236-246
+
+    if (tri < 0) {
+        // miss: environment light endpoint if any (src/scene.cpp:321-331), then the walk ends (:276-278)
+        if (s.env_light >= 0 && direct_ok) {
+            const LightDev& l = s.lights[s.env_light];
+            float mis = 1.f;
+            if (p.sampling_mode == 2 && prev_nee) {
+                const F3 np = f3(aux.y, aux.z, aux.w);
+                const float c = fabsf(dot(np, rdir));
+                const float pl = c == 0.f ? 0.f : inv_nl * (1.0f / (4.0f * kPiF)) / c;   // light_envconst.cpp:116-119
+                mis = (aux.x == 0.f && pl == 0.f) ? 0.f : aux.x / (aux.x + pl);
+            }
+            out.emit = thr * f3(l.Ke[0], l.Ke[1], l.Ke[2]) * mis;
+        }
+        return out;
+    }
+
+    const SurfPoint sp = surface_point(s, (uint32_t)tri, hit.y, hit.z);
+    const PrimDev& prim = s.prims[sp.prim];
+    const MaterialDev& mat = s.mats[prim.material];
+
+    // direct hit on an emitter (renderer_pt.cpp:248-270)
+    if (prim.light >= 0 && direct_ok) {
+        const LightDev& l = s.lights[prim.light];
+        if (dot(wi, sp.n) > 0.f) {                                          // light_area.cpp:185-187
+            float mis = 1.f;
+            if (p.sampling_mode == 2 && prev_nee) {
+                const F3 po = f3(ro.x, ro.y, ro.z), np = f3(aux.y, aux.z, aux.w);
+                const float G = geometry_term(po, np, sp.p, sp.n);
+                const float pl = G == 0.f ? 0.f : inv_nl * l.inv_area_j / G;   // light_area.cpp:172-178
+                mis = (aux.x == 0.f && pl == 0.f) ? 0.f : aux.x / (aux.x + pl);
+            }
+            out.emit = thr * f3(l.Ke[0], l.Ke[1], l.Ke[2]) * mis;
+        }
+    }
+
+    const R4 u0 = rand4(p.seed, pixel, p.sample_offset + sample, num_verts * 4u + 0u);   // ud0, ud1, rr, uc0
+    // Russian roulette (renderer_pt.cpp:281-287)
+    if (num_verts > 5u) {
+        const float q = fmaxf(0.2f, 1.0f - max3(thr));
+        if (u0.z < q) return out;
+        thr = thr * (1.0f / (1.0f - q));
+    }
+    num_verts++;
+    if ((int)num_verts >= p.max_verts) return out;                          // loop bound, renderer_pt.cpp:123
+
+    const bool specular = mat_is_specular(mat.type);
+    const bool nee = p.sampling_mode != 0 /*naive*/ && !specular;           // renderer_pt.cpp:127-140 (num_verts > 1 here)
+
+    // next-event estimation (renderer_pt.cpp:142-192)
+    if (nee && s.num_lights > 0) {
+        const R4 u1 = rand4(p.seed, pixel, p.sample_offset + sample, num_verts * 4u + 1u);   // sel, upc, up0, up1
+        int li = (int)(u1.x * (float)s.num_lights);
+        li = li < 0 ? 0 : (li > s.num_lights - 1 ? s.num_lights - 1 : li);  // src/scene.cpp:374-387
+        const LightDev& l = s.lights[li];
+        F3 wo;              // direction from the vertex toward the light
+        float pl = 0.f;     // pdf_direct, projected SA, without the selection probability
+        float tmax = 0.f;
+        if (l.type == LIGHT_AREA) {                                         // light_area.cpp:47-59,148-178
+            const int ti = cdf_sample(s.cdf + l.cdf_offset, l.num_tris, u1.y);
+            const EmitTri& e = s.emit[l.tri_offset + ti];
+            const float sq = safe_sqrt(u1.z);
+            const float b1 = 1.0f - sq, b2 = u1.w * sq;
+            const F3 a = f3(e.p1.x, e.p1.y, e.p1.z), b = f3(e.p2.x, e.p2.y, e.p2.z), c = f3(e.p3.x, e.p3.y, e.p3.z);
+            const F3 xl = a * (1.0f - b1 - b2) + b * b1 + c * b2;
+            const F3 nl = f3(e.n.x, e.n.y, e.n.z);
+            const F3 dv = xl - sp.p;
+            const float dist = sqrtf(dot(dv, dv));
+            wo = dv * (1.0f / dist);
+            if (dot(-wo, nl) > 0.f) {
+                const float G = geometry_term(sp.p, sp.n, xl, nl);
+                pl = G == 0.f ? 0.f : l.inv_area_j / G;
+            }
+            tmax = dist * (1.0f - (float)kEps);                             // include/lm/scene.h:349-356
+        } else {                                                            // light_envconst.cpp:100-119
+            const R4 u2 = rand4(p.seed, pixel, p.sample_offset + sample, num_verts * 4u + 2u);
+            const F3 wl = sample_uniform_sphere(u2.x, u2.y);
+            wo = -wl;
+            const float c = fabsf(dot(sp.n, wo));
+            pl = c == 0.f ? 0.f : (1.0f / (4.0f * kPiF)) / c;
+            tmax = (float)(kInf - 1.0);
+        }
+        if (pl > 0.f) {
+            const F3 fs = mat_eval(mat, sp.n, wi, wo) * sn_correction(sp.n, sp.gn, wi, wo);
+            if (!is_zero(fs)) {
+                float mis = 1.f;
+                if (p.sampling_mode == 2) {
+                    const float p_light = pl * inv_nl;
+                    const float p_bsdf = mat_pdf(mat, sp.n, wi, wo);
+                    mis = (p_light == 0.f && p_bsdf == 0.f) ? 0.f : p_light / (p_light + p_bsdf);   // math.h:697-702
+                }
+                const F3 C = thr * fs * f3(l.Ke[0], l.Ke[1], l.Ke[2]) * (mis / (pl * inv_nl));
+                out.shadow = true;
+                out.sh_o = make_float4(sp.p.x, sp.p.y, sp.p.z, (float)kEps);
+                out.sh_d = make_float4(wo.x, wo.y, wo.z, tmax);
+                out.sh_c = make_float4(C.x, C.y, C.z, u2f(pixel));
+            }
+        }
+    }
+
+    // direction sampling (renderer_pt.cpp:197-209) with the component picked at the hit (:292-293)
+    const BsdfSample bs = mat_sample(mat, sp.n, sp.gn, wi, u0.x, u0.y, u0.w);
+    if (!bs.valid) return out;
+    thr = thr * bs.weight;
+    if (is_zero(thr)) return out;          // every later contribution is multiplied by zero
+    out.alive = true;
+    out.o = make_float4(sp.p.x, sp.p.y, sp.p.z, (float)kEps);
+    out.d = make_float4(bs.wo.x, bs.wo.y, bs.wo.z, (float)kInf);
+    out.thr_pix = make_float4(thr.x, thr.y, thr.z, u2f(pixel));
+    out.aux = make_float4(bs.pdf, sp.n.x, sp.n.y, sp.n.z);
+    out.info = make_uint2(sample, num_verts | ((nee ? 1u : 0u) << 8));
+    return out;
+}
+
+}  // namespace lmcu

@@ -1,0 +1,865 @@
+// lmcu.cu — liblmcu.so: kernels (sm_100a) + host orchestration + the C ABI of include/lmcu.h.
+//
+// There is NO CPU path in this library: without a CUDA device every entry returns
+// LMCU_ERR_NO_DEVICE.  Kernel launch geometry: persistent grids sized as a multiple of the SM
+// count (148 on B200); traversal kernels fetch work one warp (32 rays) at a time from a global
+// cursor; the path-tracer queues are compacted with warp ballots + one atomic per CTA.
+#include <cuda_runtime.h>
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <vector>
+
+#include "../../include/lmcu.h"
+#include "kernels.cuh"
+#include "prep.hpp"
+
+using namespace lmcu;
+
+// ================================================================================================
+// error handling
+// ================================================================================================
+static thread_local std::string g_error;
+
+static int fail(int code, const std::string& msg) {
+    g_error = msg;
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            return fail(LMCU_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));        \
+        }                                                                                          \
+    } while (0)
+
+// ================================================================================================
+// kernels: builder
+// ================================================================================================
+__device__ __forceinline__ void atomic_min_f(float* a, float v) {
+    // ordered-int trick, valid for mixed signs
+    if (v >= 0.f) atomicMin((int*)a, __float_as_int(v)); else atomicMax((unsigned int*)a, __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_max_f(float* a, float v) {
+    if (v >= 0.f) atomicMax((int*)a, __float_as_int(v)); else atomicMin((unsigned int*)a, __float_as_uint(v));
+}
+
+// scene_bounds: [0..2] min, [3..5] max (floats, outward); flags[0] &= exact
+__global__ void k_flatten(const PrimDev* prims, int num_prims, const double* mesh_p, uint32_t nt, double* wp,
+                          float* tri_lo, float* tri_hi, double* centre, float* scene_bounds, int* flags) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    bool exact = true;
+    float lo[3] = { 3e38f, 3e38f, 3e38f }, hi[3] = { -3e38f, -3e38f, -3e38f };
+    if (g < nt) {
+        exact = flatten_body(g, prims, num_prims, mesh_p, wp, tri_lo, tri_hi, centre);
+        for (int a = 0; a < 3; a++) { lo[a] = tri_lo[(size_t)g * 3 + a]; hi[a] = tri_hi[(size_t)g * 3 + a]; }
+    }
+    // warp reduce, one atomic per warp
+    for (int a = 0; a < 3; a++) {
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+            hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+        }
+    }
+    const bool all_exact = __all_sync(0xffffffffu, exact);
+    if ((threadIdx.x & 31) == 0) {
+        for (int a = 0; a < 3; a++) {
+            if (lo[a] <= hi[a]) { atomic_min_f(scene_bounds + a, lo[a]); atomic_max_f(scene_bounds + 3 + a, hi[a]); }
+        }
+        if (!all_exact) atomicAnd(flags, 0);
+    }
+}
+
+__global__ void k_morton(const double* centre, uint32_t nt, const float* scene_bounds, uint64_t* keys, uint32_t* vals) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= nt) return;
+    const double slo[3] = { scene_bounds[0], scene_bounds[1], scene_bounds[2] };
+    const double shi[3] = { scene_bounds[3], scene_bounds[4], scene_bounds[5] };
+    keys[g] = morton_body(centre, g, slo, shi);
+    vals[g] = g;
+}
+
+__global__ void k_hierarchy(const uint64_t* keys, int n, BinNode* nodes, uint32_t* parent) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n - 1) hierarchy_body(i, keys, n, nodes, parent);
+}
+
+// leaves: bounds from the sorted triangles; then climb, the second arrival at a node fits it
+__global__ void k_fit(BinNode* nodes, const uint32_t* parent, const uint32_t* sorted_tri, const float* tri_lo,
+                      const float* tri_hi, int n, uint32_t* arrive) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const uint32_t g = sorted_tri[j];
+    BinNode leaf;
+    for (int a = 0; a < 3; a++) { leaf.lo[a] = tri_lo[(size_t)g * 3 + a]; leaf.hi[a] = tri_hi[(size_t)g * 3 + a]; }
+    leaf.left = leaf.right = 0xffffffffu;
+    leaf.first = (uint32_t)j; leaf.count = 1;
+    uint32_t id = (uint32_t)(n - 1 + j);
+    nodes[id] = leaf;
+    if (n == 1) return;
+    __threadfence();
+    uint32_t cur = parent[id];
+    while (true) {
+        const uint32_t old = atomicAdd(&arrive[cur], 1u);
+        if (old == 0) return;                 // first arrival: the sibling subtree is not ready yet
+        __threadfence();
+        BinNode* nd = nodes + cur;
+        const uint32_t l = nd->left, r = nd->right;
+        for (int a = 0; a < 3; a++) {
+            const float llo = __ldcg(&nodes[l].lo[a]), rlo = __ldcg(&nodes[r].lo[a]);
+            const float lhi = __ldcg(&nodes[l].hi[a]), rhi = __ldcg(&nodes[r].hi[a]);
+            nd->lo[a] = fminf(llo, rlo);
+            nd->hi[a] = fmaxf(lhi, rhi);
+        }
+        __threadfence();
+        if (cur == 0) return;                 // root
+        cur = parent[cur];
+    }
+}
+
+__global__ void k_collapse(CollapseCtx c, const CollapseItem* queue, uint32_t count) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) collapse_body(c, queue[i]);
+}
+
+__global__ void k_emit(const uint32_t* tri_order, uint32_t nt, const PrimDev* prims, int num_prims, const double* wp,
+                       const double* mesh_p, const double* mesh_n, TriF32* t32, TriF64* t64, TriShade* shade) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < nt) emit_body(k, tri_order, prims, num_prims, wp, mesh_p, mesh_n, t32, t64, shade);
+}
+
+// ================================================================================================
+// kernels: accel batches
+// ================================================================================================
+// Persistent threads: each warp claims 32 consecutive rays from a global cursor.
+__device__ __forceinline__ unsigned long long warp_fetch(unsigned long long* cursor) {
+    unsigned long long base = 0;
+    if ((threadIdx.x & 31) == 0) base = atomicAdd(cursor, 32ull);
+    return __shfl_sync(0xffffffffu, base, 0);
+}
+
+template <typename TriT, bool COUNT>
+__global__ void __launch_bounds__(128) k_intersect(DevScene s, const LmcuRay* __restrict__ rays, unsigned long long n,
+                                                   LmcuHit* __restrict__ hits, unsigned long long* cursor,
+                                                   unsigned long long* counters, uint32_t* overflow) {
+    uint2 stack[kStackSize];
+    unsigned long long c_nodes = 0, c_tris = 0;
+    while (true) {
+        const unsigned long long base = warp_fetch(cursor);
+        if (base >= n) break;
+        const unsigned long long i = base + (threadIdx.x & 31);
+        if (i >= n) continue;
+        const double2* src = reinterpret_cast<const double2*>(rays + i);
+        const double2 a = src[0], b = src[1], c = src[2], d = src[3];
+        RayD r;
+        r.o = d3(a.x, a.y, b.x); r.d = d3(b.y, c.x, c.y); r.tmin = d.x; r.tmax = d.y;
+        HitD h; h.t = r.tmax; h.u = h.v = 0; h.tri = -1;
+        TraverseCounters tc; tc.nodes = tc.tris = 0;
+        if (!traverse<false, COUNT, TriT>(s.nodes, scene_tris<TriT>(s), r, h, stack, &tc)) atomicExch(overflow, 1u);
+        if (COUNT) { c_nodes += tc.nodes; c_tris += tc.tris; }
+        int32_t prim = -1, face = -1;
+        if (h.tri >= 0) {
+            F3 p1, p2, p3; int32_t pi;
+            tri_fetch(s, (uint32_t)h.tri, p1, p2, p3, pi, face);
+            prim = s.prims[pi].node_index;
+        }
+        double2* dst = reinterpret_cast<double2*>(hits + i);
+        dst[0] = make_double2(h.t, h.u);
+        double2 o2; o2.x = h.v;
+        int2 pf = make_int2(prim, face);
+        memcpy(&o2.y, &pf, 8);
+        dst[1] = o2;
+    }
+    if (COUNT) { atomicAdd(counters, c_nodes); atomicAdd(counters + 1, c_tris); }
+}
+
+// ================================================================================================
+// kernels: renderers
+// ================================================================================================
+template <typename TriT>
+__global__ void __launch_bounds__(128) k_raycast(DevScene s, RaycastParams p, float* film, unsigned long long* cursor) {
+    uint2 stack[kStackSize];
+    const unsigned long long n = (unsigned long long)p.width * p.height;
+    const bool tiled = (p.width % 8 == 0) && (p.height % 4 == 0);
+    while (true) {
+        const unsigned long long base = warp_fetch(cursor);
+        if (base >= n) break;
+        const unsigned long long i = base + (threadIdx.x & 31);
+        if (i >= n) continue;
+        int x, y;
+        if (tiled) {
+            const uint32_t tiles_x = (uint32_t)p.width / 8u, tile = (uint32_t)(i >> 5), idx = (uint32_t)i & 31u;
+            x = (int)((tile % tiles_x) * 8u + (idx & 7u)); y = (int)((tile / tiles_x) * 4u + (idx >> 3));
+        } else {
+            x = (int)(i % p.width); y = (int)(i / p.width);
+        }
+        raycast_pixel<TriT>(s, p, x, y, film, stack);
+    }
+}
+
+template <typename TriT>
+__global__ void __launch_bounds__(128) k_ao(DevScene s, int width, int height, long long spp, unsigned long long sample_offset,
+                                            uint32_t seed, double ao_distance, float* film, unsigned long long* cursor,
+                                            unsigned long long* rays) {
+    uint2 stack[kStackSize];
+    const unsigned long long n = (unsigned long long)width * height;
+    const bool tiled = (width % 8 == 0) && (height % 4 == 0);
+    uint32_t local_rays = 0;
+    while (true) {
+        const unsigned long long base = warp_fetch(cursor);
+        if (base >= n) break;
+        const unsigned long long i = base + (threadIdx.x & 31);
+        if (i >= n) continue;
+        int x, y;
+        if (tiled) {
+            const uint32_t tiles_x = (uint32_t)width / 8u, tile = (uint32_t)(i >> 5), idx = (uint32_t)i & 31u;
+            x = (int)((tile % tiles_x) * 8u + (idx & 7u)); y = (int)((tile / tiles_x) * 4u + (idx >> 3));
+        } else {
+            x = (int)(i % width); y = (int)(i / width);
+        }
+        ao_pixel<TriT>(s, width, height, x, y, spp, sample_offset, seed, ao_distance, film, stack, &local_rays);
+    }
+    atomicAdd(rays, (unsigned long long)local_rays);
+}
+
+// -- wavefront pt ----------------------------------------------------------------------------------
+// generate: refill the current queue up to capacity with new camera paths (contiguous -> coherent warps)
+__global__ void k_pt_generate(DevScene s, PtParams p, PathQueue q, PtCounters* ctr, int cur) {
+    const uint32_t m = ctr->count[cur];
+    const unsigned long long next = ctr->next_path;
+    const unsigned long long remaining = p.total_paths - next;
+    const uint32_t room = p.capacity - m;
+    const uint32_t n_new = remaining < room ? (uint32_t)remaining : room;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_new; i += gridDim.x * blockDim.x) {
+        pt_generate_body(s, p, next + i, q, m + i);
+    }
+}
+
+// advance: single thread; publishes the refilled count and resets the per-iteration cursors
+__global__ void k_pt_advance(PtParams p, PtCounters* ctr, int cur) {
+    const uint32_t m = ctr->count[cur];
+    const unsigned long long remaining = p.total_paths - ctr->next_path;
+    const uint32_t room = p.capacity - m;
+    const uint32_t n_new = remaining < room ? (uint32_t)remaining : room;
+    ctr->count[cur] = m + n_new;
+    ctr->next_path += n_new;
+    ctr->count[cur ^ 1] = 0;
+    ctr->shadow_count = 0;
+    ctr->fetch_extend = 0;
+    ctr->fetch_shadow = 0;
+    ctr->rays += m + n_new;
+    ctr->iterations += 1;
+}
+
+template <typename TriT>
+__global__ void __launch_bounds__(128) k_pt_extend(DevScene s, PathQueue q, float4* hits, PtCounters* ctr, int cur) {
+    uint2 stack[kStackSize];
+    const uint32_t n = ctr->count[cur];
+    while (true) {
+        uint32_t base = 0;
+        if ((threadIdx.x & 31) == 0) base = atomicAdd(&ctr->fetch_extend, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        const uint32_t i = base + (threadIdx.x & 31);
+        if (i >= n) continue;
+        HitD h;
+        if (!pt_trace<false, TriT>(s, q.ray_o[i], q.ray_d[i], h, stack)) atomicExch(&ctr->overflow, 1u);
+        hits[i] = make_float4((float)h.t, (float)h.u, (float)h.v, __int_as_float(h.tri));
+    }
+}
+
+// Block-wide compaction: returns the queue position for threads with `pred`, using warp ballots,
+// a shared-memory scan of the warp totals and ONE global atomic per CTA.
+__device__ __forceinline__ uint32_t block_compact(bool pred, uint32_t* global_counter, uint32_t* smem /* [33] */) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const uint32_t ballot = __ballot_sync(0xffffffffu, pred);
+    if (lane == 0) smem[warp] = __popc(ballot);
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t v = lane < nwarps ? smem[lane] : 0u;
+        uint32_t incl = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= (uint32_t)o) incl += t;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        uint32_t base = 0;
+        if (lane == 0 && total) base = atomicAdd(global_counter, total);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (lane < nwarps) smem[lane] = base + incl - v;
+    }
+    __syncthreads();
+    const uint32_t pos = smem[warp] + __popc(ballot & ((1u << lane) - 1u));
+    __syncthreads();
+    return pos;
+}
+
+__global__ void __launch_bounds__(256) k_pt_shade(DevScene s, PtParams p, PathQueue qin, PathQueue qout, ShadowQueue sq,
+                                                  const float4* hits, float* film, PtCounters* ctr, int cur) {
+    __shared__ uint32_t smem[33];
+    const uint32_t n = ctr->count[cur];
+    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+        const uint32_t i = base + threadIdx.x;
+        ShadeOut o;
+        o.alive = false; o.shadow = false;
+        if (i < n) {
+            o = pt_shade_body(s, p, qin.ray_o[i], qin.ray_d[i], qin.thr_pix[i], qin.aux[i], qin.info[i], hits[i]);
+            if (!is_zero(o.emit)) {
+                float* px = film + (size_t)f2u(qin.thr_pix[i].w) * 3;
+                atomicAdd(px + 0, o.emit.x); atomicAdd(px + 1, o.emit.y); atomicAdd(px + 2, o.emit.z);
+            }
+        }
+        const uint32_t pos = block_compact(o.alive, &ctr->count[cur ^ 1], smem);
+        if (o.alive) {
+            qout.ray_o[pos] = o.o; qout.ray_d[pos] = o.d; qout.thr_pix[pos] = o.thr_pix; qout.aux[pos] = o.aux;
+            qout.info[pos] = o.info;
+        }
+        const uint32_t spos = block_compact(o.shadow, &ctr->shadow_count, smem);
+        if (o.shadow) {
+            sq.ray_o[spos] = o.sh_o; sq.ray_d[spos] = o.sh_d; sq.contrib[spos] = o.sh_c;
+        }
+    }
+}
+
+template <typename TriT>
+__global__ void __launch_bounds__(128) k_pt_shadow(DevScene s, ShadowQueue sq, float* film, PtCounters* ctr) {
+    uint2 stack[kStackSize];
+    const uint32_t n = ctr->shadow_count;
+    if (blockIdx.x == 0 && threadIdx.x == 0) ctr->rays += n;
+    while (true) {
+        uint32_t base = 0;
+        if ((threadIdx.x & 31) == 0) base = atomicAdd(&ctr->fetch_shadow, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        const uint32_t i = base + (threadIdx.x & 31);
+        if (i >= n) continue;
+        HitD h;
+        if (!pt_trace<true, TriT>(s, sq.ray_o[i], sq.ray_d[i], h, stack)) atomicExch(&ctr->overflow, 1u);
+        if (h.tri < 0) {                                     // visible (include/lm/scene.h:343-364)
+            const float4 c = sq.contrib[i];
+            float* px = film + (size_t)__float_as_uint(c.w) * 3;
+            atomicAdd(px + 0, c.x); atomicAdd(px + 1, c.y); atomicAdd(px + 2, c.z);
+        }
+    }
+}
+
+__global__ void k_scale(float* film, size_t n, float s) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) film[i] *= s;
+}
+
+// ================================================================================================
+// host side
+// ================================================================================================
+template <typename T>
+struct DBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t alloc(size_t count) {
+        release();
+        n = count;
+        if (count == 0) return cudaSuccess;
+        return cudaMalloc((void**)&p, count * sizeof(T));
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    ~DBuf() { release(); }
+    DBuf() = default;
+    DBuf(const DBuf&) = delete;
+    DBuf& operator=(const DBuf&) = delete;
+};
+
+struct LmcuScene {
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    // description (device)
+    DBuf<double> mesh_p, mesh_n;
+    DBuf<PrimDev> prims;
+    DBuf<MaterialDev> mats;
+    DBuf<LightDev> lights;
+    DBuf<EmitTri> emit;
+    DBuf<float> cdf;
+    std::vector<PrimDev> h_prims;
+    uint32_t nt = 0;
+    int num_prims = 0, num_lights = 0, env_light = -1;
+    CameraDev cam{};
+    bool has_camera = false;
+    // accel
+    DBuf<WideNode> nodes;
+    DBuf<TriF32> t32;
+    DBuf<TriF64> t64;
+    DBuf<TriShade> shade;
+    bool built = false, fp32 = false;
+    // scratch / outputs
+    DBuf<unsigned long long> cursor;     // [0] work cursor, [1..2] counters, [3] rays
+    DBuf<uint32_t> flags;                // [0] stack overflow
+    DBuf<float> film;
+    int film_w = 0, film_h = 0;
+    // pt pools
+    DBuf<float4> pq[2][4];
+    DBuf<uint2> pinfo[2];
+    DBuf<float4> hits;
+    DBuf<float4> sq[3];
+    DBuf<PtCounters> pt_ctr;
+    uint32_t pt_capacity = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+    DevScene dev() const {
+        DevScene d{};
+        d.nodes = nodes.p; d.t32 = t32.p; d.t64 = t64.p; d.shade = shade.p; d.prims = prims.p; d.mats = mats.p;
+        d.lights = lights.p; d.emit = emit.p; d.cdf = cdf.p; d.env_tex = nullptr;
+        d.num_prims = num_prims; d.num_lights = num_lights; d.env_light = env_light; d.num_tris = nt; d.cam = cam;
+        return d;
+    }
+};
+
+static inline unsigned grid_for(size_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
+
+extern "C" {
+
+const char* lmcu_last_error(void) { return g_error.c_str(); }
+const char* lmcu_version(void) { return "lmcu 0.1 (sm_100a)"; }
+
+int lmcu_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int lmcu_scene_create(int device, LmcuScene** out) {
+    if (!out) return fail(LMCU_ERR_INVALID_ARGUMENT, "out is null");
+    const int n = lmcu_device_count();
+    if (n == 0) return fail(LMCU_ERR_NO_DEVICE, "no CUDA device: liblmcu has no CPU fallback");
+    if (device < 0 || device >= n) return fail(LMCU_ERR_INVALID_ARGUMENT, "bad device index");
+    CU(cudaSetDevice(device));
+    LmcuScene* s = new LmcuScene;
+    s->device = device;
+    CU(cudaDeviceGetAttribute(&s->num_sms, cudaDevAttrMultiProcessorCount, device));
+    CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&s->ev0));
+    CU(cudaEventCreate(&s->ev1));
+    CU(s->cursor.alloc(8));
+    CU(s->flags.alloc(4));
+    CU(cudaMemset(s->cursor.p, 0, 8 * sizeof(unsigned long long)));
+    CU(cudaMemset(s->flags.p, 0, 4 * sizeof(uint32_t)));
+    *out = s;
+    return LMCU_OK;
+}
+
+void lmcu_scene_destroy(LmcuScene* s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    cudaDeviceSynchronize();
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+// -- upload -----------------------------------------------------------------------------------------
+int lmcu_scene_upload(LmcuScene* s, const LmcuSceneDesc* d) {
+    if (!s || !d) return fail(LMCU_ERR_INVALID_ARGUMENT, "null argument");
+    CU(cudaSetDevice(s->device));
+    PreparedScene ps;
+    std::string err;
+    const int rc = prepare_scene(d, ps, err);
+    if (rc) return fail(rc, err);
+    const size_t total_faces = ps.face_offset.back();
+    CU(s->mesh_p.alloc(total_faces * 9));
+    CU(s->mesh_n.alloc(total_faces * 9));
+    for (int i = 0; i < d->num_meshes; i++) {
+        const size_t bytes = (size_t)d->meshes[i].num_faces * 9 * sizeof(double);
+        CU(cudaMemcpy(s->mesh_p.p + (size_t)ps.face_offset[i] * 9, d->meshes[i].p, bytes, cudaMemcpyHostToDevice));
+        if (d->meshes[i].n) {
+            CU(cudaMemcpy(s->mesh_n.p + (size_t)ps.face_offset[i] * 9, d->meshes[i].n, bytes, cudaMemcpyHostToDevice));
+        }
+    }
+    s->h_prims = ps.prims;
+    s->nt = ps.nt;
+    s->num_prims = (int)ps.prims.size();
+    s->num_lights = (int)ps.lights.size();
+    s->env_light = ps.env_light;
+    s->cam = ps.cam;
+    s->has_camera = ps.has_camera;
+    CU(s->mats.alloc(ps.mats.size()));
+    if (!ps.mats.empty()) CU(cudaMemcpy(s->mats.p, ps.mats.data(), ps.mats.size() * sizeof(MaterialDev), cudaMemcpyHostToDevice));
+    CU(s->lights.alloc(ps.lights.size()));
+    if (!ps.lights.empty()) CU(cudaMemcpy(s->lights.p, ps.lights.data(), ps.lights.size() * sizeof(LightDev), cudaMemcpyHostToDevice));
+    CU(s->emit.alloc(ps.emit.size()));
+    if (!ps.emit.empty()) CU(cudaMemcpy(s->emit.p, ps.emit.data(), ps.emit.size() * sizeof(EmitTri), cudaMemcpyHostToDevice));
+    CU(s->cdf.alloc(ps.cdf.size()));
+    if (!ps.cdf.empty()) CU(cudaMemcpy(s->cdf.p, ps.cdf.data(), ps.cdf.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CU(s->prims.alloc(ps.prims.size()));
+    CU(cudaMemcpy(s->prims.p, ps.prims.data(), ps.prims.size() * sizeof(PrimDev), cudaMemcpyHostToDevice));
+    s->built = false;
+    return LMCU_OK;
+}
+
+// -- build ------------------------------------------------------------------------------------------
+int lmcu_accel_build(LmcuScene* s, const LmcuBuildOptions* opts, LmcuBuildStats* stats) {
+    if (!s) return fail(LMCU_ERR_INVALID_ARGUMENT, "null scene");
+    if (s->nt == 0) return fail(LMCU_ERR_UNSUPPORTED, "Missing primitives.");
+    CU(cudaSetDevice(s->device));
+    const uint32_t nt = s->nt;
+    int max_leaf = opts && opts->max_leaf_tris ? opts->max_leaf_tris : 3;
+    if (max_leaf < 1 || max_leaf > 3) return fail(LMCU_ERR_INVALID_ARGUMENT, "max_leaf_tris must be in 1..3");
+    cudaStream_t st = s->stream;
+    CU(cudaEventRecord(s->ev0, st));
+
+    DBuf<double> wp, centre;
+    DBuf<float> tri_lo, tri_hi, bounds;
+    DBuf<int> exact;
+    DBuf<uint64_t> keys, keys_sorted;
+    DBuf<uint32_t> vals, vals_sorted, parent, arrive, tri_order, counters;
+    DBuf<BinNode> bin;
+    DBuf<WideNode> wide;
+    DBuf<CollapseItem> queue[2];
+    CU(wp.alloc((size_t)nt * 9)); CU(centre.alloc((size_t)nt * 3));
+    CU(tri_lo.alloc((size_t)nt * 3)); CU(tri_hi.alloc((size_t)nt * 3));
+    CU(bounds.alloc(6)); CU(exact.alloc(1));
+    const float binit[6] = { 3e38f, 3e38f, 3e38f, -3e38f, -3e38f, -3e38f };
+    const int one = 1;
+    CU(cudaMemcpyAsync(bounds.p, binit, sizeof(binit), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(exact.p, &one, sizeof(int), cudaMemcpyHostToDevice, st));
+    k_flatten<<<grid_for(nt, 256), 256, 0, st>>>(s->prims.p, s->num_prims, s->mesh_p.p, nt, wp.p, tri_lo.p, tri_hi.p,
+                                                 centre.p, bounds.p, exact.p);
+    CU(cudaGetLastError());
+    CU(keys.alloc(nt)); CU(keys_sorted.alloc(nt)); CU(vals.alloc(nt)); CU(vals_sorted.alloc(nt));
+    k_morton<<<grid_for(nt, 256), 256, 0, st>>>(centre.p, nt, bounds.p, keys.p, vals.p);
+    CU(cudaGetLastError());
+    {
+        size_t tmp_bytes = 0;
+        CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys.p, keys_sorted.p, vals.p, vals_sorted.p, (int)nt, 0, 63, st));
+        DBuf<unsigned char> tmp;
+        CU(tmp.alloc(tmp_bytes));
+        CU(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys.p, keys_sorted.p, vals.p, vals_sorted.p, (int)nt, 0, 63, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    CU(bin.alloc((size_t)2 * nt)); CU(parent.alloc((size_t)2 * nt)); CU(arrive.alloc(nt));
+    CU(cudaMemsetAsync(arrive.p, 0, (size_t)nt * sizeof(uint32_t), st));
+    CU(cudaMemsetAsync(parent.p, 0xff, (size_t)2 * nt * sizeof(uint32_t), st));
+    if (nt > 1) {
+        k_hierarchy<<<grid_for(nt - 1, 256), 256, 0, st>>>(keys_sorted.p, (int)nt, bin.p, parent.p);
+        CU(cudaGetLastError());
+    }
+    k_fit<<<grid_for(nt, 256), 256, 0, st>>>(bin.p, parent.p, vals_sorted.p, tri_lo.p, tri_hi.p, (int)nt, arrive.p);
+    CU(cudaGetLastError());
+    // collapse, level by level
+    CU(wide.alloc(nt)); CU(tri_order.alloc(nt)); CU(counters.alloc(4));
+    CU(queue[0].alloc(nt)); CU(queue[1].alloc(nt));
+    const uint32_t cinit[4] = { 1u, 0u, 0u, 0u };   // node_counter (root = 0 taken), tri_counter, next_count, -
+    CU(cudaMemcpyAsync(counters.p, cinit, sizeof(cinit), cudaMemcpyHostToDevice, st));
+    const CollapseItem root_item = { nt > 1 ? 0u : 0u, 0u };   // binary root is internal node 0 (or leaf 0 when nt == 1)
+    CU(cudaMemcpyAsync(queue[0].p, &root_item, sizeof(root_item), cudaMemcpyHostToDevice, st));
+    uint32_t count = 1;
+    int cur = 0;
+    while (count > 0) {
+        CollapseCtx c;
+        c.bin = bin.p; c.sorted_tri = vals_sorted.p; c.n = (int)nt; c.max_leaf = max_leaf; c.wide = wide.p;
+        c.tri_order = tri_order.p; c.node_counter = counters.p; c.tri_counter = counters.p + 1;
+        c.next_queue = queue[cur ^ 1].p; c.next_count = counters.p + 2;
+        k_collapse<<<grid_for(count, 128), 128, 0, st>>>(c, queue[cur].p, count);
+        CU(cudaGetLastError());
+        uint32_t h[3];
+        CU(cudaMemcpyAsync(h, counters.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        count = h[2];
+        const uint32_t zero = 0;
+        CU(cudaMemcpyAsync(counters.p + 2, &zero, sizeof(zero), cudaMemcpyHostToDevice, st));
+        cur ^= 1;
+        if (count == 0) {
+            if (h[1] != nt) return fail(LMCU_ERR_CUDA, "bvh collapse lost triangles");
+            // shrink the node array to its final size
+            CU(s->nodes.alloc(h[0]));
+            CU(cudaMemcpyAsync(s->nodes.p, wide.p, (size_t)h[0] * sizeof(WideNode), cudaMemcpyDeviceToDevice, st));
+        }
+    }
+    int h_exact = 0;
+    CU(cudaMemcpyAsync(&h_exact, exact.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    s->fp32 = h_exact != 0;
+    s->t32.release(); s->t64.release();
+    if (s->fp32) CU(s->t32.alloc(nt)); else CU(s->t64.alloc(nt));
+    CU(s->shade.alloc(nt));
+    k_emit<<<grid_for(nt, 256), 256, 0, st>>>(tri_order.p, nt, s->prims.p, s->num_prims, wp.p, s->mesh_p.p, s->mesh_n.p,
+                                              s->t32.p, s->t64.p, s->shade.p);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(s->ev1, st));
+    CU(cudaStreamSynchronize(st));
+    s->built = true;
+    if (stats) {
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+        stats->elapsed = ms * 1e-3;
+        stats->num_triangles = nt;
+        stats->num_wide_nodes = (int64_t)s->nodes.n;
+        stats->node_bytes = (int64_t)(s->nodes.n * sizeof(WideNode));
+        stats->triangle_bytes = (int64_t)nt * (int64_t)(s->fp32 ? sizeof(TriF32) : sizeof(TriF64));
+        stats->triangles_fp32 = s->fp32 ? 1 : 0;
+        stats->sah_cost = 0.0;
+    }
+    return LMCU_OK;
+}
+
+// -- intersect ------------------------------------------------------------------------------------------
+static int launch_intersect(LmcuScene* s, const LmcuRay* d_rays, int64_t n, LmcuHit* d_hits, bool count, cudaStream_t st) {
+    CU(cudaMemsetAsync(s->cursor.p, 0, 3 * sizeof(unsigned long long), st));
+    const DevScene d = s->dev();
+    const unsigned blocks = (unsigned)std::min<int64_t>((n + 127) / 128, (int64_t)s->num_sms * 12);
+    if (s->fp32) {
+        if (count) k_intersect<TriF32, true><<<blocks, 128, 0, st>>>(d, d_rays, (unsigned long long)n, d_hits, s->cursor.p, s->cursor.p + 1, s->flags.p);
+        else k_intersect<TriF32, false><<<blocks, 128, 0, st>>>(d, d_rays, (unsigned long long)n, d_hits, s->cursor.p, s->cursor.p + 1, s->flags.p);
+    } else {
+        if (count) k_intersect<TriF64, true><<<blocks, 128, 0, st>>>(d, d_rays, (unsigned long long)n, d_hits, s->cursor.p, s->cursor.p + 1, s->flags.p);
+        else k_intersect<TriF64, false><<<blocks, 128, 0, st>>>(d, d_rays, (unsigned long long)n, d_hits, s->cursor.p, s->cursor.p + 1, s->flags.p);
+    }
+    CU(cudaGetLastError());
+    return LMCU_OK;
+}
+
+static int check_overflow(LmcuScene* s) {
+    uint32_t f = 0;
+    CU(cudaMemcpy(&f, s->flags.p, sizeof(f), cudaMemcpyDeviceToHost));
+    if (f) {
+        CU(cudaMemset(s->flags.p, 0, sizeof(uint32_t)));
+        return fail(LMCU_ERR_CUDA, "bvh traversal stack overflow");
+    }
+    return LMCU_OK;
+}
+
+int lmcu_accel_intersect_device(LmcuScene* s, const void* d_rays, int64_t n, void* d_hits, void* stream) {
+    if (!s || !s->built) return fail(LMCU_ERR_UNSUPPORTED, "Missing acceleration structure. Build first.");
+    if (n <= 0) return LMCU_OK;
+    CU(cudaSetDevice(s->device));
+    return launch_intersect(s, (const LmcuRay*)d_rays, n, (LmcuHit*)d_hits, false, stream ? (cudaStream_t)stream : s->stream);
+}
+
+static int intersect_host(LmcuScene* s, const LmcuRay* rays, int64_t n, LmcuHit* hits, bool count, double* npr, double* tpr) {
+    if (!s || !s->built) return fail(LMCU_ERR_UNSUPPORTED, "Missing acceleration structure. Build first.");
+    if (n <= 0) return LMCU_OK;
+    if (!rays || !hits) return fail(LMCU_ERR_INVALID_ARGUMENT, "null buffer");
+    CU(cudaSetDevice(s->device));
+    DBuf<LmcuRay> d_rays;
+    DBuf<LmcuHit> d_hits;
+    CU(d_rays.alloc(n)); CU(d_hits.alloc(n));
+    CU(cudaMemcpyAsync(d_rays.p, rays, (size_t)n * sizeof(LmcuRay), cudaMemcpyHostToDevice, s->stream));
+    const int rc = launch_intersect(s, d_rays.p, n, d_hits.p, count, s->stream);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(hits, d_hits.p, (size_t)n * sizeof(LmcuHit), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    if (count) {
+        unsigned long long c[2];
+        CU(cudaMemcpy(c, s->cursor.p + 1, sizeof(c), cudaMemcpyDeviceToHost));
+        if (npr) *npr = (double)c[0] / (double)n;
+        if (tpr) *tpr = (double)c[1] / (double)n;
+    }
+    return check_overflow(s);
+}
+
+int lmcu_accel_intersect(LmcuScene* s, const LmcuRay* rays, int64_t n, LmcuHit* hits) {
+    return intersect_host(s, rays, n, hits, false, nullptr, nullptr);
+}
+
+int lmcu_accel_intersect_counted(LmcuScene* s, const LmcuRay* rays, int64_t n, LmcuHit* hits, double* npr, double* tpr) {
+    return intersect_host(s, rays, n, hits, true, npr, tpr);
+}
+
+// -- film ---------------------------------------------------------------------------------------------
+static int ensure_film(LmcuScene* s, int w, int h) {
+    if (w <= 0 || h <= 0) return fail(LMCU_ERR_INVALID_ARGUMENT, "bad film size");
+    if (s->film_w != w || s->film_h != h || !s->film.p) {
+        CU(s->film.alloc((size_t)w * h * 3));
+        s->film_w = w; s->film_h = h;
+    }
+    CU(cudaMemsetAsync(s->film.p, 0, s->film.n * sizeof(float), s->stream));   // film_->clear()
+    return LMCU_OK;
+}
+
+int lmcu_film_device_ptr(LmcuScene* s, void** d_film, int64_t* num_floats) {
+    if (!s || !s->film.p) return fail(LMCU_ERR_UNSUPPORTED, "no film rendered yet");
+    if (d_film) *d_film = s->film.p;
+    if (num_floats) *num_floats = (int64_t)s->film.n;
+    return LMCU_OK;
+}
+
+int lmcu_film_rescale(LmcuScene* s, double v) {
+    if (!s || !s->film.p) return fail(LMCU_ERR_UNSUPPORTED, "no film rendered yet");
+    CU(cudaSetDevice(s->device));
+    k_scale<<<s->num_sms * 4, 256, 0, s->stream>>>(s->film.p, s->film.n, (float)v);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(s->stream));
+    return LMCU_OK;
+}
+
+int lmcu_film_download(LmcuScene* s, float* film_rgb) {
+    if (!s || !s->film.p) return fail(LMCU_ERR_UNSUPPORTED, "no film rendered yet");
+    CU(cudaSetDevice(s->device));
+    CU(cudaMemcpyAsync(film_rgb, s->film.p, s->film.n * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return LMCU_OK;
+}
+
+static int require_renderable(LmcuScene* s, bool need_light) {
+    if (!s) return fail(LMCU_ERR_INVALID_ARGUMENT, "null scene");
+    if (s->nt == 0) return fail(LMCU_ERR_UNSUPPORTED, "Missing primitives. Use lm::primitive() function to add primitives.");
+    if (!s->has_camera) return fail(LMCU_ERR_UNSUPPORTED, "Missing camera primitive.");
+    if (need_light && s->num_lights == 0) return fail(LMCU_ERR_UNSUPPORTED, "No light in the scene.");
+    if (!s->built) return fail(LMCU_ERR_UNSUPPORTED, "Missing acceleration structure.");
+    return LMCU_OK;
+}
+
+// -- raycast ------------------------------------------------------------------------------------------
+int lmcu_render_raycast(LmcuScene* s, const LmcuRenderParams* p, float* film_rgb, LmcuRenderStats* stats) {
+    int rc = require_renderable(s, false);
+    if (rc) return rc;
+    if (!p) return fail(LMCU_ERR_INVALID_ARGUMENT, "null params");
+    CU(cudaSetDevice(s->device));
+    rc = ensure_film(s, p->width, p->height);
+    if (rc) return rc;
+    RaycastParams rp{};
+    rp.width = p->width; rp.height = p->height;
+    rp.use_constant_color = p->use_constant_color; rp.visualize_normal = p->visualize_normal; rp.has_color = p->has_color;
+    for (int k = 0; k < 3; k++) { rp.bg[k] = (float)p->bg_color[k]; rp.color[k] = (float)p->color[k]; }
+    cudaStream_t st = s->stream;
+    CU(cudaMemsetAsync(s->cursor.p, 0, sizeof(unsigned long long), st));
+    CU(cudaEventRecord(s->ev0, st));
+    const size_t n = (size_t)p->width * p->height;
+    const unsigned blocks = (unsigned)std::min<size_t>((n + 127) / 128, (size_t)s->num_sms * 12);
+    const DevScene d = s->dev();
+    if (s->fp32) k_raycast<TriF32><<<blocks, 128, 0, st>>>(d, rp, s->film.p, s->cursor.p);
+    else k_raycast<TriF64><<<blocks, 128, 0, st>>>(d, rp, s->film.p, s->cursor.p);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(s->ev1, st));
+    if (film_rgb) CU(cudaMemcpyAsync(film_rgb, s->film.p, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (stats) {
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+        memset(stats, 0, sizeof(*stats));
+        stats->elapsed = ms * 1e-3; stats->processed = 1; stats->paths = (int64_t)n; stats->rays = (int64_t)n;
+        stats->kernel_launches = 1;
+    }
+    return check_overflow(s);
+}
+
+// -- ao -------------------------------------------------------------------------------------------------
+int lmcu_render_ao(LmcuScene* s, const LmcuRenderParams* p, float* film_rgb, LmcuRenderStats* stats) {
+    int rc = require_renderable(s, false);
+    if (rc) return rc;
+    if (!p || p->spp <= 0) return fail(LMCU_ERR_INVALID_ARGUMENT, "spp must be positive");
+    CU(cudaSetDevice(s->device));
+    rc = ensure_film(s, p->width, p->height);
+    if (rc) return rc;
+    cudaStream_t st = s->stream;
+    CU(cudaMemsetAsync(s->cursor.p, 0, 4 * sizeof(unsigned long long), st));
+    CU(cudaEventRecord(s->ev0, st));
+    const size_t n = (size_t)p->width * p->height;
+    const unsigned blocks = (unsigned)std::min<size_t>((n + 127) / 128, (size_t)s->num_sms * 12);
+    const DevScene d = s->dev();
+    const double dist = p->ao_distance > 0 ? p->ao_distance : 0.2;
+    if (s->fp32) k_ao<TriF32><<<blocks, 128, 0, st>>>(d, p->width, p->height, p->spp, (unsigned long long)p->sample_offset, p->seed, dist, s->film.p, s->cursor.p, s->cursor.p + 3);
+    else k_ao<TriF64><<<blocks, 128, 0, st>>>(d, p->width, p->height, p->spp, (unsigned long long)p->sample_offset, p->seed, dist, s->film.p, s->cursor.p, s->cursor.p + 3);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(s->ev1, st));
+    if (film_rgb) CU(cudaMemcpyAsync(film_rgb, s->film.p, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    unsigned long long rays = 0;
+    CU(cudaMemcpyAsync(&rays, s->cursor.p + 3, sizeof(rays), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (stats) {
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+        memset(stats, 0, sizeof(*stats));
+        stats->elapsed = ms * 1e-3; stats->processed = p->spp; stats->paths = (int64_t)n; stats->rays = (int64_t)rays;
+        stats->kernel_launches = 1;
+    }
+    return check_overflow(s);
+}
+
+// -- pt ---------------------------------------------------------------------------------------------------
+static int ensure_pt_pools(LmcuScene* s, uint32_t capacity) {
+    if (s->pt_capacity == capacity && s->pt_ctr.p) return LMCU_OK;
+    for (int b = 0; b < 2; b++) {
+        for (int k = 0; k < 4; k++) CU(s->pq[b][k].alloc(capacity));
+        CU(s->pinfo[b].alloc(capacity));
+    }
+    CU(s->hits.alloc(capacity));
+    for (int k = 0; k < 3; k++) CU(s->sq[k].alloc(capacity));
+    CU(s->pt_ctr.alloc(1));
+    s->pt_capacity = capacity;
+    return LMCU_OK;
+}
+
+int lmcu_render_pt(LmcuScene* s, const LmcuRenderParams* p, float* film_rgb, LmcuRenderStats* stats) {
+    int rc = require_renderable(s, true);
+    if (rc) return rc;
+    if (!p || p->spp <= 0) return fail(LMCU_ERR_INVALID_ARGUMENT, "spp must be positive");
+    if (p->max_verts < 2) return fail(LMCU_ERR_INVALID_ARGUMENT, "max_verts must be >= 2");
+    if (p->sampling_mode < 0 || p->sampling_mode > 2) return fail(LMCU_ERR_INVALID_ARGUMENT, "bad sampling_mode");
+    CU(cudaSetDevice(s->device));
+    rc = ensure_film(s, p->width, p->height);
+    if (rc) return rc;
+    uint32_t capacity = 1u << 20;
+    if (const char* e = getenv("LMCU_PT_POOL")) capacity = (uint32_t)std::max(1024l, atol(e));
+    rc = ensure_pt_pools(s, capacity);
+    if (rc) return rc;
+    cudaStream_t st = s->stream;
+    PtParams pp{};
+    pp.width = p->width; pp.height = p->height; pp.max_verts = p->max_verts; pp.sampling_mode = p->sampling_mode;
+    pp.seed = p->seed; pp.tiled = (p->width % 8 == 0 && p->height % 4 == 0) ? 1u : 0u;
+    pp.sample_offset = (uint64_t)p->sample_offset;
+    pp.total_paths = (uint64_t)p->width * p->height * (uint64_t)p->spp;
+    pp.capacity = capacity;
+    PathQueue q[2];
+    for (int b = 0; b < 2; b++) {
+        q[b].ray_o = s->pq[b][0].p; q[b].ray_d = s->pq[b][1].p; q[b].thr_pix = s->pq[b][2].p; q[b].aux = s->pq[b][3].p;
+        q[b].info = s->pinfo[b].p;
+    }
+    ShadowQueue sq;
+    sq.ray_o = s->sq[0].p; sq.ray_d = s->sq[1].p; sq.contrib = s->sq[2].p;
+    CU(cudaMemsetAsync(s->pt_ctr.p, 0, sizeof(PtCounters), st));
+    CU(cudaEventRecord(s->ev0, st));
+    const DevScene d = s->dev();
+    const unsigned trav_blocks = (unsigned)s->num_sms * 12, shade_blocks = (unsigned)s->num_sms * 6, gen_blocks = (unsigned)s->num_sms * 4;
+    int cur = 0;
+    int64_t launches = 0;
+    PtCounters h{};
+    while (true) {
+        for (int it = 0; it < 4; it++) {
+            k_pt_generate<<<gen_blocks, 256, 0, st>>>(d, pp, q[cur], s->pt_ctr.p, cur);
+            k_pt_advance<<<1, 1, 0, st>>>(pp, s->pt_ctr.p, cur);
+            if (s->fp32) k_pt_extend<TriF32><<<trav_blocks, 128, 0, st>>>(d, q[cur], s->hits.p, s->pt_ctr.p, cur);
+            else k_pt_extend<TriF64><<<trav_blocks, 128, 0, st>>>(d, q[cur], s->hits.p, s->pt_ctr.p, cur);
+            k_pt_shade<<<shade_blocks, 256, 0, st>>>(d, pp, q[cur], q[cur ^ 1], sq, s->hits.p, s->film.p, s->pt_ctr.p, cur);
+            if (s->fp32) k_pt_shadow<TriF32><<<trav_blocks, 128, 0, st>>>(d, sq, s->film.p, s->pt_ctr.p);
+            else k_pt_shadow<TriF64><<<trav_blocks, 128, 0, st>>>(d, sq, s->film.p, s->pt_ctr.p);
+            cur ^= 1;
+            launches += 5;
+        }
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(&h, s->pt_ctr.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (h.overflow) return fail(LMCU_ERR_CUDA, "bvh traversal stack overflow");
+        if (h.next_path >= pp.total_paths && h.count[cur] == 0) break;
+    }
+    if (p->rescale) {
+        k_scale<<<s->num_sms * 4, 256, 0, st>>>(s->film.p, s->film.n, (float)(1.0 / (double)p->spp));   // renderer_pt.cpp:307-309
+        launches++;
+    }
+    CU(cudaEventRecord(s->ev1, st));
+    if (film_rgb) CU(cudaMemcpyAsync(film_rgb, s->film.p, s->film.n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (stats) {
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+        memset(stats, 0, sizeof(*stats));
+        stats->elapsed = ms * 1e-3; stats->processed = p->spp; stats->paths = (int64_t)pp.total_paths;
+        stats->rays = (int64_t)h.rays; stats->kernel_launches = launches;
+    }
+    return LMCU_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,141 @@
+// prep.hpp — host-side preparation of an LmcuSceneDesc for upload (pure C++, no CUDA calls):
+// validation, per-primitive normal matrices, emitter triangles + area CDFs (light_area.cpp:68-73),
+// camera basis in FP64 with glm's operation order (camera_pinhole.cpp:90-95).
+#pragma once
+#include <cmath>
+#include <string>
+#include <vector>
+#include "../../include/lmcu.h"
+#include "kernels.cuh"
+
+namespace lmcu {
+
+struct PreparedScene {
+    std::vector<uint32_t> face_offset;       // per mesh, into the concatenated face arrays
+    std::vector<PrimDev> prims;
+    std::vector<MaterialDev> mats;
+    std::vector<LightDev> lights;
+    std::vector<EmitTri> emit;
+    std::vector<float> cdf;
+    CameraDev cam{};
+    bool has_camera = false;
+    int env_light = -1;
+    uint32_t nt = 0;
+};
+
+inline void mat3_normal_matrix(const double* M, double* NM, double* J, float* sign) {
+    const double a = M[0], b = M[1], c = M[2], d = M[4], e = M[5], f = M[6], g = M[8], h = M[9], i = M[10];
+    const double det = a * (e * i - f * h) - d * (b * i - c * h) + g * (b * f - c * e);
+    const double id = 1.0 / det;
+    // inverse-transpose = cofactor matrix / det (column-major: NM[col*3+row]); math.h:742-745
+    NM[0] = (e * i - f * h) * id; NM[1] = -(d * i - f * g) * id; NM[2] = (d * h - e * g) * id;
+    NM[3] = -(b * i - c * h) * id; NM[4] = (a * i - c * g) * id; NM[5] = -(a * h - b * g) * id;
+    NM[6] = (b * f - c * e) * id; NM[7] = -(a * f - c * d) * id; NM[8] = (a * e - b * d) * id;
+    *J = std::fabs(det);
+    *sign = det < 0 ? -1.f : 1.f;
+}
+
+// Returns an LMCU_* status; err receives the message.
+inline int prepare_scene(const LmcuSceneDesc* d, PreparedScene& o, std::string& err) {
+    if (d->num_primitives <= 0 || d->num_meshes <= 0) { err = "Missing primitives."; return LMCU_ERR_UNSUPPORTED; }
+    o.face_offset.assign(d->num_meshes + 1, 0);
+    for (int i = 0; i < d->num_meshes; i++) {
+        if (!d->meshes[i].p) { err = "mesh without positions"; return LMCU_ERR_INVALID_ARGUMENT; }
+        o.face_offset[i + 1] = o.face_offset[i] + (uint32_t)d->meshes[i].num_faces;
+    }
+    o.prims.assign(d->num_primitives, PrimDev{});
+    uint64_t nt = 0;
+    for (int i = 0; i < d->num_primitives; i++) {
+        const LmcuPrimitive& p = d->primitives[i];
+        if (p.mesh < 0 || p.mesh >= d->num_meshes) { err = "primitive: bad mesh index"; return LMCU_ERR_INVALID_ARGUMENT; }
+        if (p.material < 0 || p.material >= d->num_materials) { err = "primitive: bad material index"; return LMCU_ERR_INVALID_ARGUMENT; }
+        if (p.light >= d->num_lights) { err = "primitive: bad light index"; return LMCU_ERR_INVALID_ARGUMENT; }
+        PrimDev& q = o.prims[i];
+        for (int k = 0; k < 16; k++) q.M[k] = p.M[k];
+        mat3_normal_matrix(p.M, q.NM, &q.J, &q.det_sign);
+        q.node_index = p.node_index; q.mesh = p.mesh; q.material = p.material; q.light = p.light;
+        q.tri_offset = (uint32_t)nt;
+        q.num_faces = (uint32_t)d->meshes[p.mesh].num_faces;
+        q.mesh_face_offset = o.face_offset[p.mesh];
+        q.has_normals = d->meshes[p.mesh].n ? 1 : 0;
+        q.inv_area = 0.f;
+        nt += q.num_faces;
+    }
+    if (nt == 0) { err = "Missing primitives."; return LMCU_ERR_UNSUPPORTED; }
+    if (nt > 0x7fffffffull) { err = "more than 2^31 triangles"; return LMCU_ERR_UNSUPPORTED; }
+    o.nt = (uint32_t)nt;
+    o.mats.resize(d->num_materials);
+    for (int i = 0; i < d->num_materials; i++) {
+        const LmcuMaterial& m = d->materials[i];
+        if (m.type < 0 || m.type > 3) { err = "bad material type"; return LMCU_ERR_INVALID_ARGUMENT; }
+        o.mats[i].type = m.type;
+        o.mats[i].r = (float)m.color[0]; o.mats[i].g = (float)m.color[1]; o.mats[i].b = (float)m.color[2];
+        o.mats[i].ax = (float)m.ax; o.mats[i].ay = (float)m.ay; o.mats[i].Ni = (float)m.Ni; o.mats[i].pad_ = 0.f;
+    }
+    o.lights.resize(d->num_lights);
+    o.env_light = -1;
+    for (int i = 0; i < d->num_lights; i++) {
+        const LmcuLight& l = d->lights[i];
+        LightDev& t = o.lights[i];
+        memset(&t, 0, sizeof(t));
+        t.type = l.type; t.prim = l.primitive;
+        for (int k = 0; k < 3; k++) t.Ke[k] = (float)l.Ke[k];
+        if (l.type == LMCU_LIGHT_AREA) {
+            if (l.primitive < 0 || l.primitive >= d->num_primitives) { err = "area light: bad primitive"; return LMCU_ERR_INVALID_ARGUMENT; }
+            PrimDev& q = o.prims[l.primitive];
+            const LmcuMesh& m = d->meshes[q.mesh];
+            t.tri_offset = (int32_t)o.emit.size(); t.num_tris = m.num_faces; t.cdf_offset = (int32_t)o.cdf.size();
+            std::vector<double> c(1, 0.0);
+            for (int f = 0; f < m.num_faces; f++) {
+                const double* p = m.p + (size_t)f * 9;
+                const double e1[3] = { p[3] - p[0], p[4] - p[1], p[5] - p[2] }, e2[3] = { p[6] - p[0], p[7] - p[1], p[8] - p[2] };
+                const double cr[3] = { e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0] };
+                const double len = std::sqrt(cr[0] * cr[0] + cr[1] * cr[1] + cr[2] * cr[2]);
+                c.push_back(c.back() + len * 0.5);
+                EmitTri et;
+                float4* dst[3] = { &et.p1, &et.p2, &et.p3 };
+                for (int v = 0; v < 3; v++) {
+                    const D3 w = transform_point(q.M, d3(p[3 * v], p[3 * v + 1], p[3 * v + 2]));
+                    *dst[v] = make_float4((float)w.x, (float)w.y, (float)w.z, 0.f);
+                }
+                const double gl[3] = { cr[0] / len, cr[1] / len, cr[2] / len };
+                const double gw[3] = { q.NM[0] * gl[0] + q.NM[3] * gl[1] + q.NM[6] * gl[2], q.NM[1] * gl[0] + q.NM[4] * gl[1] + q.NM[7] * gl[2],
+                                       q.NM[2] * gl[0] + q.NM[5] * gl[1] + q.NM[8] * gl[2] };
+                const double gwl = std::sqrt(gw[0] * gw[0] + gw[1] * gw[1] + gw[2] * gw[2]);
+                et.n = make_float4((float)(gw[0] / gwl), (float)(gw[1] / gwl), (float)(gw[2] / gwl), 0.f);
+                o.emit.push_back(et);
+            }
+            const double sum = c.back();
+            for (double v : c) o.cdf.push_back((float)(v / sum));
+            q.inv_area = (float)(1.0 / sum);
+            t.inv_area_j = (float)((1.0 / sum) / q.J);
+        } else if (l.type == LMCU_LIGHT_ENVCONST) {
+            if (o.env_light >= 0) { err = "Environment light is already registered."; return LMCU_ERR_INVALID_ARGUMENT; }
+            o.env_light = i;
+        } else {
+            err = "light type not supported yet"; return LMCU_ERR_UNSUPPORTED;
+        }
+    }
+    o.has_camera = d->camera != nullptr;
+    if (d->camera) {
+        const LmcuCamera& c = *d->camera;
+        CameraDev& cam = o.cam;
+        const D3 pos = d3(c.position[0], c.position[1], c.position[2]);
+        const D3 wv = dsub3(pos, d3(c.center[0], c.center[1], c.center[2]));
+        const double wi = divrn(1.0, sqrtrn(ddot(wv, wv)));
+        const D3 w = d3(mulrn(wv.x, wi), mulrn(wv.y, wi), mulrn(wv.z, wi));
+        const D3 uv = dcross(d3(c.up[0], c.up[1], c.up[2]), w);
+        const double ui = divrn(1.0, sqrtrn(ddot(uv, uv)));
+        const D3 u = d3(mulrn(uv.x, ui), mulrn(uv.y, ui), mulrn(uv.z, ui));
+        const D3 v = dcross(w, u);
+        cam.pos[0] = pos.x; cam.pos[1] = pos.y; cam.pos[2] = pos.z;
+        cam.u[0] = u.x; cam.u[1] = u.y; cam.u[2] = u.z;
+        cam.v[0] = v.x; cam.v[1] = v.y; cam.v[2] = v.z;
+        cam.w[0] = w.x; cam.w[1] = w.y; cam.w[2] = w.z;
+        cam.tf = std::tan(c.vfov * 3.14159265358979323846 / 180.0 * .5);
+        cam.aspect = c.aspect;
+    }
+    return LMCU_OK;
+}
+
+}  // namespace lmcu

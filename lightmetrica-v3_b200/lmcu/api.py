@@ -1,0 +1,124 @@
+"""Python host side of the CUDA hot path: a ctypes binding of liblmcu.so (include/lmcu.h).
+
+Mirrors the reference's component interface for this path:
+  Accel     build(scene) / intersect(ray, tmin, tmax)       /root/reference/include/lm/accel.h:38,70
+  Renderer  render() -> {"elapsed", "processed"}            /root/reference/include/lm/renderer.h:25
+with batched rays instead of one virtual call per ray.  There is no CPU fallback: importing works
+anywhere, but creating a Scene without liblmcu.so or without a CUDA device raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+from .scenes import HIT_DTYPE, RAY_DTYPE
+
+_PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(_PKG, "liblmcu.so")
+_LIB = None
+
+EXPORTS = [
+    "lmcu_last_error", "lmcu_device_count", "lmcu_version", "lmcu_scene_create", "lmcu_scene_destroy",
+    "lmcu_scene_upload", "lmcu_accel_build", "lmcu_accel_intersect", "lmcu_accel_intersect_device",
+    "lmcu_accel_intersect_counted", "lmcu_render_raycast", "lmcu_render_ao", "lmcu_render_pt",
+    "lmcu_film_device_ptr", "lmcu_film_rescale", "lmcu_film_download",
+]
+
+
+class LmcuError(RuntimeError):
+    """Raised for every non-zero status; .code is the LMCU_ERR_* value (lm::Error analogue)."""
+
+    def __init__(self, code, msg):
+        super().__init__("lmcu error %d: %s" % (code, msg))
+        self.code = code
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise LmcuError(-1, "liblmcu.so is not built (run __graft_entry__.build()); there is no CPU fallback")
+        _LIB = C.CDLL(LIB_PATH)
+        _LIB.lmcu_last_error.restype = C.c_char_p
+        _LIB.lmcu_version.restype = C.c_char_p
+    return _LIB
+
+
+def _check(rc):
+    if rc != 0:
+        raise LmcuError(rc, lib().lmcu_last_error().decode())
+
+
+def device_count():
+    return lib().lmcu_device_count()
+
+
+class Scene:
+    """accel::cuda_bvh + renderer::{raycast,ao,pt}_cuda over one uploaded scene on one GPU."""
+
+    def __init__(self, builder, device=0, max_leaf_tris=3):
+        self._builder = builder
+        self._desc = builder.desc()
+        self._h = C.c_void_p()
+        _check(lib().lmcu_scene_create(int(device), C.byref(self._h)))
+        _check(lib().lmcu_scene_upload(self._h, C.byref(self._desc)))
+        opts = abi.LmcuBuildOptions()
+        opts.max_leaf_tris = max_leaf_tris
+        self.build_stats = abi.LmcuBuildStats()
+        _check(lib().lmcu_accel_build(self._h, C.byref(opts), C.byref(self.build_stats)))
+        self.last_stats = None
+
+    # -- Accel ------------------------------------------------------------------------------------
+    def intersect(self, rays, counted=False):
+        """rays: structured array RAY_DTYPE (host).  Returns HIT_DTYPE array; primitive == -1 on miss."""
+        rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+        hits = np.zeros(len(rays), dtype=HIT_DTYPE)
+        rp, hp = rays.ctypes.data_as(C.c_void_p), hits.ctypes.data_as(C.c_void_p)
+        if counted:
+            npr, tpr = C.c_double(), C.c_double()
+            _check(lib().lmcu_accel_intersect_counted(self._h, rp, C.c_int64(len(rays)), hp, C.byref(npr), C.byref(tpr)))
+            self.nodes_per_ray, self.tris_per_ray = npr.value, tpr.value
+        else:
+            _check(lib().lmcu_accel_intersect(self._h, rp, C.c_int64(len(rays)), hp))
+        return hits
+
+    def intersect_device(self, d_rays_ptr, n, d_hits_ptr, stream=0):
+        """Device buffers (e.g. torch tensors' data_ptr()); asynchronous on `stream`."""
+        _check(lib().lmcu_accel_intersect_device(self._h, C.c_void_p(d_rays_ptr), C.c_int64(n), C.c_void_p(d_hits_ptr),
+                                                 C.c_void_p(stream)))
+
+    # -- Renderer ---------------------------------------------------------------------------------
+    def render(self, renderer, params, download=True):
+        """renderer: 'raycast' | 'ao' | 'pt'.  Returns (film[h,w,3] float32 or None, stats dict)."""
+        fn = {"raycast": lib().lmcu_render_raycast, "ao": lib().lmcu_render_ao, "pt": lib().lmcu_render_pt}[renderer]
+        film = np.empty((params.height, params.width, 3), dtype=np.float32) if download else None
+        st = abi.LmcuRenderStats()
+        _check(fn(self._h, C.byref(params), film.ctypes.data_as(C.c_void_p) if download else None, C.byref(st)))
+        self.last_stats = st
+        return film, {"elapsed": st.elapsed, "processed": st.processed, "paths": st.paths, "rays": st.rays,
+                      "kernel_launches": st.kernel_launches}
+
+    def film_device(self):
+        p, n = C.c_void_p(), C.c_int64()
+        _check(lib().lmcu_film_device_ptr(self._h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def film_rescale(self, s):
+        _check(lib().lmcu_film_rescale(self._h, C.c_double(s)))
+
+    def film_download(self, width, height):
+        film = np.empty((height, width, 3), dtype=np.float32)
+        _check(lib().lmcu_film_download(self._h, film.ctypes.data_as(C.c_void_p)))
+        return film
+
+    def close(self):
+        if self._h:
+            lib().lmcu_scene_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

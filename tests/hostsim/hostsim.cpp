@@ -1,0 +1,252 @@
+// tests/hostsim/hostsim.cpp — DEBUGGING AID, NOT A PRODUCT PATH.
+//
+// The build container has no GPU.  To find logic errors before spending GPU minutes, this file
+// compiles the per-item bodies of the CUDA kernels (lightmetrica-v3_b200/csrc/*.cuh, all plain
+// `inline` functions when __CUDACC__ is undefined) with g++ and drives them with sequential loops
+// that stand in for the kernel grids (std::sort stands in for the CUB radix sort).  It is built
+// only by tests/test_hostsim.py into tests/hostsim/_build/, is never loaded by lmcu/, bench.py
+// or the plugin, and liblmcu.so contains none of it: the product has no CPU fallback.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../lightmetrica-v3_b200/csrc/prep.hpp"
+
+using namespace lmcu;
+
+namespace {
+
+struct SimScene {
+    PreparedScene ps;
+    std::vector<double> mesh_p, mesh_n;
+    std::vector<WideNode> nodes;
+    std::vector<TriF32> t32;
+    std::vector<TriF64> t64;
+    std::vector<TriShade> shade;
+    bool fp32 = false;
+    DevScene dev() const {
+        DevScene d{};
+        d.nodes = nodes.data(); d.t32 = fp32 ? t32.data() : nullptr; d.t64 = fp32 ? nullptr : t64.data();
+        d.shade = shade.data(); d.prims = ps.prims.data(); d.mats = ps.mats.data(); d.lights = ps.lights.data();
+        d.emit = ps.emit.data(); d.cdf = ps.cdf.data(); d.env_tex = nullptr;
+        d.num_prims = (int)ps.prims.size(); d.num_lights = (int)ps.lights.size(); d.env_light = ps.env_light;
+        d.num_tris = ps.nt; d.cam = ps.cam;
+        return d;
+    }
+};
+
+std::string g_err;
+
+}
+
+template <typename TriT>
+static int intersect_t(const SimScene& s, const LmcuRay* rays, long long n, LmcuHit* hits, double* npr, double* tpr) {
+    const DevScene d = s.dev();
+    uint2 stack[kStackSize];
+    unsigned long long cn = 0, ct = 0;
+    int overflow = 0;
+    for (long long i = 0; i < n; i++) {
+        RayD r;
+        r.o = d3(rays[i].o[0], rays[i].o[1], rays[i].o[2]); r.d = d3(rays[i].d[0], rays[i].d[1], rays[i].d[2]);
+        r.tmin = rays[i].tmin; r.tmax = rays[i].tmax;
+        HitD h; h.t = r.tmax; h.u = h.v = 0; h.tri = -1;
+        TraverseCounters tc; tc.nodes = tc.tris = 0;
+        if (!traverse<false, true, TriT>(d.nodes, scene_tris<TriT>(d), r, h, stack, &tc)) overflow = 1;
+        cn += tc.nodes; ct += tc.tris;
+        int32_t prim = -1, face = -1;
+        if (h.tri >= 0) {
+            F3 p1, p2, p3; int32_t pi;
+            tri_fetch(d, (uint32_t)h.tri, p1, p2, p3, pi, face);
+            prim = d.prims[pi].node_index;
+        }
+        hits[i] = LmcuHit{ h.t, h.u, h.v, prim, face };
+    }
+    if (npr) *npr = (double)cn / (double)n;
+    if (tpr) *tpr = (double)ct / (double)n;
+    return overflow;
+}
+
+
+extern "C" {
+
+const char* hostsim_last_error() { return g_err.c_str(); }
+
+int hostsim_scene_create(const LmcuSceneDesc* d, int max_leaf, void** out, long long* num_nodes) {
+    auto* s = new SimScene;
+    const int rc = prepare_scene(d, s->ps, g_err);
+    if (rc) { delete s; return rc; }
+    const uint32_t nt = s->ps.nt;
+    const size_t total_faces = s->ps.face_offset.back();
+    s->mesh_p.assign(total_faces * 9, 0.0);
+    s->mesh_n.assign(total_faces * 9, 0.0);
+    for (int i = 0; i < d->num_meshes; i++) {
+        const size_t cnt = (size_t)d->meshes[i].num_faces * 9;
+        memcpy(s->mesh_p.data() + (size_t)s->ps.face_offset[i] * 9, d->meshes[i].p, cnt * sizeof(double));
+        if (d->meshes[i].n) memcpy(s->mesh_n.data() + (size_t)s->ps.face_offset[i] * 9, d->meshes[i].n, cnt * sizeof(double));
+    }
+    // k_flatten
+    std::vector<double> wp((size_t)nt * 9), centre((size_t)nt * 3);
+    std::vector<float> tri_lo((size_t)nt * 3), tri_hi((size_t)nt * 3);
+    bool exact = true;
+    float slo[3] = { 3e38f, 3e38f, 3e38f }, shi[3] = { -3e38f, -3e38f, -3e38f };
+    for (uint32_t g = 0; g < nt; g++) {
+        exact = flatten_body(g, s->ps.prims.data(), (int)s->ps.prims.size(), s->mesh_p.data(), wp.data(), tri_lo.data(),
+                             tri_hi.data(), centre.data()) && exact;
+        for (int a = 0; a < 3; a++) { slo[a] = fminf(slo[a], tri_lo[(size_t)g * 3 + a]); shi[a] = fmaxf(shi[a], tri_hi[(size_t)g * 3 + a]); }
+    }
+    // k_morton + sort
+    const double dlo[3] = { slo[0], slo[1], slo[2] }, dhi[3] = { shi[0], shi[1], shi[2] };
+    std::vector<uint64_t> keys(nt);
+    std::vector<uint32_t> vals(nt);
+    for (uint32_t g = 0; g < nt; g++) { keys[g] = morton_body(centre.data(), g, dlo, dhi); vals[g] = g; }
+    std::vector<uint32_t> order(nt);
+    std::iota(order.begin(), order.end(), 0u);
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return keys[a] < keys[b]; });
+    std::vector<uint64_t> keys_sorted(nt);
+    std::vector<uint32_t> vals_sorted(nt);
+    for (uint32_t i = 0; i < nt; i++) { keys_sorted[i] = keys[order[i]]; vals_sorted[i] = vals[order[i]]; }
+    // k_hierarchy
+    std::vector<BinNode> bin((size_t)2 * nt);
+    std::vector<uint32_t> parent((size_t)2 * nt, 0xffffffffu), arrive(nt, 0);
+    for (int i = 0; i + 1 < (int)nt; i++) hierarchy_body(i, keys_sorted.data(), (int)nt, bin.data(), parent.data());
+    // k_fit (sequential stand-in for the atomic-arrival climb)
+    for (int j = 0; j < (int)nt; j++) {
+        const uint32_t g = vals_sorted[j];
+        BinNode leaf;
+        for (int a = 0; a < 3; a++) { leaf.lo[a] = tri_lo[(size_t)g * 3 + a]; leaf.hi[a] = tri_hi[(size_t)g * 3 + a]; }
+        leaf.left = leaf.right = 0xffffffffu; leaf.first = (uint32_t)j; leaf.count = 1;
+        const uint32_t id = (uint32_t)(nt - 1 + j);
+        bin[id] = leaf;
+        if (nt == 1) break;
+        uint32_t cur = parent[id];
+        while (true) {
+            if (arrive[cur]++ == 0) break;
+            BinNode& nd = bin[cur];
+            for (int a = 0; a < 3; a++) {
+                nd.lo[a] = fminf(bin[nd.left].lo[a], bin[nd.right].lo[a]);
+                nd.hi[a] = fmaxf(bin[nd.left].hi[a], bin[nd.right].hi[a]);
+            }
+            if (cur == 0) break;
+            cur = parent[cur];
+        }
+    }
+    // k_collapse, level by level
+    std::vector<WideNode> wide(nt);
+    std::vector<uint32_t> tri_order(nt);
+    std::vector<CollapseItem> queue[2];
+    queue[0].resize(nt); queue[1].resize(nt);
+    uint32_t counters[3] = { 1u, 0u, 0u };
+    queue[0][0] = CollapseItem{ 0u, 0u };
+    uint32_t count = 1;
+    int cur = 0;
+    while (count > 0) {
+        CollapseCtx c;
+        c.bin = bin.data(); c.sorted_tri = vals_sorted.data(); c.n = (int)nt; c.max_leaf = max_leaf; c.wide = wide.data();
+        c.tri_order = tri_order.data(); c.node_counter = &counters[0]; c.tri_counter = &counters[1];
+        c.next_queue = queue[cur ^ 1].data(); c.next_count = &counters[2];
+        for (uint32_t i = 0; i < count; i++) collapse_body(c, queue[cur][i]);
+        count = counters[2];
+        counters[2] = 0;
+        cur ^= 1;
+    }
+    if (counters[1] != nt) { g_err = "collapse lost triangles"; delete s; return 3; }
+    wide.resize(counters[0]);
+    s->nodes = wide;
+    s->fp32 = exact;
+    if (exact) s->t32.resize(nt); else s->t64.resize(nt);
+    s->shade.resize(nt);
+    for (uint32_t k = 0; k < nt; k++) {
+        emit_body(k, tri_order.data(), s->ps.prims.data(), (int)s->ps.prims.size(), wp.data(), s->mesh_p.data(), s->mesh_n.data(),
+                  exact ? s->t32.data() : nullptr, exact ? nullptr : s->t64.data(), s->shade.data());
+    }
+    if (num_nodes) *num_nodes = (long long)s->nodes.size();
+    *out = s;
+    return 0;
+}
+
+void hostsim_scene_destroy(void* p) { delete static_cast<SimScene*>(p); }
+
+int hostsim_fp32(void* p) { return static_cast<SimScene*>(p)->fp32 ? 1 : 0; }
+
+int hostsim_intersect(void* p, const LmcuRay* rays, long long n, LmcuHit* hits, double* npr, double* tpr) {
+    const SimScene& s = *static_cast<SimScene*>(p);
+    return s.fp32 ? intersect_t<TriF32>(s, rays, n, hits, npr, tpr) : intersect_t<TriF64>(s, rays, n, hits, npr, tpr);
+}
+
+int hostsim_raycast(void* p, const LmcuRenderParams* rp_, float* film) {
+    const SimScene& s = *static_cast<SimScene*>(p);
+    const DevScene d = s.dev();
+    RaycastParams rp{};
+    rp.width = rp_->width; rp.height = rp_->height;
+    rp.use_constant_color = rp_->use_constant_color; rp.visualize_normal = rp_->visualize_normal; rp.has_color = rp_->has_color;
+    for (int k = 0; k < 3; k++) { rp.bg[k] = (float)rp_->bg_color[k]; rp.color[k] = (float)rp_->color[k]; }
+    uint2 stack[kStackSize];
+    for (int y = 0; y < rp.height; y++) {
+        for (int x = 0; x < rp.width; x++) {
+            if (s.fp32) raycast_pixel<TriF32>(d, rp, x, y, film, stack); else raycast_pixel<TriF64>(d, rp, x, y, film, stack);
+        }
+    }
+    return 0;
+}
+
+int hostsim_ao(void* p, const LmcuRenderParams* rp, float* film) {
+    const SimScene& s = *static_cast<SimScene*>(p);
+    const DevScene d = s.dev();
+    uint2 stack[kStackSize];
+    uint32_t rays = 0;
+    memset(film, 0, sizeof(float) * 3 * rp->width * rp->height);
+    for (int y = 0; y < rp->height; y++) {
+        for (int x = 0; x < rp->width; x++) {
+            if (s.fp32) ao_pixel<TriF32>(d, rp->width, rp->height, x, y, rp->spp, rp->sample_offset, rp->seed, rp->ao_distance, film, stack, &rays);
+            else ao_pixel<TriF64>(d, rp->width, rp->height, x, y, rp->spp, rp->sample_offset, rp->seed, rp->ao_distance, film, stack, &rays);
+        }
+    }
+    return 0;
+}
+
+// One path at a time through the wavefront stage bodies (generate -> extend -> shade -> shadow).
+int hostsim_pt(void* p, const LmcuRenderParams* rp, float* film, long long* rays_out) {
+    const SimScene& s = *static_cast<SimScene*>(p);
+    const DevScene d = s.dev();
+    PtParams pp{};
+    pp.width = rp->width; pp.height = rp->height; pp.max_verts = rp->max_verts; pp.sampling_mode = rp->sampling_mode;
+    pp.seed = rp->seed; pp.tiled = (rp->width % 8 == 0 && rp->height % 4 == 0) ? 1u : 0u;
+    pp.sample_offset = (uint64_t)rp->sample_offset;
+    pp.total_paths = (uint64_t)rp->width * rp->height * (uint64_t)rp->spp;
+    pp.capacity = 1;
+    const size_t npix = (size_t)rp->width * rp->height;
+    std::vector<double> acc(npix * 3, 0.0);
+    float4 ro, rd, tp, aux; uint2 info;
+    PathQueue q; q.ray_o = &ro; q.ray_d = &rd; q.thr_pix = &tp; q.aux = &aux; q.info = &info;
+    uint2 stack[kStackSize];
+    long long rays = 0;
+    for (uint64_t g = 0; g < pp.total_paths; g++) {
+        pt_generate_body(d, pp, g, q, 0);
+        while (true) {
+            HitD h;
+            if (s.fp32) pt_trace<false, TriF32>(d, ro, rd, h, stack); else pt_trace<false, TriF64>(d, ro, rd, h, stack);
+            rays++;
+            const float4 hit = make_float4((float)h.t, (float)h.u, (float)h.v, u2f((uint32_t)h.tri));
+            const ShadeOut o = pt_shade_body(d, pp, ro, rd, tp, aux, info, hit);
+            const uint32_t pixel = f2u(tp.w);
+            acc[pixel * 3 + 0] += o.emit.x; acc[pixel * 3 + 1] += o.emit.y; acc[pixel * 3 + 2] += o.emit.z;
+            if (o.shadow) {
+                HitD hs;
+                if (s.fp32) pt_trace<true, TriF32>(d, o.sh_o, o.sh_d, hs, stack); else pt_trace<true, TriF64>(d, o.sh_o, o.sh_d, hs, stack);
+                rays++;
+                if (hs.tri < 0) { acc[pixel * 3 + 0] += o.sh_c.x; acc[pixel * 3 + 1] += o.sh_c.y; acc[pixel * 3 + 2] += o.sh_c.z; }
+            }
+            if (!o.alive) break;
+            ro = o.o; rd = o.d; tp = o.thr_pix; aux = o.aux; info = o.info;
+        }
+    }
+    const double sc = rp->rescale ? 1.0 / (double)rp->spp : 1.0;
+    for (size_t i = 0; i < npix * 3; i++) film[i] = (float)(acc[i] * sc);
+    if (rays_out) *rays_out = rays;
+    return 0;
+}
+
+}
