@@ -142,7 +142,7 @@ typedef struct LmcuRenderParams {
     int32_t use_constant_color;              /* raycast */
     int32_t visualize_normal;                /* raycast */
     int32_t has_color;                       /* raycast: `color` override present */
-    int32_t pad_;
+    int32_t count_traversal;                 /* pt: 1 = run the counters variant of extend/shadow (slower) */
     double bg_color[3];                      /* raycast */
     double color[3];                         /* raycast */
     double ao_distance;                      /* ao: occlusion ray tmax (0.2 in the reference) */
@@ -156,6 +156,14 @@ typedef struct LmcuRenderStats {
     int64_t kernel_launches;                 /* kernels launched by this call */
     double bvh_nodes_per_ray;                /* mean wide nodes fetched per ray (counters build only, else 0) */
     double bvh_tris_per_ray;                 /* mean triangles fetched per ray (counters build only, else 0) */
+    double shadow_nodes_per_ray;             /* same for the shadow (any-hit) rays */
+    double shadow_tris_per_ray;
+    double extend_seconds;                   /* pt: summed device time of the extend launches (CUDA events) */
+    double shade_seconds;                    /* pt: ... of the shade launches */
+    double shadow_seconds;                   /* pt: ... of the shadow launches */
+    int64_t extend_launches;                 /* pt: number of extend launches (= wavefront iterations) */
+    int64_t extend_rays;                     /* pt: closest-hit queries */
+    int64_t shadow_rays;                     /* pt: shadow queries */
 } LmcuRenderStats;
 
 typedef struct LmcuBuildOptions {
@@ -184,6 +192,9 @@ const char* lmcu_version(void);
 /* -- scene + accel: replaces lm::Accel::build / intersect (include/lm/accel.h:38,70) ---------- */
 int lmcu_scene_create(int device, LmcuScene** out);
 void lmcu_scene_destroy(LmcuScene* scene);
+/* Run all later work of this scene on `stream` (a cudaStream_t of the caller, e.g. torch's current
+ * stream; NULL restores the scene's own stream). */
+int lmcu_scene_set_stream(LmcuScene* scene, void* stream);
 /* Upload + flatten (accel_sahbvh.cpp:132-151: world p = M * (p,1) in FP64, glm operation order). */
 int lmcu_scene_upload(LmcuScene* scene, const LmcuSceneDesc* desc);
 /* Build the wide BVH (replaces accel_sahbvh.cpp:156-266). */

@@ -167,6 +167,8 @@ struct PtCounters {
     unsigned long long next_path;
     unsigned long long rays;
     unsigned long long iterations;
+    unsigned long long extend_rays, shadow_rays;
+    unsigned long long nodes_extend, tris_extend, nodes_shadow, tris_shadow;   // counters build only
 };
 
 LMCU_HD void path_pixel(const PtParams& p, uint64_t g, uint32_t& pixel, uint32_t& sample, int& x, int& y) {
@@ -203,13 +205,13 @@ LMCU_HD void pt_generate_body(const DevScene& s, const PtParams& p, uint64_t g, 
     q.info[slot] = make_uint2(sample, 1u);   // num_verts = 1, prev_nee = 0
 }
 
-template <bool ANY, typename TriT>
-LMCU_HD bool pt_trace(const DevScene& s, float4 o, float4 d, HitD& h, uint2* stack) {
+template <bool ANY, bool COUNT, typename TriT>
+LMCU_HD bool pt_trace(const DevScene& s, float4 o, float4 d, HitD& h, uint2* stack, TraverseCounters* tc) {
     RayD r;
     r.o = d3(o.x, o.y, o.z); r.d = d3(d.x, d.y, d.z);
     r.tmin = o.w; r.tmax = d.w;
     h.t = r.tmax; h.tri = -1; h.u = h.v = 0;
-    return traverse<ANY, false, TriT>(s.nodes, scene_tris<TriT>(s), r, h, stack, nullptr);
+    return traverse<ANY, COUNT, TriT>(s.nodes, scene_tris<TriT>(s), r, h, stack, tc);
 }
 
 struct ShadeOut {

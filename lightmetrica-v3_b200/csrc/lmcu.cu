@@ -253,13 +253,15 @@ __global__ void k_pt_advance(PtParams p, PtCounters* ctr, int cur) {
     ctr->fetch_extend = 0;
     ctr->fetch_shadow = 0;
     ctr->rays += m + n_new;
+    ctr->extend_rays += m + n_new;
     ctr->iterations += 1;
 }
 
-template <typename TriT>
+template <typename TriT, bool COUNT>
 __global__ void __launch_bounds__(128) k_pt_extend(DevScene s, PathQueue q, float4* hits, PtCounters* ctr, int cur) {
     uint2 stack[kStackSize];
     const uint32_t n = ctr->count[cur];
+    TraverseCounters tc; tc.nodes = tc.tris = 0;
     while (true) {
         uint32_t base = 0;
         if ((threadIdx.x & 31) == 0) base = atomicAdd(&ctr->fetch_extend, 32u);
@@ -268,9 +270,10 @@ __global__ void __launch_bounds__(128) k_pt_extend(DevScene s, PathQueue q, floa
         const uint32_t i = base + (threadIdx.x & 31);
         if (i >= n) continue;
         HitD h;
-        if (!pt_trace<false, TriT>(s, q.ray_o[i], q.ray_d[i], h, stack)) atomicExch(&ctr->overflow, 1u);
+        if (!pt_trace<false, COUNT, TriT>(s, q.ray_o[i], q.ray_d[i], h, stack, &tc)) atomicExch(&ctr->overflow, 1u);
         hits[i] = make_float4((float)h.t, (float)h.u, (float)h.v, __int_as_float(h.tri));
     }
+    if (COUNT) { atomicAdd(&ctr->nodes_extend, (unsigned long long)tc.nodes); atomicAdd(&ctr->tris_extend, (unsigned long long)tc.tris); }
 }
 
 // Block-wide compaction: returns the queue position for threads with `pred`, using warp ballots,
@@ -326,11 +329,12 @@ __global__ void __launch_bounds__(256) k_pt_shade(DevScene s, PtParams p, PathQu
     }
 }
 
-template <typename TriT>
+template <typename TriT, bool COUNT>
 __global__ void __launch_bounds__(128) k_pt_shadow(DevScene s, ShadowQueue sq, float* film, PtCounters* ctr) {
     uint2 stack[kStackSize];
     const uint32_t n = ctr->shadow_count;
-    if (blockIdx.x == 0 && threadIdx.x == 0) ctr->rays += n;
+    TraverseCounters tc; tc.nodes = tc.tris = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { ctr->rays += n; ctr->shadow_rays += n; }
     while (true) {
         uint32_t base = 0;
         if ((threadIdx.x & 31) == 0) base = atomicAdd(&ctr->fetch_shadow, 32u);
@@ -339,13 +343,14 @@ __global__ void __launch_bounds__(128) k_pt_shadow(DevScene s, ShadowQueue sq, f
         const uint32_t i = base + (threadIdx.x & 31);
         if (i >= n) continue;
         HitD h;
-        if (!pt_trace<true, TriT>(s, sq.ray_o[i], sq.ray_d[i], h, stack)) atomicExch(&ctr->overflow, 1u);
+        if (!pt_trace<true, COUNT, TriT>(s, sq.ray_o[i], sq.ray_d[i], h, stack, &tc)) atomicExch(&ctr->overflow, 1u);
         if (h.tri < 0) {                                     // visible (include/lm/scene.h:343-364)
             const float4 c = sq.contrib[i];
             float* px = film + (size_t)__float_as_uint(c.w) * 3;
             atomicAdd(px + 0, c.x); atomicAdd(px + 1, c.y); atomicAdd(px + 2, c.z);
         }
     }
+    if (COUNT) { atomicAdd(&ctr->nodes_shadow, (unsigned long long)tc.nodes); atomicAdd(&ctr->tris_shadow, (unsigned long long)tc.tris); }
 }
 
 __global__ void k_scale(float* film, size_t n, float s) {
@@ -376,6 +381,8 @@ struct LmcuScene {
     int device = 0;
     int num_sms = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;
+    std::vector<cudaEvent_t> ring;          // per-kernel timing events of the pt loop
     // description (device)
     DBuf<double> mesh_p, mesh_n;
     DBuf<PrimDev> prims;
@@ -439,7 +446,8 @@ int lmcu_scene_create(int device, LmcuScene** out) {
     LmcuScene* s = new LmcuScene;
     s->device = device;
     CU(cudaDeviceGetAttribute(&s->num_sms, cudaDevAttrMultiProcessorCount, device));
-    CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking));
+    s->stream = s->own_stream;
     CU(cudaEventCreate(&s->ev0));
     CU(cudaEventCreate(&s->ev1));
     CU(s->cursor.alloc(8));
@@ -456,8 +464,15 @@ void lmcu_scene_destroy(LmcuScene* s) {
     cudaDeviceSynchronize();
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
-    if (s->stream) cudaStreamDestroy(s->stream);
+    for (cudaEvent_t e : s->ring) cudaEventDestroy(e);
+    if (s->own_stream) cudaStreamDestroy(s->own_stream);
     delete s;
+}
+
+int lmcu_scene_set_stream(LmcuScene* s, void* stream) {
+    if (!s) return fail(LMCU_ERR_INVALID_ARGUMENT, "null scene");
+    s->stream = stream ? (cudaStream_t)stream : s->own_stream;
+    return LMCU_OK;
 }
 
 // -- upload -----------------------------------------------------------------------------------------
@@ -827,21 +842,51 @@ int lmcu_render_pt(LmcuScene* s, const LmcuRenderParams* p, float* film_rgb, Lmc
     int cur = 0;
     int64_t launches = 0;
     PtCounters h{};
+    const bool count = p->count_traversal != 0;
+    const int kGroup = 4;                       // iterations between host checks
+    if (s->ring.empty()) {
+        s->ring.resize(kGroup * 4);
+        for (auto& e : s->ring) CU(cudaEventCreate(&e));
+    }
+    double t_extend = 0, t_shade = 0, t_shadow = 0;
+    int64_t extend_launches = 0;
     while (true) {
-        for (int it = 0; it < 4; it++) {
+        for (int it = 0; it < kGroup; it++) {
+            cudaEvent_t* ev = &s->ring[it * 4];
             k_pt_generate<<<gen_blocks, 256, 0, st>>>(d, pp, q[cur], s->pt_ctr.p, cur);
             k_pt_advance<<<1, 1, 0, st>>>(pp, s->pt_ctr.p, cur);
-            if (s->fp32) k_pt_extend<TriF32><<<trav_blocks, 128, 0, st>>>(d, q[cur], s->hits.p, s->pt_ctr.p, cur);
-            else k_pt_extend<TriF64><<<trav_blocks, 128, 0, st>>>(d, q[cur], s->hits.p, s->pt_ctr.p, cur);
+            cudaEventRecord(ev[0], st);
+            if (s->fp32) {
+                if (count) k_pt_extend<TriF32, true><<<trav_blocks, 128, 0, st>>>(d, q[cur], s->hits.p, s->pt_ctr.p, cur);
+                else k_pt_extend<TriF32, false><<<trav_blocks, 128, 0, st>>>(d, q[cur], s->hits.p, s->pt_ctr.p, cur);
+            } else {
+                if (count) k_pt_extend<TriF64, true><<<trav_blocks, 128, 0, st>>>(d, q[cur], s->hits.p, s->pt_ctr.p, cur);
+                else k_pt_extend<TriF64, false><<<trav_blocks, 128, 0, st>>>(d, q[cur], s->hits.p, s->pt_ctr.p, cur);
+            }
+            cudaEventRecord(ev[1], st);
             k_pt_shade<<<shade_blocks, 256, 0, st>>>(d, pp, q[cur], q[cur ^ 1], sq, s->hits.p, s->film.p, s->pt_ctr.p, cur);
-            if (s->fp32) k_pt_shadow<TriF32><<<trav_blocks, 128, 0, st>>>(d, sq, s->film.p, s->pt_ctr.p);
-            else k_pt_shadow<TriF64><<<trav_blocks, 128, 0, st>>>(d, sq, s->film.p, s->pt_ctr.p);
+            cudaEventRecord(ev[2], st);
+            if (s->fp32) {
+                if (count) k_pt_shadow<TriF32, true><<<trav_blocks, 128, 0, st>>>(d, sq, s->film.p, s->pt_ctr.p);
+                else k_pt_shadow<TriF32, false><<<trav_blocks, 128, 0, st>>>(d, sq, s->film.p, s->pt_ctr.p);
+            } else {
+                if (count) k_pt_shadow<TriF64, true><<<trav_blocks, 128, 0, st>>>(d, sq, s->film.p, s->pt_ctr.p);
+                else k_pt_shadow<TriF64, false><<<trav_blocks, 128, 0, st>>>(d, sq, s->film.p, s->pt_ctr.p);
+            }
+            cudaEventRecord(ev[3], st);
             cur ^= 1;
             launches += 5;
+            extend_launches++;
         }
         CU(cudaGetLastError());
         CU(cudaMemcpyAsync(&h, s->pt_ctr.p, sizeof(h), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
+        for (int it = 0; it < kGroup; it++) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, s->ring[it * 4 + 0], s->ring[it * 4 + 1]); t_extend += ms * 1e-3;
+            cudaEventElapsedTime(&ms, s->ring[it * 4 + 1], s->ring[it * 4 + 2]); t_shade += ms * 1e-3;
+            cudaEventElapsedTime(&ms, s->ring[it * 4 + 2], s->ring[it * 4 + 3]); t_shadow += ms * 1e-3;
+        }
         if (h.overflow) return fail(LMCU_ERR_CUDA, "bvh traversal stack overflow");
         if (h.next_path >= pp.total_paths && h.count[cur] == 0) break;
     }
@@ -858,6 +903,15 @@ int lmcu_render_pt(LmcuScene* s, const LmcuRenderParams* p, float* film_rgb, Lmc
         memset(stats, 0, sizeof(*stats));
         stats->elapsed = ms * 1e-3; stats->processed = p->spp; stats->paths = (int64_t)pp.total_paths;
         stats->rays = (int64_t)h.rays; stats->kernel_launches = launches;
+        stats->extend_seconds = t_extend; stats->shade_seconds = t_shade; stats->shadow_seconds = t_shadow;
+        stats->extend_launches = extend_launches;
+        stats->extend_rays = (int64_t)h.extend_rays; stats->shadow_rays = (int64_t)h.shadow_rays;
+        if (count && h.extend_rays) {
+            stats->bvh_nodes_per_ray = (double)h.nodes_extend / (double)h.extend_rays;
+            stats->bvh_tris_per_ray = (double)h.tris_extend / (double)h.extend_rays;
+            stats->shadow_nodes_per_ray = h.shadow_rays ? (double)h.nodes_shadow / (double)h.shadow_rays : 0.0;
+            stats->shadow_tris_per_ray = h.shadow_rays ? (double)h.tris_shadow / (double)h.shadow_rays : 0.0;
+        }
     }
     return LMCU_OK;
 }

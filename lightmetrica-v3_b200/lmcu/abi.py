@@ -60,14 +60,17 @@ class LmcuRenderParams(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("max_verts", C.c_int32),
                 ("sampling_mode", C.c_int32), ("spp", C.c_int64), ("sample_offset", C.c_int64),
                 ("seed", C.c_uint32), ("rescale", C.c_int32), ("use_constant_color", C.c_int32),
-                ("visualize_normal", C.c_int32), ("has_color", C.c_int32), ("pad_", C.c_int32),
+                ("visualize_normal", C.c_int32), ("has_color", C.c_int32), ("count_traversal", C.c_int32),
                 ("bg_color", c_double3), ("color", c_double3), ("ao_distance", C.c_double)]
 
 
 class LmcuRenderStats(C.Structure):
     _fields_ = [("elapsed", C.c_double), ("processed", C.c_int64), ("paths", C.c_int64),
                 ("rays", C.c_int64), ("kernel_launches", C.c_int64),
-                ("bvh_nodes_per_ray", C.c_double), ("bvh_tris_per_ray", C.c_double)]
+                ("bvh_nodes_per_ray", C.c_double), ("bvh_tris_per_ray", C.c_double),
+                ("shadow_nodes_per_ray", C.c_double), ("shadow_tris_per_ray", C.c_double),
+                ("extend_seconds", C.c_double), ("shade_seconds", C.c_double), ("shadow_seconds", C.c_double),
+                ("extend_launches", C.c_int64), ("extend_rays", C.c_int64), ("shadow_rays", C.c_int64)]
 
 
 class LmcuBuildOptions(C.Structure):
@@ -82,7 +85,7 @@ class LmcuBuildStats(C.Structure):
 
 def render_params(width, height, spp=1, max_verts=20, seed=42, sampling_mode=SAMPLING_MIS,
                   sample_offset=0, rescale=1, bg_color=(0, 0, 0), use_constant_color=False,
-                  visualize_normal=False, color=None, ao_distance=0.2):
+                  visualize_normal=False, color=None, ao_distance=0.2, count_traversal=False):
     """Defaults follow the reference renderers' JSON defaults (renderer_pt.cpp:51-77,
     renderer_raycast.cpp:48-60, functest/renderer_ao.cpp:36-40)."""
     p = LmcuRenderParams()
@@ -93,4 +96,5 @@ def render_params(width, height, spp=1, max_verts=20, seed=42, sampling_mode=SAM
     p.bg_color = c_double3(*bg_color)
     p.color = c_double3(*(color if color is not None else (0, 0, 0)))
     p.ao_distance = ao_distance
+    p.count_traversal = int(count_traversal)
     return p

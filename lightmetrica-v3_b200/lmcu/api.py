@@ -20,7 +20,7 @@ _LIB = None
 
 EXPORTS = [
     "lmcu_last_error", "lmcu_device_count", "lmcu_version", "lmcu_scene_create", "lmcu_scene_destroy",
-    "lmcu_scene_upload", "lmcu_accel_build", "lmcu_accel_intersect", "lmcu_accel_intersect_device",
+    "lmcu_scene_set_stream", "lmcu_scene_upload", "lmcu_accel_build", "lmcu_accel_intersect", "lmcu_accel_intersect_device",
     "lmcu_accel_intersect_counted", "lmcu_render_raycast", "lmcu_render_ao", "lmcu_render_pt",
     "lmcu_film_device_ptr", "lmcu_film_rescale", "lmcu_film_download",
 ]
@@ -96,8 +96,11 @@ class Scene:
         st = abi.LmcuRenderStats()
         _check(fn(self._h, C.byref(params), film.ctypes.data_as(C.c_void_p) if download else None, C.byref(st)))
         self.last_stats = st
-        return film, {"elapsed": st.elapsed, "processed": st.processed, "paths": st.paths, "rays": st.rays,
-                      "kernel_launches": st.kernel_launches}
+        return film, {f: getattr(st, f) for f, _ in abi.LmcuRenderStats._fields_}
+
+    def set_stream(self, stream_ptr):
+        """Run this scene's kernels on the caller's CUDA stream (e.g. torch.cuda.current_stream().cuda_stream)."""
+        _check(lib().lmcu_scene_set_stream(self._h, C.c_void_p(stream_ptr)))
 
     def film_device(self):
         p, n = C.c_void_p(), C.c_int64()

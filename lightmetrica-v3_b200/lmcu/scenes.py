@@ -338,19 +338,27 @@ def instanced_spheres(grid=10, num_theta=112, seed=3, env=None):
 # ------------------------------------------------------------------------------------------------
 def camera_rays(camera, width, height):
     """Pixel-centre primary rays, the arithmetic of camera_pinhole.cpp:90-95,128-132."""
+    import math
+
+    def dot3(a, b):     # glm::dot: (x*x' + y*y') + z*z'
+        return (a[..., 0] * b[..., 0] + a[..., 1] * b[..., 1]) + a[..., 2] * b[..., 2]
+
+    def cross3(x, y):   # glm::cross
+        return np.stack([x[1] * y[2] - y[1] * x[2], x[2] * y[0] - y[2] * x[0], x[0] * y[1] - y[0] * x[1]])
+
     pos, center, up = (np.asarray(camera[k], dtype=np.float64) for k in ("position", "center", "up"))
     w = pos - center
-    w /= np.sqrt(np.dot(w, w))
-    u = np.cross(up, w)
-    u /= np.sqrt(np.dot(u, u))
-    v = np.cross(w, u)
-    tf = np.tan(camera["vfov"] * np.pi / 180 * .5)
+    w = w * (1.0 / np.sqrt(dot3(w, w)))          # glm::normalize = v * inversesqrt(dot(v, v))
+    u = cross3(up, w)
+    u = u * (1.0 / np.sqrt(dot3(u, u)))
+    v = cross3(w, u)
+    tf = math.tan(camera["vfov"] * math.pi / 180 * .5)
     x = (np.arange(width) + .5) / width
     y = (np.arange(height) + .5) / height
     rx, ry = np.meshgrid(2 * x - 1, 2 * y - 1, indexing="xy")
     d = np.stack([camera["aspect"] * tf * rx, tf * ry, -np.ones_like(rx)], -1)
-    d /= np.sqrt((d * d).sum(-1, keepdims=True))
-    dirs = d[..., 0:1] * u + d[..., 1:2] * v + d[..., 2:3] * w
+    d = d * (1.0 / np.sqrt(dot3(d, d)))[..., None]
+    dirs = (d[..., 0:1] * u + d[..., 1:2] * v) + d[..., 2:3] * w
     rays = np.zeros(width * height, dtype=RAY_DTYPE)
     rays["o"] = pos
     rays["d"] = dirs.reshape(-1, 3)

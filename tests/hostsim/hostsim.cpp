@@ -227,7 +227,7 @@ int hostsim_pt(void* p, const LmcuRenderParams* rp, float* film, long long* rays
         pt_generate_body(d, pp, g, q, 0);
         while (true) {
             HitD h;
-            if (s.fp32) pt_trace<false, TriF32>(d, ro, rd, h, stack); else pt_trace<false, TriF64>(d, ro, rd, h, stack);
+            if (s.fp32) pt_trace<false, false, TriF32>(d, ro, rd, h, stack, nullptr); else pt_trace<false, false, TriF64>(d, ro, rd, h, stack, nullptr);
             rays++;
             const float4 hit = make_float4((float)h.t, (float)h.u, (float)h.v, u2f((uint32_t)h.tri));
             const ShadeOut o = pt_shade_body(d, pp, ro, rd, tp, aux, info, hit);
@@ -235,7 +235,7 @@ int hostsim_pt(void* p, const LmcuRenderParams* rp, float* film, long long* rays
             acc[pixel * 3 + 0] += o.emit.x; acc[pixel * 3 + 1] += o.emit.y; acc[pixel * 3 + 2] += o.emit.z;
             if (o.shadow) {
                 HitD hs;
-                if (s.fp32) pt_trace<true, TriF32>(d, o.sh_o, o.sh_d, hs, stack); else pt_trace<true, TriF64>(d, o.sh_o, o.sh_d, hs, stack);
+                if (s.fp32) pt_trace<true, false, TriF32>(d, o.sh_o, o.sh_d, hs, stack, nullptr); else pt_trace<true, false, TriF64>(d, o.sh_o, o.sh_d, hs, stack, nullptr);
                 rays++;
                 if (hs.tri < 0) { acc[pixel * 3 + 0] += o.sh_c.x; acc[pixel * 3 + 1] += o.sh_c.y; acc[pixel * 3 + 2] += o.sh_c.z; }
             }

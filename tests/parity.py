@@ -1,0 +1,66 @@
+"""Shared parity checks (SURVEY.md §8c gates G1-G3)."""
+import numpy as np
+
+
+def rmse(a, b):
+    return float(np.sqrt(np.mean((np.asarray(a, dtype=np.float64) - np.asarray(b, dtype=np.float64)) ** 2)))
+
+
+def classify_hits(ref_hits, hits):
+    """G1 bookkeeping.  Returns dict(mismatch, ties, ref_boundary_miss, other).
+
+    tie                 both hit, t equal to 1e-12 relative (bit-equal in all but coplanar-overlap cases), different
+                        (primitive, face): coincident / shared-edge geometry.  The reference keeps the LAST triangle of
+                        its own traversal order (accel_sahbvh.cpp:286-290), and for coplanar overlapping triangles whose
+                        t differ by an ulp its box test (two roundings) can cull the nearer one
+    ref_boundary_miss   reference misses, we hit exactly ON a triangle edge (a barycentric is 0 or u+v is 1 to
+                        1e-12): the reference's box test (math.h:143-158) rejects a hit lying on a slab boundary
+                        by one ulp although its own triangle test accepts it
+    other               anything else — must be zero
+    """
+    bad = (ref_hits["primitive"] != hits["primitive"]) | (ref_hits["face"] != hits["face"])
+    ties = bad & (ref_hits["primitive"] >= 0) & (hits["primitive"] >= 0) & \
+        (np.abs(ref_hits["t"] - hits["t"]) <= 1e-12 * np.maximum(1.0, np.abs(ref_hits["t"])))
+    edge = np.minimum(np.minimum(hits["u"], hits["v"]), np.abs(1.0 - hits["u"] - hits["v"])) <= 1e-12
+    ref_miss = bad & (ref_hits["primitive"] < 0) & (hits["primitive"] >= 0) & edge
+    other = bad & ~ties & ~ref_miss
+    return {"mismatch": int(bad.sum()), "ties": int(ties.sum()), "ref_boundary_miss": int(ref_miss.sum()),
+            "other": int(other.sum()), "bad_mask": bad}
+
+
+def assert_hit_parity(ref_hits, hits, max_special_frac=2e-4):
+    c = classify_hits(ref_hits, hits)
+    assert c["other"] == 0, "non-tie closest-hit mismatches: %d" % c["other"]
+    assert c["ties"] + c["ref_boundary_miss"] <= max(4, max_special_frac * len(hits)), c
+    same = ~c["bad_mask"] & (ref_hits["primitive"] >= 0)
+    # FP64 leaf test with the reference's operation order: t, u, v are bit-identical, far inside the 1e-5 gate
+    assert (ref_hits["t"][same] == hits["t"][same]).all()
+    assert (ref_hits["u"][same] == hits["u"][same]).all() and (ref_hits["v"][same] == hits["v"][same]).all()
+    miss = (ref_hits["primitive"] < 0) & (hits["primitive"] < 0)
+    assert miss.sum() + same.sum() + c["mismatch"] == len(hits)
+    return c
+
+
+def assert_pt_parity(ref_film, film, spp, rel_mean=0.01, z_frac=2e-3):
+    """G3: statistical image parity at equal spp (the RNG streams differ by design).
+
+    - relative difference of the image means per channel <= rel_mean
+    - 8x8 block means of the difference image, z-scored by the block's own noise: the fraction of |z| > 4 stays
+      <= z_frac (both images are unbiased estimates of the same radiance, so the difference is zero-mean noise;
+      a shading or sampling error shows up as block means far from zero)
+    """
+    ref_film = np.asarray(ref_film, dtype=np.float64)
+    film = np.asarray(film, dtype=np.float64)
+    mr, mg = ref_film.mean(axis=(0, 1)), film.mean(axis=(0, 1))
+    rel = np.abs(mg - mr) / np.maximum(mr, 1e-12)
+    assert (rel <= rel_mean).all(), "image means differ: ref %s ours %s" % (mr, mg)
+    d = (film - ref_film).mean(axis=2)
+    h, w = d.shape
+    hb, wb = h // 8, w // 8
+    blocks = d[:hb * 8, :wb * 8].reshape(hb, 8, wb, 8)
+    bm = blocks.mean(axis=(1, 3))
+    bs = blocks.std(axis=(1, 3)) / np.sqrt(64) + 1e-9
+    z = bm / bs
+    frac = float((np.abs(z) > 4).mean())
+    assert frac <= max(z_frac, 2.0 / z.size), "structured difference: %.4f of 8x8 blocks have |z|>4" % frac
+    return {"rel_mean": rel, "z_frac": frac}

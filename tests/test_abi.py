@@ -1,0 +1,55 @@
+"""The C-ABI library loads and exports every symbol include/lmcu.h declares (no compute without a GPU)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "lmcu.h")).read()
+    return sorted(set(re.findall(r"\b(lmcu_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported():
+    from lmcu import api
+    assert os.path.exists(api.LIB_PATH), "liblmcu.so missing: run __graft_entry__.build()"
+    lib = C.CDLL(api.LIB_PATH)
+    names = _declared()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(lib, n), n
+    assert sorted(api.EXPORTS) == names
+
+
+def test_struct_sizes_match_header():
+    from lmcu import abi
+    assert C.sizeof(abi.LmcuRay) == 64 and C.sizeof(abi.LmcuHit) == 32
+    assert C.sizeof(abi.LmcuPrimitive) == 16 + 128
+    assert C.sizeof(abi.LmcuMaterial) == 8 + 24 + 24
+    assert C.sizeof(abi.LmcuCamera) == 88
+    from lmcu.scenes import HIT_DTYPE, RAY_DTYPE
+    assert RAY_DTYPE.itemsize == 64 and HIT_DTYPE.itemsize == 32
+
+
+def test_no_cpu_fallback_without_device():
+    """Without a CUDA device the product must fail loudly (LMCU_ERR_NO_DEVICE), never compute on the CPU."""
+    import lmcu
+    from lmcu import scenes
+    if lmcu.device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(lmcu.LmcuError) as e:
+        lmcu.Scene(scenes.cornell_box())
+    assert e.value.code == 4
+
+
+def test_product_never_references_the_checkers():
+    pkg = os.path.join(ROOT, "lightmetrica-v3_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".cpp", ".h")):
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "import oracle" not in text and "from oracle" not in text and "lm_oracle" not in text, f
+                assert "liblmref" not in text and "libhostsim" not in text, f

@@ -1,0 +1,233 @@
+"""Parity tests proper: the CUDA path (through the C ABI of liblmcu.so) against
+  (1) the committed golden outputs of the unmodified reference (tests/golden/reference_outputs.npz),
+  (2) the reference itself (oracle/_ref) run side by side on the same seeded inputs, when it travelled,
+  (3) size-independent properties at BASELINE.json's full sizes.
+Gates G1-G3 of SURVEY.md §8c; tolerances are written next to each assert."""
+import os
+
+import numpy as np
+import pytest
+
+import lmcu
+from lmcu import abi, scenes
+from parity import assert_hit_parity, assert_pt_parity, classify_hits, rmse
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_outputs.npz"))
+
+
+def golden_hits(name):
+    h = np.zeros(len(GOLDEN[name + "_t"]), dtype=scenes.HIT_DTYPE)
+    h["t"], h["u"], h["v"] = GOLDEN[name + "_t"], GOLDEN[name + "_u"], GOLDEN[name + "_v"]
+    h["primitive"], h["face"] = GOLDEN[name + "_prim"], GOLDEN[name + "_face"]
+    return h
+
+
+def golden_rays(name, sb):
+    from golden.make_golden import golden_rays as g
+    return g(name, sb)
+
+
+CASES = {
+    "cornell": lambda: scenes.cornell_box(),
+    "cornell_fp64": lambda: scenes.cornell_box(True),
+    "spheres12": lambda: scenes.cornell_spheres(12),
+    "heightfield48": lambda: scenes.heightfield_scene(48),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_g1_closest_hit_vs_golden(name):
+    """(primitive, face) equal to accel::sahbvh for every ray; t,u,v bit-identical (gate: 1e-5 relative)."""
+    sb = CASES[name]()
+    sc = lmcu.Scene(sb)
+    assert bool(sc.build_stats.triangles_fp32) == (name != "cornell_fp64")
+    hits = sc.intersect(golden_rays(name, sb))
+    assert_hit_parity(golden_hits(name), hits, max_special_frac=3e-3)
+    sc.close()
+
+
+def test_g1_full_c1_vs_reference(reference):
+    """C1: all 2 073 600 pixel-centre rays of the 1920x1080 Cornell box."""
+    sb = scenes.cornell_box()
+    sc, rs = lmcu.Scene(sb), reference.RefScene(sb)
+    rays = scenes.camera_rays(sb.camera, 1920, 1080)
+    c = assert_hit_parity(rs.intersect(rays), sc.intersect(rays), max_special_frac=2e-4)
+    print("C1 special cases:", {k: v for k, v in c.items() if k != "bad_mask"})
+    rs.close(); sc.close()
+
+
+def test_g1_asymmetric_camera_has_no_special_cases(reference):
+    """Off the symmetry plane no pixel-centre ray meets a scene edge exactly: zero mismatches of any kind."""
+    sb = scenes.cornell_spheres(32)
+    sb.set_camera(position=(0.13, 1.07, 4.9), center=(0.02, 0.97, 0), up=(0, 1, 0), vfov=31, aspect=16 / 9)
+    sc, rs = lmcu.Scene(sb), reference.RefScene(sb)
+    rays = scenes.camera_rays(sb.camera, 960, 540)
+    c = classify_hits(rs.intersect(rays), sc.intersect(rays))
+    assert c["mismatch"] == 0, c
+    rs.close(); sc.close()
+
+
+def test_g1_incoherent_and_window(reference):
+    sb = scenes.cornell_spheres(32)
+    sc, rs = lmcu.Scene(sb), reference.RefScene(sb)
+    rays = scenes.random_rays(400000, np.array([-1, 0, -1.]), np.array([1, 2, 1.]), seed=5)
+    assert_hit_parity(rs.intersect(rays), sc.intersect(rays))
+    rays["tmin"], rays["tmax"] = 0.25, 0.8
+    hr, hs = rs.intersect(rays), sc.intersect(rays)
+    assert_hit_parity(hr, hs)
+    ok = hs["primitive"] >= 0
+    assert ((hs["t"][ok] >= 0.25) & (hs["t"][ok] <= 0.8)).all()
+    rs.close(); sc.close()
+
+
+def test_g1_tiny_and_ragged_scenes(reference):
+    for nf in (1, 2, 3, 4, 5, 9, 25):
+        sb = scenes.SceneBuilder()
+        rng = np.random.RandomState(nf)
+        tri = scenes._f32(rng.rand(nf, 3, 3) * 2 - 1)
+        sb.add_primitive(sb.add_mesh(tri, scenes.flat_normals(tri)), sb.diffuse((.5, .5, .5)))
+        sb.set_camera(position=(0, 0, 4), center=(0, 0, 0), up=(0, 1, 0), vfov=40, aspect=1)
+        sc, rs = lmcu.Scene(sb), reference.RefScene(sb)
+        rays = scenes.camera_rays(sb.camera, 128, 128)
+        assert_hit_parity(rs.intersect(rays), sc.intersect(rays), max_special_frac=3e-3)
+        rs.close(); sc.close()
+
+
+def test_g1_instanced_transforms(reference):
+    """func_render_instancing pattern: one mesh, many rotated/scaled instances (FP64 triangles)."""
+    sb = scenes.instanced_spheres(grid=3, num_theta=12)
+    sc, rs = lmcu.Scene(sb), reference.RefScene(sb)
+    assert not sc.build_stats.triangles_fp32
+    rays = np.concatenate([scenes.camera_rays(sb.camera, 480, 270),
+                           scenes.random_rays(100000, np.array([-2, 0, -2.]), np.array([2, 3, 2.]))])
+    assert_hit_parity(rs.intersect(rays), sc.intersect(rays))
+    rs.close(); sc.close()
+
+
+def test_empty_batch_and_errors():
+    sb = scenes.cornell_box()
+    sc = lmcu.Scene(sb)
+    assert len(sc.intersect(np.zeros(0, dtype=scenes.RAY_DTYPE))) == 0
+    with pytest.raises(lmcu.LmcuError):
+        sc.render("pt", abi.render_params(64, 64, spp=0))
+    with pytest.raises(lmcu.LmcuError):
+        sc.render("pt", abi.render_params(64, 64, spp=1, max_verts=1))
+    sc.close()
+    empty = scenes.SceneBuilder()
+    with pytest.raises(lmcu.LmcuError) as e:
+        lmcu.Scene(empty)
+    assert e.value.code == 2          # lm::Error::Unsupported, "Missing primitives" (include/lm/scene.h:232-238)
+
+
+@pytest.mark.parametrize("name", ["cornell", "spheres12"])
+def test_g2_raycast_vs_golden(name):
+    """Deterministic rays: image RMSE <= 1e-6 outside tie pixels (FP32 shading noise only)."""
+    sb = CASES[name]()
+    sc = lmcu.Scene(sb)
+    film, _ = sc.render("raycast", abi.render_params(192, 108))
+    hits = sc.intersect(golden_rays(name, sb)[:192 * 108])
+    bad = classify_hits(golden_hits(name)[:192 * 108], hits)["bad_mask"].reshape(108, 192)
+    assert bad.mean() < 3e-3
+    assert rmse(film[~bad], GOLDEN[name + "_raycast"][~bad]) <= 1e-6
+    sc.close()
+
+
+def test_g2_raycast_full_c1_vs_reference(reference):
+    sb = scenes.cornell_box()
+    sc, rs = lmcu.Scene(sb), reference.RefScene(sb)
+    rays = scenes.camera_rays(sb.camera, 1920, 1080)
+    bad = classify_hits(rs.intersect(rays), sc.intersect(rays))["bad_mask"].reshape(1080, 1920)
+    for kw in ({}, {"visualize_normal": True}, {"use_constant_color": True}, {"color": (.2, .4, .6)}, {"bg_color": (.1, .2, .3)}):
+        p = abi.render_params(1920, 1080, **kw)
+        fr, _, _ = rs.render("raycast", p)
+        fg, _ = sc.render("raycast", p)
+        assert rmse(fg[~bad], fr[~bad]) <= 1e-6, kw
+        assert np.abs(fg[~bad] - fr[~bad]).max() <= 1e-5, kw
+    rs.close(); sc.close()
+
+
+@pytest.mark.parametrize("tag,mode", [("mis", abi.SAMPLING_MIS), ("naive", abi.SAMPLING_NAIVE)])
+def test_g3_pt_vs_golden(tag, mode):
+    """Equal spp, different RNG streams: means within 1 %, no structure in the difference image."""
+    sb = CASES["spheres12"]()
+    sc = lmcu.Scene(sb)
+    film, st = sc.render("pt", abi.render_params(96, 54, spp=1024, max_verts=12, sampling_mode=mode))
+    assert st["processed"] == 1024 and st["paths"] == 96 * 54 * 1024
+    assert_pt_parity(GOLDEN["spheres12_pt_" + tag], film, 1024, rel_mean=0.01)
+    sc.close()
+
+
+def test_g3_ao_vs_golden():
+    sb = CASES["spheres12"]()
+    sc = lmcu.Scene(sb)
+    film, _ = sc.render("ao", abi.render_params(96, 54, spp=256))
+    assert_pt_parity(GOLDEN["spheres12_ao"], film, 256, rel_mean=0.01)
+    sc.close()
+
+
+@pytest.mark.parametrize("mode", [abi.SAMPLING_MIS, abi.SAMPLING_NEE, abi.SAMPLING_NAIVE])
+def test_g3_pt_c2_vs_reference(reference, mode):
+    """C2 scene (32 268 triangles, diffuse + glass spheres, area light) at reduced resolution."""
+    sb = scenes.cornell_spheres(64)
+    sc, rs = lmcu.Scene(sb), reference.RefScene(sb)
+    p = abi.render_params(240, 136, spp=256, max_verts=20, sampling_mode=mode)
+    fr, _, _ = rs.render("pt", p)
+    fg, _ = sc.render("pt", p)
+    assert_pt_parity(fr, fg, 256, rel_mean=0.01)
+    # calibration: two reference runs with different seeds pass the same gate
+    p2 = abi.render_params(240, 136, spp=256, max_verts=20, sampling_mode=mode, seed=7)
+    fr2, _, _ = rs.render("pt", p2)
+    assert_pt_parity(fr, fr2, 256, rel_mean=0.01)
+    rs.close(); sc.close()
+
+
+def test_g3_pt_all_materials_env_light(reference):
+    """C4-style materials (glossy / glass / mirror / diffuse) under light::envconst, instanced."""
+    sb = scenes.instanced_spheres(grid=2, num_theta=24)
+    sc, rs = lmcu.Scene(sb), reference.RefScene(sb)
+    p = abi.render_params(192, 108, spp=256, max_verts=20)
+    fr, _, _ = rs.render("pt", p)
+    fg, _ = sc.render("pt", p)
+    assert_pt_parity(fr, fg, 256, rel_mean=0.015)
+    rs.close(); sc.close()
+
+
+def test_sample_split_is_additive():
+    """Sample split (multi-GPU partition): two half renders with disjoint sample offsets sum to the full render."""
+    sb = scenes.cornell_spheres(16)
+    sc = lmcu.Scene(sb)
+    full, _ = sc.render("pt", abi.render_params(128, 72, spp=64, max_verts=8, rescale=0))
+    a, _ = sc.render("pt", abi.render_params(128, 72, spp=32, max_verts=8, rescale=0, sample_offset=0))
+    b, _ = sc.render("pt", abi.render_params(128, 72, spp=32, max_verts=8, rescale=0, sample_offset=32))
+    # same counter-RNG streams; only the fp32 atomic summation order differs
+    assert np.allclose(a + b, full, rtol=1e-4, atol=1e-4)
+    sc.close()
+
+
+def test_full_size_properties_c3():
+    """C3 at full size (9 999 392 triangles): properties that need no oracle.
+    - every hit lies inside [tmin,tmax] and has valid barycentrics
+    - a second-hit query started just behind the first hit never returns the same triangle
+    - re-tracing with tmax = t_hit returns the same hit (idempotence, inclusive upper bound)"""
+    sb = scenes.heightfield_scene(2236)
+    sc = lmcu.Scene(sb)
+    assert sc.build_stats.num_triangles == 9999392
+    rays = scenes.camera_rays(sb.camera, 1024, 1024)
+    h = sc.intersect(rays)
+    ok = h["primitive"] >= 0
+    assert ok.mean() > 0.3
+    assert (h["t"][ok] >= 1e-3).all() and (h["u"][ok] >= 0).all() and (h["v"][ok] >= 0).all()
+    assert (h["u"][ok] + h["v"][ok] <= 1 + 1e-12).all()
+    r2 = rays[ok].copy()
+    r2["tmax"] = h["t"][ok]
+    h2 = sc.intersect(r2)
+    assert (h2["face"] == h["face"][ok]).all() and (h2["t"] == h["t"][ok]).all()
+    r3 = rays[ok].copy()
+    r3["tmin"] = h["t"][ok] * (1 + 1e-9)
+    h3 = sc.intersect(r3)
+    both = h3["primitive"] >= 0
+    assert (h3["face"][both] != h["face"][ok][both]).all()
+    assert (h3["t"][both] > h["t"][ok][both]).all()
+    sc.close()

@@ -1,0 +1,82 @@
+"""Kernel bodies compiled by g++ (tests/hostsim, a debugging aid — NOT a product path) against the
+unmodified reference: catches logic errors in the builder / traversal / shading source before it
+reaches a GPU.  The parity tests proper are the -m gpu ones, which run the CUDA build."""
+import numpy as np
+import pytest
+
+from lmcu import abi, scenes
+from parity import assert_hit_parity, assert_pt_parity, classify_hits, rmse
+
+
+@pytest.fixture(scope="module")
+def sim():
+    import sim as simmod
+    simmod.build()
+    return simmod
+
+
+@pytest.mark.parametrize("name,make", [
+    ("cornell", lambda: scenes.cornell_box()),
+    ("cornell_fp64", lambda: scenes.cornell_box(True)),
+    ("spheres", lambda: scenes.cornell_spheres(12)),
+    ("heightfield", lambda: scenes.heightfield_scene(48)),
+])
+def test_closest_hit_matches_sahbvh(reference, sim, name, make):
+    sb = make()
+    rs, ss = reference.RefScene(sb), sim.SimScene(sb)
+    lo, hi = (np.array([-1, 0, -1.]), np.array([1, 2, 1.])) if "height" not in name else (np.array([-1, -.2, -1.]), np.array([1, .6, 1.]))
+    rays = np.concatenate([scenes.camera_rays(sb.camera, 160, 90), scenes.random_rays(8000, lo, hi)])
+    hr, hs = rs.intersect(rays), ss.intersect(rays)
+    assert ss.overflow == 0
+    assert_hit_parity(hr, hs, max_special_frac=3e-3)
+    rs.close()
+
+
+def test_ragged_and_tiny_scenes(reference, sim):
+    """1, 2, 3, 4 and 7 triangles (leaf-only roots, a root with one internal child)."""
+    for nf in (1, 2, 3, 4, 7):
+        sb = scenes.SceneBuilder()
+        rng = np.random.RandomState(nf)
+        tri = scenes._f32(rng.rand(nf, 3, 3) * 2 - 1)
+        sb.add_primitive(sb.add_mesh(tri, scenes.flat_normals(tri)), sb.diffuse((.5, .5, .5)))
+        sb.set_camera(position=(0, 0, 4), center=(0, 0, 0), up=(0, 1, 0), vfov=40, aspect=1)
+        rs, ss = reference.RefScene(sb), sim.SimScene(sb)
+        rays = scenes.camera_rays(sb.camera, 64, 64)
+        assert_hit_parity(rs.intersect(rays), ss.intersect(rays), max_special_frac=3e-3)
+        rs.close()
+
+
+def test_tmin_tmax_window(reference, sim):
+    sb = scenes.cornell_spheres(8)
+    rs, ss = reference.RefScene(sb), sim.SimScene(sb)
+    rays = scenes.random_rays(5000, np.array([-1, 0, -1.]), np.array([1, 2, 1.]), seed=3)
+    rays["tmin"] = 0.3
+    rays["tmax"] = 0.9
+    hr, hs = rs.intersect(rays), ss.intersect(rays)
+    assert_hit_parity(hr, hs, max_special_frac=3e-3)
+    assert ((hs["t"][hs["primitive"] >= 0] >= 0.3) & (hs["t"][hs["primitive"] >= 0] <= 0.9)).all()
+    rs.close()
+
+
+def test_raycast_image(reference, sim):
+    sb = scenes.cornell_spheres(12)
+    rs, ss = reference.RefScene(sb), sim.SimScene(sb)
+    rays = scenes.camera_rays(sb.camera, 192, 108)
+    bad = classify_hits(rs.intersect(rays), ss.intersect(rays))["bad_mask"].reshape(108, 192)
+    for kw in ({}, {"visualize_normal": True}, {"use_constant_color": True}, {"color": (.2, .4, .6)}):
+        p = abi.render_params(192, 108, **kw)
+        fr, _, _ = rs.render("raycast", p)
+        fs = ss.render("raycast", p)
+        assert rmse(fs[~bad], fr[~bad]) <= 1e-6
+    rs.close()
+
+
+@pytest.mark.parametrize("mode", [abi.SAMPLING_MIS, abi.SAMPLING_NEE, abi.SAMPLING_NAIVE])
+def test_pt_statistics(reference, sim, mode):
+    sb = scenes.cornell_spheres(8)
+    rs, ss = reference.RefScene(sb), sim.SimScene(sb)
+    p = abi.render_params(96, 54, spp=96, max_verts=12, sampling_mode=mode)
+    fr, _, _ = rs.render("pt", p)
+    fs = ss.render("pt", p)
+    assert_pt_parity(fr, fs, 96, rel_mean=0.02)
+    rs.close()
