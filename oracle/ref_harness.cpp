@@ -230,7 +230,7 @@ int lmref_render(void* s, const char* renderer_key, const LmcuRenderParams* p, d
         Json prop{
             {"scene", rs->scene_loc}, {"output", film->loc()},
             {"spp", (long long)p->spp}, {"max_verts", p->max_verts}, {"seed", p->seed},
-            {"scheduler", "sample"}, {"sampling_mode", modes[p->sampling_mode]},
+            {"scheduler", "sample"}, {"sampling_mode", std::string(modes[p->sampling_mode])},   // a bare const char* would hit lm's pointer serializer
             {"bg_color", vec3(p->bg_color)}, {"use_constant_color", bool(p->use_constant_color)},
             {"visualize_normal", bool(p->visualize_normal)} };
         if (p->has_color) prop["color"] = vec3(p->color);

@@ -47,6 +47,16 @@ def main():
             f, _, _ = rs.render("ao", abi.render_params(96, 54, spp=256))
             out["spheres12_ao"] = f.astype(np.float32)
         rs.close()
+    # single-threaded reference pt: deterministic mt19937 stream (seed + thread 0); run in a fresh process because the
+    # reference's per-thread Rng is a thread_local that survives across render() calls (renderer_pt.cpp:91)
+    import pickle
+    import subprocess
+    code = ("import sys,pickle; sys.path[:0]=[%r,%r]\n"
+            "from oracle import ref; from lmcu import abi, scenes\n"
+            "ref.init(1); sb=scenes.cornell_spheres(8); rs=ref.RefScene(sb)\n"
+            "f,_,_=rs.render('pt', abi.render_params(48,27,spp=4,max_verts=10,seed=42))\n"
+            "sys.stdout.buffer.write(pickle.dumps(f))\n") % (ROOT, os.path.join(ROOT, "lightmetrica-v3_b200"))
+    out["spheres8_pt_1thread_seed42"] = pickle.loads(subprocess.check_output([sys.executable, "-c", code]))
     np.savez_compressed(os.path.join(HERE, "reference_outputs.npz"), **out)
     print({k: v.shape for k, v in out.items()})
 

@@ -1,0 +1,117 @@
+"""Pins the C restatement (oracle/lm_oracle.c) to the unmodified reference:
+  - against the committed golden outputs of the reference (always),
+  - against oracle/_ref run side by side (when it is built).
+Closest hits and raycast images must be bit-identical (ties aside); the path tracer must be
+bit-identical to the reference run single-threaded on the same mt19937 stream."""
+import os
+import pickle
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from lmcu import abi, scenes
+from parity import assert_hit_parity, classify_hits
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = np.load(os.path.join(ROOT, "tests", "golden", "reference_outputs.npz"))
+
+
+@pytest.fixture(scope="module")
+def port():
+    from oracle import port as p
+    p.build()
+    return p
+
+
+def test_rng_is_libstdcxx_mt19937(port):
+    # std::mt19937(5489) first outputs are 3499211612, 581869302 (the standard's known-answer); canonical<double,53>
+    # combines two draws: (x0 + x1 * 2^32) / 2^64
+    u = port.rng_uniforms(5489, 1)[0]
+    assert u == (3499211612 + 581869302 * 2.0 ** 32) / 2.0 ** 64
+    assert (port.rng_uniforms(42, 1000) < 1.0).all()
+
+
+@pytest.mark.parametrize("name,make", [
+    ("cornell", lambda: scenes.cornell_box()),
+    ("cornell_fp64", lambda: scenes.cornell_box(True)),
+    ("spheres12", lambda: scenes.cornell_spheres(12)),
+    ("heightfield48", lambda: scenes.heightfield_scene(48)),
+])
+def test_port_hits_vs_golden(port, name, make):
+    from golden.make_golden import golden_rays
+    sb = make()
+    ps = port.PortScene(sb)
+    h = ps.intersect(golden_rays(name, sb))
+    g = np.zeros(len(h), dtype=scenes.HIT_DTYPE)
+    g["t"], g["u"], g["v"] = GOLDEN[name + "_t"], GOLDEN[name + "_u"], GOLDEN[name + "_v"]
+    g["primitive"], g["face"] = GOLDEN[name + "_prim"], GOLDEN[name + "_face"]
+    c = assert_hit_parity(g, h, max_special_frac=3e-3)
+    assert c["ref_boundary_miss"] == 0          # same box test as the reference: misses the same boundary hits
+    assert (g["t"] == h["t"]).all()             # t is bit-identical for every ray, ties included
+    ps.close()
+
+
+@pytest.mark.parametrize("name,make", [("cornell", lambda: scenes.cornell_box()), ("spheres12", lambda: scenes.cornell_spheres(12))])
+def test_port_raycast_vs_golden(port, name, make):
+    from golden.make_golden import golden_rays
+    sb = make()
+    ps = port.PortScene(sb)
+    f = ps.render("raycast", abi.render_params(192, 108))
+    g = GOLDEN[name + "_raycast"]
+    h = ps.intersect(golden_rays(name, sb)[:192 * 108])
+    tie = ((h["primitive"] != GOLDEN[name + "_prim"][:192 * 108]) | (h["face"] != GOLDEN[name + "_face"][:192 * 108])).reshape(108, 192)
+    assert (f.astype(np.float32)[~tie] == g[~tie]).all()
+    ps.close()
+
+
+def test_port_pt_bit_exact_vs_golden_single_thread(port):
+    sb = scenes.cornell_spheres(8)
+    ps = port.PortScene(sb)
+    f = ps.render("pt", abi.render_params(48, 27, spp=4, max_verts=10, seed=42), num_threads=1)
+    assert np.abs(f - GOLDEN["spheres8_pt_1thread_seed42"]).max() <= 1e-12
+    ps.close()
+
+
+def test_port_pt_statistics_vs_golden(port):
+    from parity import assert_pt_parity
+    sb = scenes.cornell_spheres(12)
+    ps = port.PortScene(sb)
+    f = ps.render("pt", abi.render_params(96, 54, spp=1024, max_verts=12, sampling_mode=abi.SAMPLING_MIS))
+    assert_pt_parity(GOLDEN["spheres12_pt_mis"], f, 1024, rel_mean=0.01)
+    ps.close()
+
+
+def _ref_single_thread(scene_expr, params_expr):
+    code = ("import sys,pickle; sys.path[:0]=[%r,%r]\n"
+            "from oracle import ref; from lmcu import abi, scenes\n"
+            "ref.init(1); sb=%s; rs=ref.RefScene(sb)\n"
+            "f,_,_=rs.render('pt', %s)\n"
+            "sys.stdout.buffer.write(pickle.dumps(f))\n") % (ROOT, os.path.join(ROOT, "lightmetrica-v3_b200"), scene_expr, params_expr)
+    return pickle.loads(subprocess.check_output([sys.executable, "-c", code]))
+
+
+@pytest.mark.parametrize("scene_expr,mode", [
+    ("scenes.cornell_spheres(8)", 2), ("scenes.cornell_spheres(8)", 1), ("scenes.cornell_spheres(8)", 0),
+    ("scenes.instanced_spheres(2, 10)", 2),
+])
+def test_port_pt_bit_exact_vs_reference(reference, port, scene_expr, mode):
+    """Every material (diffuse, glossy, glass, mirror), area + constant env light, all three sampling modes."""
+    params_expr = "abi.render_params(40, 24, spp=3, max_verts=12, seed=11, sampling_mode=%d)" % mode
+    fr = _ref_single_thread(scene_expr, params_expr)
+    ps = port.PortScene(eval(scene_expr))
+    fp = ps.render("pt", eval(params_expr), num_threads=1)
+    assert np.abs(fr - fp).max() <= 1e-12 * max(1.0, fr.max())
+    ps.close()
+
+
+def test_port_vs_reference_accel(reference, port):
+    sb = scenes.cornell_spheres(16)
+    rs, ps = reference.RefScene(sb), port.PortScene(sb)
+    rays = np.concatenate([scenes.camera_rays(sb.camera, 200, 112), scenes.random_rays(20000, np.array([-1, 0, -1.]), np.array([1, 2, 1.]))])
+    hr, hp = rs.intersect(rays), ps.intersect(rays)
+    assert (hr["t"] == hp["t"]).all()
+    c = classify_hits(hr, hp)
+    assert c["other"] == 0 and c["ref_boundary_miss"] == 0
+    rs.close(); ps.close()
