@@ -119,6 +119,7 @@ def run_ours(args):
     import torch
     import lmcu
     from lmcu import abi, scenes
+    from lmcu import distributed as D
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -141,15 +142,16 @@ def run_ours(args):
 
     def step():
         """One pass: render this rank's samples, reduce the film, scale.  Returns the stats dict."""
-        p = abi.render_params(W, H, spp=spp, max_verts=MAX_VERTS, seed=SEED, sample_offset=rank * spp, rescale=0)
-        _, st = sc.render("pt", p, download=False)
-        ptr, n = sc.film_device()
-        film = _as_tensor(torch, ptr, n, local_rank)
-        if world > 1:
-            dist.reduce(film, dst=0, op=dist.ReduceOp.SUM)
-        if rank == 0:
-            film.mul_(1.0 / (world * spp))            # film::rescale(1/processed), renderer_pt.cpp:307-309
-        return st, film
+        out = {}
+
+        def render_sums(offset, count):
+            p = abi.render_params(W, H, spp=count, max_verts=MAX_VERTS, seed=SEED, sample_offset=offset, rescale=0)
+            _, out["st"] = sc.render("pt", p, download=False)
+            ptr, n = sc.film_device()
+            return D.film_as_tensor(torch, ptr, n, local_rank)
+
+        film = D.render_pt_sample_split(render_sums, world * spp, rank, world, dist)
+        return out["st"], film
 
     def sync():
         torch.cuda.synchronize()
@@ -192,7 +194,7 @@ def run_ours(args):
             p = abi.render_params(W, H, spp=spp, max_verts=MAX_VERTS, seed=SEED, sample_offset=rank * spp, rescale=0)
             sc2.render("pt", p, download=False)
             ptr, n = sc2.film_device()
-            film2 = _as_tensor(torch, ptr, n, local_rank)
+            film2 = D.film_as_tensor(torch, ptr, n, local_rank)
             if world > 1:
                 torch.cuda.synchronize()
                 dist.reduce(film2, dst=0, op=dist.ReduceOp.SUM)
@@ -255,15 +257,6 @@ def run_ours(args):
         }))
     if world > 1:
         dist.destroy_process_group()
-
-
-def _as_tensor(torch, ptr, n, device_index):
-    """Zero-copy torch view of the device film (plumbing for the NCCL reduce)."""
-    class _Holder:
-        pass
-    h = _Holder()
-    h.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 3, "strides": None}
-    return torch.as_tensor(h, device=torch.device("cuda", device_index))
 
 
 def main():

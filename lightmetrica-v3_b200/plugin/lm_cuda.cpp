@@ -1,0 +1,417 @@
+// lm_cuda.cpp — Lightmetrica v3 plugin: the drop-in side of the CUDA hot path.
+//
+// Registers NEW components through the reference's own registry (include/lm/component.h:816-817):
+//     accel::cuda_bvh        lm::Accel      build / intersect            (include/lm/accel.h:38,70)
+//     renderer::raycast_cuda lm::Renderer   same JSON keys as renderer::raycast (renderer_raycast.cpp:48-60)
+//     renderer::ao_cuda      lm::Renderer   same keys as renderer::ao     (functest/renderer_ao.cpp:18-22)
+//     renderer::pt_cuda      lm::Renderer   same keys as renderer::pt     (renderer_pt.cpp:51-77)
+// It is loaded with lm::comp::load_plugin("<dir>/lm_cuda") exactly like accel_nanort / accel_embree.
+//
+// This file is HOST glue only: it pulls geometry, transforms, materials, lights and the camera out of
+// lm::Scene through public interfaces and hands plain arrays to liblmcu.so over the C ABI of
+// include/lmcu.h.  All ray tracing happens on the GPU; there is no CPU fallback (a missing device or
+// library surfaces as lm::Exception).
+#include <lm/lm.h>
+
+#include <map>
+#include <mutex>
+
+#include "../../include/lmcu.h"
+
+LM_NAMESPACE_BEGIN(LM_NAMESPACE)
+
+namespace {
+
+void check(int rc) {
+    if (rc == LMCU_OK) return;
+    const std::string msg = lmcu_last_error();
+    switch (rc) {
+    case LMCU_ERR_INVALID_ARGUMENT: LM_THROW_EXCEPTION(Error::InvalidArgument, "lmcu: {}", msg);
+    case LMCU_ERR_UNSUPPORTED: LM_THROW_EXCEPTION(Error::Unsupported, "lmcu: {}", msg);
+    default: LM_THROW_EXCEPTION(Error::None, "lmcu: {}", msg);
+    }
+}
+
+// Everything liblmcu needs, gathered from an lm::Scene.  Owns the arrays the LmcuSceneDesc points to.
+struct SceneExport {
+    std::vector<std::vector<double>> mesh_p, mesh_n;
+    std::vector<LmcuMesh> meshes;
+    std::vector<LmcuPrimitive> prims;
+    std::vector<LmcuMaterial> mats;
+    std::vector<LmcuLight> lights;
+    LmcuCamera camera{};
+    bool has_camera = false;
+    std::map<int, Transform> transforms;   // SceneNode::index -> Transform for Accel::Hit
+    LmcuSceneDesc desc{};
+
+    // Material parameters are private in the reference; recover them through the public virtuals
+    // (SURVEY.md §7 "hard parts"): key() gives the type, reflectance() gives Kd / Ks, GGX roughness
+    // follows from pdf_direction() at three half vectors, the index of refraction from the Fresnel
+    // reflectance at normal incidence returned by pdf_component().
+    static LmcuMaterial probe_material(const Material* m) {
+        LmcuMaterial o{};
+        const auto geom = PointGeometry::make_on_surface(Vec3(0_f), Vec3(0_f, 0_f, 1_f), Vec3(0_f, 0_f, 1_f));
+        const auto key = m->key();
+        if (key == "material::diffuse") {
+            o.type = LMCU_MAT_DIFFUSE;
+            const Vec3 Kd = m->reflectance(geom);
+            o.color[0] = Kd.x; o.color[1] = Kd.y; o.color[2] = Kd.z;
+        }
+        else if (key == "material::glossy") {
+            o.type = LMCU_MAT_GLOSSY;
+            const Vec3 Ks = m->reflectance(geom);
+            o.color[0] = Ks.x; o.color[1] = Ks.y; o.color[2] = Ks.z;
+            // pdf(wi=wo=wh) = D(wh)/4 (material_glossy.cpp:92-99), D from :43-46
+            const auto D = [&](Vec3 w) { return 4_f * m->pdf_direction(geom, w, w, 0, false); };
+            const auto P = 1_f / (Pi * D(geom.n));                          // ax*ay
+            const auto th = .5_f;
+            const auto s2 = math::sq(std::sin(th)), c2 = math::sq(std::cos(th));
+            const auto solve = [&](Vec3 t) {
+                const auto w = glm::normalize(t * std::sin(th) + geom.n * std::cos(th));
+                const auto q = std::sqrt(1_f / (Pi * P * D(w)));            // (sin^2/a^2 + cos^2)
+                return std::sqrt(s2 / (q - c2));
+            };
+            o.ax = solve(geom.u);
+            o.ay = solve(geom.v);
+        }
+        else if (key == "material::glass") {
+            o.type = LMCU_MAT_GLASS;
+            const auto R0 = m->pdf_component(0, geom, geom.n);              // Schlick at normal incidence
+            const auto r = std::sqrt(R0);
+            o.Ni = (1_f + r) / (1_f - r);
+        }
+        else if (key == "material::mirror") {
+            o.type = LMCU_MAT_MIRROR;
+        }
+        else {
+            LM_THROW_EXCEPTION(Error::Unsupported, "renderer::*_cuda: unsupported material [key='{}']", key);
+        }
+        return o;
+    }
+
+    void gather(const Scene& scene, bool shading) {
+        std::map<const Mesh*, int> mesh_ids;
+        std::map<const Material*, int> mat_ids;
+        scene.traverse_primitive_nodes([&](const SceneNode& node, Mat4 global_transform) {
+            if (node.type != SceneNodeType::Primitive) {
+                return;
+            }
+            if (node.primitive.light && !node.primitive.mesh) {
+                if (!shading) return;
+                // environment light (src/scene.cpp:103-110)
+                LmcuLight l{};
+                const auto key = node.primitive.light->key();
+                if (key != "light::envconst") {
+                    LM_THROW_EXCEPTION(Error::Unsupported, "renderer::*_cuda: unsupported light [key='{}']", key);
+                }
+                l.type = LMCU_LIGHT_ENVCONST;
+                l.primitive = -1;
+                l.node_index = node.index;
+                const auto Le = node.primitive.light->eval(PointGeometry::make_infinite(Vec3(0_f, 0_f, 1_f)), Vec3(0_f, 0_f, 1_f), false);
+                l.Ke[0] = Le.x; l.Ke[1] = Le.y; l.Ke[2] = Le.z;
+                lights.push_back(l);
+                return;
+            }
+            if (!node.primitive.mesh) {
+                return;
+            }
+            const Mesh* mesh = node.primitive.mesh;
+            auto it = mesh_ids.find(mesh);
+            if (it == mesh_ids.end()) {
+                it = mesh_ids.emplace(mesh, int(mesh_p.size())).first;
+                mesh_p.emplace_back();
+                mesh_n.emplace_back();
+                auto& P = mesh_p.back();
+                auto& N = mesh_n.back();
+                P.reserve(size_t(mesh->num_triangles()) * 9);
+                N.reserve(size_t(mesh->num_triangles()) * 9);
+                mesh->foreach_triangle([&](int, const Mesh::Tri& tri) {
+                    for (const auto* v : { &tri.p1, &tri.p2, &tri.p3 }) {
+                        P.push_back(v->p.x); P.push_back(v->p.y); P.push_back(v->p.z);
+                        N.push_back(v->n.x); N.push_back(v->n.y); N.push_back(v->n.z);
+                    }
+                });
+            }
+            LmcuPrimitive p{};
+            p.node_index = node.index;
+            p.mesh = it->second;
+            p.material = 0;
+            p.light = -1;
+            for (int c = 0; c < 4; c++) for (int r = 0; r < 4; r++) p.M[c * 4 + r] = global_transform[c][r];
+            if (shading) {
+                const Material* m = node.primitive.material;
+                auto mi = mat_ids.find(m);
+                if (mi == mat_ids.end()) {
+                    mi = mat_ids.emplace(m, int(mats.size())).first;
+                    mats.push_back(probe_material(m));
+                }
+                p.material = mi->second;
+                if (node.primitive.light) {
+                    const auto key = node.primitive.light->key();
+                    if (key != "light::area") {
+                        LM_THROW_EXCEPTION(Error::Unsupported, "renderer::*_cuda: unsupported light [key='{}']", key);
+                    }
+                    LmcuLight l{};
+                    l.type = LMCU_LIGHT_AREA;
+                    l.primitive = int(prims.size());
+                    l.node_index = node.index;
+                    // Ke through Light::eval on the emitting side (light_area.cpp:185-187)
+                    const auto g = PointGeometry::make_on_surface(Vec3(0_f), Vec3(0_f, 0_f, 1_f), Vec3(0_f, 0_f, 1_f));
+                    const auto Ke = node.primitive.light->eval(g, Vec3(0_f, 0_f, 1_f), false);
+                    l.Ke[0] = Ke.x; l.Ke[1] = Ke.y; l.Ke[2] = Ke.z;
+                    p.light = int(lights.size());
+                    lights.push_back(l);
+                }
+            }
+            transforms.emplace(node.index, Transform(global_transform));
+            prims.push_back(p);
+        });
+        if (mats.empty()) {
+            mats.push_back(LmcuMaterial{});
+        }
+        if (shading && scene.camera_node() >= 0) {
+            // camera::pinhole exports its parameters (src/camera/camera_pinhole.cpp:66-74)
+            const auto* cam = scene.node_at(scene.camera_node()).primitive.camera;
+            const Json v = cam->underlying_value("");
+            const Vec3 eye = v["eye"], center = v["center"], up = v["up"];
+            for (int i = 0; i < 3; i++) { camera.position[i] = eye[i]; camera.center[i] = center[i]; camera.up[i] = up[i]; }
+            camera.vfov = v["vfov"];
+            camera.aspect = v["aspect"];
+            has_camera = true;
+        }
+        meshes.resize(mesh_p.size());
+        for (size_t i = 0; i < mesh_p.size(); i++) {
+            meshes[i].num_faces = int(mesh_p[i].size() / 9);
+            meshes[i].p = mesh_p[i].data();
+            meshes[i].n = mesh_n[i].data();
+        }
+        desc.num_meshes = int(meshes.size());
+        desc.num_primitives = int(prims.size());
+        desc.num_materials = int(mats.size());
+        desc.num_lights = int(lights.size());
+        desc.meshes = meshes.data();
+        desc.primitives = prims.data();
+        desc.materials = mats.data();
+        desc.lights = lights.data();
+        desc.camera = has_camera ? &camera : nullptr;
+    }
+};
+
+struct DeviceScene {
+    LmcuScene* h = nullptr;
+    ~DeviceScene() { if (h) lmcu_scene_destroy(h); }
+    void upload(const SceneExport& ex, int device) {
+        if (h) { lmcu_scene_destroy(h); h = nullptr; }
+        check(lmcu_scene_create(device, &h));
+        check(lmcu_scene_upload(h, &ex.desc));
+        check(lmcu_accel_build(h, nullptr, nullptr));
+    }
+};
+
+}
+
+// ------------------------------------------------------------------------------------------------
+
+/*
+\rst
+.. function:: accel::cuda_bvh
+
+   Compressed 8-wide BVH built and traversed on a CUDA device (sm_100a).
+
+   :param int device: CUDA device index. Default: 0.
+
+   ``intersect()`` keeps the scalar contract of :cpp:func:`lm::Accel::intersect` (one ray per call,
+   thread-safe) for callers such as ``scene::default``; batched rays and the device-resident renderers
+   are the fast path.
+\endrst
+*/
+class Accel_CudaBVH final : public Accel {
+private:
+    int device_ = 0;
+    DeviceScene dev_;
+    std::map<int, Transform> transforms_;
+    mutable std::mutex mu_;
+
+public:
+    virtual void construct(const Json& prop) override {
+        device_ = json::value<int>(prop, "device", 0);
+    }
+
+    virtual void build(const Scene& scene) override {
+        LM_INFO("Flattening scene");
+        SceneExport ex;
+        ex.gather(scene, false);
+        LM_INFO("Building");
+        dev_.upload(ex, device_);
+        transforms_ = std::move(ex.transforms);
+    }
+
+    virtual std::optional<Hit> intersect(Ray ray, Float tmin, Float tmax) const override {
+        LmcuRay r{ { ray.o.x, ray.o.y, ray.o.z }, { ray.d.x, ray.d.y, ray.d.z }, tmin, tmax };
+        LmcuHit h{};
+        {
+            std::unique_lock<std::mutex> lk(mu_);
+            check(lmcu_accel_intersect(dev_.h, &r, 1, &h));
+        }
+        if (h.primitive < 0) {
+            return {};
+        }
+        return Hit{ h.t, Vec2(h.u, h.v), transforms_.at(h.primitive), h.primitive, h.face };
+    }
+};
+
+LM_COMP_REG_IMPL(Accel_CudaBVH, "accel::cuda_bvh");
+
+// ------------------------------------------------------------------------------------------------
+
+// Shared part of the three device-resident renderers.
+class Renderer_CudaBase : public Renderer {
+protected:
+    Scene* scene_;
+    Film* film_;
+    int device_ = 0;
+    mutable DeviceScene dev_;
+
+public:
+    virtual void foreach_underlying(const ComponentVisitor& visit) override {
+        comp::visit(visit, scene_);
+        comp::visit(visit, film_);
+    }
+
+protected:
+    void construct_base(const Json& prop) {
+        scene_ = json::comp_ref<Scene>(prop, "scene");
+        film_ = json::comp_ref<Film>(prop, "output");
+        device_ = json::value<int>(prop, "device", 0);
+    }
+
+    void upload() const {
+        SceneExport ex;
+        ex.gather(*scene_, true);
+        dev_.upload(ex, device_);
+    }
+
+    void write_film(const std::vector<float>& rgb, bool skip_black) const {
+        const auto size = film_->size();
+        for (int y = 0; y < size.h; y++) {
+            for (int x = 0; x < size.w; x++) {
+                const float* c = &rgb[(size_t(y) * size.w + x) * 3];
+                if (skip_black && c[0] == 0.f && c[1] == 0.f && c[2] == 0.f) continue;
+                film_->set_pixel(x, y, Vec3(c[0], c[1], c[2]));
+            }
+        }
+    }
+};
+
+class Renderer_Raycast_Cuda final : public Renderer_CudaBase {
+private:
+    Vec3 bg_color_;
+    bool use_constant_color_;
+    bool visualize_normal_;
+    std::optional<Vec3> color_;
+
+public:
+    virtual void construct(const Json& prop) override {
+        construct_base(prop);
+        bg_color_ = json::value(prop, "bg_color", Vec3(0_f));
+        use_constant_color_ = json::value(prop, "use_constant_color", false);
+        visualize_normal_ = json::value(prop, "visualize_normal", false);
+        color_ = json::value_or_none<Vec3>(prop, "color");
+    }
+
+    virtual Json render() const override {
+        scene_->require_primitive();
+        scene_->require_camera();
+        film_->clear();
+        upload();
+        const auto size = film_->size();
+        LmcuRenderParams p{};
+        p.width = size.w; p.height = size.h; p.spp = 1;
+        p.use_constant_color = use_constant_color_; p.visualize_normal = visualize_normal_; p.has_color = color_ ? 1 : 0;
+        for (int i = 0; i < 3; i++) { p.bg_color[i] = bg_color_[i]; p.color[i] = color_ ? (*color_)[i] : 0_f; }
+        std::vector<float> rgb(size_t(size.w) * size.h * 3);
+        LmcuRenderStats st{};
+        check(lmcu_render_raycast(dev_.h, &p, rgb.data(), &st));
+        write_film(rgb, false);
+        return { {"elapsed", st.elapsed} };
+    }
+};
+
+LM_COMP_REG_IMPL(Renderer_Raycast_Cuda, "renderer::raycast_cuda");
+
+class Renderer_AO_Cuda final : public Renderer_CudaBase {
+private:
+    long long spp_;
+    int rng_seed_ = 42;
+
+public:
+    virtual void construct(const Json& prop) override {
+        construct_base(prop);
+        spp_ = json::value<long long>(prop, "spp");
+    }
+
+    virtual Json render() const override {
+        upload();
+        const auto size = film_->size();
+        LmcuRenderParams p{};
+        p.width = size.w; p.height = size.h; p.spp = spp_; p.seed = unsigned(rng_seed_); p.ao_distance = .2_f;
+        std::vector<float> rgb(size_t(size.w) * size.h * 3);
+        LmcuRenderStats st{};
+        check(lmcu_render_ao(dev_.h, &p, rgb.data(), &st));
+        write_film(rgb, false);
+        return { {"elapsed", st.elapsed} };
+    }
+};
+
+LM_COMP_REG_IMPL(Renderer_AO_Cuda, "renderer::ao_cuda");
+
+class Renderer_PT_Cuda final : public Renderer_CudaBase {
+private:
+    int max_verts_;
+    std::optional<unsigned int> seed_;
+    int sampling_mode_;
+    long long spp_;
+
+public:
+    virtual void construct(const Json& prop) override {
+        construct_base(prop);
+        max_verts_ = json::value<int>(prop, "max_verts");
+        seed_ = json::value_or_none<unsigned int>(prop, "seed");
+        {
+            const auto s = json::value<std::string>(prop, "sampling_mode", "mis");
+            if (s == "naive") sampling_mode_ = LMCU_SAMPLING_NAIVE;
+            else if (s == "nee") sampling_mode_ = LMCU_SAMPLING_NEE;
+            else sampling_mode_ = LMCU_SAMPLING_MIS;
+        }
+        {
+            const auto name = json::value<std::string>(prop, "scheduler");
+            const auto s = json::value<std::string>(prop, "primary_ray_sampling_mode", "pixel");
+            if (name != "sample" || s != "pixel") {
+                LM_THROW_EXCEPTION(Error::Unsupported,
+                    "renderer::pt_cuda supports scheduler='sample' with primary_ray_sampling_mode='pixel'");
+            }
+            spp_ = json::value<long long>(prop, "spp");
+        }
+    }
+
+    virtual Json render() const override {
+        scene_->require_renderable();
+        film_->clear();
+        upload();
+        const auto size = film_->size();
+        LmcuRenderParams p{};
+        p.width = size.w; p.height = size.h; p.spp = spp_; p.max_verts = max_verts_;
+        p.sampling_mode = sampling_mode_;
+        p.seed = seed_ ? *seed_ : math::rng_seed();
+        p.rescale = 1;
+        std::vector<float> rgb(size_t(size.w) * size.h * 3);
+        LmcuRenderStats st{};
+        check(lmcu_render_pt(dev_.h, &p, rgb.data(), &st));
+        write_film(rgb, false);
+        return { {"processed", st.processed}, {"elapsed", st.elapsed} };
+    }
+};
+
+LM_COMP_REG_IMPL(Renderer_PT_Cuda, "renderer::pt_cuda");
+
+LM_NAMESPACE_END(LM_NAMESPACE)

@@ -1,0 +1,63 @@
+"""Host logic of the multi-GPU sample split on CPU: world_size 2 and 3 over gloo.
+The per-rank renderer is a deterministic stand-in (sum over the block's sample indices of a per-sample
+image), so the reduced, rescaled film has a closed form; the real renderer is covered by the -m gpu tests
+(test_sample_split_is_additive) and by bench.py --gpus N."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from lmcu import distributed as D
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _fake_sample_image(i, npix):
+    g = torch.Generator().manual_seed(1000 + i)
+    return torch.rand(npix * 3, generator=g)
+
+
+def _worker(rank, world, port, total_spp, npix, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    def render_sums(offset, count):
+        film = torch.zeros(npix * 3)
+        for i in range(offset, offset + count):
+            film += _fake_sample_image(i, npix)
+        return film
+
+    film = D.render_pt_sample_split(render_sums, total_spp, rank, world, dist)
+    if rank == 0:
+        torch.save(film, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,total_spp", [(2, 8), (3, 7)])
+def test_sample_split_reduce(tmp_path, world, total_spp):
+    npix = 12
+    out = str(tmp_path / "film.pt")
+    mp.spawn(_worker, args=(world, _free_port(), total_spp, npix, out), nprocs=world, join=True)
+    got = torch.load(out)
+    want = sum(_fake_sample_image(i, npix) for i in range(total_spp)) / total_spp
+    assert torch.allclose(got, want, atol=1e-6)
+
+
+def test_sample_blocks_tile_the_range():
+    for total in (1, 7, 16, 1024, 16384):
+        for world in (1, 2, 3, 4, 8):
+            blocks = [D.sample_block(total, r, world) for r in range(world)]
+            assert blocks[0][0] == 0 and sum(c for _, c in blocks) == total
+            for (o0, c0), (o1, _) in zip(blocks, blocks[1:]):
+                assert o0 + c0 == o1
