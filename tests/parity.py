@@ -44,7 +44,11 @@ def assert_hit_parity(ref_hits, hits, max_special_frac=2e-4):
 def assert_pt_parity(ref_film, film, spp, rel_mean=0.01, z_frac=2e-3):
     """G3: statistical image parity at equal spp (the RNG streams differ by design).
 
-    - relative difference of the image means per channel <= rel_mean
+    - difference of the image means per channel <= max(rel_mean * mean, 4.5 standard errors of that difference):
+      rel_mean is the stated bias tolerance; the standard error (per-pixel difference std / sqrt(#pixels), both
+      images being independent estimates) keeps the gate meaningful for high-variance settings such as naive
+      sampling at low spp, where Monte-Carlo noise alone exceeds rel_mean (the reference is itself
+      non-deterministic run to run: per-thread RNG + dynamic scheduling, renderer_pt.cpp:91)
     - 8x8 block means of the difference image, z-scored by the block's own noise: the fraction of |z| > 4 stays
       <= z_frac (both images are unbiased estimates of the same radiance, so the difference is zero-mean noise;
       a shading or sampling error shows up as block means far from zero)
@@ -53,7 +57,9 @@ def assert_pt_parity(ref_film, film, spp, rel_mean=0.01, z_frac=2e-3):
     film = np.asarray(film, dtype=np.float64)
     mr, mg = ref_film.mean(axis=(0, 1)), film.mean(axis=(0, 1))
     rel = np.abs(mg - mr) / np.maximum(mr, 1e-12)
-    assert (rel <= rel_mean).all(), "image means differ: ref %s ours %s" % (mr, mg)
+    se = (film - ref_film).reshape(-1, film.shape[2]).std(axis=0) / np.sqrt(film.shape[0] * film.shape[1])
+    tol = np.maximum(rel_mean * np.maximum(mr, 1e-12), 4.5 * se)
+    assert (np.abs(mg - mr) <= tol).all(), "image means differ: ref %s ours %s (tolerance %s)" % (mr, mg, tol)
     d = (film - ref_film).mean(axis=2)
     h, w = d.shape
     hb, wb = h // 8, w // 8
