@@ -56,7 +56,8 @@ def test_renderer_raycast_cuda(plugin):
     hr = rs.intersect(rays)
     rs.close()
     rc = plugin.RefScene(sb, accel="accel::cuda_bvh")
-    tie = classify_hits(hr, rc.intersect(rays[:2000]))  # noqa: F841  (exercise the accel too)
+    c = classify_hits(hr[:2000], rc.intersect(rays[:2000]))     # exercise the scalar accel too
+    assert c["other"] == 0, c
     rc.close()
     d = np.abs(fc - fr).max(axis=2)
     assert (d > 1e-5).mean() < 3e-3                   # tie pixels only
