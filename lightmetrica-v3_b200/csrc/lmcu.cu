@@ -16,6 +16,7 @@
 
 #include "../../include/lmcu.h"
 #include "kernels.cuh"
+#include "trace.cuh"
 #include "prep.hpp"
 
 using namespace lmcu;
@@ -353,6 +354,92 @@ __global__ void __launch_bounds__(128) k_pt_shadow(DevScene s, ShadowQueue sq, f
     if (COUNT) { atomicAdd(&ctr->nodes_shadow, (unsigned long long)tc.nodes); atomicAdd(&ctr->tris_shadow, (unsigned long long)tc.tris); }
 }
 
+
+// -- queue kernels on the warp-persistent traversal (trace.cuh) -----------------------------------------
+struct BatchIO {                       // accel batches: LmcuRay in, LmcuHit out (include/lmcu.h)
+    DevScene s;
+    const LmcuRay* rays;
+    LmcuHit* hits;
+    __device__ __forceinline__ bool load(uint32_t i, RayD& r) const {
+        const double2* src = reinterpret_cast<const double2*>(rays + i);
+        const double2 a = src[0], b = src[1], c = src[2], d = src[3];
+        r.o = d3(a.x, a.y, b.x); r.d = d3(b.y, c.x, c.y); r.tmin = d.x; r.tmax = d.y;
+        return true;
+    }
+    __device__ __forceinline__ void store(uint32_t i, const RayD&, const HitD& h) const {
+        int32_t prim = -1, face = -1;
+        if (h.tri >= 0) {
+            F3 p1, p2, p3; int32_t pi;
+            tri_fetch(s, (uint32_t)h.tri, p1, p2, p3, pi, face);
+            prim = s.prims[pi].node_index;
+        }
+        double2* dst = reinterpret_cast<double2*>(hits + i);
+        dst[0] = make_double2(h.t, h.u);
+        double2 o2; o2.x = h.v;
+        const int2 pf = make_int2(prim, face);
+        memcpy(&o2.y, &pf, 8);
+        dst[1] = o2;
+    }
+};
+
+template <typename TriT, bool COUNT, int TPI>
+__global__ void __launch_bounds__(128) k_intersect_q(DevScene s, const LmcuRay* __restrict__ rays, uint32_t n,
+                                                     LmcuHit* __restrict__ hits, uint32_t* cursor,
+                                                     unsigned long long* counters, uint32_t* overflow) {
+    BatchIO io; io.s = s; io.rays = rays; io.hits = hits;
+    TraverseCounters tc; tc.nodes = tc.tris = 0;
+    trace_queue<false, COUNT, TPI, TriT>(s.nodes, scene_tris<TriT>(s), n, cursor, io, overflow, &tc);
+    if (COUNT) { atomicAdd(counters, (unsigned long long)tc.nodes); atomicAdd(counters + 1, (unsigned long long)tc.tris); }
+}
+
+struct ExtendIO {                      // pt extend: path queue in, float4 hit record out
+    const float4* ray_o; const float4* ray_d;
+    float4* hits;
+    __device__ __forceinline__ bool load(uint32_t i, RayD& r) const {
+        const float4 o = ray_o[i], d = ray_d[i];
+        r.o = d3(o.x, o.y, o.z); r.d = d3(d.x, d.y, d.z); r.tmin = o.w; r.tmax = d.w;
+        return true;
+    }
+    __device__ __forceinline__ void store(uint32_t i, const RayD&, const HitD& h) const {
+        hits[i] = make_float4((float)h.t, (float)h.u, (float)h.v, __int_as_float(h.tri));
+    }
+};
+
+template <typename TriT, bool COUNT, int TPI>
+__global__ void __launch_bounds__(128) k_pt_extend_q(DevScene s, PathQueue q, float4* hits, PtCounters* ctr, int cur) {
+    ExtendIO io; io.ray_o = q.ray_o; io.ray_d = q.ray_d; io.hits = hits;
+    TraverseCounters tc; tc.nodes = tc.tris = 0;
+    trace_queue<false, COUNT, TPI, TriT>(s.nodes, scene_tris<TriT>(s), ctr->count[cur], &ctr->fetch_extend, io, &ctr->overflow, &tc);
+    if (COUNT) { atomicAdd(&ctr->nodes_extend, (unsigned long long)tc.nodes); atomicAdd(&ctr->tris_extend, (unsigned long long)tc.tris); }
+}
+
+struct ShadowIO {                      // pt shadow: visible (include/lm/scene.h:343-364) => splat the NEE contribution
+    const float4* ray_o; const float4* ray_d; const float4* contrib;
+    float* film;
+    __device__ __forceinline__ bool load(uint32_t i, RayD& r) const {
+        const float4 o = ray_o[i], d = ray_d[i];
+        r.o = d3(o.x, o.y, o.z); r.d = d3(d.x, d.y, d.z); r.tmin = o.w; r.tmax = d.w;
+        return true;
+    }
+    __device__ __forceinline__ void store(uint32_t i, const RayD&, const HitD& h) const {
+        if (h.tri < 0) {
+            const float4 c = contrib[i];
+            float* px = film + (size_t)__float_as_uint(c.w) * 3;
+            atomicAdd(px + 0, c.x); atomicAdd(px + 1, c.y); atomicAdd(px + 2, c.z);
+        }
+    }
+};
+
+template <typename TriT, bool COUNT, int TPI>
+__global__ void __launch_bounds__(128) k_pt_shadow_q(DevScene s, ShadowQueue sq, float* film, PtCounters* ctr) {
+    const uint32_t n = ctr->shadow_count;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { ctr->rays += n; ctr->shadow_rays += n; }
+    ShadowIO io; io.ray_o = sq.ray_o; io.ray_d = sq.ray_d; io.contrib = sq.contrib; io.film = film;
+    TraverseCounters tc; tc.nodes = tc.tris = 0;
+    trace_queue<true, COUNT, TPI, TriT>(s.nodes, scene_tris<TriT>(s), n, &ctr->fetch_shadow, io, &ctr->overflow, &tc);
+    if (COUNT) { atomicAdd(&ctr->nodes_shadow, (unsigned long long)tc.nodes); atomicAdd(&ctr->tris_shadow, (unsigned long long)tc.tris); }
+}
+
 __global__ void k_scale(float* film, size_t n, float s) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) film[i] *= s;
 }
@@ -414,6 +501,8 @@ struct LmcuScene {
     DBuf<PtCounters> pt_ctr;
     uint32_t pt_capacity = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int trav = 1;                        // LMCU_TRAV: 0 = per-warp batches (bvh.cuh), 1/2 = warp-persistent queue (trace.cuh), 1 or 3 triangles per iteration
+    int ctas_per_sm = 8;                 // LMCU_CTAS: resident 128-thread CTAs per SM for the persistent traversal grids
 
     DevScene dev() const {
         DevScene d{};
@@ -450,6 +539,8 @@ int lmcu_scene_create(int device, LmcuScene** out) {
     s->stream = s->own_stream;
     CU(cudaEventCreate(&s->ev0));
     CU(cudaEventCreate(&s->ev1));
+    if (const char* e = getenv("LMCU_TRAV")) s->trav = atoi(e);
+    if (const char* e = getenv("LMCU_CTAS")) s->ctas_per_sm = std::max(1, atoi(e));
     CU(s->cursor.alloc(8));
     CU(s->flags.alloc(4));
     CU(cudaMemset(s->cursor.p, 0, 8 * sizeof(unsigned long long)));
@@ -621,18 +712,48 @@ int lmcu_accel_build(LmcuScene* s, const LmcuBuildOptions* opts, LmcuBuildStats*
 }
 
 // -- intersect ------------------------------------------------------------------------------------------
+// Picks the kernel instantiation for (triangle record, counters, triangles per iteration).
+#define LMCU_DISPATCH(KERNEL, FP32, COUNT, TPI, GRID, BLOCK, STREAM, ...)                                        \
+    do {                                                                                                         \
+        if (FP32) {                                                                                              \
+            if (COUNT) { if ((TPI) == 1) KERNEL<TriF32, true, 1><<<GRID, BLOCK, 0, STREAM>>>(__VA_ARGS__);       \
+                         else KERNEL<TriF32, true, 3><<<GRID, BLOCK, 0, STREAM>>>(__VA_ARGS__); }                \
+            else { if ((TPI) == 1) KERNEL<TriF32, false, 1><<<GRID, BLOCK, 0, STREAM>>>(__VA_ARGS__);            \
+                   else KERNEL<TriF32, false, 3><<<GRID, BLOCK, 0, STREAM>>>(__VA_ARGS__); }                     \
+        } else {                                                                                                 \
+            if (COUNT) { if ((TPI) == 1) KERNEL<TriF64, true, 1><<<GRID, BLOCK, 0, STREAM>>>(__VA_ARGS__);       \
+                         else KERNEL<TriF64, true, 3><<<GRID, BLOCK, 0, STREAM>>>(__VA_ARGS__); }                \
+            else { if ((TPI) == 1) KERNEL<TriF64, false, 1><<<GRID, BLOCK, 0, STREAM>>>(__VA_ARGS__);            \
+                   else KERNEL<TriF64, false, 3><<<GRID, BLOCK, 0, STREAM>>>(__VA_ARGS__); }                     \
+        }                                                                                                        \
+    } while (0)
+
 static int launch_intersect(LmcuScene* s, const LmcuRay* d_rays, int64_t n, LmcuHit* d_hits, bool count, cudaStream_t st) {
-    CU(cudaMemsetAsync(s->cursor.p, 0, 3 * sizeof(unsigned long long), st));
     const DevScene d = s->dev();
-    const unsigned blocks = (unsigned)std::min<int64_t>((n + 127) / 128, (int64_t)s->num_sms * 12);
-    if (s->fp32) {
-        if (count) k_intersect<TriF32, true><<<blocks, 128, 0, st>>>(d, d_rays, (unsigned long long)n, d_hits, s->cursor.p, s->cursor.p + 1, s->flags.p);
-        else k_intersect<TriF32, false><<<blocks, 128, 0, st>>>(d, d_rays, (unsigned long long)n, d_hits, s->cursor.p, s->cursor.p + 1, s->flags.p);
-    } else {
-        if (count) k_intersect<TriF64, true><<<blocks, 128, 0, st>>>(d, d_rays, (unsigned long long)n, d_hits, s->cursor.p, s->cursor.p + 1, s->flags.p);
-        else k_intersect<TriF64, false><<<blocks, 128, 0, st>>>(d, d_rays, (unsigned long long)n, d_hits, s->cursor.p, s->cursor.p + 1, s->flags.p);
+    if (s->trav == 0) {
+        CU(cudaMemsetAsync(s->cursor.p, 0, 3 * sizeof(unsigned long long), st));
+        const unsigned blocks = (unsigned)std::min<int64_t>((n + 127) / 128, (int64_t)s->num_sms * 12);
+        if (s->fp32) {
+            if (count) k_intersect<TriF32, true><<<blocks, 128, 0, st>>>(d, d_rays, (unsigned long long)n, d_hits, s->cursor.p, s->cursor.p + 1, s->flags.p);
+            else k_intersect<TriF32, false><<<blocks, 128, 0, st>>>(d, d_rays, (unsigned long long)n, d_hits, s->cursor.p, s->cursor.p + 1, s->flags.p);
+        } else {
+            if (count) k_intersect<TriF64, true><<<blocks, 128, 0, st>>>(d, d_rays, (unsigned long long)n, d_hits, s->cursor.p, s->cursor.p + 1, s->flags.p);
+            else k_intersect<TriF64, false><<<blocks, 128, 0, st>>>(d, d_rays, (unsigned long long)n, d_hits, s->cursor.p, s->cursor.p + 1, s->flags.p);
+        }
+        CU(cudaGetLastError());
+        return LMCU_OK;
     }
-    CU(cudaGetLastError());
+    if (count) CU(cudaMemsetAsync(s->cursor.p + 1, 0, 2 * sizeof(unsigned long long), st));
+    const int tpi = s->trav == 1 ? 1 : 3;
+    const int64_t kChunk = 1ll << 30;            // the queue cursor is 32-bit
+    for (int64_t off = 0; off < n; off += kChunk) {
+        const uint32_t m = (uint32_t)std::min<int64_t>(kChunk, n - off);
+        CU(cudaMemsetAsync(s->cursor.p, 0, sizeof(unsigned long long), st));
+        const unsigned blocks = (unsigned)std::min<int64_t>((m + 127) / 128, (int64_t)s->num_sms * s->ctas_per_sm);
+        LMCU_DISPATCH(k_intersect_q, s->fp32, count, tpi, blocks, 128, st, d, d_rays + off, m, d_hits + off,
+                      (uint32_t*)s->cursor.p, s->cursor.p + 1, s->flags.p);
+        CU(cudaGetLastError());
+    }
     return LMCU_OK;
 }
 
@@ -838,6 +959,8 @@ int lmcu_render_pt(LmcuScene* s, const LmcuRenderParams* p, float* film_rgb, Lmc
     CU(cudaMemsetAsync(s->pt_ctr.p, 0, sizeof(PtCounters), st));
     CU(cudaEventRecord(s->ev0, st));
     const DevScene d = s->dev();
+    const unsigned q_blocks = (unsigned)(s->num_sms * s->ctas_per_sm);
+    const int tpi = s->trav == 1 ? 1 : 3;
     const unsigned trav_blocks = (unsigned)s->num_sms * 12, shade_blocks = (unsigned)s->num_sms * 6, gen_blocks = (unsigned)s->num_sms * 4;
     int cur = 0;
     int64_t launches = 0;
@@ -856,22 +979,30 @@ int lmcu_render_pt(LmcuScene* s, const LmcuRenderParams* p, float* film_rgb, Lmc
             k_pt_generate<<<gen_blocks, 256, 0, st>>>(d, pp, q[cur], s->pt_ctr.p, cur);
             k_pt_advance<<<1, 1, 0, st>>>(pp, s->pt_ctr.p, cur);
             cudaEventRecord(ev[0], st);
-            if (s->fp32) {
-                if (count) k_pt_extend<TriF32, true><<<trav_blocks, 128, 0, st>>>(d, q[cur], s->hits.p, s->pt_ctr.p, cur);
-                else k_pt_extend<TriF32, false><<<trav_blocks, 128, 0, st>>>(d, q[cur], s->hits.p, s->pt_ctr.p, cur);
+            if (s->trav == 0) {
+                if (s->fp32) {
+                    if (count) k_pt_extend<TriF32, true><<<trav_blocks, 128, 0, st>>>(d, q[cur], s->hits.p, s->pt_ctr.p, cur);
+                    else k_pt_extend<TriF32, false><<<trav_blocks, 128, 0, st>>>(d, q[cur], s->hits.p, s->pt_ctr.p, cur);
+                } else {
+                    if (count) k_pt_extend<TriF64, true><<<trav_blocks, 128, 0, st>>>(d, q[cur], s->hits.p, s->pt_ctr.p, cur);
+                    else k_pt_extend<TriF64, false><<<trav_blocks, 128, 0, st>>>(d, q[cur], s->hits.p, s->pt_ctr.p, cur);
+                }
             } else {
-                if (count) k_pt_extend<TriF64, true><<<trav_blocks, 128, 0, st>>>(d, q[cur], s->hits.p, s->pt_ctr.p, cur);
-                else k_pt_extend<TriF64, false><<<trav_blocks, 128, 0, st>>>(d, q[cur], s->hits.p, s->pt_ctr.p, cur);
+                LMCU_DISPATCH(k_pt_extend_q, s->fp32, count, tpi, q_blocks, 128, st, d, q[cur], s->hits.p, s->pt_ctr.p, cur);
             }
             cudaEventRecord(ev[1], st);
             k_pt_shade<<<shade_blocks, 256, 0, st>>>(d, pp, q[cur], q[cur ^ 1], sq, s->hits.p, s->film.p, s->pt_ctr.p, cur);
             cudaEventRecord(ev[2], st);
-            if (s->fp32) {
-                if (count) k_pt_shadow<TriF32, true><<<trav_blocks, 128, 0, st>>>(d, sq, s->film.p, s->pt_ctr.p);
-                else k_pt_shadow<TriF32, false><<<trav_blocks, 128, 0, st>>>(d, sq, s->film.p, s->pt_ctr.p);
+            if (s->trav == 0) {
+                if (s->fp32) {
+                    if (count) k_pt_shadow<TriF32, true><<<trav_blocks, 128, 0, st>>>(d, sq, s->film.p, s->pt_ctr.p);
+                    else k_pt_shadow<TriF32, false><<<trav_blocks, 128, 0, st>>>(d, sq, s->film.p, s->pt_ctr.p);
+                } else {
+                    if (count) k_pt_shadow<TriF64, true><<<trav_blocks, 128, 0, st>>>(d, sq, s->film.p, s->pt_ctr.p);
+                    else k_pt_shadow<TriF64, false><<<trav_blocks, 128, 0, st>>>(d, sq, s->film.p, s->pt_ctr.p);
+                }
             } else {
-                if (count) k_pt_shadow<TriF64, true><<<trav_blocks, 128, 0, st>>>(d, sq, s->film.p, s->pt_ctr.p);
-                else k_pt_shadow<TriF64, false><<<trav_blocks, 128, 0, st>>>(d, sq, s->film.p, s->pt_ctr.p);
+                LMCU_DISPATCH(k_pt_shadow_q, s->fp32, count, tpi, q_blocks, 128, st, d, sq, s->film.p, s->pt_ctr.p);
             }
             cudaEventRecord(ev[3], st);
             cur ^= 1;

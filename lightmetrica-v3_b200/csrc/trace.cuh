@@ -1,0 +1,165 @@
+// trace.cuh — warp-persistent BVH traversal over a ray QUEUE with per-lane dynamic ray fetch.
+//
+// This is the form of bvh.cuh's traversal that the queue kernels (accel batches, pt extend, pt shadow)
+// run.  Same node test, same FP64 leaf test, same results; what changes is the scheduling:
+//
+//   * every lane owns one ray and runs a small state machine; one loop iteration = at most ONE
+//     wide-node step (for lanes with no pending triangles) followed by at most TRI_PER_ITER FP64
+//     triangle tests (for lanes with pending triangles), so node work and leaf work of different
+//     lanes proceed in lock-step instead of each lane's leaf loop stalling the other 31;
+//   * a lane whose ray terminates stores its result at once and goes idle; when the idle-lane debt
+//     of the warp crosses a threshold the warp leaves the traversal loop and the idle lanes claim
+//     new rays with ONE atomic on the queue cursor (ballot-ranked), so a long ray no longer holds
+//     31 finished lanes hostage until the end of the batch;
+//   * the two barycentric divisions u/|det|, v/|det| (accel_sahbvh.cpp:74) are applied once per
+//     ray, to the final closest hit, not to every intermediate candidate.  The quotients are the
+//     same IEEE operations on the same operands, so (t,u,v) stay bit-identical to accel::sahbvh.
+//
+// IO policy (template parameter), all device functions:
+//     bool load(uint32_t i, RayD& r)                       ray i of the queue
+//     void store(uint32_t i, const RayD& r, const HitD& h) result of ray i (h.tri < 0 = miss)
+#pragma once
+#include "bvh.cuh"
+
+namespace lmcu {
+
+#if defined(__CUDACC__)
+
+constexpr int kDynamicFetchThreshold = 4;     // idle lanes tolerated per iteration before re-fetching
+
+template <bool ANY, bool COUNT, int TRI_PER_ITER, typename TriT, typename IO>
+__device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, const TriT* __restrict__ tris,
+                                            uint32_t n, uint32_t* cursor, const IO& io, uint32_t* overflow,
+                                            TraverseCounters* ctr) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint4* nodes4 = reinterpret_cast<const uint4*>(nodes);
+    uint2 stack[kStackSize];
+
+    // per-lane traversal state
+    bool active = false;
+    bool exhausted = false;       // the cursor ran past n: nothing left to fetch
+    uint32_t idx = 0;
+    RayD r; r.o = d3(0, 0, 0); r.d = d3(0, 0, 1); r.tmin = 0; r.tmax = 0;
+    RayF f = make_rayf(r);
+    float tmin_dn = 0.f, tmax_up = 0.f;
+    double ht = 0, hu = 0, hv = 0, had = 1;   // closest candidate: t, raw u, raw v, |det|
+    int32_t htri = -1;
+    uint2 ngroup = make_uint2(0u, 0u), tgroup = make_uint2(0u, 0u);
+    int sp = 0;
+
+    while (true) {
+        // ---- fetch: idle lanes claim the next rays of the queue -------------------------------------
+        if (!exhausted) {
+            const uint32_t idle = __ballot_sync(0xffffffffu, !active);
+            if (idle) {
+                const int leader = __ffs(idle) - 1;
+                uint32_t base = 0;
+                if ((int)lane == leader) base = atomicAdd(cursor, (uint32_t)__popc(idle));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (base + (uint32_t)__popc(idle) >= n) exhausted = true;     // warp-uniform
+                if (!active) {
+                    idx = base + (uint32_t)__popc(idle & lt_mask);
+                    if (idx < n && io.load(idx, r)) {
+                        f = make_rayf(r);
+                        tmin_dn = f32_down(r.tmin);
+                        tmax_up = f32_up(r.tmax);
+                        ht = r.tmax; htri = -1;
+                        ngroup = make_uint2(0u, 0x80000000u);   // the root occupies virtual slot 7 of group 0
+                        tgroup = make_uint2(0u, 0u);
+                        sp = 0;
+                        active = true;
+                    }
+                }
+            }
+        }
+        if (!__any_sync(0xffffffffu, active)) {
+            if (exhausted) break;
+            continue;
+        }
+        // ---- traverse until the idle-lane debt says "re-fetch" ----------------------------------------
+        int lost = 0;
+        while (true) {
+            if (active) {
+                if (tgroup.y == 0u) {
+                    if (ngroup.y <= 0x00ffffffu) {
+                        if (sp > 0) ngroup = stack[--sp];
+                    }
+                    if (ngroup.y > 0x00ffffffu) {
+                        // ---- one wide-node step
+                        const uint32_t hits = ngroup.y;
+                        const uint32_t imask = hits & 0xffu;
+                        const int child_bit = bfind(hits);
+                        const uint32_t base = ngroup.x;
+                        ngroup.y &= ~(1u << child_bit);
+                        if (ngroup.y > 0x00ffffffu) {
+                            if (sp >= kStackSize) { atomicExch(overflow, 1u); sp = kStackSize - 1; }
+                            stack[sp++] = ngroup;
+                        }
+                        const uint32_t slot = (uint32_t)(child_bit - 24) ^ (f.octinv4 & 0xffu);
+                        const uint32_t ni = base + popc(imask & ~(0xffffffffu << slot));
+                        const uint4 n0 = __ldg(nodes4 + ni * 5 + 0), n1 = __ldg(nodes4 + ni * 5 + 1),
+                                    n2 = __ldg(nodes4 + ni * 5 + 2), n3 = __ldg(nodes4 + ni * 5 + 3),
+                                    n4 = __ldg(nodes4 + ni * 5 + 4);
+                        if (COUNT) ctr->nodes++;
+                        const uint32_t hm = node_hitmask(n0, n1, n2, n3, n4, f, tmin_dn, tmax_up);
+                        ngroup.x = n1.x;
+                        ngroup.y = (hm & 0xff000000u) | (n0.w >> 24);
+                        tgroup.x = n1.y;
+                        tgroup.y = hm & 0x00ffffffu;
+                    } else {
+                        // ---- nothing left: this ray is done
+                        HitD h;
+                        h.t = ht; h.tri = htri;
+                        h.u = htri >= 0 ? divrn(hu, had) : 0.0;
+                        h.v = htri >= 0 ? divrn(hv, had) : 0.0;
+                        io.store(idx, r, h);
+                        active = false;
+                    }
+                }
+                // ---- leaf work: FP64 Möller–Trumbore, reference operation order (accel_sahbvh.cpp:58-75)
+#pragma unroll 1
+                for (int k = 0; k < TRI_PER_ITER && active && tgroup.y != 0u; k++) {
+                    const int ti = bfind(tgroup.y);
+                    tgroup.y &= ~(1u << ti);
+                    const uint32_t tri = tgroup.x + (uint32_t)ti;
+                    D3 p1, p2, p3;
+                    load_tri(tris, tri, p1, p2, p3);
+                    if (COUNT) ctr->tris++;
+                    const D3 e1 = dsub3(p2, p1), e2 = dsub3(p3, p1);
+                    const D3 p = dcross(r.d, e2);
+                    const D3 tv = dsub3(r.o, p1);
+                    const D3 q = dcross(tv, e1);
+                    const double d = ddot(e1, p);
+                    const double ad = fabs(d);
+                    const double s = copysign(1.0, d);
+                    const double u = mulrn(ddot(tv, p), s);
+                    const double v = mulrn(ddot(r.d, q), s);
+                    if (!(ad < 1e-8 || u < 0.0 || v < 0.0 || addrn(u, v) > ad)) {
+                        const double t = divrn(ddot(e2, q), d);
+                        if (!(t < r.tmin || ht < t)) {          // inclusive bounds; a later equal-t triangle wins
+                            ht = t; hu = u; hv = v; had = ad; htri = (int32_t)tri;
+                            tmax_up = f32_up(t);
+                            if (ANY) {
+                                HitD h;
+                                h.t = t; h.tri = htri; h.u = divrn(u, ad); h.v = divrn(v, ad);
+                                io.store(idx, r, h);
+                                active = false;
+                            }
+                        }
+                    }
+                }
+            }
+            const uint32_t act = __ballot_sync(0xffffffffu, active);
+            if (act == 0u) break;
+            if (!exhausted) {
+                lost += 32 - __popc(act) - kDynamicFetchThreshold;
+                if (lost >= 0) break;
+            }
+        }
+    }
+}
+
+#endif  // __CUDACC__
+
+}  // namespace lmcu
