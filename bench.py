@@ -135,7 +135,8 @@ def run_ours(args):
     spp = args.spp
     sb = scenes.cornell_spheres(64)
     sc = lmcu.Scene(sb, device=local_rank)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=local_rank)    # handle 0 (legacy default stream) would mean "the scene's own stream"
+    torch.cuda.set_stream(stream)                    # NCCL reduce + film ops follow on the same stream
     sc.set_stream(stream.cuda_stream)
     npix = W * H
     film_ptr = None

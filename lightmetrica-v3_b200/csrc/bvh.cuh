@@ -130,6 +130,26 @@ LMCU_HD RayF make_rayf(const RayD& r) {
     return f;
 }
 
+// Byte j of `w` as the float 32768 + byte, built with ONE byte permute and no integer->float
+// conversion: the bytes land in mantissa bits 8..15 of 0x47000000 (= 2^15, ulp 2^-8).  I2F.U8 runs on
+// the XU pipe at 16 lanes/clk/SM on sm_100a — the first ncu capture of this kernel showed the XU pipe
+// 60 % busy with the 48 conversions per node while the FMA pipe idled at 13 %
+// (profiles/r01_ncu_summary_v2.md) — PRMT runs on the ALU pipe at 64 lanes/clk/SM.
+#if defined(__CUDACC__)
+// Lives in the constant bank so that ptxas keeps the SELECTOR as PRMT's immediate and reads this operand
+// from c[][] (with a literal here it spends one extra IMAD.MOV per permute to materialise the selector).
+__constant__ uint32_t kBiasBits = 0x47000000u;
+#endif
+template <int J>
+LMCU_HD float byte_as_biased_float(uint32_t w) {
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(__byte_perm(w, kBiasBits, 0x7404u | ((uint32_t)J << 4)));
+#else
+    return u2f(0x47000000u | (((w >> (8 * J)) & 0xffu) << 8));
+#endif
+}
+constexpr float kByteBias = 32768.0f;
+
 // Intersects the 8 quantised child boxes of one node; returns the CWBVH hit mask
 // (bits 31..24: internal children in traversal priority, bits 23..0: triangles).
 LMCU_HD uint32_t node_hitmask(const uint4 n0, const uint4 n1, const uint4 n2, const uint4 n3, const uint4 n4,
@@ -140,15 +160,19 @@ LMCU_HD uint32_t node_hitmask(const uint4 n0, const uint4 n1, const uint4 n2, co
     const float ax = sx * f.idx, ay = sy * f.idy, az = sz * f.idz;
     const float rx = px - f.ox, ry = py - f.oy, rz = pz - f.oz;
     const float bx = rx * f.idx, by = ry * f.idy, bz = rz * f.idz;
+    // Slab planes are evaluated as t = (32768 + q) * a + (b - 32768 a) with q the quantised coordinate.
     // Padding that covers (a) rounding o,d from FP64 to FP32, (b) the FP32 rounding of the slab
-    // arithmetic including cancellation in (p - o): 8 ulp32 of the largest magnitude involved.
+    // arithmetic including cancellation in (p - o): 8 ulp32 of the largest magnitude involved, where
+    // the grid term counts the 255-step extent plus the 32768-step bias whose rounding enters b' once
+    // (2^-24 * 32768 |a| <= 8448 * 2^-21 |a| with room to spare).
     const float kPad = 4.76837158e-7f;   // 2^-21
-    const float slx = (fabsf(rx) + 256.0f * sx + f.aox) * kPad * fabsf(f.idx);
-    const float sly = (fabsf(ry) + 256.0f * sy + f.aoy) * kPad * fabsf(f.idy);
-    const float slz = (fabsf(rz) + 256.0f * sz + f.aoz) * kPad * fabsf(f.idz);
-    const float bnx = bx - slx, bfx = bx + slx;
-    const float bny = by - sly, bfy = by + sly;
-    const float bnz = bz - slz, bfz = bz + slz;
+    const float slx = (fabsf(rx) + 8448.0f * sx + f.aox) * kPad * fabsf(f.idx);
+    const float sly = (fabsf(ry) + 8448.0f * sy + f.aoy) * kPad * fabsf(f.idy);
+    const float slz = (fabsf(rz) + 8448.0f * sz + f.aoz) * kPad * fabsf(f.idz);
+    const float cx = fmaf(-kByteBias, ax, bx), cy = fmaf(-kByteBias, ay, by), cz = fmaf(-kByteBias, az, bz);
+    const float bnx = cx - slx, bfx = cx + slx;
+    const float bny = cy - sly, bfy = cy + sly;
+    const float bnz = cz - slz, bfz = cz + slz;
     const bool negx = f.idx < 0.f, negy = f.idy < 0.f, negz = f.idz < 0.f;
     uint32_t hitmask = 0;
 #pragma unroll
@@ -163,21 +187,22 @@ LMCU_HD uint32_t node_hitmask(const uint4 n0, const uint4 n1, const uint4 n2, co
         const uint32_t nx4 = negx ? qhx : qlx, fx4 = negx ? qlx : qhx;
         const uint32_t ny4 = negy ? qhy : qly, fy4 = negy ? qly : qhy;
         const uint32_t nz4 = negz ? qhz : qlz, fz4 = negz ? qlz : qhz;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int sh = 8 * j;
-            const float tnx = fmaf((float)((nx4 >> sh) & 0xffu), ax, bnx);
-            const float tny = fmaf((float)((ny4 >> sh) & 0xffu), ay, bny);
-            const float tnz = fmaf((float)((nz4 >> sh) & 0xffu), az, bnz);
-            const float tfx = fmaf((float)((fx4 >> sh) & 0xffu), ax, bfx);
-            const float tfy = fmaf((float)((fy4 >> sh) & 0xffu), ay, bfy);
-            const float tfz = fmaf((float)((fz4 >> sh) & 0xffu), az, bfz);
-            const float cmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin_dn));
-            const float cmax = fminf(fminf(tfx, tfy), fminf(tfz, tmax_up));
-            if (cmin <= cmax) {
-                hitmask |= ((child_bits4 >> sh) & 0xffu) << ((bit_index4 >> sh) & 0xffu);
-            }
+#define LMCU_CHILD(J)                                                                                   \
+        {                                                                                               \
+            const float tnx = fmaf(byte_as_biased_float<J>(nx4), ax, bnx);                              \
+            const float tny = fmaf(byte_as_biased_float<J>(ny4), ay, bny);                              \
+            const float tnz = fmaf(byte_as_biased_float<J>(nz4), az, bnz);                              \
+            const float tfx = fmaf(byte_as_biased_float<J>(fx4), ax, bfx);                              \
+            const float tfy = fmaf(byte_as_biased_float<J>(fy4), ay, bfy);                              \
+            const float tfz = fmaf(byte_as_biased_float<J>(fz4), az, bfz);                              \
+            const float cmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin_dn));                             \
+            const float cmax = fminf(fminf(tfx, tfy), fminf(tfz, tmax_up));                             \
+            if (cmin <= cmax) {                                                                         \
+                hitmask |= ((child_bits4 >> (8 * J)) & 0xffu) << ((bit_index4 >> (8 * J)) & 0xffu);     \
+            }                                                                                           \
         }
+        LMCU_CHILD(0) LMCU_CHILD(1) LMCU_CHILD(2) LMCU_CHILD(3)
+#undef LMCU_CHILD
     }
     return hitmask;
 }

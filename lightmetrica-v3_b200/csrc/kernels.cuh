@@ -19,7 +19,8 @@ struct DevScene {
     const EmitTri* emit;
     const float* cdf;
     const float4* env_tex;
-    int32_t num_prims, num_lights, env_light, pad_;
+    int32_t num_prims, num_lights, env_light;
+    int32_t fetch_threshold;    // trace.cuh: idle lanes tolerated per iteration before the warp re-fetches
     uint32_t num_tris, pad2_;
     CameraDev cam;
 };

@@ -17,6 +17,10 @@
 #include "../../include/lmcu.h"
 #include "kernels.cuh"
 #include "trace.cuh"
+
+#ifndef LMCU_MINB
+#define LMCU_MINB 5      // resident 128-thread CTAs per SM the queue kernels are compiled for (register budget)
+#endif
 #include "prep.hpp"
 
 using namespace lmcu;
@@ -303,9 +307,39 @@ __device__ __forceinline__ uint32_t block_compact(bool pred, uint32_t* global_co
     return pos;
 }
 
+// Two compactions in one pass (next-path queue and shadow queue): the per-warp counts travel packed
+// 16+16 bits through ONE shared-memory scan, so a shade iteration costs 3 barriers instead of 6.
+__device__ __forceinline__ void block_compact2(bool p0, bool p1, uint32_t* counter0, uint32_t* counter1,
+                                               uint32_t* smem /* [34] */, uint32_t& pos0, uint32_t& pos1) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const uint32_t b0 = __ballot_sync(0xffffffffu, p0), b1 = __ballot_sync(0xffffffffu, p1);
+    if (lane == 0) smem[warp] = (uint32_t)__popc(b0) | ((uint32_t)__popc(b1) << 16);
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t v = lane < nwarps ? smem[lane] : 0u;
+        uint32_t incl = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= (uint32_t)o) incl += t;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        if (lane == 0) {
+            smem[32] = (total & 0xffffu) ? atomicAdd(counter0, total & 0xffffu) : 0u;
+            smem[33] = (total >> 16) ? atomicAdd(counter1, total >> 16) : 0u;
+        }
+        __syncwarp();
+        if (lane < nwarps) smem[lane] = incl - v;
+    }
+    __syncthreads();
+    const uint32_t ex = smem[warp], lt = (1u << lane) - 1u;
+    pos0 = smem[32] + (ex & 0xffffu) + (uint32_t)__popc(b0 & lt);
+    pos1 = smem[33] + (ex >> 16) + (uint32_t)__popc(b1 & lt);
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(256) k_pt_shade(DevScene s, PtParams p, PathQueue qin, PathQueue qout, ShadowQueue sq,
                                                   const float4* hits, float* film, PtCounters* ctr, int cur) {
-    __shared__ uint32_t smem[33];
+    __shared__ uint32_t smem[34];
     const uint32_t n = ctr->count[cur];
     for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
         const uint32_t i = base + threadIdx.x;
@@ -318,12 +352,12 @@ __global__ void __launch_bounds__(256) k_pt_shade(DevScene s, PtParams p, PathQu
                 atomicAdd(px + 0, o.emit.x); atomicAdd(px + 1, o.emit.y); atomicAdd(px + 2, o.emit.z);
             }
         }
-        const uint32_t pos = block_compact(o.alive, &ctr->count[cur ^ 1], smem);
+        uint32_t pos, spos;
+        block_compact2(o.alive, o.shadow, &ctr->count[cur ^ 1], &ctr->shadow_count, smem, pos, spos);
         if (o.alive) {
             qout.ray_o[pos] = o.o; qout.ray_d[pos] = o.d; qout.thr_pix[pos] = o.thr_pix; qout.aux[pos] = o.aux;
             qout.info[pos] = o.info;
         }
-        const uint32_t spos = block_compact(o.shadow, &ctr->shadow_count, smem);
         if (o.shadow) {
             sq.ray_o[spos] = o.sh_o; sq.ray_d[spos] = o.sh_d; sq.contrib[spos] = o.sh_c;
         }
@@ -356,6 +390,18 @@ __global__ void __launch_bounds__(128) k_pt_shadow(DevScene s, ShadowQueue sq, f
 
 
 // -- queue kernels on the warp-persistent traversal (trace.cuh) -----------------------------------------
+
+// MODE selects the scheduling of the queue traversal (tuning switch LMCU_TRAV; results are identical):
+//   1, 2  trace_queue with 1 / 3 triangle tests per iteration      3, 4, 5  trace_queue_pp with (TRI_HI, TRI_LO) = (16,8) / (12,4) / (24,12)
+template <bool ANY, bool COUNT, int MODE, typename TriT, typename IO>
+__device__ __forceinline__ void run_trace(const DevScene& s, uint32_t n, uint32_t* cursor, const IO& io, uint32_t* overflow,
+                                          TraverseCounters* tc) {
+    if constexpr (MODE == 1) trace_queue<ANY, COUNT, 1, TriT>(s.nodes, scene_tris<TriT>(s), n, cursor, io, overflow, tc, s.fetch_threshold);
+    else if constexpr (MODE == 2) trace_queue<ANY, COUNT, 3, TriT>(s.nodes, scene_tris<TriT>(s), n, cursor, io, overflow, tc, s.fetch_threshold);
+    else if constexpr (MODE == 3) trace_queue_pp<ANY, COUNT, 16, 8, TriT>(s.nodes, scene_tris<TriT>(s), n, cursor, io, overflow, tc, s.fetch_threshold);
+    else if constexpr (MODE == 4) trace_queue_pp<ANY, COUNT, 12, 4, TriT>(s.nodes, scene_tris<TriT>(s), n, cursor, io, overflow, tc, s.fetch_threshold);
+    else trace_queue_pp<ANY, COUNT, 24, 12, TriT>(s.nodes, scene_tris<TriT>(s), n, cursor, io, overflow, tc, s.fetch_threshold);
+}
 struct BatchIO {                       // accel batches: LmcuRay in, LmcuHit out (include/lmcu.h)
     DevScene s;
     const LmcuRay* rays;
@@ -383,12 +429,12 @@ struct BatchIO {                       // accel batches: LmcuRay in, LmcuHit out
 };
 
 template <typename TriT, bool COUNT, int TPI>
-__global__ void __launch_bounds__(128) k_intersect_q(DevScene s, const LmcuRay* __restrict__ rays, uint32_t n,
+__global__ void __launch_bounds__(128, LMCU_MINB) k_intersect_q(DevScene s, const LmcuRay* __restrict__ rays, uint32_t n,
                                                      LmcuHit* __restrict__ hits, uint32_t* cursor,
                                                      unsigned long long* counters, uint32_t* overflow) {
     BatchIO io; io.s = s; io.rays = rays; io.hits = hits;
     TraverseCounters tc; tc.nodes = tc.tris = 0;
-    trace_queue<false, COUNT, TPI, TriT>(s.nodes, scene_tris<TriT>(s), n, cursor, io, overflow, &tc);
+    run_trace<false, COUNT, TPI, TriT>(s, n, cursor, io, overflow, &tc);
     if (COUNT) { atomicAdd(counters, (unsigned long long)tc.nodes); atomicAdd(counters + 1, (unsigned long long)tc.tris); }
 }
 
@@ -406,10 +452,10 @@ struct ExtendIO {                      // pt extend: path queue in, float4 hit r
 };
 
 template <typename TriT, bool COUNT, int TPI>
-__global__ void __launch_bounds__(128) k_pt_extend_q(DevScene s, PathQueue q, float4* hits, PtCounters* ctr, int cur) {
+__global__ void __launch_bounds__(128, LMCU_MINB) k_pt_extend_q(DevScene s, PathQueue q, float4* hits, PtCounters* ctr, int cur) {
     ExtendIO io; io.ray_o = q.ray_o; io.ray_d = q.ray_d; io.hits = hits;
     TraverseCounters tc; tc.nodes = tc.tris = 0;
-    trace_queue<false, COUNT, TPI, TriT>(s.nodes, scene_tris<TriT>(s), ctr->count[cur], &ctr->fetch_extend, io, &ctr->overflow, &tc);
+    run_trace<false, COUNT, TPI, TriT>(s, ctr->count[cur], &ctr->fetch_extend, io, &ctr->overflow, &tc);
     if (COUNT) { atomicAdd(&ctr->nodes_extend, (unsigned long long)tc.nodes); atomicAdd(&ctr->tris_extend, (unsigned long long)tc.tris); }
 }
 
@@ -431,12 +477,12 @@ struct ShadowIO {                      // pt shadow: visible (include/lm/scene.h
 };
 
 template <typename TriT, bool COUNT, int TPI>
-__global__ void __launch_bounds__(128) k_pt_shadow_q(DevScene s, ShadowQueue sq, float* film, PtCounters* ctr) {
+__global__ void __launch_bounds__(128, LMCU_MINB) k_pt_shadow_q(DevScene s, ShadowQueue sq, float* film, PtCounters* ctr) {
     const uint32_t n = ctr->shadow_count;
     if (blockIdx.x == 0 && threadIdx.x == 0) { ctr->rays += n; ctr->shadow_rays += n; }
     ShadowIO io; io.ray_o = sq.ray_o; io.ray_d = sq.ray_d; io.contrib = sq.contrib; io.film = film;
     TraverseCounters tc; tc.nodes = tc.tris = 0;
-    trace_queue<true, COUNT, TPI, TriT>(s.nodes, scene_tris<TriT>(s), n, &ctr->fetch_shadow, io, &ctr->overflow, &tc);
+    run_trace<true, COUNT, TPI, TriT>(s, n, &ctr->fetch_shadow, io, &ctr->overflow, &tc);
     if (COUNT) { atomicAdd(&ctr->nodes_shadow, (unsigned long long)tc.nodes); atomicAdd(&ctr->tris_shadow, (unsigned long long)tc.tris); }
 }
 
@@ -502,13 +548,14 @@ struct LmcuScene {
     uint32_t pt_capacity = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int trav = 1;                        // LMCU_TRAV: 0 = per-warp batches (bvh.cuh), 1/2 = warp-persistent queue (trace.cuh), 1 or 3 triangles per iteration
-    int ctas_per_sm = 8;                 // LMCU_CTAS: resident 128-thread CTAs per SM for the persistent traversal grids
+    int fetch_threshold = 8;             // LMCU_FETCH
+    int ctas_per_sm = LMCU_MINB;                 // LMCU_CTAS: resident 128-thread CTAs per SM for the persistent traversal grids
 
     DevScene dev() const {
         DevScene d{};
         d.nodes = nodes.p; d.t32 = t32.p; d.t64 = t64.p; d.shade = shade.p; d.prims = prims.p; d.mats = mats.p;
         d.lights = lights.p; d.emit = emit.p; d.cdf = cdf.p; d.env_tex = nullptr;
-        d.num_prims = num_prims; d.num_lights = num_lights; d.env_light = env_light; d.num_tris = nt; d.cam = cam;
+        d.num_prims = num_prims; d.num_lights = num_lights; d.env_light = env_light; d.fetch_threshold = fetch_threshold; d.num_tris = nt; d.cam = cam;
         return d;
     }
 };
@@ -540,6 +587,7 @@ int lmcu_scene_create(int device, LmcuScene** out) {
     CU(cudaEventCreate(&s->ev0));
     CU(cudaEventCreate(&s->ev1));
     if (const char* e = getenv("LMCU_TRAV")) s->trav = atoi(e);
+    if (const char* e = getenv("LMCU_FETCH")) s->fetch_threshold = atoi(e);
     if (const char* e = getenv("LMCU_CTAS")) s->ctas_per_sm = std::max(1, atoi(e));
     CU(s->cursor.alloc(8));
     CU(s->flags.alloc(4));
@@ -612,6 +660,7 @@ int lmcu_accel_build(LmcuScene* s, const LmcuBuildOptions* opts, LmcuBuildStats*
     CU(cudaSetDevice(s->device));
     const uint32_t nt = s->nt;
     int max_leaf = opts && opts->max_leaf_tris ? opts->max_leaf_tris : 3;
+    if (const char* e = getenv("LMCU_LEAF")) max_leaf = atoi(e);      // tuning only
     if (max_leaf < 1 || max_leaf > 3) return fail(LMCU_ERR_INVALID_ARGUMENT, "max_leaf_tris must be in 1..3");
     cudaStream_t st = s->stream;
     CU(cudaEventRecord(s->ev0, st));
@@ -713,18 +762,24 @@ int lmcu_accel_build(LmcuScene* s, const LmcuBuildOptions* opts, LmcuBuildStats*
 
 // -- intersect ------------------------------------------------------------------------------------------
 // Picks the kernel instantiation for (triangle record, counters, triangles per iteration).
-#define LMCU_DISPATCH(KERNEL, FP32, COUNT, TPI, GRID, BLOCK, STREAM, ...)                                        \
+#define LMCU_DISPATCH_M(KERNEL, TRI, COUNT, MODE, GRID, BLOCK, STREAM, ...)                                      \
+    do {                                                                                                         \
+        switch (MODE) {                                                                                          \
+        case 1: KERNEL<TRI, COUNT, 1><<<GRID, BLOCK, 0, STREAM>>>(__VA_ARGS__); break;                           \
+        case 2: KERNEL<TRI, COUNT, 2><<<GRID, BLOCK, 0, STREAM>>>(__VA_ARGS__); break;                           \
+        case 3: KERNEL<TRI, COUNT, 3><<<GRID, BLOCK, 0, STREAM>>>(__VA_ARGS__); break;                           \
+        case 4: KERNEL<TRI, COUNT, 4><<<GRID, BLOCK, 0, STREAM>>>(__VA_ARGS__); break;                           \
+        default: KERNEL<TRI, COUNT, 5><<<GRID, BLOCK, 0, STREAM>>>(__VA_ARGS__); break;                          \
+        }                                                                                                        \
+    } while (0)
+#define LMCU_DISPATCH(KERNEL, FP32, COUNT, MODE, GRID, BLOCK, STREAM, ...)                                       \
     do {                                                                                                         \
         if (FP32) {                                                                                              \
-            if (COUNT) { if ((TPI) == 1) KERNEL<TriF32, true, 1><<<GRID, BLOCK, 0, STREAM>>>(__VA_ARGS__);       \
-                         else KERNEL<TriF32, true, 3><<<GRID, BLOCK, 0, STREAM>>>(__VA_ARGS__); }                \
-            else { if ((TPI) == 1) KERNEL<TriF32, false, 1><<<GRID, BLOCK, 0, STREAM>>>(__VA_ARGS__);            \
-                   else KERNEL<TriF32, false, 3><<<GRID, BLOCK, 0, STREAM>>>(__VA_ARGS__); }                     \
+            if (COUNT) LMCU_DISPATCH_M(KERNEL, TriF32, true, MODE, GRID, BLOCK, STREAM, __VA_ARGS__);            \
+            else LMCU_DISPATCH_M(KERNEL, TriF32, false, MODE, GRID, BLOCK, STREAM, __VA_ARGS__);                 \
         } else {                                                                                                 \
-            if (COUNT) { if ((TPI) == 1) KERNEL<TriF64, true, 1><<<GRID, BLOCK, 0, STREAM>>>(__VA_ARGS__);       \
-                         else KERNEL<TriF64, true, 3><<<GRID, BLOCK, 0, STREAM>>>(__VA_ARGS__); }                \
-            else { if ((TPI) == 1) KERNEL<TriF64, false, 1><<<GRID, BLOCK, 0, STREAM>>>(__VA_ARGS__);            \
-                   else KERNEL<TriF64, false, 3><<<GRID, BLOCK, 0, STREAM>>>(__VA_ARGS__); }                     \
+            if (COUNT) LMCU_DISPATCH_M(KERNEL, TriF64, true, MODE, GRID, BLOCK, STREAM, __VA_ARGS__);            \
+            else LMCU_DISPATCH_M(KERNEL, TriF64, false, MODE, GRID, BLOCK, STREAM, __VA_ARGS__);                 \
         }                                                                                                        \
     } while (0)
 
@@ -744,7 +799,7 @@ static int launch_intersect(LmcuScene* s, const LmcuRay* d_rays, int64_t n, Lmcu
         return LMCU_OK;
     }
     if (count) CU(cudaMemsetAsync(s->cursor.p + 1, 0, 2 * sizeof(unsigned long long), st));
-    const int tpi = s->trav == 1 ? 1 : 3;
+    const int tpi = s->trav;
     const int64_t kChunk = 1ll << 30;            // the queue cursor is 32-bit
     for (int64_t off = 0; off < n; off += kChunk) {
         const uint32_t m = (uint32_t)std::min<int64_t>(kChunk, n - off);
@@ -938,7 +993,7 @@ int lmcu_render_pt(LmcuScene* s, const LmcuRenderParams* p, float* film_rgb, Lmc
     CU(cudaSetDevice(s->device));
     rc = ensure_film(s, p->width, p->height);
     if (rc) return rc;
-    uint32_t capacity = 1u << 20;
+    uint32_t capacity = 1u << 23;        // 8 Mi paths in flight: 72 B x 2 queues + 48 B shadow + 16 B hit = 1.7 GB
     if (const char* e = getenv("LMCU_PT_POOL")) capacity = (uint32_t)std::max(1024l, atol(e));
     rc = ensure_pt_pools(s, capacity);
     if (rc) return rc;
@@ -960,7 +1015,7 @@ int lmcu_render_pt(LmcuScene* s, const LmcuRenderParams* p, float* film_rgb, Lmc
     CU(cudaEventRecord(s->ev0, st));
     const DevScene d = s->dev();
     const unsigned q_blocks = (unsigned)(s->num_sms * s->ctas_per_sm);
-    const int tpi = s->trav == 1 ? 1 : 3;
+    const int tpi = s->trav;
     const unsigned trav_blocks = (unsigned)s->num_sms * 12, shade_blocks = (unsigned)s->num_sms * 6, gen_blocks = (unsigned)s->num_sms * 4;
     int cur = 0;
     int64_t launches = 0;

@@ -15,7 +15,7 @@ from . import abi
 from .scenes import HIT_DTYPE, RAY_DTYPE
 
 _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(_PKG, "liblmcu.so")
+LIB_PATH = os.environ.get("LMCU_LIB") or os.path.join(_PKG, "liblmcu.so")   # LMCU_LIB: tuning builds only
 _LIB = None
 
 EXPORTS = [

@@ -33,7 +33,8 @@ def tri_normals(sb):
 def device_batch(sc, rays, reps=3):
     d_rays = torch.from_numpy(rays.view(np.float64).reshape(-1, 8)).cuda()
     d_hits = torch.empty((len(rays), 4), dtype=torch.float64, device="cuda")
-    st = torch.cuda.current_stream()
+    st = torch.cuda.Stream()             # a real stream: handle 0 (the legacy default stream) means "the scene's own stream"
+    st.wait_stream(torch.cuda.current_stream())
     sc.set_stream(st.cuda_stream)
     best = 1e9
     for _ in range(reps + 1):
