@@ -62,6 +62,18 @@ LMCU_HD SurfPoint surface_point(const DevScene& s, uint32_t tri, float u, float 
     return sp;
 }
 
+// Radiance of the environment light seen along direction d (scene -> sky): envconst Le or the image lookup
+LMCU_HD F3 light_env_radiance(const DevScene& s, const LightDev& l, F3 d) {
+    return l.type == LIGHT_ENV ? env_eval(l, s.env_tex, d) : f3(l.Ke[0], l.Ke[1], l.Ke[2]);
+}
+// pdf_direct (projected solid angle, without the light-selection probability) of sampling direction d from a
+// surface point with shading normal n
+LMCU_HD float light_env_pdf(const DevScene& s, const LightDev& l, F3 n, F3 d) {
+    if (l.type == LIGHT_ENV) return env_pdf_direct(l, s.cdf, n, d);
+    const float c = fabsf(dot(n, d));
+    return c == 0.f ? 0.f : (1.0f / (4.0f * kPiF)) / c;             // light_envconst.cpp:116-119
+}
+
 // -- raycast (src/renderer/renderer_raycast.cpp:70-98) -----------------------------------------------------
 struct RaycastParams {
     int32_t width, height;
@@ -81,7 +93,8 @@ LMCU_HD void raycast_pixel(const DevScene& s, const RaycastParams& p, int x, int
         if (s.env_light >= 0) {
             // miss with tmax = Inf and an environment light -> light endpoint (src/scene.cpp:321-331)
             const LightDev& l = s.lights[s.env_light];
-            c = p.visualize_normal ? f3s(0.f) : f3(l.Ke[0], l.Ke[1], l.Ke[2]);
+            const F3 dir = f3((float)r.d.x, (float)r.d.y, (float)r.d.z);
+            c = p.visualize_normal ? f3s(0.f) : light_env_radiance(s, l, dir);
         } else {
             c = f3(p.bg[0], p.bg[1], p.bg[2]);
         }
@@ -256,11 +269,10 @@ LMCU_HD ShadeOut pt_shade_body(const DevScene& s, const PtParams& p, float4 ro, 
             float mis = 1.f;
             if (p.sampling_mode == 2 && prev_nee) {
                 const F3 np = f3(aux.y, aux.z, aux.w);
-                const float c = fabsf(dot(np, rdir));
-                const float pl = c == 0.f ? 0.f : inv_nl * (1.0f / (4.0f * kPiF)) / c;   // light_envconst.cpp:116-119
+                const float pl = inv_nl * light_env_pdf(s, l, np, rdir);
                 mis = (aux.x == 0.f && pl == 0.f) ? 0.f : aux.x / (aux.x + pl);
             }
-            out.emit = thr * f3(l.Ke[0], l.Ke[1], l.Ke[2]) * mis;
+            out.emit = thr * light_env_radiance(s, l, rdir) * mis;
         }
         return out;
     }
@@ -304,6 +316,7 @@ LMCU_HD ShadeOut pt_shade_body(const DevScene& s, const PtParams& p, float4 ro, 
         li = li < 0 ? 0 : (li > s.num_lights - 1 ? s.num_lights - 1 : li);  // src/scene.cpp:374-387
         const LightDev& l = s.lights[li];
         F3 wo;              // direction from the vertex toward the light
+        F3 Le = f3(l.Ke[0], l.Ke[1], l.Ke[2]);
         float pl = 0.f;     // pdf_direct, projected SA, without the selection probability
         float tmax = 0.f;
         if (l.type == LIGHT_AREA) {                                         // light_area.cpp:47-59,148-178
@@ -322,12 +335,11 @@ LMCU_HD ShadeOut pt_shade_body(const DevScene& s, const PtParams& p, float4 ro, 
                 pl = G == 0.f ? 0.f : l.inv_area_j / G;
             }
             tmax = dist * (1.0f - (float)kEps);                             // include/lm/scene.h:349-356
-        } else {                                                            // light_envconst.cpp:100-119
+        } else {                                                            // light_envconst.cpp:100-119, light_env.cpp:139-162
             const R4 u2 = rand4(p.seed, pixel, p.sample_offset + sample, num_verts * 4u + 2u);
-            const F3 wl = sample_uniform_sphere(u2.x, u2.y);
-            wo = -wl;
-            const float c = fabsf(dot(sp.n, wo));
-            pl = c == 0.f ? 0.f : (1.0f / (4.0f * kPiF)) / c;
+            wo = l.type == LIGHT_ENV ? env_sample_dir(l, s.cdf, u2) : -sample_uniform_sphere(u2.x, u2.y);
+            pl = light_env_pdf(s, l, sp.n, wo);
+            Le = light_env_radiance(s, l, wo);
             tmax = (float)(kInf - 1.0);
         }
         if (pl > 0.f) {
@@ -339,7 +351,7 @@ LMCU_HD ShadeOut pt_shade_body(const DevScene& s, const PtParams& p, float4 ro, 
                     const float p_bsdf = mat_pdf(mat, sp.n, wi, wo);
                     mis = (p_light == 0.f && p_bsdf == 0.f) ? 0.f : p_light / (p_light + p_bsdf);   // math.h:697-702
                 }
-                const F3 C = thr * fs * f3(l.Ke[0], l.Ke[1], l.Ke[2]) * (mis / (pl * inv_nl));
+                const F3 C = thr * fs * Le * (mis / (pl * inv_nl));
                 out.shadow = true;
                 out.sh_o = make_float4(sp.p.x, sp.p.y, sp.p.z, (float)kEps);
                 out.sh_d = make_float4(wo.x, wo.y, wo.z, tmax);

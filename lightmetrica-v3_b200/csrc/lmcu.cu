@@ -18,8 +18,11 @@
 #include "kernels.cuh"
 #include "trace.cuh"
 
+#ifndef LMCU_SHADE_MINB
+#define LMCU_SHADE_MINB 2  // resident 256-thread CTAs per SM the shade kernel is compiled for
+#endif
 #ifndef LMCU_MINB
-#define LMCU_MINB 5      // resident 128-thread CTAs per SM the queue kernels are compiled for (register budget)
+#define LMCU_MINB 6      // resident 128-thread CTAs per SM the queue kernels are compiled for (register budget)
 #endif
 #include "prep.hpp"
 
@@ -148,41 +151,6 @@ __device__ __forceinline__ unsigned long long warp_fetch(unsigned long long* cur
     return __shfl_sync(0xffffffffu, base, 0);
 }
 
-template <typename TriT, bool COUNT>
-__global__ void __launch_bounds__(128) k_intersect(DevScene s, const LmcuRay* __restrict__ rays, unsigned long long n,
-                                                   LmcuHit* __restrict__ hits, unsigned long long* cursor,
-                                                   unsigned long long* counters, uint32_t* overflow) {
-    uint2 stack[kStackSize];
-    unsigned long long c_nodes = 0, c_tris = 0;
-    while (true) {
-        const unsigned long long base = warp_fetch(cursor);
-        if (base >= n) break;
-        const unsigned long long i = base + (threadIdx.x & 31);
-        if (i >= n) continue;
-        const double2* src = reinterpret_cast<const double2*>(rays + i);
-        const double2 a = src[0], b = src[1], c = src[2], d = src[3];
-        RayD r;
-        r.o = d3(a.x, a.y, b.x); r.d = d3(b.y, c.x, c.y); r.tmin = d.x; r.tmax = d.y;
-        HitD h; h.t = r.tmax; h.u = h.v = 0; h.tri = -1;
-        TraverseCounters tc; tc.nodes = tc.tris = 0;
-        if (!traverse<false, COUNT, TriT>(s.nodes, scene_tris<TriT>(s), r, h, stack, &tc)) atomicExch(overflow, 1u);
-        if (COUNT) { c_nodes += tc.nodes; c_tris += tc.tris; }
-        int32_t prim = -1, face = -1;
-        if (h.tri >= 0) {
-            F3 p1, p2, p3; int32_t pi;
-            tri_fetch(s, (uint32_t)h.tri, p1, p2, p3, pi, face);
-            prim = s.prims[pi].node_index;
-        }
-        double2* dst = reinterpret_cast<double2*>(hits + i);
-        dst[0] = make_double2(h.t, h.u);
-        double2 o2; o2.x = h.v;
-        int2 pf = make_int2(prim, face);
-        memcpy(&o2.y, &pf, 8);
-        dst[1] = o2;
-    }
-    if (COUNT) { atomicAdd(counters, c_nodes); atomicAdd(counters + 1, c_tris); }
-}
-
 // ================================================================================================
 // kernels: renderers
 // ================================================================================================
@@ -262,51 +230,6 @@ __global__ void k_pt_advance(PtParams p, PtCounters* ctr, int cur) {
     ctr->iterations += 1;
 }
 
-template <typename TriT, bool COUNT>
-__global__ void __launch_bounds__(128) k_pt_extend(DevScene s, PathQueue q, float4* hits, PtCounters* ctr, int cur) {
-    uint2 stack[kStackSize];
-    const uint32_t n = ctr->count[cur];
-    TraverseCounters tc; tc.nodes = tc.tris = 0;
-    while (true) {
-        uint32_t base = 0;
-        if ((threadIdx.x & 31) == 0) base = atomicAdd(&ctr->fetch_extend, 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n) break;
-        const uint32_t i = base + (threadIdx.x & 31);
-        if (i >= n) continue;
-        HitD h;
-        if (!pt_trace<false, COUNT, TriT>(s, q.ray_o[i], q.ray_d[i], h, stack, &tc)) atomicExch(&ctr->overflow, 1u);
-        hits[i] = make_float4((float)h.t, (float)h.u, (float)h.v, __int_as_float(h.tri));
-    }
-    if (COUNT) { atomicAdd(&ctr->nodes_extend, (unsigned long long)tc.nodes); atomicAdd(&ctr->tris_extend, (unsigned long long)tc.tris); }
-}
-
-// Block-wide compaction: returns the queue position for threads with `pred`, using warp ballots,
-// a shared-memory scan of the warp totals and ONE global atomic per CTA.
-__device__ __forceinline__ uint32_t block_compact(bool pred, uint32_t* global_counter, uint32_t* smem /* [33] */) {
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const uint32_t ballot = __ballot_sync(0xffffffffu, pred);
-    if (lane == 0) smem[warp] = __popc(ballot);
-    __syncthreads();
-    if (warp == 0) {
-        uint32_t v = lane < nwarps ? smem[lane] : 0u;
-        uint32_t incl = v;
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= (uint32_t)o) incl += t;
-        }
-        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-        uint32_t base = 0;
-        if (lane == 0 && total) base = atomicAdd(global_counter, total);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (lane < nwarps) smem[lane] = base + incl - v;
-    }
-    __syncthreads();
-    const uint32_t pos = smem[warp] + __popc(ballot & ((1u << lane) - 1u));
-    __syncthreads();
-    return pos;
-}
-
 // Two compactions in one pass (next-path queue and shadow queue): the per-warp counts travel packed
 // 16+16 bits through ONE shared-memory scan, so a shade iteration costs 3 barriers instead of 6.
 __device__ __forceinline__ void block_compact2(bool p0, bool p1, uint32_t* counter0, uint32_t* counter1,
@@ -337,7 +260,7 @@ __device__ __forceinline__ void block_compact2(bool p0, bool p1, uint32_t* count
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(256) k_pt_shade(DevScene s, PtParams p, PathQueue qin, PathQueue qout, ShadowQueue sq,
+__global__ void __launch_bounds__(256, LMCU_SHADE_MINB) k_pt_shade(DevScene s, PtParams p, PathQueue qin, PathQueue qout, ShadowQueue sq,
                                                   const float4* hits, float* film, PtCounters* ctr, int cur) {
     __shared__ uint32_t smem[34];
     const uint32_t n = ctr->count[cur];
@@ -364,44 +287,8 @@ __global__ void __launch_bounds__(256) k_pt_shade(DevScene s, PtParams p, PathQu
     }
 }
 
-template <typename TriT, bool COUNT>
-__global__ void __launch_bounds__(128) k_pt_shadow(DevScene s, ShadowQueue sq, float* film, PtCounters* ctr) {
-    uint2 stack[kStackSize];
-    const uint32_t n = ctr->shadow_count;
-    TraverseCounters tc; tc.nodes = tc.tris = 0;
-    if (blockIdx.x == 0 && threadIdx.x == 0) { ctr->rays += n; ctr->shadow_rays += n; }
-    while (true) {
-        uint32_t base = 0;
-        if ((threadIdx.x & 31) == 0) base = atomicAdd(&ctr->fetch_shadow, 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n) break;
-        const uint32_t i = base + (threadIdx.x & 31);
-        if (i >= n) continue;
-        HitD h;
-        if (!pt_trace<true, COUNT, TriT>(s, sq.ray_o[i], sq.ray_d[i], h, stack, &tc)) atomicExch(&ctr->overflow, 1u);
-        if (h.tri < 0) {                                     // visible (include/lm/scene.h:343-364)
-            const float4 c = sq.contrib[i];
-            float* px = film + (size_t)__float_as_uint(c.w) * 3;
-            atomicAdd(px + 0, c.x); atomicAdd(px + 1, c.y); atomicAdd(px + 2, c.z);
-        }
-    }
-    if (COUNT) { atomicAdd(&ctr->nodes_shadow, (unsigned long long)tc.nodes); atomicAdd(&ctr->tris_shadow, (unsigned long long)tc.tris); }
-}
-
-
 // -- queue kernels on the warp-persistent traversal (trace.cuh) -----------------------------------------
 
-// MODE selects the scheduling of the queue traversal (tuning switch LMCU_TRAV; results are identical):
-//   1, 2  trace_queue with 1 / 3 triangle tests per iteration      3, 4, 5  trace_queue_pp with (TRI_HI, TRI_LO) = (16,8) / (12,4) / (24,12)
-template <bool ANY, bool COUNT, int MODE, typename TriT, typename IO>
-__device__ __forceinline__ void run_trace(const DevScene& s, uint32_t n, uint32_t* cursor, const IO& io, uint32_t* overflow,
-                                          TraverseCounters* tc) {
-    if constexpr (MODE == 1) trace_queue<ANY, COUNT, 1, TriT>(s.nodes, scene_tris<TriT>(s), n, cursor, io, overflow, tc, s.fetch_threshold);
-    else if constexpr (MODE == 2) trace_queue<ANY, COUNT, 3, TriT>(s.nodes, scene_tris<TriT>(s), n, cursor, io, overflow, tc, s.fetch_threshold);
-    else if constexpr (MODE == 3) trace_queue_pp<ANY, COUNT, 16, 8, TriT>(s.nodes, scene_tris<TriT>(s), n, cursor, io, overflow, tc, s.fetch_threshold);
-    else if constexpr (MODE == 4) trace_queue_pp<ANY, COUNT, 12, 4, TriT>(s.nodes, scene_tris<TriT>(s), n, cursor, io, overflow, tc, s.fetch_threshold);
-    else trace_queue_pp<ANY, COUNT, 24, 12, TriT>(s.nodes, scene_tris<TriT>(s), n, cursor, io, overflow, tc, s.fetch_threshold);
-}
 struct BatchIO {                       // accel batches: LmcuRay in, LmcuHit out (include/lmcu.h)
     DevScene s;
     const LmcuRay* rays;
@@ -428,13 +315,13 @@ struct BatchIO {                       // accel batches: LmcuRay in, LmcuHit out
     }
 };
 
-template <typename TriT, bool COUNT, int TPI>
+template <typename TriT, bool COUNT>
 __global__ void __launch_bounds__(128, LMCU_MINB) k_intersect_q(DevScene s, const LmcuRay* __restrict__ rays, uint32_t n,
                                                      LmcuHit* __restrict__ hits, uint32_t* cursor,
                                                      unsigned long long* counters, uint32_t* overflow) {
     BatchIO io; io.s = s; io.rays = rays; io.hits = hits;
     TraverseCounters tc; tc.nodes = tc.tris = 0;
-    run_trace<false, COUNT, TPI, TriT>(s, n, cursor, io, overflow, &tc);
+    trace_queue<false, COUNT, TriT>(s.nodes, scene_tris<TriT>(s), n, cursor, io, overflow, &tc, s.fetch_threshold);
     if (COUNT) { atomicAdd(counters, (unsigned long long)tc.nodes); atomicAdd(counters + 1, (unsigned long long)tc.tris); }
 }
 
@@ -451,11 +338,11 @@ struct ExtendIO {                      // pt extend: path queue in, float4 hit r
     }
 };
 
-template <typename TriT, bool COUNT, int TPI>
+template <typename TriT, bool COUNT>
 __global__ void __launch_bounds__(128, LMCU_MINB) k_pt_extend_q(DevScene s, PathQueue q, float4* hits, PtCounters* ctr, int cur) {
     ExtendIO io; io.ray_o = q.ray_o; io.ray_d = q.ray_d; io.hits = hits;
     TraverseCounters tc; tc.nodes = tc.tris = 0;
-    run_trace<false, COUNT, TPI, TriT>(s, ctr->count[cur], &ctr->fetch_extend, io, &ctr->overflow, &tc);
+    trace_queue<false, COUNT, TriT>(s.nodes, scene_tris<TriT>(s), ctr->count[cur], &ctr->fetch_extend, io, &ctr->overflow, &tc, s.fetch_threshold);
     if (COUNT) { atomicAdd(&ctr->nodes_extend, (unsigned long long)tc.nodes); atomicAdd(&ctr->tris_extend, (unsigned long long)tc.tris); }
 }
 
@@ -476,13 +363,13 @@ struct ShadowIO {                      // pt shadow: visible (include/lm/scene.h
     }
 };
 
-template <typename TriT, bool COUNT, int TPI>
+template <typename TriT, bool COUNT>
 __global__ void __launch_bounds__(128, LMCU_MINB) k_pt_shadow_q(DevScene s, ShadowQueue sq, float* film, PtCounters* ctr) {
     const uint32_t n = ctr->shadow_count;
     if (blockIdx.x == 0 && threadIdx.x == 0) { ctr->rays += n; ctr->shadow_rays += n; }
     ShadowIO io; io.ray_o = sq.ray_o; io.ray_d = sq.ray_d; io.contrib = sq.contrib; io.film = film;
     TraverseCounters tc; tc.nodes = tc.tris = 0;
-    run_trace<true, COUNT, TPI, TriT>(s, n, &ctr->fetch_shadow, io, &ctr->overflow, &tc);
+    trace_queue<true, COUNT, TriT>(s.nodes, scene_tris<TriT>(s), n, &ctr->fetch_shadow, io, &ctr->overflow, &tc, s.fetch_threshold);
     if (COUNT) { atomicAdd(&ctr->nodes_shadow, (unsigned long long)tc.nodes); atomicAdd(&ctr->tris_shadow, (unsigned long long)tc.tris); }
 }
 
@@ -523,6 +410,7 @@ struct LmcuScene {
     DBuf<LightDev> lights;
     DBuf<EmitTri> emit;
     DBuf<float> cdf;
+    DBuf<float4> env_tex;
     std::vector<PrimDev> h_prims;
     uint32_t nt = 0;
     int num_prims = 0, num_lights = 0, env_light = -1;
@@ -547,14 +435,13 @@ struct LmcuScene {
     DBuf<PtCounters> pt_ctr;
     uint32_t pt_capacity = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    int trav = 1;                        // LMCU_TRAV: 0 = per-warp batches (bvh.cuh), 1/2 = warp-persistent queue (trace.cuh), 1 or 3 triangles per iteration
-    int fetch_threshold = 8;             // LMCU_FETCH
+    int fetch_threshold = 16;            // LMCU_FETCH
     int ctas_per_sm = LMCU_MINB;                 // LMCU_CTAS: resident 128-thread CTAs per SM for the persistent traversal grids
 
     DevScene dev() const {
         DevScene d{};
         d.nodes = nodes.p; d.t32 = t32.p; d.t64 = t64.p; d.shade = shade.p; d.prims = prims.p; d.mats = mats.p;
-        d.lights = lights.p; d.emit = emit.p; d.cdf = cdf.p; d.env_tex = nullptr;
+        d.lights = lights.p; d.emit = emit.p; d.cdf = cdf.p; d.env_tex = env_tex.p;
         d.num_prims = num_prims; d.num_lights = num_lights; d.env_light = env_light; d.fetch_threshold = fetch_threshold; d.num_tris = nt; d.cam = cam;
         return d;
     }
@@ -586,7 +473,6 @@ int lmcu_scene_create(int device, LmcuScene** out) {
     s->stream = s->own_stream;
     CU(cudaEventCreate(&s->ev0));
     CU(cudaEventCreate(&s->ev1));
-    if (const char* e = getenv("LMCU_TRAV")) s->trav = atoi(e);
     if (const char* e = getenv("LMCU_FETCH")) s->fetch_threshold = atoi(e);
     if (const char* e = getenv("LMCU_CTAS")) s->ctas_per_sm = std::max(1, atoi(e));
     CU(s->cursor.alloc(8));
@@ -647,6 +533,8 @@ int lmcu_scene_upload(LmcuScene* s, const LmcuSceneDesc* d) {
     if (!ps.emit.empty()) CU(cudaMemcpy(s->emit.p, ps.emit.data(), ps.emit.size() * sizeof(EmitTri), cudaMemcpyHostToDevice));
     CU(s->cdf.alloc(ps.cdf.size()));
     if (!ps.cdf.empty()) CU(cudaMemcpy(s->cdf.p, ps.cdf.data(), ps.cdf.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CU(s->env_tex.alloc(ps.env_tex.size()));
+    if (!ps.env_tex.empty()) CU(cudaMemcpy(s->env_tex.p, ps.env_tex.data(), ps.env_tex.size() * sizeof(float4), cudaMemcpyHostToDevice));
     CU(s->prims.alloc(ps.prims.size()));
     CU(cudaMemcpy(s->prims.p, ps.prims.data(), ps.prims.size() * sizeof(PrimDev), cudaMemcpyHostToDevice));
     s->built = false;
@@ -762,50 +650,26 @@ int lmcu_accel_build(LmcuScene* s, const LmcuBuildOptions* opts, LmcuBuildStats*
 
 // -- intersect ------------------------------------------------------------------------------------------
 // Picks the kernel instantiation for (triangle record, counters, triangles per iteration).
-#define LMCU_DISPATCH_M(KERNEL, TRI, COUNT, MODE, GRID, BLOCK, STREAM, ...)                                      \
-    do {                                                                                                         \
-        switch (MODE) {                                                                                          \
-        case 1: KERNEL<TRI, COUNT, 1><<<GRID, BLOCK, 0, STREAM>>>(__VA_ARGS__); break;                           \
-        case 2: KERNEL<TRI, COUNT, 2><<<GRID, BLOCK, 0, STREAM>>>(__VA_ARGS__); break;                           \
-        case 3: KERNEL<TRI, COUNT, 3><<<GRID, BLOCK, 0, STREAM>>>(__VA_ARGS__); break;                           \
-        case 4: KERNEL<TRI, COUNT, 4><<<GRID, BLOCK, 0, STREAM>>>(__VA_ARGS__); break;                           \
-        default: KERNEL<TRI, COUNT, 5><<<GRID, BLOCK, 0, STREAM>>>(__VA_ARGS__); break;                          \
-        }                                                                                                        \
-    } while (0)
-#define LMCU_DISPATCH(KERNEL, FP32, COUNT, MODE, GRID, BLOCK, STREAM, ...)                                       \
+#define LMCU_DISPATCH(KERNEL, FP32, COUNT, GRID, BLOCK, STREAM, ...)                                             \
     do {                                                                                                         \
         if (FP32) {                                                                                              \
-            if (COUNT) LMCU_DISPATCH_M(KERNEL, TriF32, true, MODE, GRID, BLOCK, STREAM, __VA_ARGS__);            \
-            else LMCU_DISPATCH_M(KERNEL, TriF32, false, MODE, GRID, BLOCK, STREAM, __VA_ARGS__);                 \
+            if (COUNT) KERNEL<TriF32, true><<<GRID, BLOCK, 0, STREAM>>>(__VA_ARGS__);                            \
+            else KERNEL<TriF32, false><<<GRID, BLOCK, 0, STREAM>>>(__VA_ARGS__);                                 \
         } else {                                                                                                 \
-            if (COUNT) LMCU_DISPATCH_M(KERNEL, TriF64, true, MODE, GRID, BLOCK, STREAM, __VA_ARGS__);            \
-            else LMCU_DISPATCH_M(KERNEL, TriF64, false, MODE, GRID, BLOCK, STREAM, __VA_ARGS__);                 \
+            if (COUNT) KERNEL<TriF64, true><<<GRID, BLOCK, 0, STREAM>>>(__VA_ARGS__);                            \
+            else KERNEL<TriF64, false><<<GRID, BLOCK, 0, STREAM>>>(__VA_ARGS__);                                 \
         }                                                                                                        \
     } while (0)
 
 static int launch_intersect(LmcuScene* s, const LmcuRay* d_rays, int64_t n, LmcuHit* d_hits, bool count, cudaStream_t st) {
     const DevScene d = s->dev();
-    if (s->trav == 0) {
-        CU(cudaMemsetAsync(s->cursor.p, 0, 3 * sizeof(unsigned long long), st));
-        const unsigned blocks = (unsigned)std::min<int64_t>((n + 127) / 128, (int64_t)s->num_sms * 12);
-        if (s->fp32) {
-            if (count) k_intersect<TriF32, true><<<blocks, 128, 0, st>>>(d, d_rays, (unsigned long long)n, d_hits, s->cursor.p, s->cursor.p + 1, s->flags.p);
-            else k_intersect<TriF32, false><<<blocks, 128, 0, st>>>(d, d_rays, (unsigned long long)n, d_hits, s->cursor.p, s->cursor.p + 1, s->flags.p);
-        } else {
-            if (count) k_intersect<TriF64, true><<<blocks, 128, 0, st>>>(d, d_rays, (unsigned long long)n, d_hits, s->cursor.p, s->cursor.p + 1, s->flags.p);
-            else k_intersect<TriF64, false><<<blocks, 128, 0, st>>>(d, d_rays, (unsigned long long)n, d_hits, s->cursor.p, s->cursor.p + 1, s->flags.p);
-        }
-        CU(cudaGetLastError());
-        return LMCU_OK;
-    }
     if (count) CU(cudaMemsetAsync(s->cursor.p + 1, 0, 2 * sizeof(unsigned long long), st));
-    const int tpi = s->trav;
     const int64_t kChunk = 1ll << 30;            // the queue cursor is 32-bit
     for (int64_t off = 0; off < n; off += kChunk) {
         const uint32_t m = (uint32_t)std::min<int64_t>(kChunk, n - off);
         CU(cudaMemsetAsync(s->cursor.p, 0, sizeof(unsigned long long), st));
         const unsigned blocks = (unsigned)std::min<int64_t>((m + 127) / 128, (int64_t)s->num_sms * s->ctas_per_sm);
-        LMCU_DISPATCH(k_intersect_q, s->fp32, count, tpi, blocks, 128, st, d, d_rays + off, m, d_hits + off,
+        LMCU_DISPATCH(k_intersect_q, s->fp32, count, blocks, 128, st, d, d_rays + off, m, d_hits + off,
                       (uint32_t*)s->cursor.p, s->cursor.p + 1, s->flags.p);
         CU(cudaGetLastError());
     }
@@ -1015,8 +879,7 @@ int lmcu_render_pt(LmcuScene* s, const LmcuRenderParams* p, float* film_rgb, Lmc
     CU(cudaEventRecord(s->ev0, st));
     const DevScene d = s->dev();
     const unsigned q_blocks = (unsigned)(s->num_sms * s->ctas_per_sm);
-    const int tpi = s->trav;
-    const unsigned trav_blocks = (unsigned)s->num_sms * 12, shade_blocks = (unsigned)s->num_sms * 6, gen_blocks = (unsigned)s->num_sms * 4;
+    const unsigned shade_blocks = (unsigned)s->num_sms * 6, gen_blocks = (unsigned)s->num_sms * 4;
     int cur = 0;
     int64_t launches = 0;
     PtCounters h{};
@@ -1034,31 +897,11 @@ int lmcu_render_pt(LmcuScene* s, const LmcuRenderParams* p, float* film_rgb, Lmc
             k_pt_generate<<<gen_blocks, 256, 0, st>>>(d, pp, q[cur], s->pt_ctr.p, cur);
             k_pt_advance<<<1, 1, 0, st>>>(pp, s->pt_ctr.p, cur);
             cudaEventRecord(ev[0], st);
-            if (s->trav == 0) {
-                if (s->fp32) {
-                    if (count) k_pt_extend<TriF32, true><<<trav_blocks, 128, 0, st>>>(d, q[cur], s->hits.p, s->pt_ctr.p, cur);
-                    else k_pt_extend<TriF32, false><<<trav_blocks, 128, 0, st>>>(d, q[cur], s->hits.p, s->pt_ctr.p, cur);
-                } else {
-                    if (count) k_pt_extend<TriF64, true><<<trav_blocks, 128, 0, st>>>(d, q[cur], s->hits.p, s->pt_ctr.p, cur);
-                    else k_pt_extend<TriF64, false><<<trav_blocks, 128, 0, st>>>(d, q[cur], s->hits.p, s->pt_ctr.p, cur);
-                }
-            } else {
-                LMCU_DISPATCH(k_pt_extend_q, s->fp32, count, tpi, q_blocks, 128, st, d, q[cur], s->hits.p, s->pt_ctr.p, cur);
-            }
+            LMCU_DISPATCH(k_pt_extend_q, s->fp32, count, q_blocks, 128, st, d, q[cur], s->hits.p, s->pt_ctr.p, cur);
             cudaEventRecord(ev[1], st);
             k_pt_shade<<<shade_blocks, 256, 0, st>>>(d, pp, q[cur], q[cur ^ 1], sq, s->hits.p, s->film.p, s->pt_ctr.p, cur);
             cudaEventRecord(ev[2], st);
-            if (s->trav == 0) {
-                if (s->fp32) {
-                    if (count) k_pt_shadow<TriF32, true><<<trav_blocks, 128, 0, st>>>(d, sq, s->film.p, s->pt_ctr.p);
-                    else k_pt_shadow<TriF32, false><<<trav_blocks, 128, 0, st>>>(d, sq, s->film.p, s->pt_ctr.p);
-                } else {
-                    if (count) k_pt_shadow<TriF64, true><<<trav_blocks, 128, 0, st>>>(d, sq, s->film.p, s->pt_ctr.p);
-                    else k_pt_shadow<TriF64, false><<<trav_blocks, 128, 0, st>>>(d, sq, s->film.p, s->pt_ctr.p);
-                }
-            } else {
-                LMCU_DISPATCH(k_pt_shadow_q, s->fp32, count, tpi, q_blocks, 128, st, d, sq, s->film.p, s->pt_ctr.p);
-            }
+            LMCU_DISPATCH(k_pt_shadow_q, s->fp32, count, q_blocks, 128, st, d, sq, s->film.p, s->pt_ctr.p);
             cudaEventRecord(ev[3], st);
             cur ^= 1;
             launches += 5;

@@ -17,6 +17,7 @@ struct PreparedScene {
     std::vector<LightDev> lights;
     std::vector<EmitTri> emit;
     std::vector<float> cdf;
+    std::vector<float4> env_tex;             // light::env texels (rgb, texture::bitmap row order)
     CameraDev cam{};
     bool has_camera = false;
     int env_light = -1;
@@ -112,8 +113,39 @@ inline int prepare_scene(const LmcuSceneDesc* d, PreparedScene& o, std::string& 
         } else if (l.type == LMCU_LIGHT_ENVCONST) {
             if (o.env_light >= 0) { err = "Environment light is already registered."; return LMCU_ERR_INVALID_ARGUMENT; }
             o.env_light = i;
+        } else if (l.type == LMCU_LIGHT_ENV) {
+            // light::env (src/light/light_env.cpp:52-77): lat-long image + Dist2 over max(rgb*scale) * sin(theta)
+            if (o.env_light >= 0) { err = "Environment light is already registered."; return LMCU_ERR_INVALID_ARGUMENT; }
+            if (!l.env_rgb || l.env_w <= 0 || l.env_h <= 0) { err = "light::env without image data"; return LMCU_ERR_INVALID_ARGUMENT; }
+            o.env_light = i;
+            const int w = l.env_w, h = l.env_h;
+            t.env_w = w; t.env_h = h;
+            t.env_rot = (float)(l.env_rot * 3.14159265358979323846 / 180.0);      // glm::radians, light_env.cpp:63
+            t.env_scale = (float)l.env_scale;
+            t.env_tex_offset = (int32_t)o.env_tex.size();
+            t.env_cdf_offset = (int32_t)o.cdf.size();
+            o.env_tex.reserve(o.env_tex.size() + (size_t)w * h);
+            for (size_t k = 0; k < (size_t)w * h; k++) {
+                o.env_tex.push_back(make_float4(l.env_rgb[3 * k], l.env_rgb[3 * k + 1], l.env_rgb[3 * k + 2], 0.f));
+            }
+            // Dist2::init (include/lm/math.h:398-410) in FP64, stored as float CDFs: rows [h][w+1], marginal [h+1]
+            std::vector<double> marg(1, 0.0), row((size_t)w + 1);
+            o.cdf.reserve(o.cdf.size() + (size_t)h * (w + 1) + h + 1);
+            for (int y = 0; y < h; y++) {
+                row[0] = 0.0;
+                for (int x = 0; x < w; x++) {
+                    const size_t k = (size_t)y * w + x;
+                    const double mx = std::fmax(std::fmax((double)l.env_rgb[3 * k], (double)l.env_rgb[3 * k + 1]), (double)l.env_rgb[3 * k + 2]) * l.env_scale;
+                    // the reference weights texel i by sin(pi * (Float(i)/w + .5) / h) with i the FLAT index (light_env.cpp:71)
+                    const double v = mx * std::sin(3.14159265358979323846 * ((double)k / w + .5) / h);
+                    row[x + 1] = row[x] + v;
+                }
+                marg.push_back(marg.back() + row[w]);
+                for (int x = 0; x <= w; x++) o.cdf.push_back((float)(row[x] / row[w]));
+            }
+            for (double v : marg) o.cdf.push_back((float)(v / marg.back()));
         } else {
-            err = "light type not supported yet"; return LMCU_ERR_UNSUPPORTED;
+            err = "bad light type"; return LMCU_ERR_INVALID_ARGUMENT;
         }
     }
     o.has_camera = d->camera != nullptr;

@@ -255,6 +255,63 @@ LMCU_HD int cdf_sample(const float* c, int n, float u) {   // c has n+1 entries,
     return i < 0 ? 0 : (i > n - 1 ? n - 1 : i);
 }
 
+// -- light::env (src/light/light_env.cpp:64-72,139-202): lat-long image, Dist2 importance sampling ---------
+// (u,v) of a direction d pointing from the scene toward the sky (d = -geomL.wo), light_env.cpp:166-176,191-199
+LMCU_HD void env_dir_to_uv(const LightDev& l, F3 d, float& u, float& v) {
+    float at = atan2f(d.x, d.z);
+    if (at < 0.f) at += 2.0f * kPiF;
+    const float t = (at - l.env_rot) * 0.5f / kPiF;
+    u = t - floorf(t);
+    v = acosf(fminf(1.f, fmaxf(-1.f, d.y))) / kPiF;
+}
+
+// Light::eval: nearest texel of texture::bitmap (src/texture/texture_bitmap.cpp:68-75) times scale
+LMCU_HD F3 env_eval(const LightDev& l, const float4* tex, F3 d) {
+    float u, v;
+    env_dir_to_uv(l, d, u, v);
+    u = u - floorf(u); v = v - floorf(v);
+    int x = (int)(u * (float)l.env_w), y = (int)(v * (float)l.env_h);
+    x = x < 0 ? 0 : (x > l.env_w - 1 ? l.env_w - 1 : x);
+    y = y < 0 ? 0 : (y > l.env_h - 1 ? l.env_h - 1 : y);
+    const float4 t = tex[l.env_tex_offset + y * l.env_w + x];
+    return f3(t.x, t.y, t.z) * l.env_scale;
+}
+
+// Dist2::pdf (include/lm/math.h:416-419); cdf layout: conditional rows [h][w+1], then marginal [h+1]
+LMCU_HD float env_dist_pdf(const LightDev& l, const float* cdf, float u, float v) {
+    const int w = l.env_w, h = l.env_h;
+    int y = (int)(v * (float)h);
+    y = y > h - 1 ? h - 1 : y;
+    const int x = (int)(u * (float)w);
+    if (y < 0 || x < 0 || x >= w) return 0.f;                       // Dist::pmf is 0 outside its range
+    const float* m = cdf + l.env_cdf_offset + (size_t)h * (w + 1);
+    const float* row = cdf + l.env_cdf_offset + (size_t)y * (w + 1);
+    return (m[y + 1] - m[y]) * (row[x + 1] - row[x]) * (float)w * (float)h;
+}
+
+// Light::pdf_direct in projected solid angle at a surface point with shading normal n (light_env.cpp:164-181)
+LMCU_HD float env_pdf_direct(const LightDev& l, const float* cdf, F3 n, F3 d) {
+    float u, v;
+    env_dir_to_uv(l, d, u, v);
+    const float st = safe_sqrt(1.0f - d.y * d.y);
+    if (st == 0.f) return 0.f;
+    const float pdf_sa = env_dist_pdf(l, cdf, u, v) / (2.0f * kPiF * kPiF * st);
+    const float J = fabsf(dot(n, d));
+    return J == 0.f ? 0.f : pdf_sa / J;
+}
+
+// Light::sample_direct: returns the direction toward the sky (light_env.cpp:146-153); u = (ud.x, ud.y, up.x, up.y)
+LMCU_HD F3 env_sample_dir(const LightDev& l, const float* cdf, R4 u) {
+    const int w = l.env_w, h = l.env_h;
+    const float* m = cdf + l.env_cdf_offset + (size_t)h * (w + 1);
+    const int y = cdf_sample(m, h, u.x);
+    const int x = cdf_sample(cdf + l.env_cdf_offset + (size_t)y * (w + 1), w, u.y);
+    const float su = ((float)x + u.z) / (float)w, sv = ((float)y + u.w) / (float)h;
+    const float t = kPiF * sv, p = 2.0f * kPiF * su + l.env_rot;
+    const float st = sinf(t);
+    return f3(st * sinf(p), cosf(t), st * cosf(p));
+}
+
 // -- camera (src/camera/camera_pinhole.cpp:90-95,102-109,128-132,207-226) ---------------------------------
 struct CameraDev {
     double pos[3], u[3], v[3], w[3];

@@ -4,11 +4,11 @@
 // run.  Same node test, same FP64 leaf test, same results; what changes is the scheduling:
 //
 //   * every lane owns one ray and runs a small state machine; one loop iteration = at most ONE
-//     wide-node step (for lanes with no pending triangles) followed by at most TRI_PER_ITER FP64
-//     triangle tests (for lanes with pending triangles), so node work and leaf work of different
-//     lanes proceed in lock-step instead of each lane's leaf loop stalling the other 31;
-//   * a lane whose ray terminates stores its result at once and goes idle; when the idle-lane debt
-//     of the warp crosses a threshold the warp leaves the traversal loop and the idle lanes claim
+//     wide-node step (for lanes with no pending triangles) followed by at most ONE FP64 triangle
+//     test (for lanes with pending triangles), so node work and leaf work of different lanes
+//     proceed in lock-step instead of each lane's leaf loop stalling the other 31;
+//   * a lane whose ray terminates stores its result at once and goes idle; as soon as
+//     `fetch_threshold` lanes are idle the warp leaves the traversal loop and the idle lanes claim
 //     new rays with ONE atomic on the queue cursor (ballot-ranked), so a long ray no longer holds
 //     31 finished lanes hostage until the end of the batch;
 //   * the two barycentric divisions u/|det|, v/|det| (accel_sahbvh.cpp:74) are applied once per
@@ -26,7 +26,7 @@ namespace lmcu {
 #if defined(__CUDACC__)
 
 
-template <bool ANY, bool COUNT, int TRI_PER_ITER, typename TriT, typename IO>
+template <bool ANY, bool COUNT, typename TriT, typename IO>
 __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, const TriT* __restrict__ tris,
                                             uint32_t n, uint32_t* cursor, const IO& io, uint32_t* overflow,
                                             TraverseCounters* ctr, int fetch_threshold) {
@@ -76,7 +76,7 @@ __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, 
             if (exhausted) break;
             continue;
         }
-        // ---- traverse until the idle-lane debt says "re-fetch" ----------------------------------------
+        // ---- traverse until enough lanes are idle to make a re-fetch worth its latency ------------------
         while (true) {
             if (active) {
                 if (tgroup.y == 0u) {
@@ -116,8 +116,7 @@ __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, 
                     }
                 }
                 // ---- leaf work: FP64 Möller–Trumbore, reference operation order (accel_sahbvh.cpp:58-75)
-#pragma unroll 1
-                for (int k = 0; k < TRI_PER_ITER && active && tgroup.y != 0u; k++) {
+                if (active && tgroup.y != 0u) {
                     const int ti = bfind(tgroup.y);
                     tgroup.y &= ~(1u << ti);
                     const uint32_t tri = tgroup.x + (uint32_t)ti;
@@ -156,160 +155,12 @@ __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, 
 }
 
 
-// ------------------------------------------------------------------------------------------------------
-// Phase-partitioned variant: the FP64 leaf test is ~3x the issue cost of everything else a lane does per
-// iteration, and in trace_queue() it ran with 12 (extend) / 5 (shadow) of 32 lanes on (ncu source page,
-// profiles/r01_ncu_summary_v2.md).  Here a lane that finds triangles POSTPONES them (first group in a
-// register, further groups on its stack, as in Ylitie et al. 2017) and keeps doing node steps; the warp
-// switches to the triangle phase only when at least TRI_HI lanes (or half of the active ones) hold
-// pending triangles, and stays there, one triangle per lane per round, until fewer than TRI_LO do.
-// Postponing only delays the shrinking of tmax (closest hit) or the termination (any hit): every
-// triangle whose box overlaps the final [tmin, t_hit] is still tested, so results are unchanged.
-template <bool ANY, bool COUNT, int TRI_HI, int TRI_LO, typename TriT, typename IO>
-__device__ __forceinline__ void trace_queue_pp(const WideNode* __restrict__ nodes, const TriT* __restrict__ tris,
-                                               uint32_t n, uint32_t* cursor, const IO& io, uint32_t* overflow,
-                                               TraverseCounters* ctr, int fetch_threshold) {
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t lt_mask = (1u << lane) - 1u;
-    const uint4* nodes4 = reinterpret_cast<const uint4*>(nodes);
-    uint2 stack[kStackSize];
-
-    bool active = false;
-    bool exhausted = false;
-    uint32_t idx = 0;
-    RayD r; r.o = d3(0, 0, 0); r.d = d3(0, 0, 1); r.tmin = 0; r.tmax = 0;
-    RayF f = make_rayf(r);
-    float tmin_dn = 0.f, tmax_up = 0.f;
-    double ht = 0, hu = 0, hv = 0, had = 1;
-    int32_t htri = -1;
-    uint2 ngroup = make_uint2(0u, 0u), tgroup = make_uint2(0u, 0u);
-    int sp = 0;
-
-    while (true) {
-        if (!exhausted) {
-            const uint32_t idle = __ballot_sync(0xffffffffu, !active);
-            if (idle) {
-                const int leader = __ffs(idle) - 1;
-                uint32_t base = 0;
-                if ((int)lane == leader) base = atomicAdd(cursor, (uint32_t)__popc(idle));
-                base = __shfl_sync(0xffffffffu, base, leader);
-                if (base + (uint32_t)__popc(idle) >= n) exhausted = true;
-                if (!active) {
-                    idx = base + (uint32_t)__popc(idle & lt_mask);
-                    if (idx < n && io.load(idx, r)) {
-                        f = make_rayf(r);
-                        tmin_dn = f32_down(r.tmin);
-                        tmax_up = f32_up(r.tmax);
-                        ht = r.tmax; htri = -1;
-                        ngroup = make_uint2(0u, 0x80000000u);
-                        tgroup = make_uint2(0u, 0u);
-                        sp = 0;
-                        active = true;
-                    }
-                }
-            }
-        }
-        if (!__any_sync(0xffffffffu, active)) {
-            if (exhausted) break;
-            continue;
-        }
-        while (true) {
-            // ---- node phase: one step for every lane that has node work (speculating past pending triangles)
-            bool progressed = false;
-            if (active) {
-                if (ngroup.y <= 0x00ffffffu && sp > 0) {
-                    const uint2 top = stack[sp - 1];
-                    if (top.y > 0x00ffffffu) { ngroup = top; sp--; progressed = true; }
-                    else if (tgroup.y == 0u) { tgroup = top; sp--; progressed = true; }
-                }
-                if (ngroup.y > 0x00ffffffu) {
-                    const uint32_t hits = ngroup.y;
-                    const uint32_t imask = hits & 0xffu;
-                    const int child_bit = bfind(hits);
-                    const uint32_t base = ngroup.x;
-                    ngroup.y &= ~(1u << child_bit);
-                    if (ngroup.y > 0x00ffffffu) {
-                        if (sp >= kStackSize) { atomicExch(overflow, 1u); sp = kStackSize - 1; }
-                        stack[sp++] = ngroup;
-                    }
-                    const uint32_t slot = (uint32_t)(child_bit - 24) ^ (f.octinv4 & 0xffu);
-                    const uint32_t ni = base + popc(imask & ~(0xffffffffu << slot));
-                    const uint4 n0 = __ldg(nodes4 + ni * 5 + 0), n1 = __ldg(nodes4 + ni * 5 + 1),
-                                n2 = __ldg(nodes4 + ni * 5 + 2), n3 = __ldg(nodes4 + ni * 5 + 3),
-                                n4 = __ldg(nodes4 + ni * 5 + 4);
-                    if (COUNT) ctr->nodes++;
-                    const uint32_t hm = node_hitmask(n0, n1, n2, n3, n4, f, tmin_dn, tmax_up);
-                    ngroup.x = n1.x;
-                    ngroup.y = (hm & 0xff000000u) | (n0.w >> 24);
-                    const uint32_t nt = hm & 0x00ffffffu;
-                    if (nt) {
-                        if (tgroup.y == 0u) { tgroup = make_uint2(n1.y, nt); }
-                        else {
-                            if (sp >= kStackSize) { atomicExch(overflow, 1u); sp = kStackSize - 1; }
-                            stack[sp++] = make_uint2(n1.y, nt);
-                        }
-                    }
-                    progressed = true;
-                } else if (tgroup.y == 0u && sp == 0) {
-                    HitD h;
-                    h.t = ht; h.tri = htri;
-                    h.u = htri >= 0 ? divrn(hu, had) : 0.0;
-                    h.v = htri >= 0 ? divrn(hv, had) : 0.0;
-                    io.store(idx, r, h);
-                    active = false;
-                    progressed = true;
-                }
-            }
-            // ---- triangle phase, entered only with enough lanes on board
-            uint32_t tri_lanes = __ballot_sync(0xffffffffu, active && tgroup.y != 0u);
-            if (tri_lanes) {
-                const uint32_t act_now = __ballot_sync(0xffffffffu, active);
-                const int need = min(TRI_HI, (__popc(act_now) + 1) >> 1);
-                if (__popc(tri_lanes) >= need || !__any_sync(0xffffffffu, progressed)) {
-                    do {
-                        if (active && tgroup.y != 0u) {
-                            const int ti = bfind(tgroup.y);
-                            tgroup.y &= ~(1u << ti);
-                            const uint32_t tri = tgroup.x + (uint32_t)ti;
-                            D3 p1, p2, p3;
-                            load_tri(tris, tri, p1, p2, p3);
-                            if (COUNT) ctr->tris++;
-                            const D3 e1 = dsub3(p2, p1), e2 = dsub3(p3, p1);
-                            const D3 p = dcross(r.d, e2);
-                            const D3 tv = dsub3(r.o, p1);
-                            const D3 q = dcross(tv, e1);
-                            const double d = ddot(e1, p);
-                            const double ad = fabs(d);
-                            const double s = copysign(1.0, d);
-                            const double u = mulrn(ddot(tv, p), s);
-                            const double v = mulrn(ddot(r.d, q), s);
-                            if (!(ad < 1e-8 || u < 0.0 || v < 0.0 || addrn(u, v) > ad)) {
-                                const double t = divrn(ddot(e2, q), d);
-                                if (!(t < r.tmin || ht < t)) {
-                                    ht = t; hu = u; hv = v; had = ad; htri = (int32_t)tri;
-                                    tmax_up = f32_up(t);
-                                    if (ANY) {
-                                        HitD h;
-                                        h.t = t; h.tri = htri; h.u = divrn(u, ad); h.v = divrn(v, ad);
-                                        io.store(idx, r, h);
-                                        active = false;
-                                    }
-                                }
-                            }
-                            // drained: continue with the next postponed group if it is on top of the stack
-                            if (active && tgroup.y == 0u && sp > 0 && stack[sp - 1].y <= 0x00ffffffu) tgroup = stack[--sp];
-                        }
-                        tri_lanes = __ballot_sync(0xffffffffu, active && tgroup.y != 0u);
-                    } while (__popc(tri_lanes) >= TRI_LO);
-                }
-            }
-            const uint32_t act = __ballot_sync(0xffffffffu, active);
-            if (act == 0u) break;
-            if (!exhausted && 32 - __popc(act) >= fetch_threshold) break;     // enough idle lanes: refill them
-        }
-    }
-}
-
 #endif  // __CUDACC__
 
 }  // namespace lmcu
+
+// Variants measured and dropped (profiles/r01_ncu_summary_v2.md, gpurun logs of round 1): 3 triangle tests
+// per iteration (-6 % Mpaths/s on C2), a CWBVH-style accumulated "lost iterations" refetch credit (never paid
+// back on rays this short), and a phase-partitioned loop that postpones FP64 triangle tests until >= 12..24
+// lanes hold some (triangle-step occupancy 9.5 -> 12.8 lanes, but the speculative node steps cost as much as
+// the batching saved: -2 % on C2, -20 % on C3 incoherent rays).

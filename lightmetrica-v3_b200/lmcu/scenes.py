@@ -334,6 +334,61 @@ def instanced_spheres(grid=10, num_theta=112, seed=3, env=None):
 
 
 # ------------------------------------------------------------------------------------------------
+# Procedural environment map (C4 variant): sun lobe + sky gradient, stored as Radiance RGBE so that the
+# reference (texture::bitmap -> stb_image) and the device see bit-identical texels
+# ------------------------------------------------------------------------------------------------
+def _rgbe_encode(rgb):
+    """float RGB -> RGBE bytes (Ward's float2rgbe: mantissa scaled by 256 / 2^e, truncated)."""
+    rgb = np.asarray(rgb, dtype=np.float64)
+    v = rgb.max(axis=-1)
+    m, e = np.frexp(v)
+    scale = np.where(v < 1e-32, 0.0, m * 256.0 / np.maximum(v, 1e-300))
+    out = np.zeros(rgb.shape[:-1] + (4,), dtype=np.uint8)
+    out[..., :3] = np.clip(rgb * scale[..., None], 0, 255).astype(np.uint8)
+    out[..., 3] = np.where(v < 1e-32, 0, e + 128).astype(np.uint8)
+    return out
+
+
+def _rgbe_decode(rgbe):
+    """stb_image's stbi__hdr_convert: rgb * 2^(e - 136), zero when e == 0; float32 like stbi_loadf."""
+    e = rgbe[..., 3].astype(np.int32)
+    f = np.where(e != 0, np.ldexp(np.float32(1.0), e - 136), np.float32(0)).astype(np.float32)
+    return (rgbe[..., :3].astype(np.float32) * f[..., None]).astype(np.float32)
+
+
+def procedural_env(w=1024, h=512, seed=5):
+    """Returns the RGBE image in TEXTURE order (row 0 = v 0 = straight up after the reference's vertical flip)."""
+    rng = np.random.RandomState(seed)
+    v = (np.arange(h) + .5) / h
+    u = (np.arange(w) + .5) / w
+    theta, phi = np.pi * v[:, None], 2 * np.pi * u[None, :]
+    d = np.stack([np.sin(theta) * np.sin(phi), np.cos(theta) * np.ones_like(phi), np.sin(theta) * np.cos(phi)], -1)
+    sky = np.array([.35, .55, 1.0]) * (0.25 + 0.75 * np.clip(d[..., 1], 0, 1))[..., None]
+    ground = np.array([.18, .15, .12]) * np.clip(-d[..., 1], 0, 1)[..., None] * .5
+    sun_dir = np.array([.45, .65, .6]) + .05 * rng.randn(3)
+    sun_dir /= np.linalg.norm(sun_dir)
+    c = np.clip((d * sun_dir).sum(-1), 0, 1)
+    sun = np.array([1.0, .9, .7]) * (40.0 * c ** 400 + 0.6 * c ** 12)[..., None]
+    return _rgbe_encode(sky + ground + sun)
+
+
+def write_hdr(path, rgbe_tex):
+    """Writes the RGBE texels as a flat (non-RLE) Radiance .hdr whose FILE rows are the texture rows reversed:
+    texture::bitmap loads with flip=true (src/texture/texture_bitmap.cpp:55-57)."""
+    h, w = rgbe_tex.shape[:2]
+    with open(path, "wb") as f:
+        f.write(b"#?RADIANCE\nFORMAT=32-bit_rle_rgbe\n\n-Y %d +X %d\n" % (h, w))
+        f.write(np.ascontiguousarray(rgbe_tex[::-1]).tobytes())
+
+
+def env_light(path, w=1024, h=512, seed=5, rot=0.0, scale=1.0):
+    """kwargs for SceneBuilder.set_env: the file for the reference, the decoded texels for the C ABI."""
+    rgbe = procedural_env(w, h, seed)
+    write_hdr(path, rgbe)
+    return dict(rgb=_rgbe_decode(rgbe), rot=rot, scale=scale, path=path)
+
+
+# ------------------------------------------------------------------------------------------------
 # Ray batches (host, FP64, float-representable origins) — SURVEY.md §8d C1/C3
 # ------------------------------------------------------------------------------------------------
 def camera_rays(camera, width, height):

@@ -89,6 +89,70 @@ struct SceneExport {
         return o;
     }
 
+    // light::env keeps its image as an underlying texture::bitmap ("envmap", src/light/light_env.cpp:42-47) but
+    // rot_ and scale_ are private.  Both follow from ONE deterministic sample_direct() call: the Dist2 the light
+    // samples from is invariant to scale_, so the texel (x, y) it picks for u = (.5,.5,.5,.5) can be recomputed
+    // here from the raw image with the reference's own arithmetic (light_env.cpp:64-72, math.h:398-431); the
+    // azimuth of the returned direction minus that texel's azimuth is rot_, and eval() over the raw texel is scale_.
+    std::vector<float> env_rgb;
+    void probe_env_light(const Light* light, LmcuLight& l) {
+        auto* tex = dynamic_cast<Texture*>(light->underlying("envmap"));
+        if (!tex) LM_THROW_EXCEPTION(Error::Unsupported, "light::env without an underlying envmap texture");
+        const auto buf = tex->buffer();
+        if (!buf.data || buf.c < 3) LM_THROW_EXCEPTION(Error::Unsupported, "light::env: envmap must have >= 3 channels");
+        const int w = buf.w, h = buf.h;
+        env_rgb.resize(size_t(w) * h * 3);
+        for (size_t i = 0; i < size_t(w) * h; i++) for (int k = 0; k < 3; k++) env_rgb[3 * i + k] = buf.data[buf.c * i + k];
+        std::vector<Float> ls(size_t(w) * h);
+        for (int i = 0; i < w * h; i++) {
+            const Float mx = std::max({ Float(env_rgb[3 * i]), Float(env_rgb[3 * i + 1]), Float(env_rgb[3 * i + 2]) });
+            ls[i] = mx * std::sin(Pi * (Float(i) / w + .5_f) / h);
+        }
+        Dist2 dist;
+        dist.init(ls, w, h);
+        const auto geom = PointGeometry::make_on_surface(Vec3(0_f), Vec3(0_f, 1_f, 0_f), Vec3(0_f, 1_f, 0_f));
+        Light::RaySampleU u{ Vec2(.5_f), .5_f, Vec2(.5_f) };
+        Float rot = 0_f, scale = 1_f;
+        bool found = false;
+        // a few (ud) choices in case the sampled direction is exactly tangent to the probe surface (pdf 0 -> no sample)
+        for (Float a : { .5_f, .25_f, .75_f, .125_f }) {
+            u.ud = Vec2(a, .5_f);
+            const auto sL = light->sample_direct(u, geom, Transform(Mat4(1_f)));
+            if (!sL) continue;
+            const Vec3 d = -sL->wo;
+            const int y = dist.m.sample(u.ud[0]);
+            const int x = dist.ds[y].sample(u.ud[1]);
+            const Float phi_tex = 2_f * Pi * (x + u.up[0]) / w;
+            rot = std::atan2(d.x, d.z) - phi_tex;
+            rot -= 2_f * Pi * std::floor(rot / (2_f * Pi));
+            const Vec3 Le = light->eval(sL->geom, sL->wo, false);
+            const size_t i = size_t(y) * w + x;
+            int k = 0;
+            for (int c = 1; c < 3; c++) if (env_rgb[3 * i + c] > env_rgb[3 * i + k]) k = c;
+            if (env_rgb[3 * i + k] > 0.f) { scale = Le[k] / Float(env_rgb[3 * i + k]); found = true; break; }
+        }
+        if (!found) LM_THROW_EXCEPTION(Error::Unsupported, "light::env: could not recover rot/scale");
+        // cross-check on other texels: eval() at the texel-centre direction must return texel * scale
+        for (int k = 1; k <= 7; k++) {
+            const int x = (w * k) / 8, y = (h * k) / 8;
+            const Float t = Pi * (y + .5_f) / h, p = 2_f * Pi * (x + .5_f) / w + rot;
+            const Vec3 wo = -Vec3(std::sin(t) * std::sin(p), std::cos(t), std::sin(t) * std::cos(p));
+            const Vec3 Le = light->eval(PointGeometry::make_infinite(wo), wo, false);
+            const size_t i = size_t(y) * w + x;
+            for (int c = 0; c < 3; c++) {
+                const Float expect = Float(env_rgb[3 * i + c]) * scale;
+                if (std::abs(Le[c] - expect) > 1e-6_f * std::max(1_f, std::abs(expect))) {
+                    LM_THROW_EXCEPTION(Error::Unsupported, "light::env: recovered rot/scale fail the cross-check");
+                }
+            }
+        }
+        l.type = LMCU_LIGHT_ENV;
+        l.env_w = w; l.env_h = h;
+        l.env_rot = glm::degrees(rot);
+        l.env_scale = scale;
+        l.env_rgb = env_rgb.data();
+    }
+
     void gather(const Scene& scene, bool shading) {
         std::map<const Mesh*, int> mesh_ids;
         std::map<const Material*, int> mat_ids;
@@ -101,14 +165,19 @@ struct SceneExport {
                 // environment light (src/scene.cpp:103-110)
                 LmcuLight l{};
                 const auto key = node.primitive.light->key();
-                if (key != "light::envconst") {
-                    LM_THROW_EXCEPTION(Error::Unsupported, "renderer::*_cuda: unsupported light [key='{}']", key);
-                }
-                l.type = LMCU_LIGHT_ENVCONST;
                 l.primitive = -1;
                 l.node_index = node.index;
-                const auto Le = node.primitive.light->eval(PointGeometry::make_infinite(Vec3(0_f, 0_f, 1_f)), Vec3(0_f, 0_f, 1_f), false);
-                l.Ke[0] = Le.x; l.Ke[1] = Le.y; l.Ke[2] = Le.z;
+                if (key == "light::envconst") {
+                    l.type = LMCU_LIGHT_ENVCONST;
+                    const auto Le = node.primitive.light->eval(PointGeometry::make_infinite(Vec3(0_f, 0_f, 1_f)), Vec3(0_f, 0_f, 1_f), false);
+                    l.Ke[0] = Le.x; l.Ke[1] = Le.y; l.Ke[2] = Le.z;
+                }
+                else if (key == "light::env") {
+                    probe_env_light(node.primitive.light, l);
+                }
+                else {
+                    LM_THROW_EXCEPTION(Error::Unsupported, "renderer::*_cuda: unsupported light [key='{}']", key);
+                }
                 lights.push_back(l);
                 return;
             }

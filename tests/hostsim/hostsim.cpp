@@ -31,7 +31,7 @@ struct SimScene {
         DevScene d{};
         d.nodes = nodes.data(); d.t32 = fp32 ? t32.data() : nullptr; d.t64 = fp32 ? nullptr : t64.data();
         d.shade = shade.data(); d.prims = ps.prims.data(); d.mats = ps.mats.data(); d.lights = ps.lights.data();
-        d.emit = ps.emit.data(); d.cdf = ps.cdf.data(); d.env_tex = nullptr;
+        d.emit = ps.emit.data(); d.cdf = ps.cdf.data(); d.env_tex = ps.env_tex.data();
         d.num_prims = (int)ps.prims.size(); d.num_lights = (int)ps.lights.size(); d.env_light = ps.env_light;
         d.num_tris = ps.nt; d.cam = ps.cam;
         return d;

@@ -194,6 +194,24 @@ def test_g3_pt_all_materials_env_light(reference):
     rs.close(); sc.close()
 
 
+def test_g3_pt_env_image_light(reference, tmp_path):
+    """C4 variant: light::env with a procedurally written 512x256 .hdr (sun lobe + sky gradient), rot and scale."""
+    env = scenes.env_light(str(tmp_path / "env.hdr"), w=512, h=256, rot=75.0, scale=0.8)
+    sb = scenes.instanced_spheres(grid=2, num_theta=24, env=env)
+    sc, rs = lmcu.Scene(sb), reference.RefScene(sb)
+    p = abi.render_params(192, 108)
+    fr, _, _ = rs.render("raycast", p)
+    fg, _ = sc.render("raycast", p)
+    d = np.abs(fg - fr).max(axis=2)
+    assert (d > 1e-4).mean() < 3e-3 and rmse(fg[d <= 1e-4], fr[d <= 1e-4]) <= 1e-6
+    for mode in (abi.SAMPLING_MIS, abi.SAMPLING_NEE, abi.SAMPLING_NAIVE):
+        p = abi.render_params(160, 90, spp=256, max_verts=12, sampling_mode=mode)
+        fr, _, _ = rs.render("pt", p)
+        fg, _ = sc.render("pt", p)
+        assert_pt_parity(fr, fg, 256, rel_mean=0.015)
+    rs.close(); sc.close()
+
+
 def test_sample_split_is_additive():
     """Sample split (multi-GPU partition): two half renders with disjoint sample offsets sum to the full render."""
     sb = scenes.cornell_spheres(16)

@@ -90,3 +90,19 @@ def test_renderer_pt_and_ao_cuda_cornell(plugin):
     fc, _, _ = rs.render("renderer::ao_cuda", pa)
     assert_pt_parity(fr, fc, 64, rel_mean=0.01)
     rs.close()
+
+
+def test_renderer_pt_cuda_env_light_probed(plugin, tmp_path):
+    """light::env: image taken from the underlying texture, rot/scale recovered from one sample_direct() probe."""
+    env = scenes.env_light(str(tmp_path / "env.hdr"), w=256, h=128, rot=200.0, scale=2.5)
+    sb = scenes.instanced_spheres(grid=2, num_theta=16, env=env)
+    rs = plugin.RefScene(sb)
+    p = abi.render_params(160, 90, spp=128, max_verts=10)
+    fr, _, _ = rs.render("pt", p)
+    fc, _, _ = rs.render("renderer::pt_cuda", p)
+    assert_pt_parity(fr, fc, 128, rel_mean=0.015)
+    fr, _, _ = rs.render("raycast", abi.render_params(160, 90))
+    fc, _, _ = rs.render("renderer::raycast_cuda", abi.render_params(160, 90))
+    d = np.abs(fc - fr).max(axis=2)
+    assert (d > 1e-4).mean() < 3e-3
+    rs.close()
