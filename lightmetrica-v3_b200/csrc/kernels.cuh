@@ -34,6 +34,8 @@ struct SurfPoint {
     F3 p, n, gn;
     int32_t prim;      // primitive ordinal
     int32_t face;
+    int32_t material;  // index into DevScene::mats
+    int32_t light;     // index into DevScene::lights if the surface is an area light, else -1
 };
 
 LMCU_HD void tri_fetch(const DevScene& s, uint32_t tri, F3& p1, F3& p2, F3& p3, int32_t& prim, int32_t& face) {
@@ -59,6 +61,7 @@ LMCU_HD SurfPoint surface_point(const DevScene& s, uint32_t tri, float u, float 
     const float4 n1 = s.shade[tri].n1, n2 = s.shade[tri].n2, n3 = s.shade[tri].n3;
     sp.n = normalize(f3(n1.x, n1.y, n1.z) * w + f3(n2.x, n2.y, n2.z) * u + f3(n3.x, n3.y, n3.z) * v);
     sp.gn = normalize(cross(p2 - p1, p3 - p1)) * n1.w;
+    sp.material = (int32_t)f2u(n2.w); sp.light = (int32_t)f2u(n3.w);
     return sp;
 }
 
@@ -103,7 +106,7 @@ LMCU_HD void raycast_pixel(const DevScene& s, const RaycastParams& p, int x, int
         if (p.visualize_normal) {
             c = f3(fabsf(sp.n.x), fabsf(sp.n.y), fabsf(sp.n.z));
         } else {
-            c = p.has_color ? f3(p.color[0], p.color[1], p.color[2]) : mat_reflectance(s.mats[s.prims[sp.prim].material]);
+            c = p.has_color ? f3(p.color[0], p.color[1], p.color[2]) : mat_reflectance(s.mats[sp.material]);
             if (!p.use_constant_color) {
                 const F3 d = f3((float)r.d.x, (float)r.d.y, (float)r.d.z);
                 c = c * (0.2f + 0.8f * fabsf(dot(sp.n, -d)));
@@ -278,12 +281,11 @@ LMCU_HD ShadeOut pt_shade_body(const DevScene& s, const PtParams& p, float4 ro, 
     }
 
     const SurfPoint sp = surface_point(s, (uint32_t)tri, hit.y, hit.z);
-    const PrimDev& prim = s.prims[sp.prim];
-    const MaterialDev& mat = s.mats[prim.material];
+    const MaterialDev& mat = s.mats[sp.material];
 
     // direct hit on an emitter (renderer_pt.cpp:248-270)
-    if (prim.light >= 0 && direct_ok) {
-        const LightDev& l = s.lights[prim.light];
+    if (sp.light >= 0 && direct_ok) {
+        const LightDev& l = s.lights[sp.light];
         if (dot(wi, sp.n) > 0.f) {                                          // light_area.cpp:185-187
             float mis = 1.f;
             if (p.sampling_mode == 2 && prev_nee) {

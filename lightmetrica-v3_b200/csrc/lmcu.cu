@@ -19,7 +19,7 @@
 #include "trace.cuh"
 
 #ifndef LMCU_SHADE_MINB
-#define LMCU_SHADE_MINB 2  // resident 256-thread CTAs per SM the shade kernel is compiled for
+#define LMCU_SHADE_MINB 3  // resident 256-thread CTAs per SM the shade kernel is compiled for
 #endif
 #ifndef LMCU_MINB
 #define LMCU_MINB 6      // resident 128-thread CTAs per SM the queue kernels are compiled for (register budget)
