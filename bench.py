@@ -11,7 +11,8 @@ Cornell box with a diffuse and a glass UV sphere (32 268 triangles), area-light 
 
 N > 1 (torchrun, one rank per GPU): sample split.  The scene and BVH are replicated, rank r renders
 its own `spp` samples of every pixel with disjoint counter-RNG sample indices (sample_offset =
-r*spp), the fp32 films are summed with ONE NCCL reduce over NVLink, rank 0 scales by 1/(N*spp).
+r*spp); rank 0 then combines the fp32 films with liblmcu's own kernel, which reads the peers' films
+over NVLink peer memory and fuses the sum with the 1/(N*spp) rescale (--reduce nccl: dist.reduce).
 Per-GPU work is fixed as N grows => "scaling": "weak".  value = paths of all ranks / max-over-ranks
 device time (the reduce is inside the timed region).
 """
@@ -114,6 +115,56 @@ def run_reference(args):
     }))
 
 
+def make_reducer(torch, dist, lmcu, D, sc, rank, world, local_rank, mode):
+    """Film combine for one scene: 'p2p' = liblmcu's fused peer-memory reduce+rescale kernel, 'nccl' = dist.reduce."""
+    if mode == "p2p":
+        return D.PeerFilmReducer(dist, rank, world, sc.film_ipc_handle, lambda h: lmcu.ipc_open(local_rank, h),
+                                 sc.film_reduce_peers, torch.cuda.synchronize)
+
+    def nccl_reduce(total_spp):
+        ptr, n = sc.film_device()
+        film = D.film_as_tensor(torch, ptr, n, local_rank)
+        D.reduce_and_rescale(film, total_spp, rank, world, dist)
+    return nccl_reduce
+
+
+def accel_rates(torch, lmcu, scenes, stream):
+    """BASELINE.json configs[2] (C3): closest-hit throughput on the 9 999 392-triangle heightfield with DEVICE-resident
+    ray batches — coherent pinhole rays and incoherent cosine-bounce rays.  Informational (not the headline)."""
+    import numpy as np
+    sb = scenes.heightfield_scene(2236)
+    sc = lmcu.Scene(sb)
+    sc.set_stream(stream.cuda_stream)
+    out = {"triangles": int(sc.build_stats.num_triangles), "build_ms": sc.build_stats.elapsed * 1e3,
+           "bvh_bytes": int(sc.build_stats.node_bytes + sc.build_stats.triangle_bytes)}
+
+    def run(rays, reps=3):
+        d_rays = torch.from_numpy(rays.view(np.float64).reshape(-1, 8)).cuda()
+        d_hits = torch.empty((len(rays), 4), dtype=torch.float64, device="cuda")
+        best = 1e9
+        for _ in range(reps + 1):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            sc.intersect_device(d_rays.data_ptr(), len(rays), d_hits.data_ptr(), stream.cuda_stream)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1) * 1e-3)
+        return len(rays) / best / 1e6, d_hits.cpu().numpy().view(scenes.HIT_DTYPE).reshape(-1)
+
+    rays = scenes.camera_rays(sb.camera, 2048, 2048)
+    out["coherent_mrays_per_s"], hits = run(rays)
+    p = sb.meshes[0][0]
+    gn = np.cross(p[:, 1] - p[:, 0], p[:, 2] - p[:, 0])
+    gn /= np.linalg.norm(gn, axis=1, keepdims=True)
+    bounce = scenes.bounce_rays(rays, hits, lambda h: gn[h["face"]].copy())
+    out["incoherent_mrays_per_s"], _ = run(bounce)
+    sc.intersect(rays[:1 << 18], counted=True)
+    out["nodes_per_ray"], out["tris_per_ray"] = sc.nodes_per_ray, sc.tris_per_ray
+    out["rays"] = {"coherent": int(len(rays)), "incoherent": int(len(bounce))}
+    sc.close()
+    return out
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -136,23 +187,20 @@ def run_ours(args):
     sb = scenes.cornell_spheres(64)
     sc = lmcu.Scene(sb, device=local_rank)
     stream = torch.cuda.Stream(device=local_rank)    # handle 0 (legacy default stream) would mean "the scene's own stream"
-    torch.cuda.set_stream(stream)                    # NCCL reduce + film ops follow on the same stream
+    torch.cuda.set_stream(stream)
     sc.set_stream(stream.cuda_stream)
     npix = W * H
-    film_ptr = None
+    reducer = None
 
     def step():
-        """One pass: render this rank's samples, reduce the film, scale.  Returns the stats dict."""
-        out = {}
-
-        def render_sums(offset, count):
-            p = abi.render_params(W, H, spp=count, max_verts=MAX_VERTS, seed=SEED, sample_offset=offset, rescale=0)
-            _, out["st"] = sc.render("pt", p, download=False)
-            ptr, n = sc.film_device()
-            return D.film_as_tensor(torch, ptr, n, local_rank)
-
-        film = D.render_pt_sample_split(render_sums, world * spp, rank, world, dist)
-        return out["st"], film
+        """One pass of the hot path: render this rank's samples of every pixel (sums), combine the films, rescale."""
+        nonlocal reducer
+        p = abi.render_params(W, H, spp=spp, max_verts=MAX_VERTS, seed=SEED, sample_offset=rank * spp, rescale=0)
+        _, st = sc.render("pt", p, download=False)
+        if reducer is None:
+            reducer = make_reducer(torch, dist, lmcu, D, sc, rank, world, local_rank, args.reduce)
+        reducer(world * spp)
+        return st
 
     def sync():
         torch.cuda.synchronize()
@@ -170,8 +218,7 @@ def run_ours(args):
     stats = []
     e0.record(stream)
     for _ in range(args.steps):
-        st, film = step()
-        stats.append(st)
+        stats.append(step())
     e1.record(stream)
     sync()
     clocks = sampler.stop() if rank == 0 else None
@@ -183,34 +230,32 @@ def run_ours(args):
     paths_per_step = npix * spp * world
     value = paths_per_step / (ms_per_step * 1e-3) / 1e6
 
-    # ---- end-to-end through the public API with HOST buffers: upload + build + render + film download
-    e2e = None
-    if rank == 0 or world > 1:
-        desc_bytes = sum(p.nbytes + (n.nbytes if n is not None else 0) for p, n in sb.meshes)
-        sync()
-        t0 = time.perf_counter()
-        e2e_steps = max(1, min(args.steps, 2))
-        for _ in range(e2e_steps):
-            sc2 = lmcu.Scene(sb, device=local_rank)                   # H2D scene + BVH build
-            p = abi.render_params(W, H, spp=spp, max_verts=MAX_VERTS, seed=SEED, sample_offset=rank * spp, rescale=0)
-            sc2.render("pt", p, download=False)
-            ptr, n = sc2.film_device()
-            film2 = D.film_as_tensor(torch, ptr, n, local_rank)
-            if world > 1:
-                torch.cuda.synchronize()
-                dist.reduce(film2, dst=0, op=dist.ReduceOp.SUM)
-            host = film2.mul(1.0 / (world * spp)).cpu() if rank == 0 else None   # D2H of the result
-            torch.cuda.synchronize()
-            sc2.close()
-        t = torch.tensor([(time.perf_counter() - t0) / e2e_steps], device="cuda")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e = {"value": paths_per_step / float(t.item()) / 1e6, "unit": "Mpaths/s",
-               "h2d_bytes_per_step": int(desc_bytes), "d2h_bytes_per_step": int(npix * 3 * 4),
-               "what": "lmcu.Scene(desc) [H2D + BVH build] + render('pt') + film reduce + D2H, wall clock, max over ranks"}
+    # ---- end to end through the public API with HOST buffers: scene description (host arrays) -> H2D upload ->
+    # BVH build -> render -> film combine -> film D2H into a host array, every step, wall clock, max over ranks
+    desc_bytes = sum(p.nbytes + (n.nbytes if n is not None else 0) for p, n in sb.meshes)
+    sync()
+    e2e_steps = max(1, min(args.steps, 2))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        sc2 = lmcu.Scene(sb, device=local_rank)
+        sc2.set_stream(stream.cuda_stream)
+        p = abi.render_params(W, H, spp=spp, max_verts=MAX_VERTS, seed=SEED, sample_offset=rank * spp, rescale=0)
+        sc2.render("pt", p, download=False)
+        make_reducer(torch, dist, lmcu, D, sc2, rank, world, local_rank, "nccl" if world > 1 else args.reduce)(world * spp)
+        host_film = sc2.film_download(W, H) if rank == 0 else None      # D2H of the result
+        torch.cuda.synchronize()
+        sc2.close()
+    t = torch.tensor([(time.perf_counter() - t0) / e2e_steps], device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e = {"value": paths_per_step / float(t.item()) / 1e6, "unit": "Mpaths/s",
+           "h2d_bytes_per_step": int(desc_bytes), "d2h_bytes_per_step": int(npix * 3 * 4),
+           "what": "lmcu.Scene(host scene description) [H2D + BVH build] + render('pt') + film combine + film D2H, "
+                   "wall clock, max over ranks"}
 
     if rank == 0:
-        # ---- roofline of the dominant kernel (k_pt_extend), SURVEY.md §8(d)
+        assert host_film is not None and np.isfinite(host_film).all() and host_film.mean() > 0.01
+        # ---- roofline of the dominant kernel (k_pt_extend_q), SURVEY.md 8(d)
         # counters pass (separate, untimed): mean nodes / triangles fetched per closest-hit ray
         pc = abi.render_params(W, H, spp=8, max_verts=MAX_VERTS, seed=SEED, count_traversal=True)
         _, stc = sc.render("pt", pc, download=False)
@@ -222,15 +267,26 @@ def run_ours(args):
         total_s = sum(s["elapsed"] for s in stats)
         peak, peak_src = load_peaks()
         achieved = ext_rays * b_ray / ext_s / 1e9
+        traffic, traffic_src = None, None
+        try:
+            with open(os.path.join(ROOT, "profiles", "r01_extend_traffic.json")) as f:
+                tr = json.load(f)
+            traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]          # bytes per launch (8 Mi-ray queue)
+            traffic_src = tr["source"]
+        except Exception:
+            pass
         roofline = {
-            "bound": "hbm", "kernel": "k_pt_extend (closest-hit BVH traversal)", "achieved": achieved, "peak": peak,
-            "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+            "bound": "hbm", "kernel": "k_pt_extend_q (closest-hit BVH traversal over the path queue)", "achieved": achieved,
+            "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes per launch",
+            "traffic_source": traffic_src, "peak_source": peak_src,
             "bytes_per_ray": b_ray, "nodes_per_ray": n_nodes, "tris_per_ray": n_tris,
+            "algorithmic_bytes_per_launch": ext_rays / max(1, ext_launches) * b_ray,
             "rays_per_launch": ext_rays / max(1, ext_launches), "avg_launch_ms": ext_s / max(1, ext_launches) * 1e3,
             "share_of_step": {"extend": ext_s / total_s, "shade": sum(s["shade_seconds"] for s in stats) / total_s,
                               "shadow": sum(s["shadow_seconds"] for s in stats) / total_s},
-            "note": "BVH + triangles of C2 are 1.9 MB and stay L1/L2-resident: algorithmic bytes are served by cache, "
-                    "so frac is a cache-level figure, not DRAM utilisation",
+            "note": "BVH + triangles of C2 are 1.9 MB and stay L1/L2-resident: the algorithmic bytes are served by cache "
+                    "(measured DRAM traffic is the ray queue only), so frac is algorithmic bytes over the HBM peak, not "
+                    "DRAM utilisation; the kernel is bound by instruction issue of divergent warps (profiles/)",
         }
         # ---- CPU baseline: the reference on this box's host cores, bounded sample
         cpu = None
@@ -242,6 +298,12 @@ def run_ours(args):
                        "sample": "%dx%d @ %d spp (full C2 image, bounded spp), 1 warm-up + 1 timed render" % (W, H, REF_SPP_PER_STEP)}
         except Exception as ex:  # the baseline must never take the bench line down
             cpu = {"value": None, "unit": "Mpaths/s", "cores": 0, "kind": "reference", "sample": "failed: %s" % ex}
+        accel = None
+        if world == 1 and not args.no_accel:
+            try:
+                accel = accel_rates(torch, lmcu, scenes, stream)
+            except Exception as ex:
+                accel = {"failed": str(ex)}
         rays = sum(s["rays"] for s in stats)
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps,
@@ -249,14 +311,16 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "f32 shading / f64 ray-triangle", "data": "synthetic",
             "config": {"workload": "C2 renderer::pt Cornell box + diffuse/glass UV spheres (32268 tris) 1920x1080 "
                                    "max_verts=20 sampling_mode=mis seed=42", "spp_per_gpu": spp, "total_spp": spp * world,
-                       "parallelism": "sample split x%d + NCCL film reduce" % world,
-                       "l2": "path queues (72 MB/iteration) + film exceed no cache assumption: every wavefront iteration "
-                             "streams 1M-path SoA queues through HBM; inputs are regenerated each step"},
+                       "parallelism": "sample split x%d, film combine = %s" % (
+                           world, "fused peer-memory reduce+rescale kernel over NVLink (CUDA IPC)" if args.reduce == "p2p" else "NCCL reduce"),
+                       "l2": "inputs larger than L2: every wavefront iteration streams the 8 Mi-path SoA queues "
+                             "(1.2 GB) through HBM, and every step regenerates all paths"},
             "mrays_per_s": rays * world / (ms_total * 1e-3) / 1e6,
-            "e2e": e2e, "gpu_launches": int(sum(s["kernel_launches"] for s in stats)),
-            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+            "e2e": e2e, "gpu_launches": int(sum(s["kernel_launches"] for s in stats)) + args.steps,
+            "roofline": roofline, "cpu_baseline": cpu, "accel_c3": accel, "clocks": clocks,
         }))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -267,6 +331,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--spp", type=int, default=GPU_SPP)
+    ap.add_argument("--reduce", default="p2p", choices=["p2p", "nccl"], help="film combine across GPUs")
+    ap.add_argument("--no-accel", action="store_true", help="skip the informational C3 accel batch rates")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -220,6 +220,23 @@ int lmcu_film_rescale(LmcuScene* scene, double s);
 /* Copy the device film to a host buffer. */
 int lmcu_film_download(LmcuScene* scene, float* film_rgb);
 
+/* -- multi-GPU film combine over NVLink peer memory (sample split) -----------------------
+ * Every GPU renders its own samples with rescale=0 into its own device film.  The root then runs ONE
+ * kernel that reads the peers' films directly over NVLink (P2P loads), adds them to its own film and
+ * applies film::rescale (src/film/film_bitmap.cpp:244-248, called once by renderer_pt.cpp:307-309) as
+ * the epilogue: film_root = (film_root + sum_p film_p) * scale.  Peers in the SAME process pass their
+ * lmcu_film_device_ptr() after lmcu_enable_peer_access(); peers in OTHER processes (one rank per GPU)
+ * export a CUDA IPC handle and the root opens it.  The caller orders the kernels (stream/event/barrier):
+ * the peers' renders must have completed before the call and their films must stay untouched until
+ * it returns (it synchronises the root's stream). */
+#define LMCU_IPC_HANDLE_BYTES 64
+#define LMCU_MAX_PEERS 15
+int lmcu_film_ipc_export(LmcuScene* scene, void* handle /* LMCU_IPC_HANDLE_BYTES */);
+int lmcu_ipc_open(int device, const void* handle, void** d_ptr);
+int lmcu_ipc_close(int device, void* d_ptr);
+int lmcu_enable_peer_access(int device, int peer_device);
+int lmcu_film_reduce_peers(LmcuScene* root, void* const* peer_films, int num_peers, double scale);
+
 #ifdef __cplusplus
 }
 #endif

@@ -11,6 +11,8 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -230,6 +232,8 @@ __global__ void k_pt_advance(PtParams p, PtCounters* ctr, int cur) {
     ctr->iterations += 1;
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // Two compactions in one pass (next-path queue and shadow queue): the per-warp counts travel packed
 // 16+16 bits through ONE shared-memory scan, so a shade iteration costs 3 barriers instead of 6.
 __device__ __forceinline__ void block_compact2(bool p0, bool p1, uint32_t* counter0, uint32_t* counter1,
@@ -266,6 +270,14 @@ __global__ void __launch_bounds__(256, LMCU_SHADE_MINB) k_pt_shade(DevScene s, P
     const uint32_t n = ctr->count[cur];
     for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
         const uint32_t i = base + threadIdx.x;
+        {   // the queues stream from HBM: pull the next grid-stride tile of this CTA into L2 while this one is shaded
+            const uint32_t nx = i + gridDim.x * blockDim.x;
+            if (nx < n && (threadIdx.x & 7u) == 0u) {          // one prefetch per 128-byte line of float4s
+                prefetch_l2(qin.ray_o + nx); prefetch_l2(qin.ray_d + nx); prefetch_l2(qin.thr_pix + nx);
+                prefetch_l2(qin.aux + nx); prefetch_l2(hits + nx);
+                if ((threadIdx.x & 15u) == 0u) prefetch_l2(qin.info + nx);
+            }
+        }
         ShadeOut o;
         o.alive = false; o.shadow = false;
         if (i < n) {
@@ -377,20 +389,80 @@ __global__ void k_scale(float* film, size_t n, float s) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) film[i] *= s;
 }
 
+// root = (root + sum over peers) * scale; the peer pointers are NVLink peer-mapped (P2P / CUDA IPC), so the
+// loads below travel over NVLink while the FADDs and the store run here: reduce + film::rescale in one pass.
+struct PeerFilms { const float* p[LMCU_MAX_PEERS]; };
+
+__global__ void __launch_bounds__(256) k_film_reduce_peers(float* __restrict__ root, PeerFilms peers, int num_peers, size_t n, float scale) {
+    const size_t n4 = n / 4;
+    float4* root4 = reinterpret_cast<float4*>(root);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        float4 acc = root4[i];
+        for (int k = 0; k < num_peers; k++) {
+            const float4 v = __ldcv(reinterpret_cast<const float4*>(peers.p[k]) + i);   // volatile-cached: peer memory is not coherent in L1
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        root4[i] = make_float4(acc.x * scale, acc.y * scale, acc.z * scale, acc.w * scale);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+        const size_t i = n4 * 4 + threadIdx.x;
+        float acc = root[i];
+        for (int k = 0; k < num_peers; k++) acc += __ldcv(peers.p[k] + i);
+        root[i] = acc * scale;
+    }
+}
+
 // ================================================================================================
 // host side
 // ================================================================================================
+// Scratch allocations (path pools, films) are recycled across scenes of a process: cudaMalloc / cudaFree of
+// the 1.7 GB of path queues cost far more than a BVH build, and a host that re-creates its scene per render
+// (the Lightmetrica plugin does) would pay it every time.  Freed blocks of >= 1 MiB are parked here per
+// (device, size), at most kCacheBytes per process, and handed out again on the next equal-sized request.
+namespace {
+struct BlockCache {
+    std::mutex mu;
+    std::multimap<std::pair<int, size_t>, void*> blocks;
+    size_t bytes = 0;
+    static constexpr size_t kCacheBytes = size_t(6) << 30;
+    void* take(int device, size_t n) {
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = blocks.find({ device, n });
+        if (it == blocks.end()) return nullptr;
+        void* p = it->second;
+        blocks.erase(it);
+        bytes -= n;
+        return p;
+    }
+    bool park(int device, size_t n, void* p) {
+        std::lock_guard<std::mutex> lk(mu);
+        if (n < (size_t(1) << 20) || bytes + n > kCacheBytes) return false;
+        blocks.insert({ { device, n }, p });
+        bytes += n;
+        return true;
+    }
+};
+BlockCache g_cache;
+}  // namespace
+
 template <typename T>
 struct DBuf {
     T* p = nullptr;
     size_t n = 0;
+    int device = -1;
     cudaError_t alloc(size_t count) {
         release();
         n = count;
         if (count == 0) return cudaSuccess;
+        cudaGetDevice(&device);
+        p = (T*)g_cache.take(device, count * sizeof(T));
+        if (p) return cudaSuccess;
         return cudaMalloc((void**)&p, count * sizeof(T));
     }
-    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void release() {
+        if (p && !g_cache.park(device, n * sizeof(T), p)) cudaFree(p);
+        p = nullptr; n = 0;
+    }
     ~DBuf() { release(); }
     DBuf() = default;
     DBuf(const DBuf&) = delete;
@@ -754,6 +826,60 @@ int lmcu_film_download(LmcuScene* s, float* film_rgb) {
     if (!s || !s->film.p) return fail(LMCU_ERR_UNSUPPORTED, "no film rendered yet");
     CU(cudaSetDevice(s->device));
     CU(cudaMemcpyAsync(film_rgb, s->film.p, s->film.n * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return LMCU_OK;
+}
+
+int lmcu_film_ipc_export(LmcuScene* s, void* handle) {
+    if (!s || !s->film.p) return fail(LMCU_ERR_UNSUPPORTED, "no film rendered yet");
+    if (!handle) return fail(LMCU_ERR_INVALID_ARGUMENT, "null handle");
+    static_assert(sizeof(cudaIpcMemHandle_t) == LMCU_IPC_HANDLE_BYTES, "IPC handle size");
+    CU(cudaSetDevice(s->device));
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, s->film.p));
+    memcpy(handle, &h, sizeof(h));
+    return LMCU_OK;
+}
+
+int lmcu_ipc_open(int device, const void* handle, void** d_ptr) {
+    if (!handle || !d_ptr) return fail(LMCU_ERR_INVALID_ARGUMENT, "null argument");
+    CU(cudaSetDevice(device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    CU(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return LMCU_OK;
+}
+
+int lmcu_ipc_close(int device, void* d_ptr) {
+    CU(cudaSetDevice(device));
+    CU(cudaIpcCloseMemHandle(d_ptr));
+    return LMCU_OK;
+}
+
+int lmcu_enable_peer_access(int device, int peer_device) {
+    if (device == peer_device) return LMCU_OK;
+    CU(cudaSetDevice(device));
+    int can = 0;
+    CU(cudaDeviceCanAccessPeer(&can, device, peer_device));
+    if (!can) return fail(LMCU_ERR_UNSUPPORTED, "devices are not P2P-capable");
+    const cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return LMCU_OK; }
+    CU(e);
+    return LMCU_OK;
+}
+
+int lmcu_film_reduce_peers(LmcuScene* s, void* const* peer_films, int num_peers, double scale) {
+    if (!s || !s->film.p) return fail(LMCU_ERR_UNSUPPORTED, "no film rendered yet");
+    if (num_peers < 0 || num_peers > LMCU_MAX_PEERS) return fail(LMCU_ERR_INVALID_ARGUMENT, "too many peers");
+    if (num_peers > 0 && !peer_films) return fail(LMCU_ERR_INVALID_ARGUMENT, "null peer list");
+    CU(cudaSetDevice(s->device));
+    PeerFilms pf{};
+    for (int k = 0; k < num_peers; k++) {
+        if (!peer_films[k]) return fail(LMCU_ERR_INVALID_ARGUMENT, "null peer film");
+        pf.p[k] = (const float*)peer_films[k];
+    }
+    k_film_reduce_peers<<<s->num_sms * 8, 256, 0, s->stream>>>(s->film.p, pf, num_peers, s->film.n, (float)scale);
+    CU(cudaGetLastError());
     CU(cudaStreamSynchronize(s->stream));
     return LMCU_OK;
 }

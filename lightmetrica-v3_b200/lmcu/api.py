@@ -23,6 +23,7 @@ EXPORTS = [
     "lmcu_scene_set_stream", "lmcu_scene_upload", "lmcu_accel_build", "lmcu_accel_intersect", "lmcu_accel_intersect_device",
     "lmcu_accel_intersect_counted", "lmcu_render_raycast", "lmcu_render_ao", "lmcu_render_pt",
     "lmcu_film_device_ptr", "lmcu_film_rescale", "lmcu_film_download",
+    "lmcu_film_ipc_export", "lmcu_ipc_open", "lmcu_ipc_close", "lmcu_enable_peer_access", "lmcu_film_reduce_peers",
 ]
 
 
@@ -52,6 +53,21 @@ def _check(rc):
 
 def device_count():
     return lib().lmcu_device_count()
+
+
+def ipc_open(device, handle):
+    """Maps a film exported by another process (Scene.film_ipc_handle) into this process; returns the device pointer."""
+    p = C.c_void_p()
+    _check(lib().lmcu_ipc_open(int(device), C.c_char_p(handle), C.byref(p)))
+    return p.value
+
+
+def ipc_close(device, ptr):
+    _check(lib().lmcu_ipc_close(int(device), C.c_void_p(ptr)))
+
+
+def enable_peer_access(device, peer_device):
+    _check(lib().lmcu_enable_peer_access(int(device), int(peer_device)))
 
 
 class Scene:
@@ -114,6 +130,18 @@ class Scene:
         film = np.empty((height, width, 3), dtype=np.float32)
         _check(lib().lmcu_film_download(self._h, film.ctypes.data_as(C.c_void_p)))
         return film
+
+    # -- multi-GPU film combine over peer memory (include/lmcu.h) -----------------------------------------
+    def film_ipc_handle(self):
+        """64-byte CUDA IPC handle of the device film (for a root in another process)."""
+        buf = C.create_string_buffer(64)
+        _check(lib().lmcu_film_ipc_export(self._h, buf))
+        return buf.raw
+
+    def film_reduce_peers(self, peer_ptrs, scale):
+        """film = (film + sum of the peer films) * scale in ONE kernel reading the peers over NVLink."""
+        arr = (C.c_void_p * max(1, len(peer_ptrs)))(*peer_ptrs)
+        _check(lib().lmcu_film_reduce_peers(self._h, arr, len(peer_ptrs), C.c_double(scale)))
 
     def close(self):
         if self._h:

@@ -6,7 +6,14 @@ of the streams is the same for any G); ONE reduce(sum) of the film goes to rank 
 NVLink on GPUs, gloo in the CPU tests of this host logic — which then applies the single
 film::rescale(1/processed) of the reference (renderer_pt.cpp:307-309).
 
-torch.distributed is plumbing only: the film tensor wraps the device buffer liblmcu rendered into.
+Two ways to combine the films:
+  reduce_and_rescale        torch.distributed reduce (NCCL) + one scale          — the baseline
+  PeerFilmReducer           liblmcu's own kernel: the root reads every peer film over NVLink peer memory
+                            (CUDA IPC mappings of the peers' device films) and fuses the sum with
+                            film::rescale in ONE pass (lmcu_film_reduce_peers)     — the default on GPUs
+
+torch.distributed is plumbing only (handle exchange, barriers): the film tensor wraps the device buffer
+liblmcu rendered into.
 """
 
 
@@ -42,3 +49,41 @@ def render_pt_sample_split(render_sums, total_spp, rank, world, dist=None):
     offset, count = sample_block(total_spp, rank, world)
     film = render_sums(offset, count)
     return reduce_and_rescale(film, total_spp, rank, world, dist)
+
+
+class PeerFilmReducer:
+    """Fused film reduce + rescale over peer memory, one process per GPU.
+
+    `film_handle()`   -> bytes: an opaque handle of this rank's film (Scene.film_ipc_handle)
+    `open_handle(h)`  -> a pointer-like object the root's reduce accepts (lmcu.ipc_open on the root's device)
+    `reduce(ptrs, s)` -> root only: film = (film + sum(peer films)) * s      (Scene.film_reduce_peers)
+    `sync()`          -> waits for this rank's render (torch.cuda.synchronize)
+    Opened mappings are cached per handle: the film buffer survives across renders of the same size.
+    """
+
+    def __init__(self, dist, rank, world, film_handle, open_handle, reduce, sync):
+        self.dist, self.rank, self.world = dist, rank, world
+        self.film_handle, self.open_handle, self.reduce, self.sync = film_handle, open_handle, reduce, sync
+        self._opened = {}
+        self._last = None
+
+    def __call__(self, total_spp):
+        scale = 1.0 / float(total_spp)
+        if self.world == 1:
+            self.sync()
+            self.reduce([], scale)
+            return
+        mine = self.film_handle()
+        # exchange handles only when somebody's film buffer changed (first step, or a new film size)
+        changed = [None] * self.world
+        self.dist.all_gather_object(changed, mine if mine != self._last else None)
+        self._last = mine
+        if self.rank == 0:
+            for r in range(1, self.world):
+                if changed[r] is not None:
+                    self._opened[r] = self.open_handle(changed[r])
+        self.sync()
+        self.dist.barrier()                 # every rank's samples are in its film
+        if self.rank == 0:
+            self.reduce([self._opened[r] for r in range(1, self.world)], scale)
+        self.dist.barrier()                 # peers may overwrite their films again

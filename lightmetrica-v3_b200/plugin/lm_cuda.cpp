@@ -15,6 +15,7 @@
 
 #include <map>
 #include <mutex>
+#include <thread>
 
 #include "../../include/lmcu.h"
 
@@ -338,7 +339,7 @@ class Renderer_CudaBase : public Renderer {
 protected:
     Scene* scene_;
     Film* film_;
-    int device_ = 0;
+    mutable int device_ = 0;
     mutable DeviceScene dev_;
 
 public:
@@ -434,12 +435,26 @@ public:
 
 LM_COMP_REG_IMPL(Renderer_AO_Cuda, "renderer::ao_cuda");
 
+/*
+\rst
+.. function:: renderer::pt_cuda
+
+   Wavefront path tracer on CUDA devices; same parameters as ``renderer::pt`` plus:
+
+   :param int device: CUDA device index. Default: 0.
+   :param list devices: Render on several GPUs of this machine by SAMPLE SPLIT: the scene and BVH are replicated,
+                        device *g* renders its block of the ``spp`` sample indices of every pixel into a private film,
+                        and the first device combines the films with one kernel over NVLink peer memory that also
+                        applies the final 1/spp rescale. Default: ``[device]``.
+\endrst
+*/
 class Renderer_PT_Cuda final : public Renderer_CudaBase {
 private:
     int max_verts_;
     std::optional<unsigned int> seed_;
     int sampling_mode_;
     long long spp_;
+    std::vector<int> devices_;
 
 public:
     virtual void construct(const Json& prop) override {
@@ -461,21 +476,66 @@ public:
             }
             spp_ = json::value<long long>(prop, "spp");
         }
+        devices_ = json::value<std::vector<int>>(prop, "devices", std::vector<int>{ device_ });
+        if (devices_.empty() || devices_.size() > LMCU_MAX_PEERS + 1) {
+            LM_THROW_EXCEPTION(Error::InvalidArgument, "renderer::pt_cuda: 'devices' must name 1..{} GPUs", LMCU_MAX_PEERS + 1);
+        }
     }
 
     virtual Json render() const override {
         scene_->require_renderable();
         film_->clear();
-        upload();
         const auto size = film_->size();
         LmcuRenderParams p{};
-        p.width = size.w; p.height = size.h; p.spp = spp_; p.max_verts = max_verts_;
+        p.width = size.w; p.height = size.h; p.max_verts = max_verts_;
         p.sampling_mode = sampling_mode_;
         p.seed = seed_ ? *seed_ : math::rng_seed();
-        p.rescale = 1;
         std::vector<float> rgb(size_t(size.w) * size.h * 3);
         LmcuRenderStats st{};
-        check(lmcu_render_pt(dev_.h, &p, rgb.data(), &st));
+        const int G = int(devices_.size());
+        if (G == 1) {
+            device_ = devices_[0];
+            upload();
+            p.spp = spp_; p.rescale = 1;
+            check(lmcu_render_pt(dev_.h, &p, rgb.data(), &st));
+        }
+        else {
+            // Sample split: one host thread + one replicated device scene per GPU
+            SceneExport ex;
+            ex.gather(*scene_, true);
+            std::vector<DeviceScene> devs(G);
+            std::vector<LmcuRenderStats> stats(G);
+            std::vector<std::string> errors(G);
+            std::vector<std::thread> threads;
+            for (int g = 0; g < G; g++) {
+                threads.emplace_back([&, g] {
+                    try {
+                        devs[g].upload(ex, devices_[g]);
+                        LmcuRenderParams q = p;
+                        const long long base = spp_ / G, rem = spp_ % G;
+                        q.spp = base + (g < rem ? 1 : 0);
+                        q.sample_offset = g * base + std::min<long long>(g, rem);
+                        q.rescale = 0;
+                        if (q.spp > 0) check(lmcu_render_pt(devs[g].h, &q, nullptr, &stats[g]));
+                    }
+                    catch (const std::exception& e) { errors[g] = e.what(); }
+                });
+            }
+            for (auto& t : threads) t.join();
+            for (const auto& e : errors) if (!e.empty()) LM_THROW_EXCEPTION(Error::None, "renderer::pt_cuda: {}", e);
+            if (spp_ < G) LM_THROW_EXCEPTION(Error::InvalidArgument, "renderer::pt_cuda: spp must be >= the number of devices");
+            std::vector<void*> peers;
+            for (int g = 1; g < G; g++) {
+                check(lmcu_enable_peer_access(devices_[0], devices_[g]));
+                void* ptr = nullptr; int64_t n = 0;
+                check(lmcu_film_device_ptr(devs[g].h, &ptr, &n));
+                peers.push_back(ptr);
+            }
+            check(lmcu_film_reduce_peers(devs[0].h, peers.data(), int(peers.size()), 1.0 / double(spp_)));   // renderer_pt.cpp:307-309
+            check(lmcu_film_download(devs[0].h, rgb.data()));
+            st.processed = spp_;
+            for (int g = 0; g < G; g++) st.elapsed = std::max(st.elapsed, stats[g].elapsed);
+        }
         write_film(rgb, false);
         return { {"processed", st.processed}, {"elapsed", st.elapsed} };
     }

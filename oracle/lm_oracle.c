@@ -141,6 +141,12 @@ typedef struct {
     double* cdf;          /* area: Dist over local triangle areas (light_area.cpp:68-73), n+1 entries */
     int ntri;
     double invA;
+    /* light::env (src/light/light_env.cpp:52-77): lat-long image, rotation (radians), scale, Dist2 */
+    int env_w, env_h;
+    double env_rot, env_scale;
+    float* env_tex;       /* [h][w][3], texture::bitmap order */
+    double* env_rows;     /* Dist2::ds: h normalised CDFs of w+1 entries (math.h:398-410) */
+    double* env_marg;     /* Dist2::m: h+1 entries */
 } Light;
 
 struct OrcScene {
@@ -293,6 +299,33 @@ OrcScene* orc_scene_create(const LmcuSceneDesc* d) {
             for (int f = 0; f <= o->ntri; f++) o->cdf[f] /= sum;            /* Dist::norm, math.h:341-346 */
         } else {
             sc->env_light = i;
+            if (l->type == LMCU_LIGHT_ENV) {                                 /* light_env.cpp:63-76 */
+                const int w = l->env_w, h = l->env_h;
+                o->env_w = w; o->env_h = h;
+                o->env_rot = l->env_rot * ORC_PI / 180.0;
+                o->env_scale = l->env_scale;
+                o->env_tex = (float*)malloc(sizeof(float) * (size_t)w * h * 3);
+                memcpy(o->env_tex, l->env_rgb, sizeof(float) * (size_t)w * h * 3);
+                o->env_rows = (double*)malloc(sizeof(double) * (size_t)h * (w + 1));
+                o->env_marg = (double*)malloc(sizeof(double) * (size_t)(h + 1));
+                o->env_marg[0] = 0.0;
+                for (int y = 0; y < h; y++) {
+                    double* row = o->env_rows + (size_t)y * (w + 1);
+                    row[0] = 0.0;
+                    for (int x = 0; x < w; x++) {
+                        const int k = y * w + x;
+                        const double r = (double)l->env_rgb[3 * k] * o->env_scale, g = (double)l->env_rgb[3 * k + 1] * o->env_scale,
+                                     b = (double)l->env_rgb[3 * k + 2] * o->env_scale;
+                        const double mx = fmax(fmax(r, g), b);                 /* glm::compMax */
+                        row[x + 1] = row[x] + mx * sin(ORC_PI * ((double)k / w + .5) / h);   /* Float(i)/w: the FLAT index */
+                    }
+                    o->env_marg[y + 1] = o->env_marg[y] + row[w];
+                    const double sum = row[w];
+                    for (int x = 0; x <= w; x++) row[x] /= sum;
+                }
+                const double msum = o->env_marg[h];
+                for (int y = 0; y <= h; y++) o->env_marg[y] /= msum;
+            }
         }
     }
     if (d->camera) {                                                         /* camera_pinhole.cpp:86-96 */
@@ -330,7 +363,9 @@ OrcScene* orc_scene_create(const LmcuSceneDesc* d) {
 void orc_scene_destroy(OrcScene* s) {
     if (!s) return;
     for (int i = 0; i < s->nmeshes; i++) { free(s->mesh_p[i]); free(s->mesh_n[i]); }
-    for (int i = 0; i < s->nlights; i++) free(s->lights[i].cdf);
+    for (int i = 0; i < s->nlights; i++) {
+        free(s->lights[i].cdf); free(s->lights[i].env_tex); free(s->lights[i].env_rows); free(s->lights[i].env_marg);
+    }
     free(s->mesh_p); free(s->mesh_n); free(s->mesh_faces); free(s->prims); free(s->mats); free(s->lights);
     free(s->tris); free(s->nodes); free(s->indices); free(s);
 }
@@ -676,13 +711,42 @@ static int mat_sample_direction(const LmcuMaterial* m, const SP* g, V3 wi, int c
 /* ------------------------------------------------------------------------------------------------
  * Lights
  * ---------------------------------------------------------------------------------------------- */
-/* Light::eval: area (light_area.cpp:185-187), envconst (light_envconst.cpp:139-141) */
+/* light::env lookup coordinates of a direction d = -geomL.wo (light_env.cpp:166-176,191-199) */
+static void env_uv(const Light* l, V3 d, double* u, double* v) {
+    double at = atan2(d.x, d.z);
+    if (at < 0.0) at += 2.0 * ORC_PI;
+    const double t = (at - l->env_rot) * .5 / ORC_PI;
+    *u = t - floor(t);
+    *v = acos(d.y) / ORC_PI;
+}
+
+/* Dist::pmf / Dist2::pdf (include/lm/math.h:352-354,416-419) */
+static double dist_pmf(const double* c, int n, int i) { return (i < 0 || i + 1 >= n + 1) ? 0.0 : c[i + 1] - c[i]; }
+static double env_dist_pdf(const Light* l, double u, double v) {
+    const int w = l->env_w, h = l->env_h;
+    int y = (int)(v * h);
+    if (y > h - 1) y = h - 1;
+    return dist_pmf(l->env_marg, h, y) * dist_pmf(l->env_rows + (size_t)y * (w + 1), w, (int)(u * w)) * w * h;
+}
+
+/* Light::eval: area (light_area.cpp:185-187), envconst (light_envconst.cpp:139-141), env (light_env.cpp:190-199 +
+ * texture_bitmap.cpp:68-75) */
 static V3 light_eval(const Light* l, const SP* geomL, V3 wo) {
     if (l->type == LMCU_LIGHT_AREA) return vdot(wo, geomL->n) <= 0.0 ? v3(0, 0, 0) : l->Ke;
+    if (l->type == LMCU_LIGHT_ENV) {
+        double u, v;
+        env_uv(l, vneg(geomL->wo), &u, &v);
+        u -= floor(u); v -= floor(v);
+        int x = (int)(u * l->env_w), y = (int)(v * l->env_h);
+        x = x < 0 ? 0 : (x > l->env_w - 1 ? l->env_w - 1 : x);
+        y = y < 0 ? 0 : (y > l->env_h - 1 ? l->env_h - 1 : y);
+        const float* t = l->env_tex + ((size_t)y * l->env_w + x) * 3;
+        return vscale(v3(t[0], t[1], t[2]), l->env_scale);
+    }
     return l->Ke;
 }
 
-/* Light::pdf_direct (light_area.cpp:172-178, light_envconst.cpp:116-119 + surface.h:377-390) */
+/* Light::pdf_direct (light_area.cpp:172-178, light_envconst.cpp:116-119, light_env.cpp:164-181 + surface.h:377-390) */
 static double light_pdf_direct(const OrcScene* sc, const Light* l, const SP* geom, const SP* geomL, V3 wo) {
     if (l->type == LMCU_LIGHT_AREA) {
         if (vdot(wo, geomL->n) <= 0.0) return 0.0;
@@ -690,9 +754,17 @@ static double light_pdf_direct(const OrcScene* sc, const Light* l, const SP* geo
         return G == 0.0 ? 0.0 : (l->invA / sc->prims[l->prim].J) / G;
     }
     const V3 d = vneg(geomL->wo);
-    if (geom->degenerated) return 1.0 / (4.0 * ORC_PI);
+    double pdf_sa = 1.0 / (4.0 * ORC_PI);
+    if (l->type == LMCU_LIGHT_ENV) {
+        double u, v;
+        env_uv(l, d, &u, &v);
+        const double st = safe_sqrt(1.0 - d.y * d.y);
+        if (st == 0.0) return 0.0;
+        pdf_sa = env_dist_pdf(l, u, v) / (2.0 * ORC_PI * ORC_PI * st);
+    }
+    if (geom->degenerated) return pdf_sa;
     const double J = fabs(vdot(geom->n, d));
-    return J == 0.0 ? 0.0 : (1.0 / (4.0 * ORC_PI)) / J;
+    return J == 0.0 ? 0.0 : pdf_sa / J;
 }
 
 /* path::sample_direct, TransDir::LE (include/lm/path.h:493-530); u = {up0,up1, upc0,upc1, ud0,ud1, udc0,udc1} */
@@ -715,6 +787,13 @@ static int sample_direct(const OrcScene* sc, const double* u, const SP* sp, SP* 
         const V3 gt = vnormalize(m3_mul(pr->NM, gn));
         make_on_surface(spL, m4_point(pr->M, p), gt, gt);
         *wo = vnormalize(vsub(sp->p, spL->p));
+    } else if (l->type == LMCU_LIGHT_ENV) {                                              /* light_env.cpp:139-162 */
+        const int y = dist_sample(l->env_marg, l->env_h, u[4]);                          /* dist_.sample({ud, up}) */
+        const int x = dist_sample(l->env_rows + (size_t)y * (l->env_w + 1), l->env_w, u[5]);
+        const double su = (x + u[0]) / l->env_w, sv = (y + u[1]) / l->env_h;
+        const double t = ORC_PI * sv, st = sin(t), p = 2.0 * ORC_PI * su + l->env_rot;
+        *wo = vneg(v3(st * sin(p), cos(t), st * cos(p)));
+        spL->infinite = 1; spL->wo = *wo;
     } else {                                                                             /* light_envconst.cpp:100-115 */
         *wo = sample_uniform_sphere(u[4], u[5]);
         spL->infinite = 1; spL->wo = *wo;

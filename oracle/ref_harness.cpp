@@ -12,6 +12,7 @@
 // the resulting liblmref.so.
 #include <lm/lm.h>
 #include <omp.h>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include "../include/lmcu.h"
@@ -234,6 +235,10 @@ int lmref_render(void* s, const char* renderer_key, const LmcuRenderParams* p, d
             {"bg_color", vec3(p->bg_color)}, {"use_constant_color", bool(p->use_constant_color)},
             {"visualize_normal", bool(p->visualize_normal)} };
         if (p->has_color) prop["color"] = vec3(p->color);
+        if (const char* e = std::getenv("LMREF_EXTRA_PROPS")) {            // tests: extra JSON keys for plugin renderers
+            const Json extra = Json::parse(e);
+            for (auto it = extra.begin(); it != extra.end(); ++it) prop[it.key()] = it.value();
+        }
         auto* renderer = lm::load<Renderer>("renderer", renderer_key, prop);
         if (!renderer) LM_THROW_EXCEPTION(Error::InvalidArgument, "unknown renderer");
         const auto t0 = std::chrono::high_resolution_clock::now();

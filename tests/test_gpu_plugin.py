@@ -106,3 +106,23 @@ def test_renderer_pt_cuda_env_light_probed(plugin, tmp_path):
     d = np.abs(fc - fr).max(axis=2)
     assert (d > 1e-4).mean() < 3e-3
     rs.close()
+
+
+def test_renderer_pt_cuda_multi_device_sample_split(plugin):
+    """'devices': [0, 1] — replicated scene, sample split, films combined by the peer-memory kernel: the image is
+    the single-GPU image up to fp32 summation order (same counter-RNG streams)."""
+    import lmcu
+    if lmcu.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    sb = scenes.cornell_spheres(16)
+    rs = plugin.RefScene(sb)
+    p = abi.render_params(128, 72, spp=64, max_verts=8)
+    f1, _, p1 = rs.render("renderer::pt_cuda", p)
+    os.environ["LMREF_EXTRA_PROPS"] = '{"devices": [0, 1]}'
+    try:
+        f2, _, p2 = rs.render("renderer::pt_cuda", p)
+    finally:
+        del os.environ["LMREF_EXTRA_PROPS"]
+    assert p1 == p2 == 64
+    assert np.allclose(f1, f2, rtol=1e-4, atol=1e-5)
+    rs.close()

@@ -44,6 +44,54 @@ def _worker(rank, world, port, total_spp, npix, out):
     dist.destroy_process_group()
 
 
+def _peer_worker(rank, world, port, total_spp, npix, tmp, out):
+    """PeerFilmReducer orchestration with files standing in for CUDA IPC mappings."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    film = torch.zeros(npix * 3)
+    opened = []
+
+    def film_handle():
+        return os.path.join(tmp, "film%d.pt" % rank).encode()
+
+    def sync():
+        torch.save(film, film_handle().decode())        # "render complete": the peer film becomes readable
+
+    def open_handle(h):
+        opened.append(h)
+        return h
+
+    def reduce(ptrs, scale):
+        acc = film.clone()
+        for h in ptrs:
+            acc += torch.load(h.decode())
+        film.copy_(acc * scale)
+
+    red = D.PeerFilmReducer(dist, rank, world, film_handle, open_handle, reduce, sync)
+    for step in range(2):                                # second step must reuse the cached mappings
+        offset, count = D.sample_block(total_spp, rank, world)
+        film.zero_()
+        for i in range(offset, offset + count):
+            film += _fake_sample_image(i, npix)
+        red(total_spp)
+    if rank == 0:
+        assert len(opened) == world - 1
+        torch.save(film, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,total_spp", [(2, 8), (3, 7)])
+def test_peer_film_reducer(tmp_path, world, total_spp):
+    npix = 12
+    out = str(tmp_path / "film.pt")
+    mp.spawn(_peer_worker, args=(world, _free_port(), total_spp, npix, str(tmp_path), out), nprocs=world, join=True)
+    got = torch.load(out)
+    want = sum(_fake_sample_image(i, npix) for i in range(total_spp)) / total_spp
+    assert torch.allclose(got, want, atol=1e-6)
+
+
 @pytest.mark.parametrize("world,total_spp", [(2, 8), (3, 7)])
 def test_sample_split_reduce(tmp_path, world, total_spp):
     npix = 12
