@@ -31,7 +31,7 @@ sys.path.insert(0, os.path.join(ROOT, "lightmetrica-v3_b200"))
 
 W, H, MAX_VERTS, SEED = 1920, 1080, 20, 42
 GPU_SPP = 1024
-REF_SPP_PER_STEP = 2          # reference arm / cpu_baseline: bounded sample of the same workload
+REF_SPP_PER_STEP = 16         # reference arm / cpu_baseline: bounded sample of the same workload (~9 s of CPU work per step)
 METRIC = "Mpaths/s renderer::pt (C2: Cornell box + diffuse/glass spheres, 1920x1080, max_verts 20, MIS)"
 
 

@@ -63,7 +63,7 @@ typedef struct LmcuHit {
  *                  primitive node that has a mesh, with its GLOBAL transform (instance groups are
  *                  flattened, src/scene.cpp:216-230), in traversal order
  *   materials   <- material::{diffuse,glossy,glass,mirror} parameters
- *   lights      <- Scene light table order (src/scene.cpp:281-286)
+ *   lights      <- Scene light table order (src/scene.cpp:281-286): area, envconst, env, point, directional
  *   camera      <- camera::pinhole (src/camera/camera_pinhole.cpp:66-97)
  * ------------------------------------------------------------------------------------------- */
 typedef struct LmcuMesh {
@@ -90,7 +90,9 @@ typedef struct LmcuMaterial {
     double Ni;                               /* glass: index of refraction */
 } LmcuMaterial;
 
-enum { LMCU_LIGHT_AREA = 0, LMCU_LIGHT_ENVCONST = 1, LMCU_LIGHT_ENV = 2 };
+enum { LMCU_LIGHT_AREA = 0, LMCU_LIGHT_ENVCONST = 1, LMCU_LIGHT_ENV = 2,
+       LMCU_LIGHT_POINT = 3,          /* light::point (src/light/light_point.cpp): Ke = Le, position */
+       LMCU_LIGHT_DIRECTIONAL = 4 };  /* light::directional (src/light/light_directional.cpp): Ke = Le, position = direction */
 
 typedef struct LmcuLight {
     int32_t type;
@@ -103,6 +105,7 @@ typedef struct LmcuLight {
     double env_scale;                        /* env: luminance scale */
     const float* env_rgb;                    /* env: [env_h][env_w][3], row order as texture::bitmap holds it */
     const char* env_path;                    /* env: image path (only the reference harness reads files) */
+    double position[3];                      /* point: position; directional: direction the light travels in */
 } LmcuLight;
 
 typedef struct LmcuCamera {

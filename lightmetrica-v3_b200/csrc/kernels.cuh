@@ -320,6 +320,7 @@ LMCU_HD ShadeOut pt_shade_body(const DevScene& s, const PtParams& p, float4 ro, 
         F3 wo;              // direction from the vertex toward the light
         F3 Le = f3(l.Ke[0], l.Ke[1], l.Ke[2]);
         float pl = 0.f;     // pdf_direct, projected SA, without the selection probability
+        bool delta_light = false;   // point / directional: not samplable by BSDF sampling => NEE only, MIS weight 1 (renderer_pt.cpp:176-180)
         float tmax = 0.f;
         if (l.type == LIGHT_AREA) {                                         // light_area.cpp:47-59,148-178
             const int ti = cdf_sample(s.cdf + l.cdf_offset, l.num_tris, u1.y);
@@ -337,6 +338,20 @@ LMCU_HD ShadeOut pt_shade_body(const DevScene& s, const PtParams& p, float4 ro, 
                 pl = G == 0.f ? 0.f : l.inv_area_j / G;
             }
             tmax = dist * (1.0f - (float)kEps);                             // include/lm/scene.h:349-356
+        } else if (l.type == LIGHT_POINT) {                                 // light_point.cpp:96-114, surface.h:329-348
+            const F3 dv = f3(l.pos[0], l.pos[1], l.pos[2]) - sp.p;
+            const float d2 = dot(dv, dv), dist = sqrtf(d2);
+            wo = dv * (1.0f / dist);
+            const float c = fabsf(dot(sp.n, wo));                           // G = |n.d| / r^2 toward a degenerated point
+            pl = c == 0.f ? 0.f : d2 / c;
+            tmax = dist * (1.0f - (float)kEps);
+            delta_light = true;
+        } else if (l.type == LIGHT_DIRECTIONAL) {                           // light_directional.cpp:93-108
+            wo = -f3(l.pos[0], l.pos[1], l.pos[2]);
+            const float c = fabsf(dot(sp.n, wo));
+            pl = c == 0.f ? 0.f : 1.0f / c;
+            tmax = (float)(kInf - 1.0);
+            delta_light = true;
         } else {                                                            // light_envconst.cpp:100-119, light_env.cpp:139-162
             const R4 u2 = rand4(p.seed, pixel, p.sample_offset + sample, num_verts * 4u + 2u);
             wo = l.type == LIGHT_ENV ? env_sample_dir(l, s.cdf, u2) : -sample_uniform_sphere(u2.x, u2.y);
@@ -348,7 +363,7 @@ LMCU_HD ShadeOut pt_shade_body(const DevScene& s, const PtParams& p, float4 ro, 
             const F3 fs = mat_eval(mat, sp.n, wi, wo) * sn_correction(sp.n, sp.gn, wi, wo);
             if (!is_zero(fs)) {
                 float mis = 1.f;
-                if (p.sampling_mode == 2) {
+                if (p.sampling_mode == 2 && !delta_light) {
                     const float p_light = pl * inv_nl;
                     const float p_bsdf = mat_pdf(mat, sp.n, wi, wo);
                     mis = (p_light == 0.f && p_bsdf == 0.f) ? 0.f : p_light / (p_light + p_bsdf);   // math.h:697-702

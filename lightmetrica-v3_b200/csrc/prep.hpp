@@ -144,6 +144,12 @@ inline int prepare_scene(const LmcuSceneDesc* d, PreparedScene& o, std::string& 
                 for (int x = 0; x <= w; x++) o.cdf.push_back((float)(row[x] / row[w]));
             }
             for (double v : marg) o.cdf.push_back((float)(v / marg.back()));
+        } else if (l.type == LMCU_LIGHT_POINT) {                 // light_point.cpp:38-41
+            for (int k = 0; k < 3; k++) t.pos[k] = (float)l.position[k];
+        } else if (l.type == LMCU_LIGHT_DIRECTIONAL) {           // light_directional.cpp:37-40: glm::normalize(direction)
+            const double len = std::sqrt(l.position[0] * l.position[0] + l.position[1] * l.position[1] + l.position[2] * l.position[2]);
+            if (!(len > 0.0)) { err = "light::directional with a zero direction"; return LMCU_ERR_INVALID_ARGUMENT; }
+            for (int k = 0; k < 3; k++) t.pos[k] = (float)(l.position[k] / len);
         } else {
             err = "bad light type"; return LMCU_ERR_INVALID_ARGUMENT;
         }

@@ -224,7 +224,7 @@ LMCU_HD F3 mat_reflectance(const MaterialDev& m) {
 }
 
 // -- lights -------------------------------------------------------------------------------------------
-enum { LIGHT_AREA = 0, LIGHT_ENVCONST = 1, LIGHT_ENV = 2 };
+enum { LIGHT_AREA = 0, LIGHT_ENVCONST = 1, LIGHT_ENV = 2, LIGHT_POINT = 3, LIGHT_DIRECTIONAL = 4 };
 
 struct alignas(16) LightDev {
     int32_t type;
@@ -240,6 +240,8 @@ struct alignas(16) LightDev {
     int32_t env_cdf_offset;  // env: conditional CDFs [h][w+1] then marginal [h+1]
     int32_t env_tex_offset;  // env: texels (float4) offset
     int32_t pad_;
+    float pos[3];            // point: position; directional: normalised direction the light travels in
+    float pad2_;
 };
 
 struct alignas(16) EmitTri { float4 p1, p2, p3, n; };   // world-space emitter triangle + geometric normal

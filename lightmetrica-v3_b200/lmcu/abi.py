@@ -27,7 +27,7 @@ class LmcuPrimitive(C.Structure):
 
 
 MAT_DIFFUSE, MAT_GLOSSY, MAT_GLASS, MAT_MIRROR = 0, 1, 2, 3
-LIGHT_AREA, LIGHT_ENVCONST, LIGHT_ENV = 0, 1, 2
+LIGHT_AREA, LIGHT_ENVCONST, LIGHT_ENV, LIGHT_POINT, LIGHT_DIRECTIONAL = 0, 1, 2, 3, 4
 SAMPLING_NAIVE, SAMPLING_NEE, SAMPLING_MIS = 0, 1, 2
 
 
@@ -40,7 +40,7 @@ class LmcuLight(C.Structure):
     _fields_ = [("type", C.c_int32), ("primitive", C.c_int32), ("node_index", C.c_int32),
                 ("env_w", C.c_int32), ("env_h", C.c_int32), ("pad_", C.c_int32),
                 ("Ke", c_double3), ("env_rot", C.c_double), ("env_scale", C.c_double),
-                ("env_rgb", C.POINTER(C.c_float)), ("env_path", C.c_char_p)]
+                ("env_rgb", C.POINTER(C.c_float)), ("env_path", C.c_char_p), ("position", c_double3)]
 
 
 class LmcuCamera(C.Structure):

@@ -76,7 +76,7 @@ class SceneBuilder:
         """Ke != None attaches a light::area to the primitive (light_area.cpp:68-73)."""
         light = -1
         if Ke is not None:
-            assert all(l["type"] == abi.LIGHT_AREA for l in self.lights), "env light must come last"
+            assert all(l["type"] == abi.LIGHT_AREA for l in self.lights), "area lights first: the reference harness adds the others after the meshes"
             self.lights.append(dict(type=abi.LIGHT_AREA, primitive=len(self.primitives), Ke=tuple(Ke)))
             light = len(self.lights) - 1
         M = np.eye(4) if M is None else np.asarray(M, dtype=np.float64)
@@ -91,6 +91,12 @@ class SceneBuilder:
         rgb = np.ascontiguousarray(rgb, dtype=np.float32)
         self.lights.append(dict(type=abi.LIGHT_ENV, primitive=-1, Ke=(0, 0, 0), rgb=rgb, rot=rot,
                                 scale=scale, path=path))
+
+    def add_point_light(self, Le, position):
+        self.lights.append(dict(type=abi.LIGHT_POINT, primitive=-1, Ke=tuple(Le), position=tuple(position)))
+
+    def add_directional_light(self, Le, direction):
+        self.lights.append(dict(type=abi.LIGHT_DIRECTIONAL, primitive=-1, Ke=tuple(Le), position=tuple(direction)))
 
     def set_camera(self, position, center, up, vfov, aspect):
         self.camera = dict(position=tuple(position), center=tuple(center), up=tuple(up),
@@ -123,6 +129,7 @@ class SceneBuilder:
             lights[i].type, lights[i].primitive = l["type"], l["primitive"]
             lights[i].node_index = l["primitive"] if l["primitive"] >= 0 else len(self.primitives)
             lights[i].Ke = abi.c_double3(*l["Ke"])
+            lights[i].position = abi.c_double3(*l.get("position", (0, 0, 0)))
             if l["type"] == abi.LIGHT_ENV:
                 lights[i].env_h, lights[i].env_w = l["rgb"].shape[:2]
                 lights[i].env_rgb = l["rgb"].ctypes.data_as(C.POINTER(C.c_float))
@@ -386,6 +393,16 @@ def env_light(path, w=1024, h=512, seed=5, rot=0.0, scale=1.0):
     rgbe = procedural_env(w, h, seed)
     write_hdr(path, rgbe)
     return dict(rgb=_rgbe_decode(rgbe), rot=rot, scale=scale, path=path)
+
+
+def delta_lights_scene(grid=2, num_theta=12):
+    """Open scene lit ONLY by a directional and a point light (func_lights.py pattern): every contribution comes
+    through next-event estimation with MIS weight 1 (renderer_pt.cpp:176-180)."""
+    sb = instanced_spheres(grid=grid, num_theta=num_theta)
+    sb.lights = []
+    sb.add_directional_light((3, 2.5, 2), (-0.3, -1, -0.2))
+    sb.add_point_light((30, 30, 40), (2.0, 4.0, 3.0))
+    return sb
 
 
 # ------------------------------------------------------------------------------------------------

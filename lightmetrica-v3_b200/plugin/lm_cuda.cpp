@@ -176,6 +176,21 @@ struct SceneExport {
                 else if (key == "light::env") {
                     probe_env_light(node.primitive.light, l);
                 }
+                else if (key == "light::point") {
+                    // position through sample_position() (light_point.cpp:81-86), Le through eval()
+                    l.type = LMCU_LIGHT_POINT;
+                    const auto sP = node.primitive.light->sample_position({}, Transform(Mat4(1_f)));
+                    const auto Le = node.primitive.light->eval(sP->geom, Vec3(0_f, 0_f, 1_f), false);
+                    for (int k = 0; k < 3; k++) { l.position[k] = sP->geom.p[k]; l.Ke[k] = Le[k]; }
+                }
+                else if (key == "light::directional") {
+                    // direction = the wo sample_direct() returns (light_directional.cpp:93-103), Le through eval()
+                    l.type = LMCU_LIGHT_DIRECTIONAL;
+                    const auto geom = PointGeometry::make_degenerated(Vec3(0_f));
+                    const auto sL = node.primitive.light->sample_direct({}, geom, Transform(Mat4(1_f)));
+                    const auto Le = node.primitive.light->eval(sL->geom, sL->wo, false);
+                    for (int k = 0; k < 3; k++) { l.position[k] = sL->wo[k]; l.Ke[k] = Le[k]; }
+                }
                 else {
                     LM_THROW_EXCEPTION(Error::Unsupported, "renderer::*_cuda: unsupported light [key='{}']", key);
                 }

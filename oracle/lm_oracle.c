@@ -147,6 +147,7 @@ typedef struct {
     float* env_tex;       /* [h][w][3], texture::bitmap order */
     double* env_rows;     /* Dist2::ds: h normalised CDFs of w+1 entries (math.h:398-410) */
     double* env_marg;     /* Dist2::m: h+1 entries */
+    V3 pos;               /* light::point position / light::directional normalised direction */
 } Light;
 
 struct OrcScene {
@@ -297,6 +298,10 @@ OrcScene* orc_scene_create(const LmcuSceneDesc* d) {
             o->invA = 1.0 / o->cdf[o->ntri];
             const double sum = o->cdf[o->ntri];
             for (int f = 0; f <= o->ntri; f++) o->cdf[f] /= sum;            /* Dist::norm, math.h:341-346 */
+        } else if (l->type == LMCU_LIGHT_POINT) {                            /* light_point.cpp:38-41 */
+            o->pos = v3(l->position[0], l->position[1], l->position[2]);
+        } else if (l->type == LMCU_LIGHT_DIRECTIONAL) {                      /* light_directional.cpp:37-40 */
+            o->pos = vnormalize(v3(l->position[0], l->position[1], l->position[2]));
         } else {
             sc->env_light = i;
             if (l->type == LMCU_LIGHT_ENV) {                                 /* light_env.cpp:63-76 */
@@ -753,8 +758,13 @@ static double light_pdf_direct(const OrcScene* sc, const Light* l, const SP* geo
         const double G = geometry_term(geom, geomL);
         return G == 0.0 ? 0.0 : (l->invA / sc->prims[l->prim].J) / G;
     }
+    if (l->type == LMCU_LIGHT_POINT) {                                                   /* light_point.cpp:111-114 */
+        const double G = geometry_term(geom, geomL);
+        return G == 0.0 ? 0.0 : 1.0 / G;
+    }
     const V3 d = vneg(geomL->wo);
     double pdf_sa = 1.0 / (4.0 * ORC_PI);
+    if (l->type == LMCU_LIGHT_DIRECTIONAL) pdf_sa = 1.0;                                 /* light_directional.cpp:105-108, eval_delta = false */
     if (l->type == LMCU_LIGHT_ENV) {
         double u, v;
         env_uv(l, d, &u, &v);
@@ -787,6 +797,12 @@ static int sample_direct(const OrcScene* sc, const double* u, const SP* sp, SP* 
         const V3 gt = vnormalize(m3_mul(pr->NM, gn));
         make_on_surface(spL, m4_point(pr->M, p), gt, gt);
         *wo = vnormalize(vsub(sp->p, spL->p));
+    } else if (l->type == LMCU_LIGHT_POINT) {                                            /* light_point.cpp:96-109 */
+        *wo = vnormalize(vsub(sp->p, l->pos));
+        spL->p = l->pos; spL->degenerated = 1;
+    } else if (l->type == LMCU_LIGHT_DIRECTIONAL) {                                      /* light_directional.cpp:93-103 */
+        *wo = l->pos;
+        spL->infinite = 1; spL->wo = *wo;
     } else if (l->type == LMCU_LIGHT_ENV) {                                              /* light_env.cpp:139-162 */
         const int y = dist_sample(l->env_marg, l->env_h, u[4]);                          /* dist_.sample({ud, up}) */
         const int x = dist_sample(l->env_rows + (size_t)y * (l->env_w + 1), l->env_w, u[5]);
@@ -948,8 +964,11 @@ void orc_render_pt(const OrcScene* sc, const LmcuRenderParams* p, double* film, 
                         const V3 fs = vscale(mat_eval(mat, &sp, wi, wo, comp, 1), sn_correction(&sp, wi, wo));
                         if (!vis_zero(fs)) {
                             double mis_w = 1.0;
-                            if (mode == LMCU_SAMPLING_MIS) {
-                                /* area and env lights are neither specular nor degenerated: samplable by BSDF */
+                            /* renderer_pt.cpp:176-180: a specular (directional) or degenerated (point) light endpoint
+                             * cannot be reached by BSDF sampling -> NEE only */
+                            const int ltype = sc->lights[spL.light].type;
+                            const int samplable_by_bsdf = ltype != LMCU_LIGHT_DIRECTIONAL && !spL.degenerated;
+                            if (mode == LMCU_SAMPLING_MIS && samplable_by_bsdf) {
                                 const double p_light = pdf_direct(sc, &sp, &spL, woL);
                                 const double p_bsdf = mat_pdf(mat, &sp, wi, wo, 1);
                                 mis_w = balance_heuristic(p_light, p_bsdf);

@@ -183,6 +183,10 @@ int lmref_scene_create(const LmcuSceneDesc* d, const char* accel_key, void** out
             } else if (l.type == LMCU_LIGHT_ENV) {
                 light = lm::load<Light>("light" + std::to_string(i), "light::env", {
                     {"path", std::string(l.env_path ? l.env_path : "")}, {"rot", l.env_rot}, {"scale", l.env_scale} });
+            } else if (l.type == LMCU_LIGHT_POINT) {
+                light = lm::load<Light>("light" + std::to_string(i), "light::point", { {"Le", vec3(l.Ke)}, {"position", vec3(l.position)} });
+            } else if (l.type == LMCU_LIGHT_DIRECTIONAL) {
+                light = lm::load<Light>("light" + std::to_string(i), "light::directional", { {"Le", vec3(l.Ke)}, {"direction", vec3(l.position)} });
             } else {
                 LM_THROW_EXCEPTION(Error::InvalidArgument, "area light without primitive");
             }

@@ -212,6 +212,26 @@ def test_g3_pt_env_image_light(reference, tmp_path):
     rs.close(); sc.close()
 
 
+def test_g3_pt_point_and_directional_lights(reference):
+    """light::point + light::directional (NEE only, MIS weight 1), mixed with an area light in a second scene."""
+    sb = scenes.delta_lights_scene(2, 24)
+    sc, rs = lmcu.Scene(sb), reference.RefScene(sb)
+    for mode in (abi.SAMPLING_MIS, abi.SAMPLING_NEE):
+        p = abi.render_params(160, 90, spp=256, max_verts=12, sampling_mode=mode)
+        fr, _, _ = rs.render("pt", p)
+        fg, _ = sc.render("pt", p)
+        assert_pt_parity(fr, fg, 256, rel_mean=0.01)
+    rs.close(); sc.close()
+    sb = scenes.cornell_spheres(16)
+    sb.add_point_light((3, 3, 3), (0.3, 1.5, 0.2))
+    sc, rs = lmcu.Scene(sb), reference.RefScene(sb)
+    p = abi.render_params(160, 90, spp=256, max_verts=12)
+    fr, _, _ = rs.render("pt", p)
+    fg, _ = sc.render("pt", p)
+    assert_pt_parity(fr, fg, 256, rel_mean=0.01)
+    rs.close(); sc.close()
+
+
 def test_sample_split_is_additive():
     """Sample split (multi-GPU partition): two half renders with disjoint sample offsets sum to the full render."""
     sb = scenes.cornell_spheres(16)

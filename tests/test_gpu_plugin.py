@@ -126,3 +126,13 @@ def test_renderer_pt_cuda_multi_device_sample_split(plugin):
     assert p1 == p2 == 64
     assert np.allclose(f1, f2, rtol=1e-4, atol=1e-5)
     rs.close()
+
+
+def test_renderer_pt_cuda_point_and_directional_probed(plugin):
+    sb = scenes.delta_lights_scene(2, 16)
+    rs = plugin.RefScene(sb)
+    p = abi.render_params(160, 90, spp=128, max_verts=10)
+    fr, _, _ = rs.render("pt", p)
+    fc, _, _ = rs.render("renderer::pt_cuda", p)
+    assert_pt_parity(fr, fc, 128, rel_mean=0.01)
+    rs.close()

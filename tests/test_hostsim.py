@@ -98,3 +98,15 @@ def test_env_light_image(reference, sim, tmp_path):
         fr, _, _ = rs.render("pt", p)
         assert_pt_parity(fr, ss.render("pt", p), 64, rel_mean=0.02)
     rs.close()
+
+
+def test_point_and_directional_lights(reference, sim):
+    sb = scenes.delta_lights_scene(2, 12)
+    rs, ss = reference.RefScene(sb), sim.SimScene(sb)
+    for mode in (abi.SAMPLING_MIS, abi.SAMPLING_NEE):
+        p = abi.render_params(64, 36, spp=128, max_verts=8, sampling_mode=mode)
+        fr, _, _ = rs.render("pt", p)
+        assert_pt_parity(fr, ss.render("pt", p), 128, rel_mean=0.015)
+    p = abi.render_params(64, 36, spp=4, max_verts=8, sampling_mode=abi.SAMPLING_NAIVE)
+    assert ss.render("pt", p).max() == 0.0          # delta lights are invisible to BSDF sampling
+    rs.close()

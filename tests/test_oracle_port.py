@@ -92,12 +92,17 @@ def _ref_single_thread(scene_expr, params_expr):
     return pickle.loads(subprocess.check_output([sys.executable, "-c", code]))
 
 
+ENV_SCENE = ("scenes.instanced_spheres(2, 10, env=scenes.env_light(__import__('os').path.join(__import__('tempfile').gettempdir(), "
+             "'lmcu_port_env.hdr'), w=64, h=32, rot=40.0, scale=1.5))")
+
+
 @pytest.mark.parametrize("scene_expr,mode", [
     ("scenes.cornell_spheres(8)", 2), ("scenes.cornell_spheres(8)", 1), ("scenes.cornell_spheres(8)", 0),
-    ("scenes.instanced_spheres(2, 10)", 2),
+    ("scenes.instanced_spheres(2, 10)", 2), (ENV_SCENE, 2), (ENV_SCENE, 1),
+    ("scenes.delta_lights_scene(2, 10)", 2), ("scenes.delta_lights_scene(2, 10)", 1),
 ])
 def test_port_pt_bit_exact_vs_reference(reference, port, scene_expr, mode):
-    """Every material (diffuse, glossy, glass, mirror), area + constant env light, all three sampling modes."""
+    """Every material (diffuse, glossy, glass, mirror), area + constant env + image env + point + directional lights, all three sampling modes."""
     params_expr = "abi.render_params(40, 24, spp=3, max_verts=12, seed=11, sampling_mode=%d)" % mode
     fr = _ref_single_thread(scene_expr, params_expr)
     ps = port.PortScene(eval(scene_expr))
