@@ -133,6 +133,12 @@ typedef struct LmcuSceneDesc {
  * renderer::ao (functest/renderer_ao.cpp:18-22) and renderer::pt (src/renderer/renderer_pt.cpp:51-77).
  * ------------------------------------------------------------------------------------------- */
 enum { LMCU_SAMPLING_NAIVE = 0, LMCU_SAMPLING_NEE = 1, LMCU_SAMPLING_MIS = 2 };
+/* primary_ray_sampling_mode (renderer_pt.cpp:65-75,96-107): the window the primary raster position is drawn from */
+enum { LMCU_PRIMARY_PIXEL = 0,        /* one pixel per sample index, scheduler::spp::* */
+       LMCU_PRIMARY_IMAGE = 1 };      /* the whole image, scheduler::spi::* */
+/* scheduler (src/scheduler.cpp): "sample" = fixed spp / num_samples (:37-49,131-141), "time" = whole passes until
+ * render_time seconds have elapsed (:75-103,162-187) */
+enum { LMCU_SCHED_SAMPLE = 0, LMCU_SCHED_TIME = 1 };
 
 typedef struct LmcuRenderParams {
     int32_t width, height;                   /* film size */
@@ -141,7 +147,8 @@ typedef struct LmcuRenderParams {
     int64_t spp;                             /* pt/ao: samples per pixel rendered by THIS call */
     int64_t sample_offset;                   /* pt/ao: global index of this call's first sample (sample split) */
     uint32_t seed;                           /* pt/ao: RNG seed */
-    int32_t rescale;                         /* pt: 1 = divide by spp at the end (renderer_pt.cpp:307-309); 0 = leave sums */
+    int32_t rescale;                         /* pt: 1 = film *= 1/processed (pixel) or w*h/processed (image) at the end
+                                                (renderer_pt.cpp:307-312); 0 = leave sums (sample split) */
     int32_t use_constant_color;              /* raycast */
     int32_t visualize_normal;                /* raycast */
     int32_t has_color;                       /* raycast: `color` override present */
@@ -149,12 +156,17 @@ typedef struct LmcuRenderParams {
     double bg_color[3];                      /* raycast */
     double color[3];                         /* raycast */
     double ao_distance;                      /* ao: occlusion ray tmax (0.2 in the reference) */
+    int32_t primary_ray_sampling_mode;       /* pt: LMCU_PRIMARY_* (default pixel) */
+    int32_t scheduler;                       /* pt: LMCU_SCHED_* (default sample) */
+    int64_t num_samples;                     /* pt, image mode + sample scheduler: samples of the whole image by THIS call */
+    int64_t samples_per_iter;                /* pt, image mode + time scheduler: samples per pass (0 = 100000, scheduler.cpp:159) */
+    double render_time;                      /* pt, time scheduler: seconds; the pass in flight always completes */
 } LmcuRenderParams;
 
 typedef struct LmcuRenderStats {
     double elapsed;                          /* seconds, device time of the render (the "elapsed" Json key) */
-    int64_t processed;                       /* the "processed" Json key: spp rendered by this call */
-    int64_t paths;                           /* width*height*spp */
+    int64_t processed;                       /* the "processed" Json key: spp (pixel mode) or samples (image mode) rendered by this call */
+    int64_t paths;                           /* paths traced: width*height*spp (pixel mode) or samples (image mode) */
     int64_t rays;                            /* closest-hit + shadow queries issued (device counter) */
     int64_t kernel_launches;                 /* kernels launched by this call */
     double bvh_nodes_per_ray;                /* mean wide nodes fetched per ray (counters build only, else 0) */

@@ -71,9 +71,10 @@ LMCU_HD F3 light_env_radiance(const DevScene& s, const LightDev& l, F3 d) {
 }
 // pdf_direct (projected solid angle, without the light-selection probability) of sampling direction d from a
 // surface point with shading normal n
-LMCU_HD float light_env_pdf(const DevScene& s, const LightDev& l, F3 n, F3 d) {
-    if (l.type == LIGHT_ENV) return env_pdf_direct(l, s.cdf, n, d);
-    const float c = fabsf(dot(n, d));
+// (degenerated = the point is a pinhole camera: no cosine, surface.h:377-390)
+LMCU_HD float light_env_pdf(const DevScene& s, const LightDev& l, F3 n, F3 d, bool degenerated = false) {
+    if (l.type == LIGHT_ENV) return env_pdf_direct(l, s.cdf, n, d, degenerated);
+    const float c = degenerated ? 1.0f : fabsf(dot(n, d));
     return c == 0.f ? 0.f : (1.0f / (4.0f * kPiF)) / c;             // light_envconst.cpp:116-119
 }
 
@@ -157,7 +158,7 @@ struct PathQueue {
     float4* ray_d;      // d.xyz, tmax
     float4* thr_pix;    // throughput.rgb, pixel (uint bits)
     float4* aux;        // pdf_bsdf (projected SA) of the sampled direction, shading normal at the previous vertex
-    uint2* info;        // x: sample index of the pixel, y: num_verts | prev_nee<<8
+    uint2* info;        // x: low 32 bits of the path's sample index, y: num_verts | prev_nee<<8 | sample index bits 32..47 << 16
 };
 
 struct ShadowQueue {
@@ -172,8 +173,12 @@ struct PtParams {
     uint32_t seed, tiled;
     uint64_t sample_offset;
     uint64_t total_paths;
-    uint32_t capacity, pad_;
+    uint32_t capacity;
+    uint32_t image_mode;        // primary_ray_sampling_mode = image: the raster window is the whole film (renderer_pt.cpp:104-106)
 };
+
+// RNG counter word 0 of a path's primary sample in image mode (no pixel is known before the raster position is drawn)
+constexpr uint32_t kImagePrimaryKey = 0xffffffffu;
 
 struct PtCounters {
     uint32_t count[2];          // entries in path queue A / B
@@ -181,6 +186,8 @@ struct PtCounters {
     uint32_t fetch_extend;      // persistent-thread work fetch cursors
     uint32_t fetch_shadow;
     uint32_t overflow;          // traversal stack overflow flag
+    uint32_t gen_slot, gen_count;   // this iteration's refill: first free queue slot, number of new paths (k_pt_advance -> k_pt_generate)
+    unsigned long long gen_first;   // ... and the index of the first new path
     unsigned long long next_path;
     unsigned long long rays;
     unsigned long long iterations;
@@ -204,22 +211,146 @@ LMCU_HD void path_pixel(const PtParams& p, uint64_t g, uint32_t& pixel, uint32_t
     pixel = (uint32_t)y * (uint32_t)p.width + (uint32_t)x;
 }
 
-// First path vertex: camera endpoint + direction through the pixel window (renderer_pt.cpp:96-113,197-206)
-LMCU_HD void pt_generate_body(const DevScene& s, const PtParams& p, uint64_t g, const PathQueue& q, uint32_t slot) {
-    uint32_t pixel, sample; int x, y;
-    path_pixel(p, g, pixel, sample, x, y);
-    const R4 u = rand4(p.seed, pixel, p.sample_offset + sample, 0);
-    const float rpx = ((float)x + u.x) / (float)p.width, rpy = ((float)y + u.y) / (float)p.height;
+// Geometry term between a surface vertex (normal n1) and a light point (normal n2): surface.h:329-348
+// (degenerated1: point 1 is a pinhole camera / point light, its cosine is 1)
+LMCU_HD float geometry_term(F3 p1, F3 n1, F3 p2, F3 n2, bool degenerated1 = false) {
+    F3 d = p2 - p1;
+    const float L2 = dot(d, d);
+    d = d * (1.0f / sqrtf(L2));
+    return (degenerated1 ? 1.0f : fabsf(dot(n1, d))) * fabsf(dot(n2, -d)) / L2;
+}
+
+// path::sample_direct toward a light from point P (include/lm/path.h:493-530, src/scene.cpp:374-387 and the lights'
+// sample_direct): direction wo toward the light, radiance Le, pdf pl in projected solid angle at P WITHOUT the
+// light-selection probability, shadow-ray length tmax.  `degenerated`: P is the pinhole camera (no cosine at P).
+struct LightSample {
+    F3 wo, Le;
+    float pl, tmax;
+    bool delta;          // point / directional: not reachable by BSDF sampling => NEE only, MIS weight 1 (renderer_pt.cpp:176-180)
+};
+
+LMCU_HD LightSample sample_light(const DevScene& s, const PtParams& p, uint32_t key, uint64_t sample_index, uint32_t block,
+                                 F3 P, F3 N, bool degenerated) {
+    const R4 u1 = rand4(p.seed, key, sample_index, block);   // sel, upc, up0, up1
+    int li = (int)(u1.x * (float)s.num_lights);
+    li = li < 0 ? 0 : (li > s.num_lights - 1 ? s.num_lights - 1 : li);  // src/scene.cpp:374-387
+    const LightDev& l = s.lights[li];
+    LightSample o;
+    o.Le = f3(l.Ke[0], l.Ke[1], l.Ke[2]);
+    o.pl = 0.f; o.delta = false; o.tmax = 0.f;
+    if (l.type == LIGHT_AREA) {                                         // light_area.cpp:47-59,148-178
+        const int ti = cdf_sample(s.cdf + l.cdf_offset, l.num_tris, u1.y);
+        const EmitTri& e = s.emit[l.tri_offset + ti];
+        const float sq = safe_sqrt(u1.z);
+        const float b1 = 1.0f - sq, b2 = u1.w * sq;
+        const F3 a = f3(e.p1.x, e.p1.y, e.p1.z), b = f3(e.p2.x, e.p2.y, e.p2.z), c = f3(e.p3.x, e.p3.y, e.p3.z);
+        const F3 xl = a * (1.0f - b1 - b2) + b * b1 + c * b2;
+        const F3 nl = f3(e.n.x, e.n.y, e.n.z);
+        const F3 dv = xl - P;
+        const float dist = sqrtf(dot(dv, dv));
+        o.wo = dv * (1.0f / dist);
+        if (dot(-o.wo, nl) > 0.f) {
+            const float G = geometry_term(P, N, xl, nl, degenerated);
+            o.pl = G == 0.f ? 0.f : l.inv_area_j / G;
+        }
+        o.tmax = dist * (1.0f - (float)kEps);                           // include/lm/scene.h:349-356
+    } else if (l.type == LIGHT_POINT) {                                 // light_point.cpp:96-114, surface.h:329-348
+        const F3 dv = f3(l.pos[0], l.pos[1], l.pos[2]) - P;
+        const float d2 = dot(dv, dv), dist = sqrtf(d2);
+        o.wo = dv * (1.0f / dist);
+        const float c = degenerated ? 1.0f : fabsf(dot(N, o.wo));       // G = |n.d| / r^2 toward a degenerated point
+        o.pl = c == 0.f ? 0.f : d2 / c;
+        o.tmax = dist * (1.0f - (float)kEps);
+        o.delta = true;
+    } else if (l.type == LIGHT_DIRECTIONAL) {                           // light_directional.cpp:93-108
+        o.wo = -f3(l.pos[0], l.pos[1], l.pos[2]);
+        const float c = degenerated ? 1.0f : fabsf(dot(N, o.wo));
+        o.pl = c == 0.f ? 0.f : 1.0f / c;
+        o.tmax = (float)(kInf - 1.0);
+        o.delta = true;
+    } else {                                                            // light_envconst.cpp:100-119, light_env.cpp:139-162
+        const R4 u2 = rand4(p.seed, key, sample_index, block + 1u);
+        o.wo = l.type == LIGHT_ENV ? env_sample_dir(l, s.cdf, u2) : -sample_uniform_sphere(u2.x, u2.y);
+        o.pl = light_env_pdf(s, l, N, o.wo, degenerated);
+        o.Le = light_env_radiance(s, l, o.wo);
+        o.tmax = (float)(kInf - 1.0);
+    }
+    return o;
+}
+
+// Film::raster_to_pixel (include/lm/film.h:166-171)
+LMCU_HD uint32_t raster_to_pixel(const PtParams& p, float rpx, float rpy) {
+    int x = (int)(rpx * (float)p.width), y = (int)(rpy * (float)p.height);
+    x = x < 0 ? 0 : (x > p.width - 1 ? p.width - 1 : x);
+    y = y < 0 ? 0 : (y > p.height - 1 ? p.height - 1 : y);
+    return (uint32_t)y * (uint32_t)p.width + (uint32_t)x;
+}
+
+struct GenOut {
+    bool shadow;            // image mode: NEE from the camera vertex produced a shadow ray
+    float4 sh_o, sh_d, sh_c;
+};
+
+// First path vertex: camera endpoint + direction through the sample window (renderer_pt.cpp:96-113,197-206).  In image
+// mode the camera vertex is itself samplable by NEE (renderer_pt.cpp:126-140): a light point is connected straight
+// to the pinhole and splatted at ITS raster position (:151-157), and the primary direction carries the camera's
+// pdf_direction J(wo) so that a direct hit on an emitter is MIS-weighted against that connection (:248-263).
+LMCU_HD GenOut pt_generate_body(const DevScene& s, const PtParams& p, uint64_t g, const PathQueue& q, uint32_t slot) {
+    GenOut out;
+    out.shadow = false;
+    uint32_t pixel, sample, sample_hi = 0; int x, y;
+    float rpx, rpy;
+    if (p.image_mode) {
+        // scheduler::spi (src/scheduler.cpp:131-141): sample g of the whole image; the raster position is uniform in
+        // [0,1)^2 and the pixel follows from it
+        const R4 u = rand4(p.seed, kImagePrimaryKey, p.sample_offset + g, 0);
+        rpx = u.x; rpy = u.y;
+        pixel = raster_to_pixel(p, rpx, rpy);
+        sample = (uint32_t)g; sample_hi = (uint32_t)(g >> 32) & 0xffffu;
+    } else {
+        path_pixel(p, g, pixel, sample, x, y);
+        const R4 u = rand4(p.seed, pixel, p.sample_offset + sample, 0);
+        rpx = ((float)x + u.x) / (float)p.width; rpy = ((float)y + u.y) / (float)p.height;
+    }
     const float rx = 2.0f * rpx - 1.0f, ry = 2.0f * rpy - 1.0f;
     const CameraDev& c = s.cam;
     const F3 dl = normalize(f3((float)(c.aspect * c.tf) * rx, (float)c.tf * ry, -1.0f));
     const F3 d = f3((float)c.u[0], (float)c.u[1], (float)c.u[2]) * dl.x + f3((float)c.v[0], (float)c.v[1], (float)c.v[2]) * dl.y
                + f3((float)c.w[0], (float)c.w[1], (float)c.w[2]) * dl.z;
-    q.ray_o[slot] = make_float4((float)c.pos[0], (float)c.pos[1], (float)c.pos[2], (float)kEps);
+    const F3 cpos = f3((float)c.pos[0], (float)c.pos[1], (float)c.pos[2]);
+    const bool camera_nee = p.image_mode && p.sampling_mode != 0 /*naive*/;
+    float pdf_dir = 0.f;
+    if (camera_nee) {
+        float tx, ty;
+        pdf_dir = camera_importance(c, d, tx, ty);
+        if (s.num_lights > 0) {
+            const uint64_t sidx = p.sample_offset + g;
+            const LightSample ls = sample_light(s, p, kImagePrimaryKey, sidx, 1u, cpos, f3s(0.f), true);
+            float lx, ly;
+            const float We = ls.pl > 0.f ? camera_importance(c, ls.wo, lx, ly) : 0.f;     // Camera::eval (camera_pinhole.cpp:233-238)
+            if (We > 0.f) {
+                float mis = 1.f;
+                if (p.sampling_mode == 2 && !ls.delta) {
+                    const float p_light = ls.pl / (float)s.num_lights;
+                    mis = p_light / (p_light + We);                                         // pdf_direction of the camera = J = We
+                }
+                const F3 C = ls.Le * (We * mis * (float)s.num_lights / ls.pl);
+                if (!is_zero(C)) {
+                    out.shadow = true;
+                    out.sh_o = make_float4(cpos.x, cpos.y, cpos.z, (float)kEps);
+                    out.sh_d = make_float4(ls.wo.x, ls.wo.y, ls.wo.z, ls.tmax);
+                    out.sh_c = make_float4(C.x, C.y, C.z, u2f(raster_to_pixel(p, lx, ly)));
+                }
+            }
+        }
+    }
+    q.ray_o[slot] = make_float4(cpos.x, cpos.y, cpos.z, (float)kEps);
     q.ray_d[slot] = make_float4(d.x, d.y, d.z, (float)kInf);
     q.thr_pix[slot] = make_float4(1.f, 1.f, 1.f, u2f(pixel));
-    q.aux[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
-    q.info[slot] = make_uint2(sample, 1u);   // num_verts = 1, prev_nee = 0
+    q.aux[slot] = make_float4(pdf_dir, 0.f, 0.f, 0.f);
+    // num_verts = 1; prev_nee + prev_degenerated (bits 8, 9) when the camera vertex was sampled by NEE
+    q.info[slot] = make_uint2(sample, 1u | (camera_nee ? 0x300u : 0u) | (sample_hi << 16));
+    return out;
 }
 
 template <bool ANY, bool COUNT, typename TriT>
@@ -240,14 +371,6 @@ struct ShadeOut {
     F3 emit;                // direct-hit contribution to add to the film now
 };
 
-// Geometry term between a surface vertex (normal n1) and a light point (normal n2): surface.h:329-348
-LMCU_HD float geometry_term(F3 p1, F3 n1, F3 p2, F3 n2) {
-    F3 d = p2 - p1;
-    const float L2 = dot(d, d);
-    d = d * (1.0f / sqrtf(L2));
-    return fabsf(dot(n1, d)) * fabsf(dot(n2, -d)) / L2;
-}
-
 // One path vertex: everything the reference does between Scene::intersect returning `hit` and the next
 // Scene::intersect (renderer_pt.cpp:229-300 for the hit, then :127-209 of the next loop iteration).
 LMCU_HD ShadeOut pt_shade_body(const DevScene& s, const PtParams& p, float4 ro, float4 rd, float4 thr_pix, float4 aux,
@@ -255,9 +378,10 @@ LMCU_HD ShadeOut pt_shade_body(const DevScene& s, const PtParams& p, float4 ro, 
     ShadeOut out;
     out.alive = false; out.shadow = false; out.emit = f3s(0.f);
     const uint32_t pixel = f2u(thr_pix.w);
-    const uint32_t sample = info.x;
+    const uint64_t sample = (uint64_t)info.x | ((uint64_t)(info.y >> 16) << 32);
     uint32_t num_verts = info.y & 0xffu;
     const bool prev_nee = (info.y >> 8) & 1u;
+    const bool prev_degen = (info.y >> 9) & 1u;       // the previous vertex is the pinhole camera (image mode)
     F3 thr = f3(thr_pix.x, thr_pix.y, thr_pix.z);
     const F3 rdir = f3(rd.x, rd.y, rd.z);
     const F3 wi = -rdir;
@@ -272,7 +396,7 @@ LMCU_HD ShadeOut pt_shade_body(const DevScene& s, const PtParams& p, float4 ro, 
             float mis = 1.f;
             if (p.sampling_mode == 2 && prev_nee) {
                 const F3 np = f3(aux.y, aux.z, aux.w);
-                const float pl = inv_nl * light_env_pdf(s, l, np, rdir);
+                const float pl = inv_nl * light_env_pdf(s, l, np, rdir, prev_degen);
                 mis = (aux.x == 0.f && pl == 0.f) ? 0.f : aux.x / (aux.x + pl);
             }
             out.emit = thr * light_env_radiance(s, l, rdir) * mis;
@@ -290,7 +414,7 @@ LMCU_HD ShadeOut pt_shade_body(const DevScene& s, const PtParams& p, float4 ro, 
             float mis = 1.f;
             if (p.sampling_mode == 2 && prev_nee) {
                 const F3 po = f3(ro.x, ro.y, ro.z), np = f3(aux.y, aux.z, aux.w);
-                const float G = geometry_term(po, np, sp.p, sp.n);
+                const float G = geometry_term(po, np, sp.p, sp.n, prev_degen);
                 const float pl = G == 0.f ? 0.f : inv_nl * l.inv_area_j / G;   // light_area.cpp:172-178
                 mis = (aux.x == 0.f && pl == 0.f) ? 0.f : aux.x / (aux.x + pl);
             }
@@ -313,52 +437,10 @@ LMCU_HD ShadeOut pt_shade_body(const DevScene& s, const PtParams& p, float4 ro, 
 
     // next-event estimation (renderer_pt.cpp:142-192)
     if (nee && s.num_lights > 0) {
-        const R4 u1 = rand4(p.seed, pixel, p.sample_offset + sample, num_verts * 4u + 1u);   // sel, upc, up0, up1
-        int li = (int)(u1.x * (float)s.num_lights);
-        li = li < 0 ? 0 : (li > s.num_lights - 1 ? s.num_lights - 1 : li);  // src/scene.cpp:374-387
-        const LightDev& l = s.lights[li];
-        F3 wo;              // direction from the vertex toward the light
-        F3 Le = f3(l.Ke[0], l.Ke[1], l.Ke[2]);
-        float pl = 0.f;     // pdf_direct, projected SA, without the selection probability
-        bool delta_light = false;   // point / directional: not samplable by BSDF sampling => NEE only, MIS weight 1 (renderer_pt.cpp:176-180)
-        float tmax = 0.f;
-        if (l.type == LIGHT_AREA) {                                         // light_area.cpp:47-59,148-178
-            const int ti = cdf_sample(s.cdf + l.cdf_offset, l.num_tris, u1.y);
-            const EmitTri& e = s.emit[l.tri_offset + ti];
-            const float sq = safe_sqrt(u1.z);
-            const float b1 = 1.0f - sq, b2 = u1.w * sq;
-            const F3 a = f3(e.p1.x, e.p1.y, e.p1.z), b = f3(e.p2.x, e.p2.y, e.p2.z), c = f3(e.p3.x, e.p3.y, e.p3.z);
-            const F3 xl = a * (1.0f - b1 - b2) + b * b1 + c * b2;
-            const F3 nl = f3(e.n.x, e.n.y, e.n.z);
-            const F3 dv = xl - sp.p;
-            const float dist = sqrtf(dot(dv, dv));
-            wo = dv * (1.0f / dist);
-            if (dot(-wo, nl) > 0.f) {
-                const float G = geometry_term(sp.p, sp.n, xl, nl);
-                pl = G == 0.f ? 0.f : l.inv_area_j / G;
-            }
-            tmax = dist * (1.0f - (float)kEps);                             // include/lm/scene.h:349-356
-        } else if (l.type == LIGHT_POINT) {                                 // light_point.cpp:96-114, surface.h:329-348
-            const F3 dv = f3(l.pos[0], l.pos[1], l.pos[2]) - sp.p;
-            const float d2 = dot(dv, dv), dist = sqrtf(d2);
-            wo = dv * (1.0f / dist);
-            const float c = fabsf(dot(sp.n, wo));                           // G = |n.d| / r^2 toward a degenerated point
-            pl = c == 0.f ? 0.f : d2 / c;
-            tmax = dist * (1.0f - (float)kEps);
-            delta_light = true;
-        } else if (l.type == LIGHT_DIRECTIONAL) {                           // light_directional.cpp:93-108
-            wo = -f3(l.pos[0], l.pos[1], l.pos[2]);
-            const float c = fabsf(dot(sp.n, wo));
-            pl = c == 0.f ? 0.f : 1.0f / c;
-            tmax = (float)(kInf - 1.0);
-            delta_light = true;
-        } else {                                                            // light_envconst.cpp:100-119, light_env.cpp:139-162
-            const R4 u2 = rand4(p.seed, pixel, p.sample_offset + sample, num_verts * 4u + 2u);
-            wo = l.type == LIGHT_ENV ? env_sample_dir(l, s.cdf, u2) : -sample_uniform_sphere(u2.x, u2.y);
-            pl = light_env_pdf(s, l, sp.n, wo);
-            Le = light_env_radiance(s, l, wo);
-            tmax = (float)(kInf - 1.0);
-        }
+        const LightSample ls = sample_light(s, p, pixel, p.sample_offset + sample, num_verts * 4u + 1u, sp.p, sp.n, false);
+        const F3 wo = ls.wo, Le = ls.Le;          // wo: direction from the vertex toward the light
+        const float pl = ls.pl, tmax = ls.tmax;   // pdf_direct, projected SA, without the selection probability
+        const bool delta_light = ls.delta;
         if (pl > 0.f) {
             const F3 fs = mat_eval(mat, sp.n, wi, wo) * sn_correction(sp.n, sp.gn, wi, wo);
             if (!is_zero(fs)) {
@@ -387,7 +469,7 @@ LMCU_HD ShadeOut pt_shade_body(const DevScene& s, const PtParams& p, float4 ro, 
     out.d = make_float4(bs.wo.x, bs.wo.y, bs.wo.z, (float)kInf);
     out.thr_pix = make_float4(thr.x, thr.y, thr.z, u2f(pixel));
     out.aux = make_float4(bs.pdf, sp.n.x, sp.n.y, sp.n.z);
-    out.info = make_uint2(sample, num_verts | ((nee ? 1u : 0u) << 8));
+    out.info = make_uint2(info.x, num_verts | ((nee ? 1u : 0u) << 8) | (info.y & 0xffff0000u));
     return out;
 }
 

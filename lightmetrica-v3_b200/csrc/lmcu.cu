@@ -8,6 +8,7 @@
 #include <cub/cub.cuh>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -203,24 +204,14 @@ __global__ void __launch_bounds__(128) k_ao(DevScene s, int width, int height, l
 }
 
 // -- wavefront pt ----------------------------------------------------------------------------------
-// generate: refill the current queue up to capacity with new camera paths (contiguous -> coherent warps)
-__global__ void k_pt_generate(DevScene s, PtParams p, PathQueue q, PtCounters* ctr, int cur) {
-    const uint32_t m = ctr->count[cur];
-    const unsigned long long next = ctr->next_path;
-    const unsigned long long remaining = p.total_paths - next;
-    const uint32_t room = p.capacity - m;
-    const uint32_t n_new = remaining < room ? (uint32_t)remaining : room;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_new; i += gridDim.x * blockDim.x) {
-        pt_generate_body(s, p, next + i, q, m + i);
-    }
-}
-
-// advance: single thread; publishes the refilled count and resets the per-iteration cursors
+// advance: single thread; sizes this iteration's refill (new camera paths up to capacity), publishes the new count
+// and resets the per-iteration cursors
 __global__ void k_pt_advance(PtParams p, PtCounters* ctr, int cur) {
     const uint32_t m = ctr->count[cur];
     const unsigned long long remaining = p.total_paths - ctr->next_path;
     const uint32_t room = p.capacity - m;
     const uint32_t n_new = remaining < room ? (uint32_t)remaining : room;
+    ctr->gen_slot = m; ctr->gen_count = n_new; ctr->gen_first = ctr->next_path;
     ctr->count[cur] = m + n_new;
     ctr->next_path += n_new;
     ctr->count[cur ^ 1] = 0;
@@ -230,6 +221,30 @@ __global__ void k_pt_advance(PtParams p, PtCounters* ctr, int cur) {
     ctr->rays += m + n_new;
     ctr->extend_rays += m + n_new;
     ctr->iterations += 1;
+}
+
+// generate: refill the current queue with new camera paths (contiguous -> coherent warps).  In image mode the camera
+// vertex's own NEE connection goes to the shadow queue (ballot-ranked, one atomic per warp).
+__global__ void k_pt_generate(DevScene s, PtParams p, PathQueue q, ShadowQueue sq, PtCounters* ctr) {
+    const uint32_t m = ctr->gen_slot, n_new = ctr->gen_count;
+    const unsigned long long first = ctr->gen_first;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t base = blockIdx.x * blockDim.x; base < n_new; base += stride) {     // warp-uniform trip count
+        const uint32_t i = base + threadIdx.x;
+        GenOut o;
+        o.shadow = false;
+        if (i < n_new) o = pt_generate_body(s, p, first + i, q, m + i);
+        if (p.image_mode) {
+            const uint32_t b = __ballot_sync(0xffffffffu, o.shadow);
+            if (b) {
+                uint32_t pos = 0;
+                if (lane == 0) pos = atomicAdd(&ctr->shadow_count, (uint32_t)__popc(b));
+                pos = __shfl_sync(0xffffffffu, pos, 0) + (uint32_t)__popc(b & ((1u << lane) - 1u));
+                if (o.shadow) { sq.ray_o[pos] = o.sh_o; sq.ray_d[pos] = o.sh_d; sq.contrib[pos] = o.sh_c; }
+            }
+        }
+    }
 }
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
@@ -697,6 +712,7 @@ int lmcu_accel_build(LmcuScene* s, const LmcuBuildOptions* opts, LmcuBuildStats*
     CU(cudaMemcpyAsync(&h_exact, exact.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     s->fp32 = h_exact != 0;
+    if (getenv("LMCU_TRI64")) s->fp32 = false;                        // tuning only: force the 80-byte FP64 triangle records
     s->t32.release(); s->t64.release();
     if (s->fp32) CU(s->t32.alloc(nt)); else CU(s->t64.alloc(nt));
     CU(s->shade.alloc(nt));
@@ -961,39 +977,31 @@ int lmcu_render_ao(LmcuScene* s, const LmcuRenderParams* p, float* film_rgb, Lmc
 }
 
 // -- pt ---------------------------------------------------------------------------------------------------
-static int ensure_pt_pools(LmcuScene* s, uint32_t capacity) {
-    if (s->pt_capacity == capacity && s->pt_ctr.p) return LMCU_OK;
+// shadow_factor: 1, or 2 in image mode where one iteration can hold a camera-vertex NEE ray per NEW path on top of one
+// NEE ray per path in the queue
+static int ensure_pt_pools(LmcuScene* s, uint32_t capacity, uint32_t shadow_factor) {
+    if (s->pt_capacity == capacity && s->pt_ctr.p && s->sq[0].n >= (size_t)capacity * shadow_factor) return LMCU_OK;
     for (int b = 0; b < 2; b++) {
         for (int k = 0; k < 4; k++) CU(s->pq[b][k].alloc(capacity));
         CU(s->pinfo[b].alloc(capacity));
     }
     CU(s->hits.alloc(capacity));
-    for (int k = 0; k < 3; k++) CU(s->sq[k].alloc(capacity));
+    for (int k = 0; k < 3; k++) CU(s->sq[k].alloc((size_t)capacity * shadow_factor));
     CU(s->pt_ctr.alloc(1));
     s->pt_capacity = capacity;
     return LMCU_OK;
 }
 
-int lmcu_render_pt(LmcuScene* s, const LmcuRenderParams* p, float* film_rgb, LmcuRenderStats* stats) {
-    int rc = require_renderable(s, true);
-    if (rc) return rc;
-    if (!p || p->spp <= 0) return fail(LMCU_ERR_INVALID_ARGUMENT, "spp must be positive");
-    if (p->max_verts < 2) return fail(LMCU_ERR_INVALID_ARGUMENT, "max_verts must be >= 2");
-    if (p->sampling_mode < 0 || p->sampling_mode > 2) return fail(LMCU_ERR_INVALID_ARGUMENT, "bad sampling_mode");
-    CU(cudaSetDevice(s->device));
-    rc = ensure_film(s, p->width, p->height);
-    if (rc) return rc;
-    uint32_t capacity = 1u << 23;        // 8 Mi paths in flight: 72 B x 2 queues + 48 B shadow + 16 B hit = 1.7 GB
-    if (const char* e = getenv("LMCU_PT_POOL")) capacity = (uint32_t)std::max(1024l, atol(e));
-    rc = ensure_pt_pools(s, capacity);
-    if (rc) return rc;
+// One wavefront pass: traces pp.total_paths paths (sample indices pp.sample_offset ...) to completion, accumulating into
+// the film.  Adds its counters and per-kernel times to `acc`.
+struct PtAccum {
+    int64_t launches = 0, extend_launches = 0;
+    double t_extend = 0, t_shade = 0, t_shadow = 0;
+    unsigned long long rays = 0, extend_rays = 0, shadow_rays = 0, nodes_extend = 0, tris_extend = 0, nodes_shadow = 0, tris_shadow = 0;
+};
+
+static int pt_pass(LmcuScene* s, const PtParams& pp, bool count, PtAccum& acc) {
     cudaStream_t st = s->stream;
-    PtParams pp{};
-    pp.width = p->width; pp.height = p->height; pp.max_verts = p->max_verts; pp.sampling_mode = p->sampling_mode;
-    pp.seed = p->seed; pp.tiled = (p->width % 8 == 0 && p->height % 4 == 0) ? 1u : 0u;
-    pp.sample_offset = (uint64_t)p->sample_offset;
-    pp.total_paths = (uint64_t)p->width * p->height * (uint64_t)p->spp;
-    pp.capacity = capacity;
     PathQueue q[2];
     for (int b = 0; b < 2; b++) {
         q[b].ray_o = s->pq[b][0].p; q[b].ray_d = s->pq[b][1].p; q[b].thr_pix = s->pq[b][2].p; q[b].aux = s->pq[b][3].p;
@@ -1002,26 +1010,21 @@ int lmcu_render_pt(LmcuScene* s, const LmcuRenderParams* p, float* film_rgb, Lmc
     ShadowQueue sq;
     sq.ray_o = s->sq[0].p; sq.ray_d = s->sq[1].p; sq.contrib = s->sq[2].p;
     CU(cudaMemsetAsync(s->pt_ctr.p, 0, sizeof(PtCounters), st));
-    CU(cudaEventRecord(s->ev0, st));
     const DevScene d = s->dev();
     const unsigned q_blocks = (unsigned)(s->num_sms * s->ctas_per_sm);
     const unsigned shade_blocks = (unsigned)s->num_sms * 6, gen_blocks = (unsigned)s->num_sms * 4;
     int cur = 0;
-    int64_t launches = 0;
     PtCounters h{};
-    const bool count = p->count_traversal != 0;
     const int kGroup = 4;                       // iterations between host checks
     if (s->ring.empty()) {
         s->ring.resize(kGroup * 4);
         for (auto& e : s->ring) CU(cudaEventCreate(&e));
     }
-    double t_extend = 0, t_shade = 0, t_shadow = 0;
-    int64_t extend_launches = 0;
     while (true) {
         for (int it = 0; it < kGroup; it++) {
             cudaEvent_t* ev = &s->ring[it * 4];
-            k_pt_generate<<<gen_blocks, 256, 0, st>>>(d, pp, q[cur], s->pt_ctr.p, cur);
             k_pt_advance<<<1, 1, 0, st>>>(pp, s->pt_ctr.p, cur);
+            k_pt_generate<<<gen_blocks, 256, 0, st>>>(d, pp, q[cur], sq, s->pt_ctr.p);
             cudaEventRecord(ev[0], st);
             LMCU_DISPATCH(k_pt_extend_q, s->fp32, count, q_blocks, 128, st, d, q[cur], s->hits.p, s->pt_ctr.p, cur);
             cudaEventRecord(ev[1], st);
@@ -1030,24 +1033,97 @@ int lmcu_render_pt(LmcuScene* s, const LmcuRenderParams* p, float* film_rgb, Lmc
             LMCU_DISPATCH(k_pt_shadow_q, s->fp32, count, q_blocks, 128, st, d, sq, s->film.p, s->pt_ctr.p);
             cudaEventRecord(ev[3], st);
             cur ^= 1;
-            launches += 5;
-            extend_launches++;
+            acc.launches += 5;
+            acc.extend_launches++;
         }
         CU(cudaGetLastError());
         CU(cudaMemcpyAsync(&h, s->pt_ctr.p, sizeof(h), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         for (int it = 0; it < kGroup; it++) {
             float ms = 0;
-            cudaEventElapsedTime(&ms, s->ring[it * 4 + 0], s->ring[it * 4 + 1]); t_extend += ms * 1e-3;
-            cudaEventElapsedTime(&ms, s->ring[it * 4 + 1], s->ring[it * 4 + 2]); t_shade += ms * 1e-3;
-            cudaEventElapsedTime(&ms, s->ring[it * 4 + 2], s->ring[it * 4 + 3]); t_shadow += ms * 1e-3;
+            cudaEventElapsedTime(&ms, s->ring[it * 4 + 0], s->ring[it * 4 + 1]); acc.t_extend += ms * 1e-3;
+            cudaEventElapsedTime(&ms, s->ring[it * 4 + 1], s->ring[it * 4 + 2]); acc.t_shade += ms * 1e-3;
+            cudaEventElapsedTime(&ms, s->ring[it * 4 + 2], s->ring[it * 4 + 3]); acc.t_shadow += ms * 1e-3;
         }
         if (h.overflow) return fail(LMCU_ERR_CUDA, "bvh traversal stack overflow");
         if (h.next_path >= pp.total_paths && h.count[cur] == 0) break;
     }
+    acc.rays += h.rays; acc.extend_rays += h.extend_rays; acc.shadow_rays += h.shadow_rays;
+    acc.nodes_extend += h.nodes_extend; acc.tris_extend += h.tris_extend;
+    acc.nodes_shadow += h.nodes_shadow; acc.tris_shadow += h.tris_shadow;
+    return LMCU_OK;
+}
+
+int lmcu_render_pt(LmcuScene* s, const LmcuRenderParams* p, float* film_rgb, LmcuRenderStats* stats) {
+    int rc = require_renderable(s, true);
+    if (rc) return rc;
+    if (!p) return fail(LMCU_ERR_INVALID_ARGUMENT, "null params");
+    const bool image = p->primary_ray_sampling_mode == LMCU_PRIMARY_IMAGE;
+    const bool timed = p->scheduler == LMCU_SCHED_TIME;
+    if (p->primary_ray_sampling_mode != LMCU_PRIMARY_PIXEL && !image) return fail(LMCU_ERR_INVALID_ARGUMENT, "bad primary_ray_sampling_mode");
+    if (p->scheduler != LMCU_SCHED_SAMPLE && !timed) return fail(LMCU_ERR_INVALID_ARGUMENT, "bad scheduler");
+    if (timed) {
+        if (!(p->render_time >= 0)) return fail(LMCU_ERR_INVALID_ARGUMENT, "render_time must be >= 0");
+    } else if (image) {
+        if (p->num_samples <= 0) return fail(LMCU_ERR_INVALID_ARGUMENT, "num_samples must be positive");
+    } else if (p->spp <= 0) {
+        return fail(LMCU_ERR_INVALID_ARGUMENT, "spp must be positive");
+    }
+    if (p->max_verts < 2) return fail(LMCU_ERR_INVALID_ARGUMENT, "max_verts must be >= 2");
+    if (p->sampling_mode < 0 || p->sampling_mode > 2) return fail(LMCU_ERR_INVALID_ARGUMENT, "bad sampling_mode");
+    CU(cudaSetDevice(s->device));
+    rc = ensure_film(s, p->width, p->height);
+    if (rc) return rc;
+    uint32_t capacity = 1u << 23;        // 8 Mi paths in flight: 72 B x 2 queues + 48 B shadow + 16 B hit = 1.7 GB
+    if (const char* e = getenv("LMCU_PT_POOL")) capacity = (uint32_t)std::max(1024l, atol(e));
+    rc = ensure_pt_pools(s, capacity, image ? 2u : 1u);
+    if (rc) return rc;
+    cudaStream_t st = s->stream;
+    const uint64_t npix = (uint64_t)p->width * p->height;
+    PtParams pp{};
+    pp.width = p->width; pp.height = p->height; pp.max_verts = p->max_verts; pp.sampling_mode = p->sampling_mode;
+    pp.seed = p->seed; pp.tiled = (p->width % 8 == 0 && p->height % 4 == 0) ? 1u : 0u;
+    pp.capacity = capacity;
+    pp.image_mode = image ? 1u : 0u;
+    const bool count = p->count_traversal != 0;
+    PtAccum acc;
+    // `unit` = what one scheduler step processes: one sample of every pixel (scheduler::spp) or one sample of the image
+    // (scheduler::spi); a pass renders `units` of them starting at sample index sample_offset + processed.
+    const uint64_t paths_per_unit = image ? 1ull : npix;
+    int64_t processed = 0;
+    auto run_units = [&](int64_t units) -> int {
+        pp.sample_offset = (uint64_t)p->sample_offset + (uint64_t)processed;
+        pp.total_paths = paths_per_unit * (uint64_t)units;
+        const int r = pt_pass(s, pp, count, acc);
+        if (r == LMCU_OK) processed += units;
+        return r;
+    };
+    CU(cudaEventRecord(s->ev0, st));
+    if (!timed) {
+        rc = run_units(image ? p->num_samples : p->spp);
+        if (rc) return rc;
+    } else {
+        // scheduler::{spp,spi}::time (src/scheduler.cpp:75-103,162-187): whole passes until the clock passes render_time,
+        // checked after each pass.  The reference's pass is 1 spp (or samples_per_iter samples); here a pass is a
+        // multiple of that, sized from the measured rate so that the wavefront stays full and the overshoot small.
+        const int64_t iter = image ? (p->samples_per_iter > 0 ? p->samples_per_iter : 100000) : 1;   // reference granularity
+        const auto t0 = std::chrono::steady_clock::now();
+        int64_t units = std::max<int64_t>(1, (int64_t)(capacity / paths_per_unit) / iter) * iter;    // first pass: one full queue
+        while (true) {
+            rc = run_units(units);
+            if (rc) return rc;
+            const double elapsed = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            if (elapsed > p->render_time) break;
+            const double rate = (double)processed / std::max(elapsed, 1e-6);                          // units per second
+            const double want = (p->render_time - elapsed) * rate * 0.5;                              // approach the budget geometrically
+            units = std::max<int64_t>(1, (int64_t)(want / (double)iter)) * iter;
+        }
+    }
     if (p->rescale) {
-        k_scale<<<s->num_sms * 4, 256, 0, st>>>(s->film.p, s->film.n, (float)(1.0 / (double)p->spp));   // renderer_pt.cpp:307-309
-        launches++;
+        // renderer_pt.cpp:307-312: 1/processed (pixel mode) or w*h/processed (image mode)
+        const double scale = image ? (double)npix / (double)processed : 1.0 / (double)processed;
+        k_scale<<<s->num_sms * 4, 256, 0, st>>>(s->film.p, s->film.n, (float)scale);
+        acc.launches++;
     }
     CU(cudaEventRecord(s->ev1, st));
     if (film_rgb) CU(cudaMemcpyAsync(film_rgb, s->film.p, s->film.n * sizeof(float), cudaMemcpyDeviceToHost, st));
@@ -1056,16 +1132,16 @@ int lmcu_render_pt(LmcuScene* s, const LmcuRenderParams* p, float* film_rgb, Lmc
         float ms = 0;
         CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
         memset(stats, 0, sizeof(*stats));
-        stats->elapsed = ms * 1e-3; stats->processed = p->spp; stats->paths = (int64_t)pp.total_paths;
-        stats->rays = (int64_t)h.rays; stats->kernel_launches = launches;
-        stats->extend_seconds = t_extend; stats->shade_seconds = t_shade; stats->shadow_seconds = t_shadow;
-        stats->extend_launches = extend_launches;
-        stats->extend_rays = (int64_t)h.extend_rays; stats->shadow_rays = (int64_t)h.shadow_rays;
-        if (count && h.extend_rays) {
-            stats->bvh_nodes_per_ray = (double)h.nodes_extend / (double)h.extend_rays;
-            stats->bvh_tris_per_ray = (double)h.tris_extend / (double)h.extend_rays;
-            stats->shadow_nodes_per_ray = h.shadow_rays ? (double)h.nodes_shadow / (double)h.shadow_rays : 0.0;
-            stats->shadow_tris_per_ray = h.shadow_rays ? (double)h.tris_shadow / (double)h.shadow_rays : 0.0;
+        stats->elapsed = ms * 1e-3; stats->processed = processed; stats->paths = (int64_t)(paths_per_unit * (uint64_t)processed);
+        stats->rays = (int64_t)acc.rays; stats->kernel_launches = acc.launches;
+        stats->extend_seconds = acc.t_extend; stats->shade_seconds = acc.t_shade; stats->shadow_seconds = acc.t_shadow;
+        stats->extend_launches = acc.extend_launches;
+        stats->extend_rays = (int64_t)acc.extend_rays; stats->shadow_rays = (int64_t)acc.shadow_rays;
+        if (count && acc.extend_rays) {
+            stats->bvh_nodes_per_ray = (double)acc.nodes_extend / (double)acc.extend_rays;
+            stats->bvh_tris_per_ray = (double)acc.tris_extend / (double)acc.extend_rays;
+            stats->shadow_nodes_per_ray = acc.shadow_rays ? (double)acc.nodes_shadow / (double)acc.shadow_rays : 0.0;
+            stats->shadow_tris_per_ray = acc.shadow_rays ? (double)acc.tris_shadow / (double)acc.shadow_rays : 0.0;
         }
     }
     return LMCU_OK;

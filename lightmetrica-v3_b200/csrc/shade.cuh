@@ -292,12 +292,13 @@ LMCU_HD float env_dist_pdf(const LightDev& l, const float* cdf, float u, float v
 }
 
 // Light::pdf_direct in projected solid angle at a surface point with shading normal n (light_env.cpp:164-181)
-LMCU_HD float env_pdf_direct(const LightDev& l, const float* cdf, F3 n, F3 d) {
+LMCU_HD float env_pdf_direct(const LightDev& l, const float* cdf, F3 n, F3 d, bool degenerated = false) {
     float u, v;
     env_dir_to_uv(l, d, u, v);
     const float st = safe_sqrt(1.0f - d.y * d.y);
     if (st == 0.f) return 0.f;
     const float pdf_sa = env_dist_pdf(l, cdf, u, v) / (2.0f * kPiF * kPiF * st);
+    if (degenerated) return pdf_sa;                                 // surface.h:377-390: no cosine at a degenerated point
     const float J = fabsf(dot(n, d));
     return J == 0.f ? 0.f : pdf_sa / J;
 }
@@ -319,6 +320,21 @@ struct CameraDev {
     double pos[3], u[3], v[3], w[3];
     double tf, aspect;
 };
+
+// Camera_Pinhole::raster_position + J (camera_pinhole.cpp:101-109,207-226), FP32: importance = pdf_direction of a
+// world direction wo leaving the camera; 0 outside the view frustum.  rp = raster position in [0,1]^2.
+LMCU_HD float camera_importance(const CameraDev& c, F3 wo, float& rpx, float& rpy) {
+    const float ex = (float)c.u[0] * wo.x + (float)c.u[1] * wo.y + (float)c.u[2] * wo.z;
+    const float ey = (float)c.v[0] * wo.x + (float)c.v[1] * wo.y + (float)c.v[2] * wo.z;
+    const float ez = (float)c.w[0] * wo.x + (float)c.w[1] * wo.y + (float)c.w[2] * wo.z;
+    if (ez >= 0.f) return 0.f;
+    const float tf = (float)c.tf, aspect = (float)c.aspect;
+    rpx = -ex / ez / tf / aspect * 0.5f + 0.5f;
+    rpy = -ey / ez / tf * 0.5f + 0.5f;
+    if (rpx < 0.f || rpx > 1.f || rpy < 0.f || rpy > 1.f) return 0.f;
+    const float inv = -1.0f / ez;
+    return inv * inv * inv / (tf * tf * aspect * 4.0f);
+}
 
 // FP64 primary ray with glm's operation order: bit-identical to Camera_Pinhole::primary_ray.
 LMCU_HD void camera_primary_ray_d(const CameraDev& c, double rpx, double rpy, D3& o, D3& d) {

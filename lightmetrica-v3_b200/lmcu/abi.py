@@ -29,6 +29,8 @@ class LmcuPrimitive(C.Structure):
 MAT_DIFFUSE, MAT_GLOSSY, MAT_GLASS, MAT_MIRROR = 0, 1, 2, 3
 LIGHT_AREA, LIGHT_ENVCONST, LIGHT_ENV, LIGHT_POINT, LIGHT_DIRECTIONAL = 0, 1, 2, 3, 4
 SAMPLING_NAIVE, SAMPLING_NEE, SAMPLING_MIS = 0, 1, 2
+PRIMARY_PIXEL, PRIMARY_IMAGE = 0, 1
+SCHED_SAMPLE, SCHED_TIME = 0, 1
 
 
 class LmcuMaterial(C.Structure):
@@ -61,7 +63,9 @@ class LmcuRenderParams(C.Structure):
                 ("sampling_mode", C.c_int32), ("spp", C.c_int64), ("sample_offset", C.c_int64),
                 ("seed", C.c_uint32), ("rescale", C.c_int32), ("use_constant_color", C.c_int32),
                 ("visualize_normal", C.c_int32), ("has_color", C.c_int32), ("count_traversal", C.c_int32),
-                ("bg_color", c_double3), ("color", c_double3), ("ao_distance", C.c_double)]
+                ("bg_color", c_double3), ("color", c_double3), ("ao_distance", C.c_double),
+                ("primary_ray_sampling_mode", C.c_int32), ("scheduler", C.c_int32), ("num_samples", C.c_int64),
+                ("samples_per_iter", C.c_int64), ("render_time", C.c_double)]
 
 
 class LmcuRenderStats(C.Structure):
@@ -85,7 +89,9 @@ class LmcuBuildStats(C.Structure):
 
 def render_params(width, height, spp=1, max_verts=20, seed=42, sampling_mode=SAMPLING_MIS,
                   sample_offset=0, rescale=1, bg_color=(0, 0, 0), use_constant_color=False,
-                  visualize_normal=False, color=None, ao_distance=0.2, count_traversal=False):
+                  visualize_normal=False, color=None, ao_distance=0.2, count_traversal=False,
+                  primary_ray_sampling_mode=PRIMARY_PIXEL, scheduler=SCHED_SAMPLE, num_samples=0,
+                  samples_per_iter=0, render_time=0.0):
     """Defaults follow the reference renderers' JSON defaults (renderer_pt.cpp:51-77,
     renderer_raycast.cpp:48-60, functest/renderer_ao.cpp:36-40)."""
     p = LmcuRenderParams()
@@ -97,4 +103,6 @@ def render_params(width, height, spp=1, max_verts=20, seed=42, sampling_mode=SAM
     p.color = c_double3(*(color if color is not None else (0, 0, 0)))
     p.ao_distance = ao_distance
     p.count_traversal = int(count_traversal)
+    p.primary_ray_sampling_mode, p.scheduler = primary_ray_sampling_mode, scheduler
+    p.num_samples, p.samples_per_iter, p.render_time = num_samples, samples_per_iter, render_time
     return p

@@ -468,7 +468,12 @@ private:
     int max_verts_;
     std::optional<unsigned int> seed_;
     int sampling_mode_;
-    long long spp_;
+    int primary_mode_ = LMCU_PRIMARY_PIXEL;     // primary_ray_sampling_mode: pixel -> scheduler::spp::*, image -> scheduler::spi::*
+    int scheduler_ = LMCU_SCHED_SAMPLE;         // scheduler: sample | time
+    long long spp_ = 0;                         // spp::sample
+    long long num_samples_ = 0;                 // spi::sample
+    long long samples_per_iter_ = 0;            // spi::time
+    Float render_time_ = 0_f;                   // {spp,spi}::time
     std::vector<int> devices_;
 
 public:
@@ -483,13 +488,23 @@ public:
             else sampling_mode_ = LMCU_SAMPLING_MIS;
         }
         {
+            // Same keys as renderer::pt (renderer_pt.cpp:63-76) and its schedulers (src/scheduler.cpp:32-35,69-72,127-129,157-160)
             const auto name = json::value<std::string>(prop, "scheduler");
             const auto s = json::value<std::string>(prop, "primary_ray_sampling_mode", "pixel");
-            if (name != "sample" || s != "pixel") {
-                LM_THROW_EXCEPTION(Error::Unsupported,
-                    "renderer::pt_cuda supports scheduler='sample' with primary_ray_sampling_mode='pixel'");
+            if (s == "pixel") primary_mode_ = LMCU_PRIMARY_PIXEL;
+            else if (s == "image") primary_mode_ = LMCU_PRIMARY_IMAGE;
+            else LM_THROW_EXCEPTION(Error::InvalidArgument, "renderer::pt_cuda: unknown primary_ray_sampling_mode '{}'", s);
+            if (name == "sample") {
+                scheduler_ = LMCU_SCHED_SAMPLE;
+                if (primary_mode_ == LMCU_PRIMARY_PIXEL) spp_ = json::value<long long>(prop, "spp");
+                else num_samples_ = json::value<long long>(prop, "num_samples");
             }
-            spp_ = json::value<long long>(prop, "spp");
+            else if (name == "time") {
+                scheduler_ = LMCU_SCHED_TIME;
+                render_time_ = json::value<Float>(prop, "render_time");
+                samples_per_iter_ = json::value<long long>(prop, "samples_per_iter", 100000);
+            }
+            else LM_THROW_EXCEPTION(Error::InvalidArgument, "renderer::pt_cuda: unknown scheduler '{}'", name);
         }
         devices_ = json::value<std::vector<int>>(prop, "devices", std::vector<int>{ device_ });
         if (devices_.empty() || devices_.size() > LMCU_MAX_PEERS + 1) {
@@ -504,18 +519,27 @@ public:
         LmcuRenderParams p{};
         p.width = size.w; p.height = size.h; p.max_verts = max_verts_;
         p.sampling_mode = sampling_mode_;
+        p.primary_ray_sampling_mode = primary_mode_;
+        p.scheduler = scheduler_;
+        p.render_time = render_time_;
+        p.samples_per_iter = samples_per_iter_;
         p.seed = seed_ ? *seed_ : math::rng_seed();
         std::vector<float> rgb(size_t(size.w) * size.h * 3);
         LmcuRenderStats st{};
         const int G = int(devices_.size());
+        const bool image = primary_mode_ == LMCU_PRIMARY_IMAGE;
+        const long long total = image ? num_samples_ : spp_;      // sample schedulers: the work to split
         if (G == 1) {
             device_ = devices_[0];
             upload();
-            p.spp = spp_; p.rescale = 1;
+            p.spp = spp_; p.num_samples = num_samples_; p.rescale = 1;
             check(lmcu_render_pt(dev_.h, &p, rgb.data(), &st));
         }
         else {
             // Sample split: one host thread + one replicated device scene per GPU
+            if (scheduler_ == LMCU_SCHED_SAMPLE && total < G) {
+                LM_THROW_EXCEPTION(Error::InvalidArgument, "renderer::pt_cuda: spp / num_samples must be >= the number of devices");
+            }
             SceneExport ex;
             ex.gather(*scene_, true);
             std::vector<DeviceScene> devs(G);
@@ -527,18 +551,25 @@ public:
                     try {
                         devs[g].upload(ex, devices_[g]);
                         LmcuRenderParams q = p;
-                        const long long base = spp_ / G, rem = spp_ % G;
-                        q.spp = base + (g < rem ? 1 : 0);
-                        q.sample_offset = g * base + std::min<long long>(g, rem);
                         q.rescale = 0;
-                        if (q.spp > 0) check(lmcu_render_pt(devs[g].h, &q, nullptr, &stats[g]));
+                        if (scheduler_ == LMCU_SCHED_SAMPLE) {
+                            const long long base = total / G, rem = total % G;
+                            const long long mine = base + (g < rem ? 1 : 0);
+                            q.spp = image ? 0 : mine; q.num_samples = image ? mine : 0;
+                            q.sample_offset = g * base + std::min<long long>(g, rem);
+                        }
+                        else {
+                            // time budget: every device runs for render_time on its own block of sample indices
+                            // and reports how many it finished; the counts are summed like the films
+                            q.sample_offset = (long long)g << 40;
+                        }
+                        check(lmcu_render_pt(devs[g].h, &q, nullptr, &stats[g]));
                     }
                     catch (const std::exception& e) { errors[g] = e.what(); }
                 });
             }
             for (auto& t : threads) t.join();
             for (const auto& e : errors) if (!e.empty()) LM_THROW_EXCEPTION(Error::None, "renderer::pt_cuda: {}", e);
-            if (spp_ < G) LM_THROW_EXCEPTION(Error::InvalidArgument, "renderer::pt_cuda: spp must be >= the number of devices");
             std::vector<void*> peers;
             for (int g = 1; g < G; g++) {
                 check(lmcu_enable_peer_access(devices_[0], devices_[g]));
@@ -546,10 +577,15 @@ public:
                 check(lmcu_film_device_ptr(devs[g].h, &ptr, &n));
                 peers.push_back(ptr);
             }
-            check(lmcu_film_reduce_peers(devs[0].h, peers.data(), int(peers.size()), 1.0 / double(spp_)));   // renderer_pt.cpp:307-309
+            st.processed = 0;
+            for (int g = 0; g < G; g++) {
+                st.processed += stats[g].processed;
+                st.elapsed = std::max(st.elapsed, stats[g].elapsed);
+            }
+            // renderer_pt.cpp:307-312 on the combined film
+            const double scale = image ? double(size.w) * size.h / double(st.processed) : 1.0 / double(st.processed);
+            check(lmcu_film_reduce_peers(devs[0].h, peers.data(), int(peers.size()), scale));
             check(lmcu_film_download(devs[0].h, rgb.data()));
-            st.processed = spp_;
-            for (int g = 0; g < G; g++) st.elapsed = std::max(st.elapsed, stats[g].elapsed);
         }
         write_film(rgb, false);
         return { {"processed", st.processed}, {"elapsed", st.elapsed} };

@@ -566,6 +566,17 @@ static int camera_raster_position(const OrcScene* sc, V3 wo, double* rx, double*
     return 1;
 }
 
+/* Camera_Pinhole::J / pdf_direction / eval (camera_pinhole.cpp:101-109,157-163,233-238): importance of direction wo */
+static double camera_pdf_direction(const OrcScene* sc, V3 wo) {
+    double rx, ry;
+    if (!camera_raster_position(sc, wo, &rx, &ry)) return 0.0;
+    const double ez = sc->cam_w.x * wo.x + sc->cam_w.y * wo.y + sc->cam_w.z * wo.z;
+    const double cos_theta = -ez;
+    const double inv = 1.0 / cos_theta;
+    const double A = sc->cam_tf * sc->cam_tf * sc->cam_aspect * 4.0;
+    return inv * inv * inv / A;
+}
+
 /* ------------------------------------------------------------------------------------------------
  * Sampling primitives (include/lm/math.h:632-702)
  * ---------------------------------------------------------------------------------------------- */
@@ -917,11 +928,13 @@ void orc_render_ao(const OrcScene* sc, const LmcuRenderParams* p, double* film, 
     }
 }
 
-/* Renderer_PT::render (src/renderer/renderer_pt.cpp:80-315), pixel mode, scheduler::spp::sample
- * (src/scheduler.cpp:37-49: index -> pixel = index / spp, sample = index % spp) */
+/* Renderer_PT::render (src/renderer/renderer_pt.cpp:80-315) with scheduler::spp::sample (src/scheduler.cpp:37-49:
+ * index -> pixel = index / spp, sample = index % spp; pixel mode) or scheduler::spi::sample (:131-141: pixel_index 0,
+ * the window is the whole image; image mode).  The time schedulers are not restated: they are not deterministic. */
 void orc_render_pt(const OrcScene* sc, const LmcuRenderParams* p, double* film, int num_threads) {
     const int w = p->width, h = p->height, nth = resolve_threads(num_threads);
-    const long long spp = p->spp, total = (long long)w * h * spp;
+    const int image = p->primary_ray_sampling_mode == LMCU_PRIMARY_IMAGE;
+    const long long spp = p->spp, total = image ? (long long)p->num_samples : (long long)w * h * spp;
     const int mode = p->sampling_mode;
     memset(film, 0, sizeof(double) * 3 * (size_t)w * h);
     #pragma omp parallel num_threads(nth)
@@ -934,10 +947,11 @@ void orc_render_pt(const OrcScene* sc, const LmcuRenderParams* p, double* film, 
 #endif
         #pragma omp for schedule(dynamic, 1)
         for (long long index = 0; index < total; index++) {
-            const long long pixel_index = index / spp;
+            const long long pixel_index = image ? 0 : index / spp;
             const int px = (int)(pixel_index % w), py = (int)(pixel_index / w);
             const double dx = 1.0 / w, dy = 1.0 / h;
-            const double win[4] = { dx * px, dy * py, dx, dy };                          /* :96-107 */
+            double win[4] = { dx * px, dy * py, dx, dy };                                /* :96-107 */
+            if (image) { win[0] = 0.0; win[1] = 0.0; win[2] = 1.0; win[3] = 1.0; }
             double u4[8];
             for (int i = 0; i < 4; i++) u4[i] = rng_u(&rng);                             /* sample_position: PositionSampleU */
             for (int i = 0; i < 2; i++) u4[i] = rng_u(&rng);                             /* sample_component: ComponentSampleU */
@@ -953,15 +967,19 @@ void orc_render_pt(const OrcScene* sc, const LmcuRenderParams* p, double* film, 
                 int samplable_by_nee = 0;                                                /* :127-140 */
                 if (mode != LMCU_SAMPLING_NAIVE) {
                     const int is_spec = mat ? mat_is_specular(mat) : 0;
-                    samplable_by_nee = num_verts > 1 && !is_spec;
+                    samplable_by_nee = image ? !is_spec : (num_verts > 1 && !is_spec);  /* image mode: NEE from the camera too */
                 }
                 if (samplable_by_nee) {                                                  /* :142-192 */
                     double u[8];
                     for (int i = 0; i < 8; i++) u[i] = rng_u(&rng);                      /* RaySampleU: up, upc, ud, udc */
                     SP spL; V3 woL, wL;
-                    if (sample_direct(sc, u, &sp, &spL, &woL, &wL) && scene_visible(sc, &sp, &spL)) {
+                    double rx = rpx, ry = rpy;                                           /* :151-157 */
+                    if (sample_direct(sc, u, &sp, &spL, &woL, &wL) && scene_visible(sc, &sp, &spL) &&
+                        (num_verts > 1 || camera_raster_position(sc, vneg(woL), &rx, &ry))) {
                         const V3 wo = vneg(woL);
-                        const V3 fs = vscale(mat_eval(mat, &sp, wi, wo, comp, 1), sn_correction(&sp, wi, wo));
+                        V3 fs;                                                           /* path::eval_contrb_direction, path.h:761-775 */
+                        if (mat) fs = vscale(mat_eval(mat, &sp, wi, wo, comp, 1), sn_correction(&sp, wi, wo));
+                        else { const double We = camera_pdf_direction(sc, wo); fs = v3(We, We, We); }
                         if (!vis_zero(fs)) {
                             double mis_w = 1.0;
                             /* renderer_pt.cpp:176-180: a specular (directional) or degenerated (point) light endpoint
@@ -970,10 +988,10 @@ void orc_render_pt(const OrcScene* sc, const LmcuRenderParams* p, double* film, 
                             const int samplable_by_bsdf = ltype != LMCU_LIGHT_DIRECTIONAL && !spL.degenerated;
                             if (mode == LMCU_SAMPLING_MIS && samplable_by_bsdf) {
                                 const double p_light = pdf_direct(sc, &sp, &spL, woL);
-                                const double p_bsdf = mat_pdf(mat, &sp, wi, wo, 1);
+                                const double p_bsdf = mat ? mat_pdf(mat, &sp, wi, wo, 1) : camera_pdf_direction(sc, wo);
                                 mis_w = balance_heuristic(p_light, p_bsdf);
                             }
-                            film_splat(film, w, h, rpx, rpy, vscale(vmul(vmul(throughput, fs), wL), mis_w));
+                            film_splat(film, w, h, rx, ry, vscale(vmul(vmul(throughput, fs), wL), mis_w));
                         }
                     }
                 }
@@ -1002,7 +1020,7 @@ void orc_render_pt(const OrcScene* sc, const LmcuRenderParams* p, double* film, 
                     const V3 fs = light_eval(&sc->lights[hit.light], &hit, woL);
                     double mis_w = 1.0;
                     if (mode != LMCU_SAMPLING_NAIVE && samplable_by_nee) {
-                        const double pdf_bsdf = mat_pdf(mat, &sp, wi, wo, 1);
+                        const double pdf_bsdf = mat ? mat_pdf(mat, &sp, wi, wo, 1) : camera_pdf_direction(sc, wo);
                         const double pdf_light = pdf_direct(sc, &sp, &hit, woL);
                         mis_w = balance_heuristic(pdf_bsdf, pdf_light);
                     }
@@ -1023,8 +1041,8 @@ void orc_render_pt(const OrcScene* sc, const LmcuRenderParams* p, double* film, 
             }
         }
     }
-    if (p->rescale) {                                                                    /* :307-309 */
-        const double s = 1.0 / (double)spp;
+    if (p->rescale) {                                                                    /* :307-312 */
+        const double s = image ? (double)(w * h) / (double)total : 1.0 / (double)spp;
         for (size_t i = 0; i < (size_t)w * h * 3; i++) film[i] *= s;
     }
 }

@@ -235,10 +235,14 @@ int lmref_render(void* s, const char* renderer_key, const LmcuRenderParams* p, d
         Json prop{
             {"scene", rs->scene_loc}, {"output", film->loc()},
             {"spp", (long long)p->spp}, {"max_verts", p->max_verts}, {"seed", p->seed},
-            {"scheduler", "sample"}, {"sampling_mode", std::string(modes[p->sampling_mode])},   // a bare const char* would hit lm's pointer serializer
+            {"scheduler", std::string(p->scheduler == LMCU_SCHED_TIME ? "time" : "sample")},
+            {"primary_ray_sampling_mode", std::string(p->primary_ray_sampling_mode == LMCU_PRIMARY_IMAGE ? "image" : "pixel")},
+            {"num_samples", (long long)p->num_samples}, {"render_time", p->render_time},
+            {"sampling_mode", std::string(modes[p->sampling_mode])},   // a bare const char* would hit lm's pointer serializer
             {"bg_color", vec3(p->bg_color)}, {"use_constant_color", bool(p->use_constant_color)},
             {"visualize_normal", bool(p->visualize_normal)} };
         if (p->has_color) prop["color"] = vec3(p->color);
+        if (p->samples_per_iter > 0) prop["samples_per_iter"] = (long long)p->samples_per_iter;
         if (const char* e = std::getenv("LMREF_EXTRA_PROPS")) {            // tests: extra JSON keys for plugin renderers
             const Json extra = Json::parse(e);
             for (auto it = extra.begin(); it != extra.end(); ++it) prop[it.key()] = it.value();

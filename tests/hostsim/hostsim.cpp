@@ -215,7 +215,9 @@ int hostsim_pt(void* p, const LmcuRenderParams* rp, float* film, long long* rays
     pp.width = rp->width; pp.height = rp->height; pp.max_verts = rp->max_verts; pp.sampling_mode = rp->sampling_mode;
     pp.seed = rp->seed; pp.tiled = (rp->width % 8 == 0 && rp->height % 4 == 0) ? 1u : 0u;
     pp.sample_offset = (uint64_t)rp->sample_offset;
-    pp.total_paths = (uint64_t)rp->width * rp->height * (uint64_t)rp->spp;
+    const bool image = rp->primary_ray_sampling_mode == LMCU_PRIMARY_IMAGE;
+    pp.image_mode = image ? 1u : 0u;
+    pp.total_paths = image ? (uint64_t)rp->num_samples : (uint64_t)rp->width * rp->height * (uint64_t)rp->spp;
     pp.capacity = 1;
     const size_t npix = (size_t)rp->width * rp->height;
     std::vector<double> acc(npix * 3, 0.0);
@@ -224,7 +226,14 @@ int hostsim_pt(void* p, const LmcuRenderParams* rp, float* film, long long* rays
     uint2 stack[kStackSize];
     long long rays = 0;
     for (uint64_t g = 0; g < pp.total_paths; g++) {
-        pt_generate_body(d, pp, g, q, 0);
+        const GenOut go = pt_generate_body(d, pp, g, q, 0);
+        if (go.shadow) {        // image mode: NEE connection of the camera vertex
+            HitD hs;
+            if (s.fp32) pt_trace<true, false, TriF32>(d, go.sh_o, go.sh_d, hs, stack, nullptr); else pt_trace<true, false, TriF64>(d, go.sh_o, go.sh_d, hs, stack, nullptr);
+            rays++;
+            const uint32_t px = f2u(go.sh_c.w);
+            if (hs.tri < 0) { acc[px * 3 + 0] += go.sh_c.x; acc[px * 3 + 1] += go.sh_c.y; acc[px * 3 + 2] += go.sh_c.z; }
+        }
         while (true) {
             HitD h;
             if (s.fp32) pt_trace<false, false, TriF32>(d, ro, rd, h, stack, nullptr); else pt_trace<false, false, TriF64>(d, ro, rd, h, stack, nullptr);
@@ -243,7 +252,7 @@ int hostsim_pt(void* p, const LmcuRenderParams* rp, float* film, long long* rays
             ro = o.o; rd = o.d; tp = o.thr_pix; aux = o.aux; info = o.info;
         }
     }
-    const double sc = rp->rescale ? 1.0 / (double)rp->spp : 1.0;
+    const double sc = !rp->rescale ? 1.0 : image ? (double)npix / (double)rp->num_samples : 1.0 / (double)rp->spp;
     for (size_t i = 0; i < npix * 3; i++) film[i] = (float)(acc[i] * sc);
     if (rays_out) *rays_out = rays;
     return 0;

@@ -232,6 +232,67 @@ def test_g3_pt_point_and_directional_lights(reference):
     rs.close(); sc.close()
 
 
+def test_g3_pt_image_mode_vs_reference(reference):
+    """primary_ray_sampling_mode=image + scheduler::spi::sample: same number of samples over the whole film."""
+    sb = scenes.cornell_spheres(32)
+    sc, rs = lmcu.Scene(sb), reference.RefScene(sb)
+    w, h, spp = 256, 144, 128
+    p = abi.render_params(w, h, max_verts=20, primary_ray_sampling_mode=abi.PRIMARY_IMAGE, num_samples=w * h * spp)
+    fr, _, pr = rs.render("pt", p)
+    fg, st = sc.render("pt", p)
+    assert pr == st["processed"] == st["paths"] == w * h * spp
+    assert_pt_parity(fr, fg, spp, rel_mean=0.01)
+    # image mode and pixel mode estimate the same image
+    fp, _ = sc.render("pt", abi.render_params(w, h, spp=spp, max_verts=20))
+    assert_pt_parity(fp, fg, spp, rel_mean=0.01)
+    # sample split over image-mode sample indices is additive and seed-stable
+    half = w * h * spp // 2
+    pa = abi.render_params(w, h, max_verts=20, primary_ray_sampling_mode=abi.PRIMARY_IMAGE, num_samples=half, rescale=0)
+    pb = abi.render_params(w, h, max_verts=20, primary_ray_sampling_mode=abi.PRIMARY_IMAGE, num_samples=half, rescale=0, sample_offset=half)
+    fa, _ = sc.render("pt", pa)
+    fb, _ = sc.render("pt", pb)
+    assert np.allclose((fa + fb) * (w * h / (2.0 * half)), fg, rtol=2e-3, atol=2e-4)
+    rs.close(); sc.close()
+
+
+@pytest.mark.parametrize("image", [False, True])
+def test_pt_time_schedulers(reference, image):
+    """scheduler::spp::time / scheduler::spi::time (src/scheduler.cpp:75-103,162-187): whole passes until render_time
+    has elapsed; `processed` reports what was rendered and the film is scaled by it.  Not deterministic => checked
+    by its contract and statistically against a fixed-spp reference image."""
+    import time
+    sb = scenes.cornell_spheres(16)
+    sc, rs = lmcu.Scene(sb), reference.RefScene(sb)
+    w, h = 160, 90
+    sc.render("pt", abi.render_params(w, h, spp=4))                        # allocate the pools outside the budget
+    kw = dict(primary_ray_sampling_mode=abi.PRIMARY_IMAGE, samples_per_iter=5000) if image else {}
+    budget = 0.12
+    p = abi.render_params(w, h, max_verts=12, scheduler=abi.SCHED_TIME, render_time=budget, **kw)
+    t0 = time.perf_counter()
+    fg, st = sc.render("pt", p)
+    wall = time.perf_counter() - t0
+    assert budget <= wall < 1.0
+    assert st["processed"] >= 1 and st["paths"] == st["processed"] * (1 if image else w * h)
+    if image:
+        assert st["processed"] % 5000 == 0
+    spp_equiv = st["paths"] / (w * h)
+    assert spp_equiv > 256                                                 # a B200 renders far more than that in 0.12 s
+    # the passes walk consecutive sample indices: the result is the fixed-count render of the same `processed`
+    # (same counter-RNG streams; fp32 summation order aside)
+    kf = dict(kw, num_samples=st["processed"]) if image else dict(spp=st["processed"])
+    kf.pop("samples_per_iter", None)
+    ff, _ = sc.render("pt", abi.render_params(w, h, max_verts=12, **kf))
+    assert np.allclose(ff, fg, rtol=2e-3, atol=2e-4)
+    # against the reference: its 1024-spp image (the block z-test assumes comparable noise in both images; a
+    # 256-spp reference against a ~10 000-spp render trips it on the skew of the reference's own noise)
+    fr, _, _ = rs.render("pt", abi.render_params(w, h, spp=1024, max_verts=12))
+    assert_pt_parity(fr, fg, 1024, rel_mean=0.01)
+    # render_time = 0: exactly one pass (the reference checks the clock after each pass)
+    fz, sz = sc.render("pt", abi.render_params(w, h, max_verts=12, scheduler=abi.SCHED_TIME, render_time=0.0, **kw))
+    assert sz["processed"] >= 1 and np.isfinite(fz).all() and fz.mean() > 0
+    rs.close(); sc.close()
+
+
 def test_sample_split_is_additive():
     """Sample split (multi-GPU partition): two half renders with disjoint sample offsets sum to the full render."""
     sb = scenes.cornell_spheres(16)

@@ -136,3 +136,25 @@ def test_renderer_pt_cuda_point_and_directional_probed(plugin):
     fc, _, _ = rs.render("renderer::pt_cuda", p)
     assert_pt_parity(fr, fc, 128, rel_mean=0.01)
     rs.close()
+
+
+def test_renderer_pt_cuda_schedulers_and_image_mode(plugin):
+    """The plugin honours renderer::pt's scheduler keys: scheduler=sample|time, primary_ray_sampling_mode=pixel|image,
+    spp / num_samples / render_time / samples_per_iter (renderer_pt.cpp:63-76)."""
+    sb = scenes.cornell_spheres(16)
+    rs = plugin.RefScene(sb)
+    w, h, spp = 128, 72, 1024
+    fr, _, _ = rs.render("pt", abi.render_params(w, h, spp=spp, max_verts=10))
+    pi = abi.render_params(w, h, max_verts=10, primary_ray_sampling_mode=abi.PRIMARY_IMAGE, num_samples=w * h * spp)
+    fi, _, proc = rs.render("renderer::pt_cuda", pi)
+    assert proc == w * h * spp
+    assert_pt_parity(fr, fi, spp, rel_mean=0.01)
+    pt = abi.render_params(w, h, max_verts=10, scheduler=abi.SCHED_TIME, render_time=0.1)
+    ft, elapsed, proc = rs.render("renderer::pt_cuda", pt)
+    assert proc >= spp and elapsed >= 0.09
+    assert_pt_parity(fr, ft, spp, rel_mean=0.01)
+    pti = abi.render_params(w, h, max_verts=10, scheduler=abi.SCHED_TIME, render_time=0.1, primary_ray_sampling_mode=abi.PRIMARY_IMAGE)
+    fti, _, proc = rs.render("renderer::pt_cuda", pti)
+    assert proc % 100000 == 0 and proc >= w * h * spp
+    assert_pt_parity(fr, fti, spp, rel_mean=0.01)
+    rs.close()

@@ -110,3 +110,24 @@ def test_point_and_directional_lights(reference, sim):
     p = abi.render_params(64, 36, spp=4, max_verts=8, sampling_mode=abi.SAMPLING_NAIVE)
     assert ss.render("pt", p).max() == 0.0          # delta lights are invisible to BSDF sampling
     rs.close()
+
+
+@pytest.mark.parametrize("scene,mode", [("spheres", abi.SAMPLING_MIS), ("spheres", abi.SAMPLING_NEE), ("spheres", abi.SAMPLING_NAIVE),
+                                        ("delta", abi.SAMPLING_MIS), ("env", abi.SAMPLING_MIS)])
+def test_pt_image_mode_statistics(reference, sim, tmp_path, scene, mode):
+    """primary_ray_sampling_mode=image: raster positions drawn over the whole film, NEE from the camera vertex splatted
+    at the light's own raster position, film scaled by w*h/num_samples (renderer_pt.cpp:104-106,126-157,310-312);
+    equal sample counts, statistical gate G3."""
+    if scene == "spheres":
+        sb = scenes.cornell_spheres(8)
+    elif scene == "delta":
+        sb = scenes.delta_lights_scene(2, 12)
+    else:
+        sb = scenes.instanced_spheres(grid=2, num_theta=12, env=scenes.env_light(str(tmp_path / "env.hdr"), w=64, h=32, rot=30.0, scale=1.5))
+    rs, ss = reference.RefScene(sb), sim.SimScene(sb)
+    n = 96 * 54 * 96
+    p = abi.render_params(96, 54, max_verts=12, sampling_mode=mode, primary_ray_sampling_mode=abi.PRIMARY_IMAGE, num_samples=n)
+    fr, _, processed = rs.render("pt", p)
+    assert processed == n
+    assert_pt_parity(fr, ss.render("pt", p), 96, rel_mean=0.02)
+    rs.close()

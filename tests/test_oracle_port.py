@@ -111,6 +111,20 @@ def test_port_pt_bit_exact_vs_reference(reference, port, scene_expr, mode):
     ps.close()
 
 
+@pytest.mark.parametrize("scene_expr,mode", [("scenes.cornell_spheres(8)", 2), ("scenes.cornell_spheres(8)", 1), ("scenes.cornell_spheres(8)", 0),
+                                             (ENV_SCENE, 2), ("scenes.delta_lights_scene(2, 10)", 2)])
+def test_port_pt_image_mode_bit_exact_vs_reference(reference, port, scene_expr, mode):
+    """primary_ray_sampling_mode=image + scheduler::spi::sample (renderer_pt.cpp:104-106,126-157,310-312,
+    scheduler.cpp:131-141), including the NEE connection of the camera vertex for every light type."""
+    params_expr = ("abi.render_params(40, 24, max_verts=12, seed=5, sampling_mode=%d, primary_ray_sampling_mode=abi.PRIMARY_IMAGE, "
+                   "num_samples=3000)" % mode)
+    fr = _ref_single_thread(scene_expr, params_expr)
+    ps = port.PortScene(eval(scene_expr))
+    fp = ps.render("pt", eval(params_expr), num_threads=1)
+    assert fr.max() > 0 and np.abs(fr - fp).max() <= 1e-12 * max(1.0, fr.max())
+    ps.close()
+
+
 def test_port_vs_reference_accel(reference, port):
     sb = scenes.cornell_spheres(16)
     rs, ps = reference.RefScene(sb), port.PortScene(sb)
