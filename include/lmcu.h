@@ -62,7 +62,9 @@ typedef struct LmcuHit {
  *   primitives  <- Scene::traverse_primitive_nodes (include/lm/scene.h:163-177): one entry per
  *                  primitive node that has a mesh, with its GLOBAL transform (instance groups are
  *                  flattened, src/scene.cpp:216-230), in traversal order
- *   materials   <- material::{diffuse,glossy,glass,mirror} parameters
+ *   materials   <- material::{diffuse,glossy,glass,mirror,mask} parameters, material::mixture_wavefrontobj and the
+ *                  constant-weight mixtures as lists of entries
+ *   textures    <- texture::bitmap texels (src/texture/texture_bitmap.cpp:41-96)
  *   lights      <- Scene light table order (src/scene.cpp:281-286): area, envconst, env, point, directional
  *   camera      <- camera::pinhole (src/camera/camera_pinhole.cpp:66-97)
  * ------------------------------------------------------------------------------------------- */
@@ -70,6 +72,7 @@ typedef struct LmcuMesh {
     int32_t num_faces;
     const double* p;                         /* [num_faces][3][3] local-space positions */
     const double* n;                         /* [num_faces][3][3] vertex normals, or NULL (use geometric normal) */
+    const double* t;                         /* [num_faces][3][2] texture coordinates (Mesh::Point::t), or NULL (0,0) */
 } LmcuMesh;
 
 typedef struct LmcuPrimitive {
@@ -80,14 +83,34 @@ typedef struct LmcuPrimitive {
     double M[16];                            /* global transform, column-major */
 } LmcuPrimitive;
 
-enum { LMCU_MAT_DIFFUSE = 0, LMCU_MAT_GLOSSY = 1, LMCU_MAT_GLASS = 2, LMCU_MAT_MIRROR = 3 };
+enum { LMCU_MAT_DIFFUSE = 0, LMCU_MAT_GLOSSY = 1, LMCU_MAT_GLASS = 2, LMCU_MAT_MIRROR = 3,
+       LMCU_MAT_MASK = 4,             /* material::mask (src/material/material_mask.cpp): pass-through delta lobe */
+       LMCU_MAT_MIXTURE_OBJ = 5,      /* material::mixture_wavefrontobj (src/model/model_wavefrontobj.cpp:339-515):
+                                         diffuse(Kd | mapKd) + glossy(Ks, ax, ay) marginalised, alpha mask from mapKd */
+       LMCU_MAT_MIXTURE_RR = 6,       /* material::constant_weight_mixture_rr (src/material/material_mixture.cpp:25-107) */
+       LMCU_MAT_MIXTURE_MARGINALIZED = 7 };  /* material::constant_weight_mixture_marginalized (:124-258) */
+
+/* texture::bitmap (src/texture/texture_bitmap.cpp:41-96): nearest-texel lookup at (u - floor u, v - floor v) */
+typedef struct LmcuTexture {
+    int32_t w, h;
+    int32_t c;                               /* channels per texel: 3 (rgb) or 4 (rgba: has_alpha()) */
+    int32_t pad_;
+    const float* data;                       /* [h][w][c] in the row order texture::bitmap holds (Texture::buffer()) */
+    const char* path;                        /* image file (only the reference harness reads files) */
+} LmcuTexture;
 
 typedef struct LmcuMaterial {
     int32_t type;
-    int32_t pad_;
-    double color[3];                         /* diffuse: Kd; glossy: Ks */
-    double ax, ay;                           /* glossy: anisotropic GGX roughness */
+    int32_t map_kd;                          /* diffuse, mixture_obj: 1 + index into textures[] of mapKd, 0 = none (use color) */
+    double color[3];                         /* diffuse, mixture_obj: Kd; glossy: Ks */
+    double ax, ay;                           /* glossy, mixture_obj: anisotropic GGX roughness */
     double Ni;                               /* glass: index of refraction */
+    double Ks[3];                            /* mixture_obj: specular reflectance of the glossy lobe */
+    int32_t alpha_mask;                      /* mixture_obj: 1 = mapKd's alpha channel masks the surface (!no_alpha_mask and
+                                                the texture has_alpha(), model_wavefrontobj.cpp:405-412) */
+    int32_t num_entries;                     /* constant-weight mixtures: number of (material, weight) entries */
+    const int32_t* entry_material;           /* ... index into materials[] of each entry (diffuse | glossy | mirror | mask) */
+    const double* entry_weight;              /* ... weight of each entry */
 } LmcuMaterial;
 
 enum { LMCU_LIGHT_AREA = 0, LMCU_LIGHT_ENVCONST = 1, LMCU_LIGHT_ENV = 2,
@@ -121,11 +144,14 @@ typedef struct LmcuSceneDesc {
     int32_t num_primitives;
     int32_t num_materials;
     int32_t num_lights;
+    int32_t num_textures;
+    int32_t pad_;
     const LmcuMesh* meshes;
     const LmcuPrimitive* primitives;
     const LmcuMaterial* materials;
     const LmcuLight* lights;
     const LmcuCamera* camera;                /* may be NULL for accel-only use */
+    const LmcuTexture* textures;             /* may be NULL when num_textures == 0 */
 } LmcuSceneDesc;
 
 /* ---------------------------------------------------------------------------------------------

@@ -325,9 +325,12 @@ LMCU_HD F3 normal_transform(const double* NM, double x, double y, double z) {
 // n2.w = material index, n3.w = light index or -1 (int bit patterns): shading needs no PrimDev lookup
 struct alignas(16) TriShade { float4 n1, n2, n3; };
 
+// per-vertex texture coordinates (Mesh::Point::t), leaf order; only built when a material reads a texture
+struct alignas(8) TriUV { float2 t1, t2, t3; };
+
 LMCU_HD void emit_body(uint32_t k, const uint32_t* tri_order, const PrimDev* prims, int num_prims,
                        const double* wp, const double* mesh_p, const double* mesh_n,
-                       TriF32* t32, TriF64* t64, TriShade* shade) {
+                       TriF32* t32, TriF64* t64, TriShade* shade, const float* mesh_t = nullptr, TriUV* uv = nullptr) {
     const uint32_t g = tri_order[k];
     const uint32_t pi = find_prim(prims, num_prims, g);
     const PrimDev& pr = prims[pi];
@@ -360,6 +363,12 @@ LMCU_HD void emit_body(uint32_t k, const uint32_t* tri_order, const PrimDev* pri
     shade[k].n1 = make_float4(n[0].x, n[0].y, n[0].z, pr.det_sign);
     shade[k].n2 = make_float4(n[1].x, n[1].y, n[1].z, u2f((uint32_t)pr.material));
     shade[k].n3 = make_float4(n[2].x, n[2].y, n[2].z, u2f((uint32_t)pr.light));
+    if (uv) {
+        const float* t = mesh_t + (size_t)(pr.mesh_face_offset + face) * 6;
+        TriUV o;
+        o.t1.x = t[0]; o.t1.y = t[1]; o.t2.x = t[2]; o.t2.y = t[3]; o.t3.x = t[4]; o.t3.y = t[5];
+        uv[k] = o;
+    }
 }
 
 }  // namespace lmcu

@@ -75,9 +75,8 @@ LMCU_HD bool tri_intersect(const RayD& r, D3 p1, D3 p2, D3 p3, double tl, double
     const D3 q = dcross(tv, e1);
     const double d = ddot(e1, p);
     const double ad = fabs(d);
-    const double s = copysign(1.0, d);
-    const double u = mulrn(ddot(tv, p), s);
-    const double v = mulrn(ddot(r.d, q), s);
+    const double u = mul_sign_of(ddot(tv, p), d);
+    const double v = mul_sign_of(ddot(r.d, q), d);
     if (ad < 1e-8 || u < 0.0 || v < 0.0 || addrn(u, v) > ad) {
         return false;
     }
@@ -115,10 +114,10 @@ struct RayF {
     uint32_t octinv4;            // (7 - octant) replicated in 4 bytes
 };
 
-LMCU_HD RayF make_rayf(const RayD& r) {
+// FP32 view of a ray whose components are given as floats (the pt queues hold float rays: no FP64 round trip)
+LMCU_HD RayF make_rayf_f(float ox, float oy, float oz, float dx, float dy, float dz) {
     RayF f;
-    f.ox = (float)r.o.x; f.oy = (float)r.o.y; f.oz = (float)r.o.z;
-    float dx = (float)r.d.x, dy = (float)r.d.y, dz = (float)r.d.z;
+    f.ox = ox; f.oy = oy; f.oz = oz;
     const float tiny = 1e-20f;
     if (fabsf(dx) < tiny) dx = copysignf(tiny, dx);
     if (fabsf(dy) < tiny) dy = copysignf(tiny, dy);
@@ -128,6 +127,10 @@ LMCU_HD RayF make_rayf(const RayD& r) {
     const uint32_t oct = (dx < 0.f ? 4u : 0u) | (dy < 0.f ? 2u : 0u) | (dz < 0.f ? 1u : 0u);
     f.octinv4 = (7u - oct) * 0x01010101u;
     return f;
+}
+
+LMCU_HD RayF make_rayf(const RayD& r) {
+    return make_rayf_f((float)r.o.x, (float)r.o.y, (float)r.o.z, (float)r.d.x, (float)r.d.y, (float)r.d.z);
 }
 
 // Byte j of `w` as the float 32768 + byte, built with ONE byte permute and no integer->float

@@ -92,6 +92,16 @@ LMCU_HD double sqrtrn(double a) {
 #endif
 }
 
+// x * copysign(1.0, d) (accel_sahbvh.cpp:66-68: u *= sign(det)): multiplying by +-1.0 is exact, so flipping the sign bit
+// with one integer op gives the same bits for every finite, zero or infinite x.
+LMCU_HD double mul_sign_of(double x, double d) {
+#if defined(__CUDA_ARCH__)
+    return __hiloint2double(__double2hiint(x) ^ (__double2hiint(d) & (int)0x80000000), __double2loint(x));
+#else
+    return x * copysign(1.0, d);
+#endif
+}
+
 // glm::dot(vec3) = (x*x' + y*y') + z*z'; glm::cross as in func_geometric.inl
 struct D3 { double x, y, z; };
 LMCU_HD D3 d3(double x, double y, double z) { D3 r; r.x = x; r.y = y; r.z = z; return r; }

@@ -19,6 +19,10 @@ struct DevScene {
     const EmitTri* emit;
     const float* cdf;
     const float4* env_tex;
+    const TriUV* uv;            // per-triangle texture coordinates in leaf order; null when no material reads a texture
+    const TextureDev* textures;
+    const float4* texels;
+    const MixEntry* mix;
     int32_t num_prims, num_lights, env_light;
     int32_t fetch_threshold;    // trace.cuh: idle lanes tolerated per iteration before the warp re-fetches
     uint32_t num_tris, pad2_;
@@ -32,6 +36,7 @@ template <> LMCU_HD const TriF64* scene_tris<TriF64>(const DevScene& s) { return
 // -- surface point at a hit (src/scene.cpp:333-344, src/mesh/mesh_raw.cpp:87-97), FP32 ------------------
 struct SurfPoint {
     F3 p, n, gn;
+    float tu, tv;      // texture coordinates (0,0 without a uv buffer)
     int32_t prim;      // primitive ordinal
     int32_t face;
     int32_t material;  // index into DevScene::mats
@@ -62,7 +67,185 @@ LMCU_HD SurfPoint surface_point(const DevScene& s, uint32_t tri, float u, float 
     sp.n = normalize(f3(n1.x, n1.y, n1.z) * w + f3(n2.x, n2.y, n2.z) * u + f3(n3.x, n3.y, n3.z) * v);
     sp.gn = normalize(cross(p2 - p1, p3 - p1)) * n1.w;
     sp.material = (int32_t)f2u(n2.w); sp.light = (int32_t)f2u(n3.w);
+    sp.tu = 0.f; sp.tv = 0.f;
+    if (s.uv) {                                            // math::mix_barycentric of Mesh::Point::t (mesh_raw.cpp:94)
+        const TriUV t = s.uv[tri];
+        sp.tu = t.t1.x * w + t.t2.x * u + t.t3.x * v;
+        sp.tv = t.t1.y * w + t.t2.y * u + t.t3.y * v;
+    }
     return sp;
+}
+
+// -- composite materials: mapKd textures, material::mask, mixture_wavefrontobj, constant-weight mixtures ---------------
+// A plain lobe (diffuse | glossy | mirror | mask | glass) with its texture resolved at the surface point
+LMCU_HD MaterialDev resolve_lobe(const DevScene& s, const MaterialDev& m, const SurfPoint& sp) {
+    MaterialDev o = m;
+    if (m.type == MAT_DIFFUSE && m.tex_kd >= 0) {          // material_diffuse.cpp:70,80,90: mapKd has priority over Kd
+        const float4 c = tex_fetch(s.textures[m.tex_kd], s.texels, sp.tu, sp.tv);
+        o.r = c.x; o.g = c.y; o.b = c.z;
+    }
+    return o;
+}
+
+// The component picked at a vertex (path::sample_component, include/lm/path.h:193-200) in a form eval / pdf / sample
+// below can iterate: `n` lobes, each with a weight (multiplies its BSDF) and a selection probability.
+struct VComp {
+    int32_t kind;        // 0: the material itself (one plain lobe), 1: the diffuse + glossy pair of mixture_obj,
+                         // 2: MixEntry range [first, first + n), 3: the pass-through component of mixture_obj
+    int32_t first, n;
+    bool marginal;       // a sampled direction is weighted by (sum of all lobes' f) / (marginal pdf)
+    bool specular;
+    float cweight;       // 1 / p(component), multiplies the throughput (renderer_pt.cpp:292-293)
+    float alpha;         // mixture_obj: scales eval
+    float wsel;          // mixture_obj: probability of sampling the diffuse lobe
+    MaterialDev l0, l1;  // kind 0: l0; kind 1: diffuse (Kd resolved), glossy
+};
+
+LMCU_HD bool mat_is_plain(const MaterialDev& m) { return m.type <= MAT_MASK && m.tex_kd < 0; }
+
+// Material::sample_component.  uc0 drives the choice (ComponentSampleU::uc[0]).
+LMCU_HD VComp pick_component(const DevScene& s, const MaterialDev& mat, const SurfPoint& sp, float uc0) {
+    VComp c;
+    c.kind = 0; c.first = 0; c.n = 1; c.marginal = false; c.cweight = 1.f; c.alpha = 1.f; c.wsel = 1.f;
+    if (mat.type <= MAT_MASK) {
+        c.l0 = resolve_lobe(s, mat, sp);
+        c.specular = mat_is_specular(mat.type);
+    } else if (mat.type == MAT_MIXTURE_OBJ) {              // model_wavefrontobj.cpp:417-424
+        F3 kd = f3(mat.r, mat.g, mat.b);
+        float alpha = 1.f;
+        if (mat.tex_kd >= 0) {
+            const float4 t = tex_fetch(s.textures[mat.tex_kd], s.texels, sp.tu, sp.tv);
+            kd = f3(t.x, t.y, t.z);
+            if (mat.alpha_mask) alpha = t.w;
+        }
+        if (uc0 < alpha) {
+            c.kind = 1; c.n = 2; c.marginal = true; c.specular = false;
+            c.cweight = 1.0f / alpha; c.alpha = alpha;
+            c.l0 = mat; c.l0.type = MAT_DIFFUSE; c.l0.r = kd.x; c.l0.g = kd.y; c.l0.b = kd.z;
+            c.l1 = mat; c.l1.type = MAT_GLOSSY; c.l1.r = mat.ks_r; c.l1.g = mat.ks_g; c.l1.b = mat.ks_b;
+            const float wd = max3(kd), wg = fmaxf(mat.ks_r, fmaxf(mat.ks_g, mat.ks_b));       // :431-439
+            c.wsel = (wd == 0.f && wg == 0.f) ? 1.f : wd / (wd + wg);
+        } else {
+            c.kind = 3; c.n = 0; c.specular = true;
+            c.cweight = 1.0f / (1.0f - alpha);
+        }
+    } else if (mat.type == MAT_MIXTURE_RR) {               // material_mixture.cpp:61-65: one entry is the component
+        float acc = 0.f;
+        int k = 0;
+        for (; k < mat.num_entries - 1; k++) {
+            acc += s.mix[mat.entry_offset + k].prob;
+            if (uc0 < acc) break;
+        }
+        const MixEntry e = s.mix[mat.entry_offset + k];
+        c.kind = 2; c.first = mat.entry_offset + k; c.n = 1;
+        c.cweight = 1.0f / e.prob;
+        c.specular = mat_is_specular(s.mats[e.material].type);
+    } else {                                               // marginalized, :191-195: group 0 or one specular entry
+        const int n0 = mat.num_group0;
+        float acc = n0 > 0 ? s.mix[mat.entry_offset].group_prob : 0.f;
+        if (n0 > 0 && (uc0 < acc || n0 == mat.num_entries)) {
+            c.kind = 2; c.first = mat.entry_offset; c.n = n0; c.marginal = true; c.specular = false;
+            c.cweight = 1.0f / s.mix[mat.entry_offset].group_prob;
+        } else {
+            int k = n0;
+            for (; k < mat.num_entries - 1; k++) {
+                acc += s.mix[mat.entry_offset + k].group_prob;
+                if (uc0 < acc) break;
+            }
+            c.kind = 2; c.first = mat.entry_offset + k; c.n = 1; c.specular = true;
+            c.cweight = 1.0f / s.mix[mat.entry_offset + k].group_prob;
+        }
+    }
+    return c;
+}
+
+// lobe k of a component: the plain material, its weight and its selection probability
+LMCU_HD MaterialDev comp_lobe(const DevScene& s, const VComp& c, const SurfPoint& sp, int k, float& w, float& sel) {
+    if (c.kind == 2) {
+        const MixEntry e = s.mix[c.first + k];
+        w = e.weight; sel = c.marginal ? e.prob : 1.f;
+        return resolve_lobe(s, s.mats[e.material], sp);
+    }
+    if (c.kind == 1) {
+        w = c.alpha; sel = k == 0 ? c.wsel : 1.0f - c.wsel;
+        return k == 0 ? c.l0 : c.l1;
+    }
+    w = 1.f; sel = 1.f;
+    return c.l0;
+}
+
+// Material::eval(comp, eval_delta = true) and Material::pdf_direction(comp, eval_delta = true)
+LMCU_HD F3 comp_eval(const DevScene& s, const VComp& c, const SurfPoint& sp, F3 wi, F3 wo) {
+    if (c.kind == 0) return mat_eval(c.l0, sp.n, wi, wo);
+    F3 f = f3s(0.f);
+    for (int k = 0; k < c.n; k++) {
+        float w, sel;
+        const MaterialDev m = comp_lobe(s, c, sp, k, w, sel);
+        f = f + mat_eval(m, sp.n, wi, wo) * w;
+    }
+    return f;
+}
+LMCU_HD float comp_pdf(const DevScene& s, const VComp& c, const SurfPoint& sp, F3 wi, F3 wo) {
+    if (c.kind == 0) return mat_pdf(c.l0, sp.n, wi, wo);
+    float p = 0.f;
+    for (int k = 0; k < c.n; k++) {
+        float w, sel;
+        const MaterialDev m = comp_lobe(s, c, sp, k, w, sel);
+        p += sel * mat_pdf(m, sp.n, wi, wo);
+    }
+    return p;
+}
+
+// Material::sample_direction(comp): ud0, ud1 = DirectionSampleU::ud, udc0 = udc[0] (lobe choice inside a marginal
+// group, model_wavefrontobj.cpp:441-468, material_mixture.cpp:201-224; Fresnel choice of glass)
+LMCU_HD BsdfSample comp_sample(const DevScene& s, const VComp& c, const SurfPoint& sp, F3 wi, float ud0, float ud1, float udc0) {
+    if (c.kind == 0) return mat_sample(c.l0, sp.n, sp.gn, wi, ud0, ud1, udc0);
+    BsdfSample bs;
+    if (c.kind == 3) {                                     // model_wavefrontobj.cpp:470-479: weight is Vec3(1), not f/p
+        bs.valid = true; bs.specular = true; bs.pdf = 0.f;
+        bs.wo = -wi;
+        bs.weight = f3s(sn_correction(sp.n, sp.gn, wi, bs.wo));
+        return bs;
+    }
+    int k = 0;
+    float w = 1.f, sel = 1.f, acc = 0.f;
+    MaterialDev m = comp_lobe(s, c, sp, 0, w, sel);
+    if (c.marginal) {
+        for (; k < c.n - 1; k++) {
+            acc += sel;
+            if (udc0 < acc) break;
+            m = comp_lobe(s, c, sp, k + 1, w, sel);
+        }
+    }
+    bs = mat_sample(m, sp.n, sp.gn, wi, ud0, ud1, udc0);
+    if (!bs.valid) return bs;
+    if (c.marginal) {
+        const F3 f = comp_eval(s, c, sp, wi, bs.wo);
+        const float p = comp_pdf(s, c, sp, wi, bs.wo);
+        if (!(p > 0.f)) { bs.valid = false; return bs; }   // the reference divides 0 by 0 here; the path carries nothing
+        bs.weight = f * (sn_correction(sp.n, sp.gn, wi, bs.wo) / p);
+        bs.pdf = p;
+    } else {
+        bs.weight = bs.weight * w;
+    }
+    return bs;
+}
+
+// Material::reflectance (raycast shading): mixture_obj shows its diffuse lobe (model_wavefrontobj.cpp:482-485), the
+// constant-weight mixtures the weighted sum (material_mixture.cpp:80-86,226-234)
+LMCU_HD F3 surface_reflectance(const DevScene& s, const MaterialDev& mat, const SurfPoint& sp) {
+    if (mat.type <= MAT_MASK) return mat_reflectance(resolve_lobe(s, mat, sp));
+    if (mat.type == MAT_MIXTURE_OBJ) {
+        if (mat.tex_kd < 0) return f3(mat.r, mat.g, mat.b);
+        const float4 t = tex_fetch(s.textures[mat.tex_kd], s.texels, sp.tu, sp.tv);
+        return f3(t.x, t.y, t.z);
+    }
+    F3 sum = f3s(0.f);
+    for (int k = 0; k < mat.num_entries; k++) {
+        const MixEntry e = s.mix[mat.entry_offset + k];
+        sum = sum + mat_reflectance(resolve_lobe(s, s.mats[e.material], sp)) * e.weight;
+    }
+    return sum;
 }
 
 // Radiance of the environment light seen along direction d (scene -> sky): envconst Le or the image lookup
@@ -107,7 +290,7 @@ LMCU_HD void raycast_pixel(const DevScene& s, const RaycastParams& p, int x, int
         if (p.visualize_normal) {
             c = f3(fabsf(sp.n.x), fabsf(sp.n.y), fabsf(sp.n.z));
         } else {
-            c = p.has_color ? f3(p.color[0], p.color[1], p.color[2]) : mat_reflectance(s.mats[sp.material]);
+            c = p.has_color ? f3(p.color[0], p.color[1], p.color[2]) : surface_reflectance(s, s.mats[sp.material], sp);
             if (!p.use_constant_color) {
                 const F3 d = f3((float)r.d.x, (float)r.d.y, (float)r.d.z);
                 c = c * (0.2f + 0.8f * fabsf(dot(sp.n, -d)));
@@ -373,6 +556,9 @@ struct ShadeOut {
 
 // One path vertex: everything the reference does between Scene::intersect returning `hit` and the next
 // Scene::intersect (renderer_pt.cpp:229-300 for the hit, then :127-209 of the next loop iteration).
+// COMPOSITE = the scene holds a textured or mixture material; the <false> instantiation (every BASELINE config) carries
+// none of that code or its registers.
+template <bool COMPOSITE>
 LMCU_HD ShadeOut pt_shade_body(const DevScene& s, const PtParams& p, float4 ro, float4 rd, float4 thr_pix, float4 aux,
                                uint2 info, float4 hit) {
     ShadeOut out;
@@ -432,7 +618,17 @@ LMCU_HD ShadeOut pt_shade_body(const DevScene& s, const PtParams& p, float4 ro, 
     num_verts++;
     if ((int)num_verts >= p.max_verts) return out;                          // loop bound, renderer_pt.cpp:123
 
-    const bool specular = mat_is_specular(mat.type);
+    // component of the material at this vertex (renderer_pt.cpp:292-293; its weight multiplies the throughput).  Plain
+    // single-lobe materials keep the direct calls; everything composite goes through VComp.
+    const bool plain = !COMPOSITE || mat_is_plain(mat);
+    VComp vc;
+    float udc0 = u0.w;
+    if (!plain) {
+        vc = pick_component(s, mat, sp, u0.w);
+        thr = thr * vc.cweight;
+        udc0 = rand4(p.seed, pixel, p.sample_offset + sample, num_verts * 4u + 3u).x;
+    }
+    const bool specular = plain ? mat_is_specular(mat.type) : vc.specular;
     const bool nee = p.sampling_mode != 0 /*naive*/ && !specular;           // renderer_pt.cpp:127-140 (num_verts > 1 here)
 
     // next-event estimation (renderer_pt.cpp:142-192)
@@ -442,12 +638,15 @@ LMCU_HD ShadeOut pt_shade_body(const DevScene& s, const PtParams& p, float4 ro, 
         const float pl = ls.pl, tmax = ls.tmax;   // pdf_direct, projected SA, without the selection probability
         const bool delta_light = ls.delta;
         if (pl > 0.f) {
-            const F3 fs = mat_eval(mat, sp.n, wi, wo) * sn_correction(sp.n, sp.gn, wi, wo);
+            F3 fs;
+            float p_bsdf = 0.f;
+            if (plain) fs = mat_eval(mat, sp.n, wi, wo); else { fs = comp_eval(s, vc, sp, wi, wo); p_bsdf = comp_pdf(s, vc, sp, wi, wo); }
+            fs = fs * sn_correction(sp.n, sp.gn, wi, wo);
             if (!is_zero(fs)) {
                 float mis = 1.f;
                 if (p.sampling_mode == 2 && !delta_light) {
                     const float p_light = pl * inv_nl;
-                    const float p_bsdf = mat_pdf(mat, sp.n, wi, wo);
+                    if (plain) p_bsdf = mat_pdf(mat, sp.n, wi, wo);
                     mis = (p_light == 0.f && p_bsdf == 0.f) ? 0.f : p_light / (p_light + p_bsdf);   // math.h:697-702
                 }
                 const F3 C = thr * fs * Le * (mis / (pl * inv_nl));
@@ -460,7 +659,8 @@ LMCU_HD ShadeOut pt_shade_body(const DevScene& s, const PtParams& p, float4 ro, 
     }
 
     // direction sampling (renderer_pt.cpp:197-209) with the component picked at the hit (:292-293)
-    const BsdfSample bs = mat_sample(mat, sp.n, sp.gn, wi, u0.x, u0.y, u0.w);
+    BsdfSample bs;
+    if (plain) bs = mat_sample(mat, sp.n, sp.gn, wi, u0.x, u0.y, u0.w); else bs = comp_sample(s, vc, sp, wi, u0.x, u0.y, udc0);
     if (!bs.valid) return out;
     thr = thr * bs.weight;
     if (is_zero(thr)) return out;          // every later contribution is multiplied by zero

@@ -139,9 +139,10 @@ __global__ void k_collapse(CollapseCtx c, const CollapseItem* queue, uint32_t co
 }
 
 __global__ void k_emit(const uint32_t* tri_order, uint32_t nt, const PrimDev* prims, int num_prims, const double* wp,
-                       const double* mesh_p, const double* mesh_n, TriF32* t32, TriF64* t64, TriShade* shade) {
+                       const double* mesh_p, const double* mesh_n, TriF32* t32, TriF64* t64, TriShade* shade,
+                       const float* mesh_t, TriUV* uv) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < nt) emit_body(k, tri_order, prims, num_prims, wp, mesh_p, mesh_n, t32, t64, shade);
+    if (k < nt) emit_body(k, tri_order, prims, num_prims, wp, mesh_p, mesh_n, t32, t64, shade, mesh_t, uv);
 }
 
 // ================================================================================================
@@ -279,6 +280,7 @@ __device__ __forceinline__ void block_compact2(bool p0, bool p1, uint32_t* count
     __syncthreads();
 }
 
+template <bool COMPOSITE>
 __global__ void __launch_bounds__(256, LMCU_SHADE_MINB) k_pt_shade(DevScene s, PtParams p, PathQueue qin, PathQueue qout, ShadowQueue sq,
                                                   const float4* hits, float* film, PtCounters* ctr, int cur) {
     __shared__ uint32_t smem[34];
@@ -296,7 +298,7 @@ __global__ void __launch_bounds__(256, LMCU_SHADE_MINB) k_pt_shade(DevScene s, P
         ShadeOut o;
         o.alive = false; o.shadow = false;
         if (i < n) {
-            o = pt_shade_body(s, p, qin.ray_o[i], qin.ray_d[i], qin.thr_pix[i], qin.aux[i], qin.info[i], hits[i]);
+            o = pt_shade_body<COMPOSITE>(s, p, qin.ray_o[i], qin.ray_d[i], qin.thr_pix[i], qin.aux[i], qin.info[i], hits[i]);
             if (!is_zero(o.emit)) {
                 float* px = film + (size_t)f2u(qin.thr_pix[i].w) * 3;
                 atomicAdd(px + 0, o.emit.x); atomicAdd(px + 1, o.emit.y); atomicAdd(px + 2, o.emit.z);
@@ -320,10 +322,12 @@ struct BatchIO {                       // accel batches: LmcuRay in, LmcuHit out
     DevScene s;
     const LmcuRay* rays;
     LmcuHit* hits;
-    __device__ __forceinline__ bool load(uint32_t i, RayD& r) const {
+    __device__ __forceinline__ bool load(uint32_t i, RayD& r, RayF& f, float& tmin_dn, float& tmax_up) const {
         const double2* src = reinterpret_cast<const double2*>(rays + i);
         const double2 a = src[0], b = src[1], c = src[2], d = src[3];
         r.o = d3(a.x, a.y, b.x); r.d = d3(b.y, c.x, c.y); r.tmin = d.x; r.tmax = d.y;
+        f = make_rayf(r);
+        tmin_dn = f32_down(r.tmin); tmax_up = f32_up(r.tmax);
         return true;
     }
     __device__ __forceinline__ void store(uint32_t i, const RayD&, const HitD& h) const {
@@ -355,9 +359,11 @@ __global__ void __launch_bounds__(128, LMCU_MINB) k_intersect_q(DevScene s, cons
 struct ExtendIO {                      // pt extend: path queue in, float4 hit record out
     const float4* ray_o; const float4* ray_d;
     float4* hits;
-    __device__ __forceinline__ bool load(uint32_t i, RayD& r) const {
+    __device__ __forceinline__ bool load(uint32_t i, RayD& r, RayF& f, float& tmin_dn, float& tmax_up) const {
         const float4 o = ray_o[i], d = ray_d[i];
         r.o = d3(o.x, o.y, o.z); r.d = d3(d.x, d.y, d.z); r.tmin = o.w; r.tmax = d.w;
+        f = make_rayf_f(o.x, o.y, o.z, d.x, d.y, d.z);          // the queue holds float rays: exact in both views
+        tmin_dn = o.w; tmax_up = d.w;
         return true;
     }
     __device__ __forceinline__ void store(uint32_t i, const RayD&, const HitD& h) const {
@@ -376,9 +382,11 @@ __global__ void __launch_bounds__(128, LMCU_MINB) k_pt_extend_q(DevScene s, Path
 struct ShadowIO {                      // pt shadow: visible (include/lm/scene.h:343-364) => splat the NEE contribution
     const float4* ray_o; const float4* ray_d; const float4* contrib;
     float* film;
-    __device__ __forceinline__ bool load(uint32_t i, RayD& r) const {
+    __device__ __forceinline__ bool load(uint32_t i, RayD& r, RayF& f, float& tmin_dn, float& tmax_up) const {
         const float4 o = ray_o[i], d = ray_d[i];
         r.o = d3(o.x, o.y, o.z); r.d = d3(d.x, d.y, d.z); r.tmin = o.w; r.tmax = d.w;
+        f = make_rayf_f(o.x, o.y, o.z, d.x, d.y, d.z);          // the queue holds float rays: exact in both views
+        tmin_dn = o.w; tmax_up = d.w;
         return true;
     }
     __device__ __forceinline__ void store(uint32_t i, const RayD&, const HitD& h) const {
@@ -498,6 +506,10 @@ struct LmcuScene {
     DBuf<EmitTri> emit;
     DBuf<float> cdf;
     DBuf<float4> env_tex;
+    DBuf<float> mesh_t;                  // texture coordinates per mesh face (only when a material reads a texture)
+    DBuf<TextureDev> textures;
+    DBuf<float4> texels;
+    DBuf<MixEntry> mix;
     std::vector<PrimDev> h_prims;
     uint32_t nt = 0;
     int num_prims = 0, num_lights = 0, env_light = -1;
@@ -508,7 +520,9 @@ struct LmcuScene {
     DBuf<TriF32> t32;
     DBuf<TriF64> t64;
     DBuf<TriShade> shade;
+    DBuf<TriUV> uv;
     bool built = false, fp32 = false;
+    bool composite = false;              // a material is textured or a mixture: the shade kernel's <true> instantiation
     // scratch / outputs
     DBuf<unsigned long long> cursor;     // [0] work cursor, [1..2] counters, [3] rays
     DBuf<uint32_t> flags;                // [0] stack overflow
@@ -529,6 +543,7 @@ struct LmcuScene {
         DevScene d{};
         d.nodes = nodes.p; d.t32 = t32.p; d.t64 = t64.p; d.shade = shade.p; d.prims = prims.p; d.mats = mats.p;
         d.lights = lights.p; d.emit = emit.p; d.cdf = cdf.p; d.env_tex = env_tex.p;
+        d.uv = uv.p; d.textures = textures.p; d.texels = texels.p; d.mix = mix.p;
         d.num_prims = num_prims; d.num_lights = num_lights; d.env_light = env_light; d.fetch_threshold = fetch_threshold; d.num_tris = nt; d.cam = cam;
         return d;
     }
@@ -612,6 +627,8 @@ int lmcu_scene_upload(LmcuScene* s, const LmcuSceneDesc* d) {
     s->env_light = ps.env_light;
     s->cam = ps.cam;
     s->has_camera = ps.has_camera;
+    s->composite = false;
+    for (const MaterialDev& m : ps.mats) if (!mat_is_plain(m)) s->composite = true;
     CU(s->mats.alloc(ps.mats.size()));
     if (!ps.mats.empty()) CU(cudaMemcpy(s->mats.p, ps.mats.data(), ps.mats.size() * sizeof(MaterialDev), cudaMemcpyHostToDevice));
     CU(s->lights.alloc(ps.lights.size()));
@@ -622,6 +639,14 @@ int lmcu_scene_upload(LmcuScene* s, const LmcuSceneDesc* d) {
     if (!ps.cdf.empty()) CU(cudaMemcpy(s->cdf.p, ps.cdf.data(), ps.cdf.size() * sizeof(float), cudaMemcpyHostToDevice));
     CU(s->env_tex.alloc(ps.env_tex.size()));
     if (!ps.env_tex.empty()) CU(cudaMemcpy(s->env_tex.p, ps.env_tex.data(), ps.env_tex.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    CU(s->mesh_t.alloc(ps.mesh_t.size()));
+    if (!ps.mesh_t.empty()) CU(cudaMemcpy(s->mesh_t.p, ps.mesh_t.data(), ps.mesh_t.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CU(s->textures.alloc(ps.textures.size()));
+    if (!ps.textures.empty()) CU(cudaMemcpy(s->textures.p, ps.textures.data(), ps.textures.size() * sizeof(TextureDev), cudaMemcpyHostToDevice));
+    CU(s->texels.alloc(ps.texels.size()));
+    if (!ps.texels.empty()) CU(cudaMemcpy(s->texels.p, ps.texels.data(), ps.texels.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    CU(s->mix.alloc(ps.mix.size()));
+    if (!ps.mix.empty()) CU(cudaMemcpy(s->mix.p, ps.mix.data(), ps.mix.size() * sizeof(MixEntry), cudaMemcpyHostToDevice));
     CU(s->prims.alloc(ps.prims.size()));
     CU(cudaMemcpy(s->prims.p, ps.prims.data(), ps.prims.size() * sizeof(PrimDev), cudaMemcpyHostToDevice));
     s->built = false;
@@ -716,8 +741,9 @@ int lmcu_accel_build(LmcuScene* s, const LmcuBuildOptions* opts, LmcuBuildStats*
     s->t32.release(); s->t64.release();
     if (s->fp32) CU(s->t32.alloc(nt)); else CU(s->t64.alloc(nt));
     CU(s->shade.alloc(nt));
+    CU(s->uv.alloc(s->mesh_t.p ? nt : 0));
     k_emit<<<grid_for(nt, 256), 256, 0, st>>>(tri_order.p, nt, s->prims.p, s->num_prims, wp.p, s->mesh_p.p, s->mesh_n.p,
-                                              s->t32.p, s->t64.p, s->shade.p);
+                                              s->t32.p, s->t64.p, s->shade.p, s->mesh_t.p, s->uv.p);
     CU(cudaGetLastError());
     CU(cudaEventRecord(s->ev1, st));
     CU(cudaStreamSynchronize(st));
@@ -1028,7 +1054,8 @@ static int pt_pass(LmcuScene* s, const PtParams& pp, bool count, PtAccum& acc) {
             cudaEventRecord(ev[0], st);
             LMCU_DISPATCH(k_pt_extend_q, s->fp32, count, q_blocks, 128, st, d, q[cur], s->hits.p, s->pt_ctr.p, cur);
             cudaEventRecord(ev[1], st);
-            k_pt_shade<<<shade_blocks, 256, 0, st>>>(d, pp, q[cur], q[cur ^ 1], sq, s->hits.p, s->film.p, s->pt_ctr.p, cur);
+            if (s->composite) k_pt_shade<true><<<shade_blocks, 256, 0, st>>>(d, pp, q[cur], q[cur ^ 1], sq, s->hits.p, s->film.p, s->pt_ctr.p, cur);
+            else k_pt_shade<false><<<shade_blocks, 256, 0, st>>>(d, pp, q[cur], q[cur ^ 1], sq, s->hits.p, s->film.p, s->pt_ctr.p, cur);
             cudaEventRecord(ev[2], st);
             LMCU_DISPATCH(k_pt_shadow_q, s->fp32, count, q_blocks, 128, st, d, sq, s->film.p, s->pt_ctr.p);
             cudaEventRecord(ev[3], st);

@@ -18,6 +18,10 @@ struct PreparedScene {
     std::vector<EmitTri> emit;
     std::vector<float> cdf;
     std::vector<float4> env_tex;             // light::env texels (rgb, texture::bitmap row order)
+    std::vector<TextureDev> textures;        // texture::bitmap assets
+    std::vector<float4> texels;              // ... their texels (rgba; alpha = 1 without a channel)
+    std::vector<MixEntry> mix;               // entries of the constant-weight mixtures
+    std::vector<float> mesh_t;               // [total faces][3][2] texture coordinates; empty when no material reads a texture
     CameraDev cam{};
     bool has_camera = false;
     int env_light = -1;
@@ -65,13 +69,96 @@ inline int prepare_scene(const LmcuSceneDesc* d, PreparedScene& o, std::string& 
     if (nt == 0) { err = "Missing primitives."; return LMCU_ERR_UNSUPPORTED; }
     if (nt > 0x7fffffffull) { err = "more than 2^31 triangles"; return LMCU_ERR_UNSUPPORTED; }
     o.nt = (uint32_t)nt;
+    // textures (texture::bitmap, src/texture/texture_bitmap.cpp:41-96)
+    if (d->num_textures < 0 || (d->num_textures > 0 && !d->textures)) { err = "bad texture table"; return LMCU_ERR_INVALID_ARGUMENT; }
+    o.textures.resize(d->num_textures);
+    for (int i = 0; i < d->num_textures; i++) {
+        const LmcuTexture& t = d->textures[i];
+        if (t.w <= 0 || t.h <= 0 || (t.c != 3 && t.c != 4) || !t.data) { err = "texture: need w, h > 0, 3 or 4 channels and texel data"; return LMCU_ERR_INVALID_ARGUMENT; }
+        TextureDev& q = o.textures[i];
+        q.w = t.w; q.h = t.h; q.offset = (int32_t)o.texels.size(); q.has_alpha = t.c == 4 ? 1 : 0;
+        o.texels.reserve(o.texels.size() + (size_t)t.w * t.h);
+        for (size_t k = 0; k < (size_t)t.w * t.h; k++) {
+            const float* c = t.data + k * t.c;
+            o.texels.push_back(make_float4(c[0], c[1], c[2], t.c == 4 ? c[3] : 1.f));
+        }
+    }
     o.mats.resize(d->num_materials);
+    bool reads_texture = false;
     for (int i = 0; i < d->num_materials; i++) {
         const LmcuMaterial& m = d->materials[i];
-        if (m.type < 0 || m.type > 3) { err = "bad material type"; return LMCU_ERR_INVALID_ARGUMENT; }
-        o.mats[i].type = m.type;
-        o.mats[i].r = (float)m.color[0]; o.mats[i].g = (float)m.color[1]; o.mats[i].b = (float)m.color[2];
-        o.mats[i].ax = (float)m.ax; o.mats[i].ay = (float)m.ay; o.mats[i].Ni = (float)m.Ni; o.mats[i].pad_ = 0.f;
+        if (m.type < 0 || m.type > LMCU_MAT_MIXTURE_MARGINALIZED) { err = "bad material type"; return LMCU_ERR_INVALID_ARGUMENT; }
+        MaterialDev& q = o.mats[i];
+        memset(&q, 0, sizeof(q));
+        q.type = m.type;
+        q.r = (float)m.color[0]; q.g = (float)m.color[1]; q.b = (float)m.color[2];
+        q.ax = (float)m.ax; q.ay = (float)m.ay; q.Ni = (float)m.Ni;
+        q.tex_kd = -1;
+        if (m.map_kd != 0 && (m.type == LMCU_MAT_DIFFUSE || m.type == LMCU_MAT_MIXTURE_OBJ)) {
+            if (m.map_kd < 0 || m.map_kd > d->num_textures) { err = "material: bad mapKd texture index"; return LMCU_ERR_INVALID_ARGUMENT; }
+            q.tex_kd = m.map_kd - 1;
+            reads_texture = true;
+        }
+        if (m.type == LMCU_MAT_MIXTURE_OBJ) {
+            q.ks_r = (float)m.Ks[0]; q.ks_g = (float)m.Ks[1]; q.ks_b = (float)m.Ks[2];
+            // model_wavefrontobj.cpp:405-412: the mask exists only when the texture has an alpha channel
+            q.alpha_mask = (m.alpha_mask && q.tex_kd >= 0 && o.textures[q.tex_kd].has_alpha) ? 1 : 0;
+        }
+    }
+    // constant-weight mixtures (src/material/material_mixture.cpp:51-59,156-186): entries, Dist::norm() pmfs
+    for (int i = 0; i < d->num_materials; i++) {
+        const LmcuMaterial& m = d->materials[i];
+        if (m.type != LMCU_MAT_MIXTURE_RR && m.type != LMCU_MAT_MIXTURE_MARGINALIZED) continue;
+        if (m.num_entries <= 0 || !m.entry_material || !m.entry_weight) { err = "mixture material without entries"; return LMCU_ERR_INVALID_ARGUMENT; }
+        MaterialDev& q = o.mats[i];
+        q.entry_offset = (int32_t)o.mix.size();
+        q.num_entries = m.num_entries;
+        double sum = 0.0, sum0 = 0.0;
+        for (int k = 0; k < m.num_entries; k++) {
+            const int e = m.entry_material[k];
+            if (e < 0 || e >= d->num_materials) { err = "mixture entry: bad material index"; return LMCU_ERR_INVALID_ARGUMENT; }
+            const int et = d->materials[e].type;
+            if (et == LMCU_MAT_GLASS || et > LMCU_MAT_MASK) {
+                // the reference hands a mixture entry component 0 whatever the entry's own components are
+                // (material_mixture.cpp:67-78): only single-component entries are meaningful
+                err = "mixture entries must be diffuse, glossy, mirror or mask"; return LMCU_ERR_UNSUPPORTED;
+            }
+            if (!(m.entry_weight[k] > 0.0)) { err = "mixture entry: weight must be positive"; return LMCU_ERR_INVALID_ARGUMENT; }
+            sum += m.entry_weight[k];
+            if (!mat_is_specular(et)) sum0 += m.entry_weight[k];
+        }
+        if (m.type == LMCU_MAT_MIXTURE_RR) {
+            for (int k = 0; k < m.num_entries; k++) {
+                MixEntry e;
+                e.material = m.entry_material[k]; e.weight = (float)m.entry_weight[k];
+                e.prob = (float)(m.entry_weight[k] / sum); e.group_prob = e.prob;
+                o.mix.push_back(e);
+            }
+        } else {
+            // group 0 = every non-specular entry, then one group per specular entry, in entry order
+            int n0 = 0;
+            for (int pass = 0; pass < 2; pass++) {
+                for (int k = 0; k < m.num_entries; k++) {
+                    const bool spec = mat_is_specular(d->materials[m.entry_material[k]].type);
+                    if (spec != (pass == 1)) continue;
+                    MixEntry e;
+                    e.material = m.entry_material[k]; e.weight = (float)m.entry_weight[k];
+                    e.prob = spec ? 1.f : (float)(m.entry_weight[k] / sum0);
+                    e.group_prob = (float)((spec ? m.entry_weight[k] : sum0) / sum);
+                    o.mix.push_back(e);
+                    if (!spec) n0++;
+                }
+            }
+            q.num_group0 = n0;
+        }
+    }
+    if (reads_texture) {
+        o.mesh_t.assign((size_t)o.face_offset.back() * 6, 0.f);
+        for (int i = 0; i < d->num_meshes; i++) {
+            if (!d->meshes[i].t) continue;
+            const size_t nf = (size_t)d->meshes[i].num_faces;
+            for (size_t k = 0; k < nf * 6; k++) o.mesh_t[(size_t)o.face_offset[i] * 6 + k] = (float)d->meshes[i].t[k];
+        }
     }
     o.lights.resize(d->num_lights);
     o.env_light = -1;

@@ -100,15 +100,35 @@ LMCU_HD float sn_correction(F3 n, F3 gn, F3 wi, F3 wo) {
 LMCU_HD bool opposite(F3 n, F3 w1, F3 w2) { return dot(w1, n) * dot(w2, n) <= 0.f; }   // surface.h:178-180
 
 // -- materials ----------------------------------------------------------------------------------------
-enum { MAT_DIFFUSE = 0, MAT_GLOSSY = 1, MAT_GLASS = 2, MAT_MIRROR = 3 };
+enum { MAT_DIFFUSE = 0, MAT_GLOSSY = 1, MAT_GLASS = 2, MAT_MIRROR = 3, MAT_MASK = 4,
+       MAT_MIXTURE_OBJ = 5, MAT_MIXTURE_RR = 6, MAT_MIXTURE_MARGINALIZED = 7 };
 
 struct alignas(16) MaterialDev {
     int32_t type;
-    float r, g, b;        // Kd / Ks
-    float ax, ay, Ni, pad_;
+    float r, g, b;              // Kd / Ks
+    float ax, ay, Ni;
+    int32_t tex_kd;             // diffuse, mixture_obj: TextureDev index of mapKd, -1 = none
+    float ks_r, ks_g, ks_b;     // mixture_obj: Ks of the glossy lobe
+    int32_t alpha_mask;         // mixture_obj: 1 = the alpha channel of mapKd masks the surface
+    int32_t entry_offset;       // constant-weight mixtures: first MixEntry
+    int32_t num_entries;        // ... number of entries; marginalized: the non-specular ones come first
+    int32_t num_group0;         // marginalized: entries of the default (non-specular) group
+    int32_t pad_;
+};
+static_assert(sizeof(MaterialDev) == 64, "MaterialDev must be 64 bytes");
+
+// One (material, weight) entry of a constant-weight mixture (src/material/material_mixture.cpp:27-36,126-145)
+struct alignas(16) MixEntry {
+    int32_t material;           // index into DevScene::mats (diffuse | glossy | mirror | mask)
+    float weight;               // multiplies the entry's BSDF
+    float prob;                 // rr: pmf of the entry as a component; marginalized: pmf inside its group
+    float group_prob;           // marginalized: pmf of the entry's group as a component
 };
 
-LMCU_HD bool mat_is_specular(int type) { return type == MAT_GLASS || type == MAT_MIRROR; }
+// texture::bitmap (src/texture/texture_bitmap.cpp:41-96); texels live in one float4 pool (alpha = 1 without a channel)
+struct alignas(16) TextureDev { int32_t w, h, offset, has_alpha; };
+
+LMCU_HD bool mat_is_specular(int type) { return type == MAT_GLASS || type == MAT_MIRROR || type == MAT_MASK; }
 
 // material_glossy.cpp:43-46
 LMCU_HD float ggx_D(const MaterialDev& m, F3 wh, const Frame& f) {
@@ -202,6 +222,10 @@ LMCU_HD BsdfSample mat_sample(const MaterialDev& m, F3 n, F3 gn, F3 wi, float ud
         s.wo = reflection(wi, n);
         s.weight = f3s(1.f);
         s.specular = true;
+    } else if (m.type == MAT_MASK) {                   // material_mask.cpp:38-43: straight through
+        s.wo = -wi;
+        s.weight = f3s(1.f);
+        s.specular = true;
     } else {                                           // material_glass.cpp:124-136,162-190
         F3 wt; float eta; bool total;
         const float Fr = glass_fresnel(m, n, wi, wt, eta, total);
@@ -218,9 +242,18 @@ LMCU_HD BsdfSample mat_sample(const MaterialDev& m, F3 n, F3 gn, F3 wi, float ud
     return s;
 }
 
-// Material::reflectance (raycast shading): Kd / Ks / 0
+// Material::reflectance of a plain lobe (raycast shading): Kd / Ks / 0
 LMCU_HD F3 mat_reflectance(const MaterialDev& m) {
     return (m.type == MAT_DIFFUSE || m.type == MAT_GLOSSY) ? f3(m.r, m.g, m.b) : f3s(0.f);
+}
+
+// Texture::eval / eval_alpha (texture_bitmap.cpp:68-75,83-90): nearest texel at the fractional part of t
+LMCU_HD float4 tex_fetch(const TextureDev& t, const float4* texels, float tu, float tv) {
+    const float u = tu - floorf(tu), v = tv - floorf(tv);
+    int x = (int)(u * (float)t.w), y = (int)(v * (float)t.h);
+    x = x < 0 ? 0 : (x > t.w - 1 ? t.w - 1 : x);
+    y = y < 0 ? 0 : (y > t.h - 1 ? t.h - 1 : y);
+    return texels[t.offset + y * t.w + x];
 }
 
 // -- lights -------------------------------------------------------------------------------------------

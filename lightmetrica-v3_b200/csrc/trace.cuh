@@ -16,7 +16,7 @@
 //     same IEEE operations on the same operands, so (t,u,v) stay bit-identical to accel::sahbvh.
 //
 // IO policy (template parameter), all device functions:
-//     bool load(uint32_t i, RayD& r)                       ray i of the queue
+//     bool load(uint32_t i, RayD& r, RayF& f, float& tmin_dn, float& tmax_up)   ray i of the queue, FP64 + FP32 views
 //     void store(uint32_t i, const RayD& r, const HitD& h) result of ray i (h.tri < 0 = miss)
 #pragma once
 #include "bvh.cuh"
@@ -59,10 +59,7 @@ __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, 
                 if (base + (uint32_t)__popc(idle) >= n) exhausted = true;     // warp-uniform
                 if (!active) {
                     idx = base + (uint32_t)__popc(idle & lt_mask);
-                    if (idx < n && io.load(idx, r)) {
-                        f = make_rayf(r);
-                        tmin_dn = f32_down(r.tmin);
-                        tmax_up = f32_up(r.tmax);
+                    if (idx < n && io.load(idx, r, f, tmin_dn, tmax_up)) {
                         ht = r.tmax; htri = -1;
                         ngroup = make_uint2(0u, 0x80000000u);   // the root occupies virtual slot 7 of group 0
                         tgroup = make_uint2(0u, 0u);
@@ -129,9 +126,8 @@ __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, 
                     const D3 q = dcross(tv, e1);
                     const double d = ddot(e1, p);
                     const double ad = fabs(d);
-                    const double s = copysign(1.0, d);
-                    const double u = mulrn(ddot(tv, p), s);
-                    const double v = mulrn(ddot(r.d, q), s);
+                    const double u = mul_sign_of(ddot(tv, p), d);
+                    const double v = mul_sign_of(ddot(r.d, q), d);
                     if (!(ad < 1e-8 || u < 0.0 || v < 0.0 || addrn(u, v) > ad)) {
                         const double t = divrn(ddot(e2, q), d);
                         if (!(t < r.tmin || ht < t)) {          // inclusive bounds; a later equal-t triangle wins
@@ -159,7 +155,10 @@ __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, 
 
 }  // namespace lmcu
 
-// Variants measured and dropped (profiles/r01_ncu_summary_v2.md, gpurun logs of round 1): 3 triangle tests
+// Variants measured and dropped (profiles/r01_ncu_summary_v2.md, gpurun logs of round 1): warp-private chunks of 32..128
+// rays claimed with one atomic, the next chunk claimed in advance and prefetched toward L2 (-3 % on C2 pt, 1195 vs 1232
+// Mpaths/s at 256 spp, for every refill threshold 4..16: the atomic's latency is already covered by the scheduler's other
+// warps, whole-chunk tails at the end of each launch are not; chunk 128 lost 30 % on a 2 M-ray batch); 3 triangle tests
 // per iteration (-6 % Mpaths/s on C2), a CWBVH-style accumulated "lost iterations" refetch credit (never paid
 // back on rays this short), and a phase-partitioned loop that postpones FP64 triangle tests until >= 12..24
 // lanes hold some (triangle-step occupancy 9.5 -> 12.8 lanes, but the speculative node steps cost as much as

@@ -18,7 +18,8 @@ class LmcuHit(C.Structure):
 
 
 class LmcuMesh(C.Structure):
-    _fields_ = [("num_faces", C.c_int32), ("p", C.POINTER(C.c_double)), ("n", C.POINTER(C.c_double))]
+    _fields_ = [("num_faces", C.c_int32), ("p", C.POINTER(C.c_double)), ("n", C.POINTER(C.c_double)),
+                ("t", C.POINTER(C.c_double))]
 
 
 class LmcuPrimitive(C.Structure):
@@ -27,15 +28,23 @@ class LmcuPrimitive(C.Structure):
 
 
 MAT_DIFFUSE, MAT_GLOSSY, MAT_GLASS, MAT_MIRROR = 0, 1, 2, 3
+MAT_MASK, MAT_MIXTURE_OBJ, MAT_MIXTURE_RR, MAT_MIXTURE_MARGINALIZED = 4, 5, 6, 7
 LIGHT_AREA, LIGHT_ENVCONST, LIGHT_ENV, LIGHT_POINT, LIGHT_DIRECTIONAL = 0, 1, 2, 3, 4
 SAMPLING_NAIVE, SAMPLING_NEE, SAMPLING_MIS = 0, 1, 2
 PRIMARY_PIXEL, PRIMARY_IMAGE = 0, 1
 SCHED_SAMPLE, SCHED_TIME = 0, 1
 
 
+class LmcuTexture(C.Structure):
+    _fields_ = [("w", C.c_int32), ("h", C.c_int32), ("c", C.c_int32), ("pad_", C.c_int32),
+                ("data", C.POINTER(C.c_float)), ("path", C.c_char_p)]
+
+
 class LmcuMaterial(C.Structure):
-    _fields_ = [("type", C.c_int32), ("pad_", C.c_int32), ("color", c_double3),
-                ("ax", C.c_double), ("ay", C.c_double), ("Ni", C.c_double)]
+    _fields_ = [("type", C.c_int32), ("map_kd", C.c_int32), ("color", c_double3),
+                ("ax", C.c_double), ("ay", C.c_double), ("Ni", C.c_double), ("Ks", c_double3),
+                ("alpha_mask", C.c_int32), ("num_entries", C.c_int32),
+                ("entry_material", C.POINTER(C.c_int32)), ("entry_weight", C.POINTER(C.c_double))]
 
 
 class LmcuLight(C.Structure):
@@ -53,9 +62,10 @@ class LmcuCamera(C.Structure):
 class LmcuSceneDesc(C.Structure):
     _fields_ = [("num_meshes", C.c_int32), ("num_primitives", C.c_int32),
                 ("num_materials", C.c_int32), ("num_lights", C.c_int32),
+                ("num_textures", C.c_int32), ("pad_", C.c_int32),
                 ("meshes", C.POINTER(LmcuMesh)), ("primitives", C.POINTER(LmcuPrimitive)),
                 ("materials", C.POINTER(LmcuMaterial)), ("lights", C.POINTER(LmcuLight)),
-                ("camera", C.POINTER(LmcuCamera))]
+                ("camera", C.POINTER(LmcuCamera)), ("textures", C.POINTER(LmcuTexture))]
 
 
 class LmcuRenderParams(C.Structure):

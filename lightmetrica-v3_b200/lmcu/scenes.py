@@ -44,23 +44,51 @@ class SceneBuilder:
         self.lights = []        # dict
         self.primitives = []    # dict
         self.camera = None
+        self.textures = []      # dict(data=float32[h,w,c] in texture::bitmap row order, path=str or None)
+        self.mesh_t = {}        # mesh index -> t[nf,3,2] texture coordinates
         self._keep = []
 
     # -- assets -------------------------------------------------------------------------------
-    def add_mesh(self, p, n=None):
+    def add_mesh(self, p, n=None, t=None):
         p = np.ascontiguousarray(p, dtype=np.float64).reshape(-1, 3, 3)
         if n is not None:
             n = np.ascontiguousarray(n, dtype=np.float64).reshape(-1, 3, 3)
             assert n.shape == p.shape
         self.meshes.append((p, n))
+        if t is not None:
+            t = np.ascontiguousarray(t, dtype=np.float64).reshape(-1, 3, 2)
+            assert t.shape[0] == p.shape[0]
+            self.mesh_t[len(self.meshes) - 1] = t
         return len(self.meshes) - 1
 
-    def add_material(self, type, color=(1, 1, 1), ax=0.0, ay=0.0, Ni=1.0):
-        self.materials.append(dict(type=type, color=tuple(color), ax=ax, ay=ay, Ni=Ni))
+    def add_texture(self, data, path=None):
+        """texture::bitmap: data = float32 [h,w,3|4] in the row order the reference holds after loading `path`."""
+        data = np.ascontiguousarray(data, dtype=np.float32)
+        assert data.ndim == 3 and data.shape[2] in (3, 4)
+        self.textures.append(dict(data=data, path=path))
+        return len(self.textures) - 1
+
+    def add_material(self, type, color=(1, 1, 1), ax=0.0, ay=0.0, Ni=1.0, **extra):
+        self.materials.append(dict(type=type, color=tuple(color), ax=ax, ay=ay, Ni=Ni, **extra))
         return len(self.materials) - 1
 
-    def diffuse(self, Kd):
-        return self.add_material(abi.MAT_DIFFUSE, Kd)
+    def diffuse(self, Kd, map_kd=None):
+        return self.add_material(abi.MAT_DIFFUSE, Kd, map_kd=map_kd)
+
+    def mask(self):
+        return self.add_material(abi.MAT_MASK, (0, 0, 0))
+
+    def mixture_obj(self, Kd, Ks, ax, ay, map_kd=None, alpha_mask=True):
+        """material::mixture_wavefrontobj: what the OBJ loader creates per .mtl entry (model_wavefrontobj.cpp:393-413)."""
+        return self.add_material(abi.MAT_MIXTURE_OBJ, Kd, ax, ay, Ks=tuple(Ks), map_kd=map_kd, alpha_mask=alpha_mask)
+
+    def mixture_rr(self, entries):
+        """material::constant_weight_mixture_rr; entries = [(material index, weight), ...]"""
+        return self.add_material(abi.MAT_MIXTURE_RR, (0, 0, 0), entries=list(entries))
+
+    def mixture_marginalized(self, entries):
+        """material::constant_weight_mixture_marginalized; entries = [(material index, weight), ...]"""
+        return self.add_material(abi.MAT_MIXTURE_MARGINALIZED, (0, 0, 0), entries=list(entries))
 
     def glossy(self, Ks, ax, ay):
         return self.add_material(abi.MAT_GLOSSY, Ks, ax, ay)
@@ -115,6 +143,7 @@ class SceneBuilder:
             meshes[i].num_faces = p.shape[0]
             meshes[i].p = p.ctypes.data_as(dp)
             meshes[i].n = n.ctypes.data_as(dp) if n is not None else None
+            meshes[i].t = self.mesh_t[i].ctypes.data_as(dp) if i in self.mesh_t else None
         prims = (abi.LmcuPrimitive * max(1, len(self.primitives)))()
         for i, q in enumerate(self.primitives):
             prims[i].node_index, prims[i].mesh = q["node_index"], q["mesh"]
@@ -124,6 +153,19 @@ class SceneBuilder:
         for i, m in enumerate(self.materials):
             mats[i].type, mats[i].color = m["type"], abi.c_double3(*m["color"])
             mats[i].ax, mats[i].ay, mats[i].Ni = m["ax"], m["ay"], m["Ni"]
+            mats[i].map_kd = 0 if m.get("map_kd") is None else m["map_kd"] + 1
+            mats[i].Ks = abi.c_double3(*m.get("Ks", (0, 0, 0)))
+            mats[i].alpha_mask = 1 if m.get("alpha_mask") else 0
+            if m.get("entries"):
+                em = (C.c_int32 * len(m["entries"]))(*[e[0] for e in m["entries"]])
+                ew = (C.c_double * len(m["entries"]))(*[float(e[1]) for e in m["entries"]])
+                mats[i].num_entries, mats[i].entry_material, mats[i].entry_weight = len(m["entries"]), em, ew
+                self._keep.append((em, ew))
+        texs = (abi.LmcuTexture * max(1, len(self.textures)))()
+        for i, t in enumerate(self.textures):
+            texs[i].h, texs[i].w, texs[i].c = t["data"].shape
+            texs[i].data = t["data"].ctypes.data_as(C.POINTER(C.c_float))
+            texs[i].path = t["path"].encode() if t["path"] else None
         lights = (abi.LmcuLight * max(1, len(self.lights)))()
         for i, l in enumerate(self.lights):
             lights[i].type, lights[i].primitive = l["type"], l["primitive"]
@@ -139,6 +181,7 @@ class SceneBuilder:
         d.num_meshes, d.num_primitives = len(self.meshes), len(self.primitives)
         d.num_materials, d.num_lights = len(self.materials), len(self.lights)
         d.meshes, d.primitives, d.materials, d.lights = meshes, prims, mats, lights
+        d.num_textures, d.textures = len(self.textures), texs
         if self.camera is not None:
             cam = abi.LmcuCamera()
             cam.position = abi.c_double3(*self.camera["position"])
@@ -147,7 +190,7 @@ class SceneBuilder:
             cam.vfov, cam.aspect = self.camera["vfov"], self.camera["aspect"]
             d.camera = C.pointer(cam)
             self._keep.append(cam)
-        self._keep.append((meshes, prims, mats, lights))
+        self._keep.append((meshes, prims, mats, lights, texs))
         return d
 
 
@@ -393,6 +436,93 @@ def env_light(path, w=1024, h=512, seed=5, rot=0.0, scale=1.0):
     rgbe = procedural_env(w, h, seed)
     write_hdr(path, rgbe)
     return dict(rgb=_rgbe_decode(rgbe), rot=rot, scale=scale, path=path)
+
+
+def write_png(path, img):
+    """8-bit RGB / RGBA PNG from uint8 [h,w,3|4], row 0 = top (stdlib only)."""
+    import struct
+    import zlib
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    h, w, c = img.shape
+
+    def chunk(tag, data):
+        return struct.pack(">I", len(data)) + tag + data + struct.pack(">I", zlib.crc32(tag + data) & 0xffffffff)
+    raw = b"".join(b"\x00" + img[y].tobytes() for y in range(h))
+    with open(path, "wb") as f:
+        f.write(b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, {3: 2, 4: 6}[c], 0, 0, 0))
+                + chunk(b"IDAT", zlib.compress(raw, 6)) + chunk(b"IEND", b""))
+
+
+def png_texels(img):
+    """What texture::bitmap holds after stbi_loadf(flip=true) of that PNG: colour channels through stb's LDR->HDR ramp
+    pow(v/255, 2.2), alpha linear, rows bottom-up (src/texture/texture_bitmap.cpp:55-66)."""
+    img = np.asarray(img, dtype=np.uint8)
+    lin = img.astype(np.float32) / np.float32(255.0)
+    out = np.power(lin.astype(np.float64), float(np.float32(2.2))).astype(np.float32)
+    if img.shape[2] == 4:
+        out[..., 3] = lin[..., 3]
+    return np.ascontiguousarray(out[::-1])
+
+
+def checker_texture(path, w=64, h=32, cells=8, alpha=False, seed=11):
+    """Procedural colour checker (+ an alpha channel with holes) written as a PNG; returns kwargs for add_texture."""
+    rng = np.random.RandomState(seed)
+    ys, xs = np.mgrid[0:h, 0:w]
+    cell = (xs * cells // w) + (ys * cells // h) * cells
+    pal = rng.randint(40, 256, size=(cells * cells, 3)).astype(np.uint8)
+    img = pal[cell]
+    if alpha:
+        a = np.where(((xs * cells // w) + (ys * cells // h)) % 3 == 0, 0, 255).astype(np.uint8)
+        a[(ys * cells // h) % 4 == 1] = 128
+        img = np.concatenate([img, a[..., None]], axis=2)
+    write_png(path, img)
+    return dict(data=png_texels(img), path=path)
+
+
+def planar_uv(p, scale=1.0):
+    """Texture coordinates from the xz (or xy for vertical faces) position of each vertex."""
+    p = np.asarray(p, dtype=np.float64).reshape(-1, 3, 3)
+    n = np.cross(p[:, 1] - p[:, 0], p[:, 2] - p[:, 0])
+    vertical = np.abs(n[:, 1]) < np.maximum(np.abs(n[:, 0]), np.abs(n[:, 2]))
+    t = np.where(vertical[:, None, None], p[:, :, [0, 1]] + p[:, :, [2, 2]] * [1.0, 0.0], p[:, :, [0, 2]])
+    return np.ascontiguousarray(t * scale)
+
+
+def textured_scene(tmpdir, num_theta=12, kind="obj"):
+    """Cornell shell whose floor / back wall / spheres carry the OBJ-import material set:
+    kind = "obj": mixture_wavefrontobj with a mapKd checker (floor), with an RGBA mapKd whose alpha masks the surface
+                  (a screen in front of the back wall), plain textured diffuse (back wall), untextured mixture_obj sphere
+    kind = "mix": constant-weight mixtures (rr on one sphere, marginalized on the other, entries diffuse/glossy/mirror/mask)
+    """
+    import os
+    sb = SceneBuilder()
+    _cornell_shell(sb)
+    tex = sb.add_texture(**checker_texture(os.path.join(str(tmpdir), "checker.png")))
+    tex_a = sb.add_texture(**checker_texture(os.path.join(str(tmpdir), "checker_a.png"), alpha=True, seed=12))
+    sp, sn = uv_sphere(num_theta)
+    sp = _f32(sp * 0.35)
+    th = np.arccos(np.clip(sn[..., 1], -1, 1)) / np.pi
+    ph = (np.arctan2(sn[..., 0], sn[..., 2]) / (2 * np.pi)) % 1.0
+    st = np.stack([ph, th], -1)
+    sphere = sb.add_mesh(sp, sn, st)
+    fl = _f32(quad((-0.8, 0.01, 0.8), (0.8, 0.01, 0.8), (0.8, 0.01, -0.8), (-0.8, 0.01, -0.8)))
+    floor = sb.add_mesh(fl, flat_normals(fl), planar_uv(fl, 0.5))
+    scr = _f32(quad((-0.9, 0.2, -0.5), (0.9, 0.2, -0.5), (0.9, 1.6, -0.5), (-0.9, 1.6, -0.5)))
+    screen = sb.add_mesh(scr, flat_normals(scr), planar_uv(scr, 0.6))
+    if kind == "obj":
+        sb.add_primitive(floor, sb.mixture_obj((.5, .5, .5), (.3, .3, .3), .2, .1, map_kd=tex))
+        sb.add_primitive(screen, sb.mixture_obj((.5, .5, .5), (.05, .05, .05), .3, .3, map_kd=tex_a))
+        sb.add_primitive(sphere, sb.mixture_obj((.7, .3, .2), (.4, .4, .4), .15, .15), M=translate((-.4, .36, .1)))
+        sb.add_primitive(sphere, sb.diffuse((1, 1, 1), map_kd=tex), M=translate((.45, .36, .3)))
+    else:
+        d, g, m, k = sb.diffuse((.6, .5, .2)), sb.glossy((.7, .7, .7), .1, .2), sb.mirror(), sb.mask()
+        d2 = sb.diffuse((1, 1, 1), map_kd=tex)
+        sb.add_primitive(floor, sb.mixture_marginalized([(d2, .7), (g, .3)]))
+        sb.add_primitive(screen, sb.mixture_rr([(k, .6), (d, .4)]))
+        sb.add_primitive(sphere, sb.mixture_rr([(d, .5), (g, .3), (m, .2)]), M=translate((-.4, .36, .1)))
+        sb.add_primitive(sphere, sb.mixture_marginalized([(d, .4), (g, .3), (m, .2), (k, .1)]), M=translate((.45, .36, .3)))
+    sb.set_camera(position=(0, 1, 5), center=(0, 1, 0), up=(0, 1, 0), vfov=30, aspect=16 / 9)
+    return sb
 
 
 def delta_lights_scene(grid=2, num_theta=12):

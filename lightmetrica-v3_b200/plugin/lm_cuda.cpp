@@ -13,6 +13,7 @@
 // library surfaces as lm::Exception).
 #include <lm/lm.h>
 
+#include <cstring>
 #include <map>
 #include <mutex>
 #include <thread>
@@ -35,8 +36,14 @@ void check(int rc) {
 
 // Everything liblmcu needs, gathered from an lm::Scene.  Owns the arrays the LmcuSceneDesc points to.
 struct SceneExport {
-    std::vector<std::vector<double>> mesh_p, mesh_n;
+    std::vector<std::vector<double>> mesh_p, mesh_n, mesh_t;
     std::vector<LmcuMesh> meshes;
+    std::vector<std::vector<float>> tex_data;
+    std::vector<LmcuTexture> textures;
+    std::map<const Texture*, int> tex_ids;
+    std::map<const Material*, int> mat_ids;
+    std::vector<std::vector<int32_t>> entry_material;     // per mixture material (kept alive for LmcuMaterial's pointers)
+    std::vector<std::vector<double>> entry_weight;
     std::vector<LmcuPrimitive> prims;
     std::vector<LmcuMaterial> mats;
     std::vector<LmcuLight> lights;
@@ -49,14 +56,73 @@ struct SceneExport {
     // (SURVEY.md §7 "hard parts"): key() gives the type, reflectance() gives Kd / Ks, GGX roughness
     // follows from pdf_direction() at three half vectors, the index of refraction from the Fresnel
     // reflectance at normal incidence returned by pdf_component().
-    static LmcuMaterial probe_material(const Material* m) {
+    // texture::bitmap keeps its texels behind Texture::buffer() (src/texture/texture_bitmap.cpp:92-94); any other texture
+    // is sampled through eval() into a 1x1 image.  Returns 1 + index into textures[].
+    int register_texture(Texture* tex) {
+        auto it = tex_ids.find(tex);
+        if (it != tex_ids.end()) return it->second + 1;
+        const auto buf = tex->buffer();
+        LmcuTexture t{};
+        tex_data.emplace_back();
+        auto& data = tex_data.back();
+        if (buf.data && (buf.c == 3 || buf.c == 4)) {
+            t.w = buf.w; t.h = buf.h; t.c = buf.c;
+            data.assign(buf.data, buf.data + size_t(buf.w) * buf.h * buf.c);
+        }
+        else if (buf.data && buf.c >= 1) {                                  // grey (+alpha) images: expand to rgb(a)
+            const bool alpha = buf.c == 2;
+            t.w = buf.w; t.h = buf.h; t.c = alpha ? 4 : 3;
+            for (size_t i = 0; i < size_t(buf.w) * buf.h; i++) {
+                for (int k = 0; k < 3; k++) data.push_back(buf.data[buf.c * i + std::min(k, buf.c - 1 - (alpha ? 1 : 0))]);
+                if (alpha) data.push_back(buf.data[buf.c * i + 1]);
+            }
+        }
+        else {
+            const Vec3 c = tex->eval(Vec2(.5_f));
+            t.w = t.h = 1; t.c = 3;
+            data = { float(c.x), float(c.y), float(c.z) };
+        }
+        tex_ids.emplace(tex, int(textures.size()));
+        textures.push_back(t);                                              // data pointers are fixed up in gather()
+        return int(textures.size());
+    }
+
+    // Material parameters are private in the reference; recover them through the public virtuals
+    // (SURVEY.md §7 "hard parts"): key() gives the type, reflectance() gives Kd / Ks, GGX roughness
+    // follows from pdf_direction() at three half vectors, the index of refraction from the Fresnel
+    // reflectance at normal incidence returned by pdf_component(); composite materials expose their parts through
+    // underlying() / foreach_underlying() and their weights through eval(), pdf_component() and sample_direction().
+    // Returns the index into mats[].
+    int material_index(const Material* m) {
+        auto it = mat_ids.find(m);
+        if (it != mat_ids.end()) return it->second;
+        const LmcuMaterial o = probe_material(m);                           // may register entries first
+        mat_ids.emplace(m, int(mats.size()));
+        mats.push_back(o);
+        return int(mats.size()) - 1;
+    }
+
+    LmcuMaterial probe_material(const Material* m) {
         LmcuMaterial o{};
         const auto geom = PointGeometry::make_on_surface(Vec3(0_f), Vec3(0_f, 0_f, 1_f), Vec3(0_f, 0_f, 1_f));
-        const auto key = m->key();
+        auto key = m->key();
+        if (key == "material::proxy") {                                     // src/material/material_proxy.cpp: pure forwarding
+            const Material* ref = nullptr;
+            const_cast<Material*>(m)->foreach_underlying([&](Component*& c, bool) { ref = dynamic_cast<const Material*>(c); });
+            if (!ref) LM_THROW_EXCEPTION(Error::Unsupported, "material::proxy without a referenced material");
+            return probe_material(ref);
+        }
         if (key == "material::diffuse") {
             o.type = LMCU_MAT_DIFFUSE;
-            const Vec3 Kd = m->reflectance(geom);
-            o.color[0] = Kd.x; o.color[1] = Kd.y; o.color[2] = Kd.z;
+            auto* tex = dynamic_cast<Texture*>(m->underlying("mapKd"));
+            if (tex) {
+                o.map_kd = register_texture(tex);
+                o.color[0] = o.color[1] = o.color[2] = 1.0;
+            }
+            else {
+                const Vec3 Kd = m->reflectance(geom);
+                o.color[0] = Kd.x; o.color[1] = Kd.y; o.color[2] = Kd.z;
+            }
         }
         else if (key == "material::glossy") {
             o.type = LMCU_MAT_GLOSSY;
@@ -84,10 +150,131 @@ struct SceneExport {
         else if (key == "material::mirror") {
             o.type = LMCU_MAT_MIRROR;
         }
+        else if (key == "material::mask") {
+            o.type = LMCU_MAT_MASK;
+        }
+        else if (key == "material::mixture_wavefrontobj") {
+            // src/model/model_wavefrontobj.cpp:339-515: owns a material::diffuse ("diffuse") and a material::glossy ("glossy")
+            o.type = LMCU_MAT_MIXTURE_OBJ;
+            const auto* md = dynamic_cast<const Material*>(m->underlying("diffuse"));
+            const auto* mg = dynamic_cast<const Material*>(m->underlying("glossy"));
+            if (!md || !mg) LM_THROW_EXCEPTION(Error::Unsupported, "material::mixture_wavefrontobj without its underlying lobes");
+            const LmcuMaterial d = probe_material(md), g = probe_material(mg);
+            for (int k = 0; k < 3; k++) { o.color[k] = d.color[k]; o.Ks[k] = g.color[k]; }
+            o.map_kd = d.map_kd;
+            o.ax = g.ax; o.ay = g.ay;
+            // the alpha mask (mask_tex_, private) shows in pdf_component(0) = alpha at a texel whose alpha is not 1
+            o.alpha_mask = 0;
+            if (o.map_kd > 0 && textures[o.map_kd - 1].c == 4) {
+                const auto& t = textures[o.map_kd - 1];
+                const auto& data = tex_data[o.map_kd - 1];
+                for (size_t i = 0; i < size_t(t.w) * t.h; i++) {
+                    if (data[4 * i + 3] == 1.f) continue;
+                    const Vec2 uv((Float(i % t.w) + .5_f) / t.w, (Float(i / t.w) + .5_f) / t.h);
+                    const auto gt = PointGeometry::make_on_surface(Vec3(0_f), Vec3(0_f, 0_f, 1_f), Vec3(0_f, 0_f, 1_f), uv);
+                    o.alpha_mask = m->pdf_component(0, gt, geom.n) != 1_f ? 1 : 0;
+                    break;
+                }
+            }
+        }
+        else if (key == "material::constant_weight_mixture_rr" || key == "material::constant_weight_mixture_marginalized") {
+            probe_mixture(m, key == "material::constant_weight_mixture_rr", o);
+        }
         else {
             LM_THROW_EXCEPTION(Error::Unsupported, "renderer::*_cuda: unsupported material [key='{}']", key);
         }
         return o;
+    }
+
+    // Constant-weight mixtures (src/material/material_mixture.cpp): the entries come out of foreach_underlying() in
+    // construction order; their weights are private and recovered from the mixture's own answers:
+    //   rr            component i IS entry i; sample_direction(comp i).weight = weight_i * (the entry's own sample weight)
+    //   marginalized  component 0 = all non-specular entries with eval = sum_i weight_i f_i (solved by least squares over a
+    //                 few direction pairs and the 3 colour channels), component g >= 1 = the g-th specular entry with
+    //                 sample_direction(comp g).weight = weight
+    void probe_mixture(const Material* m, bool rr, LmcuMaterial& o) {
+        std::vector<const Material*> entries;
+        const_cast<Material*>(m)->foreach_underlying([&](Component*& c, bool) {
+            if (auto* e = dynamic_cast<const Material*>(c)) entries.push_back(e);
+        });
+        if (entries.empty()) LM_THROW_EXCEPTION(Error::Unsupported, "mixture material without entries");
+        const auto geom = PointGeometry::make_on_surface(Vec3(0_f), Vec3(0_f, 0_f, 1_f), Vec3(0_f, 0_f, 1_f));
+        const Vec3 wi = glm::normalize(Vec3(.3_f, .2_f, 1_f));
+        const Material::DirectionSampleU us{ Vec2(.37_f, .61_f), Vec2(.5_f) };
+        const auto max_ratio = [](Vec3 a, Vec3 b) {                         // a = weight * b, from the largest channel of b
+            int k = 0;
+            for (int c = 1; c < 3; c++) if (std::abs(b[c]) > std::abs(b[k])) k = c;
+            if (b[k] == 0_f) LM_THROW_EXCEPTION(Error::Unsupported, "mixture entry with a zero sample weight: its weight cannot be recovered");
+            return a[k] / b[k];
+        };
+        const auto sampled_weight = [&](int comp, const Material* entry) {
+            const auto sm = m->sample_direction(us, geom, wi, comp, Material::TransDir::EL);
+            const auto se = entry->sample_direction(us, geom, wi, 0, Material::TransDir::EL);
+            if (!sm || !se) LM_THROW_EXCEPTION(Error::Unsupported, "mixture entry could not be sampled for probing");
+            return max_ratio(sm->weight, se->weight);
+        };
+        std::vector<int32_t> ids;
+        std::vector<double> ws(entries.size(), 0.0);
+        for (const auto* e : entries) ids.push_back(material_index(e));
+        if (rr) {
+            o.type = LMCU_MAT_MIXTURE_RR;
+            for (size_t i = 0; i < entries.size(); i++) ws[i] = sampled_weight(int(i), entries[i]);
+        }
+        else {
+            o.type = LMCU_MAT_MIXTURE_MARGINALIZED;
+            std::vector<size_t> diffuse_like;
+            int group = 0;
+            for (size_t i = 0; i < entries.size(); i++) {
+                if (entries[i]->is_specular_component(0)) ws[i] = sampled_weight(++group, entries[i]);
+                else diffuse_like.push_back(i);
+            }
+            const size_t n = diffuse_like.size();
+            if (n == 1) {
+                const Vec3 wo = glm::normalize(Vec3(-.2_f, .4_f, 1_f));
+                ws[diffuse_like[0]] = max_ratio(m->eval(geom, wi, wo, 0, Material::TransDir::EL, false), entries[diffuse_like[0]]->eval(geom, wi, wo, 0, Material::TransDir::EL, false));
+            }
+            else if (n > 1) {
+                // normal equations A^T A w = A^T b with a tiny ridge (entries with identical lobes are interchangeable)
+                std::vector<double> ata(n * n, 0.0), atb(n, 0.0);
+                for (int k = 0; k < 12; k++) {
+                    const Float a = .4_f + .9_f * k, b = .15_f + .1_f * k;
+                    const Vec3 w1 = glm::normalize(Vec3(std::cos(a) * std::sin(b), std::sin(a) * std::sin(b), std::cos(b)));
+                    const Vec3 w2 = glm::normalize(Vec3(std::cos(2.1_f * a) * std::sin(1.3_f - b), std::sin(2.1_f * a) * std::sin(1.3_f - b), std::cos(1.3_f - b)));
+                    const Vec3 fm = m->eval(geom, w1, w2, 0, Material::TransDir::EL, false);
+                    std::vector<Vec3> fe(n);
+                    for (size_t i = 0; i < n; i++) fe[i] = entries[diffuse_like[i]]->eval(geom, w1, w2, 0, Material::TransDir::EL, false);
+                    for (int c = 0; c < 3; c++) {
+                        for (size_t i = 0; i < n; i++) {
+                            atb[i] += fe[i][c] * fm[c];
+                            for (size_t j = 0; j < n; j++) ata[i * n + j] += fe[i][c] * fe[j][c];
+                        }
+                    }
+                }
+                double tr = 0.0;
+                for (size_t i = 0; i < n; i++) tr += ata[i * n + i];
+                for (size_t i = 0; i < n; i++) ata[i * n + i] += 1e-12 * tr;
+                for (size_t c = 0; c < n; c++) {                            // Gaussian elimination with partial pivoting
+                    size_t piv = c;
+                    for (size_t r = c + 1; r < n; r++) if (std::abs(ata[r * n + c]) > std::abs(ata[piv * n + c])) piv = r;
+                    for (size_t j = 0; j < n; j++) std::swap(ata[c * n + j], ata[piv * n + j]);
+                    std::swap(atb[c], atb[piv]);
+                    for (size_t r = c + 1; r < n; r++) {
+                        const double f = ata[r * n + c] / ata[c * n + c];
+                        for (size_t j = c; j < n; j++) ata[r * n + j] -= f * ata[c * n + j];
+                        atb[r] -= f * atb[c];
+                    }
+                }
+                for (size_t c = n; c-- > 0;) {
+                    double v = atb[c];
+                    for (size_t j = c + 1; j < n; j++) v -= ata[c * n + j] * ws[diffuse_like[j]];
+                    ws[diffuse_like[c]] = v / ata[c * n + c];
+                }
+            }
+        }
+        entry_material.push_back(ids);
+        entry_weight.push_back(ws);
+        o.num_entries = int(ids.size());
+        o.entry_material = reinterpret_cast<const int32_t*>(entry_material.size());   // slot + 1; turned into pointers in gather()
     }
 
     // light::env keeps its image as an underlying texture::bitmap ("envmap", src/light/light_env.cpp:42-47) but
@@ -156,7 +343,6 @@ struct SceneExport {
 
     void gather(const Scene& scene, bool shading) {
         std::map<const Mesh*, int> mesh_ids;
-        std::map<const Material*, int> mat_ids;
         scene.traverse_primitive_nodes([&](const SceneNode& node, Mat4 global_transform) {
             if (node.type != SceneNodeType::Primitive) {
                 return;
@@ -206,14 +392,18 @@ struct SceneExport {
                 it = mesh_ids.emplace(mesh, int(mesh_p.size())).first;
                 mesh_p.emplace_back();
                 mesh_n.emplace_back();
+                mesh_t.emplace_back();
                 auto& P = mesh_p.back();
                 auto& N = mesh_n.back();
+                auto& T = mesh_t.back();
                 P.reserve(size_t(mesh->num_triangles()) * 9);
                 N.reserve(size_t(mesh->num_triangles()) * 9);
+                T.reserve(size_t(mesh->num_triangles()) * 6);
                 mesh->foreach_triangle([&](int, const Mesh::Tri& tri) {
                     for (const auto* v : { &tri.p1, &tri.p2, &tri.p3 }) {
                         P.push_back(v->p.x); P.push_back(v->p.y); P.push_back(v->p.z);
                         N.push_back(v->n.x); N.push_back(v->n.y); N.push_back(v->n.z);
+                        T.push_back(v->t.x); T.push_back(v->t.y);
                     }
                 });
             }
@@ -224,13 +414,7 @@ struct SceneExport {
             p.light = -1;
             for (int c = 0; c < 4; c++) for (int r = 0; r < 4; r++) p.M[c * 4 + r] = global_transform[c][r];
             if (shading) {
-                const Material* m = node.primitive.material;
-                auto mi = mat_ids.find(m);
-                if (mi == mat_ids.end()) {
-                    mi = mat_ids.emplace(m, int(mats.size())).first;
-                    mats.push_back(probe_material(m));
-                }
-                p.material = mi->second;
+                p.material = material_index(node.primitive.material);
                 if (node.primitive.light) {
                     const auto key = node.primitive.light->key();
                     if (key != "light::area") {
@@ -269,7 +453,18 @@ struct SceneExport {
             meshes[i].num_faces = int(mesh_p[i].size() / 9);
             meshes[i].p = mesh_p[i].data();
             meshes[i].n = mesh_n[i].data();
+            meshes[i].t = shading ? mesh_t[i].data() : nullptr;
         }
+        for (size_t i = 0; i < textures.size(); i++) textures[i].data = tex_data[i].data();
+        for (auto& m : mats) {
+            if (m.num_entries > 0) {
+                const size_t slot = reinterpret_cast<size_t>(m.entry_material) - 1;
+                m.entry_material = entry_material[slot].data();
+                m.entry_weight = entry_weight[slot].data();
+            }
+        }
+        desc.num_textures = int(textures.size());
+        desc.textures = textures.data();
         desc.num_meshes = int(meshes.size());
         desc.num_primitives = int(prims.size());
         desc.num_materials = int(mats.size());
@@ -595,3 +790,41 @@ public:
 LM_COMP_REG_IMPL(Renderer_PT_Cuda, "renderer::pt_cuda");
 
 LM_NAMESPACE_END(LM_NAMESPACE)
+
+// Host-logic test hook (tests/test_plugin_probe.py): what the plugin recovers from an lm::Scene through the public
+// component interfaces, as JSON, without touching a GPU.  Returns the length written, or -1.
+extern "C" int lm_cuda_probe_scene(const char* scene_loc, char* out, int cap) {
+    try {
+        auto* scene = lm::comp::get<lm::Scene>(scene_loc);
+        if (!scene) return -1;
+        lm::SceneExport ex;
+        ex.gather(*scene, true);
+        lm::Json j;
+        j["materials"] = lm::Json::array();
+        for (const auto& m : ex.mats) {
+            lm::Json e{ {"type", m.type}, {"map_kd", m.map_kd}, {"color", { m.color[0], m.color[1], m.color[2] }}, {"ax", m.ax}, {"ay", m.ay},
+                        {"Ni", m.Ni}, {"Ks", { m.Ks[0], m.Ks[1], m.Ks[2] }}, {"alpha_mask", m.alpha_mask}, {"entries", lm::Json::array()} };
+            for (int k = 0; k < m.num_entries; k++) e["entries"].push_back({ m.entry_material[k], m.entry_weight[k] });
+            j["materials"].push_back(e);
+        }
+        j["textures"] = lm::Json::array();
+        for (const auto& t : ex.textures) {
+            double sum = 0;
+            for (size_t i = 0; i < size_t(t.w) * t.h * t.c; i++) sum += t.data[i];
+            j["textures"].push_back({ {"w", t.w}, {"h", t.h}, {"c", t.c}, {"sum", sum} });
+        }
+        j["primitive_materials"] = lm::Json::array();
+        for (const auto& p : ex.prims) j["primitive_materials"].push_back(p.material);
+        double tsum = 0;
+        for (const auto& t : ex.mesh_t) for (double v : t) tsum += v;
+        j["texcoord_sum"] = tsum;
+        const std::string text = j.dump();
+        if (int(text.size()) + 1 > cap) return -1;
+        std::memcpy(out, text.c_str(), text.size() + 1);
+        return int(text.size());
+    }
+    catch (const std::exception& e) {
+        std::snprintf(out, size_t(cap), "%s", e.what());
+        return -1;
+    }
+}

@@ -241,6 +241,11 @@ static void build_bvh(OrcScene* sc) {
 
 OrcScene* orc_scene_create(const LmcuSceneDesc* d) {
     if (!d || d->num_primitives <= 0) return NULL;
+    /* the port restates the four plain BSDFs only; textured and mixture materials are checked against
+       the reference itself (oracle/_ref) */
+    for (int i = 0; i < d->num_materials; i++) {
+        if (d->materials[i].type > LMCU_MAT_MIRROR || d->materials[i].map_kd != 0) return NULL;
+    }
     OrcScene* sc = (OrcScene*)calloc(1, sizeof(OrcScene));
     sc->nmeshes = d->num_meshes;
     sc->mesh_faces = (int*)malloc(sizeof(int) * (size_t)d->num_meshes);

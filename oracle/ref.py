@@ -70,6 +70,11 @@ class RefScene:
                                   C.byref(elapsed), C.byref(processed)))
         return film, elapsed.value, processed.value
 
+    def loc(self):
+        """Locator of the lm::Scene asset inside the reference's asset tree."""
+        lib().lmref_scene_loc.restype = C.c_char_p
+        return lib().lmref_scene_loc(self._h).decode()
+
     def close(self):
         if self._h:
             lib().lmref_scene_destroy(self._h)

@@ -27,14 +27,18 @@ LM_NAMESPACE_BEGIN(LM_NAMESPACE)
 class Mesh_Soup final : public Mesh {
 private:
     std::vector<Vec3> ps_, ns_;
+    std::vector<Vec2> ts_;
     int nf_ = 0;
 public:
     virtual void construct(const Json& prop) override {
         nf_ = json::value<int>(prop, "num_faces");
         const auto* p = reinterpret_cast<const double*>(json::value<std::uintptr_t>(prop, "p"));
         const auto* n = reinterpret_cast<const double*>(json::value<std::uintptr_t>(prop, "n"));
+        const auto* t = reinterpret_cast<const double*>(json::value<std::uintptr_t>(prop, "t", std::uintptr_t(0)));
         ps_.resize(size_t(nf_) * 3);
         ns_.resize(size_t(nf_) * 3);
+        ts_.assign(size_t(nf_) * 3, Vec2());
+        if (t) for (size_t i = 0; i < size_t(nf_) * 3; i++) ts_[i] = Vec2(t[2*i], t[2*i+1]);
         for (size_t i = 0; i < size_t(nf_) * 3; i++) {
             ps_[i] = Vec3(p[3*i], p[3*i+1], p[3*i+2]);
         }
@@ -53,7 +57,7 @@ public:
     }
     virtual Tri triangle_at(int face) const override {
         const size_t i = size_t(face) * 3;
-        return { { ps_[i], ns_[i], Vec2() }, { ps_[i+1], ns_[i+1], Vec2() }, { ps_[i+2], ns_[i+2], Vec2() } };
+        return { { ps_[i], ns_[i], ts_[i] }, { ps_[i+1], ns_[i+1], ts_[i+1] }, { ps_[i+2], ns_[i+2], ts_[i+2] } };
     }
     virtual InterpolatedPoint surface_point(int face, Vec2 uv) const override {
         const size_t i = size_t(face) * 3;
@@ -61,7 +65,7 @@ public:
             math::mix_barycentric(ps_[i], ps_[i+1], ps_[i+2], uv),
             glm::normalize(math::mix_barycentric(ns_[i], ns_[i+1], ns_[i+2], uv)),
             math::geometry_normal(ps_[i], ps_[i+1], ps_[i+2]),
-            Vec2()
+            math::mix_barycentric(ts_[i], ts_[i+1], ts_[i+2], uv)     // mesh_raw.cpp:94
         };
     }
     virtual int num_triangles() const override { return nf_; }
@@ -129,14 +133,40 @@ int lmref_scene_create(const LmcuSceneDesc* d, const char* accel_key, void** out
             meshes.push_back(lm::load<Mesh>("mesh" + std::to_string(i), "mesh::lmref_soup", {
                 {"num_faces", m.num_faces},
                 {"p", std::uintptr_t(m.p)},
-                {"n", std::uintptr_t(m.n)} }));
+                {"n", std::uintptr_t(m.n)},
+                {"t", std::uintptr_t(m.t)} }));
         }
+        std::vector<Texture*> textures;
+        for (int i = 0; i < d->num_textures; i++) {
+            const auto& t = d->textures[i];
+            if (!t.path) LM_THROW_EXCEPTION(Error::InvalidArgument, "texture without a file path");
+            textures.push_back(lm::load<Texture>("tex" + std::to_string(i), "texture::bitmap", { {"path", std::string(t.path)} }));
+        }
+        const auto tex_loc = [&](int map_kd) { return map_kd > 0 ? textures.at(map_kd - 1)->loc() : std::string(); };
         std::vector<Material*> mats;
         for (int i = 0; i < d->num_materials; i++) {
             const auto& m = d->materials[i];
             const auto name = "mat" + std::to_string(i);
             switch (m.type) {
-            case LMCU_MAT_DIFFUSE: mats.push_back(lm::load<Material>(name, "material::diffuse", { {"Kd", vec3(m.color)} })); break;
+            case LMCU_MAT_DIFFUSE: mats.push_back(lm::load<Material>(name, "material::diffuse", { {"Kd", vec3(m.color)}, {"mapKd", tex_loc(m.map_kd)} })); break;
+            case LMCU_MAT_MASK:    mats.push_back(lm::load<Material>(name, "material::mask", {})); break;
+            case LMCU_MAT_MIXTURE_OBJ:
+                mats.push_back(lm::load<Material>(name, "material::mixture_wavefrontobj", {
+                    {"Kd", vec3(m.color)}, {"mapKd", tex_loc(m.map_kd)}, {"Ks", vec3(m.Ks)}, {"ax", m.ax}, {"ay", m.ay},
+                    {"no_alpha_mask", !m.alpha_mask} }));
+                break;
+            case LMCU_MAT_MIXTURE_RR:
+            case LMCU_MAT_MIXTURE_MARGINALIZED: {
+                // entries refer to materials by index: they must precede the mixture in the table
+                Json entries = Json::array();
+                for (int k = 0; k < m.num_entries; k++) {
+                    if (m.entry_material[k] >= i) LM_THROW_EXCEPTION(Error::InvalidArgument, "mixture entries must precede the mixture");
+                    entries.push_back({ {"material", mats.at(m.entry_material[k])->loc()}, {"weight", m.entry_weight[k]} });
+                }
+                mats.push_back(lm::load<Material>(name, m.type == LMCU_MAT_MIXTURE_RR ? "material::constant_weight_mixture_rr"
+                                                                                       : "material::constant_weight_mixture_marginalized", entries));
+                break;
+            }
             case LMCU_MAT_GLOSSY:  mats.push_back(lm::load<Material>(name, "material::glossy", { {"Ks", vec3(m.color)}, {"ax", m.ax}, {"ay", m.ay} })); break;
             case LMCU_MAT_GLASS:   mats.push_back(lm::load<Material>(name, "material::glass", { {"Ni", m.Ni} })); break;
             case LMCU_MAT_MIRROR:  mats.push_back(lm::load<Material>(name, "material::mirror", {})); break;
@@ -201,6 +231,9 @@ int lmref_scene_create(const LmcuSceneDesc* d, const char* accel_key, void** out
 }
 
 void lmref_scene_destroy(void* s) { delete static_cast<RefScene*>(s); }
+
+// Locator of the lm::Scene asset (for hooks that look the scene up themselves, e.g. the plugin's probe test)
+const char* lmref_scene_loc(void* s) { return static_cast<RefScene*>(s)->scene_loc.c_str(); }
 
 // rays[i] -> Accel::intersect(ray, tmin, tmax) (include/lm/accel.h:70) under OpenMP.
 int lmref_accel_intersect(void* s, const LmcuRay* rays, int64_t n, LmcuHit* hits, double* seconds) {

@@ -26,6 +26,7 @@ struct SimScene {
     std::vector<TriF32> t32;
     std::vector<TriF64> t64;
     std::vector<TriShade> shade;
+    std::vector<TriUV> uv;
     bool fp32 = false;
     DevScene dev() const {
         DevScene d{};
@@ -34,6 +35,7 @@ struct SimScene {
         d.emit = ps.emit.data(); d.cdf = ps.cdf.data(); d.env_tex = ps.env_tex.data();
         d.num_prims = (int)ps.prims.size(); d.num_lights = (int)ps.lights.size(); d.env_light = ps.env_light;
         d.num_tris = ps.nt; d.cam = ps.cam;
+        d.uv = uv.empty() ? nullptr : uv.data(); d.textures = ps.textures.data(); d.texels = ps.texels.data(); d.mix = ps.mix.data();
         return d;
     }
 };
@@ -158,9 +160,11 @@ int hostsim_scene_create(const LmcuSceneDesc* d, int max_leaf, void** out, long 
     s->fp32 = exact;
     if (exact) s->t32.resize(nt); else s->t64.resize(nt);
     s->shade.resize(nt);
+    if (!s->ps.mesh_t.empty()) s->uv.resize(nt);
     for (uint32_t k = 0; k < nt; k++) {
         emit_body(k, tri_order.data(), s->ps.prims.data(), (int)s->ps.prims.size(), wp.data(), s->mesh_p.data(), s->mesh_n.data(),
-                  exact ? s->t32.data() : nullptr, exact ? nullptr : s->t64.data(), s->shade.data());
+                  exact ? s->t32.data() : nullptr, exact ? nullptr : s->t64.data(), s->shade.data(),
+                  s->uv.empty() ? nullptr : s->ps.mesh_t.data(), s->uv.empty() ? nullptr : s->uv.data());
     }
     if (num_nodes) *num_nodes = (long long)s->nodes.size();
     *out = s;
@@ -239,7 +243,7 @@ int hostsim_pt(void* p, const LmcuRenderParams* rp, float* film, long long* rays
             if (s.fp32) pt_trace<false, false, TriF32>(d, ro, rd, h, stack, nullptr); else pt_trace<false, false, TriF64>(d, ro, rd, h, stack, nullptr);
             rays++;
             const float4 hit = make_float4((float)h.t, (float)h.u, (float)h.v, u2f((uint32_t)h.tri));
-            const ShadeOut o = pt_shade_body(d, pp, ro, rd, tp, aux, info, hit);
+            const ShadeOut o = pt_shade_body<true>(d, pp, ro, rd, tp, aux, info, hit);
             const uint32_t pixel = f2u(tp.w);
             acc[pixel * 3 + 0] += o.emit.x; acc[pixel * 3 + 1] += o.emit.y; acc[pixel * 3 + 2] += o.emit.z;
             if (o.shadow) {

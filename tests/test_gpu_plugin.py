@@ -158,3 +158,24 @@ def test_renderer_pt_cuda_schedulers_and_image_mode(plugin):
     assert proc % 100000 == 0 and proc >= w * h * spp
     assert_pt_parity(fr, fti, spp, rel_mean=0.01)
     rs.close()
+
+
+@pytest.mark.parametrize("kind", ["obj", "mix"])
+def test_renderer_cuda_obj_material_set(plugin, tmp_path, kind):
+    """SURVEY.md 8f N2 through the drop-in boundary: texture::bitmap assets, mesh texture coordinates, material::mask,
+    material::mixture_wavefrontobj and the constant-weight mixtures are created by the reference from its own JSON, probed
+    by the plugin through the public component interfaces (tests/test_plugin_probe.py checks the probing on the CPU) and
+    rendered on the GPU."""
+    sb = scenes.textured_scene(tmp_path, 16, kind)
+    rs = plugin.RefScene(sb)
+    p = abi.render_params(192, 108)
+    fr, _, _ = rs.render("raycast", p)
+    fc, _, _ = rs.render("renderer::raycast_cuda", p)
+    d = np.abs(fc - fr).max(axis=2)
+    assert (d > 1e-4).mean() < 3e-3 and rmse(fc[d <= 1e-4], fr[d <= 1e-4]) <= 1e-6
+    p = abi.render_params(160, 90, spp=256, max_verts=12)
+    fr, _, pr = rs.render("pt", p)
+    fc, _, pc = rs.render("renderer::pt_cuda", p)
+    assert pr == pc == 256
+    assert_pt_parity(fr, fc, 256, rel_mean=0.015)
+    rs.close()

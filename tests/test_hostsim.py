@@ -100,6 +100,24 @@ def test_env_light_image(reference, sim, tmp_path):
     rs.close()
 
 
+@pytest.mark.parametrize("kind", ["obj", "mix"])
+def test_textured_and_mixture_materials(reference, sim, tmp_path, kind):
+    """mapKd textures, material::mixture_wavefrontobj (+ alpha mask), material::mask and the constant-weight mixtures:
+    the shading source against the reference before it reaches a GPU (tests/test_gpu_parity.py has the CUDA run)."""
+    sb = scenes.textured_scene(tmp_path, 12, kind)
+    rs, ss = reference.RefScene(sb), sim.SimScene(sb)
+    p = abi.render_params(192, 108)
+    fr, _, _ = rs.render("raycast", p)
+    fs = ss.render("raycast", p)
+    d = np.abs(fs - fr).max(axis=2)
+    assert (d > 1e-4).mean() < 3e-3 and rmse(fs[d <= 1e-4], fr[d <= 1e-4]) <= 1e-6
+    for mode in (abi.SAMPLING_MIS, abi.SAMPLING_NAIVE):
+        p = abi.render_params(96, 54, spp=96, max_verts=10, sampling_mode=mode)
+        fr, _, _ = rs.render("pt", p)
+        assert_pt_parity(fr, ss.render("pt", p), 96, rel_mean=0.02)
+    rs.close()
+
+
 def test_point_and_directional_lights(reference, sim):
     sb = scenes.delta_lights_scene(2, 12)
     rs, ss = reference.RefScene(sb), sim.SimScene(sb)
