@@ -13,6 +13,7 @@
 // library surfaces as lm::Exception).
 #include <lm/lm.h>
 
+#include <cstdio>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -526,6 +527,13 @@ public:
         transforms_ = std::move(ex.transforms);
     }
 
+    // Batched closest hit: n rays in, n hits out, one kernel launch.  Hit::primitive is the scene node
+    // index as in the scalar contract; the transform of that node is transforms_.at(primitive).
+    void intersect_batch(const LmcuRay* rays, long long n, LmcuHit* hits) const {
+        std::unique_lock<std::mutex> lk(mu_);
+        check(lmcu_accel_intersect(dev_.h, rays, n, hits));
+    }
+
     virtual std::optional<Hit> intersect(Ray ray, Float tmin, Float tmax) const override {
         LmcuRay r{ { ray.o.x, ray.o.y, ray.o.z }, { ray.d.x, ray.d.y, ray.d.z }, tmin, tmax };
         LmcuHit h{};
@@ -541,6 +549,107 @@ public:
 };
 
 LM_COMP_REG_IMPL(Accel_CudaBVH, "accel::cuda_bvh");
+
+// ------------------------------------------------------------------------------------------------
+
+/*
+\rst
+.. function:: film::cuda
+
+   Film whose pixels are the fp32 RGB buffer the CUDA renderers produce.
+
+   :param int w: Width of the film.
+   :param int h: Height of the film.
+
+   ``renderer::*_cuda`` write their result into it with ONE device-to-host copy; with ``film::bitmap`` the same result
+   goes through ``w*h`` ``set_pixel`` calls, each a compare-and-swap loop on a 24-byte atomic
+   (src/film/film_bitmap.cpp:41-54,152-154).  Everything else behaves like ``film::bitmap``: pixel (x, y) with y growing
+   upward, ``buffer()`` returns ``w*h*3`` Floats, ``save()`` writes .pfm itself and hands the other formats to a
+   temporary ``film::bitmap``.
+\endrst
+*/
+class Film_Cuda final : public Film {
+private:
+    int w_ = 0, h_ = 0;
+    std::vector<float> rgb_;                // [h][w][3], row 0 = bottom row (pixel y = 0)
+    std::vector<Float> temp_;               // buffer() view
+
+    static void atomic_add(float* p, float v) {
+        auto* a = reinterpret_cast<uint32_t*>(p);
+        uint32_t old = __atomic_load_n(a, __ATOMIC_RELAXED);
+        for (;;) {
+            float f; std::memcpy(&f, &old, 4);
+            f += v;
+            uint32_t nw; std::memcpy(&nw, &f, 4);
+            if (__atomic_compare_exchange_n(a, &old, nw, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) return;
+        }
+    }
+
+public:
+    virtual void construct(const Json& prop) override {
+        w_ = json::value<int>(prop, "w");
+        h_ = json::value<int>(prop, "h");
+        rgb_.assign(size_t(w_) * h_ * 3, 0.f);
+    }
+    // bulk interface of the CUDA renderers
+    float* data() { return rgb_.data(); }
+    size_t num_floats() const { return rgb_.size(); }
+
+    virtual FilmSize size() const override { return { w_, h_ }; }
+    virtual long long num_pixels() const override { return (long long)(w_) * h_; }
+    virtual void set_pixel(int x, int y, Vec3 v) override {
+        float* p = &rgb_[(size_t(y) * w_ + x) * 3];
+        p[0] = float(v.x); p[1] = float(v.y); p[2] = float(v.z);
+    }
+    virtual bool save(const std::string& outpath) const override {
+        const auto dot = outpath.find_last_of('.');
+        const std::string ext = dot == std::string::npos ? "" : outpath.substr(dot);
+        if (ext == ".pfm") {                                               // film_bitmap.cpp:62-80,197-203 (no flip)
+            FILE* f = std::fopen(outpath.c_str(), "wb");
+            if (!f) { LM_ERROR("Failed to open [file='{}']", outpath); return false; }
+            std::fprintf(f, "PF\n%d %d\n-1\n", w_, h_);
+            std::fwrite(rgb_.data(), 4, rgb_.size(), f);
+            std::fclose(f);
+            return true;
+        }
+        auto tmp = comp::create<Film>("film::bitmap", "", { {"w", w_}, {"h", h_} });
+        if (!tmp) return false;
+        for (int y = 0; y < h_; y++) for (int x = 0; x < w_; x++) {
+            const float* p = &rgb_[(size_t(y) * w_ + x) * 3];
+            tmp->set_pixel(x, y, Vec3(p[0], p[1], p[2]));
+        }
+        return tmp->save(outpath);
+    }
+    virtual FilmBuffer buffer() override {
+        temp_.assign(rgb_.begin(), rgb_.end());
+        return FilmBuffer{ w_, h_, temp_.data() };
+    }
+    virtual void accum(const Film* film_) override {
+        const auto* film = dynamic_cast<const Film_Cuda*>(film_);
+        if (!film || film->w_ != w_ || film->h_ != h_) {
+            LM_ERROR("Could not accumuate film. Invalid film type or size.");
+            return;
+        }
+        for (size_t i = 0; i < rgb_.size(); i++) rgb_[i] += film->rgb_[i];
+    }
+    virtual void splat_pixel(int x, int y, Vec3 v) override {
+        float* p = &rgb_[(size_t(y) * w_ + x) * 3];
+        atomic_add(p, float(v.x)); atomic_add(p + 1, float(v.y)); atomic_add(p + 2, float(v.z));
+    }
+    virtual void update_pixel(int x, int y, const PixelUpdateFunc& update_func) override {
+        float* p = &rgb_[(size_t(y) * w_ + x) * 3];
+        const Vec3 v = update_func(Vec3(p[0], p[1], p[2]));
+        p[0] = float(v.x); p[1] = float(v.y); p[2] = float(v.z);
+    }
+    virtual void rescale(Float s) override {
+        for (auto& v : rgb_) v = float(v * s);
+    }
+    virtual void clear() override {
+        rgb_.assign(rgb_.size(), 0.f);
+    }
+};
+
+LM_COMP_REG_IMPL(Film_Cuda, "film::cuda");
 
 // ------------------------------------------------------------------------------------------------
 
@@ -571,7 +680,16 @@ protected:
         dev_.upload(ex, device_);
     }
 
+    // Host destination of the device film: film::cuda's own pixel buffer (one copy), else a staging vector
+    float* film_target(std::vector<float>& staging) const {
+        if (auto* fc = dynamic_cast<Film_Cuda*>(film_)) return fc->data();
+        const auto size = film_->size();
+        staging.resize(size_t(size.w) * size.h * 3);
+        return staging.data();
+    }
+
     void write_film(const std::vector<float>& rgb, bool skip_black) const {
+        if (dynamic_cast<Film_Cuda*>(film_)) return;                       // already written in place
         const auto size = film_->size();
         for (int y = 0; y < size.h; y++) {
             for (int x = 0; x < size.w; x++) {
@@ -609,9 +727,9 @@ public:
         p.width = size.w; p.height = size.h; p.spp = 1;
         p.use_constant_color = use_constant_color_; p.visualize_normal = visualize_normal_; p.has_color = color_ ? 1 : 0;
         for (int i = 0; i < 3; i++) { p.bg_color[i] = bg_color_[i]; p.color[i] = color_ ? (*color_)[i] : 0_f; }
-        std::vector<float> rgb(size_t(size.w) * size.h * 3);
+        std::vector<float> rgb;
         LmcuRenderStats st{};
-        check(lmcu_render_raycast(dev_.h, &p, rgb.data(), &st));
+        check(lmcu_render_raycast(dev_.h, &p, film_target(rgb), &st));
         write_film(rgb, false);
         return { {"elapsed", st.elapsed} };
     }
@@ -635,9 +753,9 @@ public:
         const auto size = film_->size();
         LmcuRenderParams p{};
         p.width = size.w; p.height = size.h; p.spp = spp_; p.seed = unsigned(rng_seed_); p.ao_distance = .2_f;
-        std::vector<float> rgb(size_t(size.w) * size.h * 3);
+        std::vector<float> rgb;
         LmcuRenderStats st{};
-        check(lmcu_render_ao(dev_.h, &p, rgb.data(), &st));
+        check(lmcu_render_ao(dev_.h, &p, film_target(rgb), &st));
         write_film(rgb, false);
         return { {"elapsed", st.elapsed} };
     }
@@ -719,7 +837,8 @@ public:
         p.render_time = render_time_;
         p.samples_per_iter = samples_per_iter_;
         p.seed = seed_ ? *seed_ : math::rng_seed();
-        std::vector<float> rgb(size_t(size.w) * size.h * 3);
+        std::vector<float> rgb;
+        float* target = film_target(rgb);
         LmcuRenderStats st{};
         const int G = int(devices_.size());
         const bool image = primary_mode_ == LMCU_PRIMARY_IMAGE;
@@ -728,7 +847,7 @@ public:
             device_ = devices_[0];
             upload();
             p.spp = spp_; p.num_samples = num_samples_; p.rescale = 1;
-            check(lmcu_render_pt(dev_.h, &p, rgb.data(), &st));
+            check(lmcu_render_pt(dev_.h, &p, target, &st));
         }
         else {
             // Sample split: one host thread + one replicated device scene per GPU
@@ -780,7 +899,7 @@ public:
             // renderer_pt.cpp:307-312 on the combined film
             const double scale = image ? double(size.w) * size.h / double(st.processed) : 1.0 / double(st.processed);
             check(lmcu_film_reduce_peers(devs[0].h, peers.data(), int(peers.size()), scale));
-            check(lmcu_film_download(devs[0].h, rgb.data()));
+            check(lmcu_film_download(devs[0].h, target));
         }
         write_film(rgb, false);
         return { {"processed", st.processed}, {"elapsed", st.elapsed} };
@@ -790,6 +909,22 @@ public:
 LM_COMP_REG_IMPL(Renderer_PT_Cuda, "renderer::pt_cuda");
 
 LM_NAMESPACE_END(LM_NAMESPACE)
+
+// Batched rays for hosts that hold numpy / torch buffers (func_accel_consistency-style notebooks): `accel_loc` is the
+// locator of an accel::cuda_bvh asset that Scene::build() has built; rays / hits are the POD records of include/lmcu.h.
+// Returns 0, or -1 with the message in `err`.
+extern "C" int lm_cuda_accel_intersect_batch(const char* accel_loc, const LmcuRay* rays, long long n, LmcuHit* hits, char* err, int cap) {
+    try {
+        auto* accel = dynamic_cast<lm::Accel_CudaBVH*>(lm::comp::get<lm::Accel>(accel_loc));
+        if (!accel) throw std::runtime_error("not an accel::cuda_bvh asset");
+        accel->intersect_batch(rays, n, hits);
+        return 0;
+    }
+    catch (const std::exception& e) {
+        if (err && cap > 0) std::snprintf(err, size_t(cap), "%s", e.what());
+        return -1;
+    }
+}
 
 // Host-logic test hook (tests/test_plugin_probe.py): what the plugin recovers from an lm::Scene through the public
 // component interfaces, as JSON, without touching a GPU.  Returns the length written, or -1.

@@ -263,7 +263,9 @@ int lmref_render(void* s, const char* renderer_key, const LmcuRenderParams* p, d
                  double* elapsed, long long* processed) {
     return guarded([&] {
         auto* rs = static_cast<RefScene*>(s);
-        auto* film = lm::load<Film>("film", "film::bitmap", { {"w", p->width}, {"h", p->height} });
+        const char* film_key = std::getenv("LMREF_FILM");                  // tests: e.g. the plugin's film::cuda
+        auto* film = lm::load<Film>("film", film_key ? film_key : "film::bitmap", { {"w", p->width}, {"h", p->height} });
+        if (!film) LM_THROW_EXCEPTION(Error::InvalidArgument, "unknown film");
         static const char* modes[] = { "naive", "nee", "mis" };
         Json prop{
             {"scene", rs->scene_loc}, {"output", film->loc()},

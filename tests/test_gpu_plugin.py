@@ -179,3 +179,47 @@ def test_renderer_cuda_obj_material_set(plugin, tmp_path, kind):
     assert pr == pc == 256
     assert_pt_parity(fr, fc, 256, rel_mean=0.015)
     rs.close()
+
+
+def test_film_cuda_bulk_write_equals_set_pixel_path(plugin, monkeypatch):
+    """renderer::*_cuda -> film::cuda is ONE device-to-host copy into the film's own buffer; -> film::bitmap is w*h
+    set_pixel calls.  Same seed, same device film: the two must agree to the last bit (fp32 -> fp64 is exact)."""
+    sb = scenes.cornell_spheres(12)
+    rs = plugin.RefScene(sb)
+    p = abi.render_params(160, 90, spp=32, max_verts=10)
+    out = {}
+    for film in ("film::bitmap", "film::cuda"):
+        monkeypatch.setenv("LMREF_FILM", film)
+        out[film] = [rs.render(k, p)[0] for k in ("renderer::raycast_cuda", "renderer::ao_cuda", "renderer::pt_cuda")]
+    rs.close()
+    for a, b in zip(out["film::bitmap"], out["film::cuda"]):
+        assert a.max() > 0 and np.array_equal(a, b)
+
+
+def test_accel_cuda_bvh_batched_rays(plugin):
+    """SURVEY.md 8f N1: the batched entry of accel::cuda_bvh (numpy buffers in, hit records out, one launch) against
+    accel::sahbvh called ray by ray, func_accel_consistency style."""
+    import ctypes as C
+    sb = scenes.cornell_spheres(16)
+    rays = np.concatenate([scenes.camera_rays(sb.camera, 256, 144),
+                           scenes.random_rays(20000, np.array([-1, 0, -1.]), np.array([1, 2, 1.]))])
+    rs = plugin.RefScene(sb)
+    hr = rs.intersect(rays)
+    rs.close()
+    rc = plugin.RefScene(sb, accel="accel::cuda_bvh")
+    so = C.CDLL(PLUGIN + ".so")
+    hits = np.zeros(len(rays), dtype=scenes.HIT_DTYPE)
+    err = C.create_string_buffer(512)
+    rc_ = so.lm_cuda_accel_intersect_batch(b"$.assets.accel", rays.ctypes.data_as(C.c_void_p), C.c_longlong(len(rays)),
+                                           hits.ctypes.data_as(C.c_void_p), err, len(err))
+    assert rc_ == 0, err.value
+    # the harness numbers scene nodes in creation order; the batched entry reports SceneNode::index like Accel::Hit
+    hs = rc.intersect(rays[:3000])                       # scalar contract of the same accel, mapped to desc indices
+    rc.close()
+    same_geom = (hits["t"][:3000] == hs["t"]) & (hits["face"][:3000] == hs["face"])
+    assert same_geom.all()
+    hit_r, hit_c = hr["primitive"] >= 0, hits["primitive"] >= 0
+    assert (hit_r == hit_c).mean() > 0.999
+    both = hit_r & hit_c
+    agree = (hr["face"][both] == hits["face"][both]) & (hr["t"][both] == hits["t"][both])
+    assert agree.mean() > 0.995                          # the rest are exact ties on shared edges (see parity.py)

@@ -97,3 +97,22 @@ def test_constant_weight_mixtures(probe, tmp_path):
         for (gi, gw), (wi, ww) in zip(got["entries"], want["entries"]):
             assert mats[gi]["type"] == sb.materials[wi]["type"]
             assert abs(gw - ww) < 1e-6, (got["entries"], want["entries"])
+
+
+def test_film_cuda_behaves_like_film_bitmap(reference, probe, monkeypatch):
+    """film::cuda (the plugin's bulk-write film, SURVEY.md 8f N1) under the reference's OWN CPU renderers: set_pixel
+    (renderer::raycast) and concurrent splat (renderer::pt) must give what film::bitmap gives, through Film::buffer()."""
+    sb = scenes.cornell_spheres(8)
+    rs = reference.RefScene(sb)
+    p = abi.render_params(96, 54)
+    fb, _, _ = rs.render("raycast", p)
+    pp = abi.render_params(64, 36, spp=64, max_verts=8)
+    pb, _, _ = rs.render("pt", pp)
+    monkeypatch.setenv("LMREF_FILM", "film::cuda")
+    fc, _, _ = rs.render("raycast", p)
+    pc, _, nproc = rs.render("pt", pp)
+    rs.close()
+    assert np.abs(fc - fb).max() <= 1e-7 * max(1.0, np.abs(fb).max())      # fp32 pixels vs fp64 pixels
+    assert nproc == 64
+    from parity import assert_pt_parity
+    assert_pt_parity(pb, pc, 64, rel_mean=0.03)
