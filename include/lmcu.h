@@ -248,6 +248,16 @@ int lmcu_accel_intersect_device(LmcuScene* scene, const void* d_rays, int64_t n,
 int lmcu_accel_intersect_counted(LmcuScene* scene, const LmcuRay* rays, int64_t n, LmcuHit* hits,
                                  double* nodes_per_ray, double* tris_per_ray);
 
+/* Serialisation of the built accel: replaces Component::save / load of an Accel (include/lm/component.h:210-266;
+ * accel::sahbvh archives nodes_, trs_, indices_, src/accel/accel_sahbvh.cpp:122-124).  The blob holds the wide nodes, the
+ * triangles in leaf order, the shading records and the primitive table, with a checksum; lmcu_accel_load() restores them
+ * without running the builder.  On a scene WITH an uploaded description the blob must match it (triangle and primitive
+ * counts), and the renderers work as after lmcu_accel_build(); on a fresh scene the result serves lmcu_accel_intersect*
+ * only.  A blob is valid for the library version that wrote it. */
+int lmcu_accel_save_size(LmcuScene* scene, int64_t* bytes);
+int lmcu_accel_save(LmcuScene* scene, void* buffer, int64_t bytes);
+int lmcu_accel_load(LmcuScene* scene, const void* buffer, int64_t bytes);
+
 /* -- renderers: replace lm::Renderer::render (include/lm/renderer.h:25) ------------------------ */
 /* film_rgb: HOST buffer of width*height*3 floats, or NULL to keep the result only in the device film. */
 int lmcu_render_raycast(LmcuScene* scene, const LmcuRenderParams* p, float* film_rgb, LmcuRenderStats* stats);

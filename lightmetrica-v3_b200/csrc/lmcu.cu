@@ -762,6 +762,109 @@ int lmcu_accel_build(LmcuScene* s, const LmcuBuildOptions* opts, LmcuBuildStats*
     return LMCU_OK;
 }
 
+// -- save / load ----------------------------------------------------------------------------------------
+namespace {
+struct AccelBlobHeader {
+    char magic[8];                // "LMCUBVH1"
+    uint32_t version, fp32, nt, num_nodes, num_prims, has_uv;
+    uint64_t payload_bytes, checksum;
+};
+constexpr uint32_t kBlobVersion = 1;
+inline uint64_t fnv1a(const unsigned char* p, size_t n) {
+    uint64_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < n; i++) { h ^= p[i]; h *= 1099511628211ull; }
+    return h;
+}
+inline size_t blob_payload(const AccelBlobHeader& h) {
+    return (size_t)h.num_nodes * sizeof(WideNode) + (size_t)h.nt * (h.fp32 ? sizeof(TriF32) : sizeof(TriF64)) +
+           (size_t)h.nt * sizeof(TriShade) + (h.has_uv ? (size_t)h.nt * sizeof(TriUV) : 0) + (size_t)h.num_prims * sizeof(PrimDev);
+}
+}  // namespace
+
+int lmcu_accel_save_size(LmcuScene* s, int64_t* bytes) {
+    if (!s || !bytes) return fail(LMCU_ERR_INVALID_ARGUMENT, "null argument");
+    if (!s->built) return fail(LMCU_ERR_INVALID_ARGUMENT, "accel not built");
+    AccelBlobHeader h{};
+    h.fp32 = s->fp32; h.nt = s->nt; h.num_nodes = (uint32_t)s->nodes.n; h.num_prims = (uint32_t)s->num_prims; h.has_uv = s->uv.p ? 1 : 0;
+    *bytes = (int64_t)(sizeof(AccelBlobHeader) + blob_payload(h));
+    return LMCU_OK;
+}
+
+int lmcu_accel_save(LmcuScene* s, void* buffer, int64_t bytes) {
+    int64_t need = 0;
+    const int rc = lmcu_accel_save_size(s, &need);
+    if (rc) return rc;
+    if (!buffer || bytes < need) return fail(LMCU_ERR_INVALID_ARGUMENT, "buffer too small for the accel blob");
+    CU(cudaSetDevice(s->device));
+    CU(cudaStreamSynchronize(s->stream));
+    AccelBlobHeader h{};
+    memcpy(h.magic, "LMCUBVH1", 8);
+    h.version = kBlobVersion; h.fp32 = s->fp32; h.nt = s->nt; h.num_nodes = (uint32_t)s->nodes.n;
+    h.num_prims = (uint32_t)s->num_prims; h.has_uv = s->uv.p ? 1 : 0;
+    h.payload_bytes = blob_payload(h);
+    unsigned char* base = static_cast<unsigned char*>(buffer) + sizeof(AccelBlobHeader);
+    unsigned char* p = base;
+    const auto pull = [&](const void* d, size_t n) -> cudaError_t {
+        const cudaError_t e = n ? cudaMemcpy(p, d, n, cudaMemcpyDeviceToHost) : cudaSuccess;
+        p += n;
+        return e;
+    };
+    CU(pull(s->nodes.p, (size_t)h.num_nodes * sizeof(WideNode)));
+    if (h.fp32) CU(pull(s->t32.p, (size_t)h.nt * sizeof(TriF32))); else CU(pull(s->t64.p, (size_t)h.nt * sizeof(TriF64)));
+    CU(pull(s->shade.p, (size_t)h.nt * sizeof(TriShade)));
+    if (h.has_uv) CU(pull(s->uv.p, (size_t)h.nt * sizeof(TriUV)));
+    memcpy(p, s->h_prims.data(), (size_t)h.num_prims * sizeof(PrimDev));
+    h.checksum = fnv1a(base, h.payload_bytes);
+    memcpy(buffer, &h, sizeof(h));
+    return LMCU_OK;
+}
+
+int lmcu_accel_load(LmcuScene* s, const void* buffer, int64_t bytes) {
+    if (!s || !buffer) return fail(LMCU_ERR_INVALID_ARGUMENT, "null argument");
+    if (bytes < (int64_t)sizeof(AccelBlobHeader)) return fail(LMCU_ERR_INVALID_ARGUMENT, "accel blob: truncated header");
+    AccelBlobHeader h;
+    memcpy(&h, buffer, sizeof(h));
+    if (memcmp(h.magic, "LMCUBVH1", 8) != 0 || h.version != kBlobVersion) return fail(LMCU_ERR_INVALID_ARGUMENT, "accel blob: bad magic or version");
+    if (h.nt == 0 || h.num_nodes == 0 || h.payload_bytes != blob_payload(h) || bytes < (int64_t)(sizeof(h) + h.payload_bytes)) {
+        return fail(LMCU_ERR_INVALID_ARGUMENT, "accel blob: inconsistent sizes");
+    }
+    const unsigned char* base = static_cast<const unsigned char*>(buffer) + sizeof(h);
+    if (fnv1a(base, h.payload_bytes) != h.checksum) return fail(LMCU_ERR_INVALID_ARGUMENT, "accel blob: checksum mismatch");
+    const bool described = s->nt != 0;
+    if (described && (s->nt != h.nt || (uint32_t)s->num_prims != h.num_prims || (s->mesh_t.p != nullptr) != (h.has_uv != 0))) {
+        return fail(LMCU_ERR_INVALID_ARGUMENT, "accel blob does not belong to the uploaded scene");
+    }
+    CU(cudaSetDevice(s->device));
+    CU(cudaStreamSynchronize(s->stream));
+    const unsigned char* p = base;
+    const auto push = [&](void* d, size_t n) -> cudaError_t {
+        const cudaError_t e = n ? cudaMemcpy(d, p, n, cudaMemcpyHostToDevice) : cudaSuccess;
+        p += n;
+        return e;
+    };
+    s->built = false;
+    CU(s->nodes.alloc(h.num_nodes));
+    CU(push(s->nodes.p, (size_t)h.num_nodes * sizeof(WideNode)));
+    s->fp32 = h.fp32 != 0;
+    s->t32.release(); s->t64.release();
+    if (s->fp32) { CU(s->t32.alloc(h.nt)); CU(push(s->t32.p, (size_t)h.nt * sizeof(TriF32))); }
+    else { CU(s->t64.alloc(h.nt)); CU(push(s->t64.p, (size_t)h.nt * sizeof(TriF64))); }
+    CU(s->shade.alloc(h.nt));
+    CU(push(s->shade.p, (size_t)h.nt * sizeof(TriShade)));
+    CU(s->uv.alloc(h.has_uv ? h.nt : 0));
+    if (h.has_uv) CU(push(s->uv.p, (size_t)h.nt * sizeof(TriUV)));
+    if (!described) {
+        s->h_prims.resize(h.num_prims);
+        memcpy(s->h_prims.data(), p, (size_t)h.num_prims * sizeof(PrimDev));
+        CU(s->prims.alloc(h.num_prims));
+        CU(cudaMemcpy(s->prims.p, s->h_prims.data(), (size_t)h.num_prims * sizeof(PrimDev), cudaMemcpyHostToDevice));
+        s->nt = h.nt;
+        s->num_prims = (int)h.num_prims;
+    }
+    s->built = true;
+    return LMCU_OK;
+}
+
 // -- intersect ------------------------------------------------------------------------------------------
 // Picks the kernel instantiation for (triangle record, counters, triangles per iteration).
 #define LMCU_DISPATCH(KERNEL, FP32, COUNT, GRID, BLOCK, STREAM, ...)                                             \

@@ -21,7 +21,7 @@ _LIB = None
 EXPORTS = [
     "lmcu_last_error", "lmcu_device_count", "lmcu_version", "lmcu_scene_create", "lmcu_scene_destroy",
     "lmcu_scene_set_stream", "lmcu_scene_upload", "lmcu_accel_build", "lmcu_accel_intersect", "lmcu_accel_intersect_device",
-    "lmcu_accel_intersect_counted", "lmcu_render_raycast", "lmcu_render_ao", "lmcu_render_pt",
+    "lmcu_accel_intersect_counted", "lmcu_accel_save_size", "lmcu_accel_save", "lmcu_accel_load", "lmcu_render_raycast", "lmcu_render_ao", "lmcu_render_pt",
     "lmcu_film_device_ptr", "lmcu_film_rescale", "lmcu_film_download",
     "lmcu_film_ipc_export", "lmcu_ipc_open", "lmcu_ipc_close", "lmcu_enable_peer_access", "lmcu_film_reduce_peers",
 ]
@@ -73,17 +73,33 @@ def enable_peer_access(device, peer_device):
 class Scene:
     """accel::cuda_bvh + renderer::{raycast,ao,pt}_cuda over one uploaded scene on one GPU."""
 
-    def __init__(self, builder, device=0, max_leaf_tris=3):
+    def __init__(self, builder=None, device=0, max_leaf_tris=3, accel_blob=None):
+        """builder: scene description (None = accel-only scene restored from `accel_blob`).  accel_blob: bytes written by
+        save_accel(); when given, the BVH is loaded instead of built (Component::save / load of an Accel)."""
         self._builder = builder
-        self._desc = builder.desc()
         self._h = C.c_void_p()
         _check(lib().lmcu_scene_create(int(device), C.byref(self._h)))
-        _check(lib().lmcu_scene_upload(self._h, C.byref(self._desc)))
-        opts = abi.LmcuBuildOptions()
-        opts.max_leaf_tris = max_leaf_tris
+        if builder is not None:
+            self._desc = builder.desc()
+            _check(lib().lmcu_scene_upload(self._h, C.byref(self._desc)))
+        elif accel_blob is None:
+            raise LmcuError(1, "Scene needs a scene description or an accel blob")
         self.build_stats = abi.LmcuBuildStats()
-        _check(lib().lmcu_accel_build(self._h, C.byref(opts), C.byref(self.build_stats)))
+        if accel_blob is not None:
+            _check(lib().lmcu_accel_load(self._h, C.c_char_p(bytes(accel_blob)), C.c_int64(len(accel_blob))))
+        else:
+            opts = abi.LmcuBuildOptions()
+            opts.max_leaf_tris = max_leaf_tris
+            _check(lib().lmcu_accel_build(self._h, C.byref(opts), C.byref(self.build_stats)))
         self.last_stats = None
+
+    def save_accel(self):
+        """The built BVH as bytes (wide nodes, leaf-ordered triangles, shading records, primitive table, checksum)."""
+        n = C.c_int64()
+        _check(lib().lmcu_accel_save_size(self._h, C.byref(n)))
+        buf = C.create_string_buffer(n.value)
+        _check(lib().lmcu_accel_save(self._h, buf, n))
+        return buf.raw
 
     # -- Accel ------------------------------------------------------------------------------------
     def intersect(self, rays, counted=False):

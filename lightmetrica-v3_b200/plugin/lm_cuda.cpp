@@ -518,6 +518,38 @@ public:
         device_ = json::value<int>(prop, "device", 0);
     }
 
+    // Component::save / load (include/lm/component.h:210-236), the counterpart of accel::sahbvh archiving nodes_, trs_,
+    // indices_ (accel_sahbvh.cpp:122-124): the device BVH travels as the blob of lmcu_accel_save(), so a loaded state
+    // answers intersect() without rebuilding.  NOTE: this image has no cereal (oracle/shim/cereal provides no-op archives),
+    // so these two functions are compiled but never exercised here; the blob itself is round-tripped through the C ABI
+    // in tests/test_gpu_parity.py::test_accel_save_load_round_trip.
+    virtual void save(OutputArchive& ar) override {
+        std::vector<unsigned char> blob;
+        if (dev_.h) {
+            int64_t n = 0;
+            check(lmcu_accel_save_size(dev_.h, &n));
+            blob.resize(size_t(n));
+            check(lmcu_accel_save(dev_.h, blob.data(), n));
+        }
+        std::vector<int> keys;
+        std::vector<Transform> values;
+        for (const auto& [k, v] : transforms_) { keys.push_back(k); values.push_back(v); }
+        ar(device_, blob, keys, values);
+    }
+
+    virtual void load(InputArchive& ar) override {
+        std::vector<unsigned char> blob;
+        std::vector<int> keys;
+        std::vector<Transform> values;
+        ar(device_, blob, keys, values);
+        transforms_.clear();
+        for (size_t i = 0; i < keys.size() && i < values.size(); i++) transforms_.emplace(keys[i], values[i]);
+        if (blob.empty()) return;
+        if (dev_.h) { lmcu_scene_destroy(dev_.h); dev_.h = nullptr; }
+        check(lmcu_scene_create(device_, &dev_.h));
+        check(lmcu_accel_load(dev_.h, blob.data(), int64_t(blob.size())));
+    }
+
     virtual void build(const Scene& scene) override {
         LM_INFO("Flattening scene");
         SceneExport ex;

@@ -24,12 +24,22 @@ def test_header_symbols_are_exported():
     assert sorted(api.EXPORTS) == names
 
 
-def test_struct_sizes_match_header():
+def test_struct_sizes_match_header(tmp_path):
+    """Every POD struct of include/lmcu.h has the same size in the ctypes mirror as gcc gives it (layout drift between
+    the header and lmcu/abi.py would corrupt scene descriptions silently)."""
+    import subprocess
     from lmcu import abi
+    names = ["LmcuRay", "LmcuHit", "LmcuMesh", "LmcuPrimitive", "LmcuTexture", "LmcuMaterial", "LmcuLight", "LmcuCamera",
+             "LmcuSceneDesc", "LmcuRenderParams", "LmcuRenderStats", "LmcuBuildOptions", "LmcuBuildStats"]
+    src = tmp_path / "sizes.c"
+    src.write_text('#include <stdio.h>\n#include "lmcu.h"\nint main(void) {\n' +
+                   "".join('  printf("%s %%zu\\n", sizeof(%s));\n' % (n, n) for n in names) + "  return 0;\n}\n")
+    exe = tmp_path / "sizes"
+    subprocess.check_call(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    sizes = dict(line.split() for line in subprocess.check_output([str(exe)]).decode().splitlines())
+    for n in names:
+        assert C.sizeof(getattr(abi, n)) == int(sizes[n]), n
     assert C.sizeof(abi.LmcuRay) == 64 and C.sizeof(abi.LmcuHit) == 32
-    assert C.sizeof(abi.LmcuPrimitive) == 16 + 128
-    assert C.sizeof(abi.LmcuMaterial) == 8 + 24 + 24
-    assert C.sizeof(abi.LmcuCamera) == 88
     from lmcu.scenes import HIT_DTYPE, RAY_DTYPE
     assert RAY_DTYPE.itemsize == 64 and HIT_DTYPE.itemsize == 32
 

@@ -106,6 +106,40 @@ def test_g1_instanced_transforms(reference):
     rs.close(); sc.close()
 
 
+def test_accel_save_load_round_trip(tmp_path):
+    """SURVEY.md 8f N4 (Component::save / load of an Accel): the built BVH written by lmcu_accel_save and restored by
+    lmcu_accel_load (a) into a scene with the same description: hits AND a pt render identical to the built scene's, no
+    builder run; (b) into a fresh accel-only scene: identical hits; (c) a corrupted, truncated or foreign blob is refused."""
+    for sb in (scenes.cornell_spheres(16), scenes.cornell_box(True), scenes.textured_scene(tmp_path, 8, "obj")):
+        rays = np.concatenate([scenes.camera_rays(sb.camera, 128, 72), scenes.random_rays(4000, np.array([-1, 0, -1.]), np.array([1, 2, 1.]))])
+        a = lmcu.Scene(sb)
+        blob = a.save_accel()
+        ha = a.intersect(rays)
+        p = abi.render_params(96, 54, spp=8, max_verts=8)
+        fa, _ = a.render("pt", p)
+        a.close()
+        b = lmcu.Scene(sb, accel_blob=blob)
+        assert b.build_stats.elapsed == 0.0
+        hb = b.intersect(rays)
+        fb, _ = b.render("pt", p)
+        b.close()
+        c = lmcu.Scene(None, accel_blob=blob)
+        hc = c.intersect(rays)
+        c.close()
+        for h in (hb, hc):
+            assert all(np.array_equal(ha[k], h[k]) for k in ("t", "u", "v", "primitive", "face"))
+        assert np.array_equal(fa, fb)                      # same seed, same traversal order, same film
+    bad = bytearray(blob)
+    bad[len(bad) // 2] ^= 0x40
+    for broken in (bytes(bad), blob[:len(blob) // 2], b"not a blob" * 20):
+        with pytest.raises(lmcu.LmcuError) as e:
+            lmcu.Scene(None, accel_blob=broken)
+        assert e.value.code == 1
+    with pytest.raises(lmcu.LmcuError) as e:           # a blob of another scene
+        lmcu.Scene(scenes.cornell_box(), accel_blob=blob)
+    assert e.value.code == 1
+
+
 def test_empty_batch_and_errors():
     sb = scenes.cornell_box()
     sc = lmcu.Scene(sb)
