@@ -330,16 +330,18 @@ struct BatchIO {                       // accel batches: LmcuRay in, LmcuHit out
         tmin_dn = f32_down(r.tmin); tmax_up = f32_up(r.tmax);
         return true;
     }
-    __device__ __forceinline__ void store(uint32_t i, const RayD&, const HitD& h) const {
+    __device__ __forceinline__ void store(uint32_t i, double t, double u_raw, double v_raw, double ad, int32_t tri) const {
         int32_t prim = -1, face = -1;
-        if (h.tri >= 0) {
+        double u = 0.0, v = 0.0;
+        if (tri >= 0) {
             F3 p1, p2, p3; int32_t pi;
-            tri_fetch(s, (uint32_t)h.tri, p1, p2, p3, pi, face);
+            tri_fetch(s, (uint32_t)tri, p1, p2, p3, pi, face);
             prim = s.prims[pi].node_index;
+            u = divrn(u_raw, ad); v = divrn(v_raw, ad);         // accel_sahbvh.cpp:74, the same IEEE quotients
         }
         double2* dst = reinterpret_cast<double2*>(hits + i);
-        dst[0] = make_double2(h.t, h.u);
-        double2 o2; o2.x = h.v;
+        dst[0] = make_double2(t, u);
+        double2 o2; o2.x = v;
         const int2 pf = make_int2(prim, face);
         memcpy(&o2.y, &pf, 8);
         dst[1] = o2;
@@ -366,8 +368,11 @@ struct ExtendIO {                      // pt extend: path queue in, float4 hit r
         tmin_dn = o.w; tmax_up = d.w;
         return true;
     }
-    __device__ __forceinline__ void store(uint32_t i, const RayD&, const HitD& h) const {
-        hits[i] = make_float4((float)h.t, (float)h.u, (float)h.v, __int_as_float(h.tri));
+    __device__ __forceinline__ void store(uint32_t i, double t, double u_raw, double v_raw, double ad, int32_t tri) const {
+        // the path tracer shades in FP32: the barycentrics are formed in FP32 here (two FP64 divisions cost ~60
+        // instructions at the 2-3 lanes that finish per iteration, 14 % of this kernel's issue slots)
+        const float inv = tri >= 0 ? __frcp_rn((float)ad) : 0.f;
+        hits[i] = make_float4((float)t, (float)u_raw * inv, (float)v_raw * inv, __int_as_float(tri));
     }
 };
 
@@ -389,8 +394,8 @@ struct ShadowIO {                      // pt shadow: visible (include/lm/scene.h
         tmin_dn = o.w; tmax_up = d.w;
         return true;
     }
-    __device__ __forceinline__ void store(uint32_t i, const RayD&, const HitD& h) const {
-        if (h.tri < 0) {
+    __device__ __forceinline__ void store(uint32_t i, double, double, double, double, int32_t tri) const {
+        if (tri < 0) {
             const float4 c = contrib[i];
             float* px = film + (size_t)__float_as_uint(c.w) * 3;
             atomicAdd(px + 0, c.x); atomicAdd(px + 1, c.y); atomicAdd(px + 2, c.z);

@@ -17,7 +17,8 @@
 //
 // IO policy (template parameter), all device functions:
 //     bool load(uint32_t i, RayD& r, RayF& f, float& tmin_dn, float& tmax_up)   ray i of the queue, FP64 + FP32 views
-//     void store(uint32_t i, const RayD& r, const HitD& h) result of ray i (h.tri < 0 = miss)
+//     void store(uint32_t i, double t, double u_raw, double v_raw, double ad, int32_t tri)
+//                                                          result of ray i (tri < 0 = miss); u = u_raw / ad, v = v_raw / ad
 #pragma once
 #include "bvh.cuh"
 
@@ -103,12 +104,9 @@ __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, 
                         tgroup.x = n1.y;
                         tgroup.y = hm & 0x00ffffffu;
                     } else {
-                        // ---- nothing left: this ray is done
-                        HitD h;
-                        h.t = ht; h.tri = htri;
-                        h.u = htri >= 0 ? divrn(hu, had) : 0.0;
-                        h.v = htri >= 0 ? divrn(hv, had) : 0.0;
-                        io.store(idx, r, h);
+                        // ---- nothing left: this ray is done.  The IO policy finishes the barycentrics (u, v = raw / |det|):
+                        // only a few lanes are here at a time, so what it costs is paid at ~3/32 occupancy
+                        io.store(idx, ht, hu, hv, had, htri);
                         active = false;
                     }
                 }
@@ -134,9 +132,7 @@ __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, 
                             ht = t; hu = u; hv = v; had = ad; htri = (int32_t)tri;
                             tmax_up = f32_up(t);
                             if (ANY) {
-                                HitD h;
-                                h.t = t; h.tri = htri; h.u = divrn(u, ad); h.v = divrn(v, ad);
-                                io.store(idx, r, h);
+                                io.store(idx, t, u, v, ad, htri);
                                 active = false;
                             }
                         }
