@@ -208,7 +208,7 @@ typedef struct LmcuRenderStats {
 } LmcuRenderStats;
 
 typedef struct LmcuBuildOptions {
-    int32_t max_leaf_tris;                   /* 1..3 triangles per leaf slot (default 3) */
+    int32_t max_leaf_tris;                   /* 1..3 triangles per leaf slot (0 = default 2) */
     int32_t reserved_[7];
 } LmcuBuildOptions;
 

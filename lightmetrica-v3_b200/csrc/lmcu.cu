@@ -319,6 +319,7 @@ __global__ void __launch_bounds__(256, LMCU_SHADE_MINB) k_pt_shade(DevScene s, P
 // -- queue kernels on the warp-persistent traversal (trace.cuh) -----------------------------------------
 
 struct BatchIO {                       // accel batches: LmcuRay in, LmcuHit out (include/lmcu.h)
+    static constexpr bool kExactT = true;
     DevScene s;
     const LmcuRay* rays;
     LmcuHit* hits;
@@ -359,6 +360,7 @@ __global__ void __launch_bounds__(128, LMCU_MINB) k_intersect_q(DevScene s, cons
 }
 
 struct ExtendIO {                      // pt extend: path queue in, float4 hit record out
+    static constexpr bool kExactT = false;
     const float4* ray_o; const float4* ray_d;
     float4* hits;
     __device__ __forceinline__ bool load(uint32_t i, RayD& r, RayF& f, float& tmin_dn, float& tmax_up) const {
@@ -385,6 +387,7 @@ __global__ void __launch_bounds__(128, LMCU_MINB) k_pt_extend_q(DevScene s, Path
 }
 
 struct ShadowIO {                      // pt shadow: visible (include/lm/scene.h:343-364) => splat the NEE contribution
+    static constexpr bool kExactT = false;
     const float4* ray_o; const float4* ray_d; const float4* contrib;
     float* film;
     __device__ __forceinline__ bool load(uint32_t i, RayD& r, RayF& f, float& tmin_dn, float& tmax_up) const {
@@ -664,7 +667,7 @@ int lmcu_accel_build(LmcuScene* s, const LmcuBuildOptions* opts, LmcuBuildStats*
     if (s->nt == 0) return fail(LMCU_ERR_UNSUPPORTED, "Missing primitives.");
     CU(cudaSetDevice(s->device));
     const uint32_t nt = s->nt;
-    int max_leaf = opts && opts->max_leaf_tris ? opts->max_leaf_tris : 3;
+    int max_leaf = opts && opts->max_leaf_tris ? opts->max_leaf_tris : 2;
     if (const char* e = getenv("LMCU_LEAF")) max_leaf = atoi(e);      // tuning only
     if (max_leaf < 1 || max_leaf > 3) return fail(LMCU_ERR_INVALID_ARGUMENT, "max_leaf_tris must be in 1..3");
     cudaStream_t st = s->stream;

@@ -17,6 +17,7 @@
 //
 // IO policy (template parameter), all device functions:
 //     bool load(uint32_t i, RayD& r, RayF& f, float& tmin_dn, float& tmax_up)   ray i of the queue, FP64 + FP32 views
+//     static constexpr bool kExactT                        true: t is the IEEE quotient of accel_sahbvh.cpp:70 (bit-exact hits)
 //     void store(uint32_t i, double t, double u_raw, double v_raw, double ad, int32_t tri)
 //                                                          result of ray i (tri < 0 = miss); u = u_raw / ad, v = v_raw / ad
 #pragma once
@@ -26,6 +27,14 @@ namespace lmcu {
 
 #if defined(__CUDACC__)
 
+
+// 1/d with relative error ~2^-46: MUFU.RCP64H seed (2^-23) and one Newton step
+__device__ __forceinline__ double rcp_newton(double d) {
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+    const double e = fma(-d, x, 1.0);
+    return fma(x, e, x);
+}
 
 template <bool ANY, bool COUNT, typename TriT, typename IO>
 __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, const TriT* __restrict__ tris,
@@ -127,7 +136,10 @@ __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, 
                     const double u = mul_sign_of(ddot(tv, p), d);
                     const double v = mul_sign_of(ddot(r.d, q), d);
                     if (!(ad < 1e-8 || u < 0.0 || v < 0.0 || addrn(u, v) > ad)) {
-                        const double t = divrn(ddot(e2, q), d);
+                        // accel batches: the reference's IEEE quotient.  Path-tracer queues (their hit record is FP32): a
+                        // Newton-refined reciprocal, relative error 2^-46 — the exact division is ~30 instructions that
+                        // run at the 3-4 lanes whose triangle passed the barycentric test.
+                        const double t = IO::kExactT ? divrn(ddot(e2, q), d) : mulrn(ddot(e2, q), rcp_newton(d));
                         if (!(t < r.tmin || ht < t)) {          // inclusive bounds; a later equal-t triangle wins
                             ht = t; hu = u; hv = v; had = ad; htri = (int32_t)tri;
                             tmax_up = f32_up(t);
@@ -151,7 +163,9 @@ __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, 
 
 }  // namespace lmcu
 
-// Variants measured and dropped (profiles/r01_ncu_summary_v2.md, gpurun logs of round 1): warp-private chunks of 32..128
+// Variants measured and dropped (profiles/r01_ncu_summary_v2.md, gpurun logs of round 1): the FP64 triangle test of the
+// path-tracer queues with fused multiply-adds (14 fewer FP64 instructions, but the DFMA chains are longer than the
+// independent DMULs they replace: extend +4 % time, 1296 vs 1321 Mpaths/s on C2); warp-private chunks of 32..128
 // rays claimed with one atomic, the next chunk claimed in advance and prefetched toward L2 (-3 % on C2 pt, 1195 vs 1232
 // Mpaths/s at 256 spp, for every refill threshold 4..16: the atomic's latency is already covered by the scheduler's other
 // warps, whole-chunk tails at the end of each launch are not; chunk 128 lost 30 % on a 2 M-ray batch); 3 triangle tests

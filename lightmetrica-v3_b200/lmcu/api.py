@@ -73,7 +73,7 @@ def enable_peer_access(device, peer_device):
 class Scene:
     """accel::cuda_bvh + renderer::{raycast,ao,pt}_cuda over one uploaded scene on one GPU."""
 
-    def __init__(self, builder=None, device=0, max_leaf_tris=3, accel_blob=None):
+    def __init__(self, builder=None, device=0, max_leaf_tris=0, accel_blob=None):
         """builder: scene description (None = accel-only scene restored from `accel_blob`).  accel_blob: bytes written by
         save_accel(); when given, the BVH is loaded instead of built (Component::save / load of an Accel)."""
         self._builder = builder
