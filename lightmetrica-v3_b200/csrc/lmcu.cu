@@ -21,8 +21,11 @@
 #include "kernels.cuh"
 #include "trace.cuh"
 
+#ifndef LMCU_SHADE_BLOCK
+#define LMCU_SHADE_BLOCK 256   // threads per CTA of the shade kernel
+#endif
 #ifndef LMCU_SHADE_MINB
-#define LMCU_SHADE_MINB 3  // resident 256-thread CTAs per SM the shade kernel is compiled for
+#define LMCU_SHADE_MINB 3  // resident CTAs per SM the shade kernel is compiled for
 #endif
 #ifndef LMCU_MINB
 #define LMCU_MINB 6      // resident 128-thread CTAs per SM the queue kernels are compiled for (register budget)
@@ -281,7 +284,7 @@ __device__ __forceinline__ void block_compact2(bool p0, bool p1, uint32_t* count
 }
 
 template <bool COMPOSITE>
-__global__ void __launch_bounds__(256, LMCU_SHADE_MINB) k_pt_shade(DevScene s, PtParams p, PathQueue qin, PathQueue qout, ShadowQueue sq,
+__global__ void __launch_bounds__(LMCU_SHADE_BLOCK, LMCU_SHADE_MINB) k_pt_shade(DevScene s, PtParams p, PathQueue qin, PathQueue qout, ShadowQueue sq,
                                                   const float4* hits, float* film, PtCounters* ctr, int cur) {
     __shared__ uint32_t smem[34];
     const uint32_t n = ctr->count[cur];
@@ -331,6 +334,7 @@ struct BatchIO {                       // accel batches: LmcuRay in, LmcuHit out
         tmin_dn = f32_down(r.tmin); tmax_up = f32_up(r.tmax);
         return true;
     }
+    __device__ __forceinline__ void prefetch(uint32_t i) const { prefetch_l2(rays + i); }
     __device__ __forceinline__ void store(uint32_t i, double t, double u_raw, double v_raw, double ad, int32_t tri) const {
         int32_t prim = -1, face = -1;
         double u = 0.0, v = 0.0;
@@ -370,6 +374,7 @@ struct ExtendIO {                      // pt extend: path queue in, float4 hit r
         tmin_dn = o.w; tmax_up = d.w;
         return true;
     }
+    __device__ __forceinline__ void prefetch(uint32_t i) const { prefetch_l2(ray_o + i); prefetch_l2(ray_d + i); }
     __device__ __forceinline__ void store(uint32_t i, double t, double u_raw, double v_raw, double ad, int32_t tri) const {
         // the path tracer shades in FP32: the barycentrics are formed in FP32 here (two FP64 divisions cost ~60
         // instructions at the 2-3 lanes that finish per iteration, 14 % of this kernel's issue slots)
@@ -397,6 +402,7 @@ struct ShadowIO {                      // pt shadow: visible (include/lm/scene.h
         tmin_dn = o.w; tmax_up = d.w;
         return true;
     }
+    __device__ __forceinline__ void prefetch(uint32_t i) const { prefetch_l2(ray_o + i); prefetch_l2(ray_d + i); }
     __device__ __forceinline__ void store(uint32_t i, double, double, double, double, int32_t tri) const {
         if (tri < 0) {
             const float4 c = contrib[i];
@@ -545,6 +551,7 @@ struct LmcuScene {
     uint32_t pt_capacity = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int fetch_threshold = 16;            // LMCU_FETCH
+    int shade_ctas_per_sm = 3;                   // LMCU_SHADE_GRID: CTAs per SM in the shade kernel's grid-stride grid
     int ctas_per_sm = LMCU_MINB;                 // LMCU_CTAS: resident 128-thread CTAs per SM for the persistent traversal grids
 
     DevScene dev() const {
@@ -585,6 +592,7 @@ int lmcu_scene_create(int device, LmcuScene** out) {
     CU(cudaEventCreate(&s->ev1));
     if (const char* e = getenv("LMCU_FETCH")) s->fetch_threshold = atoi(e);
     if (const char* e = getenv("LMCU_CTAS")) s->ctas_per_sm = std::max(1, atoi(e));
+    if (const char* e = getenv("LMCU_SHADE_GRID")) s->shade_ctas_per_sm = std::max(1, atoi(e));
     CU(s->cursor.alloc(8));
     CU(s->flags.alloc(4));
     CU(cudaMemset(s->cursor.p, 0, 8 * sizeof(unsigned long long)));
@@ -1149,7 +1157,7 @@ static int pt_pass(LmcuScene* s, const PtParams& pp, bool count, PtAccum& acc) {
     CU(cudaMemsetAsync(s->pt_ctr.p, 0, sizeof(PtCounters), st));
     const DevScene d = s->dev();
     const unsigned q_blocks = (unsigned)(s->num_sms * s->ctas_per_sm);
-    const unsigned shade_blocks = (unsigned)s->num_sms * 6, gen_blocks = (unsigned)s->num_sms * 4;
+    const unsigned shade_blocks = (unsigned)(s->num_sms * s->shade_ctas_per_sm), gen_blocks = (unsigned)s->num_sms * 4;
     int cur = 0;
     PtCounters h{};
     const int kGroup = 4;                       // iterations between host checks
@@ -1165,8 +1173,8 @@ static int pt_pass(LmcuScene* s, const PtParams& pp, bool count, PtAccum& acc) {
             cudaEventRecord(ev[0], st);
             LMCU_DISPATCH(k_pt_extend_q, s->fp32, count, q_blocks, 128, st, d, q[cur], s->hits.p, s->pt_ctr.p, cur);
             cudaEventRecord(ev[1], st);
-            if (s->composite) k_pt_shade<true><<<shade_blocks, 256, 0, st>>>(d, pp, q[cur], q[cur ^ 1], sq, s->hits.p, s->film.p, s->pt_ctr.p, cur);
-            else k_pt_shade<false><<<shade_blocks, 256, 0, st>>>(d, pp, q[cur], q[cur ^ 1], sq, s->hits.p, s->film.p, s->pt_ctr.p, cur);
+            if (s->composite) k_pt_shade<true><<<shade_blocks, LMCU_SHADE_BLOCK, 0, st>>>(d, pp, q[cur], q[cur ^ 1], sq, s->hits.p, s->film.p, s->pt_ctr.p, cur);
+            else k_pt_shade<false><<<shade_blocks, LMCU_SHADE_BLOCK, 0, st>>>(d, pp, q[cur], q[cur ^ 1], sq, s->hits.p, s->film.p, s->pt_ctr.p, cur);
             cudaEventRecord(ev[2], st);
             LMCU_DISPATCH(k_pt_shadow_q, s->fp32, count, q_blocks, 128, st, d, sq, s->film.p, s->pt_ctr.p);
             cudaEventRecord(ev[3], st);
