@@ -334,7 +334,6 @@ struct BatchIO {                       // accel batches: LmcuRay in, LmcuHit out
         tmin_dn = f32_down(r.tmin); tmax_up = f32_up(r.tmax);
         return true;
     }
-    __device__ __forceinline__ void prefetch(uint32_t i) const { prefetch_l2(rays + i); }
     __device__ __forceinline__ void store(uint32_t i, double t, double u_raw, double v_raw, double ad, int32_t tri) const {
         int32_t prim = -1, face = -1;
         double u = 0.0, v = 0.0;
@@ -374,7 +373,6 @@ struct ExtendIO {                      // pt extend: path queue in, float4 hit r
         tmin_dn = o.w; tmax_up = d.w;
         return true;
     }
-    __device__ __forceinline__ void prefetch(uint32_t i) const { prefetch_l2(ray_o + i); prefetch_l2(ray_d + i); }
     __device__ __forceinline__ void store(uint32_t i, double t, double u_raw, double v_raw, double ad, int32_t tri) const {
         // the path tracer shades in FP32: the barycentrics are formed in FP32 here (two FP64 divisions cost ~60
         // instructions at the 2-3 lanes that finish per iteration, 14 % of this kernel's issue slots)
@@ -402,7 +400,6 @@ struct ShadowIO {                      // pt shadow: visible (include/lm/scene.h
         tmin_dn = o.w; tmax_up = d.w;
         return true;
     }
-    __device__ __forceinline__ void prefetch(uint32_t i) const { prefetch_l2(ray_o + i); prefetch_l2(ray_d + i); }
     __device__ __forceinline__ void store(uint32_t i, double, double, double, double, int32_t tri) const {
         if (tri < 0) {
             const float4 c = contrib[i];
@@ -752,8 +749,12 @@ int lmcu_accel_build(LmcuScene* s, const LmcuBuildOptions* opts, LmcuBuildStats*
     int h_exact = 0;
     CU(cudaMemcpyAsync(&h_exact, exact.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    s->fp32 = h_exact != 0;
-    if (getenv("LMCU_TRI64")) s->fp32 = false;                        // tuning only: force the 80-byte FP64 triangle records
+    // 48-byte float records when every vertex is float-representable AND the triangle array is too large to stay in
+    // cache (C3: 480 MB instead of 800 MB streamed from HBM).  A small scene keeps the 80-byte FP64 records: they are
+    // served by L1 / L2 either way and spare the 9 F2F.F64.F32 per triangle test, the largest stall site of the extend
+    // kernel (profiles/r01_ncu_summary_v6.md; C2 pt 1322 -> 1340 Mpaths/s).
+    s->fp32 = h_exact != 0 && (size_t)nt * sizeof(TriF64) > (size_t(48) << 20);
+    if (const char* e = getenv("LMCU_TRI64")) s->fp32 = h_exact != 0 && atoi(e) == 0;   // tuning only: 1 = FP64 records, 0 = float records
     s->t32.release(); s->t64.release();
     if (s->fp32) CU(s->t32.alloc(nt)); else CU(s->t64.alloc(nt));
     CU(s->shade.alloc(nt));

@@ -27,12 +27,6 @@ namespace lmcu {
 
 #if defined(__CUDACC__)
 
-#ifndef LMCU_PF_RAY
-#define LMCU_PF_RAY 0        // ray-queue L2 prefetch distance in rays (0 = off)
-#endif
-#ifndef LMCU_PF_NODE
-#define LMCU_PF_NODE 0       // 1 = L1 prefetch of the next child node at the end of a node step
-#endif
 
 // 1/d with relative error ~2^-46: MUFU.RCP64H seed (2^-23) and one Newton step
 __device__ __forceinline__ double rcp_newton(double d) {
@@ -75,11 +69,6 @@ __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, 
                 if (base + (uint32_t)__popc(idle) >= n) exhausted = true;     // warp-uniform
                 if (!active) {
                     idx = base + (uint32_t)__popc(idle & lt_mask);
-#if LMCU_PF_RAY
-                    // the queue streams from HBM in cursor order: pull the rays LMCU_PF_RAY slots ahead toward L2 now, so that
-                    // the warp that claims them later does not wait on DRAM with its other lanes parked
-                    if (idx + (uint32_t)LMCU_PF_RAY < n) io.prefetch(idx + (uint32_t)LMCU_PF_RAY);
-#endif
                     if (idx < n && io.load(idx, r, f, tmin_dn, tmax_up)) {
                         ht = r.tmax; htri = -1;
                         ngroup = make_uint2(0u, 0x80000000u);   // the root occupies virtual slot 7 of group 0
@@ -123,13 +112,6 @@ __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, 
                         ngroup.y = (hm & 0xff000000u) | (n0.w >> 24);
                         tgroup.x = n1.y;
                         tgroup.y = hm & 0x00ffffffu;
-#if LMCU_PF_NODE
-                        if (ngroup.y > 0x00ffffffu) {        // the child this lane descends into next: warm L1 while the leaf work runs
-                            const uint32_t nslot = (uint32_t)(bfind(ngroup.y) - 24) ^ (f.octinv4 & 0xffu);
-                            const uint32_t nn = ngroup.x + popc(ngroup.y & 0xffu & ~(0xffffffffu << nslot));
-                            asm volatile("prefetch.global.L1 [%0];" ::"l"(nodes4 + nn * 5));
-                        }
-#endif
                     } else {
                         // ---- nothing left: this ray is done.  The IO policy finishes the barycentrics (u, v = raw / |det|):
                         // only a few lanes are here at a time, so what it costs is paid at ~3/32 occupancy
@@ -181,7 +163,10 @@ __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, 
 
 }  // namespace lmcu
 
-// Variants measured and dropped (profiles/r01_ncu_summary_v2.md, gpurun logs of round 1): the FP64 triangle test of the
+// Variants measured and dropped (profiles/r01_ncu_summary_v2.md, _v6.md, gpurun logs of round 1): an L1 prefetch of the
+// child a lane descends into next, issued at the end of the node step (-3 %: 8 more instructions per step for a node that
+// hits L1 80 % of the time anyway); an L2 prefetch of the queue 16 K / 64 K rays ahead of the cursor (+0.3 %, noise); the
+// FP64 triangle test of the
 // path-tracer queues with fused multiply-adds (14 fewer FP64 instructions, but the DFMA chains are longer than the
 // independent DMULs they replace: extend +4 % time, 1296 vs 1321 Mpaths/s on C2); warp-private chunks of 32..128
 // rays claimed with one atomic, the next chunk claimed in advance and prefetched toward L2 (-3 % on C2 pt, 1195 vs 1232

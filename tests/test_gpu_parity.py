@@ -37,14 +37,22 @@ CASES = {
 }
 
 
+@pytest.mark.parametrize("records", ["default", "float"])
 @pytest.mark.parametrize("name", sorted(CASES))
-def test_g1_closest_hit_vs_golden(name):
-    """(primitive, face) equal to accel::sahbvh for every ray; t,u,v bit-identical (gate: 1e-5 relative)."""
+def test_g1_closest_hit_vs_golden(name, records, monkeypatch):
+    """(primitive, face) equal to accel::sahbvh for every ray; t,u,v bit-identical (gate: 1e-5 relative).  Both triangle
+    records: small scenes keep 80-byte FP64 records by default; `float` forces the 48-byte records a large
+    float-representable scene (C3) gets, which promote to the same FP64 values on load."""
+    if records == "float":
+        monkeypatch.setenv("LMCU_TRI64", "0")
     sb = CASES[name]()
     sc = lmcu.Scene(sb)
-    assert bool(sc.build_stats.triangles_fp32) == (name != "cornell_fp64")
+    assert bool(sc.build_stats.triangles_fp32) == (records == "float" and name != "cornell_fp64")
     hits = sc.intersect(golden_rays(name, sb))
     assert_hit_parity(golden_hits(name), hits, max_special_frac=3e-3)
+    if name == "spheres12":
+        film, _ = sc.render("pt", abi.render_params(96, 54, spp=8, max_verts=8))
+        assert np.isfinite(film).all() and film.mean() > 0.01
     sc.close()
 
 
@@ -384,7 +392,7 @@ def test_full_size_properties_c3():
     - re-tracing with tmax = t_hit returns the same hit (idempotence, inclusive upper bound)"""
     sb = scenes.heightfield_scene(2236)
     sc = lmcu.Scene(sb)
-    assert sc.build_stats.num_triangles == 9999392
+    assert sc.build_stats.num_triangles == 9999392 and sc.build_stats.triangles_fp32     # 48-byte float records at this size
     rays = scenes.camera_rays(sb.camera, 1024, 1024)
     h = sc.intersect(rays)
     ok = h["primitive"] >= 0
