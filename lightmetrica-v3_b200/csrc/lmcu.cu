@@ -254,7 +254,9 @@ __global__ void k_pt_generate(DevScene s, PtParams p, PathQueue q, ShadowQueue s
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // Two compactions in one pass (next-path queue and shadow queue): the per-warp counts travel packed
-// 16+16 bits through ONE shared-memory scan, so a shade iteration costs 3 barriers instead of 6.
+// 16+16 bits through ONE shared-memory scan.  `smem` is one of two alternating 34-word buffers: a warp can run at
+// most one tile ahead of the slowest (it meets it again at the first barrier of the next tile), so the buffer of the
+// previous tile needs no trailing barrier — 2 barriers per tile.
 __device__ __forceinline__ void block_compact2(bool p0, bool p1, uint32_t* counter0, uint32_t* counter1,
                                                uint32_t* smem /* [34] */, uint32_t& pos0, uint32_t& pos1) {
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -280,15 +282,15 @@ __device__ __forceinline__ void block_compact2(bool p0, bool p1, uint32_t* count
     const uint32_t ex = smem[warp], lt = (1u << lane) - 1u;
     pos0 = smem[32] + (ex & 0xffffu) + (uint32_t)__popc(b0 & lt);
     pos1 = smem[33] + (ex >> 16) + (uint32_t)__popc(b1 & lt);
-    __syncthreads();
 }
 
 template <bool COMPOSITE>
 __global__ void __launch_bounds__(LMCU_SHADE_BLOCK, LMCU_SHADE_MINB) k_pt_shade(DevScene s, PtParams p, PathQueue qin, PathQueue qout, ShadowQueue sq,
                                                   const float4* hits, float* film, PtCounters* ctr, int cur) {
-    __shared__ uint32_t smem[34];
+    __shared__ uint32_t smem[2][34];
     const uint32_t n = ctr->count[cur];
-    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+    uint32_t tile = 0;
+    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x, tile ^= 1u) {
         const uint32_t i = base + threadIdx.x;
         {   // the queues stream from HBM: pull the next grid-stride tile of this CTA into L2 while this one is shaded
             const uint32_t nx = i + gridDim.x * blockDim.x;
@@ -308,7 +310,7 @@ __global__ void __launch_bounds__(LMCU_SHADE_BLOCK, LMCU_SHADE_MINB) k_pt_shade(
             }
         }
         uint32_t pos, spos;
-        block_compact2(o.alive, o.shadow, &ctr->count[cur ^ 1], &ctr->shadow_count, smem, pos, spos);
+        block_compact2(o.alive, o.shadow, &ctr->count[cur ^ 1], &ctr->shadow_count, smem[tile], pos, spos);
         if (o.alive) {
             qout.ray_o[pos] = o.o; qout.ray_d[pos] = o.d; qout.thr_pix[pos] = o.thr_pix; qout.aux[pos] = o.aux;
             qout.info[pos] = o.info;
