@@ -25,6 +25,20 @@ def sample_block(total_spp, rank, world):
     return offset, count
 
 
+def intersect_ray_split(intersect, rays, rank, world, dist=None):
+    """Accel batches on several GPUs (SURVEY.md §8e "accel batches"): the BVH is replicated, rank r traces the contiguous
+    block of the batch that `sample_block` gives it, and the hit records are gathered on rank 0 in ray order — there is no
+    other exchange.  intersect(rays_block) -> hits_block (numpy structured arrays).  Returns all hits on rank 0, else None."""
+    import numpy as np
+    offset, count = sample_block(len(rays), rank, world)
+    mine = intersect(rays[offset:offset + count])
+    if world == 1:
+        return mine
+    parts = [None] * world if rank == 0 else None
+    dist.gather_object(mine, parts, dst=0)
+    return np.concatenate(parts) if rank == 0 else None
+
+
 def film_as_tensor(torch, ptr, n, device_index):
     """Zero-copy torch view of liblmcu's device film."""
     class _Holder:

@@ -109,3 +109,36 @@ def test_sample_blocks_tile_the_range():
             assert blocks[0][0] == 0 and sum(c for _, c in blocks) == total
             for (o0, c0), (o1, _) in zip(blocks, blocks[1:]):
                 assert o0 + c0 == o1
+
+
+def _ray_worker(rank, world, port, n, out):
+    import numpy as np
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rays = np.arange(n, dtype=np.float64)
+
+    def intersect(block):                                # stand-in accel: a pure function of each ray
+        return np.stack([block * 2.0, np.full(len(block), float(rank))], -1)
+
+    hits = D.intersect_ray_split(intersect, rays, rank, world, dist)
+    if rank == 0:
+        np.save(out, hits)
+    else:
+        assert hits is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n", [(2, 1001), (3, 10), (3, 2)])
+def test_accel_batch_ray_split(tmp_path, world, n):
+    """Ray batches split by contiguous ranges across ranks and gathered in ray order on rank 0 (ragged and tiny batches:
+    a rank may own zero rays)."""
+    import numpy as np
+    out = str(tmp_path / "hits.npy")
+    mp.spawn(_ray_worker, args=(world, _free_port(), n, out), nprocs=world, join=True)
+    hits = np.load(out)
+    assert hits.shape == (n, 2)
+    assert np.array_equal(hits[:, 0], np.arange(n) * 2.0)
+    owners = hits[:, 1]
+    assert (np.diff(owners) >= 0).all() and set(owners.astype(int)) <= set(range(world))     # contiguous blocks in rank order
