@@ -162,6 +162,11 @@ struct OrcScene {
     int* mesh_faces;
     double** mesh_p;
     double** mesh_n;      /* always present: geometric normal replicated when the description has none */
+    double** mesh_t;      /* [faces][3][2] texture coordinates or NULL */
+    int ntex;
+    LmcuTexture* tex;     /* texture::bitmap texels (copied) */
+    int** mix_mat;        /* per material: entry tables of the constant-weight mixtures (copied) */
+    double** mix_w;
     int has_camera;
     V3 cam_pos, cam_u, cam_v, cam_w;
     double cam_tf, cam_aspect;
@@ -241,16 +246,28 @@ static void build_bvh(OrcScene* sc) {
 
 OrcScene* orc_scene_create(const LmcuSceneDesc* d) {
     if (!d || d->num_primitives <= 0) return NULL;
-    /* the port restates the four plain BSDFs only; textured and mixture materials are checked against
-       the reference itself (oracle/_ref) */
-    for (int i = 0; i < d->num_materials; i++) {
-        if (d->materials[i].type > LMCU_MAT_MIRROR || d->materials[i].map_kd != 0) return NULL;
-    }
     OrcScene* sc = (OrcScene*)calloc(1, sizeof(OrcScene));
     sc->nmeshes = d->num_meshes;
     sc->mesh_faces = (int*)malloc(sizeof(int) * (size_t)d->num_meshes);
     sc->mesh_p = (double**)malloc(sizeof(double*) * (size_t)d->num_meshes);
     sc->mesh_n = (double**)malloc(sizeof(double*) * (size_t)d->num_meshes);
+    sc->mesh_t = (double**)calloc((size_t)d->num_meshes, sizeof(double*));
+    for (int i = 0; i < d->num_meshes; i++) {
+        if (d->meshes[i].t) {
+            const size_t tc = (size_t)d->meshes[i].num_faces * 6;
+            sc->mesh_t[i] = (double*)malloc(sizeof(double) * tc);
+            memcpy(sc->mesh_t[i], d->meshes[i].t, sizeof(double) * tc);
+        }
+    }
+    sc->ntex = d->num_textures;
+    sc->tex = (LmcuTexture*)calloc((size_t)(d->num_textures > 0 ? d->num_textures : 1), sizeof(LmcuTexture));
+    for (int i = 0; i < d->num_textures; i++) {
+        const size_t cnt = (size_t)d->textures[i].w * d->textures[i].h * d->textures[i].c;
+        float* data = (float*)malloc(sizeof(float) * cnt);
+        memcpy(data, d->textures[i].data, sizeof(float) * cnt);
+        sc->tex[i] = d->textures[i];
+        sc->tex[i].data = data; sc->tex[i].path = NULL;
+    }
     for (int i = 0; i < d->num_meshes; i++) {
         const size_t cnt = (size_t)d->meshes[i].num_faces * 9;
         sc->mesh_faces[i] = d->meshes[i].num_faces;
@@ -282,6 +299,16 @@ OrcScene* orc_scene_create(const LmcuSceneDesc* d) {
     sc->nmats = d->num_materials;
     sc->mats = (LmcuMaterial*)malloc(sizeof(LmcuMaterial) * (size_t)(d->num_materials > 0 ? d->num_materials : 1));
     memcpy(sc->mats, d->materials, sizeof(LmcuMaterial) * (size_t)d->num_materials);
+    sc->mix_mat = (int**)calloc((size_t)(d->num_materials > 0 ? d->num_materials : 1), sizeof(int*));
+    sc->mix_w = (double**)calloc((size_t)(d->num_materials > 0 ? d->num_materials : 1), sizeof(double*));
+    for (int i = 0; i < d->num_materials; i++) {
+        const LmcuMaterial* m = &d->materials[i];
+        if (m->num_entries <= 0) continue;
+        sc->mix_mat[i] = (int*)malloc(sizeof(int) * (size_t)m->num_entries);
+        sc->mix_w[i] = (double*)malloc(sizeof(double) * (size_t)m->num_entries);
+        for (int k = 0; k < m->num_entries; k++) { sc->mix_mat[i][k] = m->entry_material[k]; sc->mix_w[i][k] = m->entry_weight[k]; }
+        sc->mats[i].entry_material = sc->mix_mat[i]; sc->mats[i].entry_weight = sc->mix_w[i];
+    }
     sc->nlights = d->num_lights;
     sc->lights = (Light*)calloc((size_t)(d->num_lights > 0 ? d->num_lights : 1), sizeof(Light));
     sc->env_light = -1;
@@ -372,7 +399,10 @@ OrcScene* orc_scene_create(const LmcuSceneDesc* d) {
 
 void orc_scene_destroy(OrcScene* s) {
     if (!s) return;
-    for (int i = 0; i < s->nmeshes; i++) { free(s->mesh_p[i]); free(s->mesh_n[i]); }
+    for (int i = 0; i < s->nmeshes; i++) { free(s->mesh_p[i]); free(s->mesh_n[i]); free(s->mesh_t[i]); }
+    for (int i = 0; i < s->ntex; i++) free((void*)s->tex[i].data);
+    for (int i = 0; i < s->nmats; i++) { free(s->mix_mat[i]); free(s->mix_w[i]); }
+    free(s->mesh_t); free(s->tex); free(s->mix_mat); free(s->mix_w);
     for (int i = 0; i < s->nlights; i++) {
         free(s->lights[i].cdf); free(s->lights[i].env_tex); free(s->lights[i].env_rows); free(s->lights[i].env_marg);
     }
@@ -465,6 +495,7 @@ typedef struct {
     int light;          /* light index for light endpoints */
     int infinite, degenerated;
     V3 p, n, gn, wo, u, v;
+    double tu, tv;      /* PointGeometry::t */
 } SP;
 
 /* math::orthonormal_basis, Duff et al. (math.h:540-547) */
@@ -508,6 +539,12 @@ static int scene_intersect(const OrcScene* sc, Ray ray, double tmin, double tmax
     memset(sp, 0, sizeof(*sp));
     sp->type = SP_SURFACE; sp->prim = t->prim; sp->light = pr->light;
     make_on_surface(sp, m4_point(pr->M, pl), vnormalize(m3_mul(pr->NM, nl)), vnormalize(m3_mul(pr->NM, gl)));
+    if (sc->mesh_t[pr->mesh]) {                                                   /* mix_barycentric of Mesh::Point::t */
+        const double* T = sc->mesh_t[pr->mesh] + (size_t)t->face * 6;
+        const double w0 = 1.0 - h.u - h.v;
+        sp->tu = (T[0] * w0 + T[2] * h.u) + T[4] * h.v;
+        sp->tv = (T[1] * w0 + T[3] * h.u) + T[5] * h.v;
+    }
     return 1;
 }
 
@@ -730,6 +767,258 @@ static int mat_sample_direction(const LmcuMaterial* m, const SP* g, V3 wi, int c
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * Composite materials: mapKd textures (src/texture/texture_bitmap.cpp:68-90), material::mask (material_mask.cpp),
+ * material::mixture_wavefrontobj (src/model/model_wavefrontobj.cpp:339-515) and the constant-weight mixtures
+ * (src/material/material_mixture.cpp).  The cm_* functions are Material::* of whatever sits on the primitive; plain lobes
+ * fall through to the mat_* functions above.  `comp` is the component Material::sample_component returned.
+ * ---------------------------------------------------------------------------------------------- */
+static void tex_lookup(const LmcuTexture* t, double tu, double tv, V3* rgb, double* alpha) {
+    const double u = tu - floor(tu), v = tv - floor(tv);
+    int x = (int)(u * t->w), y = (int)(v * t->h);
+    x = x < 0 ? 0 : (x > t->w - 1 ? t->w - 1 : x);
+    y = y < 0 ? 0 : (y > t->h - 1 ? t->h - 1 : y);
+    const float* c = t->data + (size_t)t->c * ((size_t)t->w * y + x);
+    *rgb = v3(c[0], c[1], c[2]);
+    *alpha = t->c == 4 ? (double)c[3] : 0.0;                                             /* Texture::eval_alpha default: 0 */
+}
+
+/* a plain lobe with its mapKd resolved at the surface point (material_diffuse.cpp:70,80,90) */
+static LmcuMaterial lobe_at(const OrcScene* sc, const LmcuMaterial* m, const SP* g) {
+    LmcuMaterial o = *m;
+    if (m->type == LMCU_MAT_DIFFUSE && m->map_kd > 0) {
+        V3 c; double a;
+        tex_lookup(&sc->tex[m->map_kd - 1], g->tu, g->tv, &c, &a);
+        o.color[0] = c.x; o.color[1] = c.y; o.color[2] = c.z;
+    }
+    return o;
+}
+
+static int plain_is_specular(int type) { return type == LMCU_MAT_GLASS || type == LMCU_MAT_MIRROR || type == LMCU_MAT_MASK; }
+
+/* the diffuse and glossy lobes mixture_wavefrontobj owns (:393-403), its alpha (:376-378) and diffuse_selection_prob (:431-439) */
+static void obj_parts(const OrcScene* sc, const LmcuMaterial* m, const SP* g, LmcuMaterial* d, LmcuMaterial* gl, double* alpha, double* w) {
+    *d = *m; d->type = LMCU_MAT_DIFFUSE;
+    *gl = *m; gl->type = LMCU_MAT_GLOSSY; gl->color[0] = m->Ks[0]; gl->color[1] = m->Ks[1]; gl->color[2] = m->Ks[2];
+    *alpha = 1.0;
+    if (m->map_kd > 0) {
+        V3 c; double a;
+        tex_lookup(&sc->tex[m->map_kd - 1], g->tu, g->tv, &c, &a);
+        d->color[0] = c.x; d->color[1] = c.y; d->color[2] = c.z;
+        if (m->alpha_mask && sc->tex[m->map_kd - 1].c == 4) *alpha = a;
+    }
+    const double wd = fmax(fmax(d->color[0], d->color[1]), d->color[2]), wg = fmax(fmax(gl->color[0], gl->color[1]), gl->color[2]);
+    *w = (wd == 0.0 && wg == 0.0) ? 1.0 : wd / (wd + wg);
+}
+
+/* Dist over n weights (math.h:310-370): cdf by running sums, normalised by the total */
+static void dist_build(const double* w, int n, double* cdf) {
+    cdf[0] = 0.0;
+    for (int i = 0; i < n; i++) cdf[i + 1] = cdf[i] + w[i];
+    const double sum = cdf[n];
+    for (int i = 0; i <= n; i++) cdf[i] /= sum;
+}
+
+#define ORC_MAX_MIX 16
+/* groups of constant_weight_mixture_marginalized (:156-186): group 0 = non-specular entries, then one per specular entry */
+typedef struct { int ngroups; int count[ORC_MAX_MIX + 1]; int entry[ORC_MAX_MIX + 1][ORC_MAX_MIX]; double gcdf[ORC_MAX_MIX + 2]; } MixGroups;
+static void mix_groups(const OrcScene* sc, const LmcuMaterial* m, MixGroups* G) {
+    G->ngroups = 1; G->count[0] = 0;
+    for (int k = 0; k < m->num_entries && k < ORC_MAX_MIX; k++) {
+        const int spec = plain_is_specular(sc->mats[m->entry_material[k]].type);
+        if (spec) { G->count[G->ngroups] = 1; G->entry[G->ngroups][0] = k; G->ngroups++; }
+        else G->entry[0][G->count[0]++] = k;
+    }
+    double sums[ORC_MAX_MIX + 1];
+    for (int g = 0; g < G->ngroups; g++) {
+        sums[g] = 0.0;
+        for (int i = 0; i < G->count[g]; i++) sums[g] += m->entry_weight[G->entry[g][i]];
+    }
+    dist_build(sums, G->ngroups, G->gcdf);
+}
+static void group_cdf(const LmcuMaterial* m, const MixGroups* G, int g, double* cdf) {
+    double w[ORC_MAX_MIX];
+    for (int i = 0; i < G->count[g]; i++) w[i] = m->entry_weight[G->entry[g][i]];
+    dist_build(w, G->count[g], cdf);
+}
+
+static int cm_is_specular(const OrcScene* sc, const LmcuMaterial* m, int comp) {
+    switch (m->type) {
+    case LMCU_MAT_MIXTURE_OBJ: return comp != 0;
+    case LMCU_MAT_MIXTURE_RR: return plain_is_specular(sc->mats[m->entry_material[comp]].type);
+    case LMCU_MAT_MIXTURE_MARGINALIZED: return comp != 0;
+    default: return plain_is_specular(m->type);
+    }
+}
+
+static V3 plain_eval(const LmcuMaterial* m, const SP* g, V3 wi, V3 wo, int comp, int eval_delta) {
+    if (m->type == LMCU_MAT_MASK) return eval_delta ? v3(0, 0, 0) : v3(1, 1, 1);          /* material_mask.cpp:49-51 */
+    return mat_eval(m, g, wi, wo, comp, eval_delta);
+}
+static double plain_pdf(const LmcuMaterial* m, const SP* g, V3 wi, V3 wo, int eval_delta) {
+    if (m->type == LMCU_MAT_MASK) return eval_delta ? 0.0 : 1.0;                           /* material_mask.cpp:45-47 */
+    return mat_pdf(m, g, wi, wo, eval_delta);
+}
+static int plain_sample_direction(const LmcuMaterial* m, const SP* g, V3 wi, int comp, double ud0, double ud1, V3* wo, V3* weight) {
+    if (m->type == LMCU_MAT_MASK) { *wo = vneg(wi); *weight = v3(1, 1, 1); return 1; }    /* material_mask.cpp:38-43 */
+    return mat_sample_direction(m, g, wi, comp, ud0, ud1, wo, weight);
+}
+
+static V3 cm_eval(const OrcScene* sc, const LmcuMaterial* m, const SP* g, V3 wi, V3 wo, int comp, int eval_delta) {
+    switch (m->type) {
+    case LMCU_MAT_MIXTURE_OBJ: {                                                         /* model_wavefrontobj.cpp:500-511 */
+        LmcuMaterial d, gl; double alpha, w;
+        obj_parts(sc, m, g, &d, &gl, &alpha, &w);
+        if (comp == 0) {
+            V3 sum = v3(0, 0, 0);
+            sum = vadd(sum, mat_eval(&d, g, wi, wo, 0, eval_delta));
+            sum = vadd(sum, mat_eval(&gl, g, wi, wo, 0, eval_delta));
+            return vscale(sum, alpha);
+        }
+        return eval_delta ? v3(0, 0, 0) : v3(1.0 - alpha, 1.0 - alpha, 1.0 - alpha);
+    }
+    case LMCU_MAT_MIXTURE_RR: {                                                          /* material_mixture.cpp:92-95 */
+        const LmcuMaterial e = lobe_at(sc, &sc->mats[m->entry_material[comp]], g);
+        return vscale(plain_eval(&e, g, wi, wo, 0, eval_delta), m->entry_weight[comp]);
+    }
+    case LMCU_MAT_MIXTURE_MARGINALIZED: {                                                /* :248-256 */
+        MixGroups G; mix_groups(sc, m, &G);
+        V3 r = v3(0, 0, 0);
+        for (int i = 0; i < G.count[comp]; i++) {
+            const int k = G.entry[comp][i];
+            const LmcuMaterial e = lobe_at(sc, &sc->mats[m->entry_material[k]], g);
+            r = vadd(r, vscale(plain_eval(&e, g, wi, wo, 0, eval_delta), m->entry_weight[k]));
+        }
+        return r;
+    }
+    default: {
+        const LmcuMaterial e = lobe_at(sc, m, g);
+        return plain_eval(&e, g, wi, wo, comp, eval_delta);
+    }
+    }
+}
+
+static double cm_pdf(const OrcScene* sc, const LmcuMaterial* m, const SP* g, V3 wi, V3 wo, int comp, int eval_delta) {
+    switch (m->type) {
+    case LMCU_MAT_MIXTURE_OBJ: {                                                         /* model_wavefrontobj.cpp:487-498 */
+        if (comp != 0) return eval_delta ? 0.0 : 1.0;
+        LmcuMaterial d, gl; double alpha, w;
+        obj_parts(sc, m, g, &d, &gl, &alpha, &w);
+        double p = 0.0;
+        p += w * mat_pdf(&d, g, wi, wo, eval_delta);
+        p += (1.0 - w) * mat_pdf(&gl, g, wi, wo, eval_delta);
+        return p;
+    }
+    case LMCU_MAT_MIXTURE_RR:                                                            /* material_mixture.cpp:88-90 */
+        return plain_pdf(&sc->mats[m->entry_material[comp]], g, wi, wo, eval_delta);
+    case LMCU_MAT_MIXTURE_MARGINALIZED: {                                                /* :236-246 */
+        MixGroups G; mix_groups(sc, m, &G);
+        double cdf[ORC_MAX_MIX + 1]; group_cdf(m, &G, comp, cdf);
+        double p = 0.0;
+        for (int i = 0; i < G.count[comp]; i++) {
+            const double psel = cdf[i + 1] - cdf[i];
+            p += psel * plain_pdf(&sc->mats[m->entry_material[G.entry[comp][i]]], g, wi, wo, eval_delta);
+        }
+        return p;
+    }
+    default: return plain_pdf(m, g, wi, wo, eval_delta);
+    }
+}
+
+/* Material::sample_component; uc0 = ComponentSampleU::uc[0] */
+static int cm_sample_component(const OrcScene* sc, const LmcuMaterial* m, const SP* g, V3 wi, double uc0, double* weight) {
+    switch (m->type) {
+    case LMCU_MAT_MIXTURE_OBJ: {                                                         /* model_wavefrontobj.cpp:417-424 */
+        LmcuMaterial d, gl; double alpha, w;
+        obj_parts(sc, m, g, &d, &gl, &alpha, &w);
+        if (uc0 < alpha) { *weight = 1.0 / alpha; return 0; }
+        *weight = 1.0 / (1.0 - alpha);
+        return 1;
+    }
+    case LMCU_MAT_MIXTURE_RR: {                                                          /* material_mixture.cpp:61-65 */
+        double cdf[ORC_MAX_MIX + 1]; dist_build(m->entry_weight, m->num_entries, cdf);
+        const int c = dist_sample(cdf, m->num_entries, uc0);
+        *weight = 1.0 / (cdf[c + 1] - cdf[c]);
+        return c;
+    }
+    case LMCU_MAT_MIXTURE_MARGINALIZED: {                                                /* :191-195 */
+        MixGroups G; mix_groups(sc, m, &G);
+        const int c = dist_sample(G.gcdf, G.ngroups, uc0);
+        *weight = 1.0 / (G.gcdf[c + 1] - G.gcdf[c]);
+        return c;
+    }
+    case LMCU_MAT_MASK: *weight = 1.0; return 0;
+    default: return mat_sample_component(m, g, wi, uc0, weight);
+    }
+}
+
+/* Material::sample_direction; ud = DirectionSampleU::ud, udc0 = udc[0]; returns 0 when the sample is invalid */
+static int cm_sample_direction(const OrcScene* sc, const LmcuMaterial* m, const SP* g, V3 wi, int comp, double ud0, double ud1,
+                               double udc0, V3* wo, V3* weight) {
+    switch (m->type) {
+    case LMCU_MAT_MIXTURE_OBJ: {                                                         /* model_wavefrontobj.cpp:441-480 */
+        if (comp != 0) { *wo = vneg(wi); *weight = v3(1, 1, 1); return 1; }            /* returns Vec3(1), not f/p (:470-479) */
+        LmcuMaterial d, gl; double alpha, w;
+        obj_parts(sc, m, g, &d, &gl, &alpha, &w);
+        V3 ws;
+        if (!mat_sample_direction(udc0 < w ? &d : &gl, g, wi, 0, ud0, ud1, wo, &ws)) return 0;
+        *weight = vdivs(cm_eval(sc, m, g, wi, *wo, comp, 0), cm_pdf(sc, m, g, wi, *wo, comp, 0));
+        return 1;
+    }
+    case LMCU_MAT_MIXTURE_RR: {                                                          /* material_mixture.cpp:67-78 */
+        const LmcuMaterial e = lobe_at(sc, &sc->mats[m->entry_material[comp]], g);
+        V3 ws;
+        if (!plain_sample_direction(&e, g, wi, 0, ud0, ud1, wo, &ws)) return 0;
+        *weight = vscale(ws, m->entry_weight[comp]);
+        return 1;
+    }
+    case LMCU_MAT_MIXTURE_MARGINALIZED: {                                                /* :201-224 */
+        MixGroups G; mix_groups(sc, m, &G);
+        double cdf[ORC_MAX_MIX + 1]; group_cdf(m, &G, comp, cdf);
+        const int i = dist_sample(cdf, G.count[comp], udc0);
+        const LmcuMaterial e = lobe_at(sc, &sc->mats[m->entry_material[G.entry[comp][i]]], g);
+        V3 ws;
+        if (!plain_sample_direction(&e, g, wi, 0, ud0, ud1, wo, &ws)) return 0;
+        *weight = vdivs(cm_eval(sc, m, g, wi, *wo, comp, 0), cm_pdf(sc, m, g, wi, *wo, comp, 0));
+        return 1;
+    }
+    default: {
+        const LmcuMaterial e = lobe_at(sc, m, g);
+        return plain_sample_direction(&e, g, wi, comp, ud0, ud1, wo, weight);
+    }
+    }
+}
+
+/* Material::reflectance (raycast shading) */
+static V3 cm_reflectance(const OrcScene* sc, const LmcuMaterial* m, const SP* g) {
+    switch (m->type) {
+    case LMCU_MAT_MIXTURE_OBJ: {                                                         /* model_wavefrontobj.cpp:482-485 */
+        LmcuMaterial d, gl; double alpha, w;
+        obj_parts(sc, m, g, &d, &gl, &alpha, &w);
+        return v3(d.color[0], d.color[1], d.color[2]);
+    }
+    case LMCU_MAT_MIXTURE_RR:
+    case LMCU_MAT_MIXTURE_MARGINALIZED: {                                                /* material_mixture.cpp:80-86,226-234 */
+        V3 sum = v3(0, 0, 0);
+        if (m->type == LMCU_MAT_MIXTURE_RR) {
+            for (int k = 0; k < m->num_entries; k++) sum = vadd(sum, vscale(cm_reflectance(sc, &sc->mats[m->entry_material[k]], g), m->entry_weight[k]));
+        } else {
+            MixGroups G; mix_groups(sc, m, &G);
+            for (int gi = 0; gi < G.ngroups; gi++) for (int i = 0; i < G.count[gi]; i++) {
+                const int k = G.entry[gi][i];
+                sum = vadd(sum, vscale(cm_reflectance(sc, &sc->mats[m->entry_material[k]], g), m->entry_weight[k]));
+            }
+        }
+        return sum;
+    }
+    case LMCU_MAT_DIFFUSE: case LMCU_MAT_GLOSSY: {
+        const LmcuMaterial e = lobe_at(sc, m, g);
+        return v3(e.color[0], e.color[1], e.color[2]);
+    }
+    default: return v3(0, 0, 0);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------
  * Lights
  * ---------------------------------------------------------------------------------------------- */
 /* light::env lookup coordinates of a direction d = -geomL.wo (light_env.cpp:166-176,191-199) */
@@ -878,8 +1167,7 @@ void orc_render_raycast(const OrcScene* sc, const LmcuRenderParams* p, double* f
             } else {
                 const LmcuMaterial* m = &sc->mats[sc->prims[sp.prim].material];
                 if (p->has_color) C = v3(p->color[0], p->color[1], p->color[2]);
-                else if (m->type == LMCU_MAT_DIFFUSE || m->type == LMCU_MAT_GLOSSY) C = v3(m->color[0], m->color[1], m->color[2]);
-                else C = v3(0, 0, 0);
+                else C = cm_reflectance(sc, m, &sp);
                 if (!p->use_constant_color) C = vscale(C, .2 + .8 * fabs(vdot(sp.n, vneg(ray.d))));
             }
             double* px = film + ((size_t)y * w + x) * 3;
@@ -971,7 +1259,7 @@ void orc_render_pt(const OrcScene* sc, const LmcuRenderParams* p, double* film, 
                 const LmcuMaterial* mat = sp.type == SP_SURFACE ? &sc->mats[sc->prims[sp.prim].material] : NULL;
                 int samplable_by_nee = 0;                                                /* :127-140 */
                 if (mode != LMCU_SAMPLING_NAIVE) {
-                    const int is_spec = mat ? mat_is_specular(mat) : 0;
+                    const int is_spec = mat ? cm_is_specular(sc, mat, comp) : 0;
                     samplable_by_nee = image ? !is_spec : (num_verts > 1 && !is_spec);  /* image mode: NEE from the camera too */
                 }
                 if (samplable_by_nee) {                                                  /* :142-192 */
@@ -983,7 +1271,7 @@ void orc_render_pt(const OrcScene* sc, const LmcuRenderParams* p, double* film, 
                         (num_verts > 1 || camera_raster_position(sc, vneg(woL), &rx, &ry))) {
                         const V3 wo = vneg(woL);
                         V3 fs;                                                           /* path::eval_contrb_direction, path.h:761-775 */
-                        if (mat) fs = vscale(mat_eval(mat, &sp, wi, wo, comp, 1), sn_correction(&sp, wi, wo));
+                        if (mat) fs = vscale(cm_eval(sc, mat, &sp, wi, wo, comp, 1), sn_correction(&sp, wi, wo));
                         else { const double We = camera_pdf_direction(sc, wo); fs = v3(We, We, We); }
                         if (!vis_zero(fs)) {
                             double mis_w = 1.0;
@@ -993,7 +1281,7 @@ void orc_render_pt(const OrcScene* sc, const LmcuRenderParams* p, double* film, 
                             const int samplable_by_bsdf = ltype != LMCU_LIGHT_DIRECTIONAL && !spL.degenerated;
                             if (mode == LMCU_SAMPLING_MIS && samplable_by_bsdf) {
                                 const double p_light = pdf_direct(sc, &sp, &spL, woL);
-                                const double p_bsdf = mat ? mat_pdf(mat, &sp, wi, wo, 1) : camera_pdf_direction(sc, wo);
+                                const double p_bsdf = mat ? cm_pdf(sc, mat, &sp, wi, wo, comp, 1) : camera_pdf_direction(sc, wo);
                                 mis_w = balance_heuristic(p_light, p_bsdf);
                             }
                             film_splat(film, w, h, rx, ry, vscale(vmul(vmul(throughput, fs), wL), mis_w));
@@ -1011,7 +1299,7 @@ void orc_render_pt(const OrcScene* sc, const LmcuRenderParams* p, double* film, 
                 } else {
                     double u[4];
                     for (int i = 0; i < 4; i++) u[i] = rng_u(&rng);                      /* DirectionSampleU: ud, udc */
-                    if (!mat_sample_direction(mat, &sp, wi, comp, u[0], u[1], &wo, &weight)) break;
+                    if (!cm_sample_direction(sc, mat, &sp, wi, comp, u[0], u[1], u[2], &wo, &weight)) break;
                     weight = vscale(weight, sn_correction(&sp, wi, wo));                 /* include/lm/path.h:415-419 */
                 }
                 if (num_verts == 1) camera_raster_position(sc, wo, &rpx, &rpy);         /* :214-216 */
@@ -1025,7 +1313,7 @@ void orc_render_pt(const OrcScene* sc, const LmcuRenderParams* p, double* film, 
                     const V3 fs = light_eval(&sc->lights[hit.light], &hit, woL);
                     double mis_w = 1.0;
                     if (mode != LMCU_SAMPLING_NAIVE && samplable_by_nee) {
-                        const double pdf_bsdf = mat ? mat_pdf(mat, &sp, wi, wo, 1) : camera_pdf_direction(sc, wo);
+                        const double pdf_bsdf = mat ? cm_pdf(sc, mat, &sp, wi, wo, comp, 1) : camera_pdf_direction(sc, wo);
                         const double pdf_light = pdf_direct(sc, &sp, &hit, woL);
                         mis_w = balance_heuristic(pdf_bsdf, pdf_light);
                     }
@@ -1040,7 +1328,7 @@ void orc_render_pt(const OrcScene* sc, const LmcuRenderParams* p, double* film, 
                 const double uc0 = rng_u(&rng);                                          /* :292-293, ComponentSampleU */
                 rng_u(&rng);
                 double cw;
-                const int ncomp = mat_sample_component(&sc->mats[sc->prims[hit.prim].material], &hit, vneg(wo), uc0, &cw);
+                const int ncomp = cm_sample_component(sc, &sc->mats[sc->prims[hit.prim].material], &hit, vneg(wo), uc0, &cw);
                 throughput = vscale(throughput, cw);
                 wi = vneg(wo); sp = hit; comp = ncomp;                                   /* :298-300 */
             }
