@@ -91,8 +91,23 @@ LMCU_HD uint64_t expand_bits21(uint64_t v) {   // spread the low 20 bits: bit i 
     return v;
 }
 
-LMCU_HD uint64_t morton_body(const double* centre, uint32_t g, const double* slo, const double* shi) {
+// `big_frac` > 0: a triangle whose bound diagonal exceeds big_frac x the scene diagonal gets key bit 60 set, so that the
+// radix tree keeps all such triangles in ONE subtree under the root.  Sorted by centre alone, a wall or ground polygon
+// lands in a leaf next to millimetre-sized neighbours and inflates the bounds of every ancestor on its path: most rays
+// then walk that whole path for nothing.  Measured (tools/big_probe.py): C2 4.89 -> 3.16 nodes per closest-hit ray and
+// 4.35 -> 1.96 per shadow ray, 1331 -> 1599 Mpaths/s; C4 22.1 -> 20.2 nodes per ray, 369 -> 391 Mpaths/s; thresholds 1/4 .. 1/64
+// give the same trees on both.
+LMCU_HD uint64_t morton_body(const double* centre, uint32_t g, const double* slo, const double* shi,
+                             const float* tri_lo = nullptr, const float* tri_hi = nullptr, double big_frac = 0.0) {
     uint64_t code = 0;
+    if (big_frac > 0.0 && tri_lo) {
+        double d2 = 0.0, s2 = 0.0;
+        for (int a = 0; a < 3; a++) {
+            const double e = (double)tri_hi[(size_t)g * 3 + a] - (double)tri_lo[(size_t)g * 3 + a], se = shi[a] - slo[a];
+            d2 += e * e; s2 += se * se;
+        }
+        if (d2 > big_frac * big_frac * s2) code = 1ull << 60;
+    }
     for (int a = 0; a < 3; a++) {
         const double ext = shi[a] - slo[a];
         double u = ext > 0 ? (centre[(size_t)g * 3 + a] - slo[a]) / ext : 0.0;

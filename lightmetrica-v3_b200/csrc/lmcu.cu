@@ -89,12 +89,13 @@ __global__ void k_flatten(const PrimDev* prims, int num_prims, const double* mes
     }
 }
 
-__global__ void k_morton(const double* centre, uint32_t nt, const float* scene_bounds, uint64_t* keys, uint32_t* vals) {
+__global__ void k_morton(const double* centre, uint32_t nt, const float* scene_bounds, uint64_t* keys, uint32_t* vals,
+                         const float* tri_lo, const float* tri_hi, double big_frac) {
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= nt) return;
     const double slo[3] = { scene_bounds[0], scene_bounds[1], scene_bounds[2] };
     const double shi[3] = { scene_bounds[3], scene_bounds[4], scene_bounds[5] };
-    keys[g] = morton_body(centre, g, slo, shi);
+    keys[g] = morton_body(centre, g, slo, shi, tri_lo, tri_hi, big_frac);
     vals[g] = g;
 }
 
@@ -699,7 +700,9 @@ int lmcu_accel_build(LmcuScene* s, const LmcuBuildOptions* opts, LmcuBuildStats*
                                                  centre.p, bounds.p, exact.p);
     CU(cudaGetLastError());
     CU(keys.alloc(nt)); CU(keys_sorted.alloc(nt)); CU(vals.alloc(nt)); CU(vals_sorted.alloc(nt));
-    k_morton<<<grid_for(nt, 256), 256, 0, st>>>(centre.p, nt, bounds.p, keys.p, vals.p);
+    double big_frac = 1.0 / 16.0;                                    // LMCU_BIG: denominator (0 = off), tuning only
+    if (const char* e = getenv("LMCU_BIG")) big_frac = atof(e) > 0 ? 1.0 / atof(e) : 0.0;
+    k_morton<<<grid_for(nt, 256), 256, 0, st>>>(centre.p, nt, bounds.p, keys.p, vals.p, tri_lo.p, tri_hi.p, big_frac);
     CU(cudaGetLastError());
     {
         size_t tmp_bytes = 0;

@@ -103,7 +103,7 @@ int hostsim_scene_create(const LmcuSceneDesc* d, int max_leaf, void** out, long 
     const double dlo[3] = { slo[0], slo[1], slo[2] }, dhi[3] = { shi[0], shi[1], shi[2] };
     std::vector<uint64_t> keys(nt);
     std::vector<uint32_t> vals(nt);
-    for (uint32_t g = 0; g < nt; g++) { keys[g] = morton_body(centre.data(), g, dlo, dhi); vals[g] = g; }
+    for (uint32_t g = 0; g < nt; g++) { keys[g] = morton_body(centre.data(), g, dlo, dhi, tri_lo.data(), tri_hi.data(), 1.0 / 16.0); vals[g] = g; }
     std::vector<uint32_t> order(nt);
     std::iota(order.begin(), order.end(), 0u);
     std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return keys[a] < keys[b]; });
