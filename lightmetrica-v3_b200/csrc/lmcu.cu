@@ -550,7 +550,7 @@ struct LmcuScene {
     DBuf<PtCounters> pt_ctr;
     uint32_t pt_capacity = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    int fetch_threshold = 16;            // LMCU_FETCH
+    int fetch_threshold = 12;            // LMCU_FETCH
     int shade_ctas_per_sm = 3;                   // LMCU_SHADE_GRID: CTAs per SM in the shade kernel's grid-stride grid
     int ctas_per_sm = LMCU_MINB;                 // LMCU_CTAS: resident 128-thread CTAs per SM for the persistent traversal grids
 
