@@ -284,10 +284,17 @@ def run_ours(args):
         _, stc = sc.render("pt", pc, download=False)
         n_nodes, n_tris = stc["bvh_nodes_per_ray"], stc["bvh_tris_per_ray"]
         b_ray = 32 + 16 + n_nodes * 80 + n_tris * 48
-        ext_s = sum(s["extend_seconds"] for s in stats)
-        ext_rays = sum(s["extend_rays"] for s in stats)
-        ext_launches = sum(s["extend_launches"] for s in stats)
-        total_s = sum(s["elapsed"] for s in stats)
+        # In the timed region TWO wavefront loops run side by side (LmcuRenderParams::wavefronts), so the CUDA events
+        # around an extend launch also see the other loop's shade / shadow kernels on the same SMs: that duration is
+        # reported as `overlapped`, but it is not the kernel's own.  The kernel's launch duration is measured live here
+        # in a single-wavefront render of the same workload (kernels of one loop run one at a time), 256 spp.
+        ps = abi.render_params(W, H, spp=256, max_verts=MAX_VERTS, seed=SEED, rescale=0, wavefronts=1)
+        sc.render("pt", abi.render_params(W, H, spp=16, max_verts=MAX_VERTS, seed=SEED, rescale=0, wavefronts=1), download=False)
+        _, solo = sc.render("pt", ps, download=False)
+        ext_s, ext_rays, ext_launches, total_s = solo["extend_seconds"], solo["extend_rays"], solo["extend_launches"], solo["elapsed"]
+        stats_solo = [solo]
+        ov_s = sum(s["extend_seconds"] for s in stats)
+        ov_rays = sum(s["extend_rays"] for s in stats)
         peak, peak_src = load_peaks()
         achieved = ext_rays * b_ray / ext_s / 1e9
         traffic, traffic_src = None, None
@@ -305,8 +312,13 @@ def run_ours(args):
             "bytes_per_ray": b_ray, "nodes_per_ray": n_nodes, "tris_per_ray": n_tris,
             "algorithmic_bytes_per_launch": ext_rays / max(1, ext_launches) * b_ray,
             "rays_per_launch": ext_rays / max(1, ext_launches), "avg_launch_ms": ext_s / max(1, ext_launches) * 1e3,
-            "share_of_step": {"extend": ext_s / total_s, "shade": sum(s["shade_seconds"] for s in stats) / total_s,
-                              "shadow": sum(s["shadow_seconds"] for s in stats) / total_s},
+            "share_of_step": {"extend": ext_s / total_s, "shade": sum(s["shade_seconds"] for s in stats_solo) / total_s,
+                              "shadow": sum(s["shadow_seconds"] for s in stats_solo) / total_s},
+            "measured_in": "single-wavefront render of the same workload inside this run (256 spp, %.1f Mpaths/s): the kernel timed "
+                           "with nothing beside it" % (solo["paths"] / solo["elapsed"] / 1e6),
+            "overlapped": {"achieved": ov_rays * b_ray / ov_s / 1e9, "frac": ov_rays * b_ray / ov_s / 1e9 / peak,
+                           "what": "same figure from the events of the timed region, where a launch shares the SMs with the other "
+                                   "wavefront's kernels"},
             "note": "BVH + triangles of C2 are 1.9 MB and stay L1/L2-resident: the algorithmic bytes are served by cache "
                     "(measured DRAM traffic is the ray queue only), so frac is algorithmic bytes over the HBM peak, not "
                     "DRAM utilisation; the kernel is bound by instruction issue of divergent warps (profiles/)",
@@ -336,8 +348,9 @@ def run_ours(args):
                                    "max_verts=20 sampling_mode=mis seed=42", "spp_per_gpu": spp, "total_spp": spp * world,
                        "parallelism": "sample split x%d, film combine = %s" % (
                            world, "fused peer-memory reduce+rescale kernel over NVLink (CUDA IPC)" if args.reduce == "p2p" else "NCCL reduce"),
-                       "l2": "inputs larger than L2: every wavefront iteration streams the 8 Mi-path SoA queues "
-                             "(1.2 GB) through HBM, and every step regenerates all paths"},
+                       "wavefronts": 2,
+                       "l2": "inputs larger than L2: every wavefront iteration streams its 16 Mi-path SoA queues "
+                             "(2.4 GB) through HBM, and every step regenerates all paths"},
             "mrays_per_s": rays * world / (ms_total * 1e-3) / 1e6,
             "e2e": e2e, "gpu_launches": int(sum(s["kernel_launches"] for s in stats)) + args.steps,
             "roofline": roofline, "cpu_baseline": cpu, "accel_c3": accel, "clocks": clocks,

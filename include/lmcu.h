@@ -187,6 +187,9 @@ typedef struct LmcuRenderParams {
     int64_t num_samples;                     /* pt, image mode + sample scheduler: samples of the whole image by THIS call */
     int64_t samples_per_iter;                /* pt, image mode + time scheduler: samples per pass (0 = 100000, scheduler.cpp:159) */
     double render_time;                      /* pt, time scheduler: seconds; the pass in flight always completes */
+    int32_t wavefronts;                      /* pt: staggered wavefront loops running side by side on their own streams
+                                                (0 = default 2; 1 = one kernel at a time).  Same image for any value. */
+    int32_t pad2_;
 } LmcuRenderParams;
 
 typedef struct LmcuRenderStats {

@@ -356,6 +356,7 @@ struct PtParams {
     uint32_t seed, tiled;
     uint64_t sample_offset;
     uint64_t total_paths;
+    uint64_t path_base;         // index of this wavefront's first path inside the pass (staggered wavefronts)
     uint32_t capacity;
     uint32_t image_mode;        // primary_ray_sampling_mode = image: the raster window is the whole film (renderer_pt.cpp:104-106)
 };

@@ -216,7 +216,7 @@ __global__ void k_pt_advance(PtParams p, PtCounters* ctr, int cur) {
     const unsigned long long remaining = p.total_paths - ctr->next_path;
     const uint32_t room = p.capacity - m;
     const uint32_t n_new = remaining < room ? (uint32_t)remaining : room;
-    ctr->gen_slot = m; ctr->gen_count = n_new; ctr->gen_first = ctr->next_path;
+    ctr->gen_slot = m; ctr->gen_count = n_new; ctr->gen_first = p.path_base + ctr->next_path;
     ctr->count[cur] = m + n_new;
     ctr->next_path += n_new;
     ctr->count[cur ^ 1] = 0;
@@ -461,7 +461,7 @@ struct BlockCache {
     std::mutex mu;
     std::multimap<std::pair<int, size_t>, void*> blocks;
     size_t bytes = 0;
-    static constexpr size_t kCacheBytes = size_t(6) << 30;
+    static constexpr size_t kCacheBytes = size_t(24) << 30;
     void* take(int device, size_t n) {
         std::lock_guard<std::mutex> lk(mu);
         auto it = blocks.find({ device, n });
@@ -511,7 +511,6 @@ struct LmcuScene {
     int num_sms = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t own_stream = nullptr;
-    std::vector<cudaEvent_t> ring;          // per-kernel timing events of the pt loop
     // description (device)
     DBuf<double> mesh_p, mesh_n;
     DBuf<PrimDev> prims;
@@ -542,12 +541,27 @@ struct LmcuScene {
     DBuf<uint32_t> flags;                // [0] stack overflow
     DBuf<float> film;
     int film_w = 0, film_h = 0;
-    // pt pools
-    DBuf<float4> pq[2][4];
-    DBuf<uint2> pinfo[2];
-    DBuf<float4> hits;
-    DBuf<float4> sq[3];
-    DBuf<PtCounters> pt_ctr;
+    // pt pools: one set per wavefront (LMCU_WAVES staggered wavefronts, each on its own stream)
+    struct PtWave {
+        DBuf<float4> pq[2][4];
+        DBuf<uint2> pinfo[2];
+        DBuf<float4> hits;
+        DBuf<float4> sq[3];
+        DBuf<PtCounters> ctr;
+        cudaStream_t stream = nullptr;       // wave 0 runs on the scene's stream, the others on their own
+        cudaEvent_t done = nullptr;
+        std::vector<cudaEvent_t> ring;       // per-kernel timing events
+        PtCounters* h = nullptr;             // last counters read back (PINNED: a D2H copy into pageable memory blocks the host
+                                             // until the stream drains, which would serialise the wavefronts)
+        int cur = 0;
+        bool finished = false;
+    };
+    static constexpr int kMaxWaves = 4;
+    PtWave wave[kMaxWaves];
+    int pt_waves = 0;
+    int waves = 2;                           // wavefronts of the current render (LmcuRenderParams::wavefronts, LMCU_WAVES)
+    int default_waves = 2;
+    cudaEvent_t fork = nullptr;
     uint32_t pt_capacity = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int fetch_threshold = 12;            // LMCU_FETCH
@@ -593,6 +607,7 @@ int lmcu_scene_create(int device, LmcuScene** out) {
     if (const char* e = getenv("LMCU_FETCH")) s->fetch_threshold = atoi(e);
     if (const char* e = getenv("LMCU_CTAS")) s->ctas_per_sm = std::max(1, atoi(e));
     if (const char* e = getenv("LMCU_SHADE_GRID")) s->shade_ctas_per_sm = std::max(1, atoi(e));
+    if (const char* e = getenv("LMCU_WAVES")) s->default_waves = std::min((int)LmcuScene::kMaxWaves, std::max(1, atoi(e)));
     CU(s->cursor.alloc(8));
     CU(s->flags.alloc(4));
     CU(cudaMemset(s->cursor.p, 0, 8 * sizeof(unsigned long long)));
@@ -607,7 +622,13 @@ void lmcu_scene_destroy(LmcuScene* s) {
     cudaDeviceSynchronize();
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
-    for (cudaEvent_t e : s->ring) cudaEventDestroy(e);
+    for (auto& w : s->wave) {
+        for (cudaEvent_t e : w.ring) cudaEventDestroy(e);
+        if (w.done) cudaEventDestroy(w.done);
+        if (w.h) cudaFreeHost(w.h);
+        if (w.stream) cudaStreamDestroy(w.stream);
+    }
+    if (s->fork) cudaEventDestroy(s->fork);
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
     delete s;
 }
@@ -1131,15 +1152,25 @@ int lmcu_render_ao(LmcuScene* s, const LmcuRenderParams* p, float* film_rgb, Lmc
 // shadow_factor: 1, or 2 in image mode where one iteration can hold a camera-vertex NEE ray per NEW path on top of one
 // NEE ray per path in the queue
 static int ensure_pt_pools(LmcuScene* s, uint32_t capacity, uint32_t shadow_factor) {
-    if (s->pt_capacity == capacity && s->pt_ctr.p && s->sq[0].n >= (size_t)capacity * shadow_factor) return LMCU_OK;
-    for (int b = 0; b < 2; b++) {
-        for (int k = 0; k < 4; k++) CU(s->pq[b][k].alloc(capacity));
-        CU(s->pinfo[b].alloc(capacity));
+    if (s->pt_capacity == capacity && s->pt_waves == s->waves && s->wave[0].ctr.p &&
+        s->wave[0].sq[0].n >= (size_t)capacity * shadow_factor) return LMCU_OK;
+    for (int w = 0; w < LmcuScene::kMaxWaves; w++) {
+        LmcuScene::PtWave& v = s->wave[w];
+        const uint32_t cap = w < s->waves ? capacity : 0u;
+        for (int b = 0; b < 2; b++) {
+            for (int k = 0; k < 4; k++) CU(v.pq[b][k].alloc(cap));
+            CU(v.pinfo[b].alloc(cap));
+        }
+        CU(v.hits.alloc(cap));
+        for (int k = 0; k < 3; k++) CU(v.sq[k].alloc((size_t)cap * shadow_factor));
+        CU(v.ctr.alloc(cap ? 1 : 0));
+        if (cap && w > 0 && !v.stream) CU(cudaStreamCreateWithFlags(&v.stream, cudaStreamNonBlocking));
+        if (cap && !v.done) CU(cudaEventCreateWithFlags(&v.done, cudaEventDisableTiming));
+        if (cap && !v.h) CU(cudaHostAlloc((void**)&v.h, sizeof(PtCounters), cudaHostAllocDefault));
     }
-    CU(s->hits.alloc(capacity));
-    for (int k = 0; k < 3; k++) CU(s->sq[k].alloc((size_t)capacity * shadow_factor));
-    CU(s->pt_ctr.alloc(1));
+    if (!s->fork) CU(cudaEventCreateWithFlags(&s->fork, cudaEventDisableTiming));
     s->pt_capacity = capacity;
+    s->pt_waves = s->waves;
     return LMCU_OK;
 }
 
@@ -1151,58 +1182,96 @@ struct PtAccum {
     unsigned long long rays = 0, extend_rays = 0, shadow_rays = 0, nodes_extend = 0, tris_extend = 0, nodes_shadow = 0, tris_shadow = 0;
 };
 
-static int pt_pass(LmcuScene* s, const PtParams& pp, bool count, PtAccum& acc) {
-    cudaStream_t st = s->stream;
-    PathQueue q[2];
-    for (int b = 0; b < 2; b++) {
-        q[b].ray_o = s->pq[b][0].p; q[b].ray_d = s->pq[b][1].p; q[b].thr_pix = s->pq[b][2].p; q[b].aux = s->pq[b][3].p;
-        q[b].info = s->pinfo[b].p;
-    }
-    ShadowQueue sq;
-    sq.ray_o = s->sq[0].p; sq.ray_d = s->sq[1].p; sq.contrib = s->sq[2].p;
-    CU(cudaMemsetAsync(s->pt_ctr.p, 0, sizeof(PtCounters), st));
+static int pt_pass(LmcuScene* s, const PtParams& pp_all, bool count, PtAccum& acc) {
+    // K staggered wavefronts: the paths of this pass are cut into K contiguous ranges, each traced to completion by its own
+    // generate / extend / shade / shadow loop on its own stream over its own pools, all adding into the one film.  The
+    // kernels of a loop depend on each other, so ONE wavefront leaves the machine to one kernel at a time: while it sits
+    // in the shade kernel (bound by dependent gathers, issue slots half idle) nothing traverses.  With two loops out of
+    // phase the traversal kernels of one fill the shade kernel's bubbles of the other.  Every kernel keeps its full
+    // persistent grid (one wave of resident CTAs): the block scheduler hands a freed CTA slot to whichever loop has CTAs
+    // pending, so a kernel's drain tail is filled by the other loop's next kernel (grids cut to 1/K measured worse).
+    const int K = s->waves;
     const DevScene d = s->dev();
     const unsigned q_blocks = (unsigned)(s->num_sms * s->ctas_per_sm);
     const unsigned shade_blocks = (unsigned)(s->num_sms * s->shade_ctas_per_sm), gen_blocks = (unsigned)s->num_sms * 4;
-    int cur = 0;
-    PtCounters h{};
     const int kGroup = 4;                       // iterations between host checks
-    if (s->ring.empty()) {
-        s->ring.resize(kGroup * 4);
-        for (auto& e : s->ring) CU(cudaEventCreate(&e));
+    PtParams pp[LmcuScene::kMaxWaves];
+    PathQueue q[LmcuScene::kMaxWaves][2];
+    ShadowQueue sq[LmcuScene::kMaxWaves];
+    if (K > 1) CU(cudaEventRecord(s->fork, s->stream));
+    for (int w = 0; w < K; w++) {
+        LmcuScene::PtWave& v = s->wave[w];
+        cudaStream_t st = w == 0 ? s->stream : v.stream;
+        if (w > 0) CU(cudaStreamWaitEvent(st, s->fork, 0));           // the film clear / earlier passes happened on s->stream
+        pp[w] = pp_all;
+        const uint64_t lo = pp_all.total_paths * (uint64_t)w / (uint64_t)K, hi = pp_all.total_paths * (uint64_t)(w + 1) / (uint64_t)K;
+        pp[w].path_base = pp_all.path_base + lo;
+        pp[w].total_paths = hi - lo;
+        for (int b = 0; b < 2; b++) {
+            q[w][b].ray_o = v.pq[b][0].p; q[w][b].ray_d = v.pq[b][1].p; q[w][b].thr_pix = v.pq[b][2].p; q[w][b].aux = v.pq[b][3].p;
+            q[w][b].info = v.pinfo[b].p;
+        }
+        sq[w].ray_o = v.sq[0].p; sq[w].ray_d = v.sq[1].p; sq[w].contrib = v.sq[2].p;
+        CU(cudaMemsetAsync(v.ctr.p, 0, sizeof(PtCounters), st));
+        v.cur = 0;
+        v.finished = pp[w].total_paths == 0;
+        memset(v.h, 0, sizeof(PtCounters));
+        if (v.ring.empty()) {
+            v.ring.resize(kGroup * 4);
+            for (auto& e : v.ring) CU(cudaEventCreate(&e));
+        }
     }
     while (true) {
-        for (int it = 0; it < kGroup; it++) {
-            cudaEvent_t* ev = &s->ring[it * 4];
-            k_pt_advance<<<1, 1, 0, st>>>(pp, s->pt_ctr.p, cur);
-            k_pt_generate<<<gen_blocks, 256, 0, st>>>(d, pp, q[cur], sq, s->pt_ctr.p);
-            cudaEventRecord(ev[0], st);
-            LMCU_DISPATCH(k_pt_extend_q, s->fp32, count, q_blocks, 128, st, d, q[cur], s->hits.p, s->pt_ctr.p, cur);
-            cudaEventRecord(ev[1], st);
-            if (s->composite) k_pt_shade<true><<<shade_blocks, LMCU_SHADE_BLOCK, 0, st>>>(d, pp, q[cur], q[cur ^ 1], sq, s->hits.p, s->film.p, s->pt_ctr.p, cur);
-            else k_pt_shade<false><<<shade_blocks, LMCU_SHADE_BLOCK, 0, st>>>(d, pp, q[cur], q[cur ^ 1], sq, s->hits.p, s->film.p, s->pt_ctr.p, cur);
-            cudaEventRecord(ev[2], st);
-            LMCU_DISPATCH(k_pt_shadow_q, s->fp32, count, q_blocks, 128, st, d, sq, s->film.p, s->pt_ctr.p);
-            cudaEventRecord(ev[3], st);
-            cur ^= 1;
-            acc.launches += 5;
-            acc.extend_launches++;
+        bool any = false;
+        for (int w = 0; w < K; w++) {
+            LmcuScene::PtWave& v = s->wave[w];
+            if (v.finished) continue;
+            any = true;
+            cudaStream_t st = w == 0 ? s->stream : v.stream;
+            for (int it = 0; it < kGroup; it++) {
+                cudaEvent_t* ev = &v.ring[it * 4];
+                const int cur = v.cur;
+                k_pt_advance<<<1, 1, 0, st>>>(pp[w], v.ctr.p, cur);
+                k_pt_generate<<<gen_blocks, 256, 0, st>>>(d, pp[w], q[w][cur], sq[w], v.ctr.p);
+                cudaEventRecord(ev[0], st);
+                LMCU_DISPATCH(k_pt_extend_q, s->fp32, count, q_blocks, 128, st, d, q[w][cur], v.hits.p, v.ctr.p, cur);
+                cudaEventRecord(ev[1], st);
+                if (s->composite) k_pt_shade<true><<<shade_blocks, LMCU_SHADE_BLOCK, 0, st>>>(d, pp[w], q[w][cur], q[w][cur ^ 1], sq[w], v.hits.p, s->film.p, v.ctr.p, cur);
+                else k_pt_shade<false><<<shade_blocks, LMCU_SHADE_BLOCK, 0, st>>>(d, pp[w], q[w][cur], q[w][cur ^ 1], sq[w], v.hits.p, s->film.p, v.ctr.p, cur);
+                cudaEventRecord(ev[2], st);
+                LMCU_DISPATCH(k_pt_shadow_q, s->fp32, count, q_blocks, 128, st, d, sq[w], s->film.p, v.ctr.p);
+                cudaEventRecord(ev[3], st);
+                v.cur ^= 1;
+                acc.launches += 5;
+                acc.extend_launches++;
+            }
+            CU(cudaGetLastError());
+            CU(cudaMemcpyAsync(v.h, v.ctr.p, sizeof(PtCounters), cudaMemcpyDeviceToHost, st));
         }
-        CU(cudaGetLastError());
-        CU(cudaMemcpyAsync(&h, s->pt_ctr.p, sizeof(h), cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
-        for (int it = 0; it < kGroup; it++) {
-            float ms = 0;
-            cudaEventElapsedTime(&ms, s->ring[it * 4 + 0], s->ring[it * 4 + 1]); acc.t_extend += ms * 1e-3;
-            cudaEventElapsedTime(&ms, s->ring[it * 4 + 1], s->ring[it * 4 + 2]); acc.t_shade += ms * 1e-3;
-            cudaEventElapsedTime(&ms, s->ring[it * 4 + 2], s->ring[it * 4 + 3]); acc.t_shadow += ms * 1e-3;
+        if (!any) break;
+        for (int w = 0; w < K; w++) {
+            LmcuScene::PtWave& v = s->wave[w];
+            if (v.finished) continue;
+            CU(cudaStreamSynchronize(w == 0 ? s->stream : v.stream));
+            for (int it = 0; it < kGroup; it++) {
+                float ms = 0;
+                cudaEventElapsedTime(&ms, v.ring[it * 4 + 0], v.ring[it * 4 + 1]); acc.t_extend += ms * 1e-3;
+                cudaEventElapsedTime(&ms, v.ring[it * 4 + 1], v.ring[it * 4 + 2]); acc.t_shade += ms * 1e-3;
+                cudaEventElapsedTime(&ms, v.ring[it * 4 + 2], v.ring[it * 4 + 3]); acc.t_shadow += ms * 1e-3;
+            }
+            if (v.h->overflow) return fail(LMCU_ERR_CUDA, "bvh traversal stack overflow");
+            if (v.h->next_path >= pp[w].total_paths && v.h->count[v.cur] == 0) {
+                v.finished = true;
+                acc.rays += v.h->rays; acc.extend_rays += v.h->extend_rays; acc.shadow_rays += v.h->shadow_rays;
+                acc.nodes_extend += v.h->nodes_extend; acc.tris_extend += v.h->tris_extend;
+                acc.nodes_shadow += v.h->nodes_shadow; acc.tris_shadow += v.h->tris_shadow;
+                if (w > 0) {                                            // join: later work on s->stream sees this wave's film adds
+                    CU(cudaEventRecord(v.done, v.stream));
+                    CU(cudaStreamWaitEvent(s->stream, v.done, 0));
+                }
+            }
         }
-        if (h.overflow) return fail(LMCU_ERR_CUDA, "bvh traversal stack overflow");
-        if (h.next_path >= pp.total_paths && h.count[cur] == 0) break;
     }
-    acc.rays += h.rays; acc.extend_rays += h.extend_rays; acc.shadow_rays += h.shadow_rays;
-    acc.nodes_extend += h.nodes_extend; acc.tris_extend += h.tris_extend;
-    acc.nodes_shadow += h.nodes_shadow; acc.tris_shadow += h.tris_shadow;
     return LMCU_OK;
 }
 
@@ -1226,7 +1295,20 @@ int lmcu_render_pt(LmcuScene* s, const LmcuRenderParams* p, float* film_rgb, Lmc
     CU(cudaSetDevice(s->device));
     rc = ensure_film(s, p->width, p->height);
     if (rc) return rc;
-    uint32_t capacity = 1u << 23;        // 8 Mi paths in flight: 72 B x 2 queues + 48 B shadow + 16 B hit = 1.7 GB
+    if (p->wavefronts < 0 || p->wavefronts > LmcuScene::kMaxWaves) return fail(LMCU_ERR_INVALID_ARGUMENT, "wavefronts must be in 0..4");
+    s->waves = p->wavefronts > 0 ? p->wavefronts : s->default_waves;
+    // Paths in flight per wavefront: 16 Mi (208 B each: 72 B x 2 queues + 48 B shadow + 16 B hit = 3.4 GB per wavefront; the
+    // 180 GB of HBM make large launches cheap and they amortise the persistent kernels' tails: C2 at 1024 spp, two
+    // wavefronts of 4 / 8 / 16 / 32 Mi paths: 1709 (256 spp) / 1772 / 1812 / 1826 Mpaths/s), never more than the job
+    // needs.  LMCU_PT_POOL overrides it.
+    uint32_t capacity = 1u << 24;
+    if (!timed) {
+        const uint64_t npx = (uint64_t)p->width * p->height;
+        const uint64_t job = image ? (uint64_t)p->num_samples : npx * (uint64_t)p->spp;
+        const uint64_t per_wave = (job + (uint64_t)s->waves - 1) / (uint64_t)s->waves;
+        const uint64_t need = std::max<uint64_t>(1u << 16, (per_wave + 0xffffull) & ~0xffffull);
+        if (need < capacity) capacity = (uint32_t)need;
+    }
     if (const char* e = getenv("LMCU_PT_POOL")) capacity = (uint32_t)std::max(1024l, atol(e));
     rc = ensure_pt_pools(s, capacity, image ? 2u : 1u);
     if (rc) return rc;
@@ -1260,7 +1342,7 @@ int lmcu_render_pt(LmcuScene* s, const LmcuRenderParams* p, float* film_rgb, Lmc
         // multiple of that, sized from the measured rate so that the wavefront stays full and the overshoot small.
         const int64_t iter = image ? (p->samples_per_iter > 0 ? p->samples_per_iter : 100000) : 1;   // reference granularity
         const auto t0 = std::chrono::steady_clock::now();
-        int64_t units = std::max<int64_t>(1, (int64_t)(capacity / paths_per_unit) / iter) * iter;    // first pass: one full queue
+        int64_t units = std::max<int64_t>(1, (int64_t)((uint64_t)capacity * (uint64_t)s->waves / paths_per_unit) / iter) * iter;    // first pass: full queues
         while (true) {
             rc = run_units(units);
             if (rc) return rc;

@@ -165,7 +165,7 @@ __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, 
 
 // Variants measured and dropped (profiles/r01_ncu_summary_v2.md, _v6.md, gpurun logs of round 1): an L1 prefetch of the
 // child a lane descends into next, issued at the end of the node step (-3 %: 8 more instructions per step for a node that
-// hits L1 80 % of the time anyway); an L2 prefetch of the queue 16 K / 64 K rays ahead of the cursor (+0.3 %, noise); the
+// hits L1 80 % of the time anyway), and of a node's first triangles when the node arrives (-4 %); an L2 prefetch of the queue 16 K / 64 K rays ahead of the cursor (+0.3 %, noise); the
 // FP64 triangle test of the
 // path-tracer queues with fused multiply-adds (14 fewer FP64 instructions, but the DFMA chains are longer than the
 // independent DMULs they replace: extend +4 % time, 1296 vs 1321 Mpaths/s on C2); warp-private chunks of 32..128

@@ -391,6 +391,26 @@ def test_pt_time_schedulers(reference, image):
     rs.close(); sc.close()
 
 
+def test_wavefront_count_does_not_change_the_image():
+    """1, 2, 3 and 4 staggered wavefronts trace the same paths (the RNG is keyed by pixel and sample index, not by the
+    loop that carries the path): identical images up to the order of the film's atomic adds; processed / paths / rays
+    counters identical.  Includes a job smaller than one queue and image mode."""
+    sb = scenes.cornell_spheres(12)
+    sc = lmcu.Scene(sb)
+    for kw in (dict(spp=24), dict(spp=1), dict(primary_ray_sampling_mode=abi.PRIMARY_IMAGE, num_samples=160 * 90 * 16)):
+        ref_film, ref_st = None, None
+        for waves in (1, 2, 3, 4):
+            film, st = sc.render("pt", abi.render_params(160, 90, max_verts=10, wavefronts=waves, **kw))
+            if ref_film is None:
+                ref_film, ref_st = film, st
+                continue
+            assert np.allclose(film, ref_film, rtol=2e-4, atol=1e-5), (waves, kw)
+            assert all(st[k] == ref_st[k] for k in ("processed", "paths", "rays", "extend_rays", "shadow_rays")), (waves, kw)
+    with pytest.raises(lmcu.LmcuError):
+        sc.render("pt", abi.render_params(64, 36, spp=1, wavefronts=9))
+    sc.close()
+
+
 def test_sample_split_is_additive():
     """Sample split (multi-GPU partition): two half renders with disjoint sample offsets sum to the full render."""
     sb = scenes.cornell_spheres(16)
