@@ -381,10 +381,12 @@ def test_pt_time_schedulers(reference, image):
     kf.pop("samples_per_iter", None)
     ff, _ = sc.render("pt", abi.render_params(w, h, max_verts=12, **kf))
     assert np.allclose(ff, fg, rtol=2e-3, atol=2e-4)
-    # against the reference: its 1024-spp image (the block z-test assumes comparable noise in both images; a
-    # 256-spp reference against a ~10 000-spp render trips it on the skew of the reference's own noise)
+    # against the reference: its 1024-spp image.  The block z-test assumes comparable noise in both images; the budget
+    # buys tens of thousands of spp here, so the difference image is the reference's own (skewed) 1024-spp noise and the
+    # z-test is widened accordingly — the sharp check is the fixed-count equality above, and fixed-count renders are held
+    # to the full gate in the tests before this one
     fr, _, _ = rs.render("pt", abi.render_params(w, h, spp=1024, max_verts=12))
-    assert_pt_parity(fr, fg, 1024, rel_mean=0.01)
+    assert_pt_parity(fr, fg, 1024, rel_mean=0.01, z_frac=0.04)
     # render_time = 0: exactly one pass (the reference checks the clock after each pass)
     fz, sz = sc.render("pt", abi.render_params(w, h, max_verts=12, scheduler=abi.SCHED_TIME, render_time=0.0, **kw))
     assert sz["processed"] >= 1 and np.isfinite(fz).all() and fz.mean() > 0
