@@ -550,10 +550,14 @@ struct LmcuScene {
         DBuf<PtCounters> ctr;
         cudaStream_t stream = nullptr;       // wave 0 runs on the scene's stream, the others on their own
         cudaEvent_t done = nullptr;
-        std::vector<cudaEvent_t> ring;       // per-kernel timing events
-        PtCounters* h = nullptr;             // last counters read back (PINNED: a D2H copy into pageable memory blocks the host
-                                             // until the stream drains, which would serialise the wavefronts)
-        int cur = 0;
+        // two groups of iterations are in flight per wavefront; per slot: per-kernel timing events, a "group complete"
+        // event and the counters read back after the group (PINNED: a D2H copy into pageable memory blocks the host
+        // until the stream drains, which would serialise the wavefronts)
+        std::vector<cudaEvent_t> ring[2];
+        cudaEvent_t grp[2] = { nullptr, nullptr };
+        PtCounters* h = nullptr;             // [2]
+        int cur = 0;                         // ping-pong queue index of the next iteration to enqueue
+        int cur_after[2] = { 0, 0 };         // ... as it stands after the group of a slot
         bool finished = false;
     };
     static constexpr int kMaxWaves = 4;
@@ -623,7 +627,10 @@ void lmcu_scene_destroy(LmcuScene* s) {
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     for (auto& w : s->wave) {
-        for (cudaEvent_t e : w.ring) cudaEventDestroy(e);
+        for (int k = 0; k < 2; k++) {
+            for (cudaEvent_t e : w.ring[k]) cudaEventDestroy(e);
+            if (w.grp[k]) cudaEventDestroy(w.grp[k]);
+        }
         if (w.done) cudaEventDestroy(w.done);
         if (w.h) cudaFreeHost(w.h);
         if (w.stream) cudaStreamDestroy(w.stream);
@@ -1166,7 +1173,7 @@ static int ensure_pt_pools(LmcuScene* s, uint32_t capacity, uint32_t shadow_fact
         CU(v.ctr.alloc(cap ? 1 : 0));
         if (cap && w > 0 && !v.stream) CU(cudaStreamCreateWithFlags(&v.stream, cudaStreamNonBlocking));
         if (cap && !v.done) CU(cudaEventCreateWithFlags(&v.done, cudaEventDisableTiming));
-        if (cap && !v.h) CU(cudaHostAlloc((void**)&v.h, sizeof(PtCounters), cudaHostAllocDefault));
+        if (cap && !v.h) CU(cudaHostAlloc((void**)&v.h, 2 * sizeof(PtCounters), cudaHostAllocDefault));
     }
     if (!s->fork) CU(cudaEventCreateWithFlags(&s->fork, cudaEventDisableTiming));
     s->pt_capacity = capacity;
@@ -1214,61 +1221,83 @@ static int pt_pass(LmcuScene* s, const PtParams& pp_all, bool count, PtAccum& ac
         sq[w].ray_o = v.sq[0].p; sq[w].ray_d = v.sq[1].p; sq[w].contrib = v.sq[2].p;
         CU(cudaMemsetAsync(v.ctr.p, 0, sizeof(PtCounters), st));
         v.cur = 0;
-        v.finished = pp[w].total_paths == 0;
-        memset(v.h, 0, sizeof(PtCounters));
-        if (v.ring.empty()) {
-            v.ring.resize(kGroup * 4);
-            for (auto& e : v.ring) CU(cudaEventCreate(&e));
+        v.finished = false;
+        memset(v.h, 0, 2 * sizeof(PtCounters));
+        for (int k = 0; k < 2; k++) {
+            if (v.ring[k].empty()) {
+                v.ring[k].resize(kGroup * 4);
+                for (auto& e : v.ring[k]) CU(cudaEventCreate(&e));
+                CU(cudaEventCreateWithFlags(&v.grp[k], cudaEventDisableTiming));
+            }
         }
     }
-    while (true) {
-        bool any = false;
-        for (int w = 0; w < K; w++) {
-            LmcuScene::PtWave& v = s->wave[w];
-            if (v.finished) continue;
-            any = true;
-            cudaStream_t st = w == 0 ? s->stream : v.stream;
-            for (int it = 0; it < kGroup; it++) {
-                cudaEvent_t* ev = &v.ring[it * 4];
-                const int cur = v.cur;
-                k_pt_advance<<<1, 1, 0, st>>>(pp[w], v.ctr.p, cur);
-                k_pt_generate<<<gen_blocks, 256, 0, st>>>(d, pp[w], q[w][cur], sq[w], v.ctr.p);
-                cudaEventRecord(ev[0], st);
-                LMCU_DISPATCH(k_pt_extend_q, s->fp32, count, q_blocks, 128, st, d, q[w][cur], v.hits.p, v.ctr.p, cur);
-                cudaEventRecord(ev[1], st);
-                if (s->composite) k_pt_shade<true><<<shade_blocks, LMCU_SHADE_BLOCK, 0, st>>>(d, pp[w], q[w][cur], q[w][cur ^ 1], sq[w], v.hits.p, s->film.p, v.ctr.p, cur);
-                else k_pt_shade<false><<<shade_blocks, LMCU_SHADE_BLOCK, 0, st>>>(d, pp[w], q[w][cur], q[w][cur ^ 1], sq[w], v.hits.p, s->film.p, v.ctr.p, cur);
-                cudaEventRecord(ev[2], st);
-                LMCU_DISPATCH(k_pt_shadow_q, s->fp32, count, q_blocks, 128, st, d, sq[w], s->film.p, v.ctr.p);
-                cudaEventRecord(ev[3], st);
-                v.cur ^= 1;
-                acc.launches += 5;
-                acc.extend_launches++;
-            }
-            CU(cudaGetLastError());
-            CU(cudaMemcpyAsync(v.h, v.ctr.p, sizeof(PtCounters), cudaMemcpyDeviceToHost, st));
+    // One group = kGroup iterations + the counters' read-back + the slot's completion event, all asynchronous.
+    auto enqueue_group = [&](int w, int slot) -> int {
+        LmcuScene::PtWave& v = s->wave[w];
+        cudaStream_t st = w == 0 ? s->stream : v.stream;
+        for (int it = 0; it < kGroup; it++) {
+            cudaEvent_t* ev = &v.ring[slot][it * 4];
+            const int cur = v.cur;
+            k_pt_advance<<<1, 1, 0, st>>>(pp[w], v.ctr.p, cur);
+            k_pt_generate<<<gen_blocks, 256, 0, st>>>(d, pp[w], q[w][cur], sq[w], v.ctr.p);
+            cudaEventRecord(ev[0], st);
+            LMCU_DISPATCH(k_pt_extend_q, s->fp32, count, q_blocks, 128, st, d, q[w][cur], v.hits.p, v.ctr.p, cur);
+            cudaEventRecord(ev[1], st);
+            if (s->composite) k_pt_shade<true><<<shade_blocks, LMCU_SHADE_BLOCK, 0, st>>>(d, pp[w], q[w][cur], q[w][cur ^ 1], sq[w], v.hits.p, s->film.p, v.ctr.p, cur);
+            else k_pt_shade<false><<<shade_blocks, LMCU_SHADE_BLOCK, 0, st>>>(d, pp[w], q[w][cur], q[w][cur ^ 1], sq[w], v.hits.p, s->film.p, v.ctr.p, cur);
+            cudaEventRecord(ev[2], st);
+            LMCU_DISPATCH(k_pt_shadow_q, s->fp32, count, q_blocks, 128, st, d, sq[w], s->film.p, v.ctr.p);
+            cudaEventRecord(ev[3], st);
+            v.cur ^= 1;
+            acc.launches += 5;
+            acc.extend_launches++;
         }
-        if (!any) break;
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(v.h + slot, v.ctr.p, sizeof(PtCounters), cudaMemcpyDeviceToHost, st));
+        CU(cudaEventRecord(v.grp[slot], st));
+        v.cur_after[slot] = v.cur;
+        return LMCU_OK;
+    };
+    // Two groups in flight per wavefront: the host reads the counters of group g while group g+1 runs, so no loop ever
+    // waits for the host and the loops drift out of phase on their own.  The end of a wavefront is seen one group late:
+    // the group already in flight then runs kGroup empty iterations (queues of 0 paths, a few microseconds).
+    for (int slot = 0; slot < 2; slot++) {
+        for (int w = 0; w < K; w++) {
+            if (pp[w].total_paths == 0 && slot == 1) continue;
+            const int rc = enqueue_group(w, slot);
+            if (rc) return rc;
+        }
+    }
+    int remaining = K;
+    for (int slot = 0; remaining > 0; slot ^= 1) {
         for (int w = 0; w < K; w++) {
             LmcuScene::PtWave& v = s->wave[w];
             if (v.finished) continue;
-            CU(cudaStreamSynchronize(w == 0 ? s->stream : v.stream));
+            CU(cudaEventSynchronize(v.grp[slot]));
+            const PtCounters& h = v.h[slot];
             for (int it = 0; it < kGroup; it++) {
                 float ms = 0;
-                cudaEventElapsedTime(&ms, v.ring[it * 4 + 0], v.ring[it * 4 + 1]); acc.t_extend += ms * 1e-3;
-                cudaEventElapsedTime(&ms, v.ring[it * 4 + 1], v.ring[it * 4 + 2]); acc.t_shade += ms * 1e-3;
-                cudaEventElapsedTime(&ms, v.ring[it * 4 + 2], v.ring[it * 4 + 3]); acc.t_shadow += ms * 1e-3;
+                cudaEventElapsedTime(&ms, v.ring[slot][it * 4 + 0], v.ring[slot][it * 4 + 1]); acc.t_extend += ms * 1e-3;
+                cudaEventElapsedTime(&ms, v.ring[slot][it * 4 + 1], v.ring[slot][it * 4 + 2]); acc.t_shade += ms * 1e-3;
+                cudaEventElapsedTime(&ms, v.ring[slot][it * 4 + 2], v.ring[slot][it * 4 + 3]); acc.t_shadow += ms * 1e-3;
             }
-            if (v.h->overflow) return fail(LMCU_ERR_CUDA, "bvh traversal stack overflow");
-            if (v.h->next_path >= pp[w].total_paths && v.h->count[v.cur] == 0) {
+            if (h.overflow) return fail(LMCU_ERR_CUDA, "bvh traversal stack overflow");
+            if (h.next_path >= pp[w].total_paths && h.count[v.cur_after[slot]] == 0) {
+                // done; the other slot's group (if one was enqueued) only runs empty iterations: wait for it, then join
                 v.finished = true;
-                acc.rays += v.h->rays; acc.extend_rays += v.h->extend_rays; acc.shadow_rays += v.h->shadow_rays;
-                acc.nodes_extend += v.h->nodes_extend; acc.tris_extend += v.h->tris_extend;
-                acc.nodes_shadow += v.h->nodes_shadow; acc.tris_shadow += v.h->tris_shadow;
-                if (w > 0) {                                            // join: later work on s->stream sees this wave's film adds
+                remaining--;
+                cudaStream_t st = w == 0 ? s->stream : v.stream;
+                CU(cudaStreamSynchronize(st));
+                acc.rays += h.rays; acc.extend_rays += h.extend_rays; acc.shadow_rays += h.shadow_rays;
+                acc.nodes_extend += h.nodes_extend; acc.tris_extend += h.tris_extend;
+                acc.nodes_shadow += h.nodes_shadow; acc.tris_shadow += h.tris_shadow;
+                if (w > 0) {                                            // later work on s->stream sees this wave's film adds
                     CU(cudaEventRecord(v.done, v.stream));
                     CU(cudaStreamWaitEvent(s->stream, v.done, 0));
                 }
+            } else {
+                const int rc = enqueue_group(w, slot);
+                if (rc) return rc;
             }
         }
     }
