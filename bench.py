@@ -301,8 +301,10 @@ def run_ours(args):
         try:
             with open(os.path.join(ROOT, "profiles", "r01_extend_traffic.json")) as f:
                 tr = json.load(f)
-            traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]          # bytes per launch (8 Mi-ray queue)
-            traffic_src = tr["source"]
+            # the captured launch traced tr["rays"] rays; a launch of this run traces rays_per_launch: same bytes per ray
+            traffic = (tr["dram_bytes_read"] + tr["dram_bytes_write"]) / tr["rays"] * (ext_rays / max(1, ext_launches))
+            traffic_src = tr["source"] + "; %.1f DRAM bytes per ray, scaled to this run's rays per launch" % (
+                (tr["dram_bytes_read"] + tr["dram_bytes_write"]) / tr["rays"])
         except Exception:
             pass
         roofline = {
