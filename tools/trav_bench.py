@@ -1,6 +1,11 @@
 """A/B harness for traversal / pipeline tuning knobs on a GPU box (diagnostic, not the bench).
 
-  python tools/trav_bench.py "LMCU_TRAV=0" "LMCU_TRAV=1" "LMCU_TRAV=2,LMCU_CTAS=5" ...
+  python tools/trav_bench.py "LMCU_FETCH=12" "LMCU_FETCH=16,LMCU_CTAS=5" "LMCU_WAVES=1,LMCU_PT_POOL=8388608" ...
+
+Knobs liblmcu reads (tuning only): LMCU_FETCH (idle lanes before a warp refills), LMCU_CTAS (traversal CTAs per SM),
+LMCU_SHADE_GRID (shade CTAs per SM), LMCU_WAVES (staggered wavefronts), LMCU_PT_POOL (paths in flight per wavefront),
+LMCU_LEAF (triangles per leaf slot), LMCU_BIG (size-class threshold denominator, 0 = off), LMCU_TRI64 (1 = FP64 triangle
+records, 0 = float records); LMCU_LIB points the binding at another build of the library.
 
 Each argument is a comma-separated list of environment settings applied before the scenes are created
 (liblmcu reads its knobs at lmcu_scene_create).  Per setting it prints:
@@ -49,7 +54,7 @@ def device_batch(sc, rays, reps=3):
 
 
 def main():
-    settings = sys.argv[1:] or ["LMCU_TRAV=1"]
+    settings = sys.argv[1:] or ["LMCU_FETCH=12"]
     c2 = scenes.cornell_spheres(64)
     t = time.time()
     c3 = scenes.heightfield_scene(C3_N) if C3_N > 0 else None
