@@ -22,10 +22,11 @@
 #include "trace.cuh"
 
 #ifndef LMCU_SHADE_BLOCK
-#define LMCU_SHADE_BLOCK 256   // threads per CTA of the shade kernel
+#define LMCU_SHADE_BLOCK 64    // threads per CTA of the shade kernel: small CTAs slip into the register space a single
+                               // traversal CTA of the other wavefront frees (256 / 128 / 64 threads: 1810 / 1826 / 1833 Mpaths/s on C2)
 #endif
 #ifndef LMCU_SHADE_MINB
-#define LMCU_SHADE_MINB 3  // resident CTAs per SM the shade kernel is compiled for
+#define LMCU_SHADE_MINB 12 // resident CTAs per SM the shade kernel is compiled for (80 registers)
 #endif
 #ifndef LMCU_MINB
 #define LMCU_MINB 6      // resident 128-thread CTAs per SM the queue kernels are compiled for (register budget)
@@ -569,7 +570,7 @@ struct LmcuScene {
     uint32_t pt_capacity = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int fetch_threshold = 12;            // LMCU_FETCH
-    int shade_ctas_per_sm = 3;                   // LMCU_SHADE_GRID: CTAs per SM in the shade kernel's grid-stride grid
+    int shade_ctas_per_sm = LMCU_SHADE_MINB;     // LMCU_SHADE_GRID: CTAs per SM in the shade kernel's grid-stride grid
     int ctas_per_sm = LMCU_MINB;                 // LMCU_CTAS: resident 128-thread CTAs per SM for the persistent traversal grids
 
     DevScene dev() const {
