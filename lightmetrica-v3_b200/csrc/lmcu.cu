@@ -28,8 +28,12 @@
 #ifndef LMCU_SHADE_MINB
 #define LMCU_SHADE_MINB 12 // resident CTAs per SM the shade kernel is compiled for (80 registers)
 #endif
+#ifndef LMCU_TRAV_BLOCK
+#define LMCU_TRAV_BLOCK 128    // threads per CTA of the queue-traversal kernels (the loop is per warp; this only sets the granularity
+                               // at which the block scheduler hands SM resources to the kernels of different wavefronts)
+#endif
 #ifndef LMCU_MINB
-#define LMCU_MINB 6      // resident 128-thread CTAs per SM the queue kernels are compiled for (register budget)
+#define LMCU_MINB 6      // resident CTAs per SM the queue kernels are compiled for (register budget: 80 registers)
 #endif
 #include "prep.hpp"
 
@@ -357,7 +361,7 @@ struct BatchIO {                       // accel batches: LmcuRay in, LmcuHit out
 };
 
 template <typename TriT, bool COUNT>
-__global__ void __launch_bounds__(128, LMCU_MINB) k_intersect_q(DevScene s, const LmcuRay* __restrict__ rays, uint32_t n,
+__global__ void __launch_bounds__(LMCU_TRAV_BLOCK, LMCU_MINB) k_intersect_q(DevScene s, const LmcuRay* __restrict__ rays, uint32_t n,
                                                      LmcuHit* __restrict__ hits, uint32_t* cursor,
                                                      unsigned long long* counters, uint32_t* overflow) {
     BatchIO io; io.s = s; io.rays = rays; io.hits = hits;
@@ -386,7 +390,7 @@ struct ExtendIO {                      // pt extend: path queue in, float4 hit r
 };
 
 template <typename TriT, bool COUNT>
-__global__ void __launch_bounds__(128, LMCU_MINB) k_pt_extend_q(DevScene s, PathQueue q, float4* hits, PtCounters* ctr, int cur) {
+__global__ void __launch_bounds__(LMCU_TRAV_BLOCK, LMCU_MINB) k_pt_extend_q(DevScene s, PathQueue q, float4* hits, PtCounters* ctr, int cur) {
     ExtendIO io; io.ray_o = q.ray_o; io.ray_d = q.ray_d; io.hits = hits;
     TraverseCounters tc; tc.nodes = tc.tris = 0;
     trace_queue<false, COUNT, TriT>(s.nodes, scene_tris<TriT>(s), ctr->count[cur], &ctr->fetch_extend, io, &ctr->overflow, &tc, s.fetch_threshold);
@@ -414,7 +418,7 @@ struct ShadowIO {                      // pt shadow: visible (include/lm/scene.h
 };
 
 template <typename TriT, bool COUNT>
-__global__ void __launch_bounds__(128, LMCU_MINB) k_pt_shadow_q(DevScene s, ShadowQueue sq, float* film, PtCounters* ctr) {
+__global__ void __launch_bounds__(LMCU_TRAV_BLOCK, LMCU_MINB) k_pt_shadow_q(DevScene s, ShadowQueue sq, float* film, PtCounters* ctr) {
     const uint32_t n = ctr->shadow_count;
     if (blockIdx.x == 0 && threadIdx.x == 0) { ctr->rays += n; ctr->shadow_rays += n; }
     ShadowIO io; io.ray_o = sq.ray_o; io.ray_d = sq.ray_d; io.contrib = sq.contrib; io.film = film;
@@ -936,8 +940,8 @@ static int launch_intersect(LmcuScene* s, const LmcuRay* d_rays, int64_t n, Lmcu
     for (int64_t off = 0; off < n; off += kChunk) {
         const uint32_t m = (uint32_t)std::min<int64_t>(kChunk, n - off);
         CU(cudaMemsetAsync(s->cursor.p, 0, sizeof(unsigned long long), st));
-        const unsigned blocks = (unsigned)std::min<int64_t>((m + 127) / 128, (int64_t)s->num_sms * s->ctas_per_sm);
-        LMCU_DISPATCH(k_intersect_q, s->fp32, count, blocks, 128, st, d, d_rays + off, m, d_hits + off,
+        const unsigned blocks = (unsigned)std::min<int64_t>((m + LMCU_TRAV_BLOCK - 1) / LMCU_TRAV_BLOCK, (int64_t)s->num_sms * s->ctas_per_sm);
+        LMCU_DISPATCH(k_intersect_q, s->fp32, count, blocks, LMCU_TRAV_BLOCK, st, d, d_rays + off, m, d_hits + off,
                       (uint32_t*)s->cursor.p, s->cursor.p + 1, s->flags.p);
         CU(cudaGetLastError());
     }
@@ -1242,12 +1246,12 @@ static int pt_pass(LmcuScene* s, const PtParams& pp_all, bool count, PtAccum& ac
             k_pt_advance<<<1, 1, 0, st>>>(pp[w], v.ctr.p, cur);
             k_pt_generate<<<gen_blocks, 256, 0, st>>>(d, pp[w], q[w][cur], sq[w], v.ctr.p);
             cudaEventRecord(ev[0], st);
-            LMCU_DISPATCH(k_pt_extend_q, s->fp32, count, q_blocks, 128, st, d, q[w][cur], v.hits.p, v.ctr.p, cur);
+            LMCU_DISPATCH(k_pt_extend_q, s->fp32, count, q_blocks, LMCU_TRAV_BLOCK, st, d, q[w][cur], v.hits.p, v.ctr.p, cur);
             cudaEventRecord(ev[1], st);
             if (s->composite) k_pt_shade<true><<<shade_blocks, LMCU_SHADE_BLOCK, 0, st>>>(d, pp[w], q[w][cur], q[w][cur ^ 1], sq[w], v.hits.p, s->film.p, v.ctr.p, cur);
             else k_pt_shade<false><<<shade_blocks, LMCU_SHADE_BLOCK, 0, st>>>(d, pp[w], q[w][cur], q[w][cur ^ 1], sq[w], v.hits.p, s->film.p, v.ctr.p, cur);
             cudaEventRecord(ev[2], st);
-            LMCU_DISPATCH(k_pt_shadow_q, s->fp32, count, q_blocks, 128, st, d, sq[w], s->film.p, v.ctr.p);
+            LMCU_DISPATCH(k_pt_shadow_q, s->fp32, count, q_blocks, LMCU_TRAV_BLOCK, st, d, sq[w], s->film.p, v.ctr.p);
             cudaEventRecord(ev[3], st);
             v.cur ^= 1;
             acc.launches += 5;
