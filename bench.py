@@ -259,11 +259,10 @@ def run_ours(args):
         sc2.close()
         return film
 
-    # one untimed pass at a few spp: the first scene of this kind pays the process-wide one-off allocation of a second
-    # set of path pools (the resident scene above keeps its own), exactly like the warm-up of the timed loop above
-    spp_keep, spp = spp, 4
+    # one untimed pass: the first scene of this kind pays the process-wide one-off allocation of a second set of path
+    # pools (the resident scene above keeps its own; the pools are sized by the job, so the warm-up runs the same job),
+    # exactly like the warm-up of the timed loop above
     e2e_step()
-    spp = spp_keep
     sync()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
