@@ -802,6 +802,8 @@ LM_COMP_REG_IMPL(Renderer_AO_Cuda, "renderer::ao_cuda");
    Wavefront path tracer on CUDA devices; same parameters as ``renderer::pt`` plus:
 
    :param int device: CUDA device index. Default: 0.
+   :param int wavefronts: Staggered wavefront loops per GPU (each on its own CUDA stream; their kernels overlap).
+                          Default: 0 = the library's default (2). The image does not depend on it.
    :param list devices: Render on several GPUs of this machine by SAMPLE SPLIT: the scene and BVH are replicated,
                         device *g* renders its block of the ``spp`` sample indices of every pixel into a private film,
                         and the first device combines the films with one kernel over NVLink peer memory that also
@@ -820,6 +822,7 @@ private:
     long long samples_per_iter_ = 0;            // spi::time
     Float render_time_ = 0_f;                   // {spp,spi}::time
     std::vector<int> devices_;
+    int wavefronts_ = 0;                        // LmcuRenderParams::wavefronts (0 = library default)
 
 public:
     virtual void construct(const Json& prop) override {
@@ -851,6 +854,7 @@ public:
             }
             else LM_THROW_EXCEPTION(Error::InvalidArgument, "renderer::pt_cuda: unknown scheduler '{}'", name);
         }
+        wavefronts_ = json::value<int>(prop, "wavefronts", 0);
         devices_ = json::value<std::vector<int>>(prop, "devices", std::vector<int>{ device_ });
         if (devices_.empty() || devices_.size() > LMCU_MAX_PEERS + 1) {
             LM_THROW_EXCEPTION(Error::InvalidArgument, "renderer::pt_cuda: 'devices' must name 1..{} GPUs", LMCU_MAX_PEERS + 1);
@@ -868,6 +872,7 @@ public:
         p.scheduler = scheduler_;
         p.render_time = render_time_;
         p.samples_per_iter = samples_per_iter_;
+        p.wavefronts = wavefronts_;
         p.seed = seed_ ? *seed_ : math::rng_seed();
         std::vector<float> rgb;
         float* target = film_target(rgb);

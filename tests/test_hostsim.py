@@ -170,3 +170,32 @@ def test_edge_cases_closest_hit(reference, sim):
             again = ss.intersect(at)
             assert all(np.array_equal(again[k], hs[k][ok]) for k in ("t", "u", "v", "primitive", "face")), name
         rs.close()
+
+
+def test_scene_description_validation(sim):
+    """prepare_scene (csrc/prep.hpp) — the validation lmcu_scene_upload runs before anything reaches the device — refuses
+    inconsistent descriptions with the reference's error classes (missing primitives = Unsupported, include/lm/scene.h:232-238;
+    bad indices = InvalidArgument).  Runs on the CPU through the hostsim build of the same header."""
+    def fails(sb, needle):
+        with pytest.raises(RuntimeError) as e:
+            sim.SimScene(sb)
+        assert needle in str(e.value), str(e.value)
+
+    fails(scenes.SceneBuilder(), "Missing primitives")
+    sb = scenes.cornell_box(); sb.primitives[0]["material"] = 99
+    fails(sb, "bad material index")
+    sb = scenes.cornell_box(); sb.primitives[0]["mesh"] = 99
+    fails(sb, "bad mesh index")
+    sb = scenes.cornell_box(); sb.primitives[0]["material"] = sb.diffuse((1, 1, 1), map_kd=5)
+    fails(sb, "bad mapKd texture index")
+    sb = scenes.cornell_box(); sb.primitives[0]["material"] = sb.mixture_rr([(sb.glass(1.5), 1.0)])
+    fails(sb, "diffuse, glossy, mirror or mask")
+    sb = scenes.cornell_box(); sb.primitives[0]["material"] = sb.mixture_marginalized([(0, -1.0)])
+    fails(sb, "weight must be positive")
+    sb = scenes.cornell_box(); sb.set_envconst((1, 1, 1)); sb.set_envconst((1, 1, 1))
+    fails(sb, "Environment light is already registered")
+    sb = scenes.cornell_box(); sb.add_directional_light((1, 1, 1), (0, 0, 0))
+    fails(sb, "zero direction")
+    sb = scenes.cornell_box(); sb.add_texture(np.zeros((2, 2, 3), np.float32)); sb.textures[0]["data"] = np.zeros((2, 2, 3), np.float32)[:, :, :2]
+    with pytest.raises((RuntimeError, AssertionError, ValueError)):
+        sim.SimScene(sb)
