@@ -227,6 +227,22 @@ LMCU_HD void collapse_body(const CollapseCtx& c, CollapseItem item) {
             ch[best] = b.left;
             ch[nch++] = b.right;
         }
+        // Bottom nodes: every child is a leaf cluster now and slots are left over.  Split the clusters (largest area
+        // first) down to single triangles while slots remain: same node, tighter leaf boxes, fewer FP64 triangle tests.
+        while (nch < 8) {
+            int best = -1;
+            float best_area = -1.f;
+            for (int k = 0; k < nch; k++) {
+                if (ch[k] >= (uint32_t)(c.n - 1)) continue;                 // a single triangle
+                const BinNode& b = bin[ch[k]];
+                const float a = box_area(b.lo, b.hi);
+                if (a > best_area) { best_area = a; best = k; }
+            }
+            if (best < 0) break;
+            const BinNode& b = bin[ch[best]];
+            ch[best] = b.left;
+            ch[nch++] = b.right;
+        }
     }
     // node bounds
     float lo[3] = { 3.0e38f, 3.0e38f, 3.0e38f }, hi[3] = { -3.0e38f, -3.0e38f, -3.0e38f };
