@@ -24,7 +24,7 @@ def build():
         for f in ("common.cuh", "bvh.cuh", "build.cuh", "shade.cuh", "kernels.cuh", "prep.hpp")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2", "-fPIC", "-ffp-contract=off", "-shared",
-                               "-o", so, srcs[0]])
+                               "-o", so, srcs[0]] + os.environ.get("HOSTSIM_CXXFLAGS", "").split())
     return so
 
 
