@@ -476,6 +476,14 @@ struct BlockCache {
         bytes -= n;
         return p;
     }
+    // gives every parked block of `device` back to the driver (an allocation failed: the memory is needed now)
+    void flush(int device) {
+        std::lock_guard<std::mutex> lk(mu);
+        for (auto it = blocks.begin(); it != blocks.end();) {
+            if (it->first.first == device) { cudaFree(it->second); bytes -= it->first.second; it = blocks.erase(it); }
+            else ++it;
+        }
+    }
     bool park(int device, size_t n, void* p) {
         std::lock_guard<std::mutex> lk(mu);
         if (n < (size_t(1) << 20) || bytes + n > kCacheBytes) return false;
@@ -499,7 +507,13 @@ struct DBuf {
         cudaGetDevice(&device);
         p = (T*)g_cache.take(device, count * sizeof(T));
         if (p) return cudaSuccess;
-        return cudaMalloc((void**)&p, count * sizeof(T));
+        cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+        if (e == cudaErrorMemoryAllocation) {            // out of memory with blocks parked in the cache: release them, retry once
+            cudaGetLastError();
+            g_cache.flush(device);
+            e = cudaMalloc((void**)&p, count * sizeof(T));
+        }
+        return e;
     }
     void release() {
         if (p && !g_cache.park(device, n * sizeof(T), p)) cudaFree(p);
