@@ -722,14 +722,17 @@ protected:
 
     void write_film(const std::vector<float>& rgb, bool skip_black) const {
         if (dynamic_cast<Film_Cuda*>(film_)) return;                       // already written in place
+        // a foreign film takes its pixels one set_pixel at a time (film::bitmap: a CAS loop on a 24-byte atomic per call,
+        // src/film/film_bitmap.cpp:41-54): rows go out through the reference's own parallel::foreach, otherwise this
+        // write-back of a 4K image costs more than rendering it
         const auto size = film_->size();
-        for (int y = 0; y < size.h; y++) {
+        parallel::foreach(size.h, [&](long long y, int) {
             for (int x = 0; x < size.w; x++) {
                 const float* c = &rgb[(size_t(y) * size.w + x) * 3];
                 if (skip_black && c[0] == 0.f && c[1] == 0.f && c[2] == 0.f) continue;
-                film_->set_pixel(x, y, Vec3(c[0], c[1], c[2]));
+                film_->set_pixel(x, int(y), Vec3(c[0], c[1], c[2]));
             }
-        }
+        });
     }
 };
 

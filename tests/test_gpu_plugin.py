@@ -152,11 +152,13 @@ def test_renderer_pt_cuda_schedulers_and_image_mode(plugin):
     pt = abi.render_params(w, h, max_verts=10, scheduler=abi.SCHED_TIME, render_time=0.1)
     ft, elapsed, proc = rs.render("renderer::pt_cuda", pt)
     assert proc >= spp and elapsed >= 0.09
-    assert_pt_parity(fr, ft, spp, rel_mean=0.01)
+    # a time budget buys tens of thousands of spp: the difference image is then the 1024-spp reference's own skewed noise,
+    # so the block z-test is widened (see test_pt_time_schedulers); equal-spp renders keep the full gate
+    assert_pt_parity(fr, ft, spp, rel_mean=0.01, z_frac=0.04)
     pti = abi.render_params(w, h, max_verts=10, scheduler=abi.SCHED_TIME, render_time=0.1, primary_ray_sampling_mode=abi.PRIMARY_IMAGE)
     fti, _, proc = rs.render("renderer::pt_cuda", pti)
     assert proc % 100000 == 0 and proc >= w * h * spp
-    assert_pt_parity(fr, fti, spp, rel_mean=0.01)
+    assert_pt_parity(fr, fti, spp, rel_mean=0.01, z_frac=0.04)
     rs.close()
 
 
