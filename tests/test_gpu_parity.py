@@ -294,6 +294,22 @@ def test_g3_textured_and_mixture_materials(reference, tmp_path, kind):
     rs.close(); sc.close()
 
 
+@pytest.mark.parametrize("kind", ["obj", "mix"])
+def test_textured_and_mixture_materials_vs_golden(tmp_path, kind):
+    """The same material set against the COMMITTED outputs of the reference (tests/golden/reference_outputs_materials.npz):
+    needs no reference on the box."""
+    golden = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_outputs_materials.npz"))
+    sb = scenes.textured_scene(tmp_path, 12, kind)
+    sc = lmcu.Scene(sb)
+    fg, _ = sc.render("raycast", abi.render_params(192, 108))
+    fr = golden[kind + "_raycast"]
+    d = np.abs(fg - fr).max(axis=2)
+    assert (d > 1e-4).mean() < 3e-3 and rmse(fg[d <= 1e-4], fr[d <= 1e-4]) <= 1e-6
+    fg, _ = sc.render("pt", abi.render_params(96, 54, spp=1024, max_verts=12))
+    assert_pt_parity(golden[kind + "_pt_mis"], fg, 1024, rel_mean=0.01)
+    sc.close()
+
+
 def test_composite_material_validation():
     """Mixture entries must be single-component lobes (the reference hands an entry component 0 whatever it is,
     material_mixture.cpp:67-78), texture indices must exist."""

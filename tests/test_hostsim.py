@@ -118,6 +118,22 @@ def test_textured_and_mixture_materials(reference, sim, tmp_path, kind):
     rs.close()
 
 
+@pytest.mark.parametrize("kind", ["obj", "mix"])
+def test_textured_and_mixture_materials_vs_golden(sim, tmp_path, kind):
+    """Same source against the committed reference outputs (no reference needed): raycast to G2 tolerances, pt means."""
+    import os
+    golden = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_outputs_materials.npz"))
+    sb = scenes.textured_scene(tmp_path, 12, kind)
+    ss = sim.SimScene(sb)
+    fs = ss.render("raycast", abi.render_params(192, 108))
+    fr = golden[kind + "_raycast"]
+    d = np.abs(fs - fr).max(axis=2)
+    assert (d > 1e-4).mean() < 3e-3 and rmse(fs[d <= 1e-4], fr[d <= 1e-4]) <= 1e-6
+    fs = ss.render("pt", abi.render_params(96, 54, spp=64, max_verts=12))
+    gm, sm = golden[kind + "_pt_mis"].mean(axis=(0, 1)), fs.mean(axis=(0, 1))
+    assert (np.abs(sm - gm) <= 0.03 * gm).all()           # 64 spp against the 1024-spp golden image: means only
+
+
 def test_point_and_directional_lights(reference, sim):
     sb = scenes.delta_lights_scene(2, 12)
     rs, ss = reference.RefScene(sb), sim.SimScene(sb)

@@ -150,6 +150,23 @@ def test_port_composite_materials_bit_exact_vs_reference(reference, port, tmp_pa
     ps.close()
 
 
+GOLDEN_MAT = np.load(os.path.join(ROOT, "tests", "golden", "reference_outputs_materials.npz"))
+
+
+@pytest.mark.parametrize("kind", ["obj", "mix"])
+def test_port_composite_materials_vs_golden(port, tmp_path, kind):
+    """The committed outputs of the reference for the OBJ-import material set (tests/golden/make_golden_materials.py): the
+    port's single-threaded pt must reproduce them bit for bit, its raycast image outside the tie pixels."""
+    sb = scenes.textured_scene(str(tmp_path), 12, kind)
+    ps = port.PortScene(sb)
+    f = ps.render("pt", abi.render_params(40, 24, spp=4, max_verts=12, seed=13), num_threads=1)
+    g = GOLDEN_MAT[kind + "_pt_1thread_seed13"]
+    assert g.max() > 0 and np.abs(f - g).max() <= 1e-12 * max(1.0, g.max())
+    r = ps.render("raycast", abi.render_params(192, 108)).astype(np.float32)
+    assert (np.abs(r - GOLDEN_MAT[kind + "_raycast"]).max(axis=2) > 0).mean() < 3e-3
+    ps.close()
+
+
 def test_port_vs_reference_accel(reference, port):
     sb = scenes.cornell_spheres(16)
     rs, ps = reference.RefScene(sb), port.PortScene(sb)
