@@ -4,17 +4,22 @@
   python bench.py --gpus N --steps K --warmup W            our CUDA path on N B200s
   python bench.py --impl reference --gpus N --steps K ...   the reference's own CPU path (oracle/_ref)
 
-Workload (config.workload): BASELINE.json configs[1] = C2, `renderer::pt` of the procedural
-Cornell box with a diffuse and a glass UV sphere (32 268 triangles), area-light NEE + MIS,
-1920x1080, max_verts 20, seed 42 — one STEP renders the whole image at SPP samples per pixel
-(1024 on the GPU arm).  Metric: Mpaths/s = width*height*spp / elapsed / 1e6.
+Headline workload (config.workload): BASELINE.json configs[1] = C2, `renderer::pt` of the procedural Cornell box with a
+diffuse and a glass UV sphere (32 268 triangles), area-light NEE + MIS, 1920x1080, max_verts 20, seed 42 — one STEP renders
+the whole image at SPP samples per pixel (1024 on the GPU arm).  Metric: Mpaths/s = width*height*spp / elapsed / 1e6.
 
-N > 1 (torchrun, one rank per GPU): sample split.  The scene and BVH are replicated, rank r renders
-its own `spp` samples of every pixel with disjoint counter-RNG sample indices (sample_offset =
-r*spp); rank 0 then combines the fp32 films with liblmcu's own kernel, which reads the peers' films
-over NVLink peer memory and fuses the sum with the 1/(N*spp) rescale (--reduce nccl: dist.reduce).
-Per-GPU work is fixed as N grows => "scaling": "weak".  value = paths of all ranks / max-over-ranks
-device time (the reduce is inside the timed region).
+N > 1 (torchrun, one rank per GPU): sample split.  The scene and BVH are replicated, rank r renders its own samples of
+every pixel with disjoint counter-RNG sample indices; the fp32 films are then combined by liblmcu's own kernels over
+NVLink peer memory (CUDA IPC): slice-parallel by default (every rank sums its slice of all films and stores it, rescaled,
+into rank 0's film), --reduce root = rank 0 pulls whole films, --reduce nccl = dist.reduce.  The headline `value` keeps
+per-GPU work fixed as N grows ("scaling": "weak": 1024 spp per GPU); the line also carries `c5_strong`: BASELINE configs[4],
+the same scene at 3840x2160 with a FIXED total spp split over the N ranks, timed the same way, with the single-GPU time
+of the same job measured in the same run (strong_efficiency = T1 / (N * TN)) and the combined image asserted against the
+single-GPU image.
+
+Everything else the line carries is measured live in the same run on rank 0: the roofline of the dominant kernel and, for
+the configs whose BVH does not fit the L2 (C3, C4), the HBM fraction; the drop-in path through the unmodified reference
+(`renderer::pt_cuda` loaded as a plugin); statistical parity of the 1024-spp GPU film against the CPU baseline's film.
 """
 import argparse
 import json
@@ -28,11 +33,14 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "lightmetrica-v3_b200"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 W, H, MAX_VERTS, SEED = 1920, 1080, 20, 42
 GPU_SPP = 1024
+C5_W, C5_H, C5_TOTAL_SPP = 3840, 2160, 2048
 REF_SPP_PER_STEP = 16         # reference arm / cpu_baseline: bounded sample of the same workload (~9 s of CPU work per step)
 METRIC = "Mpaths/s renderer::pt (C2: Cornell box + diffuse/glass spheres, 1920x1080, max_verts 20, MIS)"
+PLUGIN = os.path.join(ROOT, "lightmetrica-v3_b200", "plugin", "lm_cuda")
 
 
 def load_peaks():
@@ -41,6 +49,15 @@ def load_peaks():
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def load_profile(name):
+    """ncu figures committed under profiles/ (per-launch DRAM bytes, lane efficiency ...) of the kernels timed live here."""
+    try:
+        with open(os.path.join(ROOT, "profiles", name)) as f:
+            return json.load(f)
+    except Exception:
+        return None
 
 
 class ClockSampler:
@@ -76,22 +93,28 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def reference_rate(spp, steps, warmup):
-    """The reference's renderer::pt + accel::sahbvh under parallel::openmp on every host core."""
+# ----------------------------------------------------------------------------------------------------------------------
+# reference arm
+# ----------------------------------------------------------------------------------------------------------------------
+def reference_rate(spp, steps, warmup, rs=None):
+    """The reference's renderer::pt + accel::sahbvh under parallel::openmp on every host core.  Returns the rate, the mean
+    time per render, the thread count and the last film."""
     from oracle import ref
     from lmcu import abi, scenes
     threads = ref.init(0)
-    sb = scenes.cornell_spheres(64)
-    rs = ref.RefScene(sb)
+    own = rs is None
+    if own:
+        rs = ref.RefScene(scenes.cornell_spheres(64))
     p = abi.render_params(W, H, spp=spp, max_verts=MAX_VERTS, seed=SEED)
-    times = []
+    times, film = [], None
     for i in range(warmup + steps):
-        _, elapsed, _ = rs.render("pt", p)
+        film, elapsed, _ = rs.render("pt", p)
         if i >= warmup:
             times.append(elapsed)
-    rs.close()
+    if own:
+        rs.close()
     t = sum(times) / len(times)
-    return W * H * spp / t / 1e6, t, threads
+    return W * H * spp / t / 1e6, t, threads, film
 
 
 def run_reference(args):
@@ -102,7 +125,7 @@ def run_reference(args):
     if not ref.available():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/liblmref.so was not built"}))
         return
-    value, t, threads = reference_rate(REF_SPP_PER_STEP, args.steps, args.warmup)
+    value, t, threads, _ = reference_rate(REF_SPP_PER_STEP, args.steps, args.warmup)
     sample = "%dx%d @ %d spp per step (full C2 image, bounded spp; rate is spp-independent)" % (W, H, REF_SPP_PER_STEP)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "Mpaths/s", "n_gpus": args.gpus,
@@ -115,28 +138,47 @@ def run_reference(args):
     }))
 
 
-def make_reducer(torch, dist, lmcu, D, sc, rank, world, local_rank, mode):
-    """Film combine for one scene: 'p2p' = liblmcu's fused peer-memory reduce+rescale kernel, 'nccl' = dist.reduce."""
-    if mode == "p2p":
-        return D.PeerFilmReducer(dist, rank, world, sc.film_ipc_handle, lambda h: lmcu.ipc_open(local_rank, h),
-                                 sc.film_reduce_peers, torch.cuda.synchronize)
+# ----------------------------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------------------------
+REDUCE_NAMES = {
+    "slice": "fused slice-parallel reduce + rescale kernel over NVLink peer memory (CUDA IPC): every rank sums its slice of all "
+             "films and stores it into rank 0's film",
+    "root": "fused root-gather reduce + rescale kernel over NVLink peer memory (CUDA IPC)",
+    "nccl": "NCCL reduce + scale",
+}
+
+
+def make_reducer(torch, dist, lmcu, D, scene, rank, world, local_rank, mode):
+    """Film combine: 'slice' / 'root' = liblmcu's fused peer-memory kernels, 'nccl' = dist.reduce.  `scene` may be a callable
+    returning the current scene.  Returns (reduce(total_spp), close())."""
+    if mode in ("slice", "root"):
+        def any_changed(flag):
+            t = torch.tensor([1 if flag else 0], device="cuda", dtype=torch.int32)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return bool(t.item())
+        red = D.PeerFilmReducer(dist, rank, world, D.SceneFilmOps(lmcu, scene, local_rank, torch.cuda.synchronize), any_changed, mode=mode)
+        return red, red.close
 
     def nccl_reduce(total_spp):
+        sc = scene() if callable(scene) else scene
         ptr, n = sc.film_device()
         film = D.film_as_tensor(torch, ptr, n, local_rank)
         D.reduce_and_rescale(film, total_spp, rank, world, dist)
-    return nccl_reduce
+    return nccl_reduce, (lambda: None)
 
 
-def accel_rates(torch, lmcu, scenes, stream):
-    """BASELINE.json configs[2] (C3): closest-hit throughput on the 9 999 392-triangle heightfield with DEVICE-resident
-    ray batches — coherent pinhole rays and incoherent cosine-bounce rays.  Informational (not the headline)."""
+def accel_rates(torch, lmcu, scenes, stream, peak):
+    """BASELINE.json configs[2] (C3): closest-hit throughput on the 9 999 392-triangle heightfield (627 MB of BVH + triangle
+    records: HBM-resident) with DEVICE-resident ray batches — coherent pinhole rays and incoherent cosine-bounce rays —
+    and the HBM roofline of k_intersect_q on both."""
     import numpy as np
     sb = scenes.heightfield_scene(2236)
     sc = lmcu.Scene(sb)
     sc.set_stream(stream.cuda_stream)
-    out = {"triangles": int(sc.build_stats.num_triangles), "build_ms": sc.build_stats.elapsed * 1e3,
-           "bvh_bytes": int(sc.build_stats.node_bytes + sc.build_stats.triangle_bytes)}
+    bs = sc.build_stats
+    out = {"triangles": int(bs.num_triangles), "build_ms": bs.elapsed * 1e3, "bvh_bytes": int(bs.node_bytes + bs.triangle_bytes),
+           "tri_record_bytes": 48 if bs.triangles_fp32 else 80, "sah_cost": bs.sah_cost}
 
     def run(rays, reps=3):
         d_rays = torch.from_numpy(rays.view(np.float64).reshape(-1, 8)).cuda()
@@ -149,20 +191,109 @@ def accel_rates(torch, lmcu, scenes, stream):
             e1.record(stream)
             torch.cuda.synchronize()
             best = min(best, e0.elapsed_time(e1) * 1e-3)
-        return len(rays) / best / 1e6, d_hits.cpu().numpy().view(scenes.HIT_DTYPE).reshape(-1)
+        return len(rays) / best, d_hits.cpu().numpy().view(scenes.HIT_DTYPE).reshape(-1)
+
+    def roof(rate, rays):
+        sc.intersect(rays[:1 << 18], counted=True)
+        nn, nt = sc.nodes_per_ray, sc.tris_per_ray
+        b_ray = 64 + 32 + nn * 80 + nt * out["tri_record_bytes"]       # LmcuRay in (64 B) + LmcuHit out (32 B): the FP64 batch ABI
+        return {"mrays_per_s": rate / 1e6, "nodes_per_ray": nn, "tris_per_ray": nt, "bytes_per_ray": b_ray,
+                "achieved": rate * b_ray / 1e9, "peak": peak, "unit": "GB/s", "frac": rate * b_ray / 1e9 / peak, "rays": int(len(rays))}
 
     rays = scenes.camera_rays(sb.camera, 2048, 2048)
-    out["coherent_mrays_per_s"], hits = run(rays)
+    rate, hits = run(rays)
+    out["coherent"] = roof(rate, rays)
     p = sb.meshes[0][0]
     gn = np.cross(p[:, 1] - p[:, 0], p[:, 2] - p[:, 0])
     gn /= np.linalg.norm(gn, axis=1, keepdims=True)
     bounce = scenes.bounce_rays(rays, hits, lambda h: gn[h["face"]].copy())
-    out["incoherent_mrays_per_s"], _ = run(bounce)
-    sc.intersect(rays[:1 << 18], counted=True)
-    out["nodes_per_ray"], out["tris_per_ray"] = sc.nodes_per_ray, sc.tris_per_ray
-    out["rays"] = {"coherent": int(len(rays)), "incoherent": int(len(bounce))}
+    rate, _ = run(bounce)
+    out["incoherent"] = roof(rate, bounce)
+    prof = load_profile("r02_ncu_c3_intersect.json")
+    if prof:
+        out["incoherent"]["traffic"] = prof.get("dram_bytes_per_ray", 0) * len(bounce)
+        out["incoherent"]["traffic_source"] = prof.get("source")
     sc.close()
     return out
+
+
+def c4_rates(lmcu, abi, scenes, stream, peak):
+    """BASELINE.json configs[3] (C4): renderer::pt, 1000 instances of a 49 728-triangle sphere (49.7 M triangles), glossy /
+    glass / mirror / diffuse, constant env light, 3840x2160 — bounded spp.  HBM roofline of k_pt_extend_q on it."""
+    sb = scenes.instanced_spheres(grid=10, num_theta=112)
+    sc = lmcu.Scene(sb)
+    sc.set_stream(stream.cuda_stream)
+    bs = sc.build_stats
+    out = {"triangles": int(bs.num_triangles), "build_ms": bs.elapsed * 1e3, "bvh_bytes": int(bs.node_bytes + bs.triangle_bytes),
+           "tri_record_bytes": 48 if bs.triangles_fp32 else 80, "sah_cost": bs.sah_cost, "layout": getattr(bs, "layout_name", "flattened")}
+    spp = 8
+    _, stc = sc.render("pt", abi.render_params(C5_W, C5_H, spp=2, max_verts=MAX_VERTS, seed=SEED, count_traversal=True), download=False)
+    nn, nt = stc["bvh_nodes_per_ray"], stc["bvh_tris_per_ray"]
+    sc.render("pt", abi.render_params(C5_W, C5_H, spp=2, max_verts=MAX_VERTS, seed=SEED), download=False)
+    _, st = sc.render("pt", abi.render_params(C5_W, C5_H, spp=spp, max_verts=MAX_VERTS, seed=SEED), download=False)
+    out.update({"spp": spp, "mpaths_per_s": st["paths"] / st["elapsed"] / 1e6, "mrays_per_s": st["rays"] / st["elapsed"] / 1e6})
+    _, solo = sc.render("pt", abi.render_params(C5_W, C5_H, spp=spp, max_verts=MAX_VERTS, seed=SEED, wavefronts=1), download=False)
+    b_ray = 32 + 16 + nn * 80 + nt * out["tri_record_bytes"]
+    rate = solo["extend_rays"] / solo["extend_seconds"]
+    out["extend"] = {"kernel": "k_pt_extend_q", "nodes_per_ray": nn, "tris_per_ray": nt, "bytes_per_ray": b_ray,
+                     "mrays_per_s": rate / 1e6, "achieved": rate * b_ray / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": rate * b_ray / 1e9 / peak, "share_of_step": solo["extend_seconds"] / solo["elapsed"],
+                     "measured_in": "single-wavefront render (the kernel timed with nothing beside it)"}
+    prof = load_profile("r02_ncu_c4_extend.json")
+    if prof:
+        out["extend"]["traffic"] = prof.get("dram_bytes_per_ray", 0) * solo["extend_rays"] / max(1, solo["extend_launches"])
+        out["extend"]["traffic_source"] = prof.get("source")
+    sc.close()
+    return out
+
+
+def c1_rates(lmcu, abi, scenes, stream):
+    """BASELINE.json configs[0] (C1): renderer::raycast of the 36-triangle Cornell box at 1920x1080."""
+    sb = scenes.cornell_box()
+    sc = lmcu.Scene(sb)
+    sc.set_stream(stream.cuda_stream)
+    p = abi.render_params(W, H)
+    best = 1e9
+    for _ in range(4):
+        _, st = sc.render("raycast", p, download=False)
+        best = min(best, st["elapsed"])
+    sc.close()
+    return {"ms": best * 1e3, "mrays_per_s": W * H / best / 1e6}
+
+
+def plugin_e2e(sb, abi, spp, paths):
+    """The drop-in path a Lightmetrica user calls: the UNMODIFIED reference (oracle/_ref/liblm.so) loads plugin/lm_cuda.so,
+    holds the scene as its own lm::Scene, creates renderer::pt_cuda from JSON and calls Renderer::render(); the image comes
+    back through lm::Film::buffer().  Wall clock around asset creation + render() + buffer() copy, host buffers on both sides."""
+    from oracle import ref
+    ref.init(0)
+    ref.load_plugin(PLUGIN)
+    rs = ref.RefScene(sb)                                   # host lm::Scene (its CPU accel::sahbvh build is not timed)
+    p = abi.render_params(W, H, spp=spp, max_verts=MAX_VERTS, seed=SEED)
+    out = {}
+    film = None
+    for name, film_key, extra in (("plugin_film_cuda", "film::cuda", '{"cache": false}'),
+                                  ("plugin_film_cuda_cached", "film::cuda", None),
+                                  ("plugin_film_bitmap", "film::bitmap", '{"cache": false}')):
+        os.environ["LMREF_FILM"] = film_key
+        if extra:
+            os.environ["LMREF_EXTRA_PROPS"] = extra
+        else:
+            os.environ.pop("LMREF_EXTRA_PROPS", None)
+        try:
+            rs.render("renderer::pt_cuda", abi.render_params(W, H, spp=16, max_verts=MAX_VERTS, seed=SEED))    # warm the path pools
+            t0 = time.perf_counter()
+            film, elapsed, processed = rs.render("renderer::pt_cuda", p)
+            wall = time.perf_counter() - t0
+            out[name] = {"value": paths / wall / 1e6, "unit": "Mpaths/s", "wall_s": wall, "render_json_elapsed_s": elapsed,
+                         "processed": int(processed)}
+        finally:
+            os.environ.pop("LMREF_FILM", None)
+            os.environ.pop("LMREF_EXTRA_PROPS", None)
+    out["what"] = ("reference liblm + load_plugin(lm_cuda): lm::load<Film> + lm::load<Renderer>('renderer::pt_cuda') + render() + Film::buffer(); "
+                   "cache:false = the scene is exported from lm::Scene (traverse_primitive_nodes / foreach_triangle), uploaded and built "
+                   "inside the timed region; _cached = the device scene of an earlier render is reused")
+    return out, rs, film
 
 
 def run_ours(args):
@@ -202,16 +333,13 @@ def run_ours(args):
     torch.cuda.set_stream(stream)
     sc.set_stream(stream.cuda_stream)
     npix = W * H
-    reducer = None
+    reduce_main, close_main = make_reducer(torch, dist, lmcu, D, sc, rank, world, local_rank, args.reduce)
 
     def step():
         """One pass of the hot path: render this rank's samples of every pixel (sums), combine the films, rescale."""
-        nonlocal reducer
         p = abi.render_params(W, H, spp=spp, max_verts=MAX_VERTS, seed=SEED, sample_offset=rank * spp, rescale=0)
         _, st = sc.render("pt", p, download=False)
-        if reducer is None:
-            reducer = make_reducer(torch, dist, lmcu, D, sc, rank, world, local_rank, args.reduce)
-        reducer(world * spp)
+        reduce_main(world * spp)
         return st
 
     def sync():
@@ -219,6 +347,12 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        t = torch.tensor([v], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     for _ in range(args.warmup):
         step()
@@ -234,127 +368,238 @@ def run_ours(args):
     e1.record(stream)
     sync()
     clocks = sampler.stop() if rank == 0 else None
-    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms.item())
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
     ms_per_step = ms_total / args.steps
     paths_per_step = npix * spp * world
     value = paths_per_step / (ms_per_step * 1e-3) / 1e6
 
+    # ---- N > 1: the combined film is CHECKED, not just timed.  Small film (240x136), every rank renders its block of the
+    # sample indices; the film combined by the advertised reducer must equal (a) the film combined by dist.reduce and
+    # (b) rank 0's own render of ALL the sample indices (same counter-RNG streams: only the fp32 summation order differs).
+    multi_check = None
+    if world > 1:
+        cw, ch, ctotal = 240, 136, 16 * world
+        chk = lmcu.Scene(sb, device=local_rank)
+        chk.set_stream(stream.cuda_stream)
+        films = {}
+        for mode in dict.fromkeys([args.reduce, "slice", "root", "nccl"]):
+            red, close = make_reducer(torch, dist, lmcu, D, chk, rank, world, local_rank, mode)
+            off, cnt = D.sample_block(ctotal, rank, world)
+            chk.render("pt", abi.render_params(cw, ch, spp=cnt, max_verts=MAX_VERTS, seed=SEED, sample_offset=off, rescale=0), download=False)
+            red(ctotal)
+            films[mode] = chk.film_download(cw, ch).astype(np.float64) if rank == 0 else None
+            sync()
+            close()                                                     # unmap before the next reducer maps the same films
+        if rank == 0:
+            single, _ = chk.render("pt", abi.render_params(cw, ch, spp=ctotal, max_verts=MAX_VERTS, seed=SEED))
+            scale = np.abs(single).max()
+            multi_check = {"size": "%dx%d" % (cw, ch), "total_spp": ctotal,
+                           "max_abs_err_vs_single_gpu_render": {m: float(np.abs(f - single).max() / scale) for m, f in films.items()},
+                           "tolerance": 1e-4}
+            for m, f in films.items():
+                assert np.allclose(f, single, rtol=1e-4, atol=1e-5 * scale), "film combined by '%s' differs from the single-GPU render" % m
+            multi_check["pass"] = True
+        sync()
+        chk.close()
+
     # ---- end to end through the public API with HOST buffers: scene description (host arrays) -> H2D upload ->
-    # BVH build -> render -> film combine -> film D2H into a host array, every step, wall clock, max over ranks
+    # BVH build -> render -> film combine (the SAME reducer as the timed loop) -> film D2H into a host array, every step,
+    # wall clock, max over ranks
     desc_bytes = sum(p.nbytes + (n.nbytes if n is not None else 0) for p, n in sb.meshes)
     sync()
     e2e_steps = max(1, min(args.steps, 2))
+    cur = {}
+    reduce_e2e, close_e2e = make_reducer(torch, dist, lmcu, D, lambda: cur["sc"], rank, world, local_rank, args.reduce)
 
     def e2e_step():
-        sc2 = lmcu.Scene(sb, device=local_rank)
+        cur["sc"] = sc2 = lmcu.Scene(sb, device=local_rank)
         sc2.set_stream(stream.cuda_stream)
         p = abi.render_params(W, H, spp=spp, max_verts=MAX_VERTS, seed=SEED, sample_offset=rank * spp, rescale=0)
         sc2.render("pt", p, download=False)
-        make_reducer(torch, dist, lmcu, D, sc2, rank, world, local_rank, "nccl" if world > 1 else args.reduce)(world * spp)
+        reduce_e2e(world * spp)
         film = sc2.film_download(W, H) if rank == 0 else None           # D2H of the result
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()                                              # nobody recycles its film before rank 0 has read
         sc2.close()
         return film
 
     # one untimed pass: the first scene of this kind pays the process-wide one-off allocation of a second set of path
-    # pools (the resident scene above keeps its own; the pools are sized by the job, so the warm-up runs the same job),
-    # exactly like the warm-up of the timed loop above
+    # pools (the resident scene above keeps its own; the pools are sized by the job, so the warm-up runs the same job)
     e2e_step()
     sync()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         host_film = e2e_step()
-    t = torch.tensor([(time.perf_counter() - t0) / e2e_steps], device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e = {"value": paths_per_step / float(t.item()) / 1e6, "unit": "Mpaths/s",
+    t_e2e = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
+    close_e2e()
+    e2e = {"value": paths_per_step / t_e2e / 1e6, "unit": "Mpaths/s",
            "h2d_bytes_per_step": int(desc_bytes), "d2h_bytes_per_step": int(npix * 3 * 4),
-           "what": "lmcu.Scene(host scene description) [H2D + BVH build] + render('pt') + film combine + film D2H, "
-                   "wall clock, max over ranks"}
+           "what": "lmcu.Scene(host scene description) [H2D + BVH build] + render('pt') + film combine (%s) + film D2H, "
+                   "wall clock, max over ranks" % args.reduce}
+
+    # ---- C5 (BASELINE configs[4]): the same scene at 3840x2160, FIXED total spp split over the ranks (strong scaling)
+    c5 = None
+    if not args.no_c5:
+        total = args.c5_spp
+        off, cnt = D.sample_block(total, rank, world)
+
+        def c5_step(count):
+            sc.render("pt", abi.render_params(C5_W, C5_H, spp=count, max_verts=MAX_VERTS, seed=SEED, sample_offset=off, rescale=0), download=False)
+            reduce_main(total)
+
+        c5_step(max(1, cnt // 8))                                       # warm-up: 4K film + FP64 film + mappings
+        sync()
+        c5_steps = 2
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(stream)
+        for _ in range(c5_steps):
+            c5_step(cnt)
+        f1.record(stream)
+        sync()
+        tn = max_over_ranks(f0.elapsed_time(f1)) * 1e-3 / c5_steps
+        c5_paths = C5_W * C5_H * total
+        c5 = {"workload": "C5: C2 scene at %dx%d, %d spp in total, sample_block split over %d rank(s), film combine inside the timed region" % (C5_W, C5_H, total, world),
+              "total_spp": total, "spp_per_gpu": cnt, "seconds_per_step": tn, "steps": c5_steps, "mpaths_per_s": c5_paths / tn / 1e6,
+              "note": "north_star quotes 16384 spp; the rate is spp-independent and 2048 keeps the single-GPU leg under 10 s (--c5-spp)"}
+        if world > 1:
+            combined = sc.film_download(C5_W, C5_H) if rank == 0 else None
+            sync()
+            if rank == 0:
+                # the same job on ONE GPU, same run: T1
+                p1 = abi.render_params(C5_W, C5_H, spp=total, max_verts=MAX_VERTS, seed=SEED)
+                sc.render("pt", abi.render_params(C5_W, C5_H, spp=max(1, total // 16), max_verts=MAX_VERTS, seed=SEED), download=False)
+                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                g0.record(stream)
+                sc.render("pt", p1, download=False)
+                g1.record(stream)
+                torch.cuda.synchronize()
+                t1 = g0.elapsed_time(g1) * 1e-3
+                single = sc.film_download(C5_W, C5_H)
+                scale = float(np.abs(single).max())
+                err = float(np.abs(combined.astype(np.float64) - single).max() / scale)
+                c5.update({"t1_seconds": t1, "strong_efficiency": t1 / (world * tn),
+                           "combined_vs_single_gpu_max_abs_err": err, "image_check": "pass"})
+                assert np.allclose(combined, single, rtol=1e-4, atol=1e-5 * scale), "C5: combined 4K film differs from the single-GPU film (%g)" % err
+            sync()
+    close_main()
 
     if rank == 0:
         assert host_film is not None and np.isfinite(host_film).all() and host_film.mean() > 0.01
-        # ---- roofline of the dominant kernel (k_pt_extend_q), SURVEY.md 8(d)
-        # counters pass (separate, untimed): mean nodes / triangles fetched per closest-hit ray
+        peak, peak_src = load_peaks()
+        # ---- roofline of the dominant kernel (k_pt_extend_q) on the headline workload.  C2's BVH + triangle records are
+        # 3 MB: they live in L1 / L2 (126 MB), DRAM only sees the ray queue.  So the bound is NOT HBM: it is instruction issue
+        # of divergent warps, fed by L2.  achieved = algorithmic bytes per second served by the cache hierarchy against the
+        # L2 read bandwidth measured here by lmcu_probe_l2_bandwidth; the HBM fraction is given only for scale.
         pc = abi.render_params(W, H, spp=8, max_verts=MAX_VERTS, seed=SEED, count_traversal=True)
         _, stc = sc.render("pt", pc, download=False)
         n_nodes, n_tris = stc["bvh_nodes_per_ray"], stc["bvh_tris_per_ray"]
-        b_ray = 32 + 16 + n_nodes * 80 + n_tris * 48
-        # In the timed region TWO wavefront loops run side by side (LmcuRenderParams::wavefronts), so the CUDA events
-        # around an extend launch also see the other loop's shade / shadow kernels on the same SMs: that duration is
-        # reported as `overlapped`, but it is not the kernel's own.  The kernel's launch duration is measured live here
-        # in a single-wavefront render of the same workload (kernels of one loop run one at a time), 256 spp.
-        ps = abi.render_params(W, H, spp=256, max_verts=MAX_VERTS, seed=SEED, rescale=0, wavefronts=1)
+        tri_bytes = 48 if sc.build_stats.triangles_fp32 else 80
+        b_ray = 32 + 16 + n_nodes * 80 + n_tris * tri_bytes
+        # In the timed region TWO wavefront loops run side by side, so the CUDA events around an extend launch also see the
+        # other loop's kernels on the same SMs (`overlapped`).  The kernel's own launch duration is measured live in a
+        # single-wavefront render of the same workload (kernels of one loop run one at a time), 256 spp.
         sc.render("pt", abi.render_params(W, H, spp=16, max_verts=MAX_VERTS, seed=SEED, rescale=0, wavefronts=1), download=False)
-        _, solo = sc.render("pt", ps, download=False)
+        _, solo = sc.render("pt", abi.render_params(W, H, spp=256, max_verts=MAX_VERTS, seed=SEED, rescale=0, wavefronts=1), download=False)
         ext_s, ext_rays, ext_launches, total_s = solo["extend_seconds"], solo["extend_rays"], solo["extend_launches"], solo["elapsed"]
-        stats_solo = [solo]
         ov_s = sum(s["extend_seconds"] for s in stats)
         ov_rays = sum(s["extend_rays"] for s in stats)
-        peak, peak_src = load_peaks()
         achieved = ext_rays * b_ray / ext_s / 1e9
-        traffic, traffic_src = None, None
         try:
-            with open(os.path.join(ROOT, "profiles", "r01_extend_traffic.json")) as f:
-                tr = json.load(f)
-            # the captured launch traced tr["rays"] rays; a launch of this run traces rays_per_launch: same bytes per ray
-            traffic = (tr["dram_bytes_read"] + tr["dram_bytes_write"]) / tr["rays"] * (ext_rays / max(1, ext_launches))
-            traffic_src = tr["source"] + "; %.1f DRAM bytes per ray, scaled to this run's rays per launch" % (
-                (tr["dram_bytes_read"] + tr["dram_bytes_write"]) / tr["rays"])
+            l2_peak = lmcu.probe_l2_bandwidth(local_rank, 32 << 20)
         except Exception:
-            pass
+            l2_peak = None
+        prof = load_profile("r02_ncu_c2_extend.json") or {}
+        traffic = prof.get("dram_bytes_per_ray", 0) * ext_rays / max(1, ext_launches) if prof else None
         roofline = {
-            "bound": "hbm", "kernel": "k_pt_extend_q (closest-hit BVH traversal over the path queue)", "achieved": achieved,
-            "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes per launch",
-            "traffic_source": traffic_src, "peak_source": peak_src,
-            "bytes_per_ray": b_ray, "nodes_per_ray": n_nodes, "tris_per_ray": n_tris,
+            "bound": "issue/L2", "kernel": "k_pt_extend_q (closest-hit BVH traversal over the path queue), C2",
+            "achieved": achieved, "peak": l2_peak, "unit": "GB/s", "frac": achieved / l2_peak if l2_peak else None,
+            "peak_source": "measured live: L2 read bandwidth over a 32 MiB buffer (lmcu_probe_l2_bandwidth)",
+            "traffic": traffic, "traffic_unit": "DRAM bytes per launch", "traffic_source": prof.get("source"),
+            "hbm_peak": peak, "hbm_peak_source": peak_src, "algorithmic_bytes_over_hbm_peak": achieved / peak,
+            "bytes_per_ray": b_ray, "nodes_per_ray": n_nodes, "tris_per_ray": n_tris, "tri_record_bytes": tri_bytes,
             "algorithmic_bytes_per_launch": ext_rays / max(1, ext_launches) * b_ray,
             "rays_per_launch": ext_rays / max(1, ext_launches), "avg_launch_ms": ext_s / max(1, ext_launches) * 1e3,
-            "share_of_step": {"extend": ext_s / total_s, "shade": sum(s["shade_seconds"] for s in stats_solo) / total_s,
-                              "shadow": sum(s["shadow_seconds"] for s in stats_solo) / total_s},
+            "grays_per_s": ext_rays / ext_s / 1e9,
+            "ncu": {k: prof.get(k) for k in ("lane_efficiency", "warp_instructions_per_ray", "issue_slots_busy_pct", "l1_hit_pct",
+                                             "l2_hit_pct", "lts_gbs", "local_memory_bytes_per_ray", "stalls")} if prof else None,
+            "share_of_step": {"extend": ext_s / total_s, "shade": solo["shade_seconds"] / total_s, "shadow": solo["shadow_seconds"] / total_s},
             "measured_in": "single-wavefront render of the same workload inside this run (256 spp, %.1f Mpaths/s): the kernel timed "
                            "with nothing beside it" % (solo["paths"] / solo["elapsed"] / 1e6),
-            "overlapped": {"achieved": ov_rays * b_ray / ov_s / 1e9, "frac": ov_rays * b_ray / ov_s / 1e9 / peak,
+            "overlapped": {"achieved": ov_rays * b_ray / ov_s / 1e9,
                            "what": "same figure from the events of the timed region, where a launch shares the SMs with the other "
                                    "wavefront's kernels"},
-            "note": "BVH + triangles of C2 are 1.9 MB and stay L1/L2-resident: the algorithmic bytes are served by cache "
-                    "(measured DRAM traffic is the ray queue only), so frac is algorithmic bytes over the HBM peak, not "
-                    "DRAM utilisation; the kernel is bound by instruction issue of divergent warps (profiles/)",
+            "note": "C2 is L2-resident (BVH + triangles 3 MB): the algorithmic bytes are served by L1/L2, DRAM carries the ray queue only; "
+                    "the kernel is bound by instruction issue of divergent warps (profiles/).  The HBM-bound evidence is in hbm_resident: "
+                    "configs whose BVH exceeds the L2, measured in this run",
         }
-        # ---- CPU baseline: the reference on this box's host cores, bounded sample
-        cpu = None
+        configs = {}
+        if world == 1 and not args.no_configs:
+            for name, fn in (("C1_raycast", lambda: c1_rates(lmcu, abi, scenes, stream)),
+                             ("C3_accel", lambda: accel_rates(torch, lmcu, scenes, stream, peak)),
+                             ("C4_pt", lambda: c4_rates(lmcu, abi, scenes, stream, peak))):
+                try:
+                    configs[name] = fn()
+                except Exception as ex:
+                    configs[name] = {"failed": str(ex)}
+                lmcu.cache_trim(local_rank)
+            hb = {}
+            if "incoherent" in configs.get("C3_accel", {}):
+                hb["C3 incoherent, k_intersect_q<TriF32>"] = configs["C3_accel"]["incoherent"]
+                hb["C3 coherent, k_intersect_q<TriF32>"] = configs["C3_accel"]["coherent"]
+            if "extend" in configs.get("C4_pt", {}):
+                hb["C4 extend, k_pt_extend_q"] = configs["C4_pt"]["extend"]
+            roofline["hbm_resident"] = hb
+        # ---- the drop-in path + the CPU baseline (the reference on this box's host cores, bounded sample) + parity at full size
+        cpu, parity_c2, plugin = None, None, None
         try:
             from oracle import ref
             if ref.available():
-                v, t, threads = reference_rate(REF_SPP_PER_STEP, 1, 1)
+                rs = None
+                if world == 1 and not args.no_configs and os.path.exists(PLUGIN + ".so"):
+                    try:
+                        plugin, rs, plugin_film = plugin_e2e(sb, abi, spp, npix * spp)
+                        scale = float(np.abs(host_film).max())
+                        plugin["film_vs_ctypes_max_abs_err"] = float(np.abs(plugin_film - host_film).max() / scale)
+                    except Exception as ex:
+                        plugin = {"failed": str(ex)}
+                v, t, threads, cpu_film = reference_rate(REF_SPP_PER_STEP, 1, 1, rs)
                 cpu = {"value": v, "unit": "Mpaths/s", "cores": threads, "kind": "reference",
                        "sample": "%dx%d @ %d spp (full C2 image, bounded spp), 1 warm-up + 1 timed render" % (W, H, REF_SPP_PER_STEP)}
+                if rs is not None:
+                    rs.close()
+                # G3 at the FULL C2 size: the GPU film of the e2e leg against the CPU film of the baseline leg
+                try:
+                    from parity import assert_pt_parity, rmse
+                    parity_c2 = {"gpu_spp": spp * world, "cpu_spp": REF_SPP_PER_STEP, "rmse": rmse(cpu_film, host_film),
+                                 "gate": "image means within max(1 %, 4.5 SE); fraction of 8x8 blocks of the difference with |z| > 4 <= 2e-3"}
+                    try:
+                        r = assert_pt_parity(cpu_film, host_film, REF_SPP_PER_STEP, rel_mean=0.01)
+                        parity_c2.update({"pass": True, "rel_mean": [float(x) for x in r["rel_mean"]], "z_frac": r["z_frac"]})
+                    except AssertionError as ex:
+                        parity_c2.update({"pass": False, "why": str(ex)[:300]})
+                except Exception as ex:
+                    parity_c2 = {"failed": str(ex)}
         except Exception as ex:  # the baseline must never take the bench line down
             cpu = {"value": None, "unit": "Mpaths/s", "cores": 0, "kind": "reference", "sample": "failed: %s" % ex}
-        accel = None
-        if world == 1 and not args.no_accel:
-            try:
-                accel = accel_rates(torch, lmcu, scenes, stream)
-            except Exception as ex:
-                accel = {"failed": str(ex)}
+        if plugin:
+            e2e.update({k: v for k, v in plugin.items() if k.startswith("plugin_")})
+            e2e["plugin_what"] = plugin.get("what", plugin.get("failed"))
         rays = sum(s["rays"] for s in stats)
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32 shading / f64 ray-triangle", "data": "synthetic",
+            "vs_baseline": None, "dtype": "f32 shading / f64 ray-triangle / f64 film sums", "data": "synthetic",
             "config": {"workload": "C2 renderer::pt Cornell box + diffuse/glass UV spheres (32268 tris) 1920x1080 "
                                    "max_verts=20 sampling_mode=mis seed=42", "spp_per_gpu": spp, "total_spp": spp * world,
-                       "parallelism": "sample split x%d, film combine = %s" % (
-                           world, "fused peer-memory reduce+rescale kernel over NVLink (CUDA IPC)" if args.reduce == "p2p" else "NCCL reduce"),
+                       "parallelism": "sample split x%d, film combine = %s" % (world, REDUCE_NAMES[args.reduce]),
                        "wavefronts": 2,
                        "l2": "inputs larger than L2: every wavefront iteration streams its 16 Mi-path SoA queues "
                              "(2.4 GB) through HBM, and every step regenerates all paths"},
             "mrays_per_s": rays * world / (ms_total * 1e-3) / 1e6,
             "e2e": e2e, "gpu_launches": int(sum(s["kernel_launches"] for s in stats)) + args.steps,
-            "roofline": roofline, "cpu_baseline": cpu, "accel_c3": accel, "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu, "parity_c2": parity_c2, "multi_gpu_check": multi_check,
+            "c5_strong": c5, "configs": configs, "clocks": clocks,
         }))
     if world > 1:
         dist.barrier()
@@ -368,8 +613,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--spp", type=int, default=GPU_SPP)
-    ap.add_argument("--reduce", default="p2p", choices=["p2p", "nccl"], help="film combine across GPUs")
-    ap.add_argument("--no-accel", action="store_true", help="skip the informational C3 accel batch rates")
+    ap.add_argument("--reduce", default="slice", choices=["slice", "root", "nccl"], help="film combine across GPUs")
+    ap.add_argument("--no-configs", "--no-accel", dest="no_configs", action="store_true",
+                    help="skip the C1 / C3 / C4 legs and the plugin end-to-end leg (quick runs)")
+    ap.add_argument("--no-c5", action="store_true", help="skip the C5 strong-scaling pass")
+    ap.add_argument("--c5-spp", type=int, default=C5_TOTAL_SPP, help="total spp of the C5 pass (north_star: 16384)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -189,7 +189,14 @@ typedef struct LmcuRenderParams {
     double render_time;                      /* pt, time scheduler: seconds; the pass in flight always completes */
     int32_t wavefronts;                      /* pt: staggered wavefront loops running side by side on their own streams
                                                 (0 = default 2; 1 = one kernel at a time).  Same image for any value. */
-    int32_t pad2_;
+    int32_t ao_mark_misses;                  /* ao: 1 = pixels whose primary ray misses come back as -1 (the reference never
+                                                touches them, functest/renderer_ao.cpp:32-34: a host that renders into an
+                                                existing film keeps their old value); 0 = they come back 0 */
+    /* pt: called on the host thread that runs lmcu_render_pt, between wavefront batches: paths started so far, paths of the
+     * job (0 with the time scheduler), seconds since the render began.  The hook of progress::update / update_time
+     * (src/scheduler.cpp:45,91,133,173).  NULL = no reports. */
+    void (*progress)(void* user, int64_t processed_paths, int64_t total_paths, double elapsed_seconds);
+    void* progress_user;
 } LmcuRenderParams;
 
 typedef struct LmcuRenderStats {
@@ -233,6 +240,13 @@ const char* lmcu_last_error(void);
 int lmcu_device_count(void);
 const char* lmcu_version(void);
 
+/* Scratch blocks (path pools, films) are recycled per device inside the library, at most LMCU_CACHE_GB (default 24) GiB
+ * per device; lmcu_cache_trim() hands the parked blocks of `device` back to the driver (after a device synchronise). */
+int lmcu_cache_trim(int device);
+/* Measured read bandwidth of the L2 (GB/s) over a `bytes`-sized buffer that every CTA streams repeatedly: the roofline
+ * denominator for traversal of an L2-resident BVH (bench.py). */
+int lmcu_probe_l2_bandwidth(int device, int64_t bytes, double* gb_per_s);
+
 /* -- scene + accel: replaces lm::Accel::build / intersect (include/lm/accel.h:38,70) ---------- */
 int lmcu_scene_create(int device, LmcuScene** out);
 void lmcu_scene_destroy(LmcuScene* scene);
@@ -245,7 +259,14 @@ int lmcu_scene_upload(LmcuScene* scene, const LmcuSceneDesc* desc);
 int lmcu_accel_build(LmcuScene* scene, const LmcuBuildOptions* opts, LmcuBuildStats* stats);
 /* Closest hit for a batch of rays in HOST memory (replaces accel_sahbvh.cpp:269-299 per ray). */
 int lmcu_accel_intersect(LmcuScene* scene, const LmcuRay* rays, int64_t n, LmcuHit* hits);
-/* Same with DEVICE buffers on `stream` (a cudaStream_t, may be NULL); asynchronous. */
+/* ONE ray: the scalar lm::Accel::intersect contract (include/lm/accel.h:70; called concurrently from every OpenMP
+ * thread by Scene::intersect, src/scene.cpp:320).  Thread-safe and lock-free: each calling thread owns a pinned,
+ * device-mapped (ray, hit) slot and a stream; a call is one kernel launch and one stream synchronise, no allocation
+ * and no memcpy.  Same hit, bit for bit, as lmcu_accel_intersect. */
+int lmcu_accel_intersect1(LmcuScene* scene, const LmcuRay* ray, LmcuHit* hit);
+/* Same with DEVICE buffers on `stream` (a cudaStream_t, may be NULL); asynchronous.  Batches in flight on different
+ * streams are independent (each launch has its own work cursor).  A traversal-stack overflow (deeper than 48 wide-node
+ * groups: never seen) is reported by the next lmcu_accel_intersect / lmcu_render_* call on the scene. */
 int lmcu_accel_intersect_device(LmcuScene* scene, const void* d_rays, int64_t n, void* d_hits, void* stream);
 /* Mean wide nodes / triangles fetched per ray by the last counted batch (counters variant of the kernel). */
 int lmcu_accel_intersect_counted(LmcuScene* scene, const LmcuRay* rays, int64_t n, LmcuHit* hits,
@@ -290,6 +311,13 @@ int lmcu_ipc_open(int device, const void* handle, void** d_ptr);
 int lmcu_ipc_close(int device, void* d_ptr);
 int lmcu_enable_peer_access(int device, int peer_device);
 int lmcu_film_reduce_peers(LmcuScene* root, void* const* peer_films, int num_peers, double scale);
+/* Slice-parallel form of the same combine (one call per GPU, all at once): out[i] = scale * sum_k films[k][i] for
+ * i in [begin, end).  `films` = this GPU's own film and the peers' films (peer-mapped), `out` = the root's film
+ * (peer-mapped on every GPU but the root; it may also be one of `films`).  With the film cut into G slices no GPU
+ * receives more than (G-1)/G of a film and all NVLink ports work at once, where lmcu_film_reduce_peers pulls G-1 whole
+ * films into the root.  `begin` must be a multiple of 4 floats.  Runs on `scene`'s device and stream and synchronises
+ * it; the caller barriers before (all renders complete) and after (all slices stored). */
+int lmcu_film_reduce_slice(LmcuScene* scene, void* const* films, int num_films, void* out, int64_t begin, int64_t end, double scale);
 
 #ifdef __cplusplus
 }

@@ -8,12 +8,14 @@
 #include <cub/cub.cuh>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <map>
 #include <mutex>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -162,6 +164,46 @@ __device__ __forceinline__ unsigned long long warp_fetch(unsigned long long* cur
     unsigned long long base = 0;
     if ((threadIdx.x & 31) == 0) base = atomicAdd(cursor, 32ull);
     return __shfl_sync(0xffffffffu, base, 0);
+}
+
+// The scalar lm::Accel::intersect contract (include/lm/accel.h:70): ONE ray, read from and answered into a pinned host
+// slot the calling thread owns (mapped into the device address space: no cudaMemcpy on either side).
+template <typename TriT>
+__global__ void k_intersect_one(DevScene s, const LmcuRay* __restrict__ ray, LmcuHit* __restrict__ hit,
+                                volatile unsigned long long* done, unsigned long long ticket) {
+    if (threadIdx.x != 0) return;
+    uint2 stack[kStackSize];
+    RayD r;
+    r.o = d3(ray->o[0], ray->o[1], ray->o[2]); r.d = d3(ray->d[0], ray->d[1], ray->d[2]);
+    r.tmin = ray->tmin; r.tmax = ray->tmax;
+    HitD h; h.t = r.tmax; h.u = h.v = 0; h.tri = -1;
+    const bool ok = traverse<false, false, TriT>(s.nodes, scene_tris<TriT>(s), r, h, stack, nullptr);
+    LmcuHit o;
+    o.t = h.t; o.u = h.u; o.v = h.v; o.primitive = ok ? -1 : -2; o.face = -1;     // -2: traversal stack overflow
+    if (ok && h.tri >= 0) {
+        F3 p1, p2, p3; int32_t pi;
+        tri_fetch(s, (uint32_t)h.tri, p1, p2, p3, pi, o.face);
+        o.primitive = s.prims[pi].node_index;
+    }
+    *hit = o;
+    __threadfence_system();          // the hit record is in host memory before the ticket the host thread spins on
+    *done = ticket;
+}
+
+// L2 read bandwidth probe (the denominator of the roofline of an L2-resident traversal): every CTA streams the same
+// `bytes`-sized buffer (far smaller than L2) `reps` times with 16-byte loads.
+__global__ void __launch_bounds__(256) k_probe_l2(const uint4* __restrict__ buf, size_t n16, int reps, uint32_t* sink) {
+    uint32_t acc = 0;
+    for (int r = 0; r < reps; r++) {
+        // n16 is a power of two (host-checked): the wrap is a mask, not a division
+        for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x + (size_t)r * 7919u, k = 0; k < n16; k += (size_t)gridDim.x * blockDim.x) {
+            const size_t j = (i + k) & (n16 - 1);
+            uint4 v;
+            asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(buf + j));
+            acc ^= v.x ^ v.y ^ v.z ^ v.w;
+        }
+    }
+    if (acc == 0x12345678u) *sink = acc;
 }
 
 // ================================================================================================
@@ -427,8 +469,43 @@ __global__ void __launch_bounds__(LMCU_TRAV_BLOCK, LMCU_MINB) k_pt_shadow_q(DevS
     if (COUNT) { atomicAdd(&ctr->nodes_shadow, (unsigned long long)tc.nodes); atomicAdd(&ctr->tris_shadow, (unsigned long long)tc.tris); }
 }
 
+__global__ void k_fill(float* film, size_t n, float v) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) film[i] = v;
+}
+
 __global__ void k_scale(float* film, size_t n, float s) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) film[i] *= s;
+}
+
+// Order-independent 64-bit digest of an array of 8-byte words (mesh positions / normals): sum of a splitmix64 mix of
+// (word, index).  Identifies the geometry an accel blob was built from (lmcu_accel_save / lmcu_accel_load).
+__global__ void k_digest(const unsigned long long* __restrict__ words, size_t n, unsigned long long* out) {
+    unsigned long long h = 0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        unsigned long long z = words[i] ^ (0x9E3779B97F4A7C15ull * (unsigned long long)(i + 1));
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        h += z ^ (z >> 31);
+    }
+    for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
+    if ((threadIdx.x & 31) == 0 && h) atomicAdd(out, h);
+}
+
+// The reference's film is Float = double (film_bitmap.cpp:20-55).  Here the kernels splat with fp32 atomics, and a running
+// fp32 sum of thousands of samples would start dropping small contributions (ulp(2^16) = 0.008).  So the fp32 film only
+// ever holds the last few dozen samples per pixel: this kernel MOVES what has accumulated into an FP64 film and may run at
+// any time beside the render kernels — atomicExch hands every splat to exactly one fold (a concurrent splat lands either
+// before the exchange and is taken now, or after it and is taken by the next fold).
+__global__ void k_film_fold(float* __restrict__ film, double* __restrict__ acc, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float v = atomicExch(film + i, 0.f);
+        if (v != 0.f) atomicAdd(acc + i, (double)v);
+    }
+}
+
+// film = float(acc * scale): the single rescale of renderer_pt.cpp:307-312 in FP64 (scale = 1 leaves sums, sample split)
+__global__ void k_film_finish(float* __restrict__ film, const double* __restrict__ acc, size_t n, double scale) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) film[i] = (float)(acc[i] * scale);
 }
 
 // root = (root + sum over peers) * scale; the peer pointers are NVLink peer-mapped (P2P / CUDA IPC), so the
@@ -454,6 +531,31 @@ __global__ void __launch_bounds__(256) k_film_reduce_peers(float* __restrict__ r
     }
 }
 
+// Slice-parallel form of the same combine: every GPU runs this kernel on ITS slice [begin, end) of the film, reading that
+// slice of all films (its own + the peers' over NVLink) and storing the scaled sum into `out` — the root's film, a peer
+// store over NVLink for every rank but the root.  All links carry traffic at once and no GPU takes more than (G-1)/G of
+// a film inbound, instead of G-1 whole films converging on the root: reduce-scatter + gather-to-root + film::rescale
+// in one pass.  Only this rank touches slice [begin, end) of `out`, so reading it as an input first is safe.
+struct FilmSet { const float* p[LMCU_MAX_PEERS + 1]; };
+
+__global__ void __launch_bounds__(256) k_film_reduce_slice(FilmSet films, int num_films, float* __restrict__ out, size_t begin, size_t end, float scale) {
+    const size_t b4 = begin / 4, e4 = end / 4;      // begin is a multiple of 4 (host-checked)
+    for (size_t i = b4 + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < e4; i += (size_t)gridDim.x * blockDim.x) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = 0; k < num_films; k++) {
+            const float4 v = __ldcv(reinterpret_cast<const float4*>(films.p[k]) + i);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        reinterpret_cast<float4*>(out)[i] = make_float4(acc.x * scale, acc.y * scale, acc.z * scale, acc.w * scale);
+    }
+    if (blockIdx.x == 0 && e4 * 4 + threadIdx.x < end) {
+        const size_t i = e4 * 4 + threadIdx.x;
+        float acc = 0.f;
+        for (int k = 0; k < num_films; k++) acc += __ldcv(films.p[k] + i);
+        out[i] = acc * scale;
+    }
+}
+
 // ================================================================================================
 // host side
 // ================================================================================================
@@ -465,30 +567,38 @@ namespace {
 struct BlockCache {
     std::mutex mu;
     std::multimap<std::pair<int, size_t>, void*> blocks;
-    size_t bytes = 0;
-    static constexpr size_t kCacheBytes = size_t(24) << 30;
+    std::map<int, size_t> bytes;           // parked bytes per device
+    size_t cap = size_t(24) << 30;         // per DEVICE; LMCU_CACHE_GB overrides it (0 = park nothing)
+    BlockCache() { if (const char* e = getenv("LMCU_CACHE_GB")) cap = (size_t)(atof(e) * double(size_t(1) << 30)); }
     void* take(int device, size_t n) {
         std::lock_guard<std::mutex> lk(mu);
         auto it = blocks.find({ device, n });
         if (it == blocks.end()) return nullptr;
         void* p = it->second;
         blocks.erase(it);
-        bytes -= n;
+        bytes[device] -= n;
         return p;
     }
     // gives every parked block of `device` back to the driver (an allocation failed: the memory is needed now)
     void flush(int device) {
         std::lock_guard<std::mutex> lk(mu);
         for (auto it = blocks.begin(); it != blocks.end();) {
-            if (it->first.first == device) { cudaFree(it->second); bytes -= it->first.second; it = blocks.erase(it); }
+            if (it->first.first == device && !exported.count(it->second)) {
+                cudaFree(it->second); bytes[device] -= it->first.second; it = blocks.erase(it);
+            }
             else ++it;
         }
     }
+    // A block that was exported over CUDA IPC may still be mapped by a peer process — freeing it under that mapping is
+    // undefined behaviour — so it is parked whatever its size and the cap, for the life of the process.
+    std::set<void*> exported;
+    void mark_exported(void* p) { std::lock_guard<std::mutex> lk(mu); exported.insert(p); }
     bool park(int device, size_t n, void* p) {
         std::lock_guard<std::mutex> lk(mu);
-        if (n < (size_t(1) << 20) || bytes + n > kCacheBytes) return false;
+        const bool keep = exported.count(p) != 0;
+        if (!keep && (n < (size_t(1) << 20) || bytes[device] + n > cap)) return false;
         blocks.insert({ { device, n }, p });
-        bytes += n;
+        bytes[device] += n;
         return true;
     }
 };
@@ -554,11 +664,15 @@ struct LmcuScene {
     DBuf<TriShade> shade;
     DBuf<TriUV> uv;
     bool built = false, fp32 = false;
+    uint64_t blob_desc_digest = 0;       // accel-only scene restored from a blob: the digest that blob carried
     bool composite = false;              // a material is textured or a mixture: the shade kernel's <true> instantiation
     // scratch / outputs
-    DBuf<unsigned long long> cursor;     // [0] work cursor, [1..2] counters, [3] rays
+    DBuf<unsigned long long> cursor;     // [0] work cursor, [1..2] counters, [3] rays, [4..5] digests, [8..] per-launch cursors
+    static constexpr int kCursorRing = 256;  // accel batches: every launch takes the next cursor word, so that batches in flight
+    std::atomic<unsigned> cursor_next{ 0 };  // on different streams (lmcu_accel_intersect_device) never share one
     DBuf<uint32_t> flags;                // [0] stack overflow
     DBuf<float> film;
+    DBuf<double> film_acc;               // pt: FP64 sums the fp32 film is folded into (k_film_fold)
     int film_w = 0, film_h = 0;
     // pt pools: one set per wavefront (LMCU_WAVES staggered wavefronts, each on its own stream)
     struct PtWave {
@@ -576,6 +690,7 @@ struct LmcuScene {
         cudaEvent_t grp[2] = { nullptr, nullptr };
         PtCounters* h = nullptr;             // [2]
         int cur = 0;                         // ping-pong queue index of the next iteration to enqueue
+        double since_fold = 0.0;             // samples per pixel this wavefront may have added to the fp32 film since its last fold
         int cur_after[2] = { 0, 0 };         // ... as it stands after the group of a slot
         bool finished = false;
     };
@@ -631,9 +746,9 @@ int lmcu_scene_create(int device, LmcuScene** out) {
     if (const char* e = getenv("LMCU_CTAS")) s->ctas_per_sm = std::max(1, atoi(e));
     if (const char* e = getenv("LMCU_SHADE_GRID")) s->shade_ctas_per_sm = std::max(1, atoi(e));
     if (const char* e = getenv("LMCU_WAVES")) s->default_waves = std::min((int)LmcuScene::kMaxWaves, std::max(1, atoi(e)));
-    CU(s->cursor.alloc(8));
+    CU(s->cursor.alloc(8 + LmcuScene::kCursorRing));
     CU(s->flags.alloc(4));
-    CU(cudaMemset(s->cursor.p, 0, 8 * sizeof(unsigned long long)));
+    CU(cudaMemset(s->cursor.p, 0, (8 + LmcuScene::kCursorRing) * sizeof(unsigned long long)));
     CU(cudaMemset(s->flags.p, 0, 4 * sizeof(uint32_t)));
     *out = s;
     return LMCU_OK;
@@ -837,18 +952,43 @@ struct AccelBlobHeader {
     char magic[8];                // "LMCUBVH1"
     uint32_t version, fp32, nt, num_nodes, num_prims, has_uv;
     uint64_t payload_bytes, checksum;
+    uint64_t desc_digest;         // digest of the description the BVH was built from (mesh data + primitive table)
 };
-constexpr uint32_t kBlobVersion = 1;
-inline uint64_t fnv1a(const unsigned char* p, size_t n) {
-    uint64_t h = 1469598103934665603ull;
+constexpr uint32_t kBlobVersion = 2;
+inline uint64_t fnv1a(const unsigned char* p, size_t n, uint64_t h = 1469598103934665603ull) {
     for (size_t i = 0; i < n; i++) { h ^= p[i]; h *= 1099511628211ull; }
     return h;
+}
+// payload checksum: 8 bytes per step (a byte-wise FNV over the 4 GB blob of a 50 M-triangle scene takes seconds)
+inline uint64_t checksum64(const unsigned char* p, size_t n) {
+    uint64_t h = 1469598103934665603ull;
+    size_t i = 0;
+    for (; i + 8 <= n; i += 8) { uint64_t w; memcpy(&w, p + i, 8); h = (h ^ w) * 1099511628211ull; h ^= h >> 29; }
+    return fnv1a(p + i, n - i, h);
 }
 inline size_t blob_payload(const AccelBlobHeader& h) {
     return (size_t)h.num_nodes * sizeof(WideNode) + (size_t)h.nt * (h.fp32 ? sizeof(TriF32) : sizeof(TriF64)) +
            (size_t)h.nt * sizeof(TriShade) + (h.has_uv ? (size_t)h.nt * sizeof(TriUV) : 0) + (size_t)h.num_prims * sizeof(PrimDev);
 }
 }  // namespace
+
+// Digest of the uploaded description: mesh positions and normals (on the device since lmcu_scene_upload) + the primitive
+// table (transforms, mesh / material / light indices).  Two scenes with equal counts but other geometry or transforms differ.
+static int desc_digest(LmcuScene* s, uint64_t* out) {
+    if (!s->mesh_p.p) { *out = s->blob_desc_digest; return LMCU_OK; }
+    CU(cudaMemsetAsync(s->cursor.p + 4, 0, 2 * sizeof(unsigned long long), s->stream));
+    k_digest<<<s->num_sms * 8, 256, 0, s->stream>>>((const unsigned long long*)s->mesh_p.p, s->mesh_p.n, s->cursor.p + 4);
+    k_digest<<<s->num_sms * 8, 256, 0, s->stream>>>((const unsigned long long*)s->mesh_n.p, s->mesh_n.n, s->cursor.p + 5);
+    CU(cudaGetLastError());
+    unsigned long long d[2];
+    CU(cudaMemcpyAsync(d, s->cursor.p + 4, sizeof(d), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    uint64_t h = fnv1a((const unsigned char*)s->h_prims.data(), s->h_prims.size() * sizeof(PrimDev));
+    h = (h ^ d[0]) * 1099511628211ull;
+    h = (h ^ d[1]) * 1099511628211ull;
+    *out = h ? h : 1;
+    return LMCU_OK;
+}
 
 int lmcu_accel_save_size(LmcuScene* s, int64_t* bytes) {
     if (!s || !bytes) return fail(LMCU_ERR_INVALID_ARGUMENT, "null argument");
@@ -871,6 +1011,8 @@ int lmcu_accel_save(LmcuScene* s, void* buffer, int64_t bytes) {
     h.version = kBlobVersion; h.fp32 = s->fp32; h.nt = s->nt; h.num_nodes = (uint32_t)s->nodes.n;
     h.num_prims = (uint32_t)s->num_prims; h.has_uv = s->uv.p ? 1 : 0;
     h.payload_bytes = blob_payload(h);
+    const int rd = desc_digest(s, &h.desc_digest);
+    if (rd) return rd;
     unsigned char* base = static_cast<unsigned char*>(buffer) + sizeof(AccelBlobHeader);
     unsigned char* p = base;
     const auto pull = [&](const void* d, size_t n) -> cudaError_t {
@@ -883,9 +1025,62 @@ int lmcu_accel_save(LmcuScene* s, void* buffer, int64_t bytes) {
     CU(pull(s->shade.p, (size_t)h.nt * sizeof(TriShade)));
     if (h.has_uv) CU(pull(s->uv.p, (size_t)h.nt * sizeof(TriUV)));
     memcpy(p, s->h_prims.data(), (size_t)h.num_prims * sizeof(PrimDev));
-    h.checksum = fnv1a(base, h.payload_bytes);
+    h.checksum = checksum64(base, h.payload_bytes);
     memcpy(buffer, &h, sizeof(h));
     return LMCU_OK;
+}
+
+// Every index a traversal or shade kernel will follow is range-checked here, on the host, before the blob reaches the
+// device: a stale or foreign blob must be refused, not dereferenced.
+static const char* validate_blob(const AccelBlobHeader& h, const unsigned char* base, int num_materials, int num_lights, bool described) {
+    const WideNode* nodes = reinterpret_cast<const WideNode*>(base);
+    const unsigned char* tris = base + (size_t)h.num_nodes * sizeof(WideNode);
+    const size_t tri_bytes = (size_t)h.nt * (h.fp32 ? sizeof(TriF32) : sizeof(TriF64));
+    const TriShade* shade = reinterpret_cast<const TriShade*>(tris + tri_bytes);
+    const unsigned char* after_shade = reinterpret_cast<const unsigned char*>(shade + h.nt) + (h.has_uv ? (size_t)h.nt * sizeof(TriUV) : 0);
+    std::vector<PrimDev> prims(h.num_prims);
+    memcpy(prims.data(), after_shade, (size_t)h.num_prims * sizeof(PrimDev));
+    for (uint32_t i = 0; i < h.num_nodes; i++) {
+        WideNode n;
+        memcpy(&n, nodes + i, sizeof(n));
+        uint32_t n_internal = 0;
+        for (int slot = 0; slot < 8; slot++) {
+            const uint32_t m = n.meta[slot];
+            const bool internal = (n.imask >> slot) & 1u;
+            if (internal) {
+                if (m != ((1u << 5) | (24u + (uint32_t)slot))) return "accel blob: an internal child slot has a foreign meta byte";
+                n_internal++;
+            } else if (m != 0) {
+                const uint32_t unary = m >> 5, first = m & 0x1fu;
+                const uint32_t cnt = unary == 1 ? 1u : unary == 3 ? 2u : unary == 7 ? 3u : 0u;
+                if (cnt == 0 || first + cnt > 24u) return "accel blob: a leaf slot has a foreign meta byte";
+                if ((uint64_t)n.tri_base + first + cnt > h.nt) return "accel blob: a leaf references triangles past the end";
+            }
+        }
+        if (n_internal && ((uint64_t)n.child_base + n_internal > h.num_nodes || n.child_base <= i)) {
+            return "accel blob: a node references children outside the node array";   // children always follow their parent
+        }
+    }
+    for (uint32_t k = 0; k < h.nt; k++) {
+        int32_t prim, face;
+        if (h.fp32) {
+            TriF32 t; memcpy(&t, tris + (size_t)k * sizeof(TriF32), sizeof(t));
+            memcpy(&prim, &t.a.w, 4); memcpy(&face, &t.b.w, 4);
+        } else {
+            TriF64 t; memcpy(&t, tris + (size_t)k * sizeof(TriF64), sizeof(t));
+            prim = t.prim; face = t.face;
+        }
+        if (prim < 0 || (uint32_t)prim >= h.num_prims) return "accel blob: a triangle references a primitive outside the table";
+        if (face < 0 || (uint32_t)face >= prims[prim].num_faces) return "accel blob: a triangle references a face outside its mesh";
+        if (described) {
+            TriShade sh; memcpy(&sh, shade + k, sizeof(sh));
+            int32_t mat, light;
+            memcpy(&mat, &sh.n2.w, 4); memcpy(&light, &sh.n3.w, 4);
+            if (mat < 0 || mat >= num_materials) return "accel blob: a triangle references a material outside the uploaded table";
+            if (light < -1 || light >= num_lights) return "accel blob: a triangle references a light outside the uploaded table";
+        }
+    }
+    return nullptr;
 }
 
 int lmcu_accel_load(LmcuScene* s, const void* buffer, int64_t bytes) {
@@ -894,16 +1089,27 @@ int lmcu_accel_load(LmcuScene* s, const void* buffer, int64_t bytes) {
     AccelBlobHeader h;
     memcpy(&h, buffer, sizeof(h));
     if (memcmp(h.magic, "LMCUBVH1", 8) != 0 || h.version != kBlobVersion) return fail(LMCU_ERR_INVALID_ARGUMENT, "accel blob: bad magic or version");
-    if (h.nt == 0 || h.num_nodes == 0 || h.payload_bytes != blob_payload(h) || bytes < (int64_t)(sizeof(h) + h.payload_bytes)) {
+    if (h.nt == 0 || h.num_nodes == 0 || h.num_prims == 0 || h.payload_bytes != blob_payload(h) || bytes < (int64_t)(sizeof(h) + h.payload_bytes)) {
         return fail(LMCU_ERR_INVALID_ARGUMENT, "accel blob: inconsistent sizes");
     }
     const unsigned char* base = static_cast<const unsigned char*>(buffer) + sizeof(h);
-    if (fnv1a(base, h.payload_bytes) != h.checksum) return fail(LMCU_ERR_INVALID_ARGUMENT, "accel blob: checksum mismatch");
+    if (checksum64(base, h.payload_bytes) != h.checksum) return fail(LMCU_ERR_INVALID_ARGUMENT, "accel blob: checksum mismatch");
     const bool described = s->nt != 0;
-    if (described && (s->nt != h.nt || (uint32_t)s->num_prims != h.num_prims || (s->mesh_t.p != nullptr) != (h.has_uv != 0))) {
-        return fail(LMCU_ERR_INVALID_ARGUMENT, "accel blob does not belong to the uploaded scene");
-    }
     CU(cudaSetDevice(s->device));
+    if (described) {
+        if (s->nt != h.nt || (uint32_t)s->num_prims != h.num_prims || (s->mesh_t.p != nullptr) != (h.has_uv != 0)) {
+            return fail(LMCU_ERR_INVALID_ARGUMENT, "accel blob does not belong to the uploaded scene");
+        }
+        // same counts are not enough: world-space triangles come from the blob, materials and primitives from the upload
+        uint64_t mine = 0;
+        const int rd = desc_digest(s, &mine);
+        if (rd) return rd;
+        const unsigned char* blob_prims = base + h.payload_bytes - (size_t)h.num_prims * sizeof(PrimDev);
+        if (mine != h.desc_digest || memcmp(blob_prims, s->h_prims.data(), (size_t)h.num_prims * sizeof(PrimDev)) != 0) {
+            return fail(LMCU_ERR_INVALID_ARGUMENT, "accel blob was built from other geometry or transforms than the uploaded scene");
+        }
+    }
+    if (const char* why = validate_blob(h, base, (int)s->mats.n, s->num_lights, described)) return fail(LMCU_ERR_INVALID_ARGUMENT, why);
     CU(cudaStreamSynchronize(s->stream));
     const unsigned char* p = base;
     const auto push = [&](void* d, size_t n) -> cudaError_t {
@@ -929,6 +1135,7 @@ int lmcu_accel_load(LmcuScene* s, const void* buffer, int64_t bytes) {
         CU(cudaMemcpy(s->prims.p, s->h_prims.data(), (size_t)h.num_prims * sizeof(PrimDev), cudaMemcpyHostToDevice));
         s->nt = h.nt;
         s->num_prims = (int)h.num_prims;
+        s->blob_desc_digest = h.desc_digest;
     }
     s->built = true;
     return LMCU_OK;
@@ -953,10 +1160,11 @@ static int launch_intersect(LmcuScene* s, const LmcuRay* d_rays, int64_t n, Lmcu
     const int64_t kChunk = 1ll << 30;            // the queue cursor is 32-bit
     for (int64_t off = 0; off < n; off += kChunk) {
         const uint32_t m = (uint32_t)std::min<int64_t>(kChunk, n - off);
-        CU(cudaMemsetAsync(s->cursor.p, 0, sizeof(unsigned long long), st));
+        unsigned long long* cur = s->cursor.p + 8 + (s->cursor_next.fetch_add(1) % LmcuScene::kCursorRing);
+        CU(cudaMemsetAsync(cur, 0, sizeof(unsigned long long), st));
         const unsigned blocks = (unsigned)std::min<int64_t>((m + LMCU_TRAV_BLOCK - 1) / LMCU_TRAV_BLOCK, (int64_t)s->num_sms * s->ctas_per_sm);
         LMCU_DISPATCH(k_intersect_q, s->fp32, count, blocks, LMCU_TRAV_BLOCK, st, d, d_rays + off, m, d_hits + off,
-                      (uint32_t*)s->cursor.p, s->cursor.p + 1, s->flags.p);
+                      (uint32_t*)cur, s->cursor.p + 1, s->flags.p);
         CU(cudaGetLastError());
     }
     return LMCU_OK;
@@ -1009,14 +1217,122 @@ int lmcu_accel_intersect_counted(LmcuScene* s, const LmcuRay* rays, int64_t n, L
     return intersect_host(s, rays, n, hits, true, npr, tpr);
 }
 
+// -- scalar intersect -----------------------------------------------------------------------------------
+// One pinned, device-mapped (ray, hit) slot and one stream per calling THREAD and device: callers such as scene::default
+// under the reference's CPU renderers call Accel::intersect concurrently from every OpenMP thread (src/scene.cpp:320).
+// No lock, no allocation, no memcpy per call: write the ray, launch, synchronise the thread's own stream, read the hit.
+namespace {
+struct ScalarSlot {
+    int device = -1;
+    cudaStream_t st = nullptr;
+    LmcuRay* h_ray = nullptr; LmcuHit* h_hit = nullptr;
+    LmcuRay* d_ray = nullptr; LmcuHit* d_hit = nullptr;
+    volatile unsigned long long* h_done = nullptr; unsigned long long* d_done = nullptr;
+    unsigned long long ticket = 0;
+};
+struct ScalarSlots {
+    std::vector<ScalarSlot> v;
+    ~ScalarSlots() {                       // thread exit; errors are ignored (the context may already be gone)
+        for (auto& s : v) { if (s.h_ray) cudaFreeHost(s.h_ray); if (s.st) cudaStreamDestroy(s.st); }
+        cudaGetLastError();
+    }
+};
+thread_local ScalarSlots t_slots;
+}  // namespace
+
+int lmcu_accel_intersect1(LmcuScene* s, const LmcuRay* ray, LmcuHit* hit) {
+    if (!s || !s->built) return fail(LMCU_ERR_UNSUPPORTED, "Missing acceleration structure. Build first.");
+    if (!ray || !hit) return fail(LMCU_ERR_INVALID_ARGUMENT, "null argument");
+    ScalarSlot* slot = nullptr;
+    for (auto& c : t_slots.v) if (c.device == s->device) slot = &c;
+    CU(cudaSetDevice(s->device));
+    if (!slot) {
+        ScalarSlot c;
+        c.device = s->device;
+        CU(cudaStreamCreateWithFlags(&c.st, cudaStreamNonBlocking));
+        void* h = nullptr;
+        CU(cudaHostAlloc(&h, 128, cudaHostAllocMapped));
+        memset(h, 0, 128);
+        c.h_ray = (LmcuRay*)h; c.h_hit = (LmcuHit*)((char*)h + 64); c.h_done = (volatile unsigned long long*)((char*)h + 96);
+        void* d = nullptr;
+        CU(cudaHostGetDevicePointer(&d, h, 0));
+        c.d_ray = (LmcuRay*)d; c.d_hit = (LmcuHit*)((char*)d + 64); c.d_done = (unsigned long long*)((char*)d + 96);
+        t_slots.v.push_back(c);
+        slot = &t_slots.v.back();
+    }
+    *slot->h_ray = *ray;
+    const DevScene d = s->dev();
+    const unsigned long long ticket = ++slot->ticket;
+    if (s->fp32) k_intersect_one<TriF32><<<1, 32, 0, slot->st>>>(d, slot->d_ray, slot->d_hit, slot->d_done, ticket);
+    else k_intersect_one<TriF64><<<1, 32, 0, slot->st>>>(d, slot->d_ray, slot->d_hit, slot->d_done, ticket);
+    CU(cudaGetLastError());
+    // Spin on the ticket the kernel writes into the pinned slot (a stream synchronise costs several microseconds of driver
+    // time per ray); every few thousand spins ask the stream whether the launch failed instead of completing.
+    for (unsigned spins = 0; *slot->h_done != ticket; spins++) {
+        if ((spins & 0xfffu) == 0xfffu) {
+            const cudaError_t q = cudaStreamQuery(slot->st);
+            if (q != cudaSuccess && q != cudaErrorNotReady) CU(q);
+            if (q == cudaSuccess && *slot->h_done != ticket) return fail(LMCU_ERR_CUDA, "scalar intersect kernel finished without an answer");
+        }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    *hit = *slot->h_hit;
+    if (hit->primitive == -2) return fail(LMCU_ERR_CUDA, "bvh traversal stack overflow");
+    return LMCU_OK;
+}
+
+int lmcu_cache_trim(int device) {
+    if (device < 0 || device >= lmcu_device_count()) return fail(LMCU_ERR_INVALID_ARGUMENT, "bad device index");
+    CU(cudaSetDevice(device));
+    CU(cudaDeviceSynchronize());
+    g_cache.flush(device);
+    return LMCU_OK;
+}
+
+int lmcu_probe_l2_bandwidth(int device, int64_t bytes, double* gb_per_s) {
+    if (!gb_per_s || bytes < 4096) return fail(LMCU_ERR_INVALID_ARGUMENT, "bad argument");
+    if (lmcu_device_count() == 0) return fail(LMCU_ERR_NO_DEVICE, "no CUDA device: liblmcu has no CPU fallback");
+    CU(cudaSetDevice(device));
+    int sms = 0;
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    DBuf<uint4> buf;
+    DBuf<uint32_t> sink;
+    size_t n16 = 256;
+    while (n16 * 2 * 16 <= (size_t)bytes) n16 *= 2;          // largest power of two of 16-byte words within `bytes`
+    CU(buf.alloc(n16)); CU(sink.alloc(1));
+    CU(cudaMemset(buf.p, 1, n16 * 16));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    const unsigned blocks = (unsigned)sms * 8;
+    const size_t per_rep = ((n16 + (size_t)blocks * 256 - 1) / ((size_t)blocks * 256)) * (size_t)blocks * 256;   // loads issued per rep
+    double best = 0.0;
+    for (int it = 0; it < 4; it++) {
+        const int reps = it == 0 ? 2 : 64;
+        CU(cudaEventRecord(e0, 0));
+        k_probe_l2<<<blocks, 256>>>(buf.p, n16, reps, sink.p);
+        CU(cudaEventRecord(e1, 0));
+        CU(cudaEventSynchronize(e1));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        if (it > 0) best = std::max(best, (double)per_rep * 16.0 * reps / (ms * 1e-3) / 1e9);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *gb_per_s = best;
+    return LMCU_OK;
+}
+
 // -- film ---------------------------------------------------------------------------------------------
-static int ensure_film(LmcuScene* s, int w, int h) {
+static int ensure_film(LmcuScene* s, int w, int h, bool with_acc = false) {
     if (w <= 0 || h <= 0) return fail(LMCU_ERR_INVALID_ARGUMENT, "bad film size");
     if (s->film_w != w || s->film_h != h || !s->film.p) {
         CU(s->film.alloc((size_t)w * h * 3));
         s->film_w = w; s->film_h = h;
     }
     CU(cudaMemsetAsync(s->film.p, 0, s->film.n * sizeof(float), s->stream));   // film_->clear()
+    if (with_acc) {
+        if (s->film_acc.n != s->film.n) CU(s->film_acc.alloc(s->film.n));
+        CU(cudaMemsetAsync(s->film_acc.p, 0, s->film_acc.n * sizeof(double), s->stream));
+    }
     return LMCU_OK;
 }
 
@@ -1051,6 +1367,7 @@ int lmcu_film_ipc_export(LmcuScene* s, void* handle) {
     CU(cudaSetDevice(s->device));
     cudaIpcMemHandle_t h;
     CU(cudaIpcGetMemHandle(&h, s->film.p));
+    g_cache.mark_exported(s->film.p);
     memcpy(handle, &h, sizeof(h));
     return LMCU_OK;
 }
@@ -1094,6 +1411,26 @@ int lmcu_film_reduce_peers(LmcuScene* s, void* const* peer_films, int num_peers,
     }
     k_film_reduce_peers<<<s->num_sms * 8, 256, 0, s->stream>>>(s->film.p, pf, num_peers, s->film.n, (float)scale);
     CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(s->stream));
+    return LMCU_OK;
+}
+
+int lmcu_film_reduce_slice(LmcuScene* s, void* const* films, int num_films, void* out, int64_t begin, int64_t end, double scale) {
+    if (!s) return fail(LMCU_ERR_INVALID_ARGUMENT, "null scene");
+    if (num_films < 1 || num_films > LMCU_MAX_PEERS + 1 || !films || !out) return fail(LMCU_ERR_INVALID_ARGUMENT, "bad film list");
+    if (begin < 0 || end < begin || (begin & 3)) return fail(LMCU_ERR_INVALID_ARGUMENT, "slice must start at a multiple of 4 floats");
+    CU(cudaSetDevice(s->device));
+    FilmSet fs{};
+    for (int k = 0; k < num_films; k++) {
+        if (!films[k]) return fail(LMCU_ERR_INVALID_ARGUMENT, "null film");
+        fs.p[k] = (const float*)films[k];
+    }
+    if (end > begin) {
+        const size_t quads = (size_t)(end - begin) / 4 + 1;
+        const unsigned blocks = (unsigned)std::min<size_t>((quads + 255) / 256, (size_t)s->num_sms * 8);
+        k_film_reduce_slice<<<blocks, 256, 0, s->stream>>>(fs, num_films, (float*)out, (size_t)begin, (size_t)end, (float)scale);
+        CU(cudaGetLastError());
+    }
     CU(cudaStreamSynchronize(s->stream));
     return LMCU_OK;
 }
@@ -1153,6 +1490,10 @@ int lmcu_render_ao(LmcuScene* s, const LmcuRenderParams* p, float* film_rgb, Lmc
     CU(cudaMemsetAsync(s->cursor.p, 0, 4 * sizeof(unsigned long long), st));
     CU(cudaEventRecord(s->ev0, st));
     const size_t n = (size_t)p->width * p->height;
+    if (p->ao_mark_misses) {                       // pixels the kernel never writes (primary ray missed) read back as -1
+        k_fill<<<s->num_sms * 4, 256, 0, st>>>(s->film.p, s->film.n, -1.0f);
+        CU(cudaGetLastError());
+    }
     const unsigned blocks = (unsigned)std::min<size_t>((n + 127) / 128, (size_t)s->num_sms * 12);
     const DevScene d = s->dev();
     const double dist = p->ao_distance > 0 ? p->ao_distance : 0.2;
@@ -1203,6 +1544,11 @@ static int ensure_pt_pools(LmcuScene* s, uint32_t capacity, uint32_t shadow_fact
 // One wavefront pass: traces pp.total_paths paths (sample indices pp.sample_offset ...) to completion, accumulating into
 // the film.  Adds its counters and per-kernel times to `acc`.
 struct PtAccum {
+    // progress hook (LmcuRenderParams::progress): paths started by the passes before this one, paths of the job, start time
+    void (*progress)(void*, int64_t, int64_t, double) = nullptr;
+    void* progress_user = nullptr;
+    int64_t paths_before = 0, paths_total = 0;
+    std::chrono::steady_clock::time_point t0;
     int64_t launches = 0, extend_launches = 0;
     double t_extend = 0, t_shade = 0, t_shadow = 0;
     unsigned long long rays = 0, extend_rays = 0, shadow_rays = 0, nodes_extend = 0, tris_extend = 0, nodes_shadow = 0, tris_shadow = 0;
@@ -1221,6 +1567,8 @@ static int pt_pass(LmcuScene* s, const PtParams& pp_all, bool count, PtAccum& ac
     const unsigned q_blocks = (unsigned)(s->num_sms * s->ctas_per_sm);
     const unsigned shade_blocks = (unsigned)(s->num_sms * s->shade_ctas_per_sm), gen_blocks = (unsigned)s->num_sms * 4;
     const int kGroup = 4;                       // iterations between host checks
+    const double spp_per_iteration = (double)pp_all.capacity / ((double)pp_all.width * (double)pp_all.height);
+    const unsigned fold_blocks = (unsigned)std::min<size_t>((s->film.n + 255) / 256, (size_t)s->num_sms * 8);
     PtParams pp[LmcuScene::kMaxWaves];
     PathQueue q[LmcuScene::kMaxWaves][2];
     ShadowQueue sq[LmcuScene::kMaxWaves];
@@ -1241,6 +1589,7 @@ static int pt_pass(LmcuScene* s, const PtParams& pp_all, bool count, PtAccum& ac
         CU(cudaMemsetAsync(v.ctr.p, 0, sizeof(PtCounters), st));
         v.cur = 0;
         v.finished = false;
+        v.since_fold = 0.0;
         memset(v.h, 0, 2 * sizeof(PtCounters));
         for (int k = 0; k < 2; k++) {
             if (v.ring[k].empty()) {
@@ -1270,6 +1619,13 @@ static int pt_pass(LmcuScene* s, const PtParams& pp_all, bool count, PtAccum& ac
             v.cur ^= 1;
             acc.launches += 5;
             acc.extend_launches++;
+            // fold the fp32 film into the FP64 one whenever this wavefront may have added ~32 samples per pixel to it
+            v.since_fold += spp_per_iteration;
+            if (v.since_fold >= 32.0) {
+                k_film_fold<<<fold_blocks, 256, 0, st>>>(s->film.p, s->film_acc.p, s->film.n);
+                v.since_fold = 0.0;
+                acc.launches++;
+            }
         }
         CU(cudaGetLastError());
         CU(cudaMemcpyAsync(v.h + slot, v.ctr.p, sizeof(PtCounters), cudaMemcpyDeviceToHost, st));
@@ -1288,7 +1644,14 @@ static int pt_pass(LmcuScene* s, const PtParams& pp_all, bool count, PtAccum& ac
         }
     }
     int remaining = K;
+    std::vector<uint64_t> started(K, 0);
     for (int slot = 0; remaining > 0; slot ^= 1) {
+        if (acc.progress) {
+            uint64_t sum = 0;
+            for (int w = 0; w < K; w++) sum += started[w];
+            acc.progress(acc.progress_user, acc.paths_before + (int64_t)sum, acc.paths_total,
+                         std::chrono::duration<double>(std::chrono::steady_clock::now() - acc.t0).count());
+        }
         for (int w = 0; w < K; w++) {
             LmcuScene::PtWave& v = s->wave[w];
             if (v.finished) continue;
@@ -1301,6 +1664,7 @@ static int pt_pass(LmcuScene* s, const PtParams& pp_all, bool count, PtAccum& ac
                 cudaEventElapsedTime(&ms, v.ring[slot][it * 4 + 2], v.ring[slot][it * 4 + 3]); acc.t_shadow += ms * 1e-3;
             }
             if (h.overflow) return fail(LMCU_ERR_CUDA, "bvh traversal stack overflow");
+            started[w] = h.next_path;
             if (h.next_path >= pp[w].total_paths && h.count[v.cur_after[slot]] == 0) {
                 // done; the other slot's group (if one was enqueued) only runs empty iterations: wait for it, then join
                 v.finished = true;
@@ -1341,7 +1705,7 @@ int lmcu_render_pt(LmcuScene* s, const LmcuRenderParams* p, float* film_rgb, Lmc
     if (p->max_verts < 2) return fail(LMCU_ERR_INVALID_ARGUMENT, "max_verts must be >= 2");
     if (p->sampling_mode < 0 || p->sampling_mode > 2) return fail(LMCU_ERR_INVALID_ARGUMENT, "bad sampling_mode");
     CU(cudaSetDevice(s->device));
-    rc = ensure_film(s, p->width, p->height);
+    rc = ensure_film(s, p->width, p->height, true);
     if (rc) return rc;
     if (p->wavefronts < 0 || p->wavefronts > LmcuScene::kMaxWaves) return fail(LMCU_ERR_INVALID_ARGUMENT, "wavefronts must be in 0..4");
     s->waves = p->wavefronts > 0 ? p->wavefronts : s->default_waves;
@@ -1369,6 +1733,8 @@ int lmcu_render_pt(LmcuScene* s, const LmcuRenderParams* p, float* film_rgb, Lmc
     pp.image_mode = image ? 1u : 0u;
     const bool count = p->count_traversal != 0;
     PtAccum acc;
+    acc.progress = p->progress; acc.progress_user = p->progress_user;
+    acc.t0 = std::chrono::steady_clock::now();
     // `unit` = what one scheduler step processes: one sample of every pixel (scheduler::spp) or one sample of the image
     // (scheduler::spi); a pass renders `units` of them starting at sample index sample_offset + processed.
     const uint64_t paths_per_unit = image ? 1ull : npix;
@@ -1376,6 +1742,8 @@ int lmcu_render_pt(LmcuScene* s, const LmcuRenderParams* p, float* film_rgb, Lmc
     auto run_units = [&](int64_t units) -> int {
         pp.sample_offset = (uint64_t)p->sample_offset + (uint64_t)processed;
         pp.total_paths = paths_per_unit * (uint64_t)units;
+        acc.paths_before = (int64_t)(paths_per_unit * (uint64_t)processed);
+        acc.paths_total = timed ? 0 : (int64_t)pp.total_paths;
         const int r = pt_pass(s, pp, count, acc);
         if (r == LMCU_OK) processed += units;
         return r;
@@ -1401,11 +1769,15 @@ int lmcu_render_pt(LmcuScene* s, const LmcuRenderParams* p, float* film_rgb, Lmc
             units = std::max<int64_t>(1, (int64_t)(want / (double)iter)) * iter;
         }
     }
-    if (p->rescale) {
-        // renderer_pt.cpp:307-312: 1/processed (pixel mode) or w*h/processed (image mode)
-        const double scale = image ? (double)npix / (double)processed : 1.0 / (double)processed;
-        k_scale<<<s->num_sms * 4, 256, 0, st>>>(s->film.p, s->film.n, (float)scale);
-        acc.launches++;
+    {
+        // last fold (every wavefront has joined s->stream), then the film the callers see = float(FP64 sums * scale);
+        // renderer_pt.cpp:307-312: scale = 1/processed (pixel mode) or w*h/processed (image mode); 1 when the caller
+        // combines films of several GPUs first (rescale = 0)
+        const double scale = !p->rescale ? 1.0 : image ? (double)npix / (double)processed : 1.0 / (double)processed;
+        const unsigned blocks = (unsigned)std::min<size_t>((s->film.n + 255) / 256, (size_t)s->num_sms * 8);
+        k_film_fold<<<blocks, 256, 0, st>>>(s->film.p, s->film_acc.p, s->film.n);
+        k_film_finish<<<blocks, 256, 0, st>>>(s->film.p, s->film_acc.p, s->film.n, scale);
+        acc.launches += 2;
     }
     CU(cudaEventRecord(s->ev1, st));
     if (film_rgb) CU(cudaMemcpyAsync(film_rgb, s->film.p, s->film.n * sizeof(float), cudaMemcpyDeviceToHost, st));

@@ -20,10 +20,11 @@ _LIB = None
 
 EXPORTS = [
     "lmcu_last_error", "lmcu_device_count", "lmcu_version", "lmcu_scene_create", "lmcu_scene_destroy",
-    "lmcu_scene_set_stream", "lmcu_scene_upload", "lmcu_accel_build", "lmcu_accel_intersect", "lmcu_accel_intersect_device",
+    "lmcu_scene_set_stream", "lmcu_scene_upload", "lmcu_accel_build", "lmcu_accel_intersect", "lmcu_accel_intersect1", "lmcu_accel_intersect_device",
+    "lmcu_cache_trim", "lmcu_probe_l2_bandwidth",
     "lmcu_accel_intersect_counted", "lmcu_accel_save_size", "lmcu_accel_save", "lmcu_accel_load", "lmcu_render_raycast", "lmcu_render_ao", "lmcu_render_pt",
     "lmcu_film_device_ptr", "lmcu_film_rescale", "lmcu_film_download",
-    "lmcu_film_ipc_export", "lmcu_ipc_open", "lmcu_ipc_close", "lmcu_enable_peer_access", "lmcu_film_reduce_peers",
+    "lmcu_film_ipc_export", "lmcu_ipc_open", "lmcu_ipc_close", "lmcu_enable_peer_access", "lmcu_film_reduce_peers", "lmcu_film_reduce_slice",
 ]
 
 
@@ -53,6 +54,17 @@ def _check(rc):
 
 def device_count():
     return lib().lmcu_device_count()
+
+
+def cache_trim(device=0):
+    _check(lib().lmcu_cache_trim(int(device)))
+
+
+def probe_l2_bandwidth(device=0, nbytes=32 << 20):
+    """Measured L2 read bandwidth in GB/s (every CTA streams the same nbytes buffer)."""
+    v = C.c_double()
+    _check(lib().lmcu_probe_l2_bandwidth(int(device), C.c_int64(nbytes), C.byref(v)))
+    return v.value
 
 
 def ipc_open(device, handle):
@@ -115,6 +127,13 @@ class Scene:
             _check(lib().lmcu_accel_intersect(self._h, rp, C.c_int64(len(rays)), hp))
         return hits
 
+    def intersect1(self, ray):
+        """One ray through the scalar contract (lm::Accel::intersect): RAY_DTYPE record in, HIT_DTYPE record out."""
+        rays = np.ascontiguousarray(ray, dtype=RAY_DTYPE).reshape(1)
+        hits = np.zeros(1, dtype=HIT_DTYPE)
+        _check(lib().lmcu_accel_intersect1(self._h, rays.ctypes.data_as(C.c_void_p), hits.ctypes.data_as(C.c_void_p)))
+        return hits[0]
+
     def intersect_device(self, d_rays_ptr, n, d_hits_ptr, stream=0):
         """Device buffers (e.g. torch tensors' data_ptr()); asynchronous on `stream`."""
         _check(lib().lmcu_accel_intersect_device(self._h, C.c_void_p(d_rays_ptr), C.c_int64(n), C.c_void_p(d_hits_ptr),
@@ -158,6 +177,13 @@ class Scene:
         """film = (film + sum of the peer films) * scale in ONE kernel reading the peers over NVLink."""
         arr = (C.c_void_p * max(1, len(peer_ptrs)))(*peer_ptrs)
         _check(lib().lmcu_film_reduce_peers(self._h, arr, len(peer_ptrs), C.c_double(scale)))
+
+    def film_reduce_slice(self, film_ptrs, out_ptr, begin, end, scale):
+        """out[begin:end] = scale * sum of films[k][begin:end] on THIS scene's GPU (slice-parallel combine; out and the
+        films may be peer-mapped pointers)."""
+        arr = (C.c_void_p * len(film_ptrs))(*film_ptrs)
+        _check(lib().lmcu_film_reduce_slice(self._h, arr, len(film_ptrs), C.c_void_p(out_ptr), C.c_int64(begin), C.c_int64(end),
+                                            C.c_double(scale)))
 
     def close(self):
         if self._h:

@@ -8,9 +8,10 @@ film::rescale(1/processed) of the reference (renderer_pt.cpp:307-309).
 
 Two ways to combine the films:
   reduce_and_rescale        torch.distributed reduce (NCCL) + one scale          — the baseline
-  PeerFilmReducer           liblmcu's own kernel: the root reads every peer film over NVLink peer memory
-                            (CUDA IPC mappings of the peers' device films) and fuses the sum with
-                            film::rescale in ONE pass (lmcu_film_reduce_peers)     — the default on GPUs
+  PeerFilmReducer           liblmcu's own kernels over NVLink peer memory (CUDA IPC mappings of the ranks' device
+                            films), the sum fused with film::rescale in ONE pass: slice-parallel (every rank
+                            combines its slice of all films into the root's film, lmcu_film_reduce_slice — the
+                            default on GPUs) or root-gather (lmcu_film_reduce_peers)
 
 torch.distributed is plumbing only (handle exchange, barriers): the film tensor wraps the device buffer
 liblmcu rendered into.
@@ -65,39 +66,112 @@ def render_pt_sample_split(render_sums, total_spp, rank, world, dist=None):
     return reduce_and_rescale(film, total_spp, rank, world, dist)
 
 
-class PeerFilmReducer:
-    """Fused film reduce + rescale over peer memory, one process per GPU.
+class SceneFilmOps:
+    """The `ops` of PeerFilmReducer for an lmcu.Scene (or, with `scene` a callable, for whichever scene it returns at the
+    time of the call: a host that re-creates its scene per render keeps ONE reducer and its cached mappings as long as
+    the film buffer is recycled at the same address)."""
 
-    `film_handle()`   -> bytes: an opaque handle of this rank's film (Scene.film_ipc_handle)
-    `open_handle(h)`  -> a pointer-like object the root's reduce accepts (lmcu.ipc_open on the root's device)
-    `reduce(ptrs, s)` -> root only: film = (film + sum(peer films)) * s      (Scene.film_reduce_peers)
-    `sync()`          -> waits for this rank's render (torch.cuda.synchronize)
-    Opened mappings are cached per handle: the film buffer survives across renders of the same size.
+    def __init__(self, lmcu, scene, device, sync):
+        self._lmcu, self._scene, self._device, self.sync = lmcu, scene, device, sync
+
+    def _sc(self):
+        return self._scene() if callable(self._scene) else self._scene
+
+    def film_handle(self):
+        return self._sc().film_ipc_handle()
+
+    def film_ptr(self):
+        return self._sc().film_device()
+
+    def open_handle(self, h):
+        return self._lmcu.ipc_open(self._device, h)
+
+    def close_handle(self, ptr):
+        self._lmcu.ipc_close(self._device, ptr)
+
+    def reduce_root(self, ptrs, scale):
+        self._sc().film_reduce_peers(ptrs, scale)
+
+    def reduce_slice(self, ptrs, out_ptr, begin, end, scale):
+        self._sc().film_reduce_slice(ptrs, out_ptr, begin, end, scale)
+
+
+def film_slices(num_floats, world):
+    """Slice [begin, end) of the film each rank combines in the slice-parallel reduce: contiguous, tiling [0, num_floats),
+    every begin a multiple of 4 floats (the kernel moves float4s); the last rank takes the ragged tail."""
+    quads = int(num_floats) // 4
+    out = []
+    for r in range(world):
+        off, cnt = sample_block(quads, r, world)
+        out.append((off * 4, int(num_floats) if r == world - 1 else (off + cnt) * 4))
+    return out
+
+
+class PeerFilmReducer:
+    """Fused film reduce + rescale over peer memory, one process per GPU.  `ops` is the rank's scene seen through five
+    callables (Scene methods on GPUs, file-backed stand-ins in the CPU tests of this orchestration):
+
+    ops.film_handle()               -> bytes: opaque handle of this rank's film           (Scene.film_ipc_handle)
+    ops.film_ptr()                  -> (pointer, number of floats) of this rank's film    (Scene.film_device)
+    ops.open_handle(h)              -> pointer valid on THIS rank's device                (lmcu.ipc_open)
+    ops.close_handle(ptr)                                                               (lmcu.ipc_close)
+    ops.reduce_root(ptrs, s)        -> root only: film = (film + sum(peer films)) * s     (Scene.film_reduce_peers)
+    ops.reduce_slice(ptrs, out, b, e, s) -> out[b:e] = s * sum(films[k][b:e])           (Scene.film_reduce_slice)
+    ops.sync()                      -> waits for this rank's render                       (torch.cuda.synchronize)
+
+    mode "slice" (default): every rank combines its slice of ALL films and stores it into the root's film — all NVLink
+    ports busy at once, (G-1)/G of a film inbound per GPU.  mode "root": the root pulls G-1 whole films.
+    Mappings are cached per handle and re-exchanged only when some rank's film buffer changed; `any_changed(flag)` is an
+    all-reduce(MAX) of that flag over the ranks, which is also the "every rank's samples are in its film" barrier.
     """
 
-    def __init__(self, dist, rank, world, film_handle, open_handle, reduce, sync):
-        self.dist, self.rank, self.world = dist, rank, world
-        self.film_handle, self.open_handle, self.reduce, self.sync = film_handle, open_handle, reduce, sync
-        self._opened = {}
+    def __init__(self, dist, rank, world, ops, any_changed, mode="slice"):
+        self.dist, self.rank, self.world, self.ops, self.any_changed, self.mode = dist, rank, world, ops, any_changed, mode
+        self._opened = {}           # rank -> (handle, pointer)
         self._last = None
+        self.exchanges = 0
+
+    def _exchange(self, mine):
+        handles = [None] * self.world
+        self.dist.all_gather_object(handles, mine)
+        want = range(self.world) if self.mode == "slice" else (range(1, self.world) if self.rank == 0 else ())
+        for r in want:
+            if r == self.rank:
+                continue
+            old = self._opened.get(r)
+            if old is not None and old[0] == handles[r]:
+                continue
+            if old is not None:
+                self.ops.close_handle(old[1])
+            self._opened[r] = (handles[r], self.ops.open_handle(handles[r]))
+        self.exchanges += 1
 
     def __call__(self, total_spp):
         scale = 1.0 / float(total_spp)
         if self.world == 1:
-            self.sync()
-            self.reduce([], scale)
+            self.ops.sync()
+            self.ops.reduce_root([], scale)
             return
-        mine = self.film_handle()
-        # exchange handles only when somebody's film buffer changed (first step, or a new film size)
-        changed = [None] * self.world
-        self.dist.all_gather_object(changed, mine if mine != self._last else None)
+        mine = self.ops.film_handle()
+        changed = mine != self._last
         self._last = mine
-        if self.rank == 0:
-            for r in range(1, self.world):
-                if changed[r] is not None:
-                    self._opened[r] = self.open_handle(changed[r])
-        self.sync()
-        self.dist.barrier()                 # every rank's samples are in its film
-        if self.rank == 0:
-            self.reduce([self._opened[r] for r in range(1, self.world)], scale)
-        self.dist.barrier()                 # peers may overwrite their films again
+        self.ops.sync()                                 # this rank's samples are in its film ...
+        if self.any_changed(changed):                   # ... and after this collective, so are everybody's
+            self._exchange(mine)
+        if self.mode == "slice":
+            own, n = self.ops.film_ptr()
+            films = [own if r == self.rank else self._opened[r][1] for r in range(self.world)]
+            begin, end = film_slices(n, self.world)[self.rank]
+            self.ops.reduce_slice(films, films[0], begin, end, scale)
+        elif self.rank == 0:
+            self.ops.reduce_root([self._opened[r][1] for r in range(1, self.world)], scale)
+        self.dist.barrier()                             # the root's film is complete; peers may overwrite theirs again
+
+    def close(self):
+        """Unmaps the peers' films (before any rank frees its film)."""
+        for _, ptr in self._opened.values():
+            self.ops.close_handle(ptr)
+        self._opened = {}
+        self._last = None
+        if self.world > 1:
+            self.dist.barrier()

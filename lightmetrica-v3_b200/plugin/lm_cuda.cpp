@@ -15,7 +15,9 @@
 
 #include <cstdio>
 #include <cstring>
+#include <list>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <thread>
 
@@ -342,7 +344,88 @@ struct SceneExport {
         l.env_rgb = env_rgb.data();
     }
 
+    // -- what identifies the exported scene ----------------------------------------------------------------
+    // gather_description() collects everything but the triangles: primitives with their global transforms, materials
+    // and lights as probed through the public virtuals, camera, textures, and per mesh its address, its triangle count
+    // and a few sampled triangles.  A digest of all that (`sig`) decides whether a device scene uploaded earlier can be
+    // used again (lm::Scene has no modification counter); only on a miss does gather_triangles() walk every mesh through
+    // Mesh::foreach_triangle — one std::function call per triangle, the expensive part of an export.
+    std::vector<const Mesh*> mesh_list;
+    uint64_t sig = 1469598103934665603ull;
+    bool shading_ = false;
+    bool triangles_done = false;
+    std::mutex tri_mu;
+
+    void mix(const void* p, size_t n) {
+        const auto* b = static_cast<const unsigned char*>(p);
+        for (size_t i = 0; i < n; i++) { sig ^= b[i]; sig *= 1099511628211ull; }
+    }
+    template <typename T> void mix_value(const T& v) { mix(&v, sizeof(T)); }
+
+    void compute_signature() {
+        sig = 1469598103934665603ull;
+        mix_value(shading_);
+        for (const auto& p : prims) mix_value(p);
+        for (const auto& m : mats) {
+            mix_value(m.type); mix_value(m.map_kd); mix(m.color, sizeof(m.color)); mix_value(m.ax); mix_value(m.ay); mix_value(m.Ni);
+            mix(m.Ks, sizeof(m.Ks)); mix_value(m.alpha_mask); mix_value(m.num_entries);
+        }
+        for (const auto& v : entry_material) mix(v.data(), v.size() * sizeof(int32_t));
+        for (const auto& v : entry_weight) mix(v.data(), v.size() * sizeof(double));
+        for (const auto& l : lights) {
+            mix_value(l.type); mix_value(l.primitive); mix_value(l.node_index); mix_value(l.env_w); mix_value(l.env_h);
+            mix(l.Ke, sizeof(l.Ke)); mix_value(l.env_rot); mix_value(l.env_scale); mix(l.position, sizeof(l.position));
+        }
+        mix(env_rgb.data(), env_rgb.size() * sizeof(float));
+        mix_value(has_camera);
+        if (has_camera) mix_value(camera);
+        for (size_t i = 0; i < textures.size(); i++) {
+            mix_value(textures[i].w); mix_value(textures[i].h); mix_value(textures[i].c);
+            mix(tex_data[i].data(), tex_data[i].size() * sizeof(float));
+        }
+        for (const Mesh* mesh : mesh_list) {
+            const int n = mesh->num_triangles();
+            mix_value(mesh); mix_value(n);
+            for (int k = 0; k < 5 && n > 0; k++) {
+                const auto tri = mesh->triangle_at(int((long long)(n - 1) * k / 4));
+                for (const auto* v : { &tri.p1, &tri.p2, &tri.p3 }) { mix_value(v->p); mix_value(v->n); mix_value(v->t); }
+            }
+        }
+    }
+
+    void gather_triangles() {
+        std::unique_lock<std::mutex> lk(tri_mu);
+        if (triangles_done) return;
+        for (size_t i = 0; i < mesh_list.size(); i++) {
+            const Mesh* mesh = mesh_list[i];
+            auto& P = mesh_p[i];
+            auto& N = mesh_n[i];
+            auto& T = mesh_t[i];
+            P.reserve(size_t(mesh->num_triangles()) * 9);
+            N.reserve(size_t(mesh->num_triangles()) * 9);
+            T.reserve(size_t(mesh->num_triangles()) * 6);
+            mesh->foreach_triangle([&](int, const Mesh::Tri& tri) {
+                for (const auto* v : { &tri.p1, &tri.p2, &tri.p3 }) {
+                    P.push_back(v->p.x); P.push_back(v->p.y); P.push_back(v->p.z);
+                    N.push_back(v->n.x); N.push_back(v->n.y); N.push_back(v->n.z);
+                    T.push_back(v->t.x); T.push_back(v->t.y);
+                }
+            });
+            meshes[i].num_faces = int(P.size() / 9);
+            meshes[i].p = P.data();
+            meshes[i].n = N.data();
+            meshes[i].t = shading_ ? T.data() : nullptr;
+        }
+        triangles_done = true;
+    }
+
     void gather(const Scene& scene, bool shading) {
+        gather_description(scene, shading);
+        gather_triangles();
+    }
+
+    void gather_description(const Scene& scene, bool shading) {
+        shading_ = shading;
         std::map<const Mesh*, int> mesh_ids;
         scene.traverse_primitive_nodes([&](const SceneNode& node, Mat4 global_transform) {
             if (node.type != SceneNodeType::Primitive) {
@@ -394,19 +477,7 @@ struct SceneExport {
                 mesh_p.emplace_back();
                 mesh_n.emplace_back();
                 mesh_t.emplace_back();
-                auto& P = mesh_p.back();
-                auto& N = mesh_n.back();
-                auto& T = mesh_t.back();
-                P.reserve(size_t(mesh->num_triangles()) * 9);
-                N.reserve(size_t(mesh->num_triangles()) * 9);
-                T.reserve(size_t(mesh->num_triangles()) * 6);
-                mesh->foreach_triangle([&](int, const Mesh::Tri& tri) {
-                    for (const auto* v : { &tri.p1, &tri.p2, &tri.p3 }) {
-                        P.push_back(v->p.x); P.push_back(v->p.y); P.push_back(v->p.z);
-                        N.push_back(v->n.x); N.push_back(v->n.y); N.push_back(v->n.z);
-                        T.push_back(v->t.x); T.push_back(v->t.y);
-                    }
-                });
+                mesh_list.push_back(mesh);
             }
             LmcuPrimitive p{};
             p.node_index = node.index;
@@ -449,13 +520,8 @@ struct SceneExport {
             camera.aspect = v["aspect"];
             has_camera = true;
         }
-        meshes.resize(mesh_p.size());
-        for (size_t i = 0; i < mesh_p.size(); i++) {
-            meshes[i].num_faces = int(mesh_p[i].size() / 9);
-            meshes[i].p = mesh_p[i].data();
-            meshes[i].n = mesh_n[i].data();
-            meshes[i].t = shading ? mesh_t[i].data() : nullptr;
-        }
+        meshes.assign(mesh_p.size(), LmcuMesh{});
+        for (size_t i = 0; i < mesh_p.size(); i++) meshes[i].num_faces = mesh_list[i]->num_triangles();   // arrays: gather_triangles()
         for (size_t i = 0; i < textures.size(); i++) textures[i].data = tex_data[i].data();
         for (auto& m : mats) {
             if (m.num_entries > 0) {
@@ -475,19 +541,65 @@ struct SceneExport {
         desc.materials = mats.data();
         desc.lights = lights.data();
         desc.camera = has_camera ? &camera : nullptr;
+        compute_signature();
     }
 };
 
+// One uploaded + built scene on one device.  Shared (through the cache below) by every component of this plugin that
+// exports the same lm::Scene content: a renderer asset that is re-created for every render, as the reference's examples
+// do with lm::load<Renderer>, finds the scene its predecessor uploaded.
 struct DeviceScene {
     LmcuScene* h = nullptr;
+    uint64_t sig = 0;
+    int device = 0;
+    bool shading = false;
+    std::map<int, Transform> transforms;   // SceneNode::index -> Transform for Accel::Hit
+    std::mutex render_mu;                  // one render at a time per device scene (film and path pools live in it)
     ~DeviceScene() { if (h) lmcu_scene_destroy(h); }
-    void upload(const SceneExport& ex, int device) {
+    DeviceScene() = default;
+    DeviceScene(const DeviceScene&) = delete;
+    void upload(SceneExport& ex, int dev) {
+        ex.gather_triangles();
         if (h) { lmcu_scene_destroy(h); h = nullptr; }
+        device = dev; sig = ex.sig; shading = ex.shading_;
+        transforms = ex.transforms;
         check(lmcu_scene_create(device, &h));
         check(lmcu_scene_upload(h, &ex.desc));
         check(lmcu_accel_build(h, nullptr, nullptr));
     }
 };
+
+struct SceneCache {
+    std::mutex mu;
+    std::list<std::shared_ptr<DeviceScene>> entries;      // most recently used first
+    static constexpr size_t kMax = 4;
+    long long hits = 0, misses = 0;
+    std::shared_ptr<DeviceScene> acquire(SceneExport& ex, int device, bool use_cache) {
+        if (use_cache) {
+            std::unique_lock<std::mutex> lk(mu);
+            for (auto it = entries.begin(); it != entries.end(); ++it) {
+                if ((*it)->sig == ex.sig && (*it)->device == device && (*it)->shading == ex.shading_) {
+                    auto hit = *it;
+                    hits++;
+                    entries.erase(it);
+                    entries.push_front(hit);
+                    return hit;
+                }
+            }
+        }
+        auto fresh = std::make_shared<DeviceScene>();
+        fresh->upload(ex, device);
+        if (use_cache) {
+            std::unique_lock<std::mutex> lk(mu);
+            misses++;
+            entries.push_front(fresh);
+            while (entries.size() > kMax) entries.pop_back();
+        }
+        return fresh;
+    }
+    void clear() { std::unique_lock<std::mutex> lk(mu); entries.clear(); }
+};
+SceneCache g_scene_cache;
 
 }
 
@@ -500,22 +612,25 @@ struct DeviceScene {
    Compressed 8-wide BVH built and traversed on a CUDA device (sm_100a).
 
    :param int device: CUDA device index. Default: 0.
+   :param bool cache: Reuse the device scene of an earlier build of the same scene content. Default: true.
 
    ``intersect()`` keeps the scalar contract of :cpp:func:`lm::Accel::intersect` (one ray per call,
-   thread-safe) for callers such as ``scene::default``; batched rays and the device-resident renderers
-   are the fast path.
+   thread-safe and lock-free: every calling thread owns a pinned ray/hit slot and a CUDA stream) for callers
+   such as ``scene::default`` under the reference's CPU renderers; batched rays and the device-resident
+   renderers are the fast path.
 \endrst
 */
 class Accel_CudaBVH final : public Accel {
 private:
     int device_ = 0;
-    DeviceScene dev_;
-    std::map<int, Transform> transforms_;
+    bool cache_ = true;
+    std::shared_ptr<DeviceScene> dev_;
     mutable std::mutex mu_;
 
 public:
     virtual void construct(const Json& prop) override {
         device_ = json::value<int>(prop, "device", 0);
+        cache_ = json::value<bool>(prop, "cache", true);
     }
 
     // Component::save / load (include/lm/component.h:210-236), the counterpart of accel::sahbvh archiving nodes_, trs_,
@@ -525,15 +640,15 @@ public:
     // in tests/test_gpu_parity.py::test_accel_save_load_round_trip.
     virtual void save(OutputArchive& ar) override {
         std::vector<unsigned char> blob;
-        if (dev_.h) {
-            int64_t n = 0;
-            check(lmcu_accel_save_size(dev_.h, &n));
-            blob.resize(size_t(n));
-            check(lmcu_accel_save(dev_.h, blob.data(), n));
-        }
         std::vector<int> keys;
         std::vector<Transform> values;
-        for (const auto& [k, v] : transforms_) { keys.push_back(k); values.push_back(v); }
+        if (dev_ && dev_->h) {
+            int64_t n = 0;
+            check(lmcu_accel_save_size(dev_->h, &n));
+            blob.resize(size_t(n));
+            check(lmcu_accel_save(dev_->h, blob.data(), n));
+            for (const auto& [k, v] : dev_->transforms) { keys.push_back(k); values.push_back(v); }
+        }
         ar(device_, blob, keys, values);
     }
 
@@ -542,41 +657,41 @@ public:
         std::vector<int> keys;
         std::vector<Transform> values;
         ar(device_, blob, keys, values);
-        transforms_.clear();
-        for (size_t i = 0; i < keys.size() && i < values.size(); i++) transforms_.emplace(keys[i], values[i]);
+        dev_.reset();
         if (blob.empty()) return;
-        if (dev_.h) { lmcu_scene_destroy(dev_.h); dev_.h = nullptr; }
-        check(lmcu_scene_create(device_, &dev_.h));
-        check(lmcu_accel_load(dev_.h, blob.data(), int64_t(blob.size())));
+        auto fresh = std::make_shared<DeviceScene>();          // restored from the blob: never enters the cache
+        fresh->device = device_;
+        for (size_t i = 0; i < keys.size() && i < values.size(); i++) fresh->transforms.emplace(keys[i], values[i]);
+        check(lmcu_scene_create(device_, &fresh->h));
+        check(lmcu_accel_load(fresh->h, blob.data(), int64_t(blob.size())));
+        dev_ = fresh;
     }
 
     virtual void build(const Scene& scene) override {
         LM_INFO("Flattening scene");
         SceneExport ex;
-        ex.gather(scene, false);
+        ex.gather_description(scene, false);
         LM_INFO("Building");
-        dev_.upload(ex, device_);
-        transforms_ = std::move(ex.transforms);
+        dev_ = g_scene_cache.acquire(ex, device_, cache_);
     }
 
     // Batched closest hit: n rays in, n hits out, one kernel launch.  Hit::primitive is the scene node
     // index as in the scalar contract; the transform of that node is transforms_.at(primitive).
     void intersect_batch(const LmcuRay* rays, long long n, LmcuHit* hits) const {
-        std::unique_lock<std::mutex> lk(mu_);
-        check(lmcu_accel_intersect(dev_.h, rays, n, hits));
+        if (!dev_) LM_THROW_EXCEPTION(Error::Unsupported, "accel::cuda_bvh: build() or load() first");
+        std::unique_lock<std::mutex> lk(mu_);                  // the batch path stages through the scene's own stream
+        check(lmcu_accel_intersect(dev_->h, rays, n, hits));
     }
 
     virtual std::optional<Hit> intersect(Ray ray, Float tmin, Float tmax) const override {
-        LmcuRay r{ { ray.o.x, ray.o.y, ray.o.z }, { ray.d.x, ray.d.y, ray.d.z }, tmin, tmax };
+        if (!dev_) LM_THROW_EXCEPTION(Error::Unsupported, "accel::cuda_bvh: build() or load() first");
+        const LmcuRay r{ { ray.o.x, ray.o.y, ray.o.z }, { ray.d.x, ray.d.y, ray.d.z }, tmin, tmax };
         LmcuHit h{};
-        {
-            std::unique_lock<std::mutex> lk(mu_);
-            check(lmcu_accel_intersect(dev_.h, &r, 1, &h));
-        }
+        check(lmcu_accel_intersect1(dev_->h, &r, &h));         // lock-free: a pinned slot + stream per calling thread
         if (h.primitive < 0) {
             return {};
         }
-        return Hit{ h.t, Vec2(h.u, h.v), transforms_.at(h.primitive), h.primitive, h.face };
+        return Hit{ h.t, Vec2(h.u, h.v), dev_->transforms.at(h.primitive), h.primitive, h.face };
     }
 };
 
@@ -604,7 +719,8 @@ class Film_Cuda final : public Film {
 private:
     int w_ = 0, h_ = 0;
     std::vector<float> rgb_;                // [h][w][3], row 0 = bottom row (pixel y = 0)
-    std::vector<Float> temp_;               // buffer() view
+    std::vector<Float> temp_;               // buffer() view, refreshed only after the pixels changed
+    bool dirty_ = true;
 
     static void atomic_add(float* p, float v) {
         auto* a = reinterpret_cast<uint32_t*>(p);
@@ -624,7 +740,7 @@ public:
         rgb_.assign(size_t(w_) * h_ * 3, 0.f);
     }
     // bulk interface of the CUDA renderers
-    float* data() { return rgb_.data(); }
+    float* data() { dirty_ = true; return rgb_.data(); }
     size_t num_floats() const { return rgb_.size(); }
 
     virtual FilmSize size() const override { return { w_, h_ }; }
@@ -632,6 +748,7 @@ public:
     virtual void set_pixel(int x, int y, Vec3 v) override {
         float* p = &rgb_[(size_t(y) * w_ + x) * 3];
         p[0] = float(v.x); p[1] = float(v.y); p[2] = float(v.z);
+        dirty_ = true;
     }
     virtual bool save(const std::string& outpath) const override {
         const auto dot = outpath.find_last_of('.');
@@ -653,7 +770,15 @@ public:
         return tmp->save(outpath);
     }
     virtual FilmBuffer buffer() override {
-        temp_.assign(rgb_.begin(), rgb_.end());
+        if (dirty_ || temp_.size() != rgb_.size()) {
+            temp_.resize(rgb_.size());
+            const float* src = rgb_.data();
+            Float* dst = temp_.data();
+            const long long n = (long long)rgb_.size();
+            #pragma omp parallel for schedule(static)
+            for (long long i = 0; i < n; i++) dst[i] = Float(src[i]);
+            dirty_ = false;
+        }
         return FilmBuffer{ w_, h_, temp_.data() };
     }
     virtual void accum(const Film* film_) override {
@@ -663,21 +788,26 @@ public:
             return;
         }
         for (size_t i = 0; i < rgb_.size(); i++) rgb_[i] += film->rgb_[i];
+        dirty_ = true;
     }
     virtual void splat_pixel(int x, int y, Vec3 v) override {
         float* p = &rgb_[(size_t(y) * w_ + x) * 3];
         atomic_add(p, float(v.x)); atomic_add(p + 1, float(v.y)); atomic_add(p + 2, float(v.z));
+        dirty_ = true;
     }
     virtual void update_pixel(int x, int y, const PixelUpdateFunc& update_func) override {
         float* p = &rgb_[(size_t(y) * w_ + x) * 3];
         const Vec3 v = update_func(Vec3(p[0], p[1], p[2]));
         p[0] = float(v.x); p[1] = float(v.y); p[2] = float(v.z);
+        dirty_ = true;
     }
     virtual void rescale(Float s) override {
         for (auto& v : rgb_) v = float(v * s);
+        dirty_ = true;
     }
     virtual void clear() override {
         rgb_.assign(rgb_.size(), 0.f);
+        dirty_ = true;
     }
 };
 
@@ -691,7 +821,8 @@ protected:
     Scene* scene_;
     Film* film_;
     mutable int device_ = 0;
-    mutable DeviceScene dev_;
+    bool cache_ = true;
+    mutable std::shared_ptr<DeviceScene> dev_;
 
 public:
     virtual void foreach_underlying(const ComponentVisitor& visit) override {
@@ -704,12 +835,15 @@ protected:
         scene_ = json::comp_ref<Scene>(prop, "scene");
         film_ = json::comp_ref<Film>(prop, "output");
         device_ = json::value<int>(prop, "device", 0);
+        cache_ = json::value<bool>(prop, "cache", true);      // false: export, upload and build again on every render()
     }
 
+    // The device scene for the CURRENT content of scene_: found in the cache when nothing that the export reads has
+    // changed since an earlier render (by this or any other component of the plugin), else exported, uploaded and built.
     void upload() const {
         SceneExport ex;
-        ex.gather(*scene_, true);
-        dev_.upload(ex, device_);
+        ex.gather_description(*scene_, true);
+        dev_ = g_scene_cache.acquire(ex, device_, cache_);
     }
 
     // Host destination of the device film: film::cuda's own pixel buffer (one copy), else a staging vector
@@ -720,8 +854,18 @@ protected:
         return staging.data();
     }
 
-    void write_film(const std::vector<float>& rgb, bool skip_black) const {
-        if (dynamic_cast<Film_Cuda*>(film_)) return;                       // already written in place
+    // `skip_marked`: pixels whose value is negative were not written by the renderer (LmcuRenderParams::ao_mark_misses)
+    // and keep what the film held
+    void write_film(const std::vector<float>& rgb, bool skip_marked) const {
+        if (auto* fc = dynamic_cast<Film_Cuda*>(film_)) {
+            if (rgb.empty()) return;                                       // already written in place
+            float* dst = fc->data();
+            for (size_t i = 0; i < rgb.size(); i += 3) {
+                if (skip_marked && rgb[i] < 0.f) continue;
+                dst[i] = rgb[i]; dst[i + 1] = rgb[i + 1]; dst[i + 2] = rgb[i + 2];
+            }
+            return;
+        }
         // a foreign film takes its pixels one set_pixel at a time (film::bitmap: a CAS loop on a 24-byte atomic per call,
         // src/film/film_bitmap.cpp:41-54): rows go out through the reference's own parallel::foreach, otherwise this
         // write-back of a 4K image costs more than rendering it
@@ -729,7 +873,7 @@ protected:
         parallel::foreach(size.h, [&](long long y, int) {
             for (int x = 0; x < size.w; x++) {
                 const float* c = &rgb[(size_t(y) * size.w + x) * 3];
-                if (skip_black && c[0] == 0.f && c[1] == 0.f && c[2] == 0.f) continue;
+                if (skip_marked && c[0] < 0.f) continue;
                 film_->set_pixel(x, int(y), Vec3(c[0], c[1], c[2]));
             }
         });
@@ -764,7 +908,10 @@ public:
         for (int i = 0; i < 3; i++) { p.bg_color[i] = bg_color_[i]; p.color[i] = color_ ? (*color_)[i] : 0_f; }
         std::vector<float> rgb;
         LmcuRenderStats st{};
-        check(lmcu_render_raycast(dev_.h, &p, film_target(rgb), &st));
+        {
+            std::unique_lock<std::mutex> lk(dev_->render_mu);
+            check(lmcu_render_raycast(dev_->h, &p, film_target(rgb), &st));
+        }
         write_film(rgb, false);
         return { {"elapsed", st.elapsed} };
     }
@@ -784,14 +931,22 @@ public:
     }
 
     virtual Json render() const override {
+        // renderer::ao itself checks nothing and dereferences a missing camera (functest/renderer_ao.cpp:30); the checks of
+        // renderer::raycast (renderer_raycast.cpp:63-64) turn that into the reference's own exceptions
+        scene_->require_primitive();
+        scene_->require_camera();
         upload();
         const auto size = film_->size();
         LmcuRenderParams p{};
         p.width = size.w; p.height = size.h; p.spp = spp_; p.seed = unsigned(rng_seed_); p.ao_distance = .2_f;
-        std::vector<float> rgb;
+        p.ao_mark_misses = 1;                // the reference leaves a pixel whose primary ray misses untouched (:32-34)
+        std::vector<float> rgb(size_t(size.w) * size.h * 3);
         LmcuRenderStats st{};
-        check(lmcu_render_ao(dev_.h, &p, film_target(rgb), &st));
-        write_film(rgb, false);
+        {
+            std::unique_lock<std::mutex> lk(dev_->render_mu);
+            check(lmcu_render_ao(dev_->h, &p, rgb.data(), &st));
+        }
+        write_film(rgb, true);
         return { {"elapsed", st.elapsed} };
     }
 };
@@ -864,6 +1019,14 @@ public:
         }
     }
 
+    // progress::update / update_time between wavefront batches (src/scheduler.cpp:45,91,133,173 report per sample)
+    struct ProgressCtx { bool timed; int devices; };
+    static void report_progress(void* user, int64_t processed_paths, int64_t, double elapsed) {
+        const auto* c = static_cast<const ProgressCtx*>(user);
+        if (c->timed) progress::update_time(elapsed);
+        else progress::update(processed_paths * c->devices);       // every device is as far along as the reporting one
+    }
+
     virtual Json render() const override {
         scene_->require_renderable();
         film_->clear();
@@ -882,31 +1045,44 @@ public:
         LmcuRenderStats st{};
         const int G = int(devices_.size());
         const bool image = primary_mode_ == LMCU_PRIMARY_IMAGE;
+        const bool timed = scheduler_ == LMCU_SCHED_TIME;
         const long long total = image ? num_samples_ : spp_;      // sample schedulers: the work to split
+        // progress context of the reference's schedulers: samples (spp::sample counts pixels x spp, scheduler.cpp:39) or time
+        const long long total_paths = image ? num_samples_ : (long long)size.w * size.h * spp_;
+        if (timed) progress::start(progress::ProgressMode::Time, 0, render_time_);
+        else progress::start(progress::ProgressMode::Samples, total_paths, -1);
+        struct ProgressEnd { ~ProgressEnd() { progress::end(); } } progress_end;
+        ProgressCtx pctx{ timed, G };
+        p.progress = &Renderer_PT_Cuda::report_progress;
+        p.progress_user = &pctx;
         if (G == 1) {
             device_ = devices_[0];
             upload();
             p.spp = spp_; p.num_samples = num_samples_; p.rescale = 1;
-            check(lmcu_render_pt(dev_.h, &p, target, &st));
+            std::unique_lock<std::mutex> lk(dev_->render_mu);
+            check(lmcu_render_pt(dev_->h, &p, target, &st));
         }
         else {
             // Sample split: one host thread + one replicated device scene per GPU
-            if (scheduler_ == LMCU_SCHED_SAMPLE && total < G) {
+            if (!timed && total < G) {
                 LM_THROW_EXCEPTION(Error::InvalidArgument, "renderer::pt_cuda: spp / num_samples must be >= the number of devices");
             }
             SceneExport ex;
-            ex.gather(*scene_, true);
-            std::vector<DeviceScene> devs(G);
+            ex.gather_description(*scene_, true);
+            std::vector<std::shared_ptr<DeviceScene>> devs(G);
+            std::vector<std::unique_lock<std::mutex>> locks(G);
             std::vector<LmcuRenderStats> stats(G);
             std::vector<std::string> errors(G);
             std::vector<std::thread> threads;
             for (int g = 0; g < G; g++) {
                 threads.emplace_back([&, g] {
                     try {
-                        devs[g].upload(ex, devices_[g]);
+                        devs[g] = g_scene_cache.acquire(ex, devices_[g], cache_);
+                        locks[g] = std::unique_lock<std::mutex>(devs[g]->render_mu);
                         LmcuRenderParams q = p;
                         q.rescale = 0;
-                        if (scheduler_ == LMCU_SCHED_SAMPLE) {
+                        if (g != 0) q.progress = nullptr;
+                        if (!timed) {
                             const long long base = total / G, rem = total % G;
                             const long long mine = base + (g < rem ? 1 : 0);
                             q.spp = image ? 0 : mine; q.num_samples = image ? mine : 0;
@@ -917,29 +1093,39 @@ public:
                             // and reports how many it finished; the counts are summed like the films
                             q.sample_offset = (long long)g << 40;
                         }
-                        check(lmcu_render_pt(devs[g].h, &q, nullptr, &stats[g]));
+                        check(lmcu_render_pt(devs[g]->h, &q, nullptr, &stats[g]));
                     }
                     catch (const std::exception& e) { errors[g] = e.what(); }
                 });
             }
             for (auto& t : threads) t.join();
             for (const auto& e : errors) if (!e.empty()) LM_THROW_EXCEPTION(Error::None, "renderer::pt_cuda: {}", e);
-            std::vector<void*> peers;
-            for (int g = 1; g < G; g++) {
-                check(lmcu_enable_peer_access(devices_[0], devices_[g]));
-                void* ptr = nullptr; int64_t n = 0;
-                check(lmcu_film_device_ptr(devs[g].h, &ptr, &n));
-                peers.push_back(ptr);
-            }
             st.processed = 0;
             for (int g = 0; g < G; g++) {
                 st.processed += stats[g].processed;
                 st.elapsed = std::max(st.elapsed, stats[g].elapsed);
             }
-            // renderer_pt.cpp:307-312 on the combined film
+            // renderer_pt.cpp:307-312 on the combined film.  Slice-parallel combine over NVLink peer memory: device g sums
+            // slice g of all G films and stores it, rescaled, into device 0's film (include/lmcu.h, lmcu_film_reduce_slice).
             const double scale = image ? double(size.w) * size.h / double(st.processed) : 1.0 / double(st.processed);
-            check(lmcu_film_reduce_peers(devs[0].h, peers.data(), int(peers.size()), scale));
-            check(lmcu_film_download(devs[0].h, target));
+            std::vector<void*> films(G);
+            int64_t n = 0;
+            for (int g = 0; g < G; g++) check(lmcu_film_device_ptr(devs[g]->h, &films[g], &n));
+            for (int a = 0; a < G; a++) for (int b = 0; b < G; b++) if (a != b) check(lmcu_enable_peer_access(devices_[a], devices_[b]));
+            threads.clear();
+            const int64_t quads = n / 4;
+            for (int g = 0; g < G; g++) {
+                threads.emplace_back([&, g] {
+                    try {
+                        const int64_t begin = quads * g / G * 4, end = g == G - 1 ? n : quads * (g + 1) / G * 4;
+                        check(lmcu_film_reduce_slice(devs[g]->h, films.data(), G, films[0], begin, end, scale));
+                    }
+                    catch (const std::exception& e) { errors[g] = e.what(); }
+                });
+            }
+            for (auto& t : threads) t.join();
+            for (const auto& e : errors) if (!e.empty()) LM_THROW_EXCEPTION(Error::None, "renderer::pt_cuda: {}", e);
+            check(lmcu_film_download(devs[0]->h, target));
         }
         write_film(rgb, false);
         return { {"processed", st.processed}, {"elapsed", st.elapsed} };
@@ -964,6 +1150,14 @@ extern "C" int lm_cuda_accel_intersect_batch(const char* accel_loc, const LmcuRa
         if (err && cap > 0) std::snprintf(err, size_t(cap), "%s", e.what());
         return -1;
     }
+}
+
+// Test / diagnostics hook: how often a component found its scene already on the device, and how often it had to export,
+// upload and build it.  `clear` != 0 also drops the cached device scenes.
+extern "C" void lm_cuda_cache_stats(long long* hits, long long* misses, int clear) {
+    if (hits) *hits = lm::g_scene_cache.hits;
+    if (misses) *misses = lm::g_scene_cache.misses;
+    if (clear) lm::g_scene_cache.clear();
 }
 
 // Host-logic test hook (tests/test_plugin_probe.py): what the plugin recovers from an lm::Scene through the public

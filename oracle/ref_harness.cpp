@@ -266,6 +266,10 @@ int lmref_render(void* s, const char* renderer_key, const LmcuRenderParams* p, d
         const char* film_key = std::getenv("LMREF_FILM");                  // tests: e.g. the plugin's film::cuda
         auto* film = lm::load<Film>("film", film_key ? film_key : "film::bitmap", { {"w", p->width}, {"h", p->height} });
         if (!film) LM_THROW_EXCEPTION(Error::InvalidArgument, "unknown film");
+        if (const char* e = std::getenv("LMREF_FILM_PREFILL")) {           // tests: a film that already holds an image
+            const double v = std::atof(e);                                 // (renderer::ao never clears its film)
+            for (int y = 0; y < p->height; y++) for (int x = 0; x < p->width; x++) film->set_pixel(x, y, Vec3(v));
+        }
         static const char* modes[] = { "naive", "nee", "mis" };
         Json prop{
             {"scene", rs->scene_loc}, {"output", film->loc()},

@@ -43,7 +43,7 @@ def cases():
     axis = _rays(o, np.tile([0.0, 0.0, -1.0], (len(o), 1)))
     side = _rays(np.stack([np.full(49, -3.0), xs, np.zeros(49)], -1), np.tile([1.0, 0.0, 0.0], (49, 1)))   # IN the mesh plane
     diag = _rays(o, np.tile([0.0, 1e-3, -1.0], (len(o), 1)))
-    out["axis_parallel"] = (_scene(g), np.concatenate([axis, side, diag]), 0.7)
+    out["axis_parallel"] = (_scene(g), np.concatenate([axis, side, diag]), 281)
 
     # 2. degenerate triangles (zero area: repeated vertex, collinear) and exact duplicates mixed into a soup
     soup = scenes._f32(rng.rand(60, 3, 3) * 2 - 1)
@@ -52,27 +52,27 @@ def cases():
     deg[10:, 2] = deg[10:, 0] + 2 * (deg[10:, 1] - deg[10:, 0])  # collinear
     dup = soup[20:30].copy()                                     # coincident copies: exact ties
     tris = np.concatenate([soup, scenes._f32(deg), dup])
-    out["degenerate_and_duplicate"] = (_scene(tris), scenes.random_rays(6000, np.array([-1.5, -1.5, -1.5]), np.array([1.5, 1.5, 1.5]), seed=9), 0.25)
+    out["degenerate_and_duplicate"] = (_scene(tris), scenes.random_rays(6000, np.array([-1.5, -1.5, -1.5]), np.array([1.5, 1.5, 1.5]), seed=9), 99)
 
     # 3. a fan of triangles sharing one centroid region (duplicate Morton codes) + a needle and a huge triangle
     ang = np.linspace(0, 2 * np.pi, 33)
     fan = [((0, 0, 0), (np.cos(a), np.sin(a), 0.1 * k), (np.cos(b), np.sin(b), 0.1 * k)) for k in range(4) for a, b in zip(ang[:-1], ang[1:])]
     extra = [((-50, -50, -2), (50, -50, -2), (0, 80, -2)), ((0.3, 0.3, -1), (0.3000001, 0.3, 1), (0.3, 0.3000001, 1))]
     out["fan_needle_huge"] = (_scene(scenes._f32(np.asarray(fan + extra, dtype=np.float64))),
-                              scenes.random_rays(6000, np.array([-1.5, -1.5, -3.0]), np.array([1.5, 1.5, 1.5]), seed=10), 0.02)
+                              scenes.random_rays(6000, np.array([-1.5, -1.5, -3.0]), np.array([1.5, 1.5, 1.5]), seed=10), 0)
 
     # 4. far from the origin and non-float-representable (FP64 triangle records): stresses the padded FP32 node test
     M = scenes.translate((10000.25, -5000.5, 2000.125)) @ scenes.rotate(33.0, (1, 2, 3)) @ scenes.scale((1.7, 1.7, 1.7))
     soup4 = scenes._f32(rng.rand(300, 3, 3) * 2 - 1)
     r4 = scenes.random_rays(6000, np.array([-3, -3, -3.]), np.array([3, 3, 3.]), seed=11)
     r4["o"] += np.array([10000.25, -5000.5, 2000.125])
-    out["far_offset_rotated"] = (_scene(soup4, M), r4, 0.01)
+    out["far_offset_rotated"] = (_scene(soup4, M), r4, 0)
 
     # 5. tiny scale
     soup5 = scenes._f32((rng.rand(300, 3, 3) * 2 - 1) * 1e-3)
     r5 = scenes.random_rays(4000, np.array([-2e-3] * 3), np.array([2e-3] * 3), seed=12)
     r5["tmin"] = 1e-9
-    out["tiny_scale"] = (_scene(soup5), r5, 0.01)
+    out["tiny_scale"] = (_scene(soup5), r5, 0)
 
     # 6. ray parameter corner cases on a plain soup: empty interval, zero-length window, tmin = 0 on the surface,
     #    unnormalised directions (t scales with 1/|d|), a hit exactly AT tmax (inclusive) and just before it
@@ -82,5 +82,5 @@ def cases():
     zero = base.copy(); zero["tmax"] = 0.0
     longd = base.copy(); longd["d"] *= 1e3
     shortd = base.copy(); shortd["d"] *= 1e-3
-    out["ray_parameters"] = (_scene(soup6), np.concatenate([base, empty, zero, longd, shortd]), 0.01)
+    out["ray_parameters"] = (_scene(soup6), np.concatenate([base, empty, zero, longd, shortd]), 0)
     return out

@@ -28,10 +28,15 @@ def classify_hits(ref_hits, hits):
             "other": int(other.sum()), "bad_mask": bad}
 
 
-def assert_hit_parity(ref_hits, hits, max_special_frac=2e-4):
+def assert_hit_parity(ref_hits, hits, max_special=None):
+    """G1.  `max_special`: how many special rays (ties + reference boundary misses) the batch may hold.  Every fixture
+    states the count MEASURED for it (the batches are deterministic: the numbers were taken with the CPU build of the
+    traversal, tests/hostsim, against the reference); without one the allowance is 2e-4 of the batch — C1's 1920x1080
+    symmetric camera has 167 of 2 073 600 = 8e-5.  Anything that is neither kind fails whatever the allowance."""
     c = classify_hits(ref_hits, hits)
     assert c["other"] == 0, "non-tie closest-hit mismatches: %d" % c["other"]
-    assert c["ties"] + c["ref_boundary_miss"] <= max(4, max_special_frac * len(hits)), c
+    allowed = int(2e-4 * len(hits)) if max_special is None else max_special
+    assert c["ties"] + c["ref_boundary_miss"] <= allowed, {k: v for k, v in c.items() if k != "bad_mask"}
     same = ~c["bad_mask"] & (ref_hits["primitive"] >= 0)
     # FP64 leaf test with the reference's operation order: t, u, v are bit-identical, far inside the 1e-5 gate
     assert (ref_hits["t"][same] == hits["t"][same]).all()
@@ -70,3 +75,33 @@ def assert_pt_parity(ref_film, film, spp, rel_mean=0.01, z_frac=2e-3):
     frac = float((np.abs(z) > 4).mean())
     assert frac <= max(z_frac, 2.0 / z.size), "structured difference: %.4f of 8x8 blocks have |z|>4" % frac
     return {"rel_mean": rel, "z_frac": frac}
+
+
+def assert_pt_rmse(ref_batches, our_batches, k=1.25):
+    """G3, RMSE gate: both renderers deliver B independent equal-spp estimates of the same image (different
+    seeds / disjoint sample blocks).  The per-channel RMSE between the two batch MEANS must not exceed k times what
+    Monte-Carlo noise alone predicts,
+
+        rmse  <=  k * sqrt( mean over pixels of (var_ref + var_ours) / B ),
+
+    where var_* is the per-pixel sample variance ACROSS the batches — so the tolerance is measured on the spot for every
+    scene and sampling mode, not assumed.  E[rmse^2] equals the right-hand side without k when both estimators are unbiased;
+    any bias adds its mean square on top.  k = 1.25 covers the sampling error of the variance estimate itself
+    (ref-vs-ref runs with different seeds land at 0.97 .. 1.04 on these scenes; tests/test_hostsim.py calibrates it).
+    Returns rmse / predicted per channel."""
+    ref_batches = np.asarray(ref_batches, dtype=np.float64)
+    our_batches = np.asarray(our_batches, dtype=np.float64)
+    B = ref_batches.shape[0]
+    assert B >= 4 and our_batches.shape == ref_batches.shape
+    mr, mo = ref_batches.mean(axis=0), our_batches.mean(axis=0)
+    noise2 = (ref_batches.var(axis=0, ddof=1) + our_batches.var(axis=0, ddof=1)) / B
+    got = np.sqrt(((mr - mo) ** 2).mean(axis=(0, 1)))
+    want = np.sqrt(noise2.mean(axis=(0, 1)))
+    ratio = got / np.maximum(want, 1e-30)
+    assert (ratio <= k).all(), "per-channel RMSE %s exceeds %.2f x the Monte-Carlo prediction %s" % (got, k, want)
+    return ratio
+
+
+def render_batches(render, batches, spp):
+    """B estimates of spp samples each: render(batch_index) -> image."""
+    return np.stack([np.asarray(render(b), dtype=np.float64) for b in range(batches)])

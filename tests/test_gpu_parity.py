@@ -10,7 +10,7 @@ import pytest
 
 import lmcu
 from lmcu import abi, scenes
-from parity import assert_hit_parity, assert_pt_parity, classify_hits, rmse
+from parity import assert_hit_parity, assert_pt_parity, assert_pt_rmse, classify_hits, rmse
 
 pytestmark = pytest.mark.gpu
 
@@ -49,7 +49,8 @@ def test_g1_closest_hit_vs_golden(name, records, monkeypatch):
     sc = lmcu.Scene(sb)
     assert bool(sc.build_stats.triangles_fp32) == (records == "float" and name != "cornell_fp64")
     hits = sc.intersect(golden_rays(name, sb))
-    assert_hit_parity(golden_hits(name), hits, max_special_frac=3e-3)
+    # measured: the symmetric camera of the fixtures meets shared edges exactly on 22 / 21 / 16 / 0 of the 26 736 rays
+    assert_hit_parity(golden_hits(name), hits, max_special={"cornell": 22, "cornell_fp64": 21, "spheres12": 16, "heightfield48": 0}[name])
     if name == "spheres12":
         film, _ = sc.render("pt", abi.render_params(96, 54, spp=8, max_verts=8))
         assert np.isfinite(film).all() and film.mean() > 0.01
@@ -61,7 +62,7 @@ def test_g1_full_c1_vs_reference(reference):
     sb = scenes.cornell_box()
     sc, rs = lmcu.Scene(sb), reference.RefScene(sb)
     rays = scenes.camera_rays(sb.camera, 1920, 1080)
-    c = assert_hit_parity(rs.intersect(rays), sc.intersect(rays), max_special_frac=2e-4)
+    c = assert_hit_parity(rs.intersect(rays), sc.intersect(rays), max_special=167)      # measured: 151 ties + 16 boundary misses
     print("C1 special cases:", {k: v for k, v in c.items() if k != "bad_mask"})
     rs.close(); sc.close()
 
@@ -81,10 +82,10 @@ def test_g1_incoherent_and_window(reference):
     sb = scenes.cornell_spheres(32)
     sc, rs = lmcu.Scene(sb), reference.RefScene(sb)
     rays = scenes.random_rays(400000, np.array([-1, 0, -1.]), np.array([1, 2, 1.]), seed=5)
-    assert_hit_parity(rs.intersect(rays), sc.intersect(rays))
+    assert_hit_parity(rs.intersect(rays), sc.intersect(rays), max_special=0)
     rays["tmin"], rays["tmax"] = 0.25, 0.8
     hr, hs = rs.intersect(rays), sc.intersect(rays)
-    assert_hit_parity(hr, hs)
+    assert_hit_parity(hr, hs, max_special=0)
     ok = hs["primitive"] >= 0
     assert ((hs["t"][ok] >= 0.25) & (hs["t"][ok] <= 0.8)).all()
     rs.close(); sc.close()
@@ -99,7 +100,7 @@ def test_g1_tiny_and_ragged_scenes(reference):
         sb.set_camera(position=(0, 0, 4), center=(0, 0, 0), up=(0, 1, 0), vfov=40, aspect=1)
         sc, rs = lmcu.Scene(sb), reference.RefScene(sb)
         rays = scenes.camera_rays(sb.camera, 128, 128)
-        assert_hit_parity(rs.intersect(rays), sc.intersect(rays), max_special_frac=3e-3)
+        assert_hit_parity(rs.intersect(rays), sc.intersect(rays), max_special=0)
         rs.close(); sc.close()
 
 
@@ -110,7 +111,7 @@ def test_g1_instanced_transforms(reference):
     assert not sc.build_stats.triangles_fp32
     rays = np.concatenate([scenes.camera_rays(sb.camera, 480, 270),
                            scenes.random_rays(100000, np.array([-2, 0, -2.]), np.array([2, 3, 2.]))])
-    assert_hit_parity(rs.intersect(rays), sc.intersect(rays))
+    assert_hit_parity(rs.intersect(rays), sc.intersect(rays), max_special=0)
     rs.close(); sc.close()
 
 
@@ -146,6 +147,105 @@ def test_accel_save_load_round_trip(tmp_path):
     with pytest.raises(lmcu.LmcuError) as e:           # a blob of another scene
         lmcu.Scene(scenes.cornell_box(), accel_blob=blob)
     assert e.value.code == 1
+    # same triangle / primitive counts, other geometry or other transforms: refused by the description digest (the
+    # world-space triangles would come from the blob, materials and primitives from the upload)
+    base = scenes.instanced_spheres(grid=2, num_theta=8)
+    blob = lmcu.Scene(base).save_accel()
+    moved = scenes.instanced_spheres(grid=2, num_theta=8)
+    moved.primitives[1]["M"] = moved.primitives[1]["M"].copy()
+    moved.primitives[1]["M"][0, 3] += 0.25
+    bent = scenes.instanced_spheres(grid=2, num_theta=8)
+    bent.meshes[0][0][3, 1, 2] += 0.125
+    for other in (moved, bent):
+        with pytest.raises(lmcu.LmcuError) as e:
+            lmcu.Scene(other, accel_blob=blob)
+        assert e.value.code == 1 and "other geometry" in str(e.value)
+    lmcu.Scene(scenes.instanced_spheres(grid=2, num_theta=8), accel_blob=blob).close()
+    # a blob whose checksum is right but whose indices point outside its own arrays (a writer of another version):
+    # every index is range-checked on the host before anything reaches the device
+    import struct
+    raw = bytearray(blob)
+    hdr = 8 + 6 * 4 + 3 * 8
+    struct.pack_into("<I", raw, hdr + 16, 0x7fffffff)       # WideNode 0: child_base
+    _rechecksum(raw, hdr)
+    with pytest.raises(lmcu.LmcuError) as e:
+        lmcu.Scene(None, accel_blob=bytes(raw))
+    assert e.value.code == 1 and "outside the node array" in str(e.value)
+
+
+def _rechecksum(raw, hdr):
+    """checksum64 of lmcu.cu over the payload, written back into the header (tests only)."""
+    import struct
+    M = (1 << 64) - 1
+    h = 1469598103934665603
+    body = memoryview(raw)[hdr:]
+    n8 = len(body) // 8
+    for (w,) in struct.iter_unpack("<Q", body[:n8 * 8]):
+        h = ((h ^ w) * 1099511628211) & M
+        h ^= h >> 29
+    for b in body[n8 * 8:]:
+        h = ((h ^ b) * 1099511628211) & M
+    struct.pack_into("<Q", raw, 8 + 6 * 4 + 8, h)
+
+
+def test_film_accumulates_in_fp64():
+    """the film used to be ONE fp32 sum per channel until the final rescale; past ~2^16 a float's ulp is 0.008
+    and small contributions vanish (a darkening bias the <= 256 spp parity tests never saw).  Now the fp32 film is folded
+    into FP64 sums every few dozen samples per pixel (k_film_fold): 65 536 spp in ONE call must equal the FP64 sum, on the
+    host, of 64 calls of 1024 spp over the same sample indices (same counter-RNG streams => same paths)."""
+    sb = scenes.cornell_spheres(8)
+    sc = lmcu.Scene(sb)
+    w, h, n, chunk = 32, 18, 65536, 1024
+    one, st = sc.render("pt", abi.render_params(w, h, spp=n, max_verts=6))
+    acc = np.zeros((h, w, 3))
+    for k in range(n // chunk):
+        f, _ = sc.render("pt", abi.render_params(w, h, spp=chunk, max_verts=6, sample_offset=k * chunk, rescale=0))
+        acc += f
+    acc /= n
+    sc.close()
+    assert st["processed"] == n
+    assert np.allclose(one, acc, rtol=2e-4, atol=1e-6), np.abs(one / np.maximum(acc, 1e-9) - 1).max()
+
+
+def test_pt_progress_hook():
+    """LmcuRenderParams::progress (the progress::update hook of the reference's schedulers, src/scheduler.cpp:45): called
+    between wavefront batches with non-decreasing path counts that never exceed the job."""
+    sb = scenes.cornell_spheres(8)
+    sc = lmcu.Scene(sb)
+    seen = []
+    cb = abi.PROGRESS_FN(lambda user, done, total, elapsed: seen.append((done, total, elapsed)))
+    w, h, spp = 640, 360, 256
+    sc.render("pt", abi.render_params(w, h, spp=spp, max_verts=8, progress=cb), download=False)
+    sc.close()
+    assert len(seen) >= 2
+    done = [d for d, _, _ in seen]
+    assert all(t == w * h * spp for _, t, _ in seen) and done == sorted(done) and done[-1] <= w * h * spp and done[-1] > 0
+    assert all(b[2] >= a[2] for a, b in zip(seen, seen[1:]))
+
+
+def test_accel_scalar_and_concurrent_batches():
+    """lmcu_accel_intersect1 (the scalar contract) answers exactly like the batch entry; batches launched back to back on
+    two CUDA streams do not share a work cursor."""
+    import torch
+    sb = scenes.cornell_spheres(16)
+    sc = lmcu.Scene(sb)
+    rays = scenes.random_rays(200000, np.array([-1, 0, -1.]), np.array([1, 2, 1.]), seed=3)
+    want = sc.intersect(rays)
+    for i in range(0, 2000, 7):
+        one = sc.intersect1(rays[i])
+        assert all(one[k] == want[k][i] for k in ("t", "u", "v", "primitive", "face"))
+    d_rays = torch.from_numpy(rays.view(np.float64).reshape(-1, 8)).cuda()
+    half = len(rays) // 2
+    outs = [torch.empty((half, 4), dtype=torch.float64, device="cuda") for _ in range(2)]
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    torch.cuda.synchronize()
+    for rep in range(3):
+        for k in range(2):
+            sc.intersect_device(d_rays[k * half:(k + 1) * half].data_ptr(), half, outs[k].data_ptr(), streams[k].cuda_stream)
+    torch.cuda.synchronize()
+    got = np.concatenate([o.cpu().numpy().view(scenes.HIT_DTYPE).reshape(-1) for o in outs])
+    assert all(np.array_equal(got[k], want[k][:2 * half]) for k in ("t", "u", "v", "primitive", "face"))
+    sc.close()
 
 
 def test_g1_edge_cases(reference):
@@ -154,7 +254,7 @@ def test_g1_edge_cases(reference):
     for name, (sb, rays, special) in edge_cases.cases().items():
         rs, sc = reference.RefScene(sb), lmcu.Scene(sb)
         hr, hg = rs.intersect(rays), sc.intersect(rays)
-        assert_hit_parity(hr, hg, max_special_frac=special)
+        assert_hit_parity(hr, hg, max_special=special)
         # idempotence: a hit found at t is found again with tmax = t (the upper bound is inclusive).  Checked against our
         # own first answer, not the reference's: for an axis-aligned triangle the reference's FP64 slab test and its
         # triangle test round the same t differently, so accel::sahbvh itself loses such a hit when tmax = t
@@ -232,14 +332,32 @@ def test_g3_pt_c2_vs_reference(reference, mode):
     """C2 scene (32 268 triangles, diffuse + glass spheres, area light) at reduced resolution."""
     sb = scenes.cornell_spheres(64)
     sc, rs = lmcu.Scene(sb), reference.RefScene(sb)
-    p = abi.render_params(240, 136, spp=256, max_verts=20, sampling_mode=mode)
+    # 256 spp as 4 independent estimates of 64 spp each (reference: 4 seeds; ours: 4 disjoint blocks of sample indices)
+    B, spp = 4, 64
+    R = np.stack([rs.render("pt", abi.render_params(240, 136, spp=spp, max_verts=20, sampling_mode=mode, seed=42 + b))[0] for b in range(B)])
+    G = np.stack([sc.render("pt", abi.render_params(240, 136, spp=spp, max_verts=20, sampling_mode=mode, sample_offset=b * spp))[0] for b in range(B)])
+    fr, fg = R.mean(axis=0), G.mean(axis=0)
+    assert_pt_parity(fr, fg, B * spp, rel_mean=0.01)
+    ratio = assert_pt_rmse(R, G, k=1.25)                 # per-channel RMSE <= 1.25 x the Monte-Carlo prediction
+    # calibration: a second set of reference runs with other seeds passes the same gates
+    R2 = np.stack([rs.render("pt", abi.render_params(240, 136, spp=spp, max_verts=20, sampling_mode=mode, seed=7 + b))[0] for b in range(B)])
+    assert_pt_parity(fr, R2.mean(axis=0), B * spp, rel_mean=0.01)
+    print("rmse / predicted: ours", ratio, "reference vs reference", assert_pt_rmse(R, R2, k=1.25))
+    rs.close(); sc.close()
+
+
+def test_g3_pt_high_spp_bias(reference):
+    """What FP32 shading + FP32 rays cost against the all-FP64 reference, asserted: at 8192 spp on a 96x54 film the Monte-Carlo
+    error of the difference of the image means is ~6e-4 relative (measured with the CPU build of the device code: -2e-4 +-
+    3e-4 at 32 768 spp), so the 0.3 % gate below is a gate on BIAS."""
+    sb = scenes.cornell_spheres(64)
+    sc, rs = lmcu.Scene(sb), reference.RefScene(sb)
+    p = abi.render_params(96, 54, spp=8192, max_verts=20)
     fr, _, _ = rs.render("pt", p)
     fg, _ = sc.render("pt", p)
-    assert_pt_parity(fr, fg, 256, rel_mean=0.01)
-    # calibration: two reference runs with different seeds pass the same gate
-    p2 = abi.render_params(240, 136, spp=256, max_verts=20, sampling_mode=mode, seed=7)
-    fr2, _, _ = rs.render("pt", p2)
-    assert_pt_parity(fr, fr2, 256, rel_mean=0.01)
+    c = assert_pt_parity(fr, fg, 8192, rel_mean=0.003)
+    print("relative difference of the image means at 8192 spp:", c["rel_mean"])
+    assert (c["rel_mean"] <= 0.003).all()
     rs.close(); sc.close()
 
 
@@ -247,10 +365,11 @@ def test_g3_pt_all_materials_env_light(reference):
     """C4-style materials (glossy / glass / mirror / diffuse) under light::envconst, instanced."""
     sb = scenes.instanced_spheres(grid=2, num_theta=24)
     sc, rs = lmcu.Scene(sb), reference.RefScene(sb)
-    p = abi.render_params(192, 108, spp=256, max_verts=20)
-    fr, _, _ = rs.render("pt", p)
-    fg, _ = sc.render("pt", p)
-    assert_pt_parity(fr, fg, 256, rel_mean=0.015)
+    B, spp = 4, 64
+    R = np.stack([rs.render("pt", abi.render_params(192, 108, spp=spp, max_verts=20, seed=42 + b))[0] for b in range(B)])
+    G = np.stack([sc.render("pt", abi.render_params(192, 108, spp=spp, max_verts=20, sample_offset=b * spp))[0] for b in range(B)])
+    assert_pt_parity(R.mean(axis=0), G.mean(axis=0), B * spp, rel_mean=0.015)
+    assert_pt_rmse(R, G, k=1.25)
     rs.close(); sc.close()
 
 

@@ -34,7 +34,7 @@ def test_accel_cuda_bvh_scalar_contract(plugin):
     hc = rc.intersect(rays)
     fc, _, _ = rc.render("raycast", abi.render_params(64, 36))     # reference renderer on top of the CUDA accel
     rc.close()
-    assert_hit_parity(hr, hc, max_special_frac=5e-3)
+    assert_hit_parity(hr, hc, max_special=0)
     tie = classify_hits(plugin_hits(plugin, sb, 64, 36, "accel::sahbvh"), plugin_hits(plugin, sb, 64, 36, "accel::cuda_bvh"))["bad_mask"].reshape(36, 64)
     assert np.abs(fc - fr)[~tie].max() <= 1e-12      # same FP64 shading code, same hits -> identical pixels
 
@@ -60,7 +60,7 @@ def test_renderer_raycast_cuda(plugin):
     assert c["other"] == 0, c
     rc.close()
     d = np.abs(fc - fr).max(axis=2)
-    assert (d > 1e-5).mean() < 3e-3                   # tie pixels only
+    assert (d > 1e-5).sum() <= 16                     # tie pixels only: 16 of the 20 736 pixel-centre rays meet a shared edge
     assert rmse(fc[d <= 1e-5], fr[d <= 1e-5]) <= 1e-6
 
 
@@ -222,8 +222,98 @@ def test_accel_cuda_bvh_batched_rays(plugin):
     rc.close()
     same_geom = (hits["t"][:3000] == hs["t"]) & (hits["face"][:3000] == hs["face"])
     assert same_geom.all()
-    hit_r, hit_c = hr["primitive"] >= 0, hits["primitive"] >= 0
-    assert (hit_r == hit_c).mean() > 0.999
-    both = hit_r & hit_c
-    agree = (hr["face"][both] == hits["face"][both]) & (hr["t"][both] == hits["t"][both])
-    assert agree.mean() > 0.995                          # the rest are exact ties on shared edges (see parity.py)
+    # G1 through the batched entry: the harness numbers scene nodes in creation order, the batched entry reports
+    # SceneNode::index like Accel::Hit -> map it with the scalar answers' mapping before classifying
+    node_to_desc = {}
+    for a, b in zip(hits["primitive"][:3000], hs["primitive"]):
+        node_to_desc[int(a)] = int(b)
+    mapped = hits.copy()
+    mapped["primitive"] = [node_to_desc.get(int(v), -1 if v < 0 else int(v)) for v in hits["primitive"]]
+    c = classify_hits(hr, mapped)
+    assert c["other"] == 0 and c["ties"] + c["ref_boundary_miss"] <= 31, {k: v for k, v in c.items() if k != "bad_mask"}
+    same = ~c["bad_mask"] & (hr["primitive"] >= 0)
+    assert all((hr[k][same] == mapped[k][same]).all() for k in ("t", "u", "v"))
+
+
+def _cache_stats(clear=False):
+    import ctypes as C
+    so = C.CDLL(PLUGIN + ".so")
+    hits, misses = C.c_longlong(), C.c_longlong()
+    so.lm_cuda_cache_stats(C.byref(hits), C.byref(misses), int(clear))
+    return hits.value, misses.value
+
+
+def test_device_scene_is_cached_across_renders(plugin, monkeypatch):
+    """renderer::*_cuda::render() exports, uploads and builds the scene once: a renderer asset re-created for every render
+    (lm::load<Renderer>, as the reference's examples do) finds the device scene of its predecessor as long as nothing the
+    export reads has changed; any change of the content (here: one transform) is a miss; "cache": false always rebuilds."""
+    _cache_stats(clear=True)
+    h0, m0 = _cache_stats()
+    sb = scenes.cornell_spheres(12)
+    rs = plugin.RefScene(sb)
+    p = abi.render_params(96, 54, spp=16, max_verts=8)
+    f1, _, _ = rs.render("renderer::pt_cuda", p)
+    f2, _, _ = rs.render("renderer::pt_cuda", p)
+    f3, _, _ = rs.render("renderer::raycast_cuda", abi.render_params(96, 54))
+    h1, m1 = _cache_stats()
+    assert (m1 - m0, h1 - h0) == (1, 2)
+    assert np.allclose(f1, f2, rtol=1e-4, atol=1e-5) and f3.max() > 0
+    monkeypatch.setenv("LMREF_EXTRA_PROPS", '{"cache": false}')
+    f4, _, _ = rs.render("renderer::pt_cuda", p)
+    monkeypatch.delenv("LMREF_EXTRA_PROPS")
+    assert _cache_stats() == (h1, m1) and np.allclose(f1, f4, rtol=1e-4, atol=1e-5)
+    rs.close()
+    sb2 = scenes.cornell_spheres(12)
+    sb2.primitives[-1]["M"] = sb2.primitives[-1]["M"].copy()
+    sb2.primitives[-1]["M"][1, 3] += 0.2                      # same meshes, one instance moved
+    rs = plugin.RefScene(sb2)
+    f5, _, _ = rs.render("renderer::pt_cuda", p)
+    h2, m2 = _cache_stats()
+    assert m2 == m1 + 1
+    assert np.abs(f5 - f1).max() > 1e-3                       # ... and the moved instance shows in the image
+    rs.close()
+
+
+def test_accel_cuda_bvh_scalar_intersect_rate(plugin):
+    """Accel::intersect one ray at a time must not crawl (it was 2 cudaMalloc + 2 cudaFree + 2 memcpy under
+    one mutex per ray).  Now: a pinned slot + stream per calling thread, one launch per ray, no lock.  Stated bar: 50 k
+    rays/s from one thread; the rate with every OpenMP thread of the reference calling at once is printed."""
+    sb = scenes.cornell_spheres(16)
+    rays = scenes.random_rays(60000, np.array([-1, 0, -1.]), np.array([1, 2, 1.]), seed=11)
+    threads = plugin.init(0)
+    rs = plugin.RefScene(sb)
+    hr = rs.intersect(rays)
+    rs.close()
+    rc = plugin.RefScene(sb, accel="accel::cuda_bvh")
+    rc.intersect(rays[:2000])
+    hc = rc.intersect(rays)
+    all_rate = len(rays) / rc.last_seconds
+    plugin.init(1)
+    rc.intersect(rays[:2000])
+    rc.intersect(rays[:20000])
+    one_rate = 20000 / rc.last_seconds
+    plugin.init(0)
+    rc.close()
+    assert_hit_parity(hr, hc)
+    print("scalar Accel::intersect on accel::cuda_bvh: %.0f rays/s from 1 thread, %.0f rays/s from %d threads" % (one_rate, all_rate, threads))
+    assert one_rate >= 50e3
+
+
+def test_renderer_ao_cuda_leaves_missed_pixels_untouched(plugin, monkeypatch):
+    """renderer::ao never clears its film and returns early on a miss (functest/renderer_ao.cpp:32-34): a pixel whose primary
+    ray leaves the scene keeps what the film held.  Same through film::bitmap and film::cuda."""
+    sb = scenes.instanced_spheres(grid=2, num_theta=12)        # spheres over a ground quad, sky around them
+    rs = plugin.RefScene(sb)
+    p = abi.render_params(128, 72, spp=16)
+    monkeypatch.setenv("LMREF_FILM_PREFILL", "0.375")
+    fr, _, _ = rs.render("ao", p)
+    out = {}
+    for film in ("film::bitmap", "film::cuda"):
+        monkeypatch.setenv("LMREF_FILM", film)
+        out[film], _, _ = rs.render("renderer::ao_cuda", p)
+    rs.close()
+    missed = (fr == 0.375).all(axis=2)
+    assert 0.02 < missed.mean() < 0.9
+    for film, fc in out.items():
+        assert ((fc == 0.375).all(axis=2) == missed).mean() > 0.999, film      # silhouette pixels may tie
+        assert_pt_parity(np.where(missed[..., None], 0.0, fr), np.where(missed[..., None], 0.0, fc), 16, rel_mean=0.02)

@@ -47,7 +47,8 @@ def test_port_hits_vs_golden(port, name, make):
     g = np.zeros(len(h), dtype=scenes.HIT_DTYPE)
     g["t"], g["u"], g["v"] = GOLDEN[name + "_t"], GOLDEN[name + "_u"], GOLDEN[name + "_v"]
     g["primitive"], g["face"] = GOLDEN[name + "_prim"], GOLDEN[name + "_face"]
-    c = assert_hit_parity(g, h, max_special_frac=3e-3)
+    # ties only (two triangles at bit-equal t; the winner depends on the reference's build order): measured 8 / 8 / 9 / 0
+    c = assert_hit_parity(g, h, max_special={"cornell": 8, "cornell_fp64": 8, "spheres12": 9, "heightfield48": 0}[name])
     assert c["ref_boundary_miss"] == 0          # same box test as the reference: misses the same boundary hits
     assert (g["t"] == h["t"]).all()             # t is bit-identical for every ray, ties included
     ps.close()

@@ -44,52 +44,97 @@ def _worker(rank, world, port, total_spp, npix, out):
     dist.destroy_process_group()
 
 
-def _peer_worker(rank, world, port, total_spp, npix, tmp, out):
-    """PeerFilmReducer orchestration with files standing in for CUDA IPC mappings."""
+def _peer_worker(rank, world, port, total_spp, npix, tmp, out, mode):
+    """PeerFilmReducer orchestration with files standing in for CUDA IPC mappings: a "pointer" is the path of a rank's
+    film file, a peer store is a read-modify-write of that file."""
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     film = torch.zeros(npix * 3)
-    opened = []
+    opened, closed = [], []
+    mine = os.path.join(tmp, "film%d.pt" % rank)
 
-    def film_handle():
-        return os.path.join(tmp, "film%d.pt" % rank).encode()
+    class Ops:
+        @staticmethod
+        def film_handle():
+            return mine.encode()
 
-    def sync():
-        torch.save(film, film_handle().decode())        # "render complete": the peer film becomes readable
+        @staticmethod
+        def film_ptr():
+            return mine, npix * 3
 
-    def open_handle(h):
-        opened.append(h)
-        return h
+        @staticmethod
+        def sync():
+            torch.save(film, mine)                      # "render complete": the film becomes readable by the peers
 
-    def reduce(ptrs, scale):
-        acc = film.clone()
-        for h in ptrs:
-            acc += torch.load(h.decode())
-        film.copy_(acc * scale)
+        @staticmethod
+        def open_handle(h):
+            opened.append(h)
+            return h.decode()
 
-    red = D.PeerFilmReducer(dist, rank, world, film_handle, open_handle, reduce, sync)
+        @staticmethod
+        def close_handle(ptr):
+            closed.append(ptr)
+
+        @staticmethod
+        def reduce_root(ptrs, scale):
+            acc = film.clone()
+            for path in ptrs:
+                acc += torch.load(path)
+            film.copy_(acc * scale)
+
+        @staticmethod
+        def reduce_slice(ptrs, out_ptr, begin, end, scale):
+            assert begin % 4 == 0 and ptrs[rank] == mine
+            acc = torch.zeros(end - begin)
+            for path in ptrs:
+                acc += torch.load(path)[begin:end]
+            torch.save(acc * scale, os.path.join(tmp, "slice%d.pt" % rank))   # the peer store, applied once all have read
+
+    def any_changed(flag):
+        t = torch.tensor([1 if flag else 0])
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return bool(t.item())
+
+    red = D.PeerFilmReducer(dist, rank, world, Ops, any_changed, mode=mode)
     for step in range(2):                                # second step must reuse the cached mappings
         offset, count = D.sample_block(total_spp, rank, world)
         film.zero_()
         for i in range(offset, offset + count):
             film += _fake_sample_image(i, npix)
         red(total_spp)
+        if mode == "slice" and rank == 0:                # assemble the stores into the root's film
+            for r, (b, e) in enumerate(D.film_slices(npix * 3, world)):
+                film[b:e] = torch.load(os.path.join(tmp, "slice%d.pt" % r))
+        dist.barrier()
+    assert red.exchanges == 1
+    assert len(opened) == (world - 1 if (mode == "slice" or rank == 0) else 0)
+    red.close()
+    assert len(closed) == len(opened)
     if rank == 0:
-        assert len(opened) == world - 1
         torch.save(film, out)
     dist.barrier()
     dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("mode", ["slice", "root"])
 @pytest.mark.parametrize("world,total_spp", [(2, 8), (3, 7)])
-def test_peer_film_reducer(tmp_path, world, total_spp):
-    npix = 12
+def test_peer_film_reducer(tmp_path, world, total_spp, mode):
+    npix = 13                                            # 39 floats: ragged against the 4-float slices
     out = str(tmp_path / "film.pt")
-    mp.spawn(_peer_worker, args=(world, _free_port(), total_spp, npix, str(tmp_path), out), nprocs=world, join=True)
+    mp.spawn(_peer_worker, args=(world, _free_port(), total_spp, npix, str(tmp_path), out, mode), nprocs=world, join=True)
     got = torch.load(out)
     want = sum(_fake_sample_image(i, npix) for i in range(total_spp)) / total_spp
     assert torch.allclose(got, want, atol=1e-6)
+
+
+def test_film_slices_tile_the_film():
+    for n in (3, 4, 39, 1920 * 1080 * 3, 37 * 23 * 3):
+        for world in (1, 2, 3, 8):
+            sl = D.film_slices(n, world)
+            assert sl[0][0] == 0 and sl[-1][1] == n
+            for (b0, e0), (b1, _) in zip(sl, sl[1:]):
+                assert e0 == b1 and b1 % 4 == 0 and b0 <= e0
 
 
 @pytest.mark.parametrize("world,total_spp", [(2, 8), (3, 7)])
