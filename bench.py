@@ -105,16 +105,17 @@ def reference_rate(spp, steps, warmup, rs=None):
     own = rs is None
     if own:
         rs = ref.RefScene(scenes.cornell_spheres(64))
-    p = abi.render_params(W, H, spp=spp, max_verts=MAX_VERTS, seed=SEED)
-    times, film = [], None
+    times, films = [], []
     for i in range(warmup + steps):
-        film, elapsed, _ = rs.render("pt", p)
+        # a different seed per render: the films are independent estimates (used by parity_c2), the rate does not care
+        film, elapsed, _ = rs.render("pt", abi.render_params(W, H, spp=spp, max_verts=MAX_VERTS, seed=SEED + i))
+        films = (films + [film])[-2:]
         if i >= warmup:
             times.append(elapsed)
     if own:
         rs.close()
     t = sum(times) / len(times)
-    return W * H * spp / t / 1e6, t, threads, film
+    return W * H * spp / t / 1e6, t, threads, films
 
 
 def run_reference(args):
@@ -563,21 +564,32 @@ def run_ours(args):
                         plugin["film_vs_ctypes_max_abs_err"] = float(np.abs(plugin_film - host_film).max() / scale)
                     except Exception as ex:
                         plugin = {"failed": str(ex)}
-                v, t, threads, cpu_film = reference_rate(REF_SPP_PER_STEP, 1, 1, rs)
+                v, t, threads, cpu_films = reference_rate(REF_SPP_PER_STEP, 1, 1, rs)
                 cpu = {"value": v, "unit": "Mpaths/s", "cores": threads, "kind": "reference",
                        "sample": "%dx%d @ %d spp (full C2 image, bounded spp), 1 warm-up + 1 timed render" % (W, H, REF_SPP_PER_STEP)}
                 if rs is not None:
                     rs.close()
-                # G3 at the FULL C2 size: the GPU film of the e2e leg against the CPU film of the baseline leg
+                # G3 at the FULL C2 size: the GPU film of the e2e leg against the two independent 16-spp CPU films of the
+                # baseline leg (warm-up + timed render, different seeds) A, B.  Mean gate on (A+B)/2; RMSE gate with the noise
+                # measured on the spot: rmse((A+B)/2, GPU)^2 must not exceed k^2 x [mean((A-B)^2)/4 + the GPU film's own share],
+                # k = 1.25 (tests/parity.py assert_pt_rmse).  The 8x8-block z-test of the equal-spp tests is NOT applied here: a
+                # 16-spp image's noise is too skewed for it (reference 16 spp against reference 1024 spp fails it too: 0.9 % of
+                # the blocks beyond |z| = 4, measured).
                 try:
-                    from parity import assert_pt_parity, rmse
-                    parity_c2 = {"gpu_spp": spp * world, "cpu_spp": REF_SPP_PER_STEP, "rmse": rmse(cpu_film, host_film),
-                                 "gate": "image means within max(1 %, 4.5 SE); fraction of 8x8 blocks of the difference with |z| > 4 <= 2e-3"}
-                    try:
-                        r = assert_pt_parity(cpu_film, host_film, REF_SPP_PER_STEP, rel_mean=0.01)
-                        parity_c2.update({"pass": True, "rel_mean": [float(x) for x in r["rel_mean"]], "z_frac": r["z_frac"]})
-                    except AssertionError as ex:
-                        parity_c2.update({"pass": False, "why": str(ex)[:300]})
+                    A, B = [np.asarray(f, dtype=np.float64) for f in cpu_films]
+                    M, G = 0.5 * (A + B), host_film.astype(np.float64)
+                    cpu_spp, gpu_spp = 2 * REF_SPP_PER_STEP, spp * world
+                    noise2 = ((A - B) ** 2).mean(axis=(0, 1)) / 4.0
+                    pred = np.sqrt(noise2 * (1.0 + cpu_spp / gpu_spp))
+                    got = np.sqrt(((M - G) ** 2).mean(axis=(0, 1)))
+                    mr, mg = M.mean(axis=(0, 1)), G.mean(axis=(0, 1))
+                    se = (G - M).reshape(-1, 3).std(axis=0) / np.sqrt(W * H)
+                    tol = np.maximum(0.01 * mr, 4.5 * se)
+                    parity_c2 = {"gpu_spp": gpu_spp, "cpu_spp": cpu_spp, "rmse": [float(x) for x in got],
+                                 "rmse_predicted_from_noise": [float(x) for x in pred], "rmse_over_predicted": [float(x) for x in got / pred],
+                                 "rel_mean": [float(x) for x in np.abs(mg - mr) / mr],
+                                 "gate": "per-channel rmse <= 1.25 x Monte-Carlo prediction; image means within max(1 %, 4.5 SE)",
+                                 "pass": bool((got <= 1.25 * pred).all() and (np.abs(mg - mr) <= tol).all())}
                 except Exception as ex:
                     parity_c2 = {"failed": str(ex)}
         except Exception as ex:  # the baseline must never take the bench line down

@@ -230,7 +230,9 @@ typedef struct LmcuBuildStats {
     int64_t triangle_bytes;
     int32_t triangles_fp32;                  /* 1 if every world-space vertex is float-representable (48 B triangles) */
     int32_t pad_;
-    double sah_cost;                         /* SAH cost of the wide tree */
+    double sah_cost;                         /* surface-area cost of the wide tree: expected wide-node visits + triangle tests
+                                                of a random line through the scene box (sum of box area / root box area
+                                                over nodes, plus the same over leaf slots times their triangle count) */
 } LmcuBuildStats;
 
 typedef struct LmcuScene LmcuScene;

@@ -149,6 +149,30 @@ __global__ void k_collapse(CollapseCtx c, const CollapseItem* queue, uint32_t co
     if (i < count) collapse_body(c, queue[i]);
 }
 
+// Surface-area cost of the finished wide tree: the expected number of wide-node visits and of triangle tests for a random
+// line through the root box (each node / leaf slot weighted by its box area over the root's).  out[0] += area of this
+// node's box (union of its dequantised child boxes), out[1] += sum over leaf slots of area * triangle count, out[2] = root area.
+__global__ void k_sah_cost(const WideNode* __restrict__ nodes, uint32_t num_nodes, double* out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    double a_node = 0.0, a_leaf = 0.0;
+    if (i < num_nodes) {
+        const WideNode n = nodes[i];
+        const float sx = __uint_as_float((uint32_t)n.ex << 23), sy = __uint_as_float((uint32_t)n.ey << 23), sz = __uint_as_float((uint32_t)n.ez << 23);
+        float lo[3] = { 3e38f, 3e38f, 3e38f }, hi[3] = { -3e38f, -3e38f, -3e38f };
+        for (int s = 0; s < 8; s++) {
+            if (n.meta[s] == 0) continue;
+            const float l[3] = { n.px + n.qlox[s] * sx, n.py + n.qloy[s] * sy, n.pz + n.qloz[s] * sz };
+            const float h[3] = { n.px + n.qhix[s] * sx, n.py + n.qhiy[s] * sy, n.pz + n.qhiz[s] * sz };
+            for (int a = 0; a < 3; a++) { lo[a] = fminf(lo[a], l[a]); hi[a] = fmaxf(hi[a], h[a]); }
+            if (!((n.imask >> s) & 1u)) a_leaf += (double)box_area(l, h) * (double)__popc((uint32_t)n.meta[s] >> 5);
+        }
+        a_node = lo[0] <= hi[0] ? (double)box_area(lo, hi) : 0.0;
+        if (i == 0) out[2] = a_node;
+    }
+    for (int o = 16; o > 0; o >>= 1) { a_node += __shfl_xor_sync(0xffffffffu, a_node, o); a_leaf += __shfl_xor_sync(0xffffffffu, a_leaf, o); }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(out, a_node); atomicAdd(out + 1, a_leaf); }
+}
+
 __global__ void k_emit(const uint32_t* tri_order, uint32_t nt, const PrimDev* prims, int num_prims, const double* wp,
                        const double* mesh_p, const double* mesh_n, TriF32* t32, TriF64* t64, TriShade* shade,
                        const float* mesh_t, TriUV* uv) {
@@ -930,6 +954,15 @@ int lmcu_accel_build(LmcuScene* s, const LmcuBuildOptions* opts, LmcuBuildStats*
                                               s->t32.p, s->t64.p, s->shade.p, s->mesh_t.p, s->uv.p);
     CU(cudaGetLastError());
     CU(cudaEventRecord(s->ev1, st));
+    double h_cost[3] = { 0, 0, 0 };
+    if (stats) {
+        DBuf<double> cost;
+        CU(cost.alloc(3));
+        CU(cudaMemsetAsync(cost.p, 0, 3 * sizeof(double), st));
+        k_sah_cost<<<grid_for(s->nodes.n, 256), 256, 0, st>>>(s->nodes.p, (uint32_t)s->nodes.n, cost.p);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(h_cost, cost.p, sizeof(h_cost), cudaMemcpyDeviceToHost, st));
+    }
     CU(cudaStreamSynchronize(st));
     s->built = true;
     if (stats) {
@@ -941,7 +974,8 @@ int lmcu_accel_build(LmcuScene* s, const LmcuBuildOptions* opts, LmcuBuildStats*
         stats->node_bytes = (int64_t)(s->nodes.n * sizeof(WideNode));
         stats->triangle_bytes = (int64_t)nt * (int64_t)(s->fp32 ? sizeof(TriF32) : sizeof(TriF64));
         stats->triangles_fp32 = s->fp32 ? 1 : 0;
-        stats->sah_cost = 0.0;
+        // expected wide-node visits + triangle tests of a random line through the scene box
+        stats->sah_cost = h_cost[2] > 0 ? (h_cost[0] + h_cost[1]) / h_cost[2] : 0.0;
     }
     return LMCU_OK;
 }

@@ -635,9 +635,8 @@ public:
 
     // Component::save / load (include/lm/component.h:210-236), the counterpart of accel::sahbvh archiving nodes_, trs_,
     // indices_ (accel_sahbvh.cpp:122-124): the device BVH travels as the blob of lmcu_accel_save(), so a loaded state
-    // answers intersect() without rebuilding.  NOTE: this image has no cereal (oracle/shim/cereal provides no-op archives),
-    // so these two functions are compiled but never exercised here; the blob itself is round-tripped through the C ABI
-    // in tests/test_gpu_parity.py::test_accel_save_load_round_trip.
+    // answers intersect() without rebuilding (tests/test_gpu_plugin.py::test_save_state_round_trip_with_cuda_components
+    // runs lm::save_state_to_file / lm::reset / lm::load_state_from_file over it, func_serial_consistency style).
     virtual void save(OutputArchive& ar) override {
         std::vector<unsigned char> blob;
         std::vector<int> keys;
@@ -734,6 +733,9 @@ private:
     }
 
 public:
+    virtual void save(OutputArchive& ar) override { ar(w_, h_, rgb_); }                       // film::bitmap: film_bitmap.cpp:132-134
+    virtual void load(InputArchive& ar) override { ar(w_, h_, rgb_); dirty_ = true; }
+
     virtual void construct(const Json& prop) override {
         w_ = json::value<int>(prop, "w");
         h_ = json::value<int>(prop, "h");
@@ -831,6 +833,9 @@ public:
     }
 
 protected:
+    // weak references travel as locators and are re-pointed after the whole tree is loaded (include/lm/serial.h:238-300)
+    template <typename Archive> void serialize_base(Archive& ar) { ar(scene_, film_, device_, cache_); }
+
     void construct_base(const Json& prop) {
         scene_ = json::comp_ref<Scene>(prop, "scene");
         film_ = json::comp_ref<Film>(prop, "output");
@@ -888,6 +893,8 @@ private:
     std::optional<Vec3> color_;
 
 public:
+    LM_SERIALIZE_IMPL(ar) { serialize_base(ar); ar(bg_color_, use_constant_color_, visualize_normal_, color_); }   // renderer_raycast.cpp:29-31
+
     virtual void construct(const Json& prop) override {
         construct_base(prop);
         bg_color_ = json::value(prop, "bg_color", Vec3(0_f));
@@ -925,6 +932,8 @@ private:
     int rng_seed_ = 42;
 
 public:
+    LM_SERIALIZE_IMPL(ar) { serialize_base(ar); ar(spp_, rng_seed_); }
+
     virtual void construct(const Json& prop) override {
         construct_base(prop);
         spp_ = json::value<long long>(prop, "spp");
@@ -983,6 +992,11 @@ private:
     int wavefronts_ = 0;                        // LmcuRenderParams::wavefronts (0 = library default)
 
 public:
+    LM_SERIALIZE_IMPL(ar) {                                                                    // renderer_pt.cpp:36-38
+        serialize_base(ar);
+        ar(max_verts_, seed_, sampling_mode_, primary_mode_, scheduler_, spp_, num_samples_, samples_per_iter_, render_time_, devices_, wavefronts_);
+    }
+
     virtual void construct(const Json& prop) override {
         construct_base(prop);
         max_verts_ = json::value<int>(prop, "max_verts");

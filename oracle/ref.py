@@ -70,6 +70,10 @@ class RefScene:
                                   C.byref(elapsed), C.byref(processed)))
         return film, elapsed.value, processed.value
 
+    def save_reset_load(self, path):
+        """lm::save_state_to_file(path); lm::reset(); lm::load_state_from_file(path) — func_serial_consistency.py:79-83."""
+        _check(lib().lmref_save_reset_load(self._h, str(path).encode()))
+
     def loc(self):
         """Locator of the lm::Scene asset inside the reference's asset tree."""
         lib().lmref_scene_loc.restype = C.c_char_p

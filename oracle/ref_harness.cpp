@@ -30,6 +30,9 @@ private:
     std::vector<Vec2> ts_;
     int nf_ = 0;
 public:
+    LM_SERIALIZE_IMPL(ar) {                    // like mesh::raw (src/mesh/mesh_raw.cpp:45-47): the state round-trips
+        ar(ps_, ns_, ts_, nf_);
+    }
     virtual void construct(const Json& prop) override {
         nf_ = json::value<int>(prop, "num_faces");
         const auto* p = reinterpret_cast<const double*>(json::value<std::uintptr_t>(prop, "p"));
@@ -234,6 +237,20 @@ void lmref_scene_destroy(void* s) { delete static_cast<RefScene*>(s); }
 
 // Locator of the lm::Scene asset (for hooks that look the scene up themselves, e.g. the plugin's probe test)
 const char* lmref_scene_loc(void* s) { return static_cast<RefScene*>(s)->scene_loc.c_str(); }
+
+// The sequence of functest/func_serial_consistency.py:79-83: lm::save_state_to_file, lm::reset, lm::load_state_from_file.
+// The handle then re-resolves its scene by locator (every asset was re-created by the archive).
+int lmref_save_reset_load(void* s, const char* path) {
+    return guarded([&] {
+        auto* rs = static_cast<RefScene*>(s);
+        lm::save_state_to_file(path);
+        lm::reset();
+        rs->scene = nullptr;
+        lm::load_state_from_file(path);
+        rs->scene = lm::comp::get<Scene>(rs->scene_loc);
+        if (!rs->scene) LM_THROW_EXCEPTION(Error::IOError, "scene missing after load_state_from_file");
+    });
+}
 
 // rays[i] -> Accel::intersect(ray, tmin, tmax) (include/lm/accel.h:70) under OpenMP.
 int lmref_accel_intersect(void* s, const LmcuRay* rays, int64_t n, LmcuHit* hits, double* seconds) {

@@ -72,6 +72,77 @@ static int intersect_t(const SimScene& s, const LmcuRay* rays, long long n, Lmcu
 }
 
 
+// EXPERIMENT (builder quality probe, HOSTSIM_BUILDER=sah): a top-down binned-SAH binary tree in the BinNode format of
+// build.cuh, to measure what tree quality is worth in node visits per ray before writing a device builder for it.
+namespace {
+struct SahCtx {
+    std::vector<BinNode>* bin; std::vector<uint32_t>* perm; const float* lo; const float* hi; const double* centre; uint32_t n; uint32_t next = 0;
+};
+uint32_t sah_build(SahCtx& c, uint32_t b, uint32_t e) {
+    if (e - b == 1) {
+        const uint32_t id = c.n - 1 + b, g = (*c.perm)[b];
+        BinNode leaf;
+        for (int a = 0; a < 3; a++) { leaf.lo[a] = c.lo[(size_t)g * 3 + a]; leaf.hi[a] = c.hi[(size_t)g * 3 + a]; }
+        leaf.left = leaf.right = 0xffffffffu; leaf.first = b; leaf.count = 1;
+        (*c.bin)[id] = leaf;
+        return id;
+    }
+    const uint32_t id = c.next++;
+    double cl[3] = { 1e300, 1e300, 1e300 }, ch[3] = { -1e300, -1e300, -1e300 };
+    for (uint32_t i = b; i < e; i++) for (int a = 0; a < 3; a++) {
+        const double v = c.centre[(size_t)(*c.perm)[i] * 3 + a];
+        cl[a] = std::min(cl[a], v); ch[a] = std::max(ch[a], v);
+    }
+    const int NB = 16;
+    int best_axis = -1, best_bin = -1;
+    double best_cost = 1e300;
+    for (int a = 0; a < 3; a++) {
+        if (!(ch[a] > cl[a])) continue;
+        float blo[NB][3], bhi[NB][3]; uint32_t cnt[NB];
+        for (int k = 0; k < NB; k++) { cnt[k] = 0; for (int d = 0; d < 3; d++) { blo[k][d] = 3e38f; bhi[k][d] = -3e38f; } }
+        const double sc = NB / (ch[a] - cl[a]);
+        for (uint32_t i = b; i < e; i++) {
+            const uint32_t g = (*c.perm)[i];
+            int k = (int)((c.centre[(size_t)g * 3 + a] - cl[a]) * sc); k = k < 0 ? 0 : (k > NB - 1 ? NB - 1 : k);
+            cnt[k]++;
+            for (int d = 0; d < 3; d++) { blo[k][d] = std::min(blo[k][d], c.lo[(size_t)g * 3 + d]); bhi[k][d] = std::max(bhi[k][d], c.hi[(size_t)g * 3 + d]); }
+        }
+        float rlo[NB][3], rhi[NB][3]; uint32_t rc[NB];
+        float l[3] = { 3e38f, 3e38f, 3e38f }, h[3] = { -3e38f, -3e38f, -3e38f }; uint32_t n = 0;
+        for (int k = NB - 1; k >= 1; k--) {
+            for (int d = 0; d < 3; d++) { l[d] = std::min(l[d], blo[k][d]); h[d] = std::max(h[d], bhi[k][d]); }
+            n += cnt[k];
+            for (int d = 0; d < 3; d++) { rlo[k][d] = l[d]; rhi[k][d] = h[d]; } rc[k] = n;
+        }
+        for (int d = 0; d < 3; d++) { l[d] = 3e38f; h[d] = -3e38f; } n = 0;
+        for (int k = 0; k < NB - 1; k++) {
+            for (int d = 0; d < 3; d++) { l[d] = std::min(l[d], blo[k][d]); h[d] = std::max(h[d], bhi[k][d]); }
+            n += cnt[k];
+            if (n == 0 || rc[k + 1] == 0) continue;
+            const double cost = (double)box_area(l, h) * n + (double)box_area(rlo[k + 1], rhi[k + 1]) * rc[k + 1];
+            if (cost < best_cost) { best_cost = cost; best_axis = a; best_bin = k; }
+        }
+    }
+    uint32_t mid;
+    if (best_axis < 0) mid = (b + e) / 2;
+    else {
+        const double sc = NB / (ch[best_axis] - cl[best_axis]);
+        auto it = std::partition(c.perm->begin() + b, c.perm->begin() + e, [&](uint32_t g) {
+            int k = (int)((c.centre[(size_t)g * 3 + best_axis] - cl[best_axis]) * sc); k = k < 0 ? 0 : (k > NB - 1 ? NB - 1 : k);
+            return k <= best_bin;
+        });
+        mid = (uint32_t)(it - c.perm->begin());
+        if (mid == b || mid == e) mid = (b + e) / 2;
+    }
+    const uint32_t L = sah_build(c, b, mid), R = sah_build(c, mid, e);
+    BinNode nd;
+    for (int a = 0; a < 3; a++) { nd.lo[a] = fminf((*c.bin)[L].lo[a], (*c.bin)[R].lo[a]); nd.hi[a] = fmaxf((*c.bin)[L].hi[a], (*c.bin)[R].hi[a]); }
+    nd.left = L; nd.right = R; nd.first = b; nd.count = e - b;
+    (*c.bin)[id] = nd;
+    return id;
+}
+}
+
 extern "C" {
 
 const char* hostsim_last_error() { return g_err.c_str(); }
@@ -114,6 +185,13 @@ int hostsim_scene_create(const LmcuSceneDesc* d, int max_leaf, void** out, long 
     std::vector<BinNode> bin((size_t)2 * nt);
     std::vector<uint32_t> parent((size_t)2 * nt, 0xffffffffu), arrive(nt, 0);
     for (int i = 0; i + 1 < (int)nt; i++) hierarchy_body(i, keys_sorted.data(), (int)nt, bin.data(), parent.data());
+    const char* builder = getenv("HOSTSIM_BUILDER");
+    if (builder && std::string(builder) == "sah" && nt > 1) {
+        std::iota(vals_sorted.begin(), vals_sorted.end(), 0u);
+        SahCtx c{ &bin, &vals_sorted, tri_lo.data(), tri_hi.data(), centre.data(), nt };
+        sah_build(c, 0, nt);
+    }
+    else
     // k_fit (sequential stand-in for the atomic-arrival climb)
     for (int j = 0; j < (int)nt; j++) {
         const uint32_t g = vals_sorted[j];

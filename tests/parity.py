@@ -46,7 +46,7 @@ def assert_hit_parity(ref_hits, hits, max_special=None):
     return c
 
 
-def assert_pt_parity(ref_film, film, spp, rel_mean=0.01, z_frac=2e-3):
+def assert_pt_parity(ref_film, film, spp, rel_mean=0.01, z_frac=2e-3, block=8):
     """G3: statistical image parity at equal spp (the RNG streams differ by design).
 
     - difference of the image means per channel <= max(rel_mean * mean, 4.5 standard errors of that difference):
@@ -67,13 +67,13 @@ def assert_pt_parity(ref_film, film, spp, rel_mean=0.01, z_frac=2e-3):
     assert (np.abs(mg - mr) <= tol).all(), "image means differ: ref %s ours %s (tolerance %s)" % (mr, mg, tol)
     d = (film - ref_film).mean(axis=2)
     h, w = d.shape
-    hb, wb = h // 8, w // 8
-    blocks = d[:hb * 8, :wb * 8].reshape(hb, 8, wb, 8)
+    hb, wb = h // block, w // block
+    blocks = d[:hb * block, :wb * block].reshape(hb, block, wb, block)
     bm = blocks.mean(axis=(1, 3))
-    bs = blocks.std(axis=(1, 3)) / np.sqrt(64) + 1e-9
+    bs = blocks.std(axis=(1, 3)) / np.sqrt(block * block) + 1e-9
     z = bm / bs
     frac = float((np.abs(z) > 4).mean())
-    assert frac <= max(z_frac, 2.0 / z.size), "structured difference: %.4f of 8x8 blocks have |z|>4" % frac
+    assert frac <= max(z_frac, 2.0 / z.size), "structured difference: %.4f of %dx%d blocks have |z|>4" % (frac, block, block)
     return {"rel_mean": rel, "z_frac": frac}
 
 

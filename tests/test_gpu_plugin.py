@@ -224,11 +224,14 @@ def test_accel_cuda_bvh_batched_rays(plugin):
     assert same_geom.all()
     # G1 through the batched entry: the harness numbers scene nodes in creation order, the batched entry reports
     # SceneNode::index like Accel::Hit -> map it with the scalar answers' mapping before classifying
+    geom = (hits["primitive"] >= 0) & (hr["primitive"] >= 0) & (hits["t"] == hr["t"]) & (hits["face"] == hr["face"])
     node_to_desc = {}
-    for a, b in zip(hits["primitive"][:3000], hs["primitive"]):
-        node_to_desc[int(a)] = int(b)
+    for node in np.unique(hits["primitive"][geom]):
+        vals, counts = np.unique(hr["primitive"][geom & (hits["primitive"] == node)], return_counts=True)
+        node_to_desc[int(node)] = int(vals[np.argmax(counts)])
+    assert len(set(node_to_desc.values())) == len(node_to_desc)         # one scene node per description primitive
     mapped = hits.copy()
-    mapped["primitive"] = [node_to_desc.get(int(v), -1 if v < 0 else int(v)) for v in hits["primitive"]]
+    mapped["primitive"] = [node_to_desc.get(int(v), -1) for v in hits["primitive"]]
     c = classify_hits(hr, mapped)
     assert c["other"] == 0 and c["ties"] + c["ref_boundary_miss"] <= 31, {k: v for k, v in c.items() if k != "bad_mask"}
     same = ~c["bad_mask"] & (hr["primitive"] >= 0)
@@ -302,18 +305,46 @@ def test_accel_cuda_bvh_scalar_intersect_rate(plugin):
 def test_renderer_ao_cuda_leaves_missed_pixels_untouched(plugin, monkeypatch):
     """renderer::ao never clears its film and returns early on a miss (functest/renderer_ao.cpp:32-34): a pixel whose primary
     ray leaves the scene keeps what the film held.  Same through film::bitmap and film::cuda."""
-    sb = scenes.instanced_spheres(grid=2, num_theta=12)        # spheres over a ground quad, sky around them
+    sb = scenes.cornell_spheres(12)              # no environment light: the 16:9 frame is wider than the box, the margins miss
     rs = plugin.RefScene(sb)
     p = abi.render_params(128, 72, spp=16)
-    monkeypatch.setenv("LMREF_FILM_PREFILL", "0.375")
+    monkeypatch.setenv("LMREF_FILM_PREFILL", "0.3")            # not a multiple of 1/16: no AO value of a 16-spp pixel equals it
     fr, _, _ = rs.render("ao", p)
     out = {}
     for film in ("film::bitmap", "film::cuda"):
         monkeypatch.setenv("LMREF_FILM", film)
         out[film], _, _ = rs.render("renderer::ao_cuda", p)
     rs.close()
-    missed = (fr == 0.375).all(axis=2)
+    missed = (fr == 0.3).all(axis=2)
     assert 0.02 < missed.mean() < 0.9
     for film, fc in out.items():
-        assert ((fc == 0.375).all(axis=2) == missed).mean() > 0.999, film      # silhouette pixels may tie
+        assert ((fc == np.float32(0.3)).all(axis=2) == missed).sum() >= missed.size - 4, film      # silhouette pixels may tie
         assert_pt_parity(np.where(missed[..., None], 0.0, fr), np.where(missed[..., None], 0.0, fc), 16, rel_mean=0.02)
+
+
+def test_save_state_round_trip_with_cuda_components(plugin, tmp_path, monkeypatch):
+    """SURVEY.md 8f N4, functest/func_serial_consistency.py:52-100 with the plugin's components in the asset tree:
+    accel::cuda_bvh (Component::save = the blob of lmcu_accel_save + the transform table), film::cuda and
+    renderer::raycast_cuda go through lm::save_state_to_file, lm::reset, lm::load_state_from_file; the restored accel
+    answers without a rebuild, raycast before == after (RMSE 0)."""
+    sb = scenes.instanced_spheres(grid=2, num_theta=12)
+    rc = plugin.RefScene(sb, accel="accel::cuda_bvh")
+    rays = np.concatenate([scenes.camera_rays(sb.camera, 96, 54), scenes.random_rays(3000, np.array([-2, 0, -2.]), np.array([2, 3, 2.]))])
+    p = abi.render_params(160, 90)
+    monkeypatch.setenv("LMREF_FILM", "film::cuda")
+    hits_before = rc.intersect(rays)
+    ref_before, _, _ = rc.render("raycast", p)                       # the reference's renderer over the CUDA accel (scalar contract)
+    img_before, _, _ = rc.render("renderer::raycast_cuda", p)        # leaves film::cuda + renderer::raycast_cuda in the tree
+    _, misses0 = _cache_stats()
+    path = tmp_path / "lm.serialized"
+    rc.save_reset_load(path)
+    assert path.stat().st_size > 100000
+    hits_after = rc.intersect(rays)
+    ref_after, _, _ = rc.render("raycast", p)
+    img_after, _, _ = rc.render("renderer::raycast_cuda", p)
+    for k in ("t", "u", "v", "primitive", "face"):
+        assert np.array_equal(hits_before[k], hits_after[k]), k
+    assert (hits_after["primitive"] >= 0).mean() > 0.3
+    assert ref_before.max() > 0 and np.array_equal(ref_before, ref_after)
+    assert img_before.max() > 0 and np.array_equal(img_before, img_after)
+    rc.close()
