@@ -289,6 +289,12 @@ int lmcu_accel_load(LmcuScene* scene, const void* buffer, int64_t bytes);
 int lmcu_render_raycast(LmcuScene* scene, const LmcuRenderParams* p, float* film_rgb, LmcuRenderStats* stats);
 int lmcu_render_ao(LmcuScene* scene, const LmcuRenderParams* p, float* film_rgb, LmcuRenderStats* stats);
 int lmcu_render_pt(LmcuScene* scene, const LmcuRenderParams* p, float* film_rgb, LmcuRenderStats* stats);
+/* renderer::lt (src/renderer/renderer_lt.cpp:56-167): light tracing with next-event estimation toward the pinhole — paths start
+ * on a light (Light::sample_ray of a uniformly chosen light), every non-specular surface vertex is connected to the camera and
+ * the contribution splatted at the raster position of the connection (arbitrary-pixel splats).  Keys used: max_verts, seed,
+ * scheduler (sample: num_samples light paths; time: render_time, samples_per_iter), sample_offset, rescale (film *=
+ * w*h/processed, :162); the scheduler is always the image-space one (:44-47), primary_ray_sampling_mode and spp are ignored. */
+int lmcu_render_lt(LmcuScene* scene, const LmcuRenderParams* p, float* film_rgb, LmcuRenderStats* stats);
 /* Device film of the last render (width*height*3 floats) for the multi-GPU film reduce
  * (sample split: every rank renders with rescale=0, NCCL-reduces this buffer, then scales). */
 int lmcu_film_device_ptr(LmcuScene* scene, void** d_film, int64_t* num_floats);

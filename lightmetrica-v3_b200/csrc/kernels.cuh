@@ -25,7 +25,9 @@ struct DevScene {
     const MixEntry* mix;
     int32_t num_prims, num_lights, env_light;
     int32_t fetch_threshold;    // trace.cuh: idle lanes tolerated per iteration before the warp re-fetches
-    uint32_t num_tris, pad2_;
+    uint32_t num_tris;
+    int32_t pool_refill;        // trace2.cuh: empty pool slots per warp that trigger a re-fetch
+    float bound_center[3], bound_radius;   // Light::set_scene_bound (light_envconst.cpp:37-43): sphere around the scene AABB, x 1.01
     CameraDev cam;
 };
 
@@ -198,13 +200,13 @@ LMCU_HD float comp_pdf(const DevScene& s, const VComp& c, const SurfPoint& sp, F
 
 // Material::sample_direction(comp): ud0, ud1 = DirectionSampleU::ud, udc0 = udc[0] (lobe choice inside a marginal
 // group, model_wavefrontobj.cpp:441-468, material_mixture.cpp:201-224; Fresnel choice of glass)
-LMCU_HD BsdfSample comp_sample(const DevScene& s, const VComp& c, const SurfPoint& sp, F3 wi, float ud0, float ud1, float udc0) {
-    if (c.kind == 0) return mat_sample(c.l0, sp.n, sp.gn, wi, ud0, ud1, udc0);
+LMCU_HD BsdfSample comp_sample(const DevScene& s, const VComp& c, const SurfPoint& sp, F3 wi, float ud0, float ud1, float udc0, bool le = false) {
+    if (c.kind == 0) return mat_sample(c.l0, sp.n, sp.gn, wi, ud0, ud1, udc0, le);
     BsdfSample bs;
     if (c.kind == 3) {                                     // model_wavefrontobj.cpp:470-479: weight is Vec3(1), not f/p
         bs.valid = true; bs.specular = true; bs.pdf = 0.f;
         bs.wo = -wi;
-        bs.weight = f3s(sn_correction(sp.n, sp.gn, wi, bs.wo));
+        bs.weight = f3s(sn_correction(sp.n, sp.gn, wi, bs.wo, le));
         return bs;
     }
     int k = 0;
@@ -217,13 +219,13 @@ LMCU_HD BsdfSample comp_sample(const DevScene& s, const VComp& c, const SurfPoin
             m = comp_lobe(s, c, sp, k + 1, w, sel);
         }
     }
-    bs = mat_sample(m, sp.n, sp.gn, wi, ud0, ud1, udc0);
+    bs = mat_sample(m, sp.n, sp.gn, wi, ud0, ud1, udc0, le);
     if (!bs.valid) return bs;
     if (c.marginal) {
         const F3 f = comp_eval(s, c, sp, wi, bs.wo);
         const float p = comp_pdf(s, c, sp, wi, bs.wo);
         if (!(p > 0.f)) { bs.valid = false; return bs; }   // the reference divides 0 by 0 here; the path carries nothing
-        bs.weight = f * (sn_correction(sp.n, sp.gn, wi, bs.wo) / p);
+        bs.weight = f * (sn_correction(sp.n, sp.gn, wi, bs.wo, le) / p);
         bs.pdf = p;
     } else {
         bs.weight = bs.weight * w;
@@ -359,10 +361,14 @@ struct PtParams {
     uint64_t path_base;         // index of this wavefront's first path inside the pass (staggered wavefronts)
     uint32_t capacity;
     uint32_t image_mode;        // primary_ray_sampling_mode = image: the raster window is the whole film (renderer_pt.cpp:104-106)
+    uint32_t light_tracing;     // renderer::lt: paths start on the lights and connect to the camera (renderer_lt.cpp)
+    uint32_t pad_;
 };
 
 // RNG counter word 0 of a path's primary sample in image mode (no pixel is known before the raster position is drawn)
 constexpr uint32_t kImagePrimaryKey = 0xffffffffu;
+// ... and of every draw of a light-tracing path (its samples are not tied to a pixel either)
+constexpr uint32_t kLightPathKey = 0xfffffffeu;
 
 struct PtCounters {
     uint32_t count[2];          // entries in path queue A / B
@@ -671,6 +677,134 @@ LMCU_HD ShadeOut pt_shade_body(const DevScene& s, const PtParams& p, float4 ro, 
     out.thr_pix = make_float4(thr.x, thr.y, thr.z, u2f(pixel));
     out.aux = make_float4(bs.pdf, sp.n.x, sp.n.y, sp.n.z);
     out.info = make_uint2(info.x, num_verts | ((nee ? 1u : 0u) << 8) | (info.y & 0xffff0000u));
+    return out;
+}
+
+// -- light tracer (src/renderer/renderer_lt.cpp:56-167): paths start on a light, every surface vertex is connected to the
+// pinhole and splatted at the raster position of that connection ----------------------------------------------------------
+
+// path::sample_primary_ray(TransDir::LE) (include/lm/path.h:101-118): pick a light uniformly, Light::sample_ray.
+// RaySampleU = { up(2), upc(2), ud(2) }: block 0 = (upc0, upc1, up0, up1), block 1 = (ud0, ud1, -, -).
+LMCU_HD void lt_generate_body(const DevScene& s, const PtParams& p, uint64_t g, const PathQueue& q, uint32_t slot) {
+    const uint64_t sidx = p.sample_offset + g;
+    const R4 u1 = rand4(p.seed, kLightPathKey, sidx, 0);
+    const R4 u2 = rand4(p.seed, kLightPathKey, sidx, 1);
+    int li = (int)(u1.x * (float)s.num_lights);
+    li = li < 0 ? 0 : (li > s.num_lights - 1 ? s.num_lights - 1 : li);          // src/scene.cpp:374-387
+    const LightDev& l = s.lights[li];
+    const float inv_psel = (float)s.num_lights;
+    F3 o, d, w;
+    const F3 Ke = f3(l.Ke[0], l.Ke[1], l.Ke[2]);
+    const F3 bc = f3(s.bound_center[0], s.bound_center[1], s.bound_center[2]);
+    const float R = s.bound_radius;
+    if (l.type == LIGHT_AREA) {                                                  // light_area.cpp:77-97
+        const int ti = cdf_sample(s.cdf + l.cdf_offset, l.num_tris, u1.y);
+        const EmitTri& e = s.emit[l.tri_offset + ti];
+        const float sq = safe_sqrt(u1.z);
+        const float b1 = 1.0f - sq, b2 = u1.w * sq;
+        const F3 a = f3(e.p1.x, e.p1.y, e.p1.z), b = f3(e.p2.x, e.p2.y, e.p2.z), c = f3(e.p3.x, e.p3.y, e.p3.z);
+        o = a * (1.0f - b1 - b2) + b * b1 + c * b2;
+        const F3 nl = f3(e.n.x, e.n.y, e.n.z);
+        const F3 dl = sample_cosine_weighted(u2.x, u2.y);
+        F3 tu, tv;
+        orthonormal_basis(nl, tu, tv);
+        d = tu * dl.x + tv * dl.y + nl * dl.z;
+        // Le / (pA * pD): pA = invA / J, pD = 1/pi in projected solid angle; Le = Ke on the emitting side only
+        w = dot(d, nl) > 0.f ? Ke * (kPiF / l.inv_area_j) : f3s(0.f);
+    } else if (l.type == LIGHT_POINT) {                                          // light_point.cpp:36-50
+        o = f3(l.pos[0], l.pos[1], l.pos[2]);
+        d = sample_uniform_sphere(u2.x, u2.y);
+        w = Ke * (4.0f * kPiF);
+    } else {
+        // directional (light_directional.cpp:50-68), envconst (light_envconst.cpp:47-68), env (light_env.cpp:84-108): a
+        // direction (fixed / uniform on the sphere) and a point on the disk of the scene's bounding sphere facing it
+        const bool dirl = l.type == LIGHT_DIRECTIONAL;
+        d = dirl ? f3(l.pos[0], l.pos[1], l.pos[2]) : sample_uniform_sphere(u2.x, u2.y);
+        float dx, dy;
+        sample_uniform_disk(u1.z, u1.w, dx, dy);
+        F3 tu, tv;
+        orthonormal_basis(d, tu, tv);
+        o = bc - d * R + (tu * (dx * R) + tv * (dy * R));
+        const float inv_pa = kPiF * R * R;
+        w = (dirl ? Ke : light_env_radiance(s, l, -d)) * (dirl ? inv_pa : inv_pa * 4.0f * kPiF);
+    }
+    w = w * inv_psel;
+    q.ray_o[slot] = make_float4(o.x, o.y, o.z, (float)kEps);
+    q.ray_d[slot] = make_float4(d.x, d.y, d.z, (float)kInf);
+    q.thr_pix[slot] = make_float4(w.x, w.y, w.z, 0.f);
+    q.aux[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+    q.info[slot] = make_uint2((uint32_t)g, 1u | (((uint32_t)(g >> 32) & 0xffffu) << 16));    // num_verts = 1: the light endpoint
+}
+
+// One light-path vertex: Russian roulette + component (renderer_lt.cpp:143-156 of the iteration that traced this ray), then
+// the next iteration's camera connection (:96-118) and direction sample (:123-128).  A path whose throughput is zero is
+// dropped at once (the reference drags it along; it contributes nothing).
+template <bool COMPOSITE>
+LMCU_HD ShadeOut lt_shade_body(const DevScene& s, const PtParams& p, float4 ro, float4 rd, float4 thr_pix, uint2 info, float4 hit) {
+    ShadeOut out;
+    out.alive = false; out.shadow = false; out.emit = f3s(0.f);
+    const int32_t tri = (int32_t)f2u(hit.w);
+    if (tri < 0) return out;                                                // no surface (or the environment): the walk ends
+    const uint64_t sample = (uint64_t)info.x | ((uint64_t)(info.y >> 16) << 32);
+    const uint64_t sidx = p.sample_offset + sample;
+    uint32_t num_verts = info.y & 0xffu;                                    // loop counter of the iteration that traced this ray (1 = primary)
+    F3 thr = f3(thr_pix.x, thr_pix.y, thr_pix.z);
+    const F3 wi = -f3(rd.x, rd.y, rd.z);
+    const SurfPoint sp = surface_point(s, (uint32_t)tri, hit.y, hit.z);
+    const MaterialDev& mat = s.mats[sp.material];
+    const R4 u0 = rand4(p.seed, kLightPathKey, sidx, num_verts * 4u + 4u);  // ud0, ud1, rr, uc0
+    if (num_verts > 5u) {                                                   // renderer_lt.cpp:143-149
+        const float q = fmaxf(0.2f, 1.0f - max3(thr));
+        if (u0.z < q) return out;
+        thr = thr * (1.0f / (1.0f - q));
+    }
+    const bool plain = !COMPOSITE || mat_is_plain(mat);
+    VComp vc;
+    float udc0 = u0.w;
+    if (!plain) {
+        vc = pick_component(s, mat, sp, u0.w);
+        thr = thr * vc.cweight;
+        udc0 = rand4(p.seed, kLightPathKey, sidx, num_verts * 4u + 7u).x;
+    }
+    num_verts = num_verts < 2u ? 2u : num_verts + 1u;                       // the loop iteration that starts at this vertex
+    if ((int)num_verts >= p.max_verts) return out;                          // for (num_verts = 2; num_verts < max_verts; ...)
+    const bool specular = plain ? mat_is_specular(mat.type) : vc.specular;
+
+    // camera connection (path::sample_direct(EL), camera_pinhole.cpp:178-202): We / p = J(wo) * G(surface, pinhole)
+    if (!specular) {
+        const CameraDev& c = s.cam;
+        const F3 cpos = f3((float)c.pos[0], (float)c.pos[1], (float)c.pos[2]);
+        const F3 dv = sp.p - cpos;
+        const float d2 = dot(dv, dv), dist = sqrtf(d2);
+        const F3 wc = dv * (1.0f / dist);                                   // camera -> surface
+        float rx, ry;
+        const float We = camera_importance(c, wc, rx, ry);
+        if (We > 0.f) {
+            const F3 wo = -wc;                                              // surface -> camera
+            const float G = fabsf(dot(sp.n, wo)) / d2;                      // surface.h:329-348 toward a degenerated point
+            F3 fs = plain ? mat_eval(mat, sp.n, wi, wo) : comp_eval(s, vc, sp, wi, wo);
+            fs = fs * sn_correction(sp.n, sp.gn, wi, wo, true);
+            const F3 C = thr * fs * (We * G);
+            if (!is_zero(C) && G > 0.f) {
+                out.shadow = true;
+                out.sh_o = make_float4(sp.p.x, sp.p.y, sp.p.z, (float)kEps);
+                out.sh_d = make_float4(wo.x, wo.y, wo.z, dist * (1.0f - (float)kEps));
+                out.sh_c = make_float4(C.x, C.y, C.z, u2f(raster_to_pixel(p, rx, ry)));
+            }
+        }
+    }
+    // next direction (path::sample_direction(LE))
+    BsdfSample bs;
+    if (plain) bs = mat_sample(mat, sp.n, sp.gn, wi, u0.x, u0.y, u0.w, true); else bs = comp_sample(s, vc, sp, wi, u0.x, u0.y, udc0, true);
+    if (!bs.valid) return out;
+    thr = thr * bs.weight;
+    if (is_zero(thr)) return out;
+    out.alive = true;
+    out.o = make_float4(sp.p.x, sp.p.y, sp.p.z, (float)kEps);
+    out.d = make_float4(bs.wo.x, bs.wo.y, bs.wo.z, (float)kInf);
+    out.thr_pix = make_float4(thr.x, thr.y, thr.z, 0.f);
+    out.aux = make_float4(0.f, 0.f, 0.f, 0.f);
+    out.info = make_uint2(info.x, num_verts | (info.y & 0xffff0000u));
     return out;
 }
 

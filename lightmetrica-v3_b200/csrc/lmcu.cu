@@ -22,6 +22,7 @@
 #include "../../include/lmcu.h"
 #include "kernels.cuh"
 #include "trace.cuh"
+#include "trace2.cuh"
 
 #ifndef LMCU_SHADE_BLOCK
 #define LMCU_SHADE_BLOCK 64    // threads per CTA of the shade kernel: small CTAs slip into the register space a single
@@ -323,6 +324,13 @@ __global__ void k_pt_generate(DevScene s, PtParams p, PathQueue q, ShadowQueue s
     }
 }
 
+// light tracer: refill the current queue with new light paths (renderer_lt.cpp:60-66)
+__global__ void k_lt_generate(DevScene s, PtParams p, PathQueue q, PtCounters* ctr) {
+    const uint32_t m = ctr->gen_slot, n_new = ctr->gen_count;
+    const unsigned long long first = ctr->gen_first;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_new; i += gridDim.x * blockDim.x) lt_generate_body(s, p, first + i, q, m + i);
+}
+
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // Two compactions in one pass (next-path queue and shadow queue): the per-warp counts travel packed
@@ -354,6 +362,31 @@ __device__ __forceinline__ void block_compact2(bool p0, bool p1, uint32_t* count
     const uint32_t ex = smem[warp], lt = (1u << lane) - 1u;
     pos0 = smem[32] + (ex & 0xffffu) + (uint32_t)__popc(b0 & lt);
     pos1 = smem[33] + (ex >> 16) + (uint32_t)__popc(b1 & lt);
+}
+
+// light tracer: one vertex per path — Russian roulette, component, camera connection -> shadow queue, next direction ->
+// next queue.  Same two-queue compaction as k_pt_shade; nothing is added to the film here (an emitter is never "hit").
+template <bool COMPOSITE>
+__global__ void __launch_bounds__(LMCU_SHADE_BLOCK, LMCU_SHADE_MINB) k_lt_shade(DevScene s, PtParams p, PathQueue qin, PathQueue qout, ShadowQueue sq,
+                                                  const float4* hits, PtCounters* ctr, int cur) {
+    __shared__ uint32_t smem[2][34];
+    const uint32_t n = ctr->count[cur];
+    uint32_t tile = 0;
+    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x, tile ^= 1u) {
+        const uint32_t i = base + threadIdx.x;
+        ShadeOut o;
+        o.alive = false; o.shadow = false;
+        if (i < n) o = lt_shade_body<COMPOSITE>(s, p, qin.ray_o[i], qin.ray_d[i], qin.thr_pix[i], qin.info[i], hits[i]);
+        uint32_t pos, spos;
+        block_compact2(o.alive, o.shadow, &ctr->count[cur ^ 1], &ctr->shadow_count, smem[tile], pos, spos);
+        if (o.alive) {
+            qout.ray_o[pos] = o.o; qout.ray_d[pos] = o.d; qout.thr_pix[pos] = o.thr_pix; qout.aux[pos] = o.aux;
+            qout.info[pos] = o.info;
+        }
+        if (o.shadow) {
+            sq.ray_o[spos] = o.sh_o; sq.ray_d[spos] = o.sh_d; sq.contrib[spos] = o.sh_c;
+        }
+    }
 }
 
 template <bool COMPOSITE>
@@ -490,6 +523,53 @@ __global__ void __launch_bounds__(LMCU_TRAV_BLOCK, LMCU_MINB) k_pt_shadow_q(DevS
     ShadowIO io; io.ray_o = sq.ray_o; io.ray_d = sq.ray_d; io.contrib = sq.contrib; io.film = film;
     TraverseCounters tc; tc.nodes = tc.tris = 0;
     trace_queue<true, COUNT, TriT>(s.nodes, scene_tris<TriT>(s), n, &ctr->fetch_shadow, io, &ctr->overflow, &tc, s.fetch_threshold);
+    if (COUNT) { atomicAdd(&ctr->nodes_shadow, (unsigned long long)tc.nodes); atomicAdd(&ctr->tris_shadow, (unsigned long long)tc.tris); }
+}
+
+// -- the same three queue kernels on the shared-memory ray pool (trace2.cuh): K = 2 rays per lane ------------------------
+constexpr int kPoolK = 2;
+
+template <typename IO>
+__device__ __forceinline__ void pool_pointers(float4* smem, uint2* arena, float4*& pool, uint2*& stack) {
+    const uint32_t w = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    pool = smem + (size_t)w * (pool_bytes_per_warp<IO, kPoolK>() / 16);
+    stack = arena + (size_t)(blockIdx.x * wpb + w) * ((size_t)kStackSize * 32 * kPoolK);
+}
+
+template <typename TriT, bool COUNT>
+__global__ void __launch_bounds__(LMCU_TRAV_BLOCK, 5) k_intersect_p(DevScene s, const LmcuRay* __restrict__ rays, uint32_t n,
+                                                     LmcuHit* __restrict__ hits, uint32_t* cursor,
+                                                     unsigned long long* counters, uint32_t* overflow, uint2* arena) {
+    extern __shared__ float4 pool_smem[];
+    float4* pool; uint2* stack;
+    pool_pointers<BatchIO>(pool_smem, arena, pool, stack);
+    BatchIO io; io.s = s; io.rays = rays; io.hits = hits;
+    TraverseCounters tc; tc.nodes = tc.tris = 0;
+    trace_pool<false, COUNT, kPoolK, TriT>(s.nodes, scene_tris<TriT>(s), n, cursor, io, overflow, &tc, s.pool_refill, pool, stack);
+    if (COUNT) { atomicAdd(counters, (unsigned long long)tc.nodes); atomicAdd(counters + 1, (unsigned long long)tc.tris); }
+}
+
+template <typename TriT, bool COUNT>
+__global__ void __launch_bounds__(LMCU_TRAV_BLOCK, LMCU_MINB) k_pt_extend_p(DevScene s, PathQueue q, float4* hits, PtCounters* ctr, int cur, uint2* arena) {
+    extern __shared__ float4 pool_smem[];
+    float4* pool; uint2* stack;
+    pool_pointers<ExtendIO>(pool_smem, arena, pool, stack);
+    ExtendIO io; io.ray_o = q.ray_o; io.ray_d = q.ray_d; io.hits = hits;
+    TraverseCounters tc; tc.nodes = tc.tris = 0;
+    trace_pool<false, COUNT, kPoolK, TriT>(s.nodes, scene_tris<TriT>(s), ctr->count[cur], &ctr->fetch_extend, io, &ctr->overflow, &tc, s.pool_refill, pool, stack);
+    if (COUNT) { atomicAdd(&ctr->nodes_extend, (unsigned long long)tc.nodes); atomicAdd(&ctr->tris_extend, (unsigned long long)tc.tris); }
+}
+
+template <typename TriT, bool COUNT>
+__global__ void __launch_bounds__(LMCU_TRAV_BLOCK, LMCU_MINB) k_pt_shadow_p(DevScene s, ShadowQueue sq, float* film, PtCounters* ctr, uint2* arena) {
+    extern __shared__ float4 pool_smem[];
+    float4* pool; uint2* stack;
+    pool_pointers<ShadowIO>(pool_smem, arena, pool, stack);
+    const uint32_t n = ctr->shadow_count;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { ctr->rays += n; ctr->shadow_rays += n; }
+    ShadowIO io; io.ray_o = sq.ray_o; io.ray_d = sq.ray_d; io.contrib = sq.contrib; io.film = film;
+    TraverseCounters tc; tc.nodes = tc.tris = 0;
+    trace_pool<true, COUNT, kPoolK, TriT>(s.nodes, scene_tris<TriT>(s), n, &ctr->fetch_shadow, io, &ctr->overflow, &tc, s.pool_refill, pool, stack);
     if (COUNT) { atomicAdd(&ctr->nodes_shadow, (unsigned long long)tc.nodes); atomicAdd(&ctr->tris_shadow, (unsigned long long)tc.tris); }
 }
 
@@ -688,6 +768,7 @@ struct LmcuScene {
     DBuf<TriShade> shade;
     DBuf<TriUV> uv;
     bool built = false, fp32 = false;
+    float bounds[6] = { 0, 0, 0, 0, 0, 0 };   // scene AABB (float, outward): Light::set_scene_bound for the light tracer
     uint64_t blob_desc_digest = 0;       // accel-only scene restored from a blob: the digest that blob carried
     bool composite = false;              // a material is textured or a mixture: the shade kernel's <true> instantiation
     // scratch / outputs
@@ -705,6 +786,7 @@ struct LmcuScene {
         DBuf<float4> hits;
         DBuf<float4> sq[3];
         DBuf<PtCounters> ctr;
+        DBuf<uint2> arena;                   // pool mode: traversal stacks [warp][depth][slot] of this wavefront's kernels
         cudaStream_t stream = nullptr;       // wave 0 runs on the scene's stream, the others on their own
         cudaEvent_t done = nullptr;
         // two groups of iterations are in flight per wavefront; per slot: per-kernel timing events, a "group complete"
@@ -727,6 +809,9 @@ struct LmcuScene {
     uint32_t pt_capacity = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int fetch_threshold = 12;            // LMCU_FETCH
+    int pool_mode = 0;                   // LMCU_TRACE=pool: the queue kernels run on the shared-memory ray pool (trace2.cuh)
+    int pool_refill = 16;                // LMCU_POOL_FETCH
+    DBuf<uint2> batch_arena;             // pool mode: traversal stacks of the accel-batch kernel
     int shade_ctas_per_sm = LMCU_SHADE_MINB;     // LMCU_SHADE_GRID: CTAs per SM in the shade kernel's grid-stride grid
     int ctas_per_sm = LMCU_MINB;                 // LMCU_CTAS: resident 128-thread CTAs per SM for the persistent traversal grids
 
@@ -736,6 +821,16 @@ struct LmcuScene {
         d.lights = lights.p; d.emit = emit.p; d.cdf = cdf.p; d.env_tex = env_tex.p;
         d.uv = uv.p; d.textures = textures.p; d.texels = texels.p; d.mix = mix.p;
         d.num_prims = num_prims; d.num_lights = num_lights; d.env_light = env_light; d.fetch_threshold = fetch_threshold; d.num_tris = nt; d.cam = cam;
+        d.pool_refill = pool_refill;
+        {   // light_envconst.cpp:37-43: sphere around the scene AABB, radius x 1.01
+            float r2 = 0.f;
+            for (int a = 0; a < 3; a++) {
+                d.bound_center[a] = 0.5f * (bounds[a] + bounds[3 + a]);
+                const float e = bounds[3 + a] - d.bound_center[a];
+                r2 += e * e;
+            }
+            d.bound_radius = std::sqrt(r2) * 1.01f;
+        }
         return d;
     }
 };
@@ -767,6 +862,8 @@ int lmcu_scene_create(int device, LmcuScene** out) {
     CU(cudaEventCreate(&s->ev0));
     CU(cudaEventCreate(&s->ev1));
     if (const char* e = getenv("LMCU_FETCH")) s->fetch_threshold = atoi(e);
+    if (const char* e = getenv("LMCU_TRACE")) s->pool_mode = std::string(e) == "pool" ? 1 : 0;
+    if (const char* e = getenv("LMCU_POOL_FETCH")) s->pool_refill = std::max(1, atoi(e));
     if (const char* e = getenv("LMCU_CTAS")) s->ctas_per_sm = std::max(1, atoi(e));
     if (const char* e = getenv("LMCU_SHADE_GRID")) s->shade_ctas_per_sm = std::max(1, atoi(e));
     if (const char* e = getenv("LMCU_WAVES")) s->default_waves = std::min((int)LmcuScene::kMaxWaves, std::max(1, atoi(e)));
@@ -938,6 +1035,7 @@ int lmcu_accel_build(LmcuScene* s, const LmcuBuildOptions* opts, LmcuBuildStats*
         }
     }
     int h_exact = 0;
+    CU(cudaMemcpyAsync(s->bounds, bounds.p, sizeof(s->bounds), cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(&h_exact, exact.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     // 48-byte float records when every vertex is float-representable AND the triangle array is too large to stay in
@@ -987,8 +1085,10 @@ struct AccelBlobHeader {
     uint32_t version, fp32, nt, num_nodes, num_prims, has_uv;
     uint64_t payload_bytes, checksum;
     uint64_t desc_digest;         // digest of the description the BVH was built from (mesh data + primitive table)
+    float bounds[6];              // scene AABB
+    uint32_t pad_[2];
 };
-constexpr uint32_t kBlobVersion = 2;
+constexpr uint32_t kBlobVersion = 3;
 inline uint64_t fnv1a(const unsigned char* p, size_t n, uint64_t h = 1469598103934665603ull) {
     for (size_t i = 0; i < n; i++) { h ^= p[i]; h *= 1099511628211ull; }
     return h;
@@ -1045,6 +1145,7 @@ int lmcu_accel_save(LmcuScene* s, void* buffer, int64_t bytes) {
     h.version = kBlobVersion; h.fp32 = s->fp32; h.nt = s->nt; h.num_nodes = (uint32_t)s->nodes.n;
     h.num_prims = (uint32_t)s->num_prims; h.has_uv = s->uv.p ? 1 : 0;
     h.payload_bytes = blob_payload(h);
+    memcpy(h.bounds, s->bounds, sizeof(h.bounds));
     const int rd = desc_digest(s, &h.desc_digest);
     if (rd) return rd;
     unsigned char* base = static_cast<unsigned char*>(buffer) + sizeof(AccelBlobHeader);
@@ -1152,6 +1253,7 @@ int lmcu_accel_load(LmcuScene* s, const void* buffer, int64_t bytes) {
         return e;
     };
     s->built = false;
+    memcpy(s->bounds, h.bounds, sizeof(s->bounds));
     CU(s->nodes.alloc(h.num_nodes));
     CU(push(s->nodes.p, (size_t)h.num_nodes * sizeof(WideNode)));
     s->fp32 = h.fp32 != 0;
@@ -1188,6 +1290,17 @@ int lmcu_accel_load(LmcuScene* s, const void* buffer, int64_t bytes) {
         }                                                                                                        \
     } while (0)
 
+#define LMCU_DISPATCH_SMEM(KERNEL, FP32, COUNT, GRID, BLOCK, SMEM, STREAM, ...)                                  \
+    do {                                                                                                         \
+        if (FP32) {                                                                                              \
+            if (COUNT) KERNEL<TriF32, true><<<GRID, BLOCK, SMEM, STREAM>>>(__VA_ARGS__);                         \
+            else KERNEL<TriF32, false><<<GRID, BLOCK, SMEM, STREAM>>>(__VA_ARGS__);                              \
+        } else {                                                                                                 \
+            if (COUNT) KERNEL<TriF64, true><<<GRID, BLOCK, SMEM, STREAM>>>(__VA_ARGS__);                         \
+            else KERNEL<TriF64, false><<<GRID, BLOCK, SMEM, STREAM>>>(__VA_ARGS__);                              \
+        }                                                                                                        \
+    } while (0)
+
 static int launch_intersect(LmcuScene* s, const LmcuRay* d_rays, int64_t n, LmcuHit* d_hits, bool count, cudaStream_t st) {
     const DevScene d = s->dev();
     if (count) CU(cudaMemsetAsync(s->cursor.p + 1, 0, 2 * sizeof(unsigned long long), st));
@@ -1196,6 +1309,16 @@ static int launch_intersect(LmcuScene* s, const LmcuRay* d_rays, int64_t n, Lmcu
         const uint32_t m = (uint32_t)std::min<int64_t>(kChunk, n - off);
         unsigned long long* cur = s->cursor.p + 8 + (s->cursor_next.fetch_add(1) % LmcuScene::kCursorRing);
         CU(cudaMemsetAsync(cur, 0, sizeof(unsigned long long), st));
+        if (s->pool_mode && st == s->stream) {      // one arena per scene: only for launches ordered by the scene's stream
+            const unsigned pblocks = (unsigned)std::min<int64_t>((m + 2 * LMCU_TRAV_BLOCK - 1) / (2 * LMCU_TRAV_BLOCK), (int64_t)s->num_sms * 5);
+            const size_t need = (size_t)s->num_sms * 5 * (LMCU_TRAV_BLOCK / 32) * kStackSize * 32 * kPoolK;
+            if (s->batch_arena.n != need) CU(s->batch_arena.alloc(need));
+            const size_t smem = pool_bytes_per_warp<BatchIO, kPoolK>() * (LMCU_TRAV_BLOCK / 32);
+            LMCU_DISPATCH_SMEM(k_intersect_p, s->fp32, count, pblocks, LMCU_TRAV_BLOCK, smem, st, d, d_rays + off, m, d_hits + off,
+                               (uint32_t*)cur, s->cursor.p + 1, s->flags.p, s->batch_arena.p);
+            CU(cudaGetLastError());
+            continue;
+        }
         const unsigned blocks = (unsigned)std::min<int64_t>((m + LMCU_TRAV_BLOCK - 1) / LMCU_TRAV_BLOCK, (int64_t)s->num_sms * s->ctas_per_sm);
         LMCU_DISPATCH(k_intersect_q, s->fp32, count, blocks, LMCU_TRAV_BLOCK, st, d, d_rays + off, m, d_hits + off,
                       (uint32_t*)cur, s->cursor.p + 1, s->flags.p);
@@ -1565,6 +1688,7 @@ static int ensure_pt_pools(LmcuScene* s, uint32_t capacity, uint32_t shadow_fact
         CU(v.hits.alloc(cap));
         for (int k = 0; k < 3; k++) CU(v.sq[k].alloc((size_t)cap * shadow_factor));
         CU(v.ctr.alloc(cap ? 1 : 0));
+        CU(v.arena.alloc(cap && s->pool_mode ? (size_t)s->num_sms * s->ctas_per_sm * (LMCU_TRAV_BLOCK / 32) * kStackSize * 32 * kPoolK : 0));
         if (cap && w > 0 && !v.stream) CU(cudaStreamCreateWithFlags(&v.stream, cudaStreamNonBlocking));
         if (cap && !v.done) CU(cudaEventCreateWithFlags(&v.done, cudaEventDisableTiming));
         if (cap && !v.h) CU(cudaHostAlloc((void**)&v.h, 2 * sizeof(PtCounters), cudaHostAllocDefault));
@@ -1601,6 +1725,7 @@ static int pt_pass(LmcuScene* s, const PtParams& pp_all, bool count, PtAccum& ac
     const unsigned q_blocks = (unsigned)(s->num_sms * s->ctas_per_sm);
     const unsigned shade_blocks = (unsigned)(s->num_sms * s->shade_ctas_per_sm), gen_blocks = (unsigned)s->num_sms * 4;
     const int kGroup = 4;                       // iterations between host checks
+    const size_t pool_smem_pt = pool_bytes_per_warp<ExtendIO, kPoolK>() * (LMCU_TRAV_BLOCK / 32);
     const double spp_per_iteration = (double)pp_all.capacity / ((double)pp_all.width * (double)pp_all.height);
     const unsigned fold_blocks = (unsigned)std::min<size_t>((s->film.n + 255) / 256, (size_t)s->num_sms * 8);
     PtParams pp[LmcuScene::kMaxWaves];
@@ -1641,14 +1766,21 @@ static int pt_pass(LmcuScene* s, const PtParams& pp_all, bool count, PtAccum& ac
             cudaEvent_t* ev = &v.ring[slot][it * 4];
             const int cur = v.cur;
             k_pt_advance<<<1, 1, 0, st>>>(pp[w], v.ctr.p, cur);
-            k_pt_generate<<<gen_blocks, 256, 0, st>>>(d, pp[w], q[w][cur], sq[w], v.ctr.p);
+            if (pp[w].light_tracing) k_lt_generate<<<gen_blocks, 256, 0, st>>>(d, pp[w], q[w][cur], v.ctr.p);
+            else k_pt_generate<<<gen_blocks, 256, 0, st>>>(d, pp[w], q[w][cur], sq[w], v.ctr.p);
             cudaEventRecord(ev[0], st);
-            LMCU_DISPATCH(k_pt_extend_q, s->fp32, count, q_blocks, LMCU_TRAV_BLOCK, st, d, q[w][cur], v.hits.p, v.ctr.p, cur);
+            if (s->pool_mode) LMCU_DISPATCH_SMEM(k_pt_extend_p, s->fp32, count, q_blocks, LMCU_TRAV_BLOCK, pool_smem_pt, st, d, q[w][cur], v.hits.p, v.ctr.p, cur, v.arena.p);
+            else LMCU_DISPATCH(k_pt_extend_q, s->fp32, count, q_blocks, LMCU_TRAV_BLOCK, st, d, q[w][cur], v.hits.p, v.ctr.p, cur);
             cudaEventRecord(ev[1], st);
-            if (s->composite) k_pt_shade<true><<<shade_blocks, LMCU_SHADE_BLOCK, 0, st>>>(d, pp[w], q[w][cur], q[w][cur ^ 1], sq[w], v.hits.p, s->film.p, v.ctr.p, cur);
+            if (pp[w].light_tracing) {
+                if (s->composite) k_lt_shade<true><<<shade_blocks, LMCU_SHADE_BLOCK, 0, st>>>(d, pp[w], q[w][cur], q[w][cur ^ 1], sq[w], v.hits.p, v.ctr.p, cur);
+                else k_lt_shade<false><<<shade_blocks, LMCU_SHADE_BLOCK, 0, st>>>(d, pp[w], q[w][cur], q[w][cur ^ 1], sq[w], v.hits.p, v.ctr.p, cur);
+            }
+            else if (s->composite) k_pt_shade<true><<<shade_blocks, LMCU_SHADE_BLOCK, 0, st>>>(d, pp[w], q[w][cur], q[w][cur ^ 1], sq[w], v.hits.p, s->film.p, v.ctr.p, cur);
             else k_pt_shade<false><<<shade_blocks, LMCU_SHADE_BLOCK, 0, st>>>(d, pp[w], q[w][cur], q[w][cur ^ 1], sq[w], v.hits.p, s->film.p, v.ctr.p, cur);
             cudaEventRecord(ev[2], st);
-            LMCU_DISPATCH(k_pt_shadow_q, s->fp32, count, q_blocks, LMCU_TRAV_BLOCK, st, d, sq[w], s->film.p, v.ctr.p);
+            if (s->pool_mode) LMCU_DISPATCH_SMEM(k_pt_shadow_p, s->fp32, count, q_blocks, LMCU_TRAV_BLOCK, pool_smem_pt, st, d, sq[w], s->film.p, v.ctr.p, v.arena.p);
+            else LMCU_DISPATCH(k_pt_shadow_q, s->fp32, count, q_blocks, LMCU_TRAV_BLOCK, st, d, sq[w], s->film.p, v.ctr.p);
             cudaEventRecord(ev[3], st);
             v.cur ^= 1;
             acc.launches += 5;
@@ -1721,13 +1853,25 @@ static int pt_pass(LmcuScene* s, const PtParams& pp_all, bool count, PtAccum& ac
     return LMCU_OK;
 }
 
+static int render_paths(LmcuScene* s, const LmcuRenderParams* p, float* film_rgb, LmcuRenderStats* stats, bool light_tracing);
+
 int lmcu_render_pt(LmcuScene* s, const LmcuRenderParams* p, float* film_rgb, LmcuRenderStats* stats) {
+    return render_paths(s, p, film_rgb, stats, false);
+}
+
+// renderer::lt (src/renderer/renderer_lt.cpp): scheduler::spi::* only ("Scheduler is fixed to image space scheduler", :44-47)
+int lmcu_render_lt(LmcuScene* s, const LmcuRenderParams* p, float* film_rgb, LmcuRenderStats* stats) {
+    return render_paths(s, p, film_rgb, stats, true);
+}
+
+static int render_paths(LmcuScene* s, const LmcuRenderParams* p, float* film_rgb, LmcuRenderStats* stats, bool light_tracing) {
     int rc = require_renderable(s, true);
     if (rc) return rc;
     if (!p) return fail(LMCU_ERR_INVALID_ARGUMENT, "null params");
-    const bool image = p->primary_ray_sampling_mode == LMCU_PRIMARY_IMAGE;
+    const bool image = light_tracing || p->primary_ray_sampling_mode == LMCU_PRIMARY_IMAGE;
     const bool timed = p->scheduler == LMCU_SCHED_TIME;
     if (p->primary_ray_sampling_mode != LMCU_PRIMARY_PIXEL && !image) return fail(LMCU_ERR_INVALID_ARGUMENT, "bad primary_ray_sampling_mode");
+    if (light_tracing && !s->has_camera) return fail(LMCU_ERR_UNSUPPORTED, "Missing camera primitive.");
     if (p->scheduler != LMCU_SCHED_SAMPLE && !timed) return fail(LMCU_ERR_INVALID_ARGUMENT, "bad scheduler");
     if (timed) {
         if (!(p->render_time >= 0)) return fail(LMCU_ERR_INVALID_ARGUMENT, "render_time must be >= 0");
@@ -1765,6 +1909,7 @@ int lmcu_render_pt(LmcuScene* s, const LmcuRenderParams* p, float* film_rgb, Lmc
     pp.seed = p->seed; pp.tiled = (p->width % 8 == 0 && p->height % 4 == 0) ? 1u : 0u;
     pp.capacity = capacity;
     pp.image_mode = image ? 1u : 0u;
+    pp.light_tracing = light_tracing ? 1u : 0u;
     const bool count = p->count_traversal != 0;
     PtAccum acc;
     acc.progress = p->progress; acc.progress_user = p->progress_user;

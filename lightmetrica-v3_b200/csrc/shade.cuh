@@ -89,12 +89,22 @@ LMCU_HD F3 sample_uniform_sphere(float u0, float u1) {
     return f3(r * cosf(t), r * sinf(t), z);
 }
 
+// math::sample_uniform_disk (include/lm/math.h:632-638)
+LMCU_HD void sample_uniform_disk(float u0, float u1, float& x, float& y) {
+    const float r = safe_sqrt(u0);
+    const float t = 2.0f * kPiF * u1;
+    x = r * cosf(t); y = r * sinf(t);
+}
+
 LMCU_HD F3 reflection(F3 w, F3 n) { return 2.0f * dot(w, n) * n - w; }   // math.h:497-499
 
-// surface::shading_normal_correction for camera->light transport (include/lm/surface.h:424-438)
-LMCU_HD float sn_correction(F3 n, F3 gn, F3 wi, F3 wo) {
+// surface::shading_normal_correction (include/lm/surface.h:424-438).  le = false: camera->light transport (TransDir::EL,
+// the path tracer): 0 or 1.  le = true: light->camera transport (TransDir::LE, the light tracer): Veach's energy
+// compensation |wi.ns||wo.ng| / (|wo.ns||wi.ng|).
+LMCU_HD float sn_correction(F3 n, F3 gn, F3 wi, F3 wo, bool le = false) {
     const float wi_ng = dot(wi, gn), wo_ng = dot(wo, gn), wi_ns = dot(wi, n), wo_ns = dot(wo, n);
-    return (wi_ng * wi_ns <= 0.f || wo_ng * wo_ns <= 0.f) ? 0.f : 1.f;
+    if (wi_ng * wi_ns <= 0.f || wo_ng * wo_ns <= 0.f) return 0.f;
+    return le ? wi_ns * wo_ng / (wo_ns * wi_ng) : 1.f;
 }
 
 LMCU_HD bool opposite(F3 n, F3 w1, F3 w2) { return dot(w1, n) * dot(w2, n) <= 0.f; }   // surface.h:178-180
@@ -200,7 +210,9 @@ struct BsdfSample {
 
 // path::sample_component + path::sample_direction at a surface vertex (include/lm/path.h:193-200,378-422).
 // u: (ud0, ud1, -, uc0)
-LMCU_HD BsdfSample mat_sample(const MaterialDev& m, F3 n, F3 gn, F3 wi, float ud0, float ud1, float uc0) {
+// le: light->camera transport (TransDir::LE): no eta^2 radiance scaling on refraction (material_glass.cpp:85-87) and the
+// LE form of the shading-normal correction.
+LMCU_HD BsdfSample mat_sample(const MaterialDev& m, F3 n, F3 gn, F3 wi, float ud0, float ud1, float uc0, bool le = false) {
     BsdfSample s;
     s.valid = true; s.specular = false; s.pdf = 0.f;
     if (m.type == MAT_DIFFUSE) {                       // material_diffuse.cpp:68-76
@@ -235,10 +247,10 @@ LMCU_HD BsdfSample mat_sample(const MaterialDev& m, F3 n, F3 gn, F3 wi, float ud
             s.weight = f3s(1.f);                       // (1/Fr) * Fr
         } else {
             s.wo = wt;
-            s.weight = f3s(eta * eta);                 // (1/(1-Fr)) * (1-Fr) * eta^2 (refr_correction, EL)
+            s.weight = f3s(le ? 1.f : eta * eta);      // (1/(1-Fr)) * (1-Fr) * refr_correction (eta^2 for EL, 1 for LE)
         }
     }
-    s.weight = s.weight * sn_correction(n, gn, wi, s.wo);
+    s.weight = s.weight * sn_correction(n, gn, wi, s.wo, le);
     return s;
 }
 

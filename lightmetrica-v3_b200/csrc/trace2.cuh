@@ -25,7 +25,8 @@ namespace lmcu {
 
 #if defined(__CUDACC__)
 
-constexpr int kPoolChunks = 10;         // 16-byte chunks of state per ray (160 B)
+// 16-byte chunks of state per ray: 9 (144 B) for the path-tracer queues, 10 for accel batches (c9)
+template <typename IO> __host__ __device__ constexpr int pool_chunks() { return IO::kExactT ? 10 : 9; }
 //  c0: o.x o.y (f64)   c1: o.z d.x   c2: d.y d.z         FP64 ray, as the reference sees it (triangle test)
 //  c3: ox oy oz (f32), tmax_up                            FP32 view (node test) + float upper bound of the search interval
 //  c4: 1/dx 1/dy 1/dz (f32), tmin_dn
@@ -33,9 +34,10 @@ constexpr int kPoolChunks = 10;         // 16-byte chunks of state per ray (160 
 //  c6: u_raw, v_raw (f64)
 //  c7: ngroup.x ngroup.y tgroup.x tgroup.y
 //  c8: htri, queue index, sp | octinv << 8, -
-//  c9: tmin (f64), -                                       lower bound as the reference sees it
+//  c9: tmin (f64), -                                       lower bound as the reference sees it (accel batches only: the
+//                                                          path tracer's tmin IS the float tmin_dn)
 
-template <int K> constexpr size_t pool_bytes_per_warp() { return (size_t)kPoolChunks * 32 * K * 16; }
+template <typename IO, int K> __host__ __device__ constexpr size_t pool_bytes_per_warp() { return (size_t)pool_chunks<IO>() * 32 * K * 16; }
 
 enum : uint32_t { SLOT_EMPTY = 0u, SLOT_NODE = 1u, SLOT_TRI = 2u };
 
@@ -89,7 +91,7 @@ __device__ __forceinline__ void trace_pool(const WideNode* __restrict__ nodes, c
                             pool_d[CH(6, slot)] = make_double2(0.0, 0.0);
                             pool_u[CH(7, slot)] = make_uint4(0u, 0x80000000u, 0u, 0u);   // the root occupies virtual slot 7 of group 0
                             pool_u[CH(8, slot)] = make_uint4(0xffffffffu, qi, (f.octinv4 & 0xffu) << 8, 0u);
-                            pool_d[CH(9, slot)] = make_double2(r.tmin, 0.0);
+                            if (IO::kExactT) pool_d[CH(9, slot)] = make_double2(r.tmin, 0.0);
                             state |= SLOT_NODE << (2 * k);
                         }
                     }

@@ -5,6 +5,8 @@
 //     renderer::raycast_cuda lm::Renderer   same JSON keys as renderer::raycast (renderer_raycast.cpp:48-60)
 //     renderer::ao_cuda      lm::Renderer   same keys as renderer::ao     (functest/renderer_ao.cpp:18-22)
 //     renderer::pt_cuda      lm::Renderer   same keys as renderer::pt     (renderer_pt.cpp:51-77)
+//     renderer::lt_cuda      lm::Renderer   same keys as renderer::lt     (renderer_lt.cpp:37-48)
+//     film::cuda             lm::Film       the fp32 film the renderers write with one copy
 // It is loaded with lm::comp::load_plugin("<dir>/lm_cuda") exactly like accel_nanort / accel_embree.
 //
 // This file is HOST glue only: it pulls geometry, transforms, materials, lights and the camera out of
@@ -1147,6 +1149,90 @@ public:
 };
 
 LM_COMP_REG_IMPL(Renderer_PT_Cuda, "renderer::pt_cuda");
+
+/*
+\rst
+.. function:: renderer::lt_cuda
+
+   Light tracing with next-event estimation toward the camera on a CUDA device; same parameters as ``renderer::lt``
+   (``scene``, ``output``, ``max_verts``, ``seed``, ``scheduler`` = ``sample`` with ``num_samples`` or ``time`` with
+   ``render_time`` / ``samples_per_iter``; the scheduler is the image-space one, src/renderer/renderer_lt.cpp:44-47) plus
+   ``device``, ``wavefronts`` and ``cache`` as in ``renderer::pt_cuda``.
+\endrst
+*/
+class Renderer_LT_Cuda final : public Renderer_CudaBase {
+private:
+    int max_verts_;
+    std::optional<unsigned int> seed_;
+    int scheduler_ = LMCU_SCHED_SAMPLE;
+    long long num_samples_ = 0;
+    long long samples_per_iter_ = 0;
+    Float render_time_ = 0_f;
+    int wavefronts_ = 0;
+
+    static void report_progress(void* user, int64_t processed_paths, int64_t, double elapsed) {
+        if (*static_cast<const bool*>(user)) progress::update_time(elapsed);
+        else progress::update(processed_paths);
+    }
+
+public:
+    LM_SERIALIZE_IMPL(ar) {                                                                    // renderer_lt.cpp:27-29
+        serialize_base(ar);
+        ar(max_verts_, seed_, scheduler_, num_samples_, samples_per_iter_, render_time_, wavefronts_);
+    }
+
+    virtual void construct(const Json& prop) override {
+        construct_base(prop);
+        max_verts_ = json::value<int>(prop, "max_verts");
+        seed_ = json::value_or_none<unsigned int>(prop, "seed");
+        const auto name = json::value<std::string>(prop, "scheduler");
+        if (name == "sample") {
+            scheduler_ = LMCU_SCHED_SAMPLE;
+            num_samples_ = json::value<long long>(prop, "num_samples");                        // scheduler::spi::sample, scheduler.cpp:127-129
+        }
+        else if (name == "time") {
+            scheduler_ = LMCU_SCHED_TIME;
+            render_time_ = json::value<Float>(prop, "render_time");                            // scheduler::spi::time, :157-160
+            samples_per_iter_ = json::value<long long>(prop, "samples_per_iter", 100000);
+        }
+        else LM_THROW_EXCEPTION(Error::InvalidArgument, "renderer::lt_cuda: unknown scheduler '{}'", name);
+        wavefronts_ = json::value<int>(prop, "wavefronts", 0);
+    }
+
+    virtual Json render() const override {
+        scene_->require_renderable();
+        film_->clear();
+        const auto size = film_->size();
+        LmcuRenderParams p{};
+        p.width = size.w; p.height = size.h; p.max_verts = max_verts_;
+        p.primary_ray_sampling_mode = LMCU_PRIMARY_IMAGE;
+        p.scheduler = scheduler_;
+        p.num_samples = num_samples_;
+        p.render_time = render_time_;
+        p.samples_per_iter = samples_per_iter_;
+        p.wavefronts = wavefronts_;
+        p.rescale = 1;
+        p.seed = seed_ ? *seed_ : math::rng_seed();
+        bool timed = scheduler_ == LMCU_SCHED_TIME;
+        if (timed) progress::start(progress::ProgressMode::Time, 0, render_time_);
+        else progress::start(progress::ProgressMode::Samples, num_samples_, -1);
+        struct ProgressEnd { ~ProgressEnd() { progress::end(); } } progress_end;
+        p.progress = &Renderer_LT_Cuda::report_progress;
+        p.progress_user = &timed;
+        upload();
+        std::vector<float> rgb;
+        float* target = film_target(rgb);
+        LmcuRenderStats st{};
+        {
+            std::unique_lock<std::mutex> lk(dev_->render_mu);
+            check(lmcu_render_lt(dev_->h, &p, target, &st));
+        }
+        write_film(rgb, false);
+        return { {"processed", st.processed}, {"elapsed", st.elapsed} };
+    }
+};
+
+LM_COMP_REG_IMPL(Renderer_LT_Cuda, "renderer::lt_cuda");
 
 LM_NAMESPACE_END(LM_NAMESPACE)
 

@@ -7,6 +7,7 @@
 // only by tests/test_hostsim.py into tests/hostsim/_build/, is never loaded by lmcu/, bench.py
 // or the plugin, and liblmcu.so contains none of it: the product has no CPU fallback.
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <numeric>
@@ -28,6 +29,7 @@ struct SimScene {
     std::vector<TriShade> shade;
     std::vector<TriUV> uv;
     bool fp32 = false;
+    float bounds[6] = { 0, 0, 0, 0, 0, 0 };
     DevScene dev() const {
         DevScene d{};
         d.nodes = nodes.data(); d.t32 = fp32 ? t32.data() : nullptr; d.t64 = fp32 ? nullptr : t64.data();
@@ -170,6 +172,7 @@ int hostsim_scene_create(const LmcuSceneDesc* d, int max_leaf, void** out, long 
                              tri_hi.data(), centre.data()) && exact;
         for (int a = 0; a < 3; a++) { slo[a] = fminf(slo[a], tri_lo[(size_t)g * 3 + a]); shi[a] = fmaxf(shi[a], tri_hi[(size_t)g * 3 + a]); }
     }
+    for (int a = 0; a < 3; a++) { s->bounds[a] = slo[a]; s->bounds[3 + a] = shi[a]; }
     // k_morton + sort
     const double dlo[3] = { slo[0], slo[1], slo[2] }, dhi[3] = { shi[0], shi[1], shi[2] };
     std::vector<uint64_t> keys(nt);
@@ -335,6 +338,56 @@ int hostsim_pt(void* p, const LmcuRenderParams* rp, float* film, long long* rays
         }
     }
     const double sc = !rp->rescale ? 1.0 : image ? (double)npix / (double)rp->num_samples : 1.0 / (double)rp->spp;
+    for (size_t i = 0; i < npix * 3; i++) film[i] = (float)(acc[i] * sc);
+    if (rays_out) *rays_out = rays;
+    return 0;
+}
+
+
+// Light tracer, one light path at a time through lt_generate_body / lt_shade_body (renderer_lt.cpp).
+int hostsim_lt(void* p, const LmcuRenderParams* rp, float* film, long long* rays_out) {
+    const SimScene& s = *static_cast<SimScene*>(p);
+    DevScene d = s.dev();
+    {
+        float r2 = 0.f;
+        for (int a = 0; a < 3; a++) {
+            d.bound_center[a] = 0.5f * (s.bounds[a] + s.bounds[3 + a]);
+            const float e = s.bounds[3 + a] - d.bound_center[a];
+            r2 += e * e;
+        }
+        d.bound_radius = std::sqrt(r2) * 1.01f;
+    }
+    PtParams pp{};
+    pp.width = rp->width; pp.height = rp->height; pp.max_verts = rp->max_verts; pp.seed = rp->seed;
+    pp.sample_offset = (uint64_t)rp->sample_offset;
+    pp.image_mode = 1u; pp.light_tracing = 1u;
+    pp.total_paths = (uint64_t)rp->num_samples;
+    const size_t npix = (size_t)rp->width * rp->height;
+    std::vector<double> acc(npix * 3, 0.0);
+    float4 ro, rd, tp, aux; uint2 info;
+    PathQueue q; q.ray_o = &ro; q.ray_d = &rd; q.thr_pix = &tp; q.aux = &aux; q.info = &info;
+    uint2 stack[kStackSize];
+    long long rays = 0;
+    for (uint64_t g = 0; g < pp.total_paths; g++) {
+        lt_generate_body(d, pp, g, q, 0);
+        while (true) {
+            HitD h;
+            if (s.fp32) pt_trace<false, false, TriF32>(d, ro, rd, h, stack, nullptr); else pt_trace<false, false, TriF64>(d, ro, rd, h, stack, nullptr);
+            rays++;
+            const float4 hit = make_float4((float)h.t, (float)h.u, (float)h.v, u2f((uint32_t)h.tri));
+            const ShadeOut o = lt_shade_body<true>(d, pp, ro, rd, tp, info, hit);
+            if (o.shadow) {
+                HitD hs;
+                if (s.fp32) pt_trace<true, false, TriF32>(d, o.sh_o, o.sh_d, hs, stack, nullptr); else pt_trace<true, false, TriF64>(d, o.sh_o, o.sh_d, hs, stack, nullptr);
+                rays++;
+                const uint32_t px = f2u(o.sh_c.w);
+                if (hs.tri < 0) { acc[px * 3 + 0] += o.sh_c.x; acc[px * 3 + 1] += o.sh_c.y; acc[px * 3 + 2] += o.sh_c.z; }
+            }
+            if (!o.alive) break;
+            ro = o.o; rd = o.d; tp = o.thr_pix; aux = o.aux; info = o.info;
+        }
+    }
+    const double sc = rp->rescale ? (double)npix / (double)rp->num_samples : 1.0;
     for (size_t i = 0; i < npix * 3; i++) film[i] = (float)(acc[i] * sc);
     if (rays_out) *rays_out = rays;
     return 0;

@@ -64,6 +64,10 @@ class SimScene:
             lib().hostsim_raycast(self._h, C.byref(params), fp)
         elif renderer == "ao":
             lib().hostsim_ao(self._h, C.byref(params), fp)
+        elif renderer == "lt":
+            rays = C.c_longlong()
+            lib().hostsim_lt(self._h, C.byref(params), fp, C.byref(rays))
+            self.rays = rays.value
         else:
             rays = C.c_longlong()
             lib().hostsim_pt(self._h, C.byref(params), fp, C.byref(rays))

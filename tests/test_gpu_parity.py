@@ -622,3 +622,32 @@ def test_full_size_properties_c4():
     assert np.isfinite(film).all() and st["paths"] == 320 * 180 * 16
     assert 0.05 < film.mean() < 1.0 + 1e-3          # Le = 1 sky, all albedos < 1 (glass eta^2 factors cancel on exit)
     sc.close()
+
+
+@pytest.mark.parametrize("scene", ["spheres", "env", "delta", "obj"])
+def test_g3_lt_vs_reference(reference, tmp_path, scene):
+    """SURVEY.md 8f N4: renderer::lt on the device (lmcu_render_lt) against the reference's renderer::lt at equal sample
+    counts — area light + glass / diffuse, constant environment + glossy / mirror, point + directional lights, the
+    OBJ-import material set.  G3 gates: image means, block z-test, RMSE against the Monte-Carlo prediction."""
+    sb = {"spheres": lambda: scenes.cornell_spheres(32), "env": lambda: scenes.instanced_spheres(grid=2, num_theta=24),
+          "delta": lambda: scenes.delta_lights_scene(2, 16), "obj": lambda: scenes.textured_scene(tmp_path, 12, "obj")}[scene]()
+    sc, rs = lmcu.Scene(sb), reference.RefScene(sb)
+    w, h, B, spp = 160, 90, 4, 64
+    n = w * h * spp
+    img = dict(max_verts=12, num_samples=n, primary_ray_sampling_mode=abi.PRIMARY_IMAGE)
+    R = np.stack([rs.render("renderer::lt", abi.render_params(w, h, seed=42 + b, **img))[0] for b in range(B)])
+    G = np.stack([sc.render("lt", abi.render_params(w, h, sample_offset=b * n, **img))[0] for b in range(B)])
+    assert G.mean() > 0.005
+    assert_pt_parity(R.mean(axis=0), G.mean(axis=0), B * spp, rel_mean=0.02)
+    assert_pt_rmse(R, G, k=1.25)
+    # sample-split additivity: two halves rendered as sums add up to the whole (same counter-RNG streams)
+    whole, st = sc.render("lt", abi.render_params(w, h, **img))
+    assert st["processed"] == n
+    parts = [sc.render("lt", abi.render_params(w, h, max_verts=12, num_samples=n // 2, sample_offset=k * (n // 2), rescale=0,
+                                               primary_ray_sampling_mode=abi.PRIMARY_IMAGE))[0] for k in range(2)]
+    assert np.allclose((parts[0] + parts[1]) * (w * h / n), whole, rtol=1e-4, atol=1e-5)
+    # time scheduler: a budget buys at least the first full pass and the image stays the same image
+    ft, st = sc.render("lt", abi.render_params(w, h, max_verts=12, scheduler=abi.SCHED_TIME, render_time=0.05, primary_ray_sampling_mode=abi.PRIMARY_IMAGE))
+    assert st["processed"] > 0 and st["elapsed"] >= 0.04
+    assert abs(ft.mean() - whole.mean()) < 0.03 * whole.mean()
+    rs.close(); sc.close()

@@ -348,3 +348,19 @@ def test_save_state_round_trip_with_cuda_components(plugin, tmp_path, monkeypatc
     assert ref_before.max() > 0 and np.array_equal(ref_before, ref_after)
     assert img_before.max() > 0 and np.array_equal(img_before, img_after)
     rc.close()
+
+
+def test_renderer_lt_cuda(plugin):
+    """renderer::lt_cuda created by the reference from renderer::lt's own JSON keys, against renderer::lt."""
+    sb = scenes.cornell_spheres(24)
+    rs = plugin.RefScene(sb)
+    w, h, spp = 160, 90, 128
+    p = abi.render_params(w, h, max_verts=12, num_samples=w * h * spp, primary_ray_sampling_mode=abi.PRIMARY_IMAGE)
+    fr, _, pr = rs.render("renderer::lt", p)
+    fc, _, pc = rs.render("renderer::lt_cuda", p)
+    assert pr == pc == w * h * spp
+    assert_pt_parity(fr, fc, spp, rel_mean=0.02)
+    pt = abi.render_params(w, h, max_verts=12, scheduler=abi.SCHED_TIME, render_time=0.05, primary_ray_sampling_mode=abi.PRIMARY_IMAGE)
+    ft, elapsed, proc = rs.render("renderer::lt_cuda", pt)
+    assert proc % 100000 == 0 and proc > 0 and abs(ft.mean() - fr.mean()) < 0.03 * fr.mean()
+    rs.close()

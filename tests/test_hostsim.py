@@ -219,3 +219,18 @@ def test_scene_description_validation(sim):
     sb = scenes.cornell_box(); sb.add_texture(np.zeros((2, 2, 3), np.float32)); sb.textures[0]["data"] = np.zeros((2, 2, 3), np.float32)[:, :, :2]
     with pytest.raises((RuntimeError, AssertionError, ValueError)):
         sim.SimScene(sb)
+
+
+@pytest.mark.parametrize("scene", ["spheres", "env"])
+def test_lt_statistics(reference, sim, scene):
+    """The light tracer's device code (lt_generate_body / lt_shade_body: Light::sample_ray of every light type, LE transport
+    through the BSDFs, camera connections splatted at their raster position) against the reference's renderer::lt."""
+    sb = scenes.cornell_spheres(12) if scene == "spheres" else scenes.instanced_spheres(grid=2, num_theta=10)
+    rs, ss = reference.RefScene(sb), sim.SimScene(sb)
+    w, h, spp = 64, 36, 48
+    p = abi.render_params(w, h, max_verts=10, num_samples=w * h * spp, primary_ray_sampling_mode=abi.PRIMARY_IMAGE)
+    fr, _, processed = rs.render("renderer::lt", p)
+    assert processed == w * h * spp
+    fs = ss.render("lt", p)
+    assert_pt_parity(fr, fs, spp, rel_mean=0.02)
+    rs.close()
