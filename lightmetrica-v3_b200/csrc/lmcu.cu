@@ -809,6 +809,7 @@ struct LmcuScene {
     uint32_t pt_capacity = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int fetch_threshold = 12;            // LMCU_FETCH
+    uint32_t path_chunk = 64;            // LMCU_CHUNK: samples of one pixel on consecutive path indices (kernels.cuh path_pixel)
     int pool_mode = 0;                   // LMCU_TRACE=pool: the queue kernels run on the shared-memory ray pool (trace2.cuh)
     int pool_refill = 16;                // LMCU_POOL_FETCH
     DBuf<uint2> batch_arena;             // pool mode: traversal stacks of the accel-batch kernel
@@ -864,6 +865,7 @@ int lmcu_scene_create(int device, LmcuScene** out) {
     if (const char* e = getenv("LMCU_FETCH")) s->fetch_threshold = atoi(e);
     if (const char* e = getenv("LMCU_TRACE")) s->pool_mode = std::string(e) == "pool" ? 1 : 0;
     if (const char* e = getenv("LMCU_POOL_FETCH")) s->pool_refill = std::max(1, atoi(e));
+    if (const char* e = getenv("LMCU_CHUNK")) { uint32_t c = 1; while (c * 2 <= (uint32_t)std::max(1, atoi(e)) && c < 4096) c *= 2; s->path_chunk = c; }
     if (const char* e = getenv("LMCU_CTAS")) s->ctas_per_sm = std::max(1, atoi(e));
     if (const char* e = getenv("LMCU_SHADE_GRID")) s->shade_ctas_per_sm = std::max(1, atoi(e));
     if (const char* e = getenv("LMCU_WAVES")) s->default_waves = std::min((int)LmcuScene::kMaxWaves, std::max(1, atoi(e)));
@@ -1921,6 +1923,9 @@ static int render_paths(LmcuScene* s, const LmcuRenderParams* p, float* film_rgb
     auto run_units = [&](int64_t units) -> int {
         pp.sample_offset = (uint64_t)p->sample_offset + (uint64_t)processed;
         pp.total_paths = paths_per_unit * (uint64_t)units;
+        // pixel mode: samples of a pixel are walked in chunks of the largest power of two <= 16 that divides this pass
+        pp.chunk = 1u;
+        if (!image) { uint32_t c = s->path_chunk; while (c > 1u && (units % c) != 0) c >>= 1; pp.chunk = c; }
         acc.paths_before = (int64_t)(paths_per_unit * (uint64_t)processed);
         acc.paths_total = timed ? 0 : (int64_t)pp.total_paths;
         const int r = pt_pass(s, pp, count, acc);

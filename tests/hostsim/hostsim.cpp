@@ -304,6 +304,8 @@ int hostsim_pt(void* p, const LmcuRenderParams* rp, float* film, long long* rays
     pp.image_mode = image ? 1u : 0u;
     pp.total_paths = image ? (uint64_t)rp->num_samples : (uint64_t)rp->width * rp->height * (uint64_t)rp->spp;
     pp.capacity = 1;
+    pp.chunk = 1;
+    if (!image) { uint32_t c = 16; while (c > 1u && (rp->spp % c) != 0) c >>= 1; pp.chunk = c; }
     const size_t npix = (size_t)rp->width * rp->height;
     std::vector<double> acc(npix * 3, 0.0);
     float4 ro, rd, tp, aux; uint2 info;

@@ -165,7 +165,7 @@ def test_accel_save_load_round_trip(tmp_path):
     # every index is range-checked on the host before anything reaches the device
     import struct
     raw = bytearray(blob)
-    hdr = 8 + 6 * 4 + 3 * 8
+    hdr = 8 + 6 * 4 + 3 * 8 + 6 * 4 + 2 * 4             # AccelBlobHeader: magic, 6 counts, payload bytes, checksum, digest, bounds, pad
     struct.pack_into("<I", raw, hdr + 16, 0x7fffffff)       # WideNode 0: child_base
     _rechecksum(raw, hdr)
     with pytest.raises(lmcu.LmcuError) as e:

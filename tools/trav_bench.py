@@ -27,6 +27,7 @@ from lmcu import abi, scenes  # noqa: E402
 SPP = int(os.environ.get("TB_SPP", "32"))
 C3_N = int(os.environ.get("TB_C3", "2236"))
 C3_RES = int(os.environ.get("TB_C3_RES", "2048"))
+TB_W, TB_H = int(os.environ.get("TB_W", "1920")), int(os.environ.get("TB_H", "1080"))
 
 
 def tri_normals(sb):
@@ -69,11 +70,11 @@ def main():
         print("== %s" % setting, flush=True)
         sc = lmcu.Scene(c2)
         for i in range(2):
-            _, st = sc.render("pt", abi.render_params(1920, 1080, spp=SPP, max_verts=20), download=False)
+            _, st = sc.render("pt", abi.render_params(TB_W, TB_H, spp=SPP, max_verts=20), download=False)
         print("  C2 pt %d spp: %.1f Mpaths/s  %.1f Mrays/s | extend %.4f shade %.4f shadow %.4f total %.4f s | launches %d" % (
             SPP, st["paths"] / st["elapsed"] / 1e6, st["rays"] / st["elapsed"] / 1e6, st["extend_seconds"],
             st["shade_seconds"], st["shadow_seconds"], st["elapsed"], st["kernel_launches"]), flush=True)
-        film = sc.film_download(1920, 1080)
+        film = sc.film_download(TB_W, TB_H)
         print("  C2 film mean %s" % (film.mean(axis=(0, 1)) / SPP), flush=True)
         rays = scenes.camera_rays(c2.camera, 1920, 1080)
         mr, hits = device_batch(sc, rays)
