@@ -42,6 +42,20 @@
 
 using namespace lmcu;
 
+// The path / shadow queues and the hit records are written once and read once per iteration (2.4 GB per wavefront iteration):
+// streaming loads / stores (ld.global.cs / st.global.cs: evict-first) keep them from pushing BVH nodes, triangles and film
+// lines out of L1 / L2.  LMCU_STREAM_IO=0 builds the plain accesses (A/B).
+#ifndef LMCU_STREAM_IO
+#define LMCU_STREAM_IO 1
+#endif
+#if LMCU_STREAM_IO
+#define Q_LD(p) __ldcs(p)
+#define Q_ST(p, v) __stcs(p, v)
+#else
+#define Q_LD(p) (*(p))
+#define Q_ST(p, v) (*(p) = (v))
+#endif
+
 // ================================================================================================
 // error handling
 // ================================================================================================
@@ -408,20 +422,21 @@ __global__ void __launch_bounds__(LMCU_SHADE_BLOCK, LMCU_SHADE_MINB) k_pt_shade(
         ShadeOut o;
         o.alive = false; o.shadow = false;
         if (i < n) {
-            o = pt_shade_body<COMPOSITE>(s, p, qin.ray_o[i], qin.ray_d[i], qin.thr_pix[i], qin.aux[i], qin.info[i], hits[i]);
+            const float4 tp = Q_LD(qin.thr_pix + i);
+            o = pt_shade_body<COMPOSITE>(s, p, Q_LD(qin.ray_o + i), Q_LD(qin.ray_d + i), tp, Q_LD(qin.aux + i), Q_LD(qin.info + i), Q_LD(hits + i));
             if (!is_zero(o.emit)) {
-                float* px = film + (size_t)f2u(qin.thr_pix[i].w) * 3;
+                float* px = film + (size_t)f2u(tp.w) * 3;
                 atomicAdd(px + 0, o.emit.x); atomicAdd(px + 1, o.emit.y); atomicAdd(px + 2, o.emit.z);
             }
         }
         uint32_t pos, spos;
         block_compact2(o.alive, o.shadow, &ctr->count[cur ^ 1], &ctr->shadow_count, smem[tile], pos, spos);
         if (o.alive) {
-            qout.ray_o[pos] = o.o; qout.ray_d[pos] = o.d; qout.thr_pix[pos] = o.thr_pix; qout.aux[pos] = o.aux;
-            qout.info[pos] = o.info;
+            Q_ST(qout.ray_o + pos, o.o); Q_ST(qout.ray_d + pos, o.d); Q_ST(qout.thr_pix + pos, o.thr_pix); Q_ST(qout.aux + pos, o.aux);
+            Q_ST(qout.info + pos, o.info);
         }
         if (o.shadow) {
-            sq.ray_o[spos] = o.sh_o; sq.ray_d[spos] = o.sh_d; sq.contrib[spos] = o.sh_c;
+            Q_ST(sq.ray_o + spos, o.sh_o); Q_ST(sq.ray_d + spos, o.sh_d); Q_ST(sq.contrib + spos, o.sh_c);
         }
     }
 }
@@ -474,7 +489,7 @@ struct ExtendIO {                      // pt extend: path queue in, float4 hit r
     const float4* ray_o; const float4* ray_d;
     float4* hits;
     __device__ __forceinline__ bool load(uint32_t i, RayD& r, RayF& f, float& tmin_dn, float& tmax_up) const {
-        const float4 o = ray_o[i], d = ray_d[i];
+        const float4 o = Q_LD(ray_o + i), d = Q_LD(ray_d + i);
         r.o = d3(o.x, o.y, o.z); r.d = d3(d.x, d.y, d.z); r.tmin = o.w; r.tmax = d.w;
         f = make_rayf_f(o.x, o.y, o.z, d.x, d.y, d.z);          // the queue holds float rays: exact in both views
         tmin_dn = o.w; tmax_up = d.w;
@@ -484,7 +499,7 @@ struct ExtendIO {                      // pt extend: path queue in, float4 hit r
         // the path tracer shades in FP32: the barycentrics are formed in FP32 here (two FP64 divisions cost ~60
         // instructions at the 2-3 lanes that finish per iteration, 14 % of this kernel's issue slots)
         const float inv = tri >= 0 ? __frcp_rn((float)ad) : 0.f;
-        hits[i] = make_float4((float)t, (float)u_raw * inv, (float)v_raw * inv, __int_as_float(tri));
+        Q_ST(hits + i, make_float4((float)t, (float)u_raw * inv, (float)v_raw * inv, __int_as_float(tri)));
     }
 };
 
@@ -501,7 +516,7 @@ struct ShadowIO {                      // pt shadow: visible (include/lm/scene.h
     const float4* ray_o; const float4* ray_d; const float4* contrib;
     float* film;
     __device__ __forceinline__ bool load(uint32_t i, RayD& r, RayF& f, float& tmin_dn, float& tmax_up) const {
-        const float4 o = ray_o[i], d = ray_d[i];
+        const float4 o = Q_LD(ray_o + i), d = Q_LD(ray_d + i);
         r.o = d3(o.x, o.y, o.z); r.d = d3(d.x, d.y, d.z); r.tmin = o.w; r.tmax = d.w;
         f = make_rayf_f(o.x, o.y, o.z, d.x, d.y, d.z);          // the queue holds float rays: exact in both views
         tmin_dn = o.w; tmax_up = d.w;
@@ -509,7 +524,7 @@ struct ShadowIO {                      // pt shadow: visible (include/lm/scene.h
     }
     __device__ __forceinline__ void store(uint32_t i, double, double, double, double, int32_t tri) const {
         if (tri < 0) {
-            const float4 c = contrib[i];
+            const float4 c = Q_LD(contrib + i);
             float* px = film + (size_t)__float_as_uint(c.w) * 3;
             atomicAdd(px + 0, c.x); atomicAdd(px + 1, c.y); atomicAdd(px + 2, c.z);
         }
@@ -974,6 +989,9 @@ int lmcu_accel_build(LmcuScene* s, const LmcuBuildOptions* opts, LmcuBuildStats*
     DBuf<BinNode> bin;
     DBuf<WideNode> wide;
     DBuf<CollapseItem> queue[2];
+    // declared after the temporaries => destroyed before them: on an early error return kernels may still be running on
+    // the stream, and a block parked in the cache while a kernel writes it could be handed to the next allocation
+    struct SyncOnExit { cudaStream_t st; ~SyncOnExit() { cudaStreamSynchronize(st); cudaGetLastError(); } } sync_on_exit{ st };
     CU(wp.alloc((size_t)nt * 9)); CU(centre.alloc((size_t)nt * 3));
     CU(tri_lo.alloc((size_t)nt * 3)); CU(tri_hi.alloc((size_t)nt * 3));
     CU(bounds.alloc(6)); CU(exact.alloc(1));

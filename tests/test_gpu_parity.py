@@ -248,6 +248,26 @@ def test_accel_scalar_and_concurrent_batches():
     sc.close()
 
 
+def test_pool_traversal_variant_is_bit_identical(monkeypatch):
+    """trace2.cuh (LMCU_TRACE=pool: K = 2 rays per lane in a shared-memory pool, one phase per warp iteration) is an opt-in
+    scheduling variant of the same arithmetic: hits identical to the default kernel bit for bit, same pt image up to the
+    order of the film's atomic adds.  (Measured slower on B200 — profiles/r02_ncu_summary.md — hence opt-in.)"""
+    sb = scenes.cornell_spheres(24)
+    rays = np.concatenate([scenes.camera_rays(sb.camera, 320, 180), scenes.random_rays(60000, np.array([-1, 0, -1.]), np.array([1, 2, 1.]))])
+    p = abi.render_params(160, 90, spp=32, max_verts=12)
+    a = lmcu.Scene(sb)
+    ha = a.intersect(rays)
+    fa, _ = a.render("pt", p)
+    a.close()
+    monkeypatch.setenv("LMCU_TRACE", "pool")
+    b = lmcu.Scene(sb)
+    hb = b.intersect(rays)
+    fb, _ = b.render("pt", p)
+    b.close()
+    assert all(np.array_equal(ha[k], hb[k]) for k in ("t", "u", "v", "primitive", "face"))
+    assert np.allclose(fa, fb, rtol=1e-4, atol=1e-5)
+
+
 def test_g1_edge_cases(reference):
     """The edge-case batches of tests/edge_cases.py through the CUDA queue traversal (k_intersect_q)."""
     import edge_cases
