@@ -186,6 +186,7 @@ struct CollapseCtx {
     const uint32_t* sorted_tri;  // sorted leaf position -> global triangle id
     int n;                       // number of triangles
     int max_leaf;                // triangles per leaf slot (1..3)
+    int width;                   // children per wide node (2..8; 8 = the shipped layout; fewer leaves slots empty: probe only)
     WideNode* wide;
     uint32_t* tri_order;         // leaf-order position -> global triangle id
     uint32_t* node_counter;      // next free wide node
@@ -216,7 +217,8 @@ LMCU_HD void collapse_body(const CollapseCtx& c, CollapseItem item) {
         // Area-greedy opening leaves 3.7 of 8 slots occupied on C2, yet a variant that kept subtrees of <= 16..24
         // triangles whole as dense bottom nodes cut the node count by 22 % and RAISED nodes/ray by 10 % (hostsim
         // counters, round 1) — the large-area-first order is what keeps the visited set small.
-        while (nch < 8) {                 // open the child with the largest surface area
+        const int W = c.width >= 2 && c.width <= 8 ? c.width : 8;
+        while (nch < W) {                 // open the child with the largest surface area
             int best = -1;
             float best_area = -1.f;
             for (int k = 0; k < nch; k++) {
@@ -232,7 +234,7 @@ LMCU_HD void collapse_body(const CollapseCtx& c, CollapseItem item) {
         }
         // Bottom nodes: every child is a leaf cluster now and slots are left over.  Split the clusters (largest area
         // first) down to single triangles while slots remain: same node, tighter leaf boxes, fewer FP64 triangle tests.
-        while (nch < 8) {
+        while (nch < W) {
             int best = -1;
             float best_area = -1.f;
             for (int k = 0; k < nch; k++) {

@@ -1036,6 +1036,7 @@ int lmcu_accel_build(LmcuScene* s, const LmcuBuildOptions* opts, LmcuBuildStats*
     while (count > 0) {
         CollapseCtx c;
         c.bin = bin.p; c.sorted_tri = vals_sorted.p; c.n = (int)nt; c.max_leaf = max_leaf; c.wide = wide.p;
+        c.width = 8;
         c.tri_order = tri_order.p; c.node_counter = counters.p; c.tri_counter = counters.p + 1;
         c.next_queue = queue[cur ^ 1].p; c.next_count = counters.p + 2;
         k_collapse<<<grid_for(count, 128), 128, 0, st>>>(c, queue[cur].p, count);

@@ -228,6 +228,7 @@ int hostsim_scene_create(const LmcuSceneDesc* d, int max_leaf, void** out, long 
     while (count > 0) {
         CollapseCtx c;
         c.bin = bin.data(); c.sorted_tri = vals_sorted.data(); c.n = (int)nt; c.max_leaf = max_leaf; c.wide = wide.data();
+        c.width = getenv("HOSTSIM_WIDTH") ? atoi(getenv("HOSTSIM_WIDTH")) : 8;
         c.tri_order = tri_order.data(); c.node_counter = &counters[0]; c.tri_counter = &counters[1];
         c.next_queue = queue[cur ^ 1].data(); c.next_count = &counters[2];
         for (uint32_t i = 0; i < count; i++) collapse_body(c, queue[cur][i]);
