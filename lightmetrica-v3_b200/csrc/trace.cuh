@@ -47,6 +47,7 @@ __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, 
 
     // per-lane traversal state
     bool active = false;
+    bool pending = false;         // the ray of this lane is finished, its result not yet stored (see the fetch block)
     bool exhausted = false;       // the cursor ran past n: nothing left to fetch
     uint32_t idx = 0;
     RayD r; r.o = d3(0, 0, 0); r.d = d3(0, 0, 1); r.tmin = 0; r.tmax = 0;
@@ -58,6 +59,15 @@ __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, 
     int sp = 0;
 
     while (true) {
+        // ---- results of the rays that finished since the last visit here.  A lane keeps its finished ray's (t, u, v, |det|,
+        // triangle) in its registers and stores them HERE, together with the other lanes that finished, instead of at the
+        // moment it finishes: inside the traversal loop 2-3 lanes finish per iteration, so the IO policy's store — two exact
+        // FP64 divisions, a triangle and a primitive-table fetch for accel batches — ran at 2-3 of 32 lanes almost every
+        // iteration; here it runs once per refill for >= fetch_threshold lanes.
+        if (pending) {
+            io.store(idx, ht, hu, hv, had, htri);
+            pending = false;
+        }
         // ---- fetch: idle lanes claim the next rays of the queue -------------------------------------
         if (!exhausted) {
             const uint32_t idle = __ballot_sync(0xffffffffu, !active);
@@ -113,9 +123,8 @@ __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, 
                         tgroup.x = n1.y;
                         tgroup.y = hm & 0x00ffffffu;
                     } else {
-                        // ---- nothing left: this ray is done.  The IO policy finishes the barycentrics (u, v = raw / |det|):
-                        // only a few lanes are here at a time, so what it costs is paid at ~3/32 occupancy
-                        io.store(idx, ht, hu, hv, had, htri);
+                        // ---- nothing left: this ray is done; its result is stored at the next refill (top of the outer loop)
+                        pending = true;
                         active = false;
                     }
                 }
@@ -144,7 +153,7 @@ __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, 
                             ht = t; hu = u; hv = v; had = ad; htri = (int32_t)tri;
                             tmax_up = f32_up(t);
                             if (ANY) {
-                                io.store(idx, t, u, v, ad, htri);
+                                pending = true;
                                 active = false;
                             }
                         }
