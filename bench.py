@@ -273,6 +273,15 @@ def c1_rates(lmcu, abi, scenes, stream):
     return {"ms": best * 1e3, "mrays_per_s": W * H / best / 1e6}
 
 
+def lt_rate(sc, abi):
+    """renderer::lt on the device (SURVEY.md 8f N4): light paths per second on the C2 scene, 1920x1080, 64 light paths per pixel."""
+    n = W * H * 64
+    p = abi.render_params(W, H, max_verts=MAX_VERTS, seed=SEED, num_samples=n, primary_ray_sampling_mode=abi.PRIMARY_IMAGE)
+    sc.render("lt", abi.render_params(W, H, max_verts=MAX_VERTS, seed=SEED, num_samples=n // 8, primary_ray_sampling_mode=abi.PRIMARY_IMAGE), download=False)
+    _, st = sc.render("lt", p, download=False)
+    return {"light_paths": n, "mpaths_per_s": st["paths"] / st["elapsed"] / 1e6, "mrays_per_s": st["rays"] / st["elapsed"] / 1e6}
+
+
 def plugin_e2e(sb, abi, spp, paths):
     """The drop-in path a Lightmetrica user calls: the UNMODIFIED reference (oracle/_ref/liblm.so) loads plugin/lm_cuda.so,
     holds the scene as its own lm::Scene, creates renderer::pt_cuda from JSON and calls Renderer::render(); the image comes
@@ -550,7 +559,8 @@ def run_ours(args):
         }
         configs = {}
         if world == 1 and not args.no_configs:
-            for name, fn in (("C1_raycast", lambda: c1_rates(lmcu, abi, scenes, stream)),
+            for name, fn in (("C2_lt", lambda: lt_rate(sc, abi)),
+                             ("C1_raycast", lambda: c1_rates(lmcu, abi, scenes, stream)),
                              ("C3_accel", lambda: accel_rates(torch, lmcu, scenes, stream, peak)),
                              ("C4_pt", lambda: c4_rates(lmcu, abi, scenes, stream, peak))):
                 try:
