@@ -934,6 +934,9 @@ int lmcu_scene_upload(LmcuScene* s, const LmcuSceneDesc* d) {
         CU(cudaMemcpy(s->mesh_p.p + (size_t)ps.face_offset[i] * 9, d->meshes[i].p, bytes, cudaMemcpyHostToDevice));
         if (d->meshes[i].n) {
             CU(cudaMemcpy(s->mesh_n.p + (size_t)ps.face_offset[i] * 9, d->meshes[i].n, bytes, cudaMemcpyHostToDevice));
+        } else {
+            // never read by the kernels (has_normals = 0), but part of the description digest of lmcu_accel_save / load
+            CU(cudaMemset(s->mesh_n.p + (size_t)ps.face_offset[i] * 9, 0, bytes));
         }
     }
     s->h_prims = ps.prims;

@@ -161,6 +161,18 @@ def test_accel_save_load_round_trip(tmp_path):
             lmcu.Scene(other, accel_blob=blob)
         assert e.value.code == 1 and "other geometry" in str(e.value)
     lmcu.Scene(scenes.instanced_spheres(grid=2, num_theta=8), accel_blob=blob).close()
+    # a mesh without vertex normals (the geometric normal is used): its unused normal slots must not leak into the digest
+    tri = scenes._f32(np.random.RandomState(4).rand(40, 3, 3) * 2 - 1)
+    def flat():
+        sb = scenes.SceneBuilder()
+        sb.add_primitive(sb.add_mesh(tri), sb.diffuse((.5, .5, .5)))
+        sb.set_camera(position=(0, 0, 4), center=(0, 0, 0), up=(0, 1, 0), vfov=40, aspect=1)
+        return sb
+    keep = [lmcu.Scene(scenes.cornell_spheres(8)) for _ in range(2)]          # churn the allocator between the two scenes
+    blob2 = lmcu.Scene(flat()).save_accel()
+    for k in keep:
+        k.close()
+    lmcu.Scene(flat(), accel_blob=blob2).close()
     # a blob whose checksum is right but whose indices point outside its own arrays (a writer of another version):
     # every index is range-checked on the host before anything reaches the device
     import struct
