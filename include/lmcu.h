@@ -261,7 +261,7 @@ int lmcu_scene_upload(LmcuScene* scene, const LmcuSceneDesc* desc);
 int lmcu_accel_build(LmcuScene* scene, const LmcuBuildOptions* opts, LmcuBuildStats* stats);
 /* Closest hit for a batch of rays in HOST memory (replaces accel_sahbvh.cpp:269-299 per ray). */
 int lmcu_accel_intersect(LmcuScene* scene, const LmcuRay* rays, int64_t n, LmcuHit* hits);
-/* ONE ray: the scalar lm::Accel::intersect contract (include/lm/accel.h:70; called concurrently from every OpenMP
+/* ONE ray: the scalar lm::Accel::intersect contract (include/lm/accel.h:70, served by accel_sahbvh.cpp:269-299; called concurrently from every OpenMP
  * thread by Scene::intersect, src/scene.cpp:320).  Thread-safe and lock-free: each calling thread owns a pinned,
  * device-mapped (ray, hit) slot and a stream; a call is one kernel launch and one stream synchronise, no allocation
  * and no memcpy.  Same hit, bit for bit, as lmcu_accel_intersect. */
@@ -319,7 +319,8 @@ int lmcu_ipc_open(int device, const void* handle, void** d_ptr);
 int lmcu_ipc_close(int device, void* d_ptr);
 int lmcu_enable_peer_access(int device, int peer_device);
 int lmcu_film_reduce_peers(LmcuScene* root, void* const* peer_films, int num_peers, double scale);
-/* Slice-parallel form of the same combine (one call per GPU, all at once): out[i] = scale * sum_k films[k][i] for
+/* Slice-parallel form of the same combine (one call per GPU, all at once) — the multi-GPU counterpart of Film::accum +
+ * Film::rescale (src/film/film_bitmap.cpp:220-234,244-248): out[i] = scale * sum_k films[k][i] for
  * i in [begin, end).  `films` = this GPU's own film and the peers' films (peer-mapped), `out` = the root's film
  * (peer-mapped on every GPU but the root; it may also be one of `films`).  With the film cut into G slices no GPU
  * receives more than (G-1)/G of a film and all NVLink ports work at once, where lmcu_film_reduce_peers pulls G-1 whole
