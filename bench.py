@@ -127,6 +127,17 @@ def reference_rate(spp, steps, warmup, rs=None):
     return W * H * spp / t / 1e6, t, threads, films
 
 
+def workload_config(world, reduce, spp=None):
+    """`config` of the JSON line, shared by both arms (the reference arm runs a bounded sample of the same workload)."""
+    spp = GPU_SPP if spp is None else spp
+    return {"workload": "C2 renderer::pt Cornell box + diffuse/glass UV spheres (32268 tris) 1920x1080 "
+                        "max_verts=20 sampling_mode=mis seed=42", "spp_per_gpu": spp, "total_spp": spp * world,
+            "parallelism": "sample split x%d, film combine = %s" % (world, REDUCE_NAMES[reduce]),
+            "wavefronts": 2,
+            "l2": "inputs larger than L2: every wavefront iteration streams its 16 Mi-path SoA queues "
+                  "(2.4 GB) through HBM, and every step regenerates all paths"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -141,8 +152,11 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "Mpaths/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C2 renderer::pt Cornell box + diffuse/glass spheres 1920x1080 max_verts=20 mis, "
-                               "reference CPU path (accel::sahbvh, parallel::openmp)", "spp_per_step": REF_SPP_PER_STEP},
+        # the same `config` as our arm prints for this N: it names the workload both arms are quoted on; what THIS arm ran of it
+        # (a bounded sample on the host cores) is in `reference_run` and `cpu_baseline.sample`
+        "config": workload_config(max(1, args.gpus), args.reduce),
+        "reference_run": {"implementation": "unmodified reference: accel::sahbvh + renderer::pt under parallel::openmp "
+                                            "(oracle/_ref/liblm.so)", "spp_per_step": REF_SPP_PER_STEP, "threads": threads},
         "cpu_baseline": {"value": value, "unit": "Mpaths/s", "cores": threads, "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -626,12 +640,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32 shading / f64 ray-triangle / f64 film sums", "data": "synthetic",
-            "config": {"workload": "C2 renderer::pt Cornell box + diffuse/glass UV spheres (32268 tris) 1920x1080 "
-                                   "max_verts=20 sampling_mode=mis seed=42", "spp_per_gpu": spp, "total_spp": spp * world,
-                       "parallelism": "sample split x%d, film combine = %s" % (world, REDUCE_NAMES[args.reduce]),
-                       "wavefronts": 2,
-                       "l2": "inputs larger than L2: every wavefront iteration streams its 16 Mi-path SoA queues "
-                             "(2.4 GB) through HBM, and every step regenerates all paths"},
+            "config": workload_config(world, args.reduce, spp),
             "mrays_per_s": rays * world / (ms_total * 1e-3) / 1e6,
             "e2e": e2e, "gpu_launches": int(sum(s["kernel_launches"] for s in stats)) + args.steps,
             "roofline": roofline, "cpu_baseline": cpu, "parity_c2": parity_c2, "multi_gpu_check": multi_check,
