@@ -296,6 +296,33 @@ def lt_rate(sc, abi):
     return {"light_paths": n, "mpaths_per_s": st["paths"] / st["elapsed"] / 1e6, "mrays_per_s": st["rays"] / st["elapsed"] / 1e6}
 
 
+def bdpt_rate(sc, abi, sb):
+    """renderer::bdpt on the device (SURVEY.md 8f N4, the other integrators): samples (one eye + one light subpath, all
+    connections) per second on the C2 scene, 1920x1080, max_verts 10 (functest/func_renderers.py:51), 8 samples per pixel;
+    beside it the reference's renderer::bdpt on the host cores on a bounded sample (1/4 sample per pixel)."""
+    mv = 10
+    n = W * H * 8
+    kw = dict(max_verts=mv, seed=SEED, primary_ray_sampling_mode=abi.PRIMARY_IMAGE)
+    sc.render("bdpt", abi.render_params(W, H, num_samples=n // 8, **kw), download=False)
+    film, st = sc.render("bdpt", abi.render_params(W, H, num_samples=n, **kw))
+    out = {"samples": n, "max_verts": mv, "msamples_per_s": st["paths"] / st["elapsed"] / 1e6,
+           "mrays_per_s": st["rays"] / st["elapsed"] / 1e6, "rays_per_sample": st["rays"] / st["paths"],
+           "kernel": "k_bdpt: one sample per thread (both subpaths, every connection, O(n) MIS weight per connection)"}
+    try:
+        from oracle import ref
+        if ref.available():
+            threads = ref.init(0)
+            rs = ref.RefScene(sb)
+            nr = W * H // 4
+            fr, elapsed, processed = rs.render("renderer::bdpt", abi.render_params(W, H, num_samples=nr, **kw))
+            out["cpu_reference"] = {"samples": int(processed), "msamples_per_s": processed / elapsed / 1e6, "threads": threads,
+                                    "rel_mean_diff": float(abs(film.mean() - fr.mean()) / fr.mean())}
+            rs.close()
+    except Exception as ex:
+        out["cpu_reference"] = {"failed": str(ex)}
+    return out
+
+
 def plugin_e2e(sb, abi, spp, paths):
     """The drop-in path a Lightmetrica user calls: the UNMODIFIED reference (oracle/_ref/liblm.so) loads plugin/lm_cuda.so,
     holds the scene as its own lm::Scene, creates renderer::pt_cuda from JSON and calls Renderer::render(); the image comes
@@ -574,6 +601,7 @@ def run_ours(args):
         configs = {}
         if world == 1 and not args.no_configs:
             for name, fn in (("C2_lt", lambda: lt_rate(sc, abi)),
+                             ("C2_bdpt", lambda: bdpt_rate(sc, abi, sb)),
                              ("C1_raycast", lambda: c1_rates(lmcu, abi, scenes, stream)),
                              ("C3_accel", lambda: accel_rates(torch, lmcu, scenes, stream, peak)),
                              ("C4_pt", lambda: c4_rates(lmcu, abi, scenes, stream, peak))):

@@ -197,6 +197,8 @@ typedef struct LmcuRenderParams {
      * (src/scheduler.cpp:45,91,133,173).  NULL = no reports. */
     void (*progress)(void* user, int64_t processed_paths, int64_t total_paths, double elapsed_seconds);
     void* progress_user;
+    int32_t min_verts;                       /* bdpt: minimum number of path vertices (0 = 2, renderer_bdpt.cpp:51) */
+    int32_t reserved_;
 } LmcuRenderParams;
 
 typedef struct LmcuRenderStats {
@@ -295,6 +297,12 @@ int lmcu_render_pt(LmcuScene* scene, const LmcuRenderParams* p, float* film_rgb,
  * scheduler (sample: num_samples light paths; time: render_time, samples_per_iter), sample_offset, rescale (film *=
  * w*h/processed, :162); the scheduler is always the image-space one (:44-47), primary_ray_sampling_mode and spp are ignored. */
 int lmcu_render_lt(LmcuScene* scene, const LmcuRenderParams* p, float* film_rgb, LmcuRenderStats* stats);
+/* renderer::bdpt (src/renderer/renderer_bdpt.cpp:304-407, include/lm/bidir.h): per sample one eye and one light subpath of up
+ * to max_verts vertices (no Russian roulette), every connection (s, t) with min_verts <= s + t <= max_verts, power-heuristic
+ * weights over all strategies of the connected path.  Keys used: max_verts (2..20), min_verts (0 = 2), seed, scheduler (sample:
+ * num_samples; time: render_time, samples_per_iter), sample_offset, rescale (film *= w*h/processed, :390-391).  Image-space
+ * scheduler only (renderer_bdpt.cpp:54-56).  LMCU_ERR_UNSUPPORTED for scenes with textured or mixture materials. */
+int lmcu_render_bdpt(LmcuScene* scene, const LmcuRenderParams* p, float* film_rgb, LmcuRenderStats* stats);
 /* Device film of the last render (width*height*3 floats) for the multi-GPU film reduce
  * (sample split: every rank renders with rescale=0, NCCL-reduces this buffer, then scales). */
 int lmcu_film_device_ptr(LmcuScene* scene, void** d_film, int64_t* num_floats);

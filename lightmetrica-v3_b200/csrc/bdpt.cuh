@@ -1,0 +1,421 @@
+// bdpt.cuh — bidirectional path tracing, one sample per thread (src/renderer/renderer_bdpt.cpp:304-407, include/lm/bidir.h).
+//
+// A sample = one eye subpath + one light subpath of up to max_verts vertices each (no Russian roulette, bidir.h:487-537),
+// every connection (s, t) with min_verts <= s + t <= max_verts (renderer_bdpt.cpp:350-361), each weighted by the power
+// heuristic over ALL strategies that could have produced the same full path (bidir.h:446-466).
+//
+// The reference evaluates everything from the VERTICES of the connected full path (Path::eval_sampling_weight_bidir,
+// Path::pdf_bidir); so does this file, through one generic vertex record and the "extended" geometry of surface.h (points
+// at infinity, degenerated points).  Two things are done once instead of per strategy:
+//   * the subpath weights alpha_L(s), alpha_E(t) (bidir.h:252-294) depend on one subpath only and are prefix products;
+//   * p_{s'}(x) / p_s(x) for s' = 0..n is a running product of per-vertex factors fL[i] / fE[i] (density of generating
+//     vertex i from the light side / from the eye side), so the weight of one connection costs O(n) instead of O(n^2).
+//
+// Scope: plain materials (diffuse, glossy, glass, mirror, mask), the five light types, the pinhole camera.  Mixture and
+// textured materials are refused on the host (lmcu_render_bdpt).
+#pragma once
+#include "kernels.cuh"
+
+namespace lmcu {
+
+constexpr int kBdptMaxVerts = 20;
+constexpr uint32_t kEyePathKey = 0xfffffffdu;     // RNG counter word 0 of the eye subpath's draws (the light subpath uses kLightPathKey)
+
+enum { BV_CAMERA = 0, BV_LIGHT = 1, BV_SURFACE = 2 };
+
+struct BdptCounters { uint32_t rays, overflow; };   // per thread: ray queries issued, traversal stack overflow seen
+
+// lm::Vert (bidir.h:24-38): a scene interaction + the component sampled at it
+struct BVert {
+    F3 p;                 // position (infinite: a representative point, unused)
+    F3 n;                 // shading normal; infinite: PointGeometry::wo, the direction FROM the point at infinity
+    F3 gn;
+    int32_t mat;          // surface: index into DevScene::mats
+    int32_t light;        // surface: light index of an emitter, else -1; light endpoint: its light
+    uint8_t kind;         // BV_*
+    uint8_t comp;         // glass: 0 = reflection, 1 = refraction (material_glass.cpp:124-136)
+    uint8_t infinite, degenerated;
+};
+
+// Path::direction (bidir.h:143-157)
+LMCU_HD F3 bv_dir(const BVert& a, const BVert& b) {
+    if (a.infinite) return a.n;
+    if (b.infinite) return -b.n;
+    return normalize(b.p - a.p);
+}
+
+// surface::geometry_term (surface.h:329-348)
+LMCU_HD float bv_G(const BVert& a, const BVert& b) {
+    if (a.infinite && b.infinite) return 0.f;
+    F3 d;
+    float L2;
+    if (a.infinite || b.infinite) {
+        d = a.infinite ? a.n : -b.n;
+        L2 = 1.f;
+    } else {
+        d = b.p - a.p;
+        L2 = dot(d, d);
+        d = d * (1.0f / sqrtf(L2));
+    }
+    const float c1 = (a.degenerated || a.infinite) ? 1.f : fabsf(dot(a.n, d));
+    const float c2 = (b.degenerated || b.infinite) ? 1.f : fabsf(dot(b.n, -d));
+    return c1 * c2 / L2;
+}
+
+// path::is_specular_component (path.h:695-704)
+LMCU_HD bool bv_specular(const DevScene& s, const BVert& v) {
+    if (v.kind == BV_SURFACE) return mat_is_specular(s.mats[v.mat].type);
+    if (v.kind == BV_LIGHT) return s.lights[v.light].type == LIGHT_DIRECTIONAL;
+    return false;
+}
+
+// path::is_connectable_endpoint (path.h:716-725): pinhole, area and point lights; not the lights at infinity
+LMCU_HD bool bv_connectable(const DevScene& s, const BVert& v) {
+    if (v.kind == BV_CAMERA) return true;
+    const int t = s.lights[v.light].type;
+    return t == LIGHT_AREA || t == LIGHT_POINT;
+}
+
+// Fresnel reflectance of material::glass for incident direction wi (material_glass.cpp:90-99,125-131)
+LMCU_HD float bv_glass_fr(const MaterialDev& m, F3 n, F3 wi) {
+    F3 wt; float eta; bool total;
+    return glass_fresnel(m, n, wi, wt, eta, total);
+}
+
+// path::pdf_component (path.h:228-234): 1 except for glass, whose two delta lobes are components picked by Fresnel
+LMCU_HD float bv_pdf_comp(const DevScene& s, const BVert& v, F3 wi) {
+    if (v.kind != BV_SURFACE) return 1.f;
+    const MaterialDev& m = s.mats[v.mat];
+    if (m.type != MAT_GLASS) return 1.f;
+    const float Fr = bv_glass_fr(m, v.n, wi);
+    return v.comp == 0 ? Fr : 1.f - Fr;
+}
+
+// path::pdf_direction with eval_delta = false (path.h:457-470): projected solid angle; delta lobes report 1
+LMCU_HD float bv_pdf_dir(const DevScene& s, const BVert& v, F3 wi, F3 wo) {
+    if (v.kind == BV_CAMERA) {
+        float rx, ry;
+        return camera_importance(s.cam, wo, rx, ry);                       // camera_pinhole.cpp:157-163
+    }
+    if (v.kind == BV_LIGHT) {
+        const int t = s.lights[v.light].type;
+        if (t == LIGHT_AREA) return dot(wo, v.n) <= 0.f ? 0.f : 1.0f / kPiF;   // light_area.cpp:116-121
+        if (t == LIGHT_POINT) return 1.0f / (4.0f * kPiF);                     // light_point.cpp:63-65
+        return 0.f;                                                            // lights at infinity: joint sampling only
+    }
+    const MaterialDev& m = s.mats[v.mat];
+    if (mat_is_specular(m.type)) return 1.f;
+    return mat_pdf(m, v.n, wi, wo);
+}
+
+// path::eval_contrb_direction (path.h:761-775).  le: TransDir::LE.  Surfaces include the shading-normal correction.
+LMCU_HD F3 bv_eval(const DevScene& s, const BVert& v, F3 wi, F3 wo, bool le, bool eval_delta) {
+    if (v.kind == BV_CAMERA) {
+        float rx, ry;
+        return f3s(camera_importance(s.cam, wo, rx, ry));                  // camera_pinhole.cpp:232-237
+    }
+    if (v.kind == BV_LIGHT) {
+        const LightDev& l = s.lights[v.light];
+        const F3 Ke = f3(l.Ke[0], l.Ke[1], l.Ke[2]);
+        if (l.type == LIGHT_AREA) return dot(wo, v.n) <= 0.f ? f3s(0.f) : Ke;   // light_area.cpp:195-197
+        if (l.type == LIGHT_POINT) return Ke;
+        if (l.type == LIGHT_DIRECTIONAL) return eval_delta ? f3s(0.f) : Ke;      // light_directional.cpp:124-126
+        return light_env_radiance(s, l, -wo);
+    }
+    const MaterialDev& m = s.mats[v.mat];
+    F3 f;
+    if (mat_is_specular(m.type)) {
+        if (eval_delta) return f3s(0.f);
+        if (m.type == MAT_GLASS) {                                         // material_glass.cpp:249-266
+            F3 wt; float eta; bool total;
+            const float Fr = glass_fresnel(m, v.n, wi, wt, eta, total);
+            f = v.comp == 0 ? f3s(Fr) : f3s((1.f - Fr) * (le ? 1.f : eta * eta));
+        } else {
+            f = f3s(1.f);                                                  // mirror, mask
+        }
+    } else {
+        f = mat_eval(m, v.n, wi, wo);
+    }
+    return f * sn_correction(v.n, v.gn, wi, wo, le);
+}
+
+// path::pdf_position of a connectable endpoint (path.h:327-344): pinhole 1; area p_sel / (A J); point p_sel
+LMCU_HD float bv_pdf_position(const DevScene& s, const BVert& v) {
+    if (v.kind == BV_CAMERA) return 1.f;
+    const LightDev& l = s.lights[v.light];
+    const float psel = 1.0f / (float)s.num_lights;
+    return l.type == LIGHT_AREA ? psel * l.inv_area_j : psel;
+}
+
+// path::pdf_primary_ray with eval_delta = false (path.h:149-162) of a light endpoint: selection x Light::pdf_ray
+LMCU_HD float bv_pdf_primary_ray(const DevScene& s, const BVert& v, F3 wo) {
+    if (v.kind == BV_CAMERA) {
+        float rx, ry;
+        return camera_importance(s.cam, wo, rx, ry);
+    }
+    const LightDev& l = s.lights[v.light];
+    const float psel = 1.0f / (float)s.num_lights;
+    const float inv_disk = 1.0f / (kPiF * s.bound_radius * s.bound_radius);
+    if (l.type == LIGHT_AREA) return psel * l.inv_area_j * (dot(wo, v.n) <= 0.f ? 0.f : 1.0f / kPiF);
+    if (l.type == LIGHT_POINT) return psel / (4.0f * kPiF);
+    if (l.type == LIGHT_DIRECTIONAL) return psel * inv_disk;                  // light_directional.cpp:70-73
+    return psel * inv_disk / (4.0f * kPiF);                                   // light_envconst.cpp:70-74, light_env.cpp:110-114
+}
+
+// Material::sample_direction for the component stored at the vertex (materials' sample_direction; glass:
+// material_glass.cpp:140-166).  Returns false when the material rejects the sample (glossy below the surface).
+LMCU_HD bool bv_sample_dir(const DevScene& s, const BVert& v, F3 wi, float ud0, float ud1, F3& wo) {
+    const MaterialDev& m = s.mats[v.mat];
+    if (m.type == MAT_GLASS) {
+        if (v.comp == 0) { wo = reflection(wi, v.n); return true; }
+        F3 wt; float eta; bool total;
+        glass_fresnel(m, v.n, wi, wt, eta, total);
+        wo = wt;
+        return !total;
+    }
+    const BsdfSample b = mat_sample(m, v.n, v.gn, wi, ud0, ud1, 0.f, false);
+    wo = b.wo;
+    return b.valid;
+}
+
+// path::sample_subpath (bidir.h:487-553).  Fills vs[0..n), returns n.
+// Random numbers: block 0 / 1 = the primary ray (RaySampleU), block 3 + 2k = component of vertex k, 4 + 2k = its direction.
+template <typename TriT>
+LMCU_HD int bdpt_subpath(const DevScene& s, const PtParams& p, uint64_t sidx, bool light_side, int max_verts, BVert* vs,
+                         uint2* stack, BdptCounters* ctr) {
+    if (max_verts <= 0) return 0;
+    const uint32_t key = light_side ? kLightPathKey : kEyePathKey;
+    int n = 0;
+    F3 o, d;
+    {
+        BVert v;
+        v.mat = -1; v.light = -1; v.comp = 0; v.infinite = 0; v.degenerated = 0;
+        v.n = f3s(0.f); v.gn = f3s(0.f);
+        const R4 u1 = rand4(p.seed, key, sidx, 0);
+        const R4 u2 = rand4(p.seed, key, sidx, 1);
+        if (!light_side) {                                                 // Camera_Pinhole::sample_ray (camera_pinhole.cpp:135-141)
+            D3 od, dd;
+            camera_primary_ray_d(s.cam, (double)u2.x, (double)u2.y, od, dd);
+            v.kind = BV_CAMERA; v.degenerated = 1;
+            v.p = f3((float)od.x, (float)od.y, (float)od.z);
+            o = v.p; d = f3((float)dd.x, (float)dd.y, (float)dd.z);
+        } else {                                                           // path::sample_primary_ray(LE) (path.h:101-118)
+            int li = (int)(u1.x * (float)s.num_lights);
+            li = li < 0 ? 0 : (li > s.num_lights - 1 ? s.num_lights - 1 : li);
+            const LightDev& l = s.lights[li];
+            v.kind = BV_LIGHT; v.light = li;
+            if (l.type == LIGHT_AREA) {                                    // light_area.cpp:47-59,77-97
+                const int ti = cdf_sample(s.cdf + l.cdf_offset, l.num_tris, u1.y);
+                const EmitTri& e = s.emit[l.tri_offset + ti];
+                const float sq = safe_sqrt(u1.z);
+                const float b1 = 1.0f - sq, b2 = u1.w * sq;
+                const F3 a = f3(e.p1.x, e.p1.y, e.p1.z), b = f3(e.p2.x, e.p2.y, e.p2.z), c = f3(e.p3.x, e.p3.y, e.p3.z);
+                v.p = a * (1.0f - b1 - b2) + b * b1 + c * b2;
+                v.n = f3(e.n.x, e.n.y, e.n.z); v.gn = v.n;
+                const F3 dl = sample_cosine_weighted(u2.x, u2.y);
+                F3 tu, tv;
+                orthonormal_basis(v.n, tu, tv);
+                d = tu * dl.x + tv * dl.y + v.n * dl.z;
+                o = v.p;
+            } else if (l.type == LIGHT_POINT) {                            // light_point.cpp:38-48
+                v.p = f3(l.pos[0], l.pos[1], l.pos[2]); v.degenerated = 1;
+                d = sample_uniform_sphere(u2.x, u2.y);
+                o = v.p;
+            } else {                                                       // light_directional.cpp:50-68, light_envconst.cpp:47-68
+                d = l.type == LIGHT_DIRECTIONAL ? f3(l.pos[0], l.pos[1], l.pos[2]) : sample_uniform_sphere(u2.x, u2.y);
+                float dx, dy;
+                sample_uniform_disk(u1.z, u1.w, dx, dy);
+                F3 tu, tv;
+                orthonormal_basis(d, tu, tv);
+                const F3 bc = f3(s.bound_center[0], s.bound_center[1], s.bound_center[2]);
+                v.p = bc - d * s.bound_radius + (tu * (dx * s.bound_radius) + tv * (dy * s.bound_radius));
+                v.n = d; v.infinite = 1;
+                o = v.p;
+            }
+        }
+        vs[n++] = v;
+    }
+    while (true) {
+        // intersection with the next surface (scene.cpp:319-345): tmin = Eps, tmax = Inf; a miss is the environment light
+        HitD h;
+        if (!pt_trace<false, false, TriT>(s, make_float4(o.x, o.y, o.z, (float)kEps), make_float4(d.x, d.y, d.z, (float)kInf), h, stack, nullptr)) ctr->overflow = 1u;
+        ctr->rays++;
+        BVert v;
+        v.comp = 0; v.infinite = 0; v.degenerated = 0;
+        if (h.tri < 0) {
+            if (s.env_light < 0) break;
+            v.kind = BV_LIGHT; v.light = s.env_light; v.mat = -1; v.infinite = 1;
+            v.p = f3s(0.f); v.n = -d; v.gn = f3s(0.f);
+            vs[n++] = v;
+            break;
+        }
+        const SurfPoint sp = surface_point(s, (uint32_t)h.tri, (float)h.u, (float)h.v);
+        v.kind = BV_SURFACE; v.p = sp.p; v.n = sp.n; v.gn = sp.gn; v.mat = sp.material; v.light = sp.light;
+        const F3 wi = -d;
+        const MaterialDev& m = s.mats[sp.material];
+        const R4 uc = rand4(p.seed, key, sidx, 3u + 2u * (uint32_t)n);
+        if (m.type == MAT_GLASS) v.comp = uc.x < bv_glass_fr(m, sp.n, wi) ? 0 : 1;     // material_glass.cpp:124-136
+        vs[n++] = v;
+        if (n >= max_verts) break;
+        // next direction (path::sample_direction at a surface, path.h:414-424); wi is the direction to the previous VERTEX
+        const F3 wiv = bv_dir(v, vs[n - 2]);
+        const R4 ud = rand4(p.seed, key, sidx, 2u + 2u * (uint32_t)n);
+        F3 wo;
+        if (!bv_sample_dir(s, v, wiv, ud.x, ud.y, wo)) break;
+        o = v.p; d = wo;
+    }
+    return n;
+}
+
+// Path::eval_subpath_sampling_weight (bidir.h:252-294) for every prefix length: alpha[l], l = 0..n.  pc[i] = the component
+// pdf of vertex i that went into alpha[i + 1] (the caller takes it out again when the vertex becomes an endpoint).
+LMCU_HD void bdpt_alphas(const DevScene& s, const BVert* vs, int n, bool le, F3* alpha, float* pc) {
+    alpha[0] = f3s(1.f);
+    for (int l = 1; l <= n; l++) alpha[l] = f3s(0.f);
+    if (n == 0) return;
+    int i = 0;
+    pc[0] = 1.f;
+    if (bv_connectable(s, vs[0])) {
+        alpha[1] = f3s(1.0f / bv_pdf_position(s, vs[0]));
+    } else {
+        if (n < 2) return;
+        const F3 d01 = bv_dir(vs[0], vs[1]);
+        const F3 f = bv_eval(s, vs[0], f3s(0.f), d01, le, false);
+        pc[1] = bv_pdf_comp(s, vs[1], -d01);
+        const float pr = bv_pdf_primary_ray(s, vs[0], d01) * pc[1];
+        if (is_zero(f) || !(pr > 0.f)) return;
+        alpha[2] = f * (1.0f / pr);
+        i = 1;
+    }
+    for (; i < n - 1; i++) {
+        const BVert& v = vs[i];
+        const F3 wi = i > 0 ? bv_dir(v, vs[i - 1]) : f3s(0.f);
+        const F3 wo = bv_dir(v, vs[i + 1]);
+        const F3 f = bv_eval(s, v, wi, wo, le, false);
+        pc[i + 1] = bv_pdf_comp(s, vs[i + 1], -wo);
+        const float pd = bv_pdf_dir(s, v, wi, wo) * pc[i + 1];
+        if (is_zero(f) || !(pd > 0.f)) return;
+        alpha[i + 2] = alpha[i + 1] * f * (1.0f / pd);
+    }
+}
+
+// Density (area measure x component) of generating vertex `cur` from `prev`, whose own previous vertex is `prev2` (null for
+// an endpoint): one factor of the products in Path::pdf_bidir (bidir.h:397-431)
+LMCU_HD float bdpt_gen_pdf(const DevScene& s, const BVert* prev2, const BVert& prev, const BVert& cur) {
+    const F3 wo = bv_dir(prev, cur);
+    const F3 wi = prev2 ? bv_dir(prev, *prev2) : f3s(0.f);
+    return bv_pdf_dir(s, prev, wi, wo) * bv_G(prev, cur) * bv_pdf_comp(s, cur, -wo);
+}
+
+// One sample: both subpaths, every connection; splat(pixel, C) receives the weighted contributions.
+template <typename TriT, typename Splat>
+LMCU_HD void bdpt_sample(const DevScene& s, const PtParams& p, int min_verts, uint64_t g, uint2* stack, BdptCounters* ctr, Splat& splat) {
+    const uint64_t sidx = p.sample_offset + g;
+    BVert zs[kBdptMaxVerts], ys[kBdptMaxVerts];
+    F3 aE[kBdptMaxVerts + 1], aL[kBdptMaxVerts + 1];
+    float pcE[kBdptMaxVerts], pcL[kBdptMaxVerts];
+    const int nE = bdpt_subpath<TriT>(s, p, sidx, false, p.max_verts, zs, stack, ctr);
+    const int nL = bdpt_subpath<TriT>(s, p, sidx, true, p.max_verts, ys, stack, ctr);
+    bdpt_alphas(s, zs, nE, false, aE, pcE);
+    bdpt_alphas(s, ys, nL, true, aL, pcL);
+    // raster position of every strategy with t >= 2: the eye subpath's own primary ray
+    uint32_t eye_pixel = 0;
+    if (nE >= 2) {
+        float rx, ry;
+        camera_importance(s.cam, bv_dir(zs[0], zs[1]), rx, ry);
+        eye_pixel = raster_to_pixel(p, rx, ry);
+    }
+    F3 eye_sum = f3s(0.f);
+    for (int sL = 0; sL <= nL; sL++) {
+        for (int t = 1; t <= nE; t++) {                     // t = 0: a light subpath never hits the pinhole (bidir.h:600-606,626-629)
+            const int n = sL + t;
+            if (n < min_verts || n > p.max_verts || n < 2) continue;
+            // -- path::connect_subpaths (bidir.h:585-637) + Path::eval_connection_term (bidir.h:306-330)
+            F3 C;
+            uint32_t pixel = eye_pixel;
+            if (sL == 0) {
+                const BVert& zt = zs[t - 1];
+                if (zt.light < 0 || zt.kind == BV_CAMERA) continue;                   // scene->is_light(vL.sp)
+                BVert x0 = zt; x0.kind = BV_LIGHT;
+                const F3 cst = bv_eval(s, x0, f3s(0.f), bv_dir(x0, zs[t - 2]), true, true);
+                C = aE[t] * pcE[t - 1] * cst;                                         // the endpoint's component pdf is 1
+            } else {
+                const BVert& vL = ys[sL - 1];
+                const BVert& vE = zs[t - 1];
+                if (vL.infinite || vE.infinite) continue;
+                const F3 dLE = bv_dir(vL, vE);
+                const F3 fsL = bv_eval(s, vL, sL >= 2 ? bv_dir(vL, ys[sL - 2]) : f3s(0.f), dLE, true, true);
+                const F3 fsE = bv_eval(s, vE, t >= 2 ? bv_dir(vE, zs[t - 2]) : f3s(0.f), -dLE, false, true);
+                C = aL[sL] * aE[t] * fsL * fsE * bv_G(vL, vE);
+                if (t == 1) {
+                    float rx, ry;
+                    if (camera_importance(s.cam, -dLE, rx, ry) <= 0.f) continue;
+                    pixel = raster_to_pixel(p, rx, ry);
+                }
+            }
+            if (is_zero(C) || !(C.x == C.x) || !(C.y == C.y) || !(C.z == C.z)) continue;
+            if (sL > 0) {                                                             // Scene::visible (scene.h:343-364)
+                const BVert& vL = ys[sL - 1];
+                const BVert& vE = zs[t - 1];
+                const F3 dv = vE.p - vL.p;
+                const float dist = sqrtf(dot(dv, dv));
+                const F3 w = dv * (1.0f / dist);
+                HitD h;
+                if (!pt_trace<true, false, TriT>(s, make_float4(vL.p.x, vL.p.y, vL.p.z, (float)kEps),
+                                                 make_float4(w.x, w.y, w.z, dist * (1.0f - (float)kEps)), h, stack, nullptr)) ctr->overflow = 1u;
+                ctr->rays++;
+                if (h.tri >= 0) continue;
+            }
+            // -- Path::eval_mis_weight (bidir.h:446-466): full path x_0 (light) .. x_{n-1} (camera)
+            float fL[kBdptMaxVerts], fE[kBdptMaxVerts];
+            bool spec[kBdptMaxVerts];
+            BVert x0 = sL > 0 ? ys[0] : zs[t - 1];
+            x0.kind = BV_LIGHT;
+            auto X = [&](int i) -> const BVert& { return i == 0 ? x0 : (i < sL ? ys[i] : zs[n - 1 - i]); };
+            const bool conn0 = bv_connectable(s, x0);
+            for (int i = 0; i < n; i++) spec[i] = bv_specular(s, X(i));
+            fL[0] = conn0 ? bv_pdf_position(s, x0) : 1.f;
+            for (int i = 1; i < n; i++) {
+                if (i == 1) {
+                    if (conn0) fL[1] = bdpt_gen_pdf(s, nullptr, x0, X(1));
+                    else {
+                        const F3 d01 = bv_dir(x0, X(1));
+                        fL[1] = bv_pdf_primary_ray(s, x0, d01) * bv_G(x0, X(1)) * bv_pdf_comp(s, X(1), -d01);
+                    }
+                } else {
+                    fL[i] = bdpt_gen_pdf(s, &X(i - 2), X(i - 1), X(i));
+                }
+            }
+            fE[n - 1] = 1.f;                                                          // pinhole: pdf_position = 1
+            for (int i = n - 2; i >= 0; i--) fE[i] = bdpt_gen_pdf(s, i + 2 < n ? &X(i + 2) : nullptr, X(i + 1), X(i));
+            // Path::is_samplable_bidir (bidir.h:199-230)
+            auto samplable = [&](int s2) -> bool {
+                if (s2 == 0) return !x0.degenerated && !spec[0];
+                if (s2 == n) return false;                                            // the pinhole is degenerated
+                if (s2 == 1 && !conn0) return false;
+                return !spec[s2 - 1] && !spec[s2];
+            };
+            float inv_w = samplable(sL) ? 1.f : 0.f;
+            float r = 1.f;
+            for (int s2 = sL + 1; s2 <= n; s2++) {                                    // p_{s2} / p_s, upward
+                if (!(fE[s2 - 1] > 0.f)) break;
+                r *= fL[s2 - 1] / fE[s2 - 1];
+                if (!(r > 0.f)) break;
+                if (samplable(s2)) inv_w += r * r;
+            }
+            r = 1.f;
+            for (int s2 = sL - 1; s2 >= 0; s2--) {                                    // downward
+                if (!(fL[s2] > 0.f)) break;
+                r *= fE[s2] / fL[s2];
+                if (!(r > 0.f)) break;
+                if (samplable(s2)) inv_w += r * r;
+            }
+            if (!(inv_w > 0.f)) continue;
+            C = C * (1.0f / inv_w);
+            if (t >= 2) eye_sum = eye_sum + C; else splat(pixel, C);
+        }
+    }
+    if (!is_zero(eye_sum)) splat(eye_pixel, eye_sum);
+}
+
+}  // namespace lmcu

@@ -23,6 +23,7 @@
 #include "kernels.cuh"
 #include "trace.cuh"
 #include "trace2.cuh"
+#include "bdpt.cuh"
 
 #ifndef LMCU_SHADE_BLOCK
 #define LMCU_SHADE_BLOCK 64    // threads per CTA of the shade kernel: small CTAs slip into the register space a single
@@ -292,6 +293,32 @@ __global__ void __launch_bounds__(128) k_ao(DevScene s, int width, int height, l
         ao_pixel<TriT>(s, width, height, x, y, spp, sample_offset, seed, ao_distance, film, stack, &local_rays);
     }
     atomicAdd(rays, (unsigned long long)local_rays);
+}
+
+// -- bdpt: one sample per thread (bdpt.cuh), warp-granular work fetch ------------------------------------------------------
+struct FilmSplat {
+    float* film;
+    __device__ __forceinline__ void operator()(uint32_t pixel, F3 C) const {
+        float* px = film + (size_t)pixel * 3;
+        atomicAdd(px + 0, C.x); atomicAdd(px + 1, C.y); atomicAdd(px + 2, C.z);
+    }
+};
+
+template <typename TriT>
+__global__ void __launch_bounds__(128) k_bdpt(DevScene s, PtParams p, int min_verts, float* film, unsigned long long* cursor,
+                                              unsigned long long* rays, uint32_t* overflow) {
+    uint2 stack[kStackSize];
+    FilmSplat splat{film};
+    BdptCounters ctr;
+    ctr.rays = 0; ctr.overflow = 0;
+    while (true) {
+        const unsigned long long base = warp_fetch(cursor);
+        if (base >= p.total_paths) break;
+        const unsigned long long g = base + (threadIdx.x & 31);
+        if (g < p.total_paths) bdpt_sample<TriT>(s, p, min_verts, g, stack, &ctr, splat);
+    }
+    atomicAdd(rays, (unsigned long long)ctr.rays);
+    if (ctr.overflow) atomicExch(overflow, 1u);
 }
 
 // -- wavefront pt ----------------------------------------------------------------------------------
@@ -721,7 +748,9 @@ struct BlockCache {
         return true;
     }
 };
-BlockCache g_cache;
+// Never destroyed: a host may still release scenes from its own static destructors at process exit (the reference's
+// UserContext singleton owns the asset tree and outlives every library loaded after lm::init()).
+BlockCache& g_cache = *new BlockCache;
 }  // namespace
 
 template <typename T>
@@ -2005,6 +2034,94 @@ static int render_paths(LmcuScene* s, const LmcuRenderParams* p, float* film_rgb
         }
     }
     return LMCU_OK;
+}
+
+// renderer::bdpt (src/renderer/renderer_bdpt.cpp:304-407).  One kernel launch per pass of up to 4 Mi samples; the fp32 splat
+// film is folded into the FP64 sums after every pass.
+int lmcu_render_bdpt(LmcuScene* s, const LmcuRenderParams* p, float* film_rgb, LmcuRenderStats* stats) {
+    int rc = require_renderable(s, true);
+    if (rc) return rc;
+    if (!p) return fail(LMCU_ERR_INVALID_ARGUMENT, "null params");
+    const bool timed = p->scheduler == LMCU_SCHED_TIME;
+    if (p->scheduler != LMCU_SCHED_SAMPLE && !timed) return fail(LMCU_ERR_INVALID_ARGUMENT, "bad scheduler");
+    if (timed) {
+        if (!(p->render_time >= 0)) return fail(LMCU_ERR_INVALID_ARGUMENT, "render_time must be >= 0");
+    } else if (p->num_samples <= 0) {
+        return fail(LMCU_ERR_INVALID_ARGUMENT, "num_samples must be positive");
+    }
+    if (p->max_verts < 2 || p->max_verts > kBdptMaxVerts) return fail(LMCU_ERR_INVALID_ARGUMENT, "bdpt: max_verts must be in 2..20");
+    const int min_verts = p->min_verts > 0 ? p->min_verts : 2;
+    if (s->composite)
+        return fail(LMCU_ERR_UNSUPPORTED, "bdpt supports plain materials only (diffuse, glossy, glass, mirror, mask); the scene has a textured or mixture material");
+    CU(cudaSetDevice(s->device));
+    rc = ensure_film(s, p->width, p->height, true);
+    if (rc) return rc;
+    cudaStream_t st = s->stream;
+    const uint64_t npix = (uint64_t)p->width * p->height;
+    PtParams pp{};
+    pp.width = p->width; pp.height = p->height; pp.max_verts = p->max_verts; pp.seed = p->seed;
+    pp.image_mode = 1u;
+    const DevScene d = s->dev();
+    const unsigned fold_blocks = (unsigned)std::min<size_t>((s->film.n + 255) / 256, (size_t)s->num_sms * 8);
+    const auto t0 = std::chrono::steady_clock::now();
+    int64_t processed = 0, launches = 0;
+    const int64_t kPass = 1ll << 22;
+    auto run_pass = [&](int64_t count) -> int {
+        for (int64_t done = 0; done < count;) {
+            const int64_t n = std::min(kPass, count - done);
+            pp.sample_offset = (uint64_t)p->sample_offset + (uint64_t)processed;
+            pp.total_paths = (uint64_t)n;
+            CU(cudaMemsetAsync(s->cursor.p, 0, sizeof(unsigned long long), st));
+            const unsigned blocks = (unsigned)std::min<int64_t>((n + 127) / 128, (int64_t)s->num_sms * 8);
+            if (s->fp32) k_bdpt<TriF32><<<blocks, 128, 0, st>>>(d, pp, min_verts, s->film.p, s->cursor.p, s->cursor.p + 3, s->flags.p);
+            else k_bdpt<TriF64><<<blocks, 128, 0, st>>>(d, pp, min_verts, s->film.p, s->cursor.p, s->cursor.p + 3, s->flags.p);
+            CU(cudaGetLastError());
+            k_film_fold<<<fold_blocks, 256, 0, st>>>(s->film.p, s->film_acc.p, s->film.n);
+            launches += 2;
+            processed += n; done += n;
+            if (p->progress) {
+                CU(cudaStreamSynchronize(st));
+                p->progress(p->progress_user, processed, timed ? 0 : p->num_samples,
+                            std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+            }
+        }
+        return LMCU_OK;
+    };
+    CU(cudaMemsetAsync(s->cursor.p + 3, 0, sizeof(unsigned long long), st));
+    CU(cudaEventRecord(s->ev0, st));
+    if (!timed) {
+        rc = run_pass(p->num_samples);
+        if (rc) return rc;
+    } else {
+        // scheduler::spi::time (src/scheduler.cpp:162-187): whole passes of samples_per_iter until the clock passes render_time
+        const int64_t iter = p->samples_per_iter > 0 ? p->samples_per_iter : 100000;
+        int64_t units = iter;
+        while (true) {
+            rc = run_pass(units);
+            if (rc) return rc;
+            CU(cudaStreamSynchronize(st));
+            const double elapsed = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            if (elapsed > p->render_time) break;
+            const double rate = (double)processed / std::max(elapsed, 1e-6);
+            units = std::max<int64_t>(1, (int64_t)((p->render_time - elapsed) * rate * 0.5 / (double)iter)) * iter;
+        }
+    }
+    const double scale = !p->rescale ? 1.0 : (double)npix / (double)processed;      // renderer_bdpt.cpp:390-391
+    k_film_finish<<<fold_blocks, 256, 0, st>>>(s->film.p, s->film_acc.p, s->film.n, scale);
+    launches += 1;
+    CU(cudaEventRecord(s->ev1, st));
+    if (film_rgb) CU(cudaMemcpyAsync(film_rgb, s->film.p, s->film.n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    unsigned long long rays = 0;
+    CU(cudaMemcpyAsync(&rays, s->cursor.p + 3, sizeof(rays), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (stats) {
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+        memset(stats, 0, sizeof(*stats));
+        stats->elapsed = ms * 1e-3; stats->processed = processed; stats->paths = processed; stats->rays = (int64_t)rays;
+        stats->kernel_launches = launches;
+    }
+    return check_overflow(s);
 }
 
 }  // extern "C"

@@ -77,7 +77,8 @@ class LmcuRenderParams(C.Structure):
                 ("primary_ray_sampling_mode", C.c_int32), ("scheduler", C.c_int32), ("num_samples", C.c_int64),
                 ("samples_per_iter", C.c_int64), ("render_time", C.c_double),
                 ("wavefronts", C.c_int32), ("ao_mark_misses", C.c_int32),
-                ("progress", C.c_void_p), ("progress_user", C.c_void_p)]
+                ("progress", C.c_void_p), ("progress_user", C.c_void_p),
+                ("min_verts", C.c_int32), ("reserved_", C.c_int32)]
 
 
 PROGRESS_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int64, C.c_int64, C.c_double)
@@ -106,7 +107,8 @@ def render_params(width, height, spp=1, max_verts=20, seed=42, sampling_mode=SAM
                   sample_offset=0, rescale=1, bg_color=(0, 0, 0), use_constant_color=False,
                   visualize_normal=False, color=None, ao_distance=0.2, count_traversal=False,
                   primary_ray_sampling_mode=PRIMARY_PIXEL, scheduler=SCHED_SAMPLE, num_samples=0,
-                  samples_per_iter=0, render_time=0.0, wavefronts=0, ao_mark_misses=False, progress=None):
+                  samples_per_iter=0, render_time=0.0, wavefronts=0, ao_mark_misses=False, progress=None,
+                  min_verts=0):
     """Defaults follow the reference renderers' JSON defaults (renderer_pt.cpp:51-77,
     renderer_raycast.cpp:48-60, functest/renderer_ao.cpp:36-40)."""
     p = LmcuRenderParams()
@@ -122,6 +124,7 @@ def render_params(width, height, spp=1, max_verts=20, seed=42, sampling_mode=SAM
     p.num_samples, p.samples_per_iter, p.render_time = num_samples, samples_per_iter, render_time
     p.wavefronts = wavefronts
     p.ao_mark_misses = int(ao_mark_misses)
+    p.min_verts = min_verts
     if progress is not None:                      # a PROGRESS_FN instance; the params object keeps it alive
         p._progress_ref = progress
         p.progress = C.cast(progress, C.c_void_p)

@@ -22,7 +22,7 @@ EXPORTS = [
     "lmcu_last_error", "lmcu_device_count", "lmcu_version", "lmcu_scene_create", "lmcu_scene_destroy",
     "lmcu_scene_set_stream", "lmcu_scene_upload", "lmcu_accel_build", "lmcu_accel_intersect", "lmcu_accel_intersect1", "lmcu_accel_intersect_device",
     "lmcu_cache_trim", "lmcu_probe_l2_bandwidth",
-    "lmcu_accel_intersect_counted", "lmcu_accel_save_size", "lmcu_accel_save", "lmcu_accel_load", "lmcu_render_raycast", "lmcu_render_ao", "lmcu_render_pt", "lmcu_render_lt",
+    "lmcu_accel_intersect_counted", "lmcu_accel_save_size", "lmcu_accel_save", "lmcu_accel_load", "lmcu_render_raycast", "lmcu_render_ao", "lmcu_render_pt", "lmcu_render_lt", "lmcu_render_bdpt",
     "lmcu_film_device_ptr", "lmcu_film_rescale", "lmcu_film_download",
     "lmcu_film_ipc_export", "lmcu_ipc_open", "lmcu_ipc_close", "lmcu_enable_peer_access", "lmcu_film_reduce_peers", "lmcu_film_reduce_slice",
 ]
@@ -141,8 +141,9 @@ class Scene:
 
     # -- Renderer ---------------------------------------------------------------------------------
     def render(self, renderer, params, download=True):
-        """renderer: 'raycast' | 'ao' | 'pt' | 'lt'.  Returns (film[h,w,3] float32 or None, stats dict)."""
-        fn = {"raycast": lib().lmcu_render_raycast, "ao": lib().lmcu_render_ao, "pt": lib().lmcu_render_pt, "lt": lib().lmcu_render_lt}[renderer]
+        """renderer: 'raycast' | 'ao' | 'pt' | 'lt' | 'bdpt'.  Returns (film[h,w,3] float32 or None, stats dict)."""
+        fn = {"raycast": lib().lmcu_render_raycast, "ao": lib().lmcu_render_ao, "pt": lib().lmcu_render_pt, "lt": lib().lmcu_render_lt,
+              "bdpt": lib().lmcu_render_bdpt}[renderer]
         film = np.empty((params.height, params.width, 3), dtype=np.float32) if download else None
         st = abi.LmcuRenderStats()
         _check(fn(self._h, C.byref(params), film.ctypes.data_as(C.c_void_p) if download else None, C.byref(st)))

@@ -601,7 +601,9 @@ struct SceneCache {
     }
     void clear() { std::unique_lock<std::mutex> lk(mu); entries.clear(); }
 };
-SceneCache g_scene_cache;
+// Never destroyed: liblm's UserContext singleton (constructed by lm::init(), before this plugin is loaded) destroys the asset
+// tree — and with it this plugin's components — AFTER the plugin's own statics at process exit.
+SceneCache& g_scene_cache = *new SceneCache;
 
 }
 
@@ -1160,9 +1162,11 @@ LM_COMP_REG_IMPL(Renderer_PT_Cuda, "renderer::pt_cuda");
    ``device``, ``wavefronts`` and ``cache`` as in ``renderer::pt_cuda``.
 \endrst
 */
-class Renderer_LT_Cuda final : public Renderer_CudaBase {
-private:
+// Shared by the two renderers on the image-space scheduler (scheduler::spi::*): renderer::lt_cuda and renderer::bdpt_cuda
+class Renderer_SPI_CudaBase : public Renderer_CudaBase {
+protected:
     int max_verts_;
+    int min_verts_ = 0;
     std::optional<unsigned int> seed_;
     int scheduler_ = LMCU_SCHED_SAMPLE;
     long long num_samples_ = 0;
@@ -1178,12 +1182,16 @@ private:
 public:
     LM_SERIALIZE_IMPL(ar) {                                                                    // renderer_lt.cpp:27-29
         serialize_base(ar);
-        ar(max_verts_, seed_, scheduler_, num_samples_, samples_per_iter_, render_time_, wavefronts_);
+        ar(max_verts_, min_verts_, seed_, scheduler_, num_samples_, samples_per_iter_, render_time_, wavefronts_);
     }
+
+    // the C-ABI entry of the concrete renderer
+    virtual int launch(LmcuScene* h, const LmcuRenderParams* p, float* target, LmcuRenderStats* st) const = 0;
 
     virtual void construct(const Json& prop) override {
         construct_base(prop);
         max_verts_ = json::value<int>(prop, "max_verts");
+        min_verts_ = json::value<int>(prop, "min_verts", 2);                                   // renderer_bdpt.cpp:51 (unused by lt)
         seed_ = json::value_or_none<unsigned int>(prop, "seed");
         const auto name = json::value<std::string>(prop, "scheduler");
         if (name == "sample") {
@@ -1195,7 +1203,7 @@ public:
             render_time_ = json::value<Float>(prop, "render_time");                            // scheduler::spi::time, :157-160
             samples_per_iter_ = json::value<long long>(prop, "samples_per_iter", 100000);
         }
-        else LM_THROW_EXCEPTION(Error::InvalidArgument, "renderer::lt_cuda: unknown scheduler '{}'", name);
+        else LM_THROW_EXCEPTION(Error::InvalidArgument, "unknown scheduler '{}' (scheduler::spi::sample | time)", name);
         wavefronts_ = json::value<int>(prop, "wavefronts", 0);
     }
 
@@ -1204,7 +1212,7 @@ public:
         film_->clear();
         const auto size = film_->size();
         LmcuRenderParams p{};
-        p.width = size.w; p.height = size.h; p.max_verts = max_verts_;
+        p.width = size.w; p.height = size.h; p.max_verts = max_verts_; p.min_verts = min_verts_;
         p.primary_ray_sampling_mode = LMCU_PRIMARY_IMAGE;
         p.scheduler = scheduler_;
         p.num_samples = num_samples_;
@@ -1217,7 +1225,7 @@ public:
         if (timed) progress::start(progress::ProgressMode::Time, 0, render_time_);
         else progress::start(progress::ProgressMode::Samples, num_samples_, -1);
         struct ProgressEnd { ~ProgressEnd() { progress::end(); } } progress_end;
-        p.progress = &Renderer_LT_Cuda::report_progress;
+        p.progress = &Renderer_SPI_CudaBase::report_progress;
         p.progress_user = &timed;
         upload();
         std::vector<float> rgb;
@@ -1225,14 +1233,39 @@ public:
         LmcuRenderStats st{};
         {
             std::unique_lock<std::mutex> lk(dev_->render_mu);
-            check(lmcu_render_lt(dev_->h, &p, target, &st));
+            check(launch(dev_->h, &p, target, &st));
         }
         write_film(rgb, false);
         return { {"processed", st.processed}, {"elapsed", st.elapsed} };
     }
 };
 
+class Renderer_LT_Cuda final : public Renderer_SPI_CudaBase {
+    virtual int launch(LmcuScene* h, const LmcuRenderParams* p, float* target, LmcuRenderStats* st) const override {
+        return lmcu_render_lt(h, p, target, st);
+    }
+};
+
 LM_COMP_REG_IMPL(Renderer_LT_Cuda, "renderer::lt_cuda");
+
+/*
+\rst
+.. function:: renderer::bdpt_cuda
+
+   Bidirectional path tracing on the GPU: ``renderer::bdpt`` (src/renderer/renderer_bdpt.cpp:304-407) through
+   ``lmcu_render_bdpt``.  Same parameters: ``scene``, ``output``, ``max_verts`` (2..20), ``min_verts`` (default 2), ``seed``,
+   ``scheduler`` (``sample`` with ``num_samples`` | ``time`` with ``render_time``, ``samples_per_iter``); plus ``device`` and
+   ``cache`` as in ``renderer::pt_cuda``.  Plain materials only (diffuse, glossy, glass, mirror, mask): a scene with a
+   textured or mixture material raises ``Error::Unsupported``.
+\endrst
+*/
+class Renderer_BDPT_Cuda final : public Renderer_SPI_CudaBase {
+    virtual int launch(LmcuScene* h, const LmcuRenderParams* p, float* target, LmcuRenderStats* st) const override {
+        return lmcu_render_bdpt(h, p, target, st);
+    }
+};
+
+LM_COMP_REG_IMPL(Renderer_BDPT_Cuda, "renderer::bdpt_cuda");
 
 LM_NAMESPACE_END(LM_NAMESPACE)
 

@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "../../lightmetrica-v3_b200/csrc/prep.hpp"
+#include "../../lightmetrica-v3_b200/csrc/bdpt.cuh"
 
 using namespace lmcu;
 
@@ -393,6 +394,45 @@ int hostsim_lt(void* p, const LmcuRenderParams* rp, float* film, long long* rays
     const double sc = rp->rescale ? (double)npix / (double)rp->num_samples : 1.0;
     for (size_t i = 0; i < npix * 3; i++) film[i] = (float)(acc[i] * sc);
     if (rays_out) *rays_out = rays;
+    return 0;
+}
+
+// Bidirectional path tracer, one sample at a time through bdpt_sample (renderer_bdpt.cpp:304-407).
+int hostsim_bdpt(void* p, const LmcuRenderParams* rp, float* film, long long* rays_out) {
+    const SimScene& s = *static_cast<SimScene*>(p);
+    DevScene d = s.dev();
+    {
+        float r2 = 0.f;
+        for (int a = 0; a < 3; a++) {
+            d.bound_center[a] = 0.5f * (s.bounds[a] + s.bounds[3 + a]);
+            const float e = s.bounds[3 + a] - d.bound_center[a];
+            r2 += e * e;
+        }
+        d.bound_radius = std::sqrt(r2) * 1.01f;
+    }
+    PtParams pp{};
+    pp.width = rp->width; pp.height = rp->height; pp.max_verts = rp->max_verts; pp.seed = rp->seed;
+    pp.sample_offset = (uint64_t)rp->sample_offset;
+    pp.image_mode = 1u;
+    pp.total_paths = (uint64_t)rp->num_samples;
+    if (rp->max_verts > kBdptMaxVerts) { g_err = "max_verts too large"; return 1; }
+    const int min_verts = rp->min_verts > 0 ? rp->min_verts : 2;
+    const size_t npix = (size_t)rp->width * rp->height;
+    std::vector<double> acc(npix * 3, 0.0);
+    auto splat = [&](uint32_t px, F3 C) { acc[px * 3 + 0] += C.x; acc[px * 3 + 1] += C.y; acc[px * 3 + 2] += C.z; };
+    uint2 stack[kStackSize];
+    BdptCounters bc;
+    bc.rays = 0; bc.overflow = 0;
+    long long total_rays = 0;
+    for (uint64_t g = 0; g < pp.total_paths; g++) {
+        bc.rays = 0;
+        if (s.fp32) bdpt_sample<TriF32>(d, pp, min_verts, g, stack, &bc, splat); else bdpt_sample<TriF64>(d, pp, min_verts, g, stack, &bc, splat);
+        total_rays += bc.rays;
+    }
+    if (bc.overflow) { g_err = "bvh traversal stack overflow"; return 1; }
+    const double sc = rp->rescale ? (double)npix / (double)rp->num_samples : 1.0;
+    for (size_t i = 0; i < npix * 3; i++) film[i] = (float)(acc[i] * sc);
+    if (rays_out) *rays_out = total_rays;
     return 0;
 }
 

@@ -21,7 +21,7 @@ def build():
     so = os.path.join(out, "libhostsim.so")
     srcs = [os.path.join(_HERE, "hostsim.cpp")] + [
         os.path.join(_ROOT, "lightmetrica-v3_b200", "csrc", f)
-        for f in ("common.cuh", "bvh.cuh", "build.cuh", "shade.cuh", "kernels.cuh", "prep.hpp")]
+        for f in ("common.cuh", "bvh.cuh", "build.cuh", "shade.cuh", "kernels.cuh", "bdpt.cuh", "prep.hpp")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2", "-fPIC", "-ffp-contract=off", "-shared",
                                "-o", so, srcs[0]] + os.environ.get("HOSTSIM_CXXFLAGS", "").split())
@@ -64,6 +64,11 @@ class SimScene:
             lib().hostsim_raycast(self._h, C.byref(params), fp)
         elif renderer == "ao":
             lib().hostsim_ao(self._h, C.byref(params), fp)
+        elif renderer == "bdpt":
+            rays = C.c_longlong()
+            if lib().hostsim_bdpt(self._h, C.byref(params), fp, C.byref(rays)):
+                raise RuntimeError(lib().hostsim_last_error().decode())
+            self.rays = rays.value
         elif renderer == "lt":
             rays = C.c_longlong()
             lib().hostsim_lt(self._h, C.byref(params), fp, C.byref(rays))

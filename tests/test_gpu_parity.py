@@ -683,3 +683,60 @@ def test_g3_lt_vs_reference(reference, tmp_path, scene):
     assert st["processed"] > 0 and st["elapsed"] >= 0.04
     assert abs(ft.mean() - whole.mean()) < 0.03 * whole.mean()
     rs.close(); sc.close()
+
+
+@pytest.mark.parametrize("scene", ["spheres", "env", "delta", "envmap"])
+def test_g3_bdpt_vs_reference(reference, tmp_path, scene):
+    """SURVEY.md 8f N4 (the other integrators): renderer::bdpt on the device (lmcu_render_bdpt) against the reference's
+    renderer::bdpt at equal sample counts — area light + glass / diffuse (caustic paths through s >= 2 strategies), constant
+    environment + glossy / mirror / glass (lights at infinity are not connectable: joint primary-ray densities), point +
+    directional lights (degenerated and specular endpoints), an environment map.  G3 gates as for pt / lt."""
+    import os
+    sb = {"spheres": lambda: scenes.cornell_spheres(32), "env": lambda: scenes.instanced_spheres(grid=2, num_theta=24),
+          "delta": lambda: scenes.delta_lights_scene(2, 16),
+          "envmap": lambda: scenes.instanced_spheres(grid=2, num_theta=16, env=scenes.env_light(os.path.join(str(tmp_path), "e.hdr"), 64, 32))}[scene]()
+    sc, rs = lmcu.Scene(sb), reference.RefScene(sb)
+    w, h, B, spp = 128, 72, 4, 32
+    n = w * h * spp
+    img = dict(max_verts=7, num_samples=n, primary_ray_sampling_mode=abi.PRIMARY_IMAGE)
+    R = np.stack([rs.render("renderer::bdpt", abi.render_params(w, h, seed=42 + b, **img))[0] for b in range(B)])
+    G = np.stack([sc.render("bdpt", abi.render_params(w, h, sample_offset=b * n, **img))[0] for b in range(B)])
+    assert G.mean() > 0.005
+    assert_pt_parity(R.mean(axis=0), G.mean(axis=0), B * spp, rel_mean=0.02)
+    assert_pt_rmse(R, G, k=1.25)
+    # sample-split additivity (counter RNG keyed by the global sample index)
+    whole, st = sc.render("bdpt", abi.render_params(w, h, **img))
+    assert st["processed"] == n and st["rays"] > 2 * n
+    parts = [sc.render("bdpt", abi.render_params(w, h, max_verts=7, num_samples=n // 2, sample_offset=k * (n // 2), rescale=0,
+                                                 primary_ray_sampling_mode=abi.PRIMARY_IMAGE))[0] for k in range(2)]
+    assert np.allclose((parts[0] + parts[1]) * (w * h / n), whole, rtol=1e-4, atol=1e-5)
+    # time scheduler
+    ft, st = sc.render("bdpt", abi.render_params(w, h, max_verts=7, scheduler=abi.SCHED_TIME, render_time=0.05, primary_ray_sampling_mode=abi.PRIMARY_IMAGE))
+    assert st["processed"] > 0 and st["processed"] % 100000 == 0 and st["elapsed"] >= 0.04
+    assert abs(ft.mean() - whole.mean()) < 0.03 * whole.mean()
+    rs.close(); sc.close()
+
+
+def test_bdpt_agrees_with_pt_and_rejects_what_it_does_not_support(tmp_path):
+    """Bidirectional and unidirectional estimators of the same integral: image means of bdpt and pt (MIS) agree; path length
+    selection by min_verts / max_verts partitions the image; unsupported inputs fail loudly."""
+    sb = scenes.cornell_spheres(24)
+    sc = lmcu.Scene(sb)
+    w, h, spp = 160, 90, 256
+    n = w * h * spp
+    img = dict(num_samples=n, primary_ray_sampling_mode=abi.PRIMARY_IMAGE)
+    fb, _ = sc.render("bdpt", abi.render_params(w, h, max_verts=8, **img))
+    fp, _ = sc.render("pt", abi.render_params(w, h, max_verts=8, **img))
+    assert np.abs(fb.mean(axis=(0, 1)) - fp.mean(axis=(0, 1))).max() < 0.01 * fp.mean()
+    short, _ = sc.render("bdpt", abi.render_params(w, h, max_verts=4, **img))
+    long_, _ = sc.render("bdpt", abi.render_params(w, h, max_verts=8, min_verts=5, **img))
+    assert np.allclose(short + long_, fb, rtol=2e-3, atol=2e-4)          # same subpaths, disjoint sets of connections
+    with pytest.raises(lmcu.LmcuError, match="max_verts"):
+        sc.render("bdpt", abi.render_params(w, h, max_verts=21, **img))
+    with pytest.raises(lmcu.LmcuError, match="num_samples"):
+        sc.render("bdpt", abi.render_params(w, h, max_verts=8, primary_ray_sampling_mode=abi.PRIMARY_IMAGE))
+    sc.close()
+    st = lmcu.Scene(scenes.textured_scene(tmp_path, 8, "obj"))
+    with pytest.raises(lmcu.LmcuError, match="plain materials"):
+        st.render("bdpt", abi.render_params(w, h, max_verts=8, **img))
+    st.close()

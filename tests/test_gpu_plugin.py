@@ -364,3 +364,19 @@ def test_renderer_lt_cuda(plugin):
     ft, elapsed, proc = rs.render("renderer::lt_cuda", pt)
     assert proc % 100000 == 0 and proc > 0 and abs(ft.mean() - fr.mean()) < 0.03 * fr.mean()
     rs.close()
+
+
+def test_renderer_bdpt_cuda(plugin):
+    """renderer::bdpt_cuda created by the reference from renderer::bdpt's own JSON keys, against renderer::bdpt."""
+    sb = scenes.cornell_spheres(24)
+    rs = plugin.RefScene(sb)
+    w, h, spp = 128, 72, 64
+    p = abi.render_params(w, h, max_verts=7, num_samples=w * h * spp, primary_ray_sampling_mode=abi.PRIMARY_IMAGE)
+    fr, _, pr = rs.render("renderer::bdpt", p)
+    fc, _, pc = rs.render("renderer::bdpt_cuda", p)
+    assert pr == pc == w * h * spp
+    assert_pt_parity(fr, fc, spp, rel_mean=0.02)
+    pt = abi.render_params(w, h, max_verts=7, scheduler=abi.SCHED_TIME, render_time=0.05, primary_ray_sampling_mode=abi.PRIMARY_IMAGE)
+    ft, elapsed, proc = rs.render("renderer::bdpt_cuda", pt)
+    assert proc % 100000 == 0 and proc > 0 and abs(ft.mean() - fr.mean()) < 0.03 * fr.mean()
+    rs.close()

@@ -234,3 +234,23 @@ def test_lt_statistics(reference, sim, scene):
     fs = ss.render("lt", p)
     assert_pt_parity(fr, fs, spp, rel_mean=0.02)
     rs.close()
+
+
+@pytest.mark.parametrize("scene", ["spheres", "env"])
+def test_bdpt_statistics(reference, sim, scene):
+    """The bidirectional path tracer's device code (bdpt.cuh: both subpaths, every connection, power-heuristic weights from
+    the per-vertex density factors) against the reference's renderer::bdpt at equal sample counts."""
+    sb = scenes.cornell_spheres(12) if scene == "spheres" else scenes.instanced_spheres(grid=2, num_theta=10)
+    rs, ss = reference.RefScene(sb), sim.SimScene(sb)
+    w, h, spp = 64, 36, 32
+    p = abi.render_params(w, h, max_verts=6, num_samples=w * h * spp, primary_ray_sampling_mode=abi.PRIMARY_IMAGE)
+    fr, _, processed = rs.render("renderer::bdpt", p)
+    assert processed == w * h * spp
+    fs = ss.render("bdpt", p)
+    assert ss.rays > 2 * w * h * spp
+    assert_pt_parity(fr, fs, spp, rel_mean=0.02)
+    # min_verts / max_verts select path lengths: lengths 2..3 and 4..6 add up to 2..6 (same random numbers)
+    lo = ss.render("bdpt", abi.render_params(w, h, max_verts=3, num_samples=w * h * 4, primary_ray_sampling_mode=abi.PRIMARY_IMAGE))
+    al = ss.render("bdpt", abi.render_params(w, h, max_verts=3, min_verts=3, num_samples=w * h * 4, primary_ray_sampling_mode=abi.PRIMARY_IMAGE))
+    assert 0 < al.mean() < lo.mean()
+    rs.close()

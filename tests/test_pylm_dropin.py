@@ -72,7 +72,7 @@ def render(lm, renderer_key, film_key="bitmap", w=160, h=90, **kw):
 def test_plugin_registers_its_components_in_the_reference_registry(lm):
     keys = []
     lm.comp.foreach_registered(lambda k: keys.append(k))
-    for k in ("accel::cuda_bvh", "renderer::raycast_cuda", "renderer::ao_cuda", "renderer::pt_cuda", "renderer::lt_cuda", "film::cuda"):
+    for k in ("accel::cuda_bvh", "renderer::raycast_cuda", "renderer::ao_cuda", "renderer::pt_cuda", "renderer::lt_cuda", "renderer::bdpt_cuda", "film::cuda"):
         assert k in keys
     # the reference's own pipeline through its Python API (CPU): accel::sahbvh + renderer::raycast
     scene = build_scene(lm, "sahbvh")
