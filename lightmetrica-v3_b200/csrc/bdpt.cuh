@@ -9,7 +9,9 @@
 // at infinity, degenerated points).  Two things are done once instead of per strategy:
 //   * the subpath weights alpha_L(s), alpha_E(t) (bidir.h:252-294) depend on one subpath only and are prefix products;
 //   * p_{s'}(x) / p_s(x) for s' = 0..n is a running product of per-vertex factors fL[i] / fE[i] (density of generating
-//     vertex i from the light side / from the eye side), so the weight of one connection costs O(n) instead of O(n^2).
+//     vertex i from the light side / from the eye side); all of them but the four around the connecting edge belong to one
+//     subpath and are computed once per sample, so a connection costs 4 density evaluations + O(n) multiply-adds instead
+//     of the reference's O(n^2) evaluations.
 //
 // Scope: plain materials (diffuse, glossy, glass, mirror, mask), the five light types, the pinhole camera.  Mixture and
 // textured materials are refused on the host (lmcu_render_bdpt).
@@ -307,115 +309,203 @@ LMCU_HD float bdpt_gen_pdf(const DevScene& s, const BVert* prev2, const BVert& p
     return bv_pdf_dir(s, prev, wi, wo) * bv_G(prev, cur) * bv_pdf_comp(s, cur, -wo);
 }
 
-// One sample: both subpaths, every connection; splat(pixel, C) receives the weighted contributions.
+// Per-subpath halves of the strategy densities (Path::pdf_bidir, bidir.h:388-437).  For vertex i of a subpath:
+//   F[i] = density of generating it the way the subpath did (from vertex i-1, given i-2; i = 0: position pdf; a light at
+//          infinity is sampled jointly with vertex 1: F[0] = 1, F[1] = pdf_primary_ray x G x component),
+//   R[i] = density of generating it from the OTHER end, from vertex i+1 given i+2 (defined for i + 2 < n),
+//   spec[i] = the vertex is a delta interaction.
+// None of them depends on the connection; the four densities around the connecting edge are evaluated per strategy.
+LMCU_HD void bdpt_subpath_pdfs(const DevScene& s, const BVert* vs, int n, float* F, float* R, bool* spec) {
+    for (int i = 0; i < n; i++) spec[i] = bv_specular(s, vs[i]);
+    if (n == 0) return;
+    const bool conn0 = bv_connectable(s, vs[0]);
+    F[0] = conn0 ? bv_pdf_position(s, vs[0]) : 1.f;
+    for (int i = 1; i < n; i++) {
+        if (i == 1 && !conn0) {
+            const F3 d01 = bv_dir(vs[0], vs[1]);
+            F[1] = bv_pdf_primary_ray(s, vs[0], d01) * bv_G(vs[0], vs[1]) * bv_pdf_comp(s, vs[1], -d01);
+        } else {
+            F[i] = bdpt_gen_pdf(s, i >= 2 ? &vs[i - 2] : nullptr, vs[i - 1], vs[i]);
+        }
+    }
+    for (int i = 0; i + 2 < n; i++) R[i] = bdpt_gen_pdf(s, &vs[i + 2], vs[i + 1], vs[i]);
+}
+
+// What one connection (s, t) produces: the MIS-weighted contribution, the pixel it belongs to and — for s >= 1 — the
+// visibility ray that decides whether it counts (Scene::visible, scene.h:343-364).
+struct BdptConn {
+    F3 C;
+    uint32_t pixel;
+    bool shadow;
+    float4 sh_o, sh_d;
+};
+
+// Strategy (sL, t) of one sample: path::connect_subpaths (bidir.h:585-637) without the visibility test,
+// Path::eval_sampling_weight_bidir (bidir.h:319-343) and Path::eval_mis_weight (bidir.h:446-466).  `a` gives access to the
+// two subpaths and their per-vertex data (local arrays on the host, SoA loads on the device):
+//   BVert Y(i), Z(j)   light / eye subpath vertices      F3 aL(l), aE(l)   alpha of the first l vertices
+//   float pcE(j)       component pdf inside aE(j + 1)     float yF(i), yR(i), zF(j), zR(j); bool ySpec(i), zSpec(j)
+// Returns false when the strategy contributes nothing.
+template <typename Acc>
+LMCU_HD bool bdpt_connect(const DevScene& s, const PtParams& p, int sL, int t, const Acc& a, uint32_t eye_pixel, BdptConn& out) {
+    const int n = sL + t;
+    out.pixel = eye_pixel;
+    out.shadow = false;
+    F3 C;
+    BVert x0, vL, vLp, vE, vEp;
+    vE = a.Z(t - 1);
+    if (t >= 2) vEp = a.Z(t - 2);
+    if (sL == 0) {
+        if (vE.light < 0 || vE.kind == BV_CAMERA) return false;                       // scene->is_light(vL.sp)
+        x0 = vE; x0.kind = BV_LIGHT;
+        const F3 cst = bv_eval(s, x0, f3s(0.f), bv_dir(x0, vEp), true, true);         // Path::eval_connection_term, s = 0
+        C = a.aE(t) * a.pcE(t - 1) * cst;                                             // the endpoint's component pdf is 1
+    } else {
+        vL = a.Y(sL - 1);
+        if (sL >= 2) vLp = a.Y(sL - 2);
+        if (vL.infinite || vE.infinite) return false;
+        const F3 dLE = bv_dir(vL, vE);
+        const F3 fsL = bv_eval(s, vL, sL >= 2 ? bv_dir(vL, vLp) : f3s(0.f), dLE, true, true);
+        const F3 fsE = bv_eval(s, vE, t >= 2 ? bv_dir(vE, vEp) : f3s(0.f), -dLE, false, true);
+        C = a.aL(sL) * a.aE(t) * fsL * fsE * bv_G(vL, vE);
+        if (t == 1) {
+            float rx, ry;
+            if (camera_importance(s.cam, -dLE, rx, ry) <= 0.f) return false;
+            out.pixel = raster_to_pixel(p, rx, ry);
+        }
+        const F3 dv = vE.p - vL.p;
+        const float dist = sqrtf(dot(dv, dv));
+        const F3 w = dv * (1.0f / dist);
+        out.shadow = true;
+        out.sh_o = make_float4(vL.p.x, vL.p.y, vL.p.z, (float)kEps);
+        out.sh_d = make_float4(w.x, w.y, w.z, dist * (1.0f - (float)kEps));
+    }
+    if (is_zero(C) || !(C.x == C.x) || !(C.y == C.y) || !(C.z == C.z)) return false;
+    // -- the densities around the connecting edge; full path x_0 (light) .. x_{n-1} (camera), x_i = Y(i) for i < sL and
+    // Z(n-1-i) above.  fL[i] / fE[i] = density of generating x_i from the light / eye side:
+    // p_{s'} = prod_{i < s'} fL[i] * prod_{i >= s'} fE[i].
+    bool spec0, conn0, degen0;
+    float fl_a, fl_b = 0.f, fe_a, fe_b = 0.f, fl0 = 0.f;       // sL >= 1: fL[sL], fL[sL+1], fE[sL-1], fE[sL-2];  sL = 0: fL[1], -, fE[0], -, fL[0]
+    if (sL == 0) {
+        conn0 = bv_connectable(s, x0); spec0 = bv_specular(s, x0); degen0 = x0.degenerated != 0;
+        fl0 = conn0 ? bv_pdf_position(s, x0) : 1.f;
+        if (conn0) fl_a = bdpt_gen_pdf(s, nullptr, x0, vEp);
+        else {
+            const F3 d01 = bv_dir(x0, vEp);
+            fl_a = bv_pdf_primary_ray(s, x0, d01) * bv_G(x0, vEp) * bv_pdf_comp(s, vEp, -d01);
+        }
+        BVert vEpp;
+        if (t >= 3) vEpp = a.Z(t - 3);
+        fe_a = bdpt_gen_pdf(s, t >= 3 ? &vEpp : nullptr, vEp, x0);
+    } else {
+        const BVert y0 = sL == 1 ? vL : (sL == 2 ? vLp : a.Y(0));
+        conn0 = bv_connectable(s, y0); spec0 = a.ySpec(0); degen0 = y0.degenerated != 0;
+        fl_a = bdpt_gen_pdf(s, sL >= 2 ? &vLp : nullptr, vL, vE);
+        if (t >= 2) fl_b = bdpt_gen_pdf(s, &vL, vE, vEp);
+        fe_a = bdpt_gen_pdf(s, t >= 2 ? &vEp : nullptr, vE, vL);
+        if (sL >= 2) fe_b = bdpt_gen_pdf(s, &vE, vL, vLp);
+    }
+    auto FL = [&](int i) -> float {
+        if (sL == 0) return i == 0 ? fl0 : (i == 1 ? fl_a : a.zR(n - 1 - i));
+        return i < sL ? a.yF(i) : (i == sL ? fl_a : (i == sL + 1 ? fl_b : a.zR(n - 1 - i)));
+    };
+    auto FE = [&](int i) -> float {
+        if (sL == 0) return i == 0 ? fe_a : a.zF(n - 1 - i);
+        return i >= sL ? a.zF(n - 1 - i) : (i == sL - 1 ? fe_a : (i == sL - 2 ? fe_b : a.yR(i)));
+    };
+    auto spec = [&](int i) -> bool { return i == 0 ? spec0 : (i < sL ? a.ySpec(i) : a.zSpec(n - 1 - i)); };
+    // Path::is_samplable_bidir (bidir.h:199-230)
+    auto samplable = [&](int s2) -> bool {
+        if (s2 == 0) return !degen0 && !spec0;
+        if (s2 == n) return false;                                                    // the pinhole is degenerated
+        if (s2 == 1 && !conn0) return false;
+        return !spec(s2 - 1) && !spec(s2);
+    };
+    float inv_w = samplable(sL) ? 1.f : 0.f;
+    float r = 1.f;
+    for (int s2 = sL + 1; s2 <= n; s2++) {                                            // p_{s2} / p_s, upward
+        const float fe = FE(s2 - 1);
+        if (!(fe > 0.f)) break;
+        r *= FL(s2 - 1) / fe;
+        if (!(r > 0.f)) break;
+        if (samplable(s2)) inv_w += r * r;
+    }
+    r = 1.f;
+    for (int s2 = sL - 1; s2 >= 0; s2--) {                                            // downward
+        const float fl = FL(s2);
+        if (!(fl > 0.f)) break;
+        r *= FE(s2) / fl;
+        if (!(r > 0.f)) break;
+        if (samplable(s2)) inv_w += r * r;
+    }
+    if (!(inv_w > 0.f)) return false;
+    out.C = C * (1.0f / inv_w);
+    return true;
+}
+
+// Subpath data in local arrays (the one-thread-per-sample form below)
+struct BdptLocalAcc {
+    const BVert* ys; const BVert* zs;
+    const F3* aL_; const F3* aE_;
+    const float* pcE_; const float* yF_; const float* yR_; const float* zF_; const float* zR_;
+    const bool* ySpec_; const bool* zSpec_;
+    LMCU_HD BVert Y(int i) const { return ys[i]; }
+    LMCU_HD BVert Z(int j) const { return zs[j]; }
+    LMCU_HD F3 aL(int l) const { return aL_[l]; }
+    LMCU_HD F3 aE(int l) const { return aE_[l]; }
+    LMCU_HD float pcE(int j) const { return pcE_[j]; }
+    LMCU_HD float yF(int i) const { return yF_[i]; }
+    LMCU_HD float yR(int i) const { return yR_[i]; }
+    LMCU_HD float zF(int j) const { return zF_[j]; }
+    LMCU_HD float zR(int j) const { return zR_[j]; }
+    LMCU_HD bool ySpec(int i) const { return ySpec_[i]; }
+    LMCU_HD bool zSpec(int j) const { return zSpec_[j]; }
+};
+
+// raster pixel of every strategy with t >= 2: the eye subpath's own primary ray
+LMCU_HD uint32_t bdpt_eye_pixel(const DevScene& s, const PtParams& p, const BVert* zs, int nE) {
+    if (nE < 2) return 0u;
+    float rx, ry;
+    camera_importance(s.cam, bv_dir(zs[0], zs[1]), rx, ry);
+    return raster_to_pixel(p, rx, ry);
+}
+
+// One sample by one thread: both subpaths, every connection; splat(pixel, C) receives the weighted contributions.  This is
+// the form tests/hostsim runs on the CPU; the device runs the same functions as three kernels (lmcu.cu: k_bdpt_subpaths,
+// k_bdpt_connect, k_pt_shadow_q).
 template <typename TriT, typename Splat>
 LMCU_HD void bdpt_sample(const DevScene& s, const PtParams& p, int min_verts, uint64_t g, uint2* stack, BdptCounters* ctr, Splat& splat) {
     const uint64_t sidx = p.sample_offset + g;
     BVert zs[kBdptMaxVerts], ys[kBdptMaxVerts];
     F3 aE[kBdptMaxVerts + 1], aL[kBdptMaxVerts + 1];
     float pcE[kBdptMaxVerts], pcL[kBdptMaxVerts];
+    float zF[kBdptMaxVerts], zR[kBdptMaxVerts], yF[kBdptMaxVerts], yR[kBdptMaxVerts];
+    bool zSpec[kBdptMaxVerts], ySpec[kBdptMaxVerts];
     const int nE = bdpt_subpath<TriT>(s, p, sidx, false, p.max_verts, zs, stack, ctr);
     const int nL = bdpt_subpath<TriT>(s, p, sidx, true, p.max_verts, ys, stack, ctr);
     bdpt_alphas(s, zs, nE, false, aE, pcE);
     bdpt_alphas(s, ys, nL, true, aL, pcL);
-    // raster position of every strategy with t >= 2: the eye subpath's own primary ray
-    uint32_t eye_pixel = 0;
-    if (nE >= 2) {
-        float rx, ry;
-        camera_importance(s.cam, bv_dir(zs[0], zs[1]), rx, ry);
-        eye_pixel = raster_to_pixel(p, rx, ry);
-    }
-    F3 eye_sum = f3s(0.f);
+    bdpt_subpath_pdfs(s, zs, nE, zF, zR, zSpec);
+    bdpt_subpath_pdfs(s, ys, nL, yF, yR, ySpec);
+    const uint32_t eye_pixel = bdpt_eye_pixel(s, p, zs, nE);
+    BdptLocalAcc acc;
+    acc.ys = ys; acc.zs = zs; acc.aL_ = aL; acc.aE_ = aE; acc.pcE_ = pcE;
+    acc.yF_ = yF; acc.yR_ = yR; acc.zF_ = zF; acc.zR_ = zR; acc.ySpec_ = ySpec; acc.zSpec_ = zSpec;
     for (int sL = 0; sL <= nL; sL++) {
         for (int t = 1; t <= nE; t++) {                     // t = 0: a light subpath never hits the pinhole (bidir.h:600-606,626-629)
             const int n = sL + t;
             if (n < min_verts || n > p.max_verts || n < 2) continue;
-            // -- path::connect_subpaths (bidir.h:585-637) + Path::eval_connection_term (bidir.h:306-330)
-            F3 C;
-            uint32_t pixel = eye_pixel;
-            if (sL == 0) {
-                const BVert& zt = zs[t - 1];
-                if (zt.light < 0 || zt.kind == BV_CAMERA) continue;                   // scene->is_light(vL.sp)
-                BVert x0 = zt; x0.kind = BV_LIGHT;
-                const F3 cst = bv_eval(s, x0, f3s(0.f), bv_dir(x0, zs[t - 2]), true, true);
-                C = aE[t] * pcE[t - 1] * cst;                                         // the endpoint's component pdf is 1
-            } else {
-                const BVert& vL = ys[sL - 1];
-                const BVert& vE = zs[t - 1];
-                if (vL.infinite || vE.infinite) continue;
-                const F3 dLE = bv_dir(vL, vE);
-                const F3 fsL = bv_eval(s, vL, sL >= 2 ? bv_dir(vL, ys[sL - 2]) : f3s(0.f), dLE, true, true);
-                const F3 fsE = bv_eval(s, vE, t >= 2 ? bv_dir(vE, zs[t - 2]) : f3s(0.f), -dLE, false, true);
-                C = aL[sL] * aE[t] * fsL * fsE * bv_G(vL, vE);
-                if (t == 1) {
-                    float rx, ry;
-                    if (camera_importance(s.cam, -dLE, rx, ry) <= 0.f) continue;
-                    pixel = raster_to_pixel(p, rx, ry);
-                }
-            }
-            if (is_zero(C) || !(C.x == C.x) || !(C.y == C.y) || !(C.z == C.z)) continue;
-            if (sL > 0) {                                                             // Scene::visible (scene.h:343-364)
-                const BVert& vL = ys[sL - 1];
-                const BVert& vE = zs[t - 1];
-                const F3 dv = vE.p - vL.p;
-                const float dist = sqrtf(dot(dv, dv));
-                const F3 w = dv * (1.0f / dist);
+            BdptConn c;
+            if (!bdpt_connect(s, p, sL, t, acc, eye_pixel, c)) continue;
+            if (c.shadow) {
                 HitD h;
-                if (!pt_trace<true, false, TriT>(s, make_float4(vL.p.x, vL.p.y, vL.p.z, (float)kEps),
-                                                 make_float4(w.x, w.y, w.z, dist * (1.0f - (float)kEps)), h, stack, nullptr)) ctr->overflow = 1u;
+                if (!pt_trace<true, false, TriT>(s, c.sh_o, c.sh_d, h, stack, nullptr)) ctr->overflow = 1u;
                 ctr->rays++;
                 if (h.tri >= 0) continue;
             }
-            // -- Path::eval_mis_weight (bidir.h:446-466): full path x_0 (light) .. x_{n-1} (camera)
-            float fL[kBdptMaxVerts], fE[kBdptMaxVerts];
-            bool spec[kBdptMaxVerts];
-            BVert x0 = sL > 0 ? ys[0] : zs[t - 1];
-            x0.kind = BV_LIGHT;
-            auto X = [&](int i) -> const BVert& { return i == 0 ? x0 : (i < sL ? ys[i] : zs[n - 1 - i]); };
-            const bool conn0 = bv_connectable(s, x0);
-            for (int i = 0; i < n; i++) spec[i] = bv_specular(s, X(i));
-            fL[0] = conn0 ? bv_pdf_position(s, x0) : 1.f;
-            for (int i = 1; i < n; i++) {
-                if (i == 1) {
-                    if (conn0) fL[1] = bdpt_gen_pdf(s, nullptr, x0, X(1));
-                    else {
-                        const F3 d01 = bv_dir(x0, X(1));
-                        fL[1] = bv_pdf_primary_ray(s, x0, d01) * bv_G(x0, X(1)) * bv_pdf_comp(s, X(1), -d01);
-                    }
-                } else {
-                    fL[i] = bdpt_gen_pdf(s, &X(i - 2), X(i - 1), X(i));
-                }
-            }
-            fE[n - 1] = 1.f;                                                          // pinhole: pdf_position = 1
-            for (int i = n - 2; i >= 0; i--) fE[i] = bdpt_gen_pdf(s, i + 2 < n ? &X(i + 2) : nullptr, X(i + 1), X(i));
-            // Path::is_samplable_bidir (bidir.h:199-230)
-            auto samplable = [&](int s2) -> bool {
-                if (s2 == 0) return !x0.degenerated && !spec[0];
-                if (s2 == n) return false;                                            // the pinhole is degenerated
-                if (s2 == 1 && !conn0) return false;
-                return !spec[s2 - 1] && !spec[s2];
-            };
-            float inv_w = samplable(sL) ? 1.f : 0.f;
-            float r = 1.f;
-            for (int s2 = sL + 1; s2 <= n; s2++) {                                    // p_{s2} / p_s, upward
-                if (!(fE[s2 - 1] > 0.f)) break;
-                r *= fL[s2 - 1] / fE[s2 - 1];
-                if (!(r > 0.f)) break;
-                if (samplable(s2)) inv_w += r * r;
-            }
-            r = 1.f;
-            for (int s2 = sL - 1; s2 >= 0; s2--) {                                    // downward
-                if (!(fL[s2] > 0.f)) break;
-                r *= fE[s2] / fL[s2];
-                if (!(r > 0.f)) break;
-                if (samplable(s2)) inv_w += r * r;
-            }
-            if (!(inv_w > 0.f)) continue;
-            C = C * (1.0f / inv_w);
-            if (t >= 2) eye_sum = eye_sum + C; else splat(pixel, C);
+            splat(c.pixel, c.C);
         }
     }
-    if (!is_zero(eye_sum)) splat(eye_pixel, eye_sum);
 }
 
 }  // namespace lmcu

@@ -295,30 +295,130 @@ __global__ void __launch_bounds__(128) k_ao(DevScene s, int width, int height, l
     atomicAdd(rays, (unsigned long long)local_rays);
 }
 
-// -- bdpt: one sample per thread (bdpt.cuh), warp-granular work fetch ------------------------------------------------------
-struct FilmSplat {
-    float* film;
-    __device__ __forceinline__ void operator()(uint32_t pixel, F3 C) const {
-        float* px = film + (size_t)pixel * 3;
-        atomicAdd(px + 0, C.x); atomicAdd(px + 1, C.y); atomicAdd(px + 2, C.z);
+// -- bdpt (bdpt.cuh) as three kernels ---------------------------------------------------------------------------------------
+// One thread per sample doing everything (the form tests/hostsim runs) executes at 3 of 32 lanes on the device: the (s, t)
+// loops, their early exits and the traversals inside them diverge completely (ncu, profiles/r02_ncu_summary.md).  Here:
+//   k_bdpt_subpaths   one thread per SUBPATH: random walk, alpha prefixes, per-vertex densities -> SoA arrays in HBM;
+//   k_bdpt_connect    one thread per (strategy, sample), strategy-major: every lane of a warp runs the SAME (s, t) on
+//                     consecutive samples — uniform loops, coalesced loads — and appends a visibility ray carrying the
+//                     weighted contribution to the shadow queue (s = 0 strategies splat at once);
+//   k_pt_shadow_q     the path tracer's any-hit queue kernel: visible => splat.
+struct BdptStore {
+    float4* va;        // [2][mv][cap]  p.xyz, kind | comp << 8 | infinite << 16 | degenerated << 17
+    float4* vb;        //               n.xyz, material
+    float4* vc;        //               gn.xyz, light
+    float4* vd;        //               alpha of the first k + 1 vertices, component pdf of vertex k
+    float2* ve;        //               F (sign bit: the vertex is specular), R  (bdpt_subpath_pdfs)
+    int32_t* nverts;   // [2][cap]
+    uint32_t* eye_pixel;   // [cap]
+    uint32_t cap;
+    int32_t mv;
+    __host__ __device__ size_t at(int side, int k, uint32_t i) const { return (size_t)(side * mv + k) * cap + i; }
+};
+
+struct BdptSoAAcc {
+    BdptStore st;
+    uint32_t i;
+    __device__ __forceinline__ BVert load(int side, int k) const {
+        const size_t o = st.at(side, k, i);
+        const float4 a = st.va[o], b = st.vb[o], c = st.vc[o];
+        BVert v;
+        v.p = f3(a.x, a.y, a.z); v.n = f3(b.x, b.y, b.z); v.gn = f3(c.x, c.y, c.z);
+        const uint32_t bits = __float_as_uint(a.w);
+        v.kind = (uint8_t)(bits & 0xffu); v.comp = (uint8_t)((bits >> 8) & 0xffu);
+        v.infinite = (uint8_t)((bits >> 16) & 1u); v.degenerated = (uint8_t)((bits >> 17) & 1u);
+        v.mat = (int32_t)__float_as_uint(b.w); v.light = (int32_t)__float_as_uint(c.w);
+        return v;
     }
+    __device__ __forceinline__ BVert Y(int k) const { return load(1, k); }
+    __device__ __forceinline__ BVert Z(int k) const { return load(0, k); }
+    __device__ __forceinline__ F3 alpha(int side, int l) const {
+        if (l == 0) return f3s(1.f);
+        const float4 d = st.vd[st.at(side, l - 1, i)];
+        return f3(d.x, d.y, d.z);
+    }
+    __device__ __forceinline__ F3 aL(int l) const { return alpha(1, l); }
+    __device__ __forceinline__ F3 aE(int l) const { return alpha(0, l); }
+    __device__ __forceinline__ float pcE(int k) const { return st.vd[st.at(0, k, i)].w; }
+    __device__ __forceinline__ float yF(int k) const { return fabsf(st.ve[st.at(1, k, i)].x); }
+    __device__ __forceinline__ float yR(int k) const { return st.ve[st.at(1, k, i)].y; }
+    __device__ __forceinline__ float zF(int k) const { return fabsf(st.ve[st.at(0, k, i)].x); }
+    __device__ __forceinline__ float zR(int k) const { return st.ve[st.at(0, k, i)].y; }
+    __device__ __forceinline__ bool ySpec(int k) const { return signbit(st.ve[st.at(1, k, i)].x); }
+    __device__ __forceinline__ bool zSpec(int k) const { return signbit(st.ve[st.at(0, k, i)].x); }
 };
 
 template <typename TriT>
-__global__ void __launch_bounds__(128) k_bdpt(DevScene s, PtParams p, int min_verts, float* film, unsigned long long* cursor,
-                                              unsigned long long* rays, uint32_t* overflow) {
+__global__ void __launch_bounds__(128) k_bdpt_subpaths(DevScene s, PtParams p, BdptStore st, unsigned long long* cursor,
+                                                       unsigned long long* rays, uint32_t* overflow) {
     uint2 stack[kStackSize];
-    FilmSplat splat{film};
+    BVert vs[kBdptMaxVerts];
+    F3 alpha[kBdptMaxVerts + 1];
+    float pc[kBdptMaxVerts], F[kBdptMaxVerts], R[kBdptMaxVerts];
+    bool spec[kBdptMaxVerts];
     BdptCounters ctr;
     ctr.rays = 0; ctr.overflow = 0;
+    const unsigned long long total = 2ull * p.total_paths;             // eye subpaths first, then the light subpaths
     while (true) {
         const unsigned long long base = warp_fetch(cursor);
-        if (base >= p.total_paths) break;
-        const unsigned long long g = base + (threadIdx.x & 31);
-        if (g < p.total_paths) bdpt_sample<TriT>(s, p, min_verts, g, stack, &ctr, splat);
+        if (base >= total) break;
+        const unsigned long long idx = base + (threadIdx.x & 31);
+        if (idx >= total) continue;
+        const int side = idx >= p.total_paths ? 1 : 0;
+        const uint32_t g = (uint32_t)(idx - (side ? p.total_paths : 0ull));
+        const int n = bdpt_subpath<TriT>(s, p, p.sample_offset + g, side != 0, p.max_verts, vs, stack, &ctr);
+        bdpt_alphas(s, vs, n, side != 0, alpha, pc);
+        bdpt_subpath_pdfs(s, vs, n, F, R, spec);
+        st.nverts[(size_t)side * st.cap + g] = n;
+        if (!side) st.eye_pixel[g] = bdpt_eye_pixel(s, p, vs, n);
+        for (int k = 0; k < n; k++) {
+            const BVert& v = vs[k];
+            const size_t o = st.at(side, k, g);
+            const uint32_t bits = (uint32_t)v.kind | ((uint32_t)v.comp << 8) | ((uint32_t)v.infinite << 16) | ((uint32_t)v.degenerated << 17);
+            st.va[o] = make_float4(v.p.x, v.p.y, v.p.z, __uint_as_float(bits));
+            st.vb[o] = make_float4(v.n.x, v.n.y, v.n.z, __uint_as_float((uint32_t)v.mat));
+            st.vc[o] = make_float4(v.gn.x, v.gn.y, v.gn.z, __uint_as_float((uint32_t)v.light));
+            st.vd[o] = make_float4(alpha[k + 1].x, alpha[k + 1].y, alpha[k + 1].z, pc[k]);
+            st.ve[o] = make_float2(spec[k] ? -F[k] : F[k], k + 2 < n ? R[k] : 0.f);
+        }
     }
     atomicAdd(rays, (unsigned long long)ctr.rays);
     if (ctr.overflow) atomicExch(overflow, 1u);
+}
+
+__global__ void k_bdpt_reset(PtCounters* ctr) { ctr->shadow_count = 0; ctr->fetch_shadow = 0; }
+
+__global__ void __launch_bounds__(128) k_bdpt_connect(DevScene s, PtParams p, BdptStore st, const int2* __restrict__ pairs, ShadowQueue sq,
+                                                      float* film, PtCounters* ctr) {
+    const int2 pr = pairs[blockIdx.y];
+    const int sL = pr.x, t = pr.y;
+    const uint32_t total = (uint32_t)p.total_paths, lane = threadIdx.x & 31u;
+    for (uint32_t base = blockIdx.x * blockDim.x; base < total; base += gridDim.x * blockDim.x) {      // warp-uniform trip count
+        const uint32_t i = base + threadIdx.x;
+        bool push = false;
+        BdptConn c;
+        if (i < total && t <= st.nverts[i] && sL <= st.nverts[(size_t)st.cap + i]) {
+            BdptSoAAcc acc;
+            acc.st = st; acc.i = i;
+            if (bdpt_connect(s, p, sL, t, acc, st.eye_pixel[i], c)) {
+                if (c.shadow) push = true;
+                else {
+                    float* px = film + (size_t)c.pixel * 3;
+                    atomicAdd(px + 0, c.C.x); atomicAdd(px + 1, c.C.y); atomicAdd(px + 2, c.C.z);
+                }
+            }
+        }
+        const uint32_t b = __ballot_sync(0xffffffffu, push);
+        if (b) {
+            uint32_t pos = 0;
+            if (lane == (uint32_t)(__ffs(b) - 1)) pos = atomicAdd(&ctr->shadow_count, (uint32_t)__popc(b));
+            pos = __shfl_sync(0xffffffffu, pos, __ffs(b) - 1) + (uint32_t)__popc(b & ((1u << lane) - 1u));
+            if (push) {
+                Q_ST(sq.ray_o + pos, c.sh_o); Q_ST(sq.ray_d + pos, c.sh_d);
+                Q_ST(sq.contrib + pos, make_float4(c.C.x, c.C.y, c.C.z, __uint_as_float(c.pixel)));
+            }
+        }
+    }
 }
 
 // -- wavefront pt ----------------------------------------------------------------------------------
@@ -822,6 +922,15 @@ struct LmcuScene {
     DBuf<uint32_t> flags;                // [0] stack overflow
     DBuf<float> film;
     DBuf<double> film_acc;               // pt: FP64 sums the fp32 film is folded into (k_film_fold)
+    struct BdptPools {                   // bdpt: subpath SoA (BdptStore), strategy table, shadow queue, counters
+        DBuf<float4> va, vb, vc, vd, sq[3];
+        DBuf<float2> ve;
+        DBuf<int32_t> nverts;
+        DBuf<uint32_t> eye_pixel;
+        DBuf<int2> pairs;
+        DBuf<PtCounters> ctr;
+        uint32_t cap = 0; int mv = 0; size_t sq_cap = 0;
+    } bdpt;
     int film_w = 0, film_h = 0;
     // pt pools: one set per wavefront (LMCU_WAVES staggered wavefronts, each on its own stream)
     struct PtWave {
@@ -2036,8 +2145,8 @@ static int render_paths(LmcuScene* s, const LmcuRenderParams* p, float* film_rgb
     return LMCU_OK;
 }
 
-// renderer::bdpt (src/renderer/renderer_bdpt.cpp:304-407).  One kernel launch per pass of up to 4 Mi samples; the fp32 splat
-// film is folded into the FP64 sums after every pass.
+// renderer::bdpt (src/renderer/renderer_bdpt.cpp:304-407).  Passes of up to 1 Mi samples through k_bdpt_subpaths ->
+// k_bdpt_connect -> k_pt_shadow_q; the fp32 splat film is folded into the FP64 sums after every pass.
 int lmcu_render_bdpt(LmcuScene* s, const LmcuRenderParams* p, float* film_rgb, LmcuRenderStats* stats) {
     int rc = require_renderable(s, true);
     if (rc) return rc;
@@ -2065,19 +2174,51 @@ int lmcu_render_bdpt(LmcuScene* s, const LmcuRenderParams* p, float* film_rgb, L
     const unsigned fold_blocks = (unsigned)std::min<size_t>((s->film.n + 255) / 256, (size_t)s->num_sms * 8);
     const auto t0 = std::chrono::steady_clock::now();
     int64_t processed = 0, launches = 0;
-    const int64_t kPass = 1ll << 22;
+    // strategies (s, t) with min_verts <= s + t <= max_verts (renderer_bdpt.cpp:350-361); t = 0 never connects to a pinhole
+    std::vector<int2> pairs;
+    for (int n = std::max(2, min_verts); n <= p->max_verts; n++)
+        for (int sL = 0; sL < n; sL++) pairs.push_back(make_int2(sL, n - sL));
+    if (pairs.empty()) return fail(LMCU_ERR_INVALID_ARGUMENT, "bdpt: min_verts exceeds max_verts");
+    // samples per pass: the shadow queue holds one entry per (strategy, sample), at most 32 Mi (1.5 GB)
+    LmcuScene::BdptPools& B = s->bdpt;
+    const uint32_t cap = (uint32_t)std::min<size_t>(size_t(1) << 20, std::max<size_t>(size_t(1) << 14, ((size_t(1) << 25) / pairs.size()) & ~size_t(127)));
+    if (B.cap != cap || B.mv != p->max_verts) {
+        const size_t nv = (size_t)2 * p->max_verts * cap;
+        CU(B.va.alloc(nv)); CU(B.vb.alloc(nv)); CU(B.vc.alloc(nv)); CU(B.vd.alloc(nv)); CU(B.ve.alloc(nv));
+        CU(B.nverts.alloc((size_t)2 * cap)); CU(B.eye_pixel.alloc(cap));
+        if (!B.ctr.p) CU(B.ctr.alloc(1));
+        B.cap = cap; B.mv = p->max_verts;
+    }
+    if (B.sq_cap < pairs.size() * cap) {
+        for (int k = 0; k < 3; k++) CU(B.sq[k].alloc(pairs.size() * cap));
+        B.sq_cap = pairs.size() * cap;
+    }
+    if (B.pairs.n < pairs.size()) CU(B.pairs.alloc(pairs.size()));
+    CU(cudaMemcpyAsync(B.pairs.p, pairs.data(), pairs.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(B.ctr.p, 0, sizeof(PtCounters), st));
+    BdptStore store;
+    store.va = B.va.p; store.vb = B.vb.p; store.vc = B.vc.p; store.vd = B.vd.p; store.ve = B.ve.p;
+    store.nverts = B.nverts.p; store.eye_pixel = B.eye_pixel.p; store.cap = cap; store.mv = p->max_verts;
+    ShadowQueue sq;
+    sq.ray_o = B.sq[0].p; sq.ray_d = B.sq[1].p; sq.contrib = B.sq[2].p;
+    const unsigned q_blocks = (unsigned)(s->num_sms * s->ctas_per_sm);
     auto run_pass = [&](int64_t count) -> int {
         for (int64_t done = 0; done < count;) {
-            const int64_t n = std::min(kPass, count - done);
+            const int64_t n = std::min<int64_t>(cap, count - done);
             pp.sample_offset = (uint64_t)p->sample_offset + (uint64_t)processed;
             pp.total_paths = (uint64_t)n;
+            pp.capacity = cap;
             CU(cudaMemsetAsync(s->cursor.p, 0, sizeof(unsigned long long), st));
-            const unsigned blocks = (unsigned)std::min<int64_t>((n + 127) / 128, (int64_t)s->num_sms * 8);
-            if (s->fp32) k_bdpt<TriF32><<<blocks, 128, 0, st>>>(d, pp, min_verts, s->film.p, s->cursor.p, s->cursor.p + 3, s->flags.p);
-            else k_bdpt<TriF64><<<blocks, 128, 0, st>>>(d, pp, min_verts, s->film.p, s->cursor.p, s->cursor.p + 3, s->flags.p);
+            k_bdpt_reset<<<1, 1, 0, st>>>(B.ctr.p);
+            const unsigned sub_blocks = (unsigned)std::min<int64_t>((2 * n + 127) / 128, (int64_t)s->num_sms * 8);
+            if (s->fp32) k_bdpt_subpaths<TriF32><<<sub_blocks, 128, 0, st>>>(d, pp, store, s->cursor.p, s->cursor.p + 3, s->flags.p);
+            else k_bdpt_subpaths<TriF64><<<sub_blocks, 128, 0, st>>>(d, pp, store, s->cursor.p, s->cursor.p + 3, s->flags.p);
+            const dim3 cgrid((unsigned)std::min<int64_t>((n + 127) / 128, (int64_t)s->num_sms * 2), (unsigned)pairs.size());
+            k_bdpt_connect<<<cgrid, 128, 0, st>>>(d, pp, store, B.pairs.p, sq, s->film.p, B.ctr.p);
+            LMCU_DISPATCH(k_pt_shadow_q, s->fp32, false, q_blocks, LMCU_TRAV_BLOCK, st, d, sq, s->film.p, B.ctr.p);
             CU(cudaGetLastError());
             k_film_fold<<<fold_blocks, 256, 0, st>>>(s->film.p, s->film_acc.p, s->film.n);
-            launches += 2;
+            launches += 5;
             processed += n; done += n;
             if (p->progress) {
                 CU(cudaStreamSynchronize(st));
@@ -2112,15 +2253,19 @@ int lmcu_render_bdpt(LmcuScene* s, const LmcuRenderParams* p, float* film_rgb, L
     CU(cudaEventRecord(s->ev1, st));
     if (film_rgb) CU(cudaMemcpyAsync(film_rgb, s->film.p, s->film.n * sizeof(float), cudaMemcpyDeviceToHost, st));
     unsigned long long rays = 0;
+    PtCounters hc;
     CU(cudaMemcpyAsync(&rays, s->cursor.p + 3, sizeof(rays), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&hc, B.ctr.p, sizeof(hc), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     if (stats) {
         float ms = 0;
         CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
         memset(stats, 0, sizeof(*stats));
-        stats->elapsed = ms * 1e-3; stats->processed = processed; stats->paths = processed; stats->rays = (int64_t)rays;
+        stats->elapsed = ms * 1e-3; stats->processed = processed; stats->paths = processed;
+        stats->rays = (int64_t)(rays + hc.rays); stats->shadow_rays = (int64_t)hc.shadow_rays; stats->extend_rays = (int64_t)rays;
         stats->kernel_launches = launches;
     }
+    if (hc.overflow) return fail(LMCU_ERR_CUDA, "bvh traversal stack overflow");
     return check_overflow(s);
 }
 

@@ -4,6 +4,7 @@
   (3) size-independent properties at BASELINE.json's full sizes.
 Gates G1-G3 of SURVEY.md §8c; tolerances are written next to each assert."""
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -740,3 +741,22 @@ def test_bdpt_agrees_with_pt_and_rejects_what_it_does_not_support(tmp_path):
     with pytest.raises(lmcu.LmcuError, match="plain materials"):
         st.render("bdpt", abi.render_params(w, h, max_verts=8, **img))
     st.close()
+
+
+@pytest.mark.parametrize("scene", ["spheres", "env"])
+def test_bdpt_kernels_equal_the_one_thread_form(scene):
+    """The device runs bdpt as three kernels (subpaths -> strategy-major connections -> any-hit queue); tests/hostsim runs
+    the same functions as one loop per sample on the CPU.  Same counter-RNG draws, so the images agree to float rounding."""
+    import os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostsim"))
+    import sim
+    sb = scenes.cornell_spheres(12) if scene == "spheres" else scenes.instanced_spheres(grid=2, num_theta=10)
+    sc, ss = lmcu.Scene(sb), sim.SimScene(sb)
+    w, h = 48, 27
+    for mv, mn in ((7, 0), (4, 3)):
+        p = abi.render_params(w, h, max_verts=mv, min_verts=mn, num_samples=w * h * 8, primary_ray_sampling_mode=abi.PRIMARY_IMAGE)
+        fg, st = sc.render("bdpt", p)
+        fs = ss.render("bdpt", p)
+        assert st["rays"] == ss.rays
+        assert np.allclose(fg, fs, rtol=1e-3, atol=1e-4 * float(fs.max()))
+    sc.close()
