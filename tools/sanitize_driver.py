@@ -7,7 +7,7 @@
 
 Sizes are tiny (the tools slow kernels 10-100x); what matters is that each code path runs: builder (both
 triangle formats), accel batches (closest, counted, scalar), raycast / ao / pt (three sampling modes, image-space
-primary rays, sample-count scheduler) / lt, every material and light type, textures, the FP64 film fold and
+primary rays, sample-count scheduler) / lt / bdpt, every material and light type, textures, the FP64 film fold and
 finish, the film combine kernels, accel save / load."""
 import os
 import sys
@@ -21,7 +21,7 @@ import lmcu  # noqa: E402
 from lmcu import abi, scenes  # noqa: E402
 
 
-def run_scene(name, sb, w=48, h=27, spp=2, lt=True):
+def run_scene(name, sb, w=48, h=27, spp=2, lt=True, bdpt=True):
     sc = lmcu.Scene(sb, device=0)
     rays = scenes.camera_rays(sb.camera, w, h)
     hits = sc.intersect(rays)
@@ -45,6 +45,12 @@ def run_scene(name, sb, w=48, h=27, spp=2, lt=True):
         film, _ = sc.render("lt", abi.render_params(w, h, max_verts=6, num_samples=w * h * spp,
                                                     primary_ray_sampling_mode=abi.PRIMARY_IMAGE))
         assert np.isfinite(film).all()
+    if bdpt:
+        for mv, mn in ((6, 0), (3, 3)):
+            film, st = sc.render("bdpt", abi.render_params(w, h, max_verts=mv, min_verts=mn, num_samples=w * h * spp,
+                                                           primary_ray_sampling_mode=abi.PRIMARY_IMAGE))
+            assert np.isfinite(film).all() and st["rays"] > 0
+        sc.render("bdpt", abi.render_params(w, h, max_verts=5, scheduler=abi.SCHED_TIME, render_time=0.02, samples_per_iter=1000))
     # film combine kernels on one device (the peer pointers are this scene's own film)
     sc.render("pt", abi.render_params(w, h, spp=spp, max_verts=4, rescale=0), download=False)
     ptr = sc.film_device()[0]
@@ -65,8 +71,8 @@ def main():
     run_scene("instanced+envconst", scenes.instanced_spheres(grid=2, num_theta=8))
     run_scene("instanced+env", scenes.instanced_spheres(grid=2, num_theta=8,
                                                         env=scenes.env_light(os.path.join(tmp, "e.hdr"), 64, 32)))
-    run_scene("textured obj", scenes.textured_scene(tmp, 8, "obj"))
-    run_scene("textured mix", scenes.textured_scene(tmp, 8, "mix"), lt=False)
+    run_scene("textured obj", scenes.textured_scene(tmp, 8, "obj"), bdpt=False)
+    run_scene("textured mix", scenes.textured_scene(tmp, 8, "mix"), lt=False, bdpt=False)
     run_scene("delta lights", scenes.delta_lights_scene(2, 8))
     hf = scenes.heightfield_scene(40)
     hf.set_envconst((1, 1, 1))
