@@ -301,7 +301,7 @@ int lmcu_render_lt(LmcuScene* scene, const LmcuRenderParams* p, float* film_rgb,
  * to max_verts vertices (no Russian roulette), every connection (s, t) with min_verts <= s + t <= max_verts, power-heuristic
  * weights over all strategies of the connected path.  Keys used: max_verts (2..20), min_verts (0 = 2), seed, scheduler (sample:
  * num_samples; time: render_time, samples_per_iter), sample_offset, rescale (film *= w*h/processed, :390-391).  Image-space
- * scheduler only (renderer_bdpt.cpp:54-56).  LMCU_ERR_UNSUPPORTED for scenes with textured or mixture materials. */
+ * scheduler only (renderer_bdpt.cpp:54-56). */
 int lmcu_render_bdpt(LmcuScene* scene, const LmcuRenderParams* p, float* film_rgb, LmcuRenderStats* stats);
 /* Device film of the last render (width*height*3 floats) for the multi-GPU film reduce
  * (sample split: every rank renders with rescale=0, NCCL-reduces this buffer, then scales). */

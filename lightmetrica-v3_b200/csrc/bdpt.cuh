@@ -13,8 +13,8 @@
 //     subpath and are computed once per sample, so a connection costs 4 density evaluations + O(n) multiply-adds instead
 //     of the reference's O(n^2) evaluations.
 //
-// Scope: plain materials (diffuse, glossy, glass, mirror, mask), the five light types, the pinhole camera.  Mixture and
-// textured materials are refused on the host (lmcu_render_bdpt).
+// Scope: every material of the path tracer (diffuse, glossy, glass, mirror, mask, mapKd textures, mixture_wavefrontobj,
+// constant-weight mixtures), the five light types, the pinhole camera.
 #pragma once
 #include "kernels.cuh"
 
@@ -32,10 +32,13 @@ struct BVert {
     F3 p;                 // position (infinite: a representative point, unused)
     F3 n;                 // shading normal; infinite: PointGeometry::wo, the direction FROM the point at infinity
     F3 gn;
+    float tu, tv;         // texture coordinates (composite materials)
     int32_t mat;          // surface: index into DevScene::mats
     int32_t light;        // surface: light index of an emitter, else -1; light endpoint: its light
     uint8_t kind;         // BV_*
-    uint8_t comp;         // glass: 0 = reflection, 1 = refraction (material_glass.cpp:124-136)
+    uint8_t comp;         // the component Material::sample_component picked: glass 0 = reflection, 1 = refraction
+                          // (material_glass.cpp:124-136); mixture_wavefrontobj 0 = diffuse + glossy, 1 = alpha mask
+                          // (model_wavefrontobj.cpp:413-420); mixture_rr the entry; mixture_marginalized the group
     uint8_t infinite, degenerated;
 };
 
@@ -64,9 +67,94 @@ LMCU_HD float bv_G(const BVert& a, const BVert& b) {
     return c1 * c2 / L2;
 }
 
+// -- composite materials (textures, mixtures): the component by INDEX -----------------------------------------------------
+LMCU_HD SurfPoint bv_surf(const BVert& v) {
+    SurfPoint sp;
+    sp.p = v.p; sp.n = v.n; sp.gn = v.gn; sp.tu = v.tu; sp.tv = v.tv;
+    sp.prim = -1; sp.face = -1; sp.material = v.mat; sp.light = v.light;
+    return sp;
+}
+
+// Material::sample_component: the index pick_component() (kernels.cuh) would choose for uc0
+LMCU_HD int comp_pick_index(const DevScene& s, const MaterialDev& mat, const SurfPoint& sp, float uc0) {
+    if (mat.type <= MAT_MASK) return 0;
+    if (mat.type == MAT_MIXTURE_OBJ) {                                     // model_wavefrontobj.cpp:413-420
+        float alpha = 1.f;
+        if (mat.tex_kd >= 0 && mat.alpha_mask) alpha = tex_fetch(s.textures[mat.tex_kd], s.texels, sp.tu, sp.tv).w;
+        return uc0 < alpha ? 0 : 1;
+    }
+    if (mat.type == MAT_MIXTURE_RR) {                                      // material_mixture.cpp:61-65
+        float acc = 0.f;
+        int k = 0;
+        for (; k < mat.num_entries - 1; k++) {
+            acc += s.mix[mat.entry_offset + k].prob;
+            if (uc0 < acc) break;
+        }
+        return k;
+    }
+    const int n0 = mat.num_group0;                                         // marginalized, material_mixture.cpp:191-195
+    float acc = n0 > 0 ? s.mix[mat.entry_offset].group_prob : 0.f;
+    if (n0 > 0 && (uc0 < acc || n0 == mat.num_entries)) return 0;
+    int k = n0;
+    for (; k < mat.num_entries - 1; k++) {
+        acc += s.mix[mat.entry_offset + k].group_prob;
+        if (uc0 < acc) break;
+    }
+    return 1 + (k - n0);
+}
+
+// ... and the component record of that index (the same records pick_component() builds); 1 / cweight = pdf_component
+LMCU_HD VComp comp_by_index(const DevScene& s, const MaterialDev& mat, const SurfPoint& sp, int comp) {
+    VComp c;
+    c.kind = 0; c.first = 0; c.n = 1; c.marginal = false; c.cweight = 1.f; c.alpha = 1.f; c.wsel = 1.f;
+    if (mat.type <= MAT_MASK) {
+        c.l0 = resolve_lobe(s, mat, sp);
+        c.specular = mat_is_specular(mat.type);
+    } else if (mat.type == MAT_MIXTURE_OBJ) {
+        F3 kd = f3(mat.r, mat.g, mat.b);
+        float alpha = 1.f;
+        if (mat.tex_kd >= 0) {
+            const float4 t = tex_fetch(s.textures[mat.tex_kd], s.texels, sp.tu, sp.tv);
+            kd = f3(t.x, t.y, t.z);
+            if (mat.alpha_mask) alpha = t.w;
+        }
+        if (comp == 0) {
+            c.kind = 1; c.n = 2; c.marginal = true; c.specular = false;
+            c.cweight = 1.0f / alpha; c.alpha = alpha;
+            c.l0 = mat; c.l0.type = MAT_DIFFUSE; c.l0.r = kd.x; c.l0.g = kd.y; c.l0.b = kd.z;
+            c.l1 = mat; c.l1.type = MAT_GLOSSY; c.l1.r = mat.ks_r; c.l1.g = mat.ks_g; c.l1.b = mat.ks_b;
+            const float wd = max3(kd), wg = fmaxf(mat.ks_r, fmaxf(mat.ks_g, mat.ks_b));
+            c.wsel = (wd == 0.f && wg == 0.f) ? 1.f : wd / (wd + wg);
+        } else {
+            c.kind = 3; c.n = 0; c.specular = true;
+            c.cweight = 1.0f / (1.0f - alpha); c.alpha = alpha;
+        }
+    } else if (mat.type == MAT_MIXTURE_RR) {
+        const MixEntry e = s.mix[mat.entry_offset + comp];
+        c.kind = 2; c.first = mat.entry_offset + comp; c.n = 1;
+        c.cweight = 1.0f / e.prob;
+        c.specular = mat_is_specular(s.mats[e.material].type);
+    } else {
+        const int n0 = mat.num_group0;
+        if (comp == 0) {
+            c.kind = 2; c.first = mat.entry_offset; c.n = n0; c.marginal = true; c.specular = false;
+            c.cweight = n0 > 0 ? 1.0f / s.mix[mat.entry_offset].group_prob : 0.f;
+        } else {
+            const int k = n0 + comp - 1;
+            c.kind = 2; c.first = mat.entry_offset + k; c.n = 1; c.specular = true;
+            c.cweight = 1.0f / s.mix[mat.entry_offset + k].group_prob;
+        }
+    }
+    return c;
+}
+
 // path::is_specular_component (path.h:695-704)
+template <bool COMP>
 LMCU_HD bool bv_specular(const DevScene& s, const BVert& v) {
-    if (v.kind == BV_SURFACE) return mat_is_specular(s.mats[v.mat].type);
+    if (v.kind == BV_SURFACE) {
+        const MaterialDev& m = s.mats[v.mat];
+        return (!COMP || mat_is_plain(m)) ? mat_is_specular(m.type) : comp_by_index(s, m, bv_surf(v), v.comp).specular;
+    }
     if (v.kind == BV_LIGHT) return s.lights[v.light].type == LIGHT_DIRECTIONAL;
     return false;
 }
@@ -84,16 +172,22 @@ LMCU_HD float bv_glass_fr(const MaterialDev& m, F3 n, F3 wi) {
     return glass_fresnel(m, n, wi, wt, eta, total);
 }
 
-// path::pdf_component (path.h:228-234): 1 except for glass, whose two delta lobes are components picked by Fresnel
+// path::pdf_component (path.h:228-234): glass picks one of its two delta lobes by Fresnel; mixtures by their pmfs
+template <bool COMP>
 LMCU_HD float bv_pdf_comp(const DevScene& s, const BVert& v, F3 wi) {
     if (v.kind != BV_SURFACE) return 1.f;
     const MaterialDev& m = s.mats[v.mat];
-    if (m.type != MAT_GLASS) return 1.f;
-    const float Fr = bv_glass_fr(m, v.n, wi);
-    return v.comp == 0 ? Fr : 1.f - Fr;
+    if (m.type == MAT_GLASS) {
+        const float Fr = bv_glass_fr(m, v.n, wi);
+        return v.comp == 0 ? Fr : 1.f - Fr;
+    }
+    if (!COMP || mat_is_plain(m)) return 1.f;
+    const float cw = comp_by_index(s, m, bv_surf(v), v.comp).cweight;
+    return cw > 0.f ? 1.0f / cw : 0.f;
 }
 
 // path::pdf_direction with eval_delta = false (path.h:457-470): projected solid angle; delta lobes report 1
+template <bool COMP>
 LMCU_HD float bv_pdf_dir(const DevScene& s, const BVert& v, F3 wi, F3 wo) {
     if (v.kind == BV_CAMERA) {
         float rx, ry;
@@ -106,11 +200,14 @@ LMCU_HD float bv_pdf_dir(const DevScene& s, const BVert& v, F3 wi, F3 wo) {
         return 0.f;                                                            // lights at infinity: joint sampling only
     }
     const MaterialDev& m = s.mats[v.mat];
-    if (mat_is_specular(m.type)) return 1.f;
-    return mat_pdf(m, v.n, wi, wo);
+    if (!COMP || mat_is_plain(m)) return mat_is_specular(m.type) ? 1.f : mat_pdf(m, v.n, wi, wo);
+    const SurfPoint sp = bv_surf(v);
+    const VComp c = comp_by_index(s, m, sp, v.comp);
+    return c.specular ? 1.f : comp_pdf(s, c, sp, wi, wo);
 }
 
 // path::eval_contrb_direction (path.h:761-775).  le: TransDir::LE.  Surfaces include the shading-normal correction.
+template <bool COMP>
 LMCU_HD F3 bv_eval(const DevScene& s, const BVert& v, F3 wi, F3 wo, bool le, bool eval_delta) {
     if (v.kind == BV_CAMERA) {
         float rx, ry;
@@ -126,17 +223,30 @@ LMCU_HD F3 bv_eval(const DevScene& s, const BVert& v, F3 wi, F3 wo, bool le, boo
     }
     const MaterialDev& m = s.mats[v.mat];
     F3 f;
-    if (mat_is_specular(m.type)) {
-        if (eval_delta) return f3s(0.f);
-        if (m.type == MAT_GLASS) {                                         // material_glass.cpp:249-266
-            F3 wt; float eta; bool total;
-            const float Fr = glass_fresnel(m, v.n, wi, wt, eta, total);
-            f = v.comp == 0 ? f3s(Fr) : f3s((1.f - Fr) * (le ? 1.f : eta * eta));
+    if (!COMP || mat_is_plain(m)) {
+        if (mat_is_specular(m.type)) {
+            if (eval_delta) return f3s(0.f);
+            if (m.type == MAT_GLASS) {                                     // material_glass.cpp:249-266
+                F3 wt; float eta; bool total;
+                const float Fr = glass_fresnel(m, v.n, wi, wt, eta, total);
+                f = v.comp == 0 ? f3s(Fr) : f3s((1.f - Fr) * (le ? 1.f : eta * eta));
+            } else {
+                f = f3s(1.f);                                              // mirror, mask
+            }
         } else {
-            f = f3s(1.f);                                                  // mirror, mask
+            f = mat_eval(m, v.n, wi, wo);
         }
     } else {
-        f = mat_eval(m, v.n, wi, wo);
+        const SurfPoint sp = bv_surf(v);
+        const VComp c = comp_by_index(s, m, sp, v.comp);
+        if (c.specular) {
+            if (eval_delta) return f3s(0.f);
+            // delta components with eval_delta = false: the alpha mask evaluates to 1 - alpha (model_wavefrontobj.cpp:497-499),
+            // a specular mixture entry to weight x 1 (material_mixture.cpp:100-103,266-274; mirror and mask evaluate to 1)
+            f = c.kind == 3 ? f3s(1.0f - c.alpha) : (c.kind == 2 ? f3s(s.mix[c.first].weight) : f3s(1.f));
+        } else {
+            f = comp_eval(s, c, sp, wi, wo);
+        }
     }
     return f * sn_correction(v.n, v.gn, wi, wo, le);
 }
@@ -166,8 +276,15 @@ LMCU_HD float bv_pdf_primary_ray(const DevScene& s, const BVert& v, F3 wo) {
 
 // Material::sample_direction for the component stored at the vertex (materials' sample_direction; glass:
 // material_glass.cpp:140-166).  Returns false when the material rejects the sample (glossy below the surface).
-LMCU_HD bool bv_sample_dir(const DevScene& s, const BVert& v, F3 wi, float ud0, float ud1, F3& wo) {
+template <bool COMP>
+LMCU_HD bool bv_sample_dir(const DevScene& s, const BVert& v, F3 wi, float ud0, float ud1, float udc0, F3& wo) {
     const MaterialDev& m = s.mats[v.mat];
+    if (COMP && !mat_is_plain(m)) {
+        const SurfPoint sp = bv_surf(v);
+        const BsdfSample b = comp_sample(s, comp_by_index(s, m, sp, v.comp), sp, wi, ud0, ud1, udc0, false);
+        wo = b.wo;
+        return b.valid;
+    }
     if (m.type == MAT_GLASS) {
         if (v.comp == 0) { wo = reflection(wi, v.n); return true; }
         F3 wt; float eta; bool total;
@@ -182,7 +299,7 @@ LMCU_HD bool bv_sample_dir(const DevScene& s, const BVert& v, F3 wi, float ud0, 
 
 // path::sample_subpath (bidir.h:487-553).  Fills vs[0..n), returns n.
 // Random numbers: block 0 / 1 = the primary ray (RaySampleU), block 3 + 2k = component of vertex k, 4 + 2k = its direction.
-template <typename TriT>
+template <typename TriT, bool COMP>
 LMCU_HD int bdpt_subpath(const DevScene& s, const PtParams& p, uint64_t sidx, bool light_side, int max_verts, BVert* vs,
                          uint2* stack, BdptCounters* ctr) {
     if (max_verts <= 0) return 0;
@@ -192,7 +309,7 @@ LMCU_HD int bdpt_subpath(const DevScene& s, const PtParams& p, uint64_t sidx, bo
     {
         BVert v;
         v.mat = -1; v.light = -1; v.comp = 0; v.infinite = 0; v.degenerated = 0;
-        v.n = f3s(0.f); v.gn = f3s(0.f);
+        v.n = f3s(0.f); v.gn = f3s(0.f); v.tu = 0.f; v.tv = 0.f;
         const R4 u1 = rand4(p.seed, key, sidx, 0);
         const R4 u2 = rand4(p.seed, key, sidx, 1);
         if (!light_side) {                                                 // Camera_Pinhole::sample_ray (camera_pinhole.cpp:135-141)
@@ -243,7 +360,7 @@ LMCU_HD int bdpt_subpath(const DevScene& s, const PtParams& p, uint64_t sidx, bo
         if (!pt_trace<false, false, TriT>(s, make_float4(o.x, o.y, o.z, (float)kEps), make_float4(d.x, d.y, d.z, (float)kInf), h, stack, nullptr)) ctr->overflow = 1u;
         ctr->rays++;
         BVert v;
-        v.comp = 0; v.infinite = 0; v.degenerated = 0;
+        v.comp = 0; v.infinite = 0; v.degenerated = 0; v.tu = 0.f; v.tv = 0.f;
         if (h.tri < 0) {
             if (s.env_light < 0) break;
             v.kind = BV_LIGHT; v.light = s.env_light; v.mat = -1; v.infinite = 1;
@@ -252,18 +369,19 @@ LMCU_HD int bdpt_subpath(const DevScene& s, const PtParams& p, uint64_t sidx, bo
             break;
         }
         const SurfPoint sp = surface_point(s, (uint32_t)h.tri, (float)h.u, (float)h.v);
-        v.kind = BV_SURFACE; v.p = sp.p; v.n = sp.n; v.gn = sp.gn; v.mat = sp.material; v.light = sp.light;
+        v.kind = BV_SURFACE; v.p = sp.p; v.n = sp.n; v.gn = sp.gn; v.tu = sp.tu; v.tv = sp.tv; v.mat = sp.material; v.light = sp.light;
         const F3 wi = -d;
         const MaterialDev& m = s.mats[sp.material];
         const R4 uc = rand4(p.seed, key, sidx, 3u + 2u * (uint32_t)n);
         if (m.type == MAT_GLASS) v.comp = uc.x < bv_glass_fr(m, sp.n, wi) ? 0 : 1;     // material_glass.cpp:124-136
+        else if (COMP && !mat_is_plain(m)) v.comp = (uint8_t)comp_pick_index(s, m, sp, uc.x);
         vs[n++] = v;
         if (n >= max_verts) break;
         // next direction (path::sample_direction at a surface, path.h:414-424); wi is the direction to the previous VERTEX
         const F3 wiv = bv_dir(v, vs[n - 2]);
         const R4 ud = rand4(p.seed, key, sidx, 2u + 2u * (uint32_t)n);
         F3 wo;
-        if (!bv_sample_dir(s, v, wiv, ud.x, ud.y, wo)) break;
+        if (!bv_sample_dir<COMP>(s, v, wiv, ud.x, ud.y, ud.z, wo)) break;
         o = v.p; d = wo;
     }
     return n;
@@ -271,6 +389,7 @@ LMCU_HD int bdpt_subpath(const DevScene& s, const PtParams& p, uint64_t sidx, bo
 
 // Path::eval_subpath_sampling_weight (bidir.h:252-294) for every prefix length: alpha[l], l = 0..n.  pc[i] = the component
 // pdf of vertex i that went into alpha[i + 1] (the caller takes it out again when the vertex becomes an endpoint).
+template <bool COMP>
 LMCU_HD void bdpt_alphas(const DevScene& s, const BVert* vs, int n, bool le, F3* alpha, float* pc) {
     alpha[0] = f3s(1.f);
     for (int l = 1; l <= n; l++) alpha[l] = f3s(0.f);
@@ -282,8 +401,8 @@ LMCU_HD void bdpt_alphas(const DevScene& s, const BVert* vs, int n, bool le, F3*
     } else {
         if (n < 2) return;
         const F3 d01 = bv_dir(vs[0], vs[1]);
-        const F3 f = bv_eval(s, vs[0], f3s(0.f), d01, le, false);
-        pc[1] = bv_pdf_comp(s, vs[1], -d01);
+        const F3 f = bv_eval<COMP>(s, vs[0], f3s(0.f), d01, le, false);
+        pc[1] = bv_pdf_comp<COMP>(s, vs[1], -d01);
         const float pr = bv_pdf_primary_ray(s, vs[0], d01) * pc[1];
         if (is_zero(f) || !(pr > 0.f)) return;
         alpha[2] = f * (1.0f / pr);
@@ -293,9 +412,9 @@ LMCU_HD void bdpt_alphas(const DevScene& s, const BVert* vs, int n, bool le, F3*
         const BVert& v = vs[i];
         const F3 wi = i > 0 ? bv_dir(v, vs[i - 1]) : f3s(0.f);
         const F3 wo = bv_dir(v, vs[i + 1]);
-        const F3 f = bv_eval(s, v, wi, wo, le, false);
-        pc[i + 1] = bv_pdf_comp(s, vs[i + 1], -wo);
-        const float pd = bv_pdf_dir(s, v, wi, wo) * pc[i + 1];
+        const F3 f = bv_eval<COMP>(s, v, wi, wo, le, false);
+        pc[i + 1] = bv_pdf_comp<COMP>(s, vs[i + 1], -wo);
+        const float pd = bv_pdf_dir<COMP>(s, v, wi, wo) * pc[i + 1];
         if (is_zero(f) || !(pd > 0.f)) return;
         alpha[i + 2] = alpha[i + 1] * f * (1.0f / pd);
     }
@@ -303,10 +422,11 @@ LMCU_HD void bdpt_alphas(const DevScene& s, const BVert* vs, int n, bool le, F3*
 
 // Density (area measure x component) of generating vertex `cur` from `prev`, whose own previous vertex is `prev2` (null for
 // an endpoint): one factor of the products in Path::pdf_bidir (bidir.h:397-431)
+template <bool COMP>
 LMCU_HD float bdpt_gen_pdf(const DevScene& s, const BVert* prev2, const BVert& prev, const BVert& cur) {
     const F3 wo = bv_dir(prev, cur);
     const F3 wi = prev2 ? bv_dir(prev, *prev2) : f3s(0.f);
-    return bv_pdf_dir(s, prev, wi, wo) * bv_G(prev, cur) * bv_pdf_comp(s, cur, -wo);
+    return bv_pdf_dir<COMP>(s, prev, wi, wo) * bv_G(prev, cur) * bv_pdf_comp<COMP>(s, cur, -wo);
 }
 
 // Per-subpath halves of the strategy densities (Path::pdf_bidir, bidir.h:388-437).  For vertex i of a subpath:
@@ -315,20 +435,21 @@ LMCU_HD float bdpt_gen_pdf(const DevScene& s, const BVert* prev2, const BVert& p
 //   R[i] = density of generating it from the OTHER end, from vertex i+1 given i+2 (defined for i + 2 < n),
 //   spec[i] = the vertex is a delta interaction.
 // None of them depends on the connection; the four densities around the connecting edge are evaluated per strategy.
+template <bool COMP>
 LMCU_HD void bdpt_subpath_pdfs(const DevScene& s, const BVert* vs, int n, float* F, float* R, bool* spec) {
-    for (int i = 0; i < n; i++) spec[i] = bv_specular(s, vs[i]);
+    for (int i = 0; i < n; i++) spec[i] = bv_specular<COMP>(s, vs[i]);
     if (n == 0) return;
     const bool conn0 = bv_connectable(s, vs[0]);
     F[0] = conn0 ? bv_pdf_position(s, vs[0]) : 1.f;
     for (int i = 1; i < n; i++) {
         if (i == 1 && !conn0) {
             const F3 d01 = bv_dir(vs[0], vs[1]);
-            F[1] = bv_pdf_primary_ray(s, vs[0], d01) * bv_G(vs[0], vs[1]) * bv_pdf_comp(s, vs[1], -d01);
+            F[1] = bv_pdf_primary_ray(s, vs[0], d01) * bv_G(vs[0], vs[1]) * bv_pdf_comp<COMP>(s, vs[1], -d01);
         } else {
-            F[i] = bdpt_gen_pdf(s, i >= 2 ? &vs[i - 2] : nullptr, vs[i - 1], vs[i]);
+            F[i] = bdpt_gen_pdf<COMP>(s, i >= 2 ? &vs[i - 2] : nullptr, vs[i - 1], vs[i]);
         }
     }
-    for (int i = 0; i + 2 < n; i++) R[i] = bdpt_gen_pdf(s, &vs[i + 2], vs[i + 1], vs[i]);
+    for (int i = 0; i + 2 < n; i++) R[i] = bdpt_gen_pdf<COMP>(s, &vs[i + 2], vs[i + 1], vs[i]);
 }
 
 // What one connection (s, t) produces: the MIS-weighted contribution, the pixel it belongs to and — for s >= 1 — the
@@ -346,7 +467,7 @@ struct BdptConn {
 //   BVert Y(i), Z(j)   light / eye subpath vertices      F3 aL(l), aE(l)   alpha of the first l vertices
 //   float pcE(j)       component pdf inside aE(j + 1)     float yF(i), yR(i), zF(j), zR(j); bool ySpec(i), zSpec(j)
 // Returns false when the strategy contributes nothing.
-template <typename Acc>
+template <bool COMP, typename Acc>
 LMCU_HD bool bdpt_connect(const DevScene& s, const PtParams& p, int sL, int t, const Acc& a, uint32_t eye_pixel, BdptConn& out) {
     const int n = sL + t;
     out.pixel = eye_pixel;
@@ -358,15 +479,15 @@ LMCU_HD bool bdpt_connect(const DevScene& s, const PtParams& p, int sL, int t, c
     if (sL == 0) {
         if (vE.light < 0 || vE.kind == BV_CAMERA) return false;                       // scene->is_light(vL.sp)
         x0 = vE; x0.kind = BV_LIGHT;
-        const F3 cst = bv_eval(s, x0, f3s(0.f), bv_dir(x0, vEp), true, true);         // Path::eval_connection_term, s = 0
+        const F3 cst = bv_eval<COMP>(s, x0, f3s(0.f), bv_dir(x0, vEp), true, true);         // Path::eval_connection_term, s = 0
         C = a.aE(t) * a.pcE(t - 1) * cst;                                             // the endpoint's component pdf is 1
     } else {
         vL = a.Y(sL - 1);
         if (sL >= 2) vLp = a.Y(sL - 2);
         if (vL.infinite || vE.infinite) return false;
         const F3 dLE = bv_dir(vL, vE);
-        const F3 fsL = bv_eval(s, vL, sL >= 2 ? bv_dir(vL, vLp) : f3s(0.f), dLE, true, true);
-        const F3 fsE = bv_eval(s, vE, t >= 2 ? bv_dir(vE, vEp) : f3s(0.f), -dLE, false, true);
+        const F3 fsL = bv_eval<COMP>(s, vL, sL >= 2 ? bv_dir(vL, vLp) : f3s(0.f), dLE, true, true);
+        const F3 fsE = bv_eval<COMP>(s, vE, t >= 2 ? bv_dir(vE, vEp) : f3s(0.f), -dLE, false, true);
         C = a.aL(sL) * a.aE(t) * fsL * fsE * bv_G(vL, vE);
         if (t == 1) {
             float rx, ry;
@@ -387,23 +508,23 @@ LMCU_HD bool bdpt_connect(const DevScene& s, const PtParams& p, int sL, int t, c
     bool spec0, conn0, degen0;
     float fl_a, fl_b = 0.f, fe_a, fe_b = 0.f, fl0 = 0.f;       // sL >= 1: fL[sL], fL[sL+1], fE[sL-1], fE[sL-2];  sL = 0: fL[1], -, fE[0], -, fL[0]
     if (sL == 0) {
-        conn0 = bv_connectable(s, x0); spec0 = bv_specular(s, x0); degen0 = x0.degenerated != 0;
+        conn0 = bv_connectable(s, x0); spec0 = bv_specular<COMP>(s, x0); degen0 = x0.degenerated != 0;
         fl0 = conn0 ? bv_pdf_position(s, x0) : 1.f;
-        if (conn0) fl_a = bdpt_gen_pdf(s, nullptr, x0, vEp);
+        if (conn0) fl_a = bdpt_gen_pdf<COMP>(s, nullptr, x0, vEp);
         else {
             const F3 d01 = bv_dir(x0, vEp);
-            fl_a = bv_pdf_primary_ray(s, x0, d01) * bv_G(x0, vEp) * bv_pdf_comp(s, vEp, -d01);
+            fl_a = bv_pdf_primary_ray(s, x0, d01) * bv_G(x0, vEp) * bv_pdf_comp<COMP>(s, vEp, -d01);
         }
         BVert vEpp;
         if (t >= 3) vEpp = a.Z(t - 3);
-        fe_a = bdpt_gen_pdf(s, t >= 3 ? &vEpp : nullptr, vEp, x0);
+        fe_a = bdpt_gen_pdf<COMP>(s, t >= 3 ? &vEpp : nullptr, vEp, x0);
     } else {
         const BVert y0 = sL == 1 ? vL : (sL == 2 ? vLp : a.Y(0));
         conn0 = bv_connectable(s, y0); spec0 = a.ySpec(0); degen0 = y0.degenerated != 0;
-        fl_a = bdpt_gen_pdf(s, sL >= 2 ? &vLp : nullptr, vL, vE);
-        if (t >= 2) fl_b = bdpt_gen_pdf(s, &vL, vE, vEp);
-        fe_a = bdpt_gen_pdf(s, t >= 2 ? &vEp : nullptr, vE, vL);
-        if (sL >= 2) fe_b = bdpt_gen_pdf(s, &vE, vL, vLp);
+        fl_a = bdpt_gen_pdf<COMP>(s, sL >= 2 ? &vLp : nullptr, vL, vE);
+        if (t >= 2) fl_b = bdpt_gen_pdf<COMP>(s, &vL, vE, vEp);
+        fe_a = bdpt_gen_pdf<COMP>(s, t >= 2 ? &vEp : nullptr, vE, vL);
+        if (sL >= 2) fe_b = bdpt_gen_pdf<COMP>(s, &vE, vL, vLp);
     }
     auto FL = [&](int i) -> float {
         if (sL == 0) return i == 0 ? fl0 : (i == 1 ? fl_a : a.zR(n - 1 - i));
@@ -473,7 +594,7 @@ LMCU_HD uint32_t bdpt_eye_pixel(const DevScene& s, const PtParams& p, const BVer
 // One sample by one thread: both subpaths, every connection; splat(pixel, C) receives the weighted contributions.  This is
 // the form tests/hostsim runs on the CPU; the device runs the same functions as three kernels (lmcu.cu: k_bdpt_subpaths,
 // k_bdpt_connect, k_pt_shadow_q).
-template <typename TriT, typename Splat>
+template <typename TriT, bool COMP, typename Splat>
 LMCU_HD void bdpt_sample(const DevScene& s, const PtParams& p, int min_verts, uint64_t g, uint2* stack, BdptCounters* ctr, Splat& splat) {
     const uint64_t sidx = p.sample_offset + g;
     BVert zs[kBdptMaxVerts], ys[kBdptMaxVerts];
@@ -481,12 +602,12 @@ LMCU_HD void bdpt_sample(const DevScene& s, const PtParams& p, int min_verts, ui
     float pcE[kBdptMaxVerts], pcL[kBdptMaxVerts];
     float zF[kBdptMaxVerts], zR[kBdptMaxVerts], yF[kBdptMaxVerts], yR[kBdptMaxVerts];
     bool zSpec[kBdptMaxVerts], ySpec[kBdptMaxVerts];
-    const int nE = bdpt_subpath<TriT>(s, p, sidx, false, p.max_verts, zs, stack, ctr);
-    const int nL = bdpt_subpath<TriT>(s, p, sidx, true, p.max_verts, ys, stack, ctr);
-    bdpt_alphas(s, zs, nE, false, aE, pcE);
-    bdpt_alphas(s, ys, nL, true, aL, pcL);
-    bdpt_subpath_pdfs(s, zs, nE, zF, zR, zSpec);
-    bdpt_subpath_pdfs(s, ys, nL, yF, yR, ySpec);
+    const int nE = bdpt_subpath<TriT, COMP>(s, p, sidx, false, p.max_verts, zs, stack, ctr);
+    const int nL = bdpt_subpath<TriT, COMP>(s, p, sidx, true, p.max_verts, ys, stack, ctr);
+    bdpt_alphas<COMP>(s, zs, nE, false, aE, pcE);
+    bdpt_alphas<COMP>(s, ys, nL, true, aL, pcL);
+    bdpt_subpath_pdfs<COMP>(s, zs, nE, zF, zR, zSpec);
+    bdpt_subpath_pdfs<COMP>(s, ys, nL, yF, yR, ySpec);
     const uint32_t eye_pixel = bdpt_eye_pixel(s, p, zs, nE);
     BdptLocalAcc acc;
     acc.ys = ys; acc.zs = zs; acc.aL_ = aL; acc.aE_ = aE; acc.pcE_ = pcE;
@@ -496,7 +617,7 @@ LMCU_HD void bdpt_sample(const DevScene& s, const PtParams& p, int min_verts, ui
             const int n = sL + t;
             if (n < min_verts || n > p.max_verts || n < 2) continue;
             BdptConn c;
-            if (!bdpt_connect(s, p, sL, t, acc, eye_pixel, c)) continue;
+            if (!bdpt_connect<COMP>(s, p, sL, t, acc, eye_pixel, c)) continue;
             if (c.shadow) {
                 HitD h;
                 if (!pt_trace<true, false, TriT>(s, c.sh_o, c.sh_d, h, stack, nullptr)) ctr->overflow = 1u;

@@ -309,6 +309,7 @@ struct BdptStore {
     float4* vc;        //               gn.xyz, light
     float4* vd;        //               alpha of the first k + 1 vertices, component pdf of vertex k
     float2* ve;        //               F (sign bit: the vertex is specular), R  (bdpt_subpath_pdfs)
+    float2* vt;        //               texture coordinates (null when no material reads a texture)
     int32_t* nverts;   // [2][cap]
     uint32_t* eye_pixel;   // [cap]
     uint32_t cap;
@@ -328,6 +329,8 @@ struct BdptSoAAcc {
         v.kind = (uint8_t)(bits & 0xffu); v.comp = (uint8_t)((bits >> 8) & 0xffu);
         v.infinite = (uint8_t)((bits >> 16) & 1u); v.degenerated = (uint8_t)((bits >> 17) & 1u);
         v.mat = (int32_t)__float_as_uint(b.w); v.light = (int32_t)__float_as_uint(c.w);
+        v.tu = 0.f; v.tv = 0.f;
+        if (st.vt) { const float2 t = st.vt[o]; v.tu = t.x; v.tv = t.y; }
         return v;
     }
     __device__ __forceinline__ BVert Y(int k) const { return load(1, k); }
@@ -348,7 +351,7 @@ struct BdptSoAAcc {
     __device__ __forceinline__ bool zSpec(int k) const { return signbit(st.ve[st.at(0, k, i)].x); }
 };
 
-template <typename TriT>
+template <typename TriT, bool COMP>
 __global__ void __launch_bounds__(128) k_bdpt_subpaths(DevScene s, PtParams p, BdptStore st, unsigned long long* cursor,
                                                        unsigned long long* rays, uint32_t* overflow) {
     uint2 stack[kStackSize];
@@ -366,9 +369,9 @@ __global__ void __launch_bounds__(128) k_bdpt_subpaths(DevScene s, PtParams p, B
         if (idx >= total) continue;
         const int side = idx >= p.total_paths ? 1 : 0;
         const uint32_t g = (uint32_t)(idx - (side ? p.total_paths : 0ull));
-        const int n = bdpt_subpath<TriT>(s, p, p.sample_offset + g, side != 0, p.max_verts, vs, stack, &ctr);
-        bdpt_alphas(s, vs, n, side != 0, alpha, pc);
-        bdpt_subpath_pdfs(s, vs, n, F, R, spec);
+        const int n = bdpt_subpath<TriT, COMP>(s, p, p.sample_offset + g, side != 0, p.max_verts, vs, stack, &ctr);
+        bdpt_alphas<COMP>(s, vs, n, side != 0, alpha, pc);
+        bdpt_subpath_pdfs<COMP>(s, vs, n, F, R, spec);
         st.nverts[(size_t)side * st.cap + g] = n;
         if (!side) st.eye_pixel[g] = bdpt_eye_pixel(s, p, vs, n);
         for (int k = 0; k < n; k++) {
@@ -380,6 +383,7 @@ __global__ void __launch_bounds__(128) k_bdpt_subpaths(DevScene s, PtParams p, B
             st.vc[o] = make_float4(v.gn.x, v.gn.y, v.gn.z, __uint_as_float((uint32_t)v.light));
             st.vd[o] = make_float4(alpha[k + 1].x, alpha[k + 1].y, alpha[k + 1].z, pc[k]);
             st.ve[o] = make_float2(spec[k] ? -F[k] : F[k], k + 2 < n ? R[k] : 0.f);
+            if (st.vt) st.vt[o] = make_float2(v.tu, v.tv);
         }
     }
     atomicAdd(rays, (unsigned long long)ctr.rays);
@@ -388,6 +392,7 @@ __global__ void __launch_bounds__(128) k_bdpt_subpaths(DevScene s, PtParams p, B
 
 __global__ void k_bdpt_reset(PtCounters* ctr) { ctr->shadow_count = 0; ctr->fetch_shadow = 0; }
 
+template <bool COMP>
 __global__ void __launch_bounds__(128) k_bdpt_connect(DevScene s, PtParams p, BdptStore st, const int2* __restrict__ pairs, ShadowQueue sq,
                                                       float* film, PtCounters* ctr) {
     const int2 pr = pairs[blockIdx.y];
@@ -400,7 +405,7 @@ __global__ void __launch_bounds__(128) k_bdpt_connect(DevScene s, PtParams p, Bd
         if (i < total && t <= st.nverts[i] && sL <= st.nverts[(size_t)st.cap + i]) {
             BdptSoAAcc acc;
             acc.st = st; acc.i = i;
-            if (bdpt_connect(s, p, sL, t, acc, st.eye_pixel[i], c)) {
+            if (bdpt_connect<COMP>(s, p, sL, t, acc, st.eye_pixel[i], c)) {
                 if (c.shadow) push = true;
                 else {
                     float* px = film + (size_t)c.pixel * 3;
@@ -924,7 +929,7 @@ struct LmcuScene {
     DBuf<double> film_acc;               // pt: FP64 sums the fp32 film is folded into (k_film_fold)
     struct BdptPools {                   // bdpt: subpath SoA (BdptStore), strategy table, shadow queue, counters
         DBuf<float4> va, vb, vc, vd, sq[3];
-        DBuf<float2> ve;
+        DBuf<float2> ve, vt;
         DBuf<int32_t> nverts;
         DBuf<uint32_t> eye_pixel;
         DBuf<int2> pairs;
@@ -2160,8 +2165,6 @@ int lmcu_render_bdpt(LmcuScene* s, const LmcuRenderParams* p, float* film_rgb, L
     }
     if (p->max_verts < 2 || p->max_verts > kBdptMaxVerts) return fail(LMCU_ERR_INVALID_ARGUMENT, "bdpt: max_verts must be in 2..20");
     const int min_verts = p->min_verts > 0 ? p->min_verts : 2;
-    if (s->composite)
-        return fail(LMCU_ERR_UNSUPPORTED, "bdpt supports plain materials only (diffuse, glossy, glass, mirror, mask); the scene has a textured or mixture material");
     CU(cudaSetDevice(s->device));
     rc = ensure_film(s, p->width, p->height, true);
     if (rc) return rc;
@@ -2185,6 +2188,7 @@ int lmcu_render_bdpt(LmcuScene* s, const LmcuRenderParams* p, float* film_rgb, L
     if (B.cap != cap || B.mv != p->max_verts) {
         const size_t nv = (size_t)2 * p->max_verts * cap;
         CU(B.va.alloc(nv)); CU(B.vb.alloc(nv)); CU(B.vc.alloc(nv)); CU(B.vd.alloc(nv)); CU(B.ve.alloc(nv));
+        CU(B.vt.alloc(0));
         CU(B.nverts.alloc((size_t)2 * cap)); CU(B.eye_pixel.alloc(cap));
         if (!B.ctr.p) CU(B.ctr.alloc(1));
         B.cap = cap; B.mv = p->max_verts;
@@ -2198,6 +2202,8 @@ int lmcu_render_bdpt(LmcuScene* s, const LmcuRenderParams* p, float* film_rgb, L
     CU(cudaMemsetAsync(B.ctr.p, 0, sizeof(PtCounters), st));
     BdptStore store;
     store.va = B.va.p; store.vb = B.vb.p; store.vc = B.vc.p; store.vd = B.vd.p; store.ve = B.ve.p;
+    if (d.uv && B.vt.n != (size_t)2 * p->max_verts * cap) CU(B.vt.alloc((size_t)2 * p->max_verts * cap));
+    store.vt = d.uv ? B.vt.p : nullptr;
     store.nverts = B.nverts.p; store.eye_pixel = B.eye_pixel.p; store.cap = cap; store.mv = p->max_verts;
     ShadowQueue sq;
     sq.ray_o = B.sq[0].p; sq.ray_d = B.sq[1].p; sq.contrib = B.sq[2].p;
@@ -2211,10 +2217,16 @@ int lmcu_render_bdpt(LmcuScene* s, const LmcuRenderParams* p, float* film_rgb, L
             CU(cudaMemsetAsync(s->cursor.p, 0, sizeof(unsigned long long), st));
             k_bdpt_reset<<<1, 1, 0, st>>>(B.ctr.p);
             const unsigned sub_blocks = (unsigned)std::min<int64_t>((2 * n + 127) / 128, (int64_t)s->num_sms * 8);
-            if (s->fp32) k_bdpt_subpaths<TriF32><<<sub_blocks, 128, 0, st>>>(d, pp, store, s->cursor.p, s->cursor.p + 3, s->flags.p);
-            else k_bdpt_subpaths<TriF64><<<sub_blocks, 128, 0, st>>>(d, pp, store, s->cursor.p, s->cursor.p + 3, s->flags.p);
+            if (s->composite) {     // textured / mixture materials: the <true> instantiations (more registers), as for the pt shade kernel
+                if (s->fp32) k_bdpt_subpaths<TriF32, true><<<sub_blocks, 128, 0, st>>>(d, pp, store, s->cursor.p, s->cursor.p + 3, s->flags.p);
+                else k_bdpt_subpaths<TriF64, true><<<sub_blocks, 128, 0, st>>>(d, pp, store, s->cursor.p, s->cursor.p + 3, s->flags.p);
+            } else {
+                if (s->fp32) k_bdpt_subpaths<TriF32, false><<<sub_blocks, 128, 0, st>>>(d, pp, store, s->cursor.p, s->cursor.p + 3, s->flags.p);
+                else k_bdpt_subpaths<TriF64, false><<<sub_blocks, 128, 0, st>>>(d, pp, store, s->cursor.p, s->cursor.p + 3, s->flags.p);
+            }
             const dim3 cgrid((unsigned)std::min<int64_t>((n + 127) / 128, (int64_t)s->num_sms * 2), (unsigned)pairs.size());
-            k_bdpt_connect<<<cgrid, 128, 0, st>>>(d, pp, store, B.pairs.p, sq, s->film.p, B.ctr.p);
+            if (s->composite) k_bdpt_connect<true><<<cgrid, 128, 0, st>>>(d, pp, store, B.pairs.p, sq, s->film.p, B.ctr.p);
+            else k_bdpt_connect<false><<<cgrid, 128, 0, st>>>(d, pp, store, B.pairs.p, sq, s->film.p, B.ctr.p);
             LMCU_DISPATCH(k_pt_shadow_q, s->fp32, false, q_blocks, LMCU_TRAV_BLOCK, st, d, sq, s->film.p, B.ctr.p);
             CU(cudaGetLastError());
             k_film_fold<<<fold_blocks, 256, 0, st>>>(s->film.p, s->film_acc.p, s->film.n);

@@ -1255,8 +1255,7 @@ LM_COMP_REG_IMPL(Renderer_LT_Cuda, "renderer::lt_cuda");
    Bidirectional path tracing on the GPU: ``renderer::bdpt`` (src/renderer/renderer_bdpt.cpp:304-407) through
    ``lmcu_render_bdpt``.  Same parameters: ``scene``, ``output``, ``max_verts`` (2..20), ``min_verts`` (default 2), ``seed``,
    ``scheduler`` (``sample`` with ``num_samples`` | ``time`` with ``render_time``, ``samples_per_iter``); plus ``device`` and
-   ``cache`` as in ``renderer::pt_cuda``.  Plain materials only (diffuse, glossy, glass, mirror, mask): a scene with a
-   textured or mixture material raises ``Error::Unsupported``.
+   ``cache`` as in ``renderer::pt_cuda``.
 \endrst
 */
 class Renderer_BDPT_Cuda final : public Renderer_SPI_CudaBase {

@@ -426,7 +426,7 @@ int hostsim_bdpt(void* p, const LmcuRenderParams* rp, float* film, long long* ra
     long long total_rays = 0;
     for (uint64_t g = 0; g < pp.total_paths; g++) {
         bc.rays = 0;
-        if (s.fp32) bdpt_sample<TriF32>(d, pp, min_verts, g, stack, &bc, splat); else bdpt_sample<TriF64>(d, pp, min_verts, g, stack, &bc, splat);
+        if (s.fp32) bdpt_sample<TriF32, true>(d, pp, min_verts, g, stack, &bc, splat); else bdpt_sample<TriF64, true>(d, pp, min_verts, g, stack, &bc, splat);
         total_rays += bc.rays;
     }
     if (bc.overflow) { g_err = "bvh traversal stack overflow"; return 1; }

@@ -686,16 +686,18 @@ def test_g3_lt_vs_reference(reference, tmp_path, scene):
     rs.close(); sc.close()
 
 
-@pytest.mark.parametrize("scene", ["spheres", "env", "delta", "envmap"])
+@pytest.mark.parametrize("scene", ["spheres", "env", "delta", "envmap", "obj", "mix"])
 def test_g3_bdpt_vs_reference(reference, tmp_path, scene):
     """SURVEY.md 8f N4 (the other integrators): renderer::bdpt on the device (lmcu_render_bdpt) against the reference's
     renderer::bdpt at equal sample counts — area light + glass / diffuse (caustic paths through s >= 2 strategies), constant
     environment + glossy / mirror / glass (lights at infinity are not connectable: joint primary-ray densities), point +
-    directional lights (degenerated and specular endpoints), an environment map.  G3 gates as for pt / lt."""
+    directional lights (degenerated and specular endpoints), an environment map, the OBJ-import material set (textures, alpha
+    mask, mixture_wavefrontobj) and the constant-weight mixtures.  G3 gates as for pt / lt."""
     import os
     sb = {"spheres": lambda: scenes.cornell_spheres(32), "env": lambda: scenes.instanced_spheres(grid=2, num_theta=24),
           "delta": lambda: scenes.delta_lights_scene(2, 16),
-          "envmap": lambda: scenes.instanced_spheres(grid=2, num_theta=16, env=scenes.env_light(os.path.join(str(tmp_path), "e.hdr"), 64, 32))}[scene]()
+          "envmap": lambda: scenes.instanced_spheres(grid=2, num_theta=16, env=scenes.env_light(os.path.join(str(tmp_path), "e.hdr"), 64, 32)),
+          "obj": lambda: scenes.textured_scene(tmp_path, 12, "obj"), "mix": lambda: scenes.textured_scene(tmp_path, 12, "mix")}[scene]()
     sc, rs = lmcu.Scene(sb), reference.RefScene(sb)
     w, h, B, spp = 128, 72, 4, 32
     n = w * h * spp
@@ -718,9 +720,9 @@ def test_g3_bdpt_vs_reference(reference, tmp_path, scene):
     rs.close(); sc.close()
 
 
-def test_bdpt_agrees_with_pt_and_rejects_what_it_does_not_support(tmp_path):
+def test_bdpt_agrees_with_pt_and_rejects_bad_arguments():
     """Bidirectional and unidirectional estimators of the same integral: image means of bdpt and pt (MIS) agree; path length
-    selection by min_verts / max_verts partitions the image; unsupported inputs fail loudly."""
+    selection by min_verts / max_verts partitions the image; bad arguments fail loudly."""
     sb = scenes.cornell_spheres(24)
     sc = lmcu.Scene(sb)
     w, h, spp = 160, 90, 256
@@ -736,27 +738,26 @@ def test_bdpt_agrees_with_pt_and_rejects_what_it_does_not_support(tmp_path):
         sc.render("bdpt", abi.render_params(w, h, max_verts=21, **img))
     with pytest.raises(lmcu.LmcuError, match="num_samples"):
         sc.render("bdpt", abi.render_params(w, h, max_verts=8, primary_ray_sampling_mode=abi.PRIMARY_IMAGE))
+    with pytest.raises(lmcu.LmcuError, match="min_verts"):
+        sc.render("bdpt", abi.render_params(w, h, max_verts=4, min_verts=5, **img))
     sc.close()
-    st = lmcu.Scene(scenes.textured_scene(tmp_path, 8, "obj"))
-    with pytest.raises(lmcu.LmcuError, match="plain materials"):
-        st.render("bdpt", abi.render_params(w, h, max_verts=8, **img))
-    st.close()
 
 
-@pytest.mark.parametrize("scene", ["spheres", "env"])
-def test_bdpt_kernels_equal_the_one_thread_form(scene):
+@pytest.mark.parametrize("scene", ["spheres", "env", "obj"])
+def test_bdpt_kernels_equal_the_one_thread_form(scene, tmp_path):
     """The device runs bdpt as three kernels (subpaths -> strategy-major connections -> any-hit queue); tests/hostsim runs
     the same functions as one loop per sample on the CPU.  Same counter-RNG draws, so the images agree to float rounding."""
     import os
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostsim"))
     import sim
-    sb = scenes.cornell_spheres(12) if scene == "spheres" else scenes.instanced_spheres(grid=2, num_theta=10)
+    sb = {"spheres": lambda: scenes.cornell_spheres(12), "env": lambda: scenes.instanced_spheres(grid=2, num_theta=10),
+          "obj": lambda: scenes.textured_scene(tmp_path, 8, "obj")}[scene]()
     sc, ss = lmcu.Scene(sb), sim.SimScene(sb)
     w, h = 48, 27
     for mv, mn in ((7, 0), (4, 3)):
         p = abi.render_params(w, h, max_verts=mv, min_verts=mn, num_samples=w * h * 8, primary_ray_sampling_mode=abi.PRIMARY_IMAGE)
         fg, st = sc.render("bdpt", p)
         fs = ss.render("bdpt", p)
-        assert st["rays"] == ss.rays
+        assert abs(st["rays"] - ss.rays) <= 1e-3 * ss.rays          # a vertex on a decision boundary may round differently (libm vs CUDA)
         assert np.allclose(fg, fs, rtol=1e-3, atol=1e-4 * float(fs.max()))
     sc.close()

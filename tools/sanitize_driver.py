@@ -71,8 +71,8 @@ def main():
     run_scene("instanced+envconst", scenes.instanced_spheres(grid=2, num_theta=8))
     run_scene("instanced+env", scenes.instanced_spheres(grid=2, num_theta=8,
                                                         env=scenes.env_light(os.path.join(tmp, "e.hdr"), 64, 32)))
-    run_scene("textured obj", scenes.textured_scene(tmp, 8, "obj"), bdpt=False)
-    run_scene("textured mix", scenes.textured_scene(tmp, 8, "mix"), lt=False, bdpt=False)
+    run_scene("textured obj", scenes.textured_scene(tmp, 8, "obj"))
+    run_scene("textured mix", scenes.textured_scene(tmp, 8, "mix"), lt=False)
     run_scene("delta lights", scenes.delta_lights_scene(2, 8))
     hf = scenes.heightfield_scene(40)
     hf.set_envconst((1, 1, 1))
