@@ -392,20 +392,44 @@ __global__ void __launch_bounds__(128) k_bdpt_subpaths(DevScene s, PtParams p, B
 
 __global__ void k_bdpt_reset(PtCounters* ctr) { ctr->shadow_count = 0; ctr->fetch_shadow = 0; }
 
+// Work lists of the connection kernel: strategy (s, t) applies to a sample only if its subpaths are long enough — in an open
+// scene most are not (C2: 17 of the 63 possible rays per sample at max_verts 10), and a connection kernel launched over every
+// (strategy, sample) ran at 6.8 of 32 lanes.  One thread per (strategy, sample) appends the sample to the strategy's list
+// (ballot-ranked, one atomic per warp).
+__global__ void __launch_bounds__(256) k_bdpt_lists(PtParams p, BdptStore st, const int2* __restrict__ pairs, uint32_t* __restrict__ list,
+                                                    uint32_t* __restrict__ count) {
+    const int2 pr = pairs[blockIdx.y];
+    const uint32_t total = (uint32_t)p.total_paths, lane = threadIdx.x & 31u;
+    uint32_t* mine = list + (size_t)blockIdx.y * st.cap;
+    for (uint32_t base = blockIdx.x * blockDim.x; base < total; base += gridDim.x * blockDim.x) {
+        const uint32_t i = base + threadIdx.x;
+        const bool ok = i < total && pr.y <= st.nverts[i] && pr.x <= st.nverts[(size_t)st.cap + i];
+        const uint32_t b = __ballot_sync(0xffffffffu, ok);
+        if (b) {
+            uint32_t pos = 0;
+            if (lane == (uint32_t)(__ffs(b) - 1)) pos = atomicAdd(count + blockIdx.y, (uint32_t)__popc(b));
+            pos = __shfl_sync(0xffffffffu, pos, __ffs(b) - 1) + (uint32_t)__popc(b & ((1u << lane) - 1u));
+            if (ok) mine[pos] = i;
+        }
+    }
+}
+
 template <bool COMP>
-__global__ void __launch_bounds__(128) k_bdpt_connect(DevScene s, PtParams p, BdptStore st, const int2* __restrict__ pairs, ShadowQueue sq,
-                                                      float* film, PtCounters* ctr) {
+__global__ void __launch_bounds__(128) k_bdpt_connect(DevScene s, PtParams p, BdptStore st, const int2* __restrict__ pairs,
+                                                      const uint32_t* __restrict__ list, const uint32_t* __restrict__ count,
+                                                      ShadowQueue sq, float* film, PtCounters* ctr) {
     const int2 pr = pairs[blockIdx.y];
     const int sL = pr.x, t = pr.y;
-    const uint32_t total = (uint32_t)p.total_paths, lane = threadIdx.x & 31u;
+    const uint32_t total = count[blockIdx.y], lane = threadIdx.x & 31u;
+    const uint32_t* mine = list + (size_t)blockIdx.y * st.cap;
     for (uint32_t base = blockIdx.x * blockDim.x; base < total; base += gridDim.x * blockDim.x) {      // warp-uniform trip count
-        const uint32_t i = base + threadIdx.x;
+        const uint32_t j = base + threadIdx.x;
         bool push = false;
         BdptConn c;
-        if (i < total && t <= st.nverts[i] && sL <= st.nverts[(size_t)st.cap + i]) {
+        if (j < total) {
             BdptSoAAcc acc;
-            acc.st = st; acc.i = i;
-            if (bdpt_connect<COMP>(s, p, sL, t, acc, st.eye_pixel[i], c)) {
+            acc.st = st; acc.i = mine[j];
+            if (bdpt_connect<COMP>(s, p, sL, t, acc, st.eye_pixel[acc.i], c)) {
                 if (c.shadow) push = true;
                 else {
                     float* px = film + (size_t)c.pixel * 3;
@@ -933,6 +957,7 @@ struct LmcuScene {
         DBuf<int32_t> nverts;
         DBuf<uint32_t> eye_pixel;
         DBuf<int2> pairs;
+        DBuf<uint32_t> pair_list, pair_count;      // per strategy: the samples whose subpaths are long enough for it
         DBuf<PtCounters> ctr;
         uint32_t cap = 0; int mv = 0; size_t sq_cap = 0;
     } bdpt;
@@ -2195,8 +2220,10 @@ int lmcu_render_bdpt(LmcuScene* s, const LmcuRenderParams* p, float* film_rgb, L
     }
     if (B.sq_cap < pairs.size() * cap) {
         for (int k = 0; k < 3; k++) CU(B.sq[k].alloc(pairs.size() * cap));
+        CU(B.pair_list.alloc(pairs.size() * cap));
         B.sq_cap = pairs.size() * cap;
     }
+    if (B.pair_count.n < pairs.size()) CU(B.pair_count.alloc(pairs.size()));
     if (B.pairs.n < pairs.size()) CU(B.pairs.alloc(pairs.size()));
     CU(cudaMemcpyAsync(B.pairs.p, pairs.data(), pairs.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
     CU(cudaMemsetAsync(B.ctr.p, 0, sizeof(PtCounters), st));
@@ -2224,13 +2251,16 @@ int lmcu_render_bdpt(LmcuScene* s, const LmcuRenderParams* p, float* film_rgb, L
                 if (s->fp32) k_bdpt_subpaths<TriF32, false><<<sub_blocks, 128, 0, st>>>(d, pp, store, s->cursor.p, s->cursor.p + 3, s->flags.p);
                 else k_bdpt_subpaths<TriF64, false><<<sub_blocks, 128, 0, st>>>(d, pp, store, s->cursor.p, s->cursor.p + 3, s->flags.p);
             }
+            CU(cudaMemsetAsync(B.pair_count.p, 0, pairs.size() * sizeof(uint32_t), st));
+            const dim3 lgrid((unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)s->num_sms), (unsigned)pairs.size());
+            k_bdpt_lists<<<lgrid, 256, 0, st>>>(pp, store, B.pairs.p, B.pair_list.p, B.pair_count.p);
             const dim3 cgrid((unsigned)std::min<int64_t>((n + 127) / 128, (int64_t)s->num_sms * 2), (unsigned)pairs.size());
-            if (s->composite) k_bdpt_connect<true><<<cgrid, 128, 0, st>>>(d, pp, store, B.pairs.p, sq, s->film.p, B.ctr.p);
-            else k_bdpt_connect<false><<<cgrid, 128, 0, st>>>(d, pp, store, B.pairs.p, sq, s->film.p, B.ctr.p);
+            if (s->composite) k_bdpt_connect<true><<<cgrid, 128, 0, st>>>(d, pp, store, B.pairs.p, B.pair_list.p, B.pair_count.p, sq, s->film.p, B.ctr.p);
+            else k_bdpt_connect<false><<<cgrid, 128, 0, st>>>(d, pp, store, B.pairs.p, B.pair_list.p, B.pair_count.p, sq, s->film.p, B.ctr.p);
             LMCU_DISPATCH(k_pt_shadow_q, s->fp32, false, q_blocks, LMCU_TRAV_BLOCK, st, d, sq, s->film.p, B.ctr.p);
             CU(cudaGetLastError());
             k_film_fold<<<fold_blocks, 256, 0, st>>>(s->film.p, s->film_acc.p, s->film.n);
-            launches += 5;
+            launches += 6;
             processed += n; done += n;
             if (p->progress) {
                 CU(cudaStreamSynchronize(st));
