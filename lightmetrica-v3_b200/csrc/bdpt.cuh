@@ -297,91 +297,105 @@ LMCU_HD bool bv_sample_dir(const DevScene& s, const BVert& v, F3 wi, float ud0, 
     return b.valid;
 }
 
-// path::sample_subpath (bidir.h:487-553).  Fills vs[0..n), returns n.
-// Random numbers: block 0 / 1 = the primary ray (RaySampleU), block 3 + 2k = component of vertex k, 4 + 2k = its direction.
+// path::sample_subpath (bidir.h:487-553) in three steps (the device runs them as separate kernels around the extend queue).
+// Random numbers of a subpath: block 0 / 1 = the primary ray (RaySampleU), block 3 + 2k = component of vertex k, 4 + 2k = its
+// direction.
+
+// Vertex 0 and the primary ray: Camera_Pinhole::sample_ray (camera_pinhole.cpp:135-141) / path::sample_primary_ray(LE)
+// (path.h:101-118: a light chosen uniformly, Light::sample_ray)
+LMCU_HD void bdpt_first_vertex(const DevScene& s, const PtParams& p, uint64_t sidx, bool light_side, BVert& v, F3& o, F3& d) {
+    const uint32_t key = light_side ? kLightPathKey : kEyePathKey;
+    v.mat = -1; v.light = -1; v.comp = 0; v.infinite = 0; v.degenerated = 0;
+    v.n = f3s(0.f); v.gn = f3s(0.f); v.tu = 0.f; v.tv = 0.f;
+    const R4 u1 = rand4(p.seed, key, sidx, 0);
+    const R4 u2 = rand4(p.seed, key, sidx, 1);
+    if (!light_side) {
+        D3 od, dd;
+        camera_primary_ray_d(s.cam, (double)u2.x, (double)u2.y, od, dd);
+        v.kind = BV_CAMERA; v.degenerated = 1;
+        v.p = f3((float)od.x, (float)od.y, (float)od.z);
+        o = v.p; d = f3((float)dd.x, (float)dd.y, (float)dd.z);
+        return;
+    }
+    int li = (int)(u1.x * (float)s.num_lights);
+    li = li < 0 ? 0 : (li > s.num_lights - 1 ? s.num_lights - 1 : li);
+    const LightDev& l = s.lights[li];
+    v.kind = BV_LIGHT; v.light = li;
+    if (l.type == LIGHT_AREA) {                                    // light_area.cpp:47-59,77-97
+        const int ti = cdf_sample(s.cdf + l.cdf_offset, l.num_tris, u1.y);
+        const EmitTri& e = s.emit[l.tri_offset + ti];
+        const float sq = safe_sqrt(u1.z);
+        const float b1 = 1.0f - sq, b2 = u1.w * sq;
+        const F3 a = f3(e.p1.x, e.p1.y, e.p1.z), b = f3(e.p2.x, e.p2.y, e.p2.z), c = f3(e.p3.x, e.p3.y, e.p3.z);
+        v.p = a * (1.0f - b1 - b2) + b * b1 + c * b2;
+        v.n = f3(e.n.x, e.n.y, e.n.z); v.gn = v.n;
+        const F3 dl = sample_cosine_weighted(u2.x, u2.y);
+        F3 tu, tv;
+        orthonormal_basis(v.n, tu, tv);
+        d = tu * dl.x + tv * dl.y + v.n * dl.z;
+    } else if (l.type == LIGHT_POINT) {                            // light_point.cpp:38-48
+        v.p = f3(l.pos[0], l.pos[1], l.pos[2]); v.degenerated = 1;
+        d = sample_uniform_sphere(u2.x, u2.y);
+    } else {                                                       // light_directional.cpp:50-68, light_envconst.cpp:47-68
+        d = l.type == LIGHT_DIRECTIONAL ? f3(l.pos[0], l.pos[1], l.pos[2]) : sample_uniform_sphere(u2.x, u2.y);
+        float dx, dy;
+        sample_uniform_disk(u1.z, u1.w, dx, dy);
+        F3 tu, tv;
+        orthonormal_basis(d, tu, tv);
+        const F3 bc = f3(s.bound_center[0], s.bound_center[1], s.bound_center[2]);
+        v.p = bc - d * s.bound_radius + (tu * (dx * s.bound_radius) + tv * (dy * s.bound_radius));
+        v.n = d; v.infinite = 1;
+    }
+    o = v.p;
+}
+
+// Vertex k from the closest hit of the ray (o, d) (scene.cpp:319-345: a miss is the environment light's endpoint, or
+// nothing) + path::sample_component there.  Returns false when the walk ends without a vertex.
+template <bool COMP>
+LMCU_HD bool bdpt_hit_vertex(const DevScene& s, const PtParams& p, uint64_t sidx, bool light_side, int k, int32_t tri, float hu, float hv,
+                             F3 d, BVert& v) {
+    v.comp = 0; v.infinite = 0; v.degenerated = 0; v.tu = 0.f; v.tv = 0.f;
+    if (tri < 0) {
+        if (s.env_light < 0) return false;
+        v.kind = BV_LIGHT; v.light = s.env_light; v.mat = -1; v.infinite = 1;
+        v.p = f3s(0.f); v.n = -d; v.gn = f3s(0.f);
+        return true;
+    }
+    const SurfPoint sp = surface_point(s, (uint32_t)tri, hu, hv);
+    v.kind = BV_SURFACE; v.p = sp.p; v.n = sp.n; v.gn = sp.gn; v.tu = sp.tu; v.tv = sp.tv; v.mat = sp.material; v.light = sp.light;
+    const MaterialDev& m = s.mats[sp.material];
+    const R4 uc = rand4(p.seed, light_side ? kLightPathKey : kEyePathKey, sidx, 3u + 2u * (uint32_t)k);
+    if (m.type == MAT_GLASS) v.comp = uc.x < bv_glass_fr(m, sp.n, -d) ? 0 : 1;         // material_glass.cpp:124-136
+    else if (COMP && !mat_is_plain(m)) v.comp = (uint8_t)comp_pick_index(s, m, sp, uc.x);
+    return true;
+}
+
+// Direction out of surface vertex k (path::sample_direction, path.h:414-424); wi is the direction to the previous VERTEX
+template <bool COMP>
+LMCU_HD bool bdpt_next_dir(const DevScene& s, const PtParams& p, uint64_t sidx, bool light_side, int k, const BVert& v, const BVert& prev, F3& wo) {
+    const R4 ud = rand4(p.seed, light_side ? kLightPathKey : kEyePathKey, sidx, 4u + 2u * (uint32_t)k);
+    return bv_sample_dir<COMP>(s, v, bv_dir(v, prev), ud.x, ud.y, ud.z, wo);
+}
+
+// The whole walk by one thread (tests/hostsim).  Fills vs[0..n), returns n.
 template <typename TriT, bool COMP>
 LMCU_HD int bdpt_subpath(const DevScene& s, const PtParams& p, uint64_t sidx, bool light_side, int max_verts, BVert* vs,
                          uint2* stack, BdptCounters* ctr) {
     if (max_verts <= 0) return 0;
-    const uint32_t key = light_side ? kLightPathKey : kEyePathKey;
     int n = 0;
     F3 o, d;
-    {
-        BVert v;
-        v.mat = -1; v.light = -1; v.comp = 0; v.infinite = 0; v.degenerated = 0;
-        v.n = f3s(0.f); v.gn = f3s(0.f); v.tu = 0.f; v.tv = 0.f;
-        const R4 u1 = rand4(p.seed, key, sidx, 0);
-        const R4 u2 = rand4(p.seed, key, sidx, 1);
-        if (!light_side) {                                                 // Camera_Pinhole::sample_ray (camera_pinhole.cpp:135-141)
-            D3 od, dd;
-            camera_primary_ray_d(s.cam, (double)u2.x, (double)u2.y, od, dd);
-            v.kind = BV_CAMERA; v.degenerated = 1;
-            v.p = f3((float)od.x, (float)od.y, (float)od.z);
-            o = v.p; d = f3((float)dd.x, (float)dd.y, (float)dd.z);
-        } else {                                                           // path::sample_primary_ray(LE) (path.h:101-118)
-            int li = (int)(u1.x * (float)s.num_lights);
-            li = li < 0 ? 0 : (li > s.num_lights - 1 ? s.num_lights - 1 : li);
-            const LightDev& l = s.lights[li];
-            v.kind = BV_LIGHT; v.light = li;
-            if (l.type == LIGHT_AREA) {                                    // light_area.cpp:47-59,77-97
-                const int ti = cdf_sample(s.cdf + l.cdf_offset, l.num_tris, u1.y);
-                const EmitTri& e = s.emit[l.tri_offset + ti];
-                const float sq = safe_sqrt(u1.z);
-                const float b1 = 1.0f - sq, b2 = u1.w * sq;
-                const F3 a = f3(e.p1.x, e.p1.y, e.p1.z), b = f3(e.p2.x, e.p2.y, e.p2.z), c = f3(e.p3.x, e.p3.y, e.p3.z);
-                v.p = a * (1.0f - b1 - b2) + b * b1 + c * b2;
-                v.n = f3(e.n.x, e.n.y, e.n.z); v.gn = v.n;
-                const F3 dl = sample_cosine_weighted(u2.x, u2.y);
-                F3 tu, tv;
-                orthonormal_basis(v.n, tu, tv);
-                d = tu * dl.x + tv * dl.y + v.n * dl.z;
-                o = v.p;
-            } else if (l.type == LIGHT_POINT) {                            // light_point.cpp:38-48
-                v.p = f3(l.pos[0], l.pos[1], l.pos[2]); v.degenerated = 1;
-                d = sample_uniform_sphere(u2.x, u2.y);
-                o = v.p;
-            } else {                                                       // light_directional.cpp:50-68, light_envconst.cpp:47-68
-                d = l.type == LIGHT_DIRECTIONAL ? f3(l.pos[0], l.pos[1], l.pos[2]) : sample_uniform_sphere(u2.x, u2.y);
-                float dx, dy;
-                sample_uniform_disk(u1.z, u1.w, dx, dy);
-                F3 tu, tv;
-                orthonormal_basis(d, tu, tv);
-                const F3 bc = f3(s.bound_center[0], s.bound_center[1], s.bound_center[2]);
-                v.p = bc - d * s.bound_radius + (tu * (dx * s.bound_radius) + tv * (dy * s.bound_radius));
-                v.n = d; v.infinite = 1;
-                o = v.p;
-            }
-        }
-        vs[n++] = v;
-    }
+    bdpt_first_vertex(s, p, sidx, light_side, vs[0], o, d);
+    n = 1;
     while (true) {
-        // intersection with the next surface (scene.cpp:319-345): tmin = Eps, tmax = Inf; a miss is the environment light
         HitD h;
         if (!pt_trace<false, false, TriT>(s, make_float4(o.x, o.y, o.z, (float)kEps), make_float4(d.x, d.y, d.z, (float)kInf), h, stack, nullptr)) ctr->overflow = 1u;
         ctr->rays++;
         BVert v;
-        v.comp = 0; v.infinite = 0; v.degenerated = 0; v.tu = 0.f; v.tv = 0.f;
-        if (h.tri < 0) {
-            if (s.env_light < 0) break;
-            v.kind = BV_LIGHT; v.light = s.env_light; v.mat = -1; v.infinite = 1;
-            v.p = f3s(0.f); v.n = -d; v.gn = f3s(0.f);
-            vs[n++] = v;
-            break;
-        }
-        const SurfPoint sp = surface_point(s, (uint32_t)h.tri, (float)h.u, (float)h.v);
-        v.kind = BV_SURFACE; v.p = sp.p; v.n = sp.n; v.gn = sp.gn; v.tu = sp.tu; v.tv = sp.tv; v.mat = sp.material; v.light = sp.light;
-        const F3 wi = -d;
-        const MaterialDev& m = s.mats[sp.material];
-        const R4 uc = rand4(p.seed, key, sidx, 3u + 2u * (uint32_t)n);
-        if (m.type == MAT_GLASS) v.comp = uc.x < bv_glass_fr(m, sp.n, wi) ? 0 : 1;     // material_glass.cpp:124-136
-        else if (COMP && !mat_is_plain(m)) v.comp = (uint8_t)comp_pick_index(s, m, sp, uc.x);
+        if (!bdpt_hit_vertex<COMP>(s, p, sidx, light_side, n, h.tri, (float)h.u, (float)h.v, d, v)) break;
         vs[n++] = v;
-        if (n >= max_verts) break;
-        // next direction (path::sample_direction at a surface, path.h:414-424); wi is the direction to the previous VERTEX
-        const F3 wiv = bv_dir(v, vs[n - 2]);
-        const R4 ud = rand4(p.seed, key, sidx, 2u + 2u * (uint32_t)n);
+        if (v.infinite || n >= max_verts) break;
         F3 wo;
-        if (!bv_sample_dir<COMP>(s, v, wiv, ud.x, ud.y, ud.z, wo)) break;
+        if (!bdpt_next_dir<COMP>(s, p, sidx, light_side, n - 1, v, vs[n - 2], wo)) break;
         o = v.p; d = wo;
     }
     return n;

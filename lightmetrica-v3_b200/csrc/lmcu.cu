@@ -295,10 +295,12 @@ __global__ void __launch_bounds__(128) k_ao(DevScene s, int width, int height, l
     atomicAdd(rays, (unsigned long long)local_rays);
 }
 
-// -- bdpt (bdpt.cuh) as three kernels ---------------------------------------------------------------------------------------
+// -- bdpt (bdpt.cuh) as a wavefront ---------------------------------------------------------------------------------------
 // One thread per sample doing everything (the form tests/hostsim runs) executes at 3 of 32 lanes on the device: the (s, t)
 // loops, their early exits and the traversals inside them diverge completely (ncu, profiles/r02_ncu_summary.md).  Here:
-//   k_bdpt_subpaths   one thread per SUBPATH: random walk, alpha prefixes, per-vertex densities -> SoA arrays in HBM;
+//   the random walks  as a wavefront over all subpaths: k_bdpt_gen, then per vertex index k_pt_extend_q -> k_bdpt_vertex,
+//                     vertices into SoA arrays in HBM; k_bdpt_prefix: alpha prefixes and per-vertex densities per subpath;
+//   k_bdpt_lists      per strategy, the samples whose subpaths are long enough for it;
 //   k_bdpt_connect    one thread per (strategy, sample), strategy-major: every lane of a warp runs the SAME (s, t) on
 //                     consecutive samples — uniform loops, coalesced loads — and appends a visibility ray carrying the
 //                     weighted contribution to the shadow queue (s = 0 strategies splat at once);
@@ -351,46 +353,111 @@ struct BdptSoAAcc {
     __device__ __forceinline__ bool zSpec(int k) const { return signbit(st.ve[st.at(0, k, i)].x); }
 };
 
-template <typename TriT, bool COMP>
-__global__ void __launch_bounds__(128) k_bdpt_subpaths(DevScene s, PtParams p, BdptStore st, unsigned long long* cursor,
-                                                       unsigned long long* rays, uint32_t* overflow) {
-    uint2 stack[kStackSize];
+__device__ __forceinline__ void bdpt_store_vertex(const BdptStore& st, int side, int k, uint32_t g, const BVert& v) {
+    const size_t o = st.at(side, k, g);
+    const uint32_t bits = (uint32_t)v.kind | ((uint32_t)v.comp << 8) | ((uint32_t)v.infinite << 16) | ((uint32_t)v.degenerated << 17);
+    st.va[o] = make_float4(v.p.x, v.p.y, v.p.z, __uint_as_float(bits));
+    st.vb[o] = make_float4(v.n.x, v.n.y, v.n.z, __uint_as_float((uint32_t)v.mat));
+    st.vc[o] = make_float4(v.gn.x, v.gn.y, v.gn.z, __uint_as_float((uint32_t)v.light));
+    if (st.vt) st.vt[o] = make_float2(v.tu, v.tv);
+}
+
+// The random walks as a wavefront over ALL subpaths of the pass (eye subpaths first, then the light subpaths): vertex 0 + the
+// primary rays, then per vertex index k: the path tracer's extend queue kernel (k_pt_extend_q) -> k_bdpt_vertex (vertex k from
+// the hit, its component, the next direction -> the next queue, ballot-compacted) -> k_bdpt_flip.  A walk that ends simply
+// stops producing rays.  (A first version walked each subpath in one thread with the per-thread traversal: 5 of 32 lanes.)
+__global__ void k_bdpt_reset(PtCounters* ctr, uint32_t nrays) {
+    ctr->shadow_count = 0; ctr->fetch_shadow = 0; ctr->count[0] = nrays; ctr->count[1] = 0; ctr->fetch_extend = 0;
+}
+
+__global__ void k_bdpt_flip(PtCounters* ctr, int cur) {
+    ctr->rays += ctr->count[cur]; ctr->extend_rays += ctr->count[cur];
+    ctr->count[cur] = 0; ctr->fetch_extend = 0;
+}
+
+__global__ void __launch_bounds__(256) k_bdpt_gen(DevScene s, PtParams p, BdptStore st, float4* __restrict__ ro, float4* __restrict__ rd,
+                                                  uint32_t* __restrict__ id) {
+    const uint32_t n = (uint32_t)p.total_paths, total = 2u * n;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int side = i >= n ? 1 : 0;
+        const uint32_t g = i - (side ? n : 0u);
+        BVert v;
+        F3 o, d;
+        bdpt_first_vertex(s, p, p.sample_offset + g, side != 0, v, o, d);
+        bdpt_store_vertex(st, side, 0, g, v);
+        st.nverts[(size_t)side * st.cap + g] = 1;
+        ro[i] = make_float4(o.x, o.y, o.z, (float)kEps);
+        rd[i] = make_float4(d.x, d.y, d.z, (float)kInf);
+        id[i] = i;
+    }
+}
+
+template <bool COMP>
+__global__ void __launch_bounds__(128) k_bdpt_vertex(DevScene s, PtParams p, BdptStore st, int k, const float4* __restrict__ rd_in,
+                                                     const uint32_t* __restrict__ id_in, const float4* __restrict__ hits,
+                                                     float4* __restrict__ ro_out, float4* __restrict__ rd_out, uint32_t* __restrict__ id_out,
+                                                     PtCounters* ctr, int cur) {
+    const uint32_t nq = ctr->count[cur], n = (uint32_t)p.total_paths, lane = threadIdx.x & 31u;
+    for (uint32_t base = blockIdx.x * blockDim.x; base < nq; base += gridDim.x * blockDim.x) {          // warp-uniform trip count
+        const uint32_t j = base + threadIdx.x;
+        bool push = false;
+        uint32_t i = 0;
+        BVert v;
+        F3 wo;
+        if (j < nq) {
+            i = id_in[j];
+            const int side = i >= n ? 1 : 0;
+            const uint32_t g = i - (side ? n : 0u);
+            const float4 dd = Q_LD(rd_in + j), hit = Q_LD(hits + j);
+            if (bdpt_hit_vertex<COMP>(s, p, p.sample_offset + g, side != 0, k, __float_as_int(hit.w), hit.y, hit.z, f3(dd.x, dd.y, dd.z), v)) {
+                bdpt_store_vertex(st, side, k, g, v);
+                st.nverts[(size_t)side * st.cap + g] = k + 1;
+                if (!v.infinite && k + 1 < p.max_verts) {
+                    BdptSoAAcc acc;
+                    acc.st = st; acc.i = g;
+                    push = bdpt_next_dir<COMP>(s, p, p.sample_offset + g, side != 0, k, v, acc.load(side, k - 1), wo);
+                }
+            }
+        }
+        const uint32_t b = __ballot_sync(0xffffffffu, push);
+        if (b) {
+            uint32_t pos = 0;
+            if (lane == (uint32_t)(__ffs(b) - 1)) pos = atomicAdd(&ctr->count[cur ^ 1], (uint32_t)__popc(b));
+            pos = __shfl_sync(0xffffffffu, pos, __ffs(b) - 1) + (uint32_t)__popc(b & ((1u << lane) - 1u));
+            if (push) {
+                Q_ST(ro_out + pos, make_float4(v.p.x, v.p.y, v.p.z, (float)kEps));
+                Q_ST(rd_out + pos, make_float4(wo.x, wo.y, wo.z, (float)kInf));
+                id_out[pos] = i;
+            }
+        }
+    }
+}
+
+// Per subpath: alpha prefixes, component pdfs, per-vertex densities, specular flags (bdpt_alphas, bdpt_subpath_pdfs)
+template <bool COMP>
+__global__ void __launch_bounds__(128) k_bdpt_prefix(DevScene s, PtParams p, BdptStore st) {
     BVert vs[kBdptMaxVerts];
     F3 alpha[kBdptMaxVerts + 1];
     float pc[kBdptMaxVerts], F[kBdptMaxVerts], R[kBdptMaxVerts];
     bool spec[kBdptMaxVerts];
-    BdptCounters ctr;
-    ctr.rays = 0; ctr.overflow = 0;
-    const unsigned long long total = 2ull * p.total_paths;             // eye subpaths first, then the light subpaths
-    while (true) {
-        const unsigned long long base = warp_fetch(cursor);
-        if (base >= total) break;
-        const unsigned long long idx = base + (threadIdx.x & 31);
-        if (idx >= total) continue;
-        const int side = idx >= p.total_paths ? 1 : 0;
-        const uint32_t g = (uint32_t)(idx - (side ? p.total_paths : 0ull));
-        const int n = bdpt_subpath<TriT, COMP>(s, p, p.sample_offset + g, side != 0, p.max_verts, vs, stack, &ctr);
-        bdpt_alphas<COMP>(s, vs, n, side != 0, alpha, pc);
-        bdpt_subpath_pdfs<COMP>(s, vs, n, F, R, spec);
-        st.nverts[(size_t)side * st.cap + g] = n;
-        if (!side) st.eye_pixel[g] = bdpt_eye_pixel(s, p, vs, n);
-        for (int k = 0; k < n; k++) {
-            const BVert& v = vs[k];
+    const uint32_t n = (uint32_t)p.total_paths, total = 2u * n;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int side = i >= n ? 1 : 0;
+        const uint32_t g = i - (side ? n : 0u);
+        const int nv = st.nverts[(size_t)side * st.cap + g];
+        BdptSoAAcc acc;
+        acc.st = st; acc.i = g;
+        for (int k = 0; k < nv; k++) vs[k] = acc.load(side, k);
+        bdpt_alphas<COMP>(s, vs, nv, side != 0, alpha, pc);
+        bdpt_subpath_pdfs<COMP>(s, vs, nv, F, R, spec);
+        if (!side) st.eye_pixel[g] = bdpt_eye_pixel(s, p, vs, nv);
+        for (int k = 0; k < nv; k++) {
             const size_t o = st.at(side, k, g);
-            const uint32_t bits = (uint32_t)v.kind | ((uint32_t)v.comp << 8) | ((uint32_t)v.infinite << 16) | ((uint32_t)v.degenerated << 17);
-            st.va[o] = make_float4(v.p.x, v.p.y, v.p.z, __uint_as_float(bits));
-            st.vb[o] = make_float4(v.n.x, v.n.y, v.n.z, __uint_as_float((uint32_t)v.mat));
-            st.vc[o] = make_float4(v.gn.x, v.gn.y, v.gn.z, __uint_as_float((uint32_t)v.light));
             st.vd[o] = make_float4(alpha[k + 1].x, alpha[k + 1].y, alpha[k + 1].z, pc[k]);
-            st.ve[o] = make_float2(spec[k] ? -F[k] : F[k], k + 2 < n ? R[k] : 0.f);
-            if (st.vt) st.vt[o] = make_float2(v.tu, v.tv);
+            st.ve[o] = make_float2(spec[k] ? -F[k] : F[k], k + 2 < nv ? R[k] : 0.f);
         }
     }
-    atomicAdd(rays, (unsigned long long)ctr.rays);
-    if (ctr.overflow) atomicExch(overflow, 1u);
 }
-
-__global__ void k_bdpt_reset(PtCounters* ctr) { ctr->shadow_count = 0; ctr->fetch_shadow = 0; }
 
 // Work lists of the connection kernel: strategy (s, t) applies to a sample only if its subpaths are long enough — in an open
 // scene most are not (C2: 17 of the 63 possible rays per sample at max_verts 10), and a connection kernel launched over every
@@ -953,6 +1020,8 @@ struct LmcuScene {
     DBuf<double> film_acc;               // pt: FP64 sums the fp32 film is folded into (k_film_fold)
     struct BdptPools {                   // bdpt: subpath SoA (BdptStore), strategy table, shadow queue, counters
         DBuf<float4> va, vb, vc, vd, sq[3];
+        DBuf<float4> q_o[2], q_d[2], hits;        // the random walks' ray queue (ping-pong) and hit records, 2 x cap entries
+        DBuf<uint32_t> q_id[2];
         DBuf<float2> ve, vt;
         DBuf<int32_t> nverts;
         DBuf<uint32_t> eye_pixel;
@@ -2175,8 +2244,8 @@ static int render_paths(LmcuScene* s, const LmcuRenderParams* p, float* film_rgb
     return LMCU_OK;
 }
 
-// renderer::bdpt (src/renderer/renderer_bdpt.cpp:304-407).  Passes of up to 1 Mi samples through k_bdpt_subpaths ->
-// k_bdpt_connect -> k_pt_shadow_q; the fp32 splat film is folded into the FP64 sums after every pass.
+// renderer::bdpt (src/renderer/renderer_bdpt.cpp:304-407).  Passes of up to 1 Mi samples: random walks (k_bdpt_gen, then
+// k_pt_extend_q -> k_bdpt_vertex per vertex index), k_bdpt_prefix, k_bdpt_lists -> k_bdpt_connect -> k_pt_shadow_q; the fp32 splat film is folded into the FP64 sums after every pass.
 int lmcu_render_bdpt(LmcuScene* s, const LmcuRenderParams* p, float* film_rgb, LmcuRenderStats* stats) {
     int rc = require_renderable(s, true);
     if (rc) return rc;
@@ -2215,6 +2284,8 @@ int lmcu_render_bdpt(LmcuScene* s, const LmcuRenderParams* p, float* film_rgb, L
         CU(B.va.alloc(nv)); CU(B.vb.alloc(nv)); CU(B.vc.alloc(nv)); CU(B.vd.alloc(nv)); CU(B.ve.alloc(nv));
         CU(B.vt.alloc(0));
         CU(B.nverts.alloc((size_t)2 * cap)); CU(B.eye_pixel.alloc(cap));
+        for (int k = 0; k < 2; k++) { CU(B.q_o[k].alloc((size_t)2 * cap)); CU(B.q_d[k].alloc((size_t)2 * cap)); CU(B.q_id[k].alloc((size_t)2 * cap)); }
+        CU(B.hits.alloc((size_t)2 * cap));
         if (!B.ctr.p) CU(B.ctr.alloc(1));
         B.cap = cap; B.mv = p->max_verts;
     }
@@ -2241,16 +2312,23 @@ int lmcu_render_bdpt(LmcuScene* s, const LmcuRenderParams* p, float* film_rgb, L
             pp.sample_offset = (uint64_t)p->sample_offset + (uint64_t)processed;
             pp.total_paths = (uint64_t)n;
             pp.capacity = cap;
-            CU(cudaMemsetAsync(s->cursor.p, 0, sizeof(unsigned long long), st));
-            k_bdpt_reset<<<1, 1, 0, st>>>(B.ctr.p);
-            const unsigned sub_blocks = (unsigned)std::min<int64_t>((2 * n + 127) / 128, (int64_t)s->num_sms * 8);
-            if (s->composite) {     // textured / mixture materials: the <true> instantiations (more registers), as for the pt shade kernel
-                if (s->fp32) k_bdpt_subpaths<TriF32, true><<<sub_blocks, 128, 0, st>>>(d, pp, store, s->cursor.p, s->cursor.p + 3, s->flags.p);
-                else k_bdpt_subpaths<TriF64, true><<<sub_blocks, 128, 0, st>>>(d, pp, store, s->cursor.p, s->cursor.p + 3, s->flags.p);
-            } else {
-                if (s->fp32) k_bdpt_subpaths<TriF32, false><<<sub_blocks, 128, 0, st>>>(d, pp, store, s->cursor.p, s->cursor.p + 3, s->flags.p);
-                else k_bdpt_subpaths<TriF64, false><<<sub_blocks, 128, 0, st>>>(d, pp, store, s->cursor.p, s->cursor.p + 3, s->flags.p);
+            k_bdpt_reset<<<1, 1, 0, st>>>(B.ctr.p, (uint32_t)(2 * n));
+            const unsigned gen_blocks = (unsigned)std::min<int64_t>((2 * n + 255) / 256, (int64_t)s->num_sms * 8);
+            const unsigned vtx_blocks = (unsigned)std::min<int64_t>((2 * n + 127) / 128, (int64_t)s->num_sms * 8);
+            k_bdpt_gen<<<gen_blocks, 256, 0, st>>>(d, pp, store, B.q_o[0].p, B.q_d[0].p, B.q_id[0].p);
+            int cur = 0;
+            for (int k = 1; k < p->max_verts; k++) {
+                PathQueue q{};
+                q.ray_o = B.q_o[cur].p; q.ray_d = B.q_d[cur].p;
+                LMCU_DISPATCH(k_pt_extend_q, s->fp32, false, q_blocks, LMCU_TRAV_BLOCK, st, d, q, B.hits.p, B.ctr.p, cur);
+                if (s->composite) k_bdpt_vertex<true><<<vtx_blocks, 128, 0, st>>>(d, pp, store, k, B.q_d[cur].p, B.q_id[cur].p, B.hits.p, B.q_o[cur ^ 1].p, B.q_d[cur ^ 1].p, B.q_id[cur ^ 1].p, B.ctr.p, cur);
+                else k_bdpt_vertex<false><<<vtx_blocks, 128, 0, st>>>(d, pp, store, k, B.q_d[cur].p, B.q_id[cur].p, B.hits.p, B.q_o[cur ^ 1].p, B.q_d[cur ^ 1].p, B.q_id[cur ^ 1].p, B.ctr.p, cur);
+                k_bdpt_flip<<<1, 1, 0, st>>>(B.ctr.p, cur);
+                cur ^= 1;
+                launches += 3;
             }
+            if (s->composite) k_bdpt_prefix<true><<<vtx_blocks, 128, 0, st>>>(d, pp, store);
+            else k_bdpt_prefix<false><<<vtx_blocks, 128, 0, st>>>(d, pp, store);
             CU(cudaMemsetAsync(B.pair_count.p, 0, pairs.size() * sizeof(uint32_t), st));
             const dim3 lgrid((unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)s->num_sms), (unsigned)pairs.size());
             k_bdpt_lists<<<lgrid, 256, 0, st>>>(pp, store, B.pairs.p, B.pair_list.p, B.pair_count.p);
@@ -2260,7 +2338,7 @@ int lmcu_render_bdpt(LmcuScene* s, const LmcuRenderParams* p, float* film_rgb, L
             LMCU_DISPATCH(k_pt_shadow_q, s->fp32, false, q_blocks, LMCU_TRAV_BLOCK, st, d, sq, s->film.p, B.ctr.p);
             CU(cudaGetLastError());
             k_film_fold<<<fold_blocks, 256, 0, st>>>(s->film.p, s->film_acc.p, s->film.n);
-            launches += 6;
+            launches += 8;
             processed += n; done += n;
             if (p->progress) {
                 CU(cudaStreamSynchronize(st));
@@ -2270,7 +2348,6 @@ int lmcu_render_bdpt(LmcuScene* s, const LmcuRenderParams* p, float* film_rgb, L
         }
         return LMCU_OK;
     };
-    CU(cudaMemsetAsync(s->cursor.p + 3, 0, sizeof(unsigned long long), st));
     CU(cudaEventRecord(s->ev0, st));
     if (!timed) {
         rc = run_pass(p->num_samples);
@@ -2294,9 +2371,7 @@ int lmcu_render_bdpt(LmcuScene* s, const LmcuRenderParams* p, float* film_rgb, L
     launches += 1;
     CU(cudaEventRecord(s->ev1, st));
     if (film_rgb) CU(cudaMemcpyAsync(film_rgb, s->film.p, s->film.n * sizeof(float), cudaMemcpyDeviceToHost, st));
-    unsigned long long rays = 0;
     PtCounters hc;
-    CU(cudaMemcpyAsync(&rays, s->cursor.p + 3, sizeof(rays), cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(&hc, B.ctr.p, sizeof(hc), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     if (stats) {
@@ -2304,7 +2379,7 @@ int lmcu_render_bdpt(LmcuScene* s, const LmcuRenderParams* p, float* film_rgb, L
         CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
         memset(stats, 0, sizeof(*stats));
         stats->elapsed = ms * 1e-3; stats->processed = processed; stats->paths = processed;
-        stats->rays = (int64_t)(rays + hc.rays); stats->shadow_rays = (int64_t)hc.shadow_rays; stats->extend_rays = (int64_t)rays;
+        stats->rays = (int64_t)hc.rays; stats->shadow_rays = (int64_t)hc.shadow_rays; stats->extend_rays = (int64_t)hc.extend_rays;
         stats->kernel_launches = launches;
     }
     if (hc.overflow) return fail(LMCU_ERR_CUDA, "bvh traversal stack overflow");
