@@ -466,6 +466,28 @@ LMCU_HD void bdpt_subpath_pdfs(const DevScene& s, const BVert* vs, int n, float*
     for (int i = 0; i + 2 < n; i++) R[i] = bdpt_gen_pdf<COMP>(s, &vs[i + 2], vs[i + 1], vs[i]);
 }
 
+// The same per-vertex data (bdpt_alphas + bdpt_subpath_pdfs), incrementally: everything that becomes known when vertex k >= 1
+// of a subpath is created, from v_k, v_{k-1}, v_{k-2} (null for k = 1) and alpha[k] — the wavefront computes it in the
+// kernel that creates the vertex.  alpha_next = alpha[k + 1]; R_prev2 = R[k - 2] (k >= 2).
+struct BdptVertexData { F3 alpha_next; float pc, F, R_prev2; bool spec; };
+
+template <bool COMP>
+LMCU_HD BdptVertexData bdpt_vertex_data(const DevScene& s, bool le, int k, const BVert& v, const BVert& prev, const BVert* prev2, F3 alpha_k) {
+    BdptVertexData o;
+    o.spec = bv_specular<COMP>(s, v);
+    const F3 wo = bv_dir(prev, v);
+    const F3 wi = prev2 ? bv_dir(prev, *prev2) : f3s(0.f);
+    o.pc = bv_pdf_comp<COMP>(s, v, -wo);
+    const F3 f = bv_eval<COMP>(s, prev, wi, wo, le, false);
+    const bool joint = k == 1 && !bv_connectable(s, prev);          // a light at infinity: vertex 0 and 1 are sampled jointly
+    const float pdir = joint ? bv_pdf_primary_ray(s, prev, wo) : bv_pdf_dir<COMP>(s, prev, wi, wo);
+    o.F = pdir * bv_G(prev, v) * o.pc;
+    const float pd = pdir * o.pc;
+    o.alpha_next = (is_zero(f) || !(pd > 0.f)) ? f3s(0.f) : (joint ? f : alpha_k * f) * (1.0f / pd);
+    o.R_prev2 = prev2 ? bdpt_gen_pdf<COMP>(s, &v, prev, *prev2) : 0.f;
+    return o;
+}
+
 // What one connection (s, t) produces: the MIS-weighted contribution, the pixel it belongs to and — for s >= 1 — the
 // visibility ray that decides whether it counts (Scene::visible, scene.h:343-364).
 struct BdptConn {
@@ -598,11 +620,13 @@ struct BdptLocalAcc {
 };
 
 // raster pixel of every strategy with t >= 2: the eye subpath's own primary ray
-LMCU_HD uint32_t bdpt_eye_pixel(const DevScene& s, const PtParams& p, const BVert* zs, int nE) {
-    if (nE < 2) return 0u;
+LMCU_HD uint32_t bdpt_eye_pixel(const DevScene& s, const PtParams& p, const BVert& z0, const BVert& z1) {
     float rx, ry;
-    camera_importance(s.cam, bv_dir(zs[0], zs[1]), rx, ry);
+    camera_importance(s.cam, bv_dir(z0, z1), rx, ry);
     return raster_to_pixel(p, rx, ry);
+}
+LMCU_HD uint32_t bdpt_eye_pixel(const DevScene& s, const PtParams& p, const BVert* zs, int nE) {
+    return nE < 2 ? 0u : bdpt_eye_pixel(s, p, zs[0], zs[1]);
 }
 
 // One sample by one thread: both subpaths, every connection; splat(pixel, C) receives the weighted contributions.  This is

@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(128) k_ao(DevScene s, int width, int height, l
 // One thread per sample doing everything (the form tests/hostsim runs) executes at 3 of 32 lanes on the device: the (s, t)
 // loops, their early exits and the traversals inside them diverge completely (ncu, profiles/r02_ncu_summary.md).  Here:
 //   the random walks  as a wavefront over all subpaths: k_bdpt_gen, then per vertex index k_pt_extend_q -> k_bdpt_vertex,
-//                     vertices into SoA arrays in HBM; k_bdpt_prefix: alpha prefixes and per-vertex densities per subpath;
+//                     vertices + their alpha prefix and densities (bdpt_vertex_data) into SoA arrays in HBM;
 //   k_bdpt_lists      per strategy, the samples whose subpaths are long enough for it;
 //   k_bdpt_connect    one thread per (strategy, sample), strategy-major: every lane of a warp runs the SAME (s, t) on
 //                     consecutive samples — uniform loops, coalesced loads — and appends a visibility ray carrying the
@@ -386,6 +386,14 @@ __global__ void __launch_bounds__(256) k_bdpt_gen(DevScene s, PtParams p, BdptSt
         bdpt_first_vertex(s, p, p.sample_offset + g, side != 0, v, o, d);
         bdpt_store_vertex(st, side, 0, g, v);
         st.nverts[(size_t)side * st.cap + g] = 1;
+        {   // alpha[1], pc[0], F[0], spec[0] (bdpt_alphas / bdpt_subpath_pdfs for vertex 0)
+            const bool conn0 = bv_connectable(s, v);
+            const float pa = conn0 ? bv_pdf_position(s, v) : 1.f;
+            const size_t o0 = st.at(side, 0, g);
+            st.vd[o0] = conn0 ? make_float4(1.0f / pa, 1.0f / pa, 1.0f / pa, 1.f) : make_float4(0.f, 0.f, 0.f, 1.f);
+            st.ve[o0] = make_float2(bv_specular<false>(s, v) ? -pa : pa, 0.f);
+            if (!side) st.eye_pixel[g] = 0u;
+        }
         ro[i] = make_float4(o.x, o.y, o.z, (float)kEps);
         rd[i] = make_float4(d.x, d.y, d.z, (float)kInf);
         id[i] = i;
@@ -412,11 +420,19 @@ __global__ void __launch_bounds__(128) k_bdpt_vertex(DevScene s, PtParams p, Bdp
             if (bdpt_hit_vertex<COMP>(s, p, p.sample_offset + g, side != 0, k, __float_as_int(hit.w), hit.y, hit.z, f3(dd.x, dd.y, dd.z), v)) {
                 bdpt_store_vertex(st, side, k, g, v);
                 st.nverts[(size_t)side * st.cap + g] = k + 1;
-                if (!v.infinite && k + 1 < p.max_verts) {
-                    BdptSoAAcc acc;
-                    acc.st = st; acc.i = g;
-                    push = bdpt_next_dir<COMP>(s, p, p.sample_offset + g, side != 0, k, v, acc.load(side, k - 1), wo);
-                }
+                BdptSoAAcc acc;
+                acc.st = st; acc.i = g;
+                const BVert prev = acc.load(side, k - 1);
+                BVert prev2;
+                if (k >= 2) prev2 = acc.load(side, k - 2);
+                // alpha[k + 1], pc[k], F[k], spec[k], R[k - 2]: everything the connection kernel needs from this vertex
+                const BdptVertexData vd = bdpt_vertex_data<COMP>(s, side != 0, k, v, prev, k >= 2 ? &prev2 : nullptr, acc.alpha(side, k));
+                const size_t ok = st.at(side, k, g);
+                st.vd[ok] = make_float4(vd.alpha_next.x, vd.alpha_next.y, vd.alpha_next.z, vd.pc);
+                st.ve[ok] = make_float2(vd.spec ? -vd.F : vd.F, 0.f);
+                if (k >= 2) st.ve[st.at(side, k - 2, g)].y = vd.R_prev2;
+                if (!side && k == 1) st.eye_pixel[g] = bdpt_eye_pixel(s, p, prev, v);
+                if (!v.infinite && k + 1 < p.max_verts) push = bdpt_next_dir<COMP>(s, p, p.sample_offset + g, side != 0, k, v, prev, wo);
             }
         }
         const uint32_t b = __ballot_sync(0xffffffffu, push);
@@ -429,32 +445,6 @@ __global__ void __launch_bounds__(128) k_bdpt_vertex(DevScene s, PtParams p, Bdp
                 Q_ST(rd_out + pos, make_float4(wo.x, wo.y, wo.z, (float)kInf));
                 id_out[pos] = i;
             }
-        }
-    }
-}
-
-// Per subpath: alpha prefixes, component pdfs, per-vertex densities, specular flags (bdpt_alphas, bdpt_subpath_pdfs)
-template <bool COMP>
-__global__ void __launch_bounds__(128) k_bdpt_prefix(DevScene s, PtParams p, BdptStore st) {
-    BVert vs[kBdptMaxVerts];
-    F3 alpha[kBdptMaxVerts + 1];
-    float pc[kBdptMaxVerts], F[kBdptMaxVerts], R[kBdptMaxVerts];
-    bool spec[kBdptMaxVerts];
-    const uint32_t n = (uint32_t)p.total_paths, total = 2u * n;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const int side = i >= n ? 1 : 0;
-        const uint32_t g = i - (side ? n : 0u);
-        const int nv = st.nverts[(size_t)side * st.cap + g];
-        BdptSoAAcc acc;
-        acc.st = st; acc.i = g;
-        for (int k = 0; k < nv; k++) vs[k] = acc.load(side, k);
-        bdpt_alphas<COMP>(s, vs, nv, side != 0, alpha, pc);
-        bdpt_subpath_pdfs<COMP>(s, vs, nv, F, R, spec);
-        if (!side) st.eye_pixel[g] = bdpt_eye_pixel(s, p, vs, nv);
-        for (int k = 0; k < nv; k++) {
-            const size_t o = st.at(side, k, g);
-            st.vd[o] = make_float4(alpha[k + 1].x, alpha[k + 1].y, alpha[k + 1].z, pc[k]);
-            st.ve[o] = make_float2(spec[k] ? -F[k] : F[k], k + 2 < nv ? R[k] : 0.f);
         }
     }
 }
@@ -2245,7 +2235,7 @@ static int render_paths(LmcuScene* s, const LmcuRenderParams* p, float* film_rgb
 }
 
 // renderer::bdpt (src/renderer/renderer_bdpt.cpp:304-407).  Passes of up to 1 Mi samples: random walks (k_bdpt_gen, then
-// k_pt_extend_q -> k_bdpt_vertex per vertex index), k_bdpt_prefix, k_bdpt_lists -> k_bdpt_connect -> k_pt_shadow_q; the fp32 splat film is folded into the FP64 sums after every pass.
+// k_pt_extend_q -> k_bdpt_vertex per vertex index), k_bdpt_lists -> k_bdpt_connect -> k_pt_shadow_q; the fp32 splat film is folded into the FP64 sums after every pass.
 int lmcu_render_bdpt(LmcuScene* s, const LmcuRenderParams* p, float* film_rgb, LmcuRenderStats* stats) {
     int rc = require_renderable(s, true);
     if (rc) return rc;
@@ -2327,8 +2317,6 @@ int lmcu_render_bdpt(LmcuScene* s, const LmcuRenderParams* p, float* film_rgb, L
                 cur ^= 1;
                 launches += 3;
             }
-            if (s->composite) k_bdpt_prefix<true><<<vtx_blocks, 128, 0, st>>>(d, pp, store);
-            else k_bdpt_prefix<false><<<vtx_blocks, 128, 0, st>>>(d, pp, store);
             CU(cudaMemsetAsync(B.pair_count.p, 0, pairs.size() * sizeof(uint32_t), st));
             const dim3 lgrid((unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)s->num_sms), (unsigned)pairs.size());
             k_bdpt_lists<<<lgrid, 256, 0, st>>>(pp, store, B.pairs.p, B.pair_list.p, B.pair_count.p);
@@ -2338,7 +2326,7 @@ int lmcu_render_bdpt(LmcuScene* s, const LmcuRenderParams* p, float* film_rgb, L
             LMCU_DISPATCH(k_pt_shadow_q, s->fp32, false, q_blocks, LMCU_TRAV_BLOCK, st, d, sq, s->film.p, B.ctr.p);
             CU(cudaGetLastError());
             k_film_fold<<<fold_blocks, 256, 0, st>>>(s->film.p, s->film_acc.p, s->film.n);
-            launches += 8;
+            launches += 7;
             processed += n; done += n;
             if (p->progress) {
                 CU(cudaStreamSynchronize(st));
