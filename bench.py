@@ -270,6 +270,17 @@ def c4_rates(lmcu, abi, scenes, stream, peak):
         out["extend"]["traffic_source"] = prof.get("source")
         out["extend"]["ncu"] = ncu_view(prof)
     sc.close()
+    # the instancing-aware layout of the same scene (LmcuBuildOptions::two_level = 1): one tree per mesh + one over the 1001
+    # primitives; same hits (tests/test_gpu_two_level.py), resident bytes and build time of the unique triangles, slower walk
+    sc = lmcu.Scene(sb, two_level=1)
+    sc.set_stream(stream.cuda_stream)
+    bs = sc.build_stats
+    sc.render("pt", abi.render_params(C5_W, C5_H, spp=2, max_verts=MAX_VERTS, seed=SEED), download=False)
+    _, st2 = sc.render("pt", abi.render_params(C5_W, C5_H, spp=spp, max_verts=MAX_VERTS, seed=SEED), download=False)
+    out["two_level"] = {"build_ms": bs.elapsed * 1e3, "bvh_bytes": int(bs.node_bytes + bs.triangle_bytes),
+                        "mpaths_per_s": st2["paths"] / st2["elapsed"] / 1e6, "mrays_per_s": st2["rays"] / st2["elapsed"] / 1e6,
+                        "vs_flattened": (st2["paths"] / st2["elapsed"]) / (st["paths"] / st["elapsed"])}
+    sc.close()
     return out
 
 

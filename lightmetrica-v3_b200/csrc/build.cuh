@@ -357,6 +357,24 @@ LMCU_HD F3 normal_transform(const double* NM, double x, double y, double z) {
               (float)(NM[2] * x + NM[5] * y + NM[8] * z));
 }
 
+// world-space (unnormalised) vertex normals of one face; `mf` = offset of the face in the concatenated mesh arrays.  Meshes
+// without normals shade with the geometric normal of the object-space triangle.
+LMCU_HD void shade_normals(const PrimDev& pr, const double* mesh_p, const double* mesh_n, size_t mf, F3* n) {
+    if (pr.has_normals) {
+        for (int v = 0; v < 3; v++) {
+            n[v] = normal_transform(pr.NM, mesh_n[mf + 3 * v], mesh_n[mf + 3 * v + 1], mesh_n[mf + 3 * v + 2]);
+        }
+    } else {
+        const double* p = mesh_p + mf;
+        const double e1[3] = { p[3] - p[0], p[4] - p[1], p[5] - p[2] };
+        const double e2[3] = { p[6] - p[0], p[7] - p[1], p[8] - p[2] };
+        const double gx = e1[1] * e2[2] - e1[2] * e2[1], gy = e1[2] * e2[0] - e1[0] * e2[2],
+                     gz = e1[0] * e2[1] - e1[1] * e2[0];
+        const double inv = 1.0 / sqrt(gx * gx + gy * gy + gz * gz);
+        n[0] = n[1] = n[2] = normal_transform(pr.NM, gx * inv, gy * inv, gz * inv);
+    }
+}
+
 // world-space (unnormalised) vertex normals; n1.w = sign of det(M) (geometric normal orientation),
 // n2.w = material index, n3.w = light index or -1 (int bit patterns): shading needs no PrimDev lookup
 struct alignas(16) TriShade { float4 n1, n2, n3; };
@@ -381,21 +399,8 @@ LMCU_HD void emit_body(uint32_t k, const uint32_t* tri_order, const PrimDev* pri
         t64[k].prim = (int32_t)pi;
         t64[k].face = (int32_t)face;
     }
-    const size_t mf = (size_t)(pr.mesh_face_offset + face) * 9;
     F3 n[3];
-    if (pr.has_normals) {
-        for (int v = 0; v < 3; v++) {
-            n[v] = normal_transform(pr.NM, mesh_n[mf + 3 * v], mesh_n[mf + 3 * v + 1], mesh_n[mf + 3 * v + 2]);
-        }
-    } else {
-        const double* p = mesh_p + mf;
-        const double e1[3] = { p[3] - p[0], p[4] - p[1], p[5] - p[2] };
-        const double e2[3] = { p[6] - p[0], p[7] - p[1], p[8] - p[2] };
-        const double gx = e1[1] * e2[2] - e1[2] * e2[1], gy = e1[2] * e2[0] - e1[0] * e2[2],
-                     gz = e1[0] * e2[1] - e1[1] * e2[0];
-        const double inv = 1.0 / sqrt(gx * gx + gy * gy + gz * gz);
-        n[0] = n[1] = n[2] = normal_transform(pr.NM, gx * inv, gy * inv, gz * inv);
-    }
+    shade_normals(pr, mesh_p, mesh_n, (size_t)(pr.mesh_face_offset + face) * 9, n);
     shade[k].n1 = make_float4(n[0].x, n[0].y, n[0].z, pr.det_sign);
     shade[k].n2 = make_float4(n[1].x, n[1].y, n[1].z, u2f((uint32_t)pr.material));
     shade[k].n3 = make_float4(n[2].x, n[2].y, n[2].z, u2f((uint32_t)pr.light));
@@ -405,6 +410,49 @@ LMCU_HD void emit_body(uint32_t k, const uint32_t* tri_order, const PrimDev* pri
         o.t1.x = t[0]; o.t1.y = t[1]; o.t2.x = t[2]; o.t2.y = t[3]; o.t3.x = t[4]; o.t3.y = t[5];
         uv[k] = o;
     }
+}
+
+// -- two-level layout (bvh.cuh TriObj / InstDev) ---------------------------------------------------------------------------
+// Bottom level: bounds of face k of ONE mesh in object space (`p` = the mesh's first face), float rounded outward.
+LMCU_HD void obj_bounds_body(uint32_t k, const double* p, float* tri_lo, float* tri_hi, double* centre) {
+    const double* src = p + (size_t)k * 9;
+    double lo[3] = { kInf, kInf, kInf }, hi[3] = { -kInf, -kInf, -kInf };
+    for (int v = 0; v < 3; v++) for (int a = 0; a < 3; a++) { lo[a] = fmin(lo[a], src[3 * v + a]); hi[a] = fmax(hi[a], src[3 * v + a]); }
+    for (int a = 0; a < 3; a++) {
+        tri_lo[(size_t)k * 3 + a] = f32_down(lo[a]);
+        tri_hi[(size_t)k * 3 + a] = f32_up(hi[a]);
+        centre[(size_t)k * 3 + a] = (lo[a] + hi[a]) * 0.5;
+    }
+}
+
+// Top level: world-space bounds of global triangle g — the vertices the leaf test will see (transform_point), so an
+// instance's box (the union over its faces) encloses them exactly.
+LMCU_HD uint32_t world_bounds_body(uint32_t g, const PrimDev* prims, int num_prims, const double* mesh_p, float* lo, float* hi) {
+    const uint32_t pi = find_prim(prims, num_prims, g);
+    const PrimDev& pr = prims[pi];
+    const double* src = mesh_p + (size_t)(pr.mesh_face_offset + (g - pr.tri_offset)) * 9;
+    double l[3] = { kInf, kInf, kInf }, h[3] = { -kInf, -kInf, -kInf };
+    for (int k = 0; k < 3; k++) {
+        const D3 w = transform_point(pr.M, d3(src[3 * k], src[3 * k + 1], src[3 * k + 2]));
+        l[0] = fmin(l[0], w.x); l[1] = fmin(l[1], w.y); l[2] = fmin(l[2], w.z);
+        h[0] = fmax(h[0], w.x); h[1] = fmax(h[1], w.y); h[2] = fmax(h[2], w.z);
+    }
+    for (int a = 0; a < 3; a++) { lo[a] = f32_down(l[a]); hi[a] = f32_up(h[a]); }
+    return pi;
+}
+
+// Bottom-level triangle k (leaf order) of a mesh: object-space vertices + the mesh-local face
+LMCU_HD void emit_obj_body(uint32_t k, const uint32_t* order, const double* p, int32_t mesh, TriObj* out) {
+    const uint32_t face = order[k];
+    for (int i = 0; i < 9; i++) out[k].p[i] = p[(size_t)face * 9 + i];
+    out[k].mesh = mesh;
+    out[k].face = (int32_t)face;
+}
+
+// A tree built on its own (nodes and leaf items counted from 0) moved to its place in the shared arrays
+LMCU_HD void relocate_body(WideNode& w, uint32_t node_off, uint32_t item_off) {
+    w.child_base += node_off;
+    w.tri_base += item_off;
 }
 
 }  // namespace lmcu

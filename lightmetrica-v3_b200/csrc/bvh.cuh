@@ -32,9 +32,26 @@ struct alignas(16) WideNode {
 };
 static_assert(sizeof(WideNode) == 80, "WideNode must be 80 bytes");
 
-struct alignas(16) TriF32 { float4 a, b, c; };   // a=(p1,prim) b=(p2,face) c=(p3,0); prim/face are int bit patterns
-struct alignas(16) TriF64 { double p[9]; int32_t prim, face; };
+struct alignas(16) TriF32 { float4 a, b, c; static constexpr bool kTwoLevel = false; };   // a=(p1,prim) b=(p2,face) c=(p3,0); prim/face are int bit patterns
+struct alignas(16) TriF64 { double p[9]; int32_t prim, face; static constexpr bool kTwoLevel = false; };
 static_assert(sizeof(TriF32) == 48 && sizeof(TriF64) == 80, "triangle records");
+
+// Two-level layout (instanced scenes; the analogue of plugin/accel_embree/accel_embree_instanced.cpp:96-165): ONE tree per
+// mesh over its OBJECT-space triangles (TriObj, bottom level) and one tree over the instances (InstDev, top level), all in one
+// node array — the top level's root is node 0, its leaf slots index InstDev records instead of triangles.  Node tests of a
+// bottom level run on the ray taken to object space (t is the same parameter in both spaces: the direction is transformed,
+// not normalised).  The LEAF test stays in world space: the triangle's vertices are transformed on the fly with the operations
+// the flattened build applies once (transform_point: glm's mat4 * vec4 order), so the Möller–Trumbore operands — and
+// (t, u, v) — are bit-identical to the flattened tree's and to accel::sahbvh's.
+struct alignas(16) TriObj { double p[9]; int32_t mesh, face; static constexpr bool kTwoLevel = true; };
+struct alignas(16) InstDev {
+    double M[12];                // object -> world, columns 0..3 of the instance's global transform (rows 0..2)
+    double Minv[12];             // world -> object
+    uint32_t root;               // root node of the mesh's tree
+    uint32_t tri_offset;         // global id of the instance's face 0 (PrimDev::tri_offset): a hit reports tri_offset + face
+    uint32_t prim, pad_;
+};
+static_assert(sizeof(TriObj) == 80 && sizeof(InstDev) == 208, "two-level records");
 
 struct RayD {                 // FP64 ray as the reference sees it
     D3 o, d;
@@ -99,6 +116,19 @@ LMCU_HD void load_tri(const TriF64* tris, uint32_t i, D3& p1, D3& p2, D3& p3) {
     const double2 a = q[0], b = q[1], c = q[2], d = q[3];
     const double e = tris[i].p[8];
     p1 = d3(a.x, a.y, b.x); p2 = d3(b.y, c.x, c.y); p3 = d3(d.x, d.y, e);
+}
+LMCU_HD void load_tri(const TriObj* tris, uint32_t i, D3& p1, D3& p2, D3& p3) {
+    load_tri(reinterpret_cast<const TriF64*>(tris), i, p1, p2, p3);
+}
+
+// glm mat4 * vec4(p,1) on the 3x4 part: (m0*x + m1*y) + (m2*z + m3*1)   (glm/detail/type_mat4x4.inl:526-537; build.cuh
+// transform_point is the same on a 16-entry matrix)
+LMCU_HD D3 transform_point34(const double* M, D3 p) {
+    D3 r;
+    r.x = addrn(addrn(mulrn(M[0], p.x), mulrn(M[3], p.y)), addrn(mulrn(M[6], p.z), M[9]));
+    r.y = addrn(addrn(mulrn(M[1], p.x), mulrn(M[4], p.y)), addrn(mulrn(M[7], p.z), M[10]));
+    r.z = addrn(addrn(mulrn(M[2], p.x), mulrn(M[5], p.y)), addrn(mulrn(M[8], p.z), M[11]));
+    return r;
 }
 
 // -- traversal ------------------------------------------------------------------------------------
@@ -210,17 +240,37 @@ LMCU_HD uint32_t node_hitmask(const uint4 n0, const uint4 n1, const uint4 n2, co
     return hitmask;
 }
 
+// FP32 view of ray r in the object space of an instance: o' = Minv (o, 1), d' = Minv (d, 0) formed in FP64, then rounded
+// (the rounding is what node_hitmask's padding covers; d' is NOT normalised, so t means the same in both spaces).
+LMCU_HD RayF make_rayf_obj(const RayD& r, const double* Mi) {
+    const double ox = Mi[0] * r.o.x + Mi[3] * r.o.y + Mi[6] * r.o.z + Mi[9];
+    const double oy = Mi[1] * r.o.x + Mi[4] * r.o.y + Mi[7] * r.o.z + Mi[10];
+    const double oz = Mi[2] * r.o.x + Mi[5] * r.o.y + Mi[8] * r.o.z + Mi[11];
+    const double dx = Mi[0] * r.d.x + Mi[3] * r.d.y + Mi[6] * r.d.z;
+    const double dy = Mi[1] * r.d.x + Mi[4] * r.d.y + Mi[7] * r.d.z;
+    const double dz = Mi[2] * r.d.x + Mi[5] * r.d.y + Mi[8] * r.d.z;
+    return make_rayf_f((float)ox, (float)oy, (float)oz, (float)dx, (float)dy, (float)dz);
+}
+
+constexpr uint32_t kNoInst = 0xffffffffu;
+
+// Stack entries of the two-level traversal, told apart by .y: > 0x00ffffff a node group (as in the one-level tree),
+// 1..0x00ffffff the instances of a top-level leaf still to be entered, 0 the marker below which the top level continues
+// (popping it takes the ray back to world space).
+
 // Closest hit (ANY=false) or any hit (ANY=true) of ray r in [r.tmin, r.tmax].
 // hit.t must be initialised to r.tmax and hit.tri to -1.  Returns false on stack overflow.
+// TriObj (two-level): `inst` is the top level's leaf-ordered instance table; hit.tri = InstDev::tri_offset + face.
 template <bool ANY, bool COUNT, typename TriT>
 LMCU_HD bool traverse(const WideNode* __restrict__ nodes, const TriT* __restrict__ tris,
-                      const RayD& r, HitD& hit, uint2* stack, TraverseCounters* ctr) {
-    const RayF f = make_rayf(r);
+                      const RayD& r, HitD& hit, uint2* stack, TraverseCounters* ctr, const InstDev* __restrict__ inst = nullptr) {
+    RayF f = make_rayf(r);
     const float tmin_dn = f32_down(r.tmin);
     float tmax_up = f32_up(hit.t);
     int sp = 0;
     uint2 ngroup = make_uint2(0u, 0x80000000u);   // the root occupies virtual slot 7 of group 0
     uint2 tgroup = make_uint2(0u, 0u);
+    uint32_t cinst = kNoInst;
     const uint4* nodes4 = reinterpret_cast<const uint4*>(nodes);
     while (true) {
         if (ngroup.y > 0x00ffffffu) {
@@ -249,18 +299,44 @@ LMCU_HD bool traverse(const WideNode* __restrict__ nodes, const TriT* __restrict
             tgroup.y &= ~(1u << ti);
             const uint32_t tri = tgroup.x + (uint32_t)ti;
             D3 p1, p2, p3;
-            load_tri(tris, tri, p1, p2, p3);
+            int32_t id = (int32_t)tri;
+            if constexpr (TriT::kTwoLevel) {
+                if (cinst == kNoInst) {
+                    // a top-level leaf item: park what is left of this node, then walk the instance's tree in its object space
+                    if (sp + 3 > kStackSize) return false;
+                    if (ngroup.y > 0x00ffffffu) stack[sp++] = ngroup;
+                    if (tgroup.y != 0u) stack[sp++] = tgroup;
+                    stack[sp++] = make_uint2(0u, 0u);
+                    cinst = tri;
+                    f = make_rayf_obj(r, inst[cinst].Minv);
+                    ngroup = make_uint2(inst[cinst].root, 0x80000000u);
+                    tgroup = make_uint2(0u, 0u);
+                    break;
+                }
+                load_tri(tris, tri, p1, p2, p3);
+                const double* M = inst[cinst].M;
+                p1 = transform_point34(M, p1); p2 = transform_point34(M, p2); p3 = transform_point34(M, p3);
+                id = (int32_t)(inst[cinst].tri_offset + (uint32_t)tris[tri].face);
+            } else {
+                load_tri(tris, tri, p1, p2, p3);
+            }
             if (COUNT) ctr->tris++;
             double t, u, v;
             if (tri_intersect(r, p1, p2, p3, r.tmin, hit.t, t, u, v)) {
-                hit.t = t; hit.u = u; hit.v = v; hit.tri = (int32_t)tri;
+                hit.t = t; hit.u = u; hit.v = v; hit.tri = id;
                 if (ANY) return true;
                 tmax_up = f32_up(t);
             }
         }
-        if (ngroup.y <= 0x00ffffffu) {
+        if (ngroup.y <= 0x00ffffffu && tgroup.y == 0u) {
             if (sp == 0) break;
-            ngroup = stack[--sp];
+            const uint2 e = stack[--sp];
+            if (TriT::kTwoLevel && e.y <= 0x00ffffffu) {
+                if (e.y == 0u) { cinst = kNoInst; f = make_rayf(r); }      // back in the top level
+                else tgroup = e;
+            } else {
+                ngroup = e;
+            }
         }
     }
     return true;

@@ -12,6 +12,11 @@ struct DevScene {
     const WideNode* nodes;
     const TriF32* t32;          // exactly one of t32 / t64 is non-null
     const TriF64* t64;
+    const TriObj* tobj;         // two-level tree: object-space triangles of the bottom levels; t32 / t64 / shade / uv are null and
+    const InstDev* inst;        // a hit's triangle id is the GLOBAL id tri_offset + face, resolved against prims + mesh arrays
+    const double* mesh_p;       // two-level tree only: the uploaded mesh arrays (9 doubles per face, 6 floats of texture coordinates)
+    const double* mesh_n;
+    const float* mesh_t;
     const TriShade* shade;
     const PrimDev* prims;
     const MaterialDev* mats;
@@ -34,6 +39,7 @@ struct DevScene {
 template <typename TriT> LMCU_HD const TriT* scene_tris(const DevScene& s);
 template <> LMCU_HD const TriF32* scene_tris<TriF32>(const DevScene& s) { return s.t32; }
 template <> LMCU_HD const TriF64* scene_tris<TriF64>(const DevScene& s) { return s.t64; }
+template <> LMCU_HD const TriObj* scene_tris<TriObj>(const DevScene& s) { return s.tobj; }
 
 // -- surface point at a hit (src/scene.cpp:333-344, src/mesh/mesh_raw.cpp:87-97), FP32 ------------------
 struct SurfPoint {
@@ -59,7 +65,38 @@ LMCU_HD void tri_fetch(const DevScene& s, uint32_t tri, F3& p1, F3& p2, F3& p3, 
     }
 }
 
+// Two-level tree: the surface point of global triangle id `g`, from the instance's transform and the mesh arrays — the
+// operations k_flatten / k_emit apply once per flattened triangle (build.cuh), applied at the hit instead.
+LMCU_HD SurfPoint surface_point_inst(const DevScene& s, uint32_t g, float u, float v) {
+    SurfPoint sp;
+    const uint32_t pi = find_prim(s.prims, s.num_prims, g);
+    const PrimDev& pr = s.prims[pi];
+    const uint32_t face = g - pr.tri_offset;
+    const size_t mf = (size_t)(pr.mesh_face_offset + face) * 9;
+    const double* q = s.mesh_p + mf;
+    const D3 w1 = transform_point(pr.M, d3(q[0], q[1], q[2])), w2 = transform_point(pr.M, d3(q[3], q[4], q[5])),
+             w3 = transform_point(pr.M, d3(q[6], q[7], q[8]));
+    const F3 p1 = f3((float)w1.x, (float)w1.y, (float)w1.z), p2 = f3((float)w2.x, (float)w2.y, (float)w2.z),
+             p3 = f3((float)w3.x, (float)w3.y, (float)w3.z);
+    sp.prim = (int32_t)pi; sp.face = (int32_t)face;
+    const float w = 1.0f - u - v;
+    sp.p = p1 * w + p2 * u + p3 * v;
+    F3 n[3];
+    shade_normals(pr, s.mesh_p, s.mesh_n, mf, n);
+    sp.n = normalize(n[0] * w + n[1] * u + n[2] * v);
+    sp.gn = normalize(cross(p2 - p1, p3 - p1)) * pr.det_sign;
+    sp.material = pr.material; sp.light = pr.light;
+    sp.tu = 0.f; sp.tv = 0.f;
+    if (s.mesh_t) {
+        const float* t = s.mesh_t + (size_t)(pr.mesh_face_offset + face) * 6;
+        sp.tu = t[0] * w + t[2] * u + t[4] * v;
+        sp.tv = t[1] * w + t[3] * u + t[5] * v;
+    }
+    return sp;
+}
+
 LMCU_HD SurfPoint surface_point(const DevScene& s, uint32_t tri, float u, float v) {
+    if (s.tobj) return surface_point_inst(s, tri, u, v);
     SurfPoint sp;
     F3 p1, p2, p3;
     tri_fetch(s, tri, p1, p2, p3, sp.prim, sp.face);
@@ -76,6 +113,17 @@ LMCU_HD SurfPoint surface_point(const DevScene& s, uint32_t tri, float u, float 
         sp.tv = t.t1.y * w + t.t2.y * u + t.t3.y * v;
     }
     return sp;
+}
+
+// (primitive ordinal, face) of a hit's triangle id
+LMCU_HD void tri_ids(const DevScene& s, uint32_t tri, int32_t& prim, int32_t& face) {
+    if (s.tobj) {
+        prim = (int32_t)find_prim(s.prims, s.num_prims, tri);
+        face = (int32_t)(tri - s.prims[prim].tri_offset);
+    } else {
+        F3 p1, p2, p3;
+        tri_fetch(s, tri, p1, p2, p3, prim, face);
+    }
 }
 
 // -- composite materials: mapKd textures, material::mask, mixture_wavefrontobj, constant-weight mixtures ---------------
@@ -276,7 +324,7 @@ LMCU_HD void raycast_pixel(const DevScene& s, const RaycastParams& p, int x, int
     camera_primary_ray_d(s.cam, divrn(addrn((double)x, 0.5), (double)p.width), divrn(addrn((double)y, 0.5), (double)p.height), r.o, r.d);
     r.tmin = kEps; r.tmax = kInf;
     HitD h; h.t = r.tmax; h.tri = -1; h.u = h.v = 0;
-    traverse<false, false, TriT>(s.nodes, scene_tris<TriT>(s), r, h, stack, nullptr);
+    traverse<false, false, TriT>(s.nodes, scene_tris<TriT>(s), r, h, stack, nullptr, s.inst);
     F3 c;
     if (h.tri < 0) {
         if (s.env_light >= 0) {
@@ -311,7 +359,7 @@ LMCU_HD void ao_pixel(const DevScene& s, int width, int height, int x, int y, in
     camera_primary_ray_d(s.cam, divrn(addrn((double)x, 0.5), (double)width), divrn(addrn((double)y, 0.5), (double)height), r.o, r.d);
     r.tmin = kEps; r.tmax = kInf;
     HitD h; h.t = r.tmax; h.tri = -1; h.u = h.v = 0;
-    traverse<false, false, TriT>(s.nodes, scene_tris<TriT>(s), r, h, stack, nullptr);
+    traverse<false, false, TriT>(s.nodes, scene_tris<TriT>(s), r, h, stack, nullptr, s.inst);
     *ray_count += 1;
     if (h.tri < 0) return;   // the reference leaves the pixel untouched on a miss
     const SurfPoint sp = surface_point(s, (uint32_t)h.tri, (float)h.u, (float)h.v);
@@ -327,7 +375,7 @@ LMCU_HD void ao_pixel(const DevScene& s, int width, int height, int x, int y, in
         q.o = d3(sp.p.x, sp.p.y, sp.p.z); q.d = d3(wo.x, wo.y, wo.z);
         q.tmin = kEps; q.tmax = ao_distance;
         HitD hq; hq.t = q.tmax; hq.tri = -1; hq.u = hq.v = 0;
-        traverse<true, false, TriT>(s.nodes, scene_tris<TriT>(s), q, hq, stack, nullptr);
+        traverse<true, false, TriT>(s.nodes, scene_tris<TriT>(s), q, hq, stack, nullptr, s.inst);
         V += hq.tri < 0 ? 1.f : 0.f;
     }
     *ray_count += (uint32_t)spp;
@@ -594,7 +642,7 @@ LMCU_HD bool pt_trace(const DevScene& s, float4 o, float4 d, HitD& h, uint2* sta
     r.o = d3(o.x, o.y, o.z); r.d = d3(d.x, d.y, d.z);
     r.tmin = o.w; r.tmax = d.w;
     h.t = r.tmax; h.tri = -1; h.u = h.v = 0;
-    return traverse<ANY, COUNT, TriT>(s.nodes, scene_tris<TriT>(s), r, h, stack, tc);
+    return traverse<ANY, COUNT, TriT>(s.nodes, scene_tris<TriT>(s), r, h, stack, tc, s.inst);
 }
 
 struct ShadeOut {

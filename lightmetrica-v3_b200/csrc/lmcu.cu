@@ -36,6 +36,9 @@
 #define LMCU_TRAV_BLOCK 128    // threads per CTA of the queue-traversal kernels (the loop is per warp; this only sets the granularity
                                // at which the block scheduler hands SM resources to the kernels of different wavefronts)
 #endif
+#ifndef LMCU_MINB_TWO
+#define LMCU_MINB_TWO 5  // ... the two-level instantiations (TriObj): 96 registers, no spills (at 80 they spill 140 bytes)
+#endif
 #ifndef LMCU_MINB
 #define LMCU_MINB 6      // resident CTAs per SM the queue kernels are compiled for (register budget: 80 registers)
 #endif
@@ -196,6 +199,67 @@ __global__ void k_emit(const uint32_t* tri_order, uint32_t nt, const PrimDev* pr
     if (k < nt) emit_body(k, tri_order, prims, num_prims, wp, mesh_p, mesh_n, t32, t64, shade, mesh_t, uv);
 }
 
+// -- two-level layout (bvh.cuh TriObj / InstDev, build.cuh) ------------------------------------------------------------------
+__global__ void k_obj_bounds(const double* p, uint32_t n, float* tri_lo, float* tri_hi, double* centre, float* bounds6) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    float lo[3] = { 3e38f, 3e38f, 3e38f }, hi[3] = { -3e38f, -3e38f, -3e38f };
+    if (k < n) {
+        obj_bounds_body(k, p, tri_lo, tri_hi, centre);
+        for (int a = 0; a < 3; a++) { lo[a] = tri_lo[(size_t)k * 3 + a]; hi[a] = tri_hi[(size_t)k * 3 + a]; }
+    }
+    for (int a = 0; a < 3; a++) {
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+            hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+        }
+    }
+    if ((threadIdx.x & 31) == 0) {
+        for (int a = 0; a < 3; a++) if (lo[a] <= hi[a]) { atomic_min_f(bounds6 + a, lo[a]); atomic_max_f(bounds6 + 3 + a, hi[a]); }
+    }
+}
+
+// World-space box of every primitive: the union over its faces of the vertices the leaf test will form.  A warp's 32
+// consecutive triangles nearly always belong to one primitive: then one lane issues the atomics for all of them.
+__global__ void k_inst_bounds(const PrimDev* prims, int num_prims, const double* mesh_p, uint32_t nt, float* inst_lo, float* inst_hi) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    float lo[3] = { 3e38f, 3e38f, 3e38f }, hi[3] = { -3e38f, -3e38f, -3e38f };
+    uint32_t pi = 0xffffffffu;
+    if (g < nt) pi = world_bounds_body(g, prims, num_prims, mesh_p, lo, hi);
+    const uint32_t p0 = __shfl_sync(0xffffffffu, pi, 0);
+    if (__all_sync(0xffffffffu, pi == p0)) {
+        if (p0 == 0xffffffffu) return;
+        for (int a = 0; a < 3; a++) {
+            for (int o = 16; o > 0; o >>= 1) {
+                lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+                hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+            }
+        }
+        if ((threadIdx.x & 31) != 0) return;
+    }
+    if (pi == 0xffffffffu) return;
+    for (int a = 0; a < 3; a++) { atomic_min_f(inst_lo + (size_t)pi * 3 + a, lo[a]); atomic_max_f(inst_hi + (size_t)pi * 3 + a, hi[a]); }
+}
+
+__global__ void k_inst_centres(const float* inst_lo, const float* inst_hi, uint32_t np, double* centre, float* bounds6) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= np) return;
+    for (int a = 0; a < 3; a++) {
+        const float l = inst_lo[(size_t)i * 3 + a], h = inst_hi[(size_t)i * 3 + a];
+        centre[(size_t)i * 3 + a] = ((double)l + (double)h) * 0.5;
+        atomic_min_f(bounds6 + a, l); atomic_max_f(bounds6 + 3 + a, h);
+    }
+}
+
+__global__ void k_emit_obj(const uint32_t* order, const double* p, uint32_t n, int32_t mesh, TriObj* out) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) emit_obj_body(k, order, p, mesh, out);
+}
+
+__global__ void k_relocate(WideNode* nodes, uint32_t n, uint32_t node_off, uint32_t item_off) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) relocate_body(nodes[i], node_off, item_off);
+}
+
 // ================================================================================================
 // kernels: accel batches
 // ================================================================================================
@@ -217,12 +281,12 @@ __global__ void k_intersect_one(DevScene s, const LmcuRay* __restrict__ ray, Lmc
     r.o = d3(ray->o[0], ray->o[1], ray->o[2]); r.d = d3(ray->d[0], ray->d[1], ray->d[2]);
     r.tmin = ray->tmin; r.tmax = ray->tmax;
     HitD h; h.t = r.tmax; h.u = h.v = 0; h.tri = -1;
-    const bool ok = traverse<false, false, TriT>(s.nodes, scene_tris<TriT>(s), r, h, stack, nullptr);
+    const bool ok = traverse<false, false, TriT>(s.nodes, scene_tris<TriT>(s), r, h, stack, nullptr, s.inst);
     LmcuHit o;
     o.t = h.t; o.u = h.u; o.v = h.v; o.primitive = ok ? -1 : -2; o.face = -1;     // -2: traversal stack overflow
     if (ok && h.tri >= 0) {
-        F3 p1, p2, p3; int32_t pi;
-        tri_fetch(s, (uint32_t)h.tri, p1, p2, p3, pi, o.face);
+        int32_t pi;
+        tri_ids(s, (uint32_t)h.tri, pi, o.face);
         o.primitive = s.prims[pi].node_index;
     }
     *hit = o;
@@ -655,6 +719,7 @@ __global__ void __launch_bounds__(LMCU_SHADE_BLOCK, LMCU_SHADE_MINB) k_pt_shade(
 }
 
 // -- queue kernels on the warp-persistent traversal (trace.cuh) -----------------------------------------
+template <typename TriT> constexpr int trav_minb() { return TriT::kTwoLevel ? LMCU_MINB_TWO : LMCU_MINB; }
 
 struct BatchIO {                       // accel batches: LmcuRay in, LmcuHit out (include/lmcu.h)
     static constexpr bool kExactT = true;
@@ -673,8 +738,8 @@ struct BatchIO {                       // accel batches: LmcuRay in, LmcuHit out
         int32_t prim = -1, face = -1;
         double u = 0.0, v = 0.0;
         if (tri >= 0) {
-            F3 p1, p2, p3; int32_t pi;
-            tri_fetch(s, (uint32_t)tri, p1, p2, p3, pi, face);
+            int32_t pi;
+            tri_ids(s, (uint32_t)tri, pi, face);
             prim = s.prims[pi].node_index;
             u = divrn(u_raw, ad); v = divrn(v_raw, ad);         // accel_sahbvh.cpp:74, the same IEEE quotients
         }
@@ -688,12 +753,12 @@ struct BatchIO {                       // accel batches: LmcuRay in, LmcuHit out
 };
 
 template <typename TriT, bool COUNT>
-__global__ void __launch_bounds__(LMCU_TRAV_BLOCK, LMCU_MINB) k_intersect_q(DevScene s, const LmcuRay* __restrict__ rays, uint32_t n,
+__global__ void __launch_bounds__(LMCU_TRAV_BLOCK, trav_minb<TriT>()) k_intersect_q(DevScene s, const LmcuRay* __restrict__ rays, uint32_t n,
                                                      LmcuHit* __restrict__ hits, uint32_t* cursor,
                                                      unsigned long long* counters, uint32_t* overflow) {
     BatchIO io; io.s = s; io.rays = rays; io.hits = hits;
     TraverseCounters tc; tc.nodes = tc.tris = 0;
-    trace_queue<false, COUNT, TriT>(s.nodes, scene_tris<TriT>(s), n, cursor, io, overflow, &tc, s.fetch_threshold);
+    trace_queue<false, COUNT, TriT>(s.nodes, scene_tris<TriT>(s), n, cursor, io, overflow, &tc, s.fetch_threshold, s.inst);
     if (COUNT) { atomicAdd(counters, (unsigned long long)tc.nodes); atomicAdd(counters + 1, (unsigned long long)tc.tris); }
 }
 
@@ -717,10 +782,10 @@ struct ExtendIO {                      // pt extend: path queue in, float4 hit r
 };
 
 template <typename TriT, bool COUNT>
-__global__ void __launch_bounds__(LMCU_TRAV_BLOCK, LMCU_MINB) k_pt_extend_q(DevScene s, PathQueue q, float4* hits, PtCounters* ctr, int cur) {
+__global__ void __launch_bounds__(LMCU_TRAV_BLOCK, trav_minb<TriT>()) k_pt_extend_q(DevScene s, PathQueue q, float4* hits, PtCounters* ctr, int cur) {
     ExtendIO io; io.ray_o = q.ray_o; io.ray_d = q.ray_d; io.hits = hits;
     TraverseCounters tc; tc.nodes = tc.tris = 0;
-    trace_queue<false, COUNT, TriT>(s.nodes, scene_tris<TriT>(s), ctr->count[cur], &ctr->fetch_extend, io, &ctr->overflow, &tc, s.fetch_threshold);
+    trace_queue<false, COUNT, TriT>(s.nodes, scene_tris<TriT>(s), ctr->count[cur], &ctr->fetch_extend, io, &ctr->overflow, &tc, s.fetch_threshold, s.inst);
     if (COUNT) { atomicAdd(&ctr->nodes_extend, (unsigned long long)tc.nodes); atomicAdd(&ctr->tris_extend, (unsigned long long)tc.tris); }
 }
 
@@ -745,12 +810,12 @@ struct ShadowIO {                      // pt shadow: visible (include/lm/scene.h
 };
 
 template <typename TriT, bool COUNT>
-__global__ void __launch_bounds__(LMCU_TRAV_BLOCK, LMCU_MINB) k_pt_shadow_q(DevScene s, ShadowQueue sq, float* film, PtCounters* ctr) {
+__global__ void __launch_bounds__(LMCU_TRAV_BLOCK, trav_minb<TriT>()) k_pt_shadow_q(DevScene s, ShadowQueue sq, float* film, PtCounters* ctr) {
     const uint32_t n = ctr->shadow_count;
     if (blockIdx.x == 0 && threadIdx.x == 0) { ctr->rays += n; ctr->shadow_rays += n; }
     ShadowIO io; io.ray_o = sq.ray_o; io.ray_d = sq.ray_d; io.contrib = sq.contrib; io.film = film;
     TraverseCounters tc; tc.nodes = tc.tris = 0;
-    trace_queue<true, COUNT, TriT>(s.nodes, scene_tris<TriT>(s), n, &ctr->fetch_shadow, io, &ctr->overflow, &tc, s.fetch_threshold);
+    trace_queue<true, COUNT, TriT>(s.nodes, scene_tris<TriT>(s), n, &ctr->fetch_shadow, io, &ctr->overflow, &tc, s.fetch_threshold, s.inst);
     if (COUNT) { atomicAdd(&ctr->nodes_shadow, (unsigned long long)tc.nodes); atomicAdd(&ctr->tris_shadow, (unsigned long long)tc.tris); }
 }
 
@@ -997,6 +1062,13 @@ struct LmcuScene {
     DBuf<TriF64> t64;
     DBuf<TriShade> shade;
     DBuf<TriUV> uv;
+    DBuf<TriObj> tobj;                   // two-level layout (bvh.cuh): object-space triangles of the mesh trees, leaf order
+    DBuf<InstDev> inst;                  // ... instance records in the top level's leaf order
+    bool two_level = false;
+    int tri_kind() const { return two_level ? 2 : fp32 ? 1 : 0; }      // LMCU_DISPATCH: TriObj / TriF32 / TriF64 instantiations
+    int trav_ctas() const { return two_level ? std::min(ctas_per_sm, LMCU_MINB_TWO) : ctas_per_sm; }   // CTAs per SM of the persistent traversal grids
+    bool pool_on() const { return pool_mode && !two_level; }           // the shared-memory ray pool (trace2.cuh) walks one-level trees only
+    std::vector<uint32_t> face_offset;   // per mesh, first face in mesh_p / mesh_n / mesh_t
     bool built = false, fp32 = false;
     float bounds[6] = { 0, 0, 0, 0, 0, 0 };   // scene AABB (float, outward): Light::set_scene_bound for the light tracer
     uint64_t blob_desc_digest = 0;       // accel-only scene restored from a blob: the digest that blob carried
@@ -1062,6 +1134,7 @@ struct LmcuScene {
         DevScene d{};
         d.nodes = nodes.p; d.t32 = t32.p; d.t64 = t64.p; d.shade = shade.p; d.prims = prims.p; d.mats = mats.p;
         d.lights = lights.p; d.emit = emit.p; d.cdf = cdf.p; d.env_tex = env_tex.p;
+        if (two_level) { d.tobj = tobj.p; d.inst = inst.p; d.mesh_p = mesh_p.p; d.mesh_n = mesh_n.p; d.mesh_t = mesh_t.p; }
         d.uv = uv.p; d.textures = textures.p; d.texels = texels.p; d.mix = mix.p;
         d.num_prims = num_prims; d.num_lights = num_lights; d.env_light = env_light; d.fetch_threshold = fetch_threshold; d.num_tris = nt; d.cam = cam;
         d.pool_refill = pool_refill;
@@ -1167,6 +1240,7 @@ int lmcu_scene_upload(LmcuScene* s, const LmcuSceneDesc* d) {
         }
     }
     s->h_prims = ps.prims;
+    s->face_offset = ps.face_offset;
     s->nt = ps.nt;
     s->num_prims = (int)ps.prims.size();
     s->num_lights = (int)ps.lights.size();
@@ -1200,42 +1274,24 @@ int lmcu_scene_upload(LmcuScene* s, const LmcuSceneDesc* d) {
 }
 
 // -- build ------------------------------------------------------------------------------------------
-int lmcu_accel_build(LmcuScene* s, const LmcuBuildOptions* opts, LmcuBuildStats* stats) {
-    if (!s) return fail(LMCU_ERR_INVALID_ARGUMENT, "null scene");
-    if (s->nt == 0) return fail(LMCU_ERR_UNSUPPORTED, "Missing primitives.");
-    CU(cudaSetDevice(s->device));
-    const uint32_t nt = s->nt;
-    int max_leaf = opts && opts->max_leaf_tris ? opts->max_leaf_tris : 2;
-    if (const char* e = getenv("LMCU_LEAF")) max_leaf = atoi(e);      // tuning only
-    if (max_leaf < 1 || max_leaf > 3) return fail(LMCU_ERR_INVALID_ARGUMENT, "max_leaf_tris must be in 1..3");
-    cudaStream_t st = s->stream;
-    CU(cudaEventRecord(s->ev0, st));
+namespace {
+struct SyncOnExit { cudaStream_t st; ~SyncOnExit() { cudaStreamSynchronize(st); cudaGetLastError(); } };
+}
 
-    DBuf<double> wp, centre;
-    DBuf<float> tri_lo, tri_hi, bounds;
-    DBuf<int> exact;
+// morton -> radix sort -> hierarchy -> fit -> collapse over n items with float boxes lo / hi and centres, all on the device;
+// bounds6 = the items' common box.  Out: `wide` (n entries allocated, *num_nodes used, root = entry 0) and `order`
+// (leaf-order position -> item).  Shared by the flattened tree, the per-mesh trees and the tree over the instances.
+static int build_tree(cudaStream_t st, uint32_t nt, const float* tri_lo, const float* tri_hi, const double* centre, const float* bounds6,
+                      int max_leaf, double big_frac, DBuf<WideNode>& wide, DBuf<uint32_t>& tri_order, uint32_t* num_nodes) {
     DBuf<uint64_t> keys, keys_sorted;
-    DBuf<uint32_t> vals, vals_sorted, parent, arrive, tri_order, counters;
+    DBuf<uint32_t> vals, vals_sorted, parent, arrive, counters;
     DBuf<BinNode> bin;
-    DBuf<WideNode> wide;
     DBuf<CollapseItem> queue[2];
     // declared after the temporaries => destroyed before them: on an early error return kernels may still be running on
     // the stream, and a block parked in the cache while a kernel writes it could be handed to the next allocation
-    struct SyncOnExit { cudaStream_t st; ~SyncOnExit() { cudaStreamSynchronize(st); cudaGetLastError(); } } sync_on_exit{ st };
-    CU(wp.alloc((size_t)nt * 9)); CU(centre.alloc((size_t)nt * 3));
-    CU(tri_lo.alloc((size_t)nt * 3)); CU(tri_hi.alloc((size_t)nt * 3));
-    CU(bounds.alloc(6)); CU(exact.alloc(1));
-    const float binit[6] = { 3e38f, 3e38f, 3e38f, -3e38f, -3e38f, -3e38f };
-    const int one = 1;
-    CU(cudaMemcpyAsync(bounds.p, binit, sizeof(binit), cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(exact.p, &one, sizeof(int), cudaMemcpyHostToDevice, st));
-    k_flatten<<<grid_for(nt, 256), 256, 0, st>>>(s->prims.p, s->num_prims, s->mesh_p.p, nt, wp.p, tri_lo.p, tri_hi.p,
-                                                 centre.p, bounds.p, exact.p);
-    CU(cudaGetLastError());
+    SyncOnExit sync_on_exit{ st };
     CU(keys.alloc(nt)); CU(keys_sorted.alloc(nt)); CU(vals.alloc(nt)); CU(vals_sorted.alloc(nt));
-    double big_frac = 1.0 / 16.0;                                    // LMCU_BIG: denominator (0 = off), tuning only
-    if (const char* e = getenv("LMCU_BIG")) big_frac = atof(e) > 0 ? 1.0 / atof(e) : 0.0;
-    k_morton<<<grid_for(nt, 256), 256, 0, st>>>(centre.p, nt, bounds.p, keys.p, vals.p, tri_lo.p, tri_hi.p, big_frac);
+    k_morton<<<grid_for(nt, 256), 256, 0, st>>>(centre, nt, bounds6, keys.p, vals.p, tri_lo, tri_hi, big_frac);
     CU(cudaGetLastError());
     {
         size_t tmp_bytes = 0;
@@ -1252,14 +1308,14 @@ int lmcu_accel_build(LmcuScene* s, const LmcuBuildOptions* opts, LmcuBuildStats*
         k_hierarchy<<<grid_for(nt - 1, 256), 256, 0, st>>>(keys_sorted.p, (int)nt, bin.p, parent.p);
         CU(cudaGetLastError());
     }
-    k_fit<<<grid_for(nt, 256), 256, 0, st>>>(bin.p, parent.p, vals_sorted.p, tri_lo.p, tri_hi.p, (int)nt, arrive.p);
+    k_fit<<<grid_for(nt, 256), 256, 0, st>>>(bin.p, parent.p, vals_sorted.p, tri_lo, tri_hi, (int)nt, arrive.p);
     CU(cudaGetLastError());
     // collapse, level by level
     CU(wide.alloc(nt)); CU(tri_order.alloc(nt)); CU(counters.alloc(4));
     CU(queue[0].alloc(nt)); CU(queue[1].alloc(nt));
     const uint32_t cinit[4] = { 1u, 0u, 0u, 0u };   // node_counter (root = 0 taken), tri_counter, next_count, -
     CU(cudaMemcpyAsync(counters.p, cinit, sizeof(cinit), cudaMemcpyHostToDevice, st));
-    const CollapseItem root_item = { nt > 1 ? 0u : 0u, 0u };   // binary root is internal node 0 (or leaf 0 when nt == 1)
+    const CollapseItem root_item = { 0u, 0u };      // binary root is internal node 0 (or leaf 0 when nt == 1)
     CU(cudaMemcpyAsync(queue[0].p, &root_item, sizeof(root_item), cudaMemcpyHostToDevice, st));
     uint32_t count = 1;
     int cur = 0;
@@ -1280,31 +1336,148 @@ int lmcu_accel_build(LmcuScene* s, const LmcuBuildOptions* opts, LmcuBuildStats*
         cur ^= 1;
         if (count == 0) {
             if (h[1] != nt) return fail(LMCU_ERR_CUDA, "bvh collapse lost triangles");
-            // shrink the node array to its final size
-            CU(s->nodes.alloc(h[0]));
-            CU(cudaMemcpyAsync(s->nodes.p, wide.p, (size_t)h[0] * sizeof(WideNode), cudaMemcpyDeviceToDevice, st));
+            *num_nodes = h[0];
         }
     }
-    int h_exact = 0;
-    CU(cudaMemcpyAsync(s->bounds, bounds.p, sizeof(s->bounds), cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(&h_exact, exact.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    // 48-byte float records when every vertex is float-representable AND the triangle array is too large to stay in
-    // cache (C3: 480 MB instead of 800 MB streamed from HBM).  A small scene keeps the 80-byte FP64 records: they are
-    // served by L1 / L2 either way and spare the 9 F2F.F64.F32 per triangle test, the largest stall site of the extend
-    // kernel (profiles/r01_ncu_summary_v6.md; C2 pt 1322 -> 1340 Mpaths/s).
-    s->fp32 = h_exact != 0 && (size_t)nt * sizeof(TriF64) > (size_t(48) << 20);
-    if (const char* e = getenv("LMCU_TRI64")) s->fp32 = h_exact != 0 && atoi(e) == 0;   // tuning only: 1 = FP64 records, 0 = float records
-    s->t32.release(); s->t64.release();
-    if (s->fp32) CU(s->t32.alloc(nt)); else CU(s->t64.alloc(nt));
-    CU(s->shade.alloc(nt));
-    CU(s->uv.alloc(s->mesh_t.p ? nt : 0));
-    k_emit<<<grid_for(nt, 256), 256, 0, st>>>(tri_order.p, nt, s->prims.p, s->num_prims, wp.p, s->mesh_p.p, s->mesh_n.p,
-                                              s->t32.p, s->t64.p, s->shade.p, s->mesh_t.p, s->uv.p);
+    return LMCU_OK;
+}
+
+// The two-level layout (LmcuBuildOptions::two_level): node array = [tree over the primitives | one tree per mesh in use],
+// object-space triangles per mesh in leaf order, instance records in the top level's leaf order.
+static int build_two_level(LmcuScene* s, cudaStream_t st, int max_leaf, double big_frac) {
+    const uint32_t np = (uint32_t)s->num_prims, nt = s->nt;
+    const float binit[6] = { 3e38f, 3e38f, 3e38f, -3e38f, -3e38f, -3e38f };
+    DBuf<float> ilo, ihi, bounds;
+    DBuf<double> icentre;
+    DBuf<WideNode> top;
+    DBuf<uint32_t> iorder;
+    struct MeshTree { DBuf<WideNode> wide; DBuf<uint32_t> order; uint32_t num_nodes = 0, nf = 0, node_off = 0, item_off = 0; bool used = false; };
+    std::vector<MeshTree> trees(s->face_offset.empty() ? 0 : s->face_offset.size() - 1);
+    SyncOnExit sync_on_exit{ st };
+    CU(ilo.alloc((size_t)np * 3)); CU(ihi.alloc((size_t)np * 3)); CU(icentre.alloc((size_t)np * 3)); CU(bounds.alloc(6));
+    k_fill<<<grid_for((size_t)np * 3, 256), 256, 0, st>>>(ilo.p, (size_t)np * 3, 3e38f);
+    k_fill<<<grid_for((size_t)np * 3, 256), 256, 0, st>>>(ihi.p, (size_t)np * 3, -3e38f);
+    CU(cudaMemcpyAsync(bounds.p, binit, sizeof(binit), cudaMemcpyHostToDevice, st));
+    k_inst_bounds<<<grid_for(nt, 256), 256, 0, st>>>(s->prims.p, s->num_prims, s->mesh_p.p, nt, ilo.p, ihi.p);
+    k_inst_centres<<<grid_for(np, 256), 256, 0, st>>>(ilo.p, ihi.p, np, icentre.p, bounds.p);
     CU(cudaGetLastError());
+    uint32_t top_nodes = 0;
+    int rc = build_tree(st, np, ilo.p, ihi.p, icentre.p, bounds.p, max_leaf, big_frac, top, iorder, &top_nodes);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(s->bounds, bounds.p, sizeof(s->bounds), cudaMemcpyDeviceToHost, st));
+    std::vector<uint32_t> h_order(np);
+    CU(cudaMemcpyAsync(h_order.data(), iorder.p, (size_t)np * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    // bottom levels: one tree per mesh some primitive refers to
+    uint32_t total_nodes = top_nodes, total_items = 0;
+    for (const PrimDev& pr : s->h_prims) {
+        MeshTree& t = trees[pr.mesh];
+        if (t.used) continue;
+        t.used = true; t.nf = pr.num_faces;
+        const double* p = s->mesh_p.p + (size_t)pr.mesh_face_offset * 9;
+        DBuf<float> lo, hi, mb;
+        DBuf<double> centre;
+        CU(lo.alloc((size_t)t.nf * 3)); CU(hi.alloc((size_t)t.nf * 3)); CU(centre.alloc((size_t)t.nf * 3)); CU(mb.alloc(6));
+        CU(cudaMemcpyAsync(mb.p, binit, sizeof(binit), cudaMemcpyHostToDevice, st));
+        k_obj_bounds<<<grid_for(t.nf, 256), 256, 0, st>>>(p, t.nf, lo.p, hi.p, centre.p, mb.p);
+        CU(cudaGetLastError());
+        rc = build_tree(st, t.nf, lo.p, hi.p, centre.p, mb.p, max_leaf, big_frac, t.wide, t.order, &t.num_nodes);
+        if (rc) return rc;
+        t.node_off = total_nodes; t.item_off = total_items;
+        total_nodes += t.num_nodes; total_items += t.nf;
+    }
+    CU(s->nodes.alloc(total_nodes));
+    CU(s->tobj.alloc(total_items));
+    CU(cudaMemcpyAsync(s->nodes.p, top.p, (size_t)top_nodes * sizeof(WideNode), cudaMemcpyDeviceToDevice, st));
+    for (const PrimDev& pr : s->h_prims) {
+        MeshTree& t = trees[pr.mesh];
+        if (!t.used) continue;
+        t.used = false;                                   // placed once
+        k_relocate<<<grid_for(t.num_nodes, 256), 256, 0, st>>>(t.wide.p, t.num_nodes, t.node_off, t.item_off);
+        CU(cudaMemcpyAsync(s->nodes.p + t.node_off, t.wide.p, (size_t)t.num_nodes * sizeof(WideNode), cudaMemcpyDeviceToDevice, st));
+        k_emit_obj<<<grid_for(t.nf, 256), 256, 0, st>>>(t.order.p, s->mesh_p.p + (size_t)pr.mesh_face_offset * 9, t.nf, pr.mesh, s->tobj.p + t.item_off);
+        CU(cudaGetLastError());
+    }
+    std::vector<InstDev> h_inst(np);
+    for (uint32_t k = 0; k < np; k++) {
+        const uint32_t pi = h_order[k];
+        if (pi >= np || !make_inst(s->h_prims[pi], pi, trees[s->h_prims[pi].mesh].node_off, h_inst[k]))
+            return fail(LMCU_ERR_CUDA, "two-level build: bad instance record");
+    }
+    CU(s->inst.alloc(np));
+    CU(cudaMemcpyAsync(s->inst.p, h_inst.data(), (size_t)np * sizeof(InstDev), cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));
+    return LMCU_OK;
+}
+
+int lmcu_accel_build(LmcuScene* s, const LmcuBuildOptions* opts, LmcuBuildStats* stats) {
+    if (!s) return fail(LMCU_ERR_INVALID_ARGUMENT, "null scene");
+    if (s->nt == 0) return fail(LMCU_ERR_UNSUPPORTED, "Missing primitives.");
+    CU(cudaSetDevice(s->device));
+    const uint32_t nt = s->nt;
+    int max_leaf = opts && opts->max_leaf_tris ? opts->max_leaf_tris : 2;
+    if (const char* e = getenv("LMCU_LEAF")) max_leaf = atoi(e);      // tuning only
+    if (max_leaf < 1 || max_leaf > 3) return fail(LMCU_ERR_INVALID_ARGUMENT, "max_leaf_tris must be in 1..3");
+    int two_level_opt = opts ? opts->two_level : 0;
+    if (const char* e = getenv("LMCU_TWO_LEVEL")) two_level_opt = atoi(e);
+    double big_frac = 1.0 / 16.0;                                    // LMCU_BIG: denominator (0 = off), tuning only
+    if (const char* e = getenv("LMCU_BIG")) big_frac = atof(e) > 0 ? 1.0 / atof(e) : 0.0;
+    cudaStream_t st = s->stream;
+    CU(cudaEventRecord(s->ev0, st));
+    s->built = false;
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    if (const char* e = getenv("LMCU_BUILD_BUDGET_GB")) free_b = (size_t)(atof(e) * double(size_t(1) << 30));   // the memory the automatic layout choice plans with
+    s->two_level = want_two_level(two_level_opt, s->h_prims, s->face_offset, nt, (double)free_b);
+    s->t32.release(); s->t64.release(); s->tobj.release(); s->inst.release(); s->shade.release(); s->uv.release();
+
+    if (s->two_level) {
+        const int rc = build_two_level(s, st, max_leaf, big_frac);
+        if (rc) return rc;
+        s->fp32 = false;
+    } else {
+        DBuf<double> wp, centre;
+        DBuf<float> tri_lo, tri_hi, bounds;
+        DBuf<int> exact;
+        DBuf<uint32_t> tri_order;
+        DBuf<WideNode> wide;
+        SyncOnExit sync_on_exit{ st };
+        CU(wp.alloc((size_t)nt * 9)); CU(centre.alloc((size_t)nt * 3));
+        CU(tri_lo.alloc((size_t)nt * 3)); CU(tri_hi.alloc((size_t)nt * 3));
+        CU(bounds.alloc(6)); CU(exact.alloc(1));
+        const float binit[6] = { 3e38f, 3e38f, 3e38f, -3e38f, -3e38f, -3e38f };
+        const int one = 1;
+        CU(cudaMemcpyAsync(bounds.p, binit, sizeof(binit), cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(exact.p, &one, sizeof(int), cudaMemcpyHostToDevice, st));
+        k_flatten<<<grid_for(nt, 256), 256, 0, st>>>(s->prims.p, s->num_prims, s->mesh_p.p, nt, wp.p, tri_lo.p, tri_hi.p,
+                                                     centre.p, bounds.p, exact.p);
+        CU(cudaGetLastError());
+        uint32_t num_nodes = 0;
+        const int rc = build_tree(st, nt, tri_lo.p, tri_hi.p, centre.p, bounds.p, max_leaf, big_frac, wide, tri_order, &num_nodes);
+        if (rc) return rc;
+        // shrink the node array to its final size
+        CU(s->nodes.alloc(num_nodes));
+        CU(cudaMemcpyAsync(s->nodes.p, wide.p, (size_t)num_nodes * sizeof(WideNode), cudaMemcpyDeviceToDevice, st));
+        int h_exact = 0;
+        CU(cudaMemcpyAsync(s->bounds, bounds.p, sizeof(s->bounds), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(&h_exact, exact.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        // 48-byte float records when every vertex is float-representable AND the triangle array is too large to stay in
+        // cache (C3: 480 MB instead of 800 MB streamed from HBM).  A small scene keeps the 80-byte FP64 records: they are
+        // served by L1 / L2 either way and spare the 9 F2F.F64.F32 per triangle test, the largest stall site of the extend
+        // kernel (profiles/r01_ncu_summary_v6.md; C2 pt 1322 -> 1340 Mpaths/s).
+        s->fp32 = h_exact != 0 && (size_t)nt * sizeof(TriF64) > (size_t(48) << 20);
+        if (const char* e = getenv("LMCU_TRI64")) s->fp32 = h_exact != 0 && atoi(e) == 0;   // tuning only: 1 = FP64 records, 0 = float records
+        if (s->fp32) CU(s->t32.alloc(nt)); else CU(s->t64.alloc(nt));
+        CU(s->shade.alloc(nt));
+        CU(s->uv.alloc(s->mesh_t.p ? nt : 0));
+        k_emit<<<grid_for(nt, 256), 256, 0, st>>>(tri_order.p, nt, s->prims.p, s->num_prims, wp.p, s->mesh_p.p, s->mesh_n.p,
+                                                  s->t32.p, s->t64.p, s->shade.p, s->mesh_t.p, s->uv.p);
+        CU(cudaGetLastError());
+    }
     CU(cudaEventRecord(s->ev1, st));
     double h_cost[3] = { 0, 0, 0 };
-    if (stats) {
+    if (stats && !s->two_level) {
         DBuf<double> cost;
         CU(cost.alloc(3));
         CU(cudaMemsetAsync(cost.p, 0, 3 * sizeof(double), st));
@@ -1321,9 +1494,11 @@ int lmcu_accel_build(LmcuScene* s, const LmcuBuildOptions* opts, LmcuBuildStats*
         stats->num_triangles = nt;
         stats->num_wide_nodes = (int64_t)s->nodes.n;
         stats->node_bytes = (int64_t)(s->nodes.n * sizeof(WideNode));
-        stats->triangle_bytes = (int64_t)nt * (int64_t)(s->fp32 ? sizeof(TriF32) : sizeof(TriF64));
+        stats->triangle_bytes = s->two_level ? (int64_t)(s->tobj.n * sizeof(TriObj) + s->inst.n * sizeof(InstDev))
+                                             : (int64_t)nt * (int64_t)(s->fp32 ? sizeof(TriF32) : sizeof(TriF64));
         stats->triangles_fp32 = s->fp32 ? 1 : 0;
-        // expected wide-node visits + triangle tests of a random line through the scene box
+        stats->two_level = s->two_level ? 1 : 0;
+        // expected wide-node visits + triangle tests of a random line through the scene box (one-level trees only)
         stats->sah_cost = h_cost[2] > 0 ? (h_cost[0] + h_cost[1]) / h_cost[2] : 0.0;
     }
     return LMCU_OK;
@@ -1378,6 +1553,7 @@ static int desc_digest(LmcuScene* s, uint64_t* out) {
 int lmcu_accel_save_size(LmcuScene* s, int64_t* bytes) {
     if (!s || !bytes) return fail(LMCU_ERR_INVALID_ARGUMENT, "null argument");
     if (!s->built) return fail(LMCU_ERR_INVALID_ARGUMENT, "accel not built");
+    if (s->two_level) return fail(LMCU_ERR_UNSUPPORTED, "a two-level accel is rebuilt from the scene, not serialised (LmcuBuildOptions::two_level = -1 builds the flattened tree)");
     AccelBlobHeader h{};
     h.fp32 = s->fp32; h.nt = s->nt; h.num_nodes = (uint32_t)s->nodes.n; h.num_prims = (uint32_t)s->num_prims; h.has_uv = s->uv.p ? 1 : 0;
     *bytes = (int64_t)(sizeof(AccelBlobHeader) + blob_payload(h));
@@ -1508,6 +1684,7 @@ int lmcu_accel_load(LmcuScene* s, const void* buffer, int64_t bytes) {
     CU(s->nodes.alloc(h.num_nodes));
     CU(push(s->nodes.p, (size_t)h.num_nodes * sizeof(WideNode)));
     s->fp32 = h.fp32 != 0;
+    s->two_level = false; s->tobj.release(); s->inst.release();
     s->t32.release(); s->t64.release();
     if (s->fp32) { CU(s->t32.alloc(h.nt)); CU(push(s->t32.p, (size_t)h.nt * sizeof(TriF32))); }
     else { CU(s->t64.alloc(h.nt)); CU(push(s->t64.p, (size_t)h.nt * sizeof(TriF64))); }
@@ -1529,10 +1706,13 @@ int lmcu_accel_load(LmcuScene* s, const void* buffer, int64_t bytes) {
 }
 
 // -- intersect ------------------------------------------------------------------------------------------
-// Picks the kernel instantiation for (triangle record, counters, triangles per iteration).
-#define LMCU_DISPATCH(KERNEL, FP32, COUNT, GRID, BLOCK, STREAM, ...)                                             \
+// Picks the kernel instantiation for (triangle record: LmcuScene::tri_kind(), counters).
+#define LMCU_DISPATCH(KERNEL, KIND, COUNT, GRID, BLOCK, STREAM, ...)                                             \
     do {                                                                                                         \
-        if (FP32) {                                                                                              \
+        if ((KIND) == 2) {                                                                                       \
+            if (COUNT) KERNEL<TriObj, true><<<GRID, BLOCK, 0, STREAM>>>(__VA_ARGS__);                            \
+            else KERNEL<TriObj, false><<<GRID, BLOCK, 0, STREAM>>>(__VA_ARGS__);                                 \
+        } else if ((KIND) == 1) {                                                                                \
             if (COUNT) KERNEL<TriF32, true><<<GRID, BLOCK, 0, STREAM>>>(__VA_ARGS__);                            \
             else KERNEL<TriF32, false><<<GRID, BLOCK, 0, STREAM>>>(__VA_ARGS__);                                 \
         } else {                                                                                                 \
@@ -1560,7 +1740,7 @@ static int launch_intersect(LmcuScene* s, const LmcuRay* d_rays, int64_t n, Lmcu
         const uint32_t m = (uint32_t)std::min<int64_t>(kChunk, n - off);
         unsigned long long* cur = s->cursor.p + 8 + (s->cursor_next.fetch_add(1) % LmcuScene::kCursorRing);
         CU(cudaMemsetAsync(cur, 0, sizeof(unsigned long long), st));
-        if (s->pool_mode && st == s->stream) {      // one arena per scene: only for launches ordered by the scene's stream
+        if (s->pool_on() && st == s->stream) {      // one arena per scene: only for launches ordered by the scene's stream
             const unsigned pblocks = (unsigned)std::min<int64_t>((m + 2 * LMCU_TRAV_BLOCK - 1) / (2 * LMCU_TRAV_BLOCK), (int64_t)s->num_sms * 5);
             const size_t need = (size_t)s->num_sms * 5 * (LMCU_TRAV_BLOCK / 32) * kStackSize * 32 * kPoolK;
             if (s->batch_arena.n != need) CU(s->batch_arena.alloc(need));
@@ -1570,8 +1750,8 @@ static int launch_intersect(LmcuScene* s, const LmcuRay* d_rays, int64_t n, Lmcu
             CU(cudaGetLastError());
             continue;
         }
-        const unsigned blocks = (unsigned)std::min<int64_t>((m + LMCU_TRAV_BLOCK - 1) / LMCU_TRAV_BLOCK, (int64_t)s->num_sms * s->ctas_per_sm);
-        LMCU_DISPATCH(k_intersect_q, s->fp32, count, blocks, LMCU_TRAV_BLOCK, st, d, d_rays + off, m, d_hits + off,
+        const unsigned blocks = (unsigned)std::min<int64_t>((m + LMCU_TRAV_BLOCK - 1) / LMCU_TRAV_BLOCK, (int64_t)s->num_sms * s->trav_ctas());
+        LMCU_DISPATCH(k_intersect_q, s->tri_kind(), count, blocks, LMCU_TRAV_BLOCK, st, d, d_rays + off, m, d_hits + off,
                       (uint32_t*)cur, s->cursor.p + 1, s->flags.p);
         CU(cudaGetLastError());
     }
@@ -1671,7 +1851,8 @@ int lmcu_accel_intersect1(LmcuScene* s, const LmcuRay* ray, LmcuHit* hit) {
     *slot->h_ray = *ray;
     const DevScene d = s->dev();
     const unsigned long long ticket = ++slot->ticket;
-    if (s->fp32) k_intersect_one<TriF32><<<1, 32, 0, slot->st>>>(d, slot->d_ray, slot->d_hit, slot->d_done, ticket);
+    if (s->two_level) k_intersect_one<TriObj><<<1, 32, 0, slot->st>>>(d, slot->d_ray, slot->d_hit, slot->d_done, ticket);
+    else if (s->fp32) k_intersect_one<TriF32><<<1, 32, 0, slot->st>>>(d, slot->d_ray, slot->d_hit, slot->d_done, ticket);
     else k_intersect_one<TriF64><<<1, 32, 0, slot->st>>>(d, slot->d_ray, slot->d_hit, slot->d_done, ticket);
     CU(cudaGetLastError());
     // Spin on the ticket the kernel writes into the pinned slot (a stream synchronise costs several microseconds of driver
@@ -1870,7 +2051,8 @@ int lmcu_render_raycast(LmcuScene* s, const LmcuRenderParams* p, float* film_rgb
     const size_t n = (size_t)p->width * p->height;
     const unsigned blocks = (unsigned)std::min<size_t>((n + 127) / 128, (size_t)s->num_sms * 12);
     const DevScene d = s->dev();
-    if (s->fp32) k_raycast<TriF32><<<blocks, 128, 0, st>>>(d, rp, s->film.p, s->cursor.p);
+    if (s->two_level) k_raycast<TriObj><<<blocks, 128, 0, st>>>(d, rp, s->film.p, s->cursor.p);
+    else if (s->fp32) k_raycast<TriF32><<<blocks, 128, 0, st>>>(d, rp, s->film.p, s->cursor.p);
     else k_raycast<TriF64><<<blocks, 128, 0, st>>>(d, rp, s->film.p, s->cursor.p);
     CU(cudaGetLastError());
     CU(cudaEventRecord(s->ev1, st));
@@ -1905,7 +2087,8 @@ int lmcu_render_ao(LmcuScene* s, const LmcuRenderParams* p, float* film_rgb, Lmc
     const unsigned blocks = (unsigned)std::min<size_t>((n + 127) / 128, (size_t)s->num_sms * 12);
     const DevScene d = s->dev();
     const double dist = p->ao_distance > 0 ? p->ao_distance : 0.2;
-    if (s->fp32) k_ao<TriF32><<<blocks, 128, 0, st>>>(d, p->width, p->height, p->spp, (unsigned long long)p->sample_offset, p->seed, dist, s->film.p, s->cursor.p, s->cursor.p + 3);
+    if (s->two_level) k_ao<TriObj><<<blocks, 128, 0, st>>>(d, p->width, p->height, p->spp, (unsigned long long)p->sample_offset, p->seed, dist, s->film.p, s->cursor.p, s->cursor.p + 3);
+    else if (s->fp32) k_ao<TriF32><<<blocks, 128, 0, st>>>(d, p->width, p->height, p->spp, (unsigned long long)p->sample_offset, p->seed, dist, s->film.p, s->cursor.p, s->cursor.p + 3);
     else k_ao<TriF64><<<blocks, 128, 0, st>>>(d, p->width, p->height, p->spp, (unsigned long long)p->sample_offset, p->seed, dist, s->film.p, s->cursor.p, s->cursor.p + 3);
     CU(cudaGetLastError());
     CU(cudaEventRecord(s->ev1, st));
@@ -1973,7 +2156,7 @@ static int pt_pass(LmcuScene* s, const PtParams& pp_all, bool count, PtAccum& ac
     // pending, so a kernel's drain tail is filled by the other loop's next kernel (grids cut to 1/K measured worse).
     const int K = s->waves;
     const DevScene d = s->dev();
-    const unsigned q_blocks = (unsigned)(s->num_sms * s->ctas_per_sm);
+    const unsigned q_blocks = (unsigned)(s->num_sms * s->trav_ctas());
     const unsigned shade_blocks = (unsigned)(s->num_sms * s->shade_ctas_per_sm), gen_blocks = (unsigned)s->num_sms * 4;
     const int kGroup = 4;                       // iterations between host checks
     const size_t pool_smem_pt = pool_bytes_per_warp<ExtendIO, kPoolK>() * (LMCU_TRAV_BLOCK / 32);
@@ -2020,8 +2203,8 @@ static int pt_pass(LmcuScene* s, const PtParams& pp_all, bool count, PtAccum& ac
             if (pp[w].light_tracing) k_lt_generate<<<gen_blocks, 256, 0, st>>>(d, pp[w], q[w][cur], v.ctr.p);
             else k_pt_generate<<<gen_blocks, 256, 0, st>>>(d, pp[w], q[w][cur], sq[w], v.ctr.p);
             cudaEventRecord(ev[0], st);
-            if (s->pool_mode) LMCU_DISPATCH_SMEM(k_pt_extend_p, s->fp32, count, q_blocks, LMCU_TRAV_BLOCK, pool_smem_pt, st, d, q[w][cur], v.hits.p, v.ctr.p, cur, v.arena.p);
-            else LMCU_DISPATCH(k_pt_extend_q, s->fp32, count, q_blocks, LMCU_TRAV_BLOCK, st, d, q[w][cur], v.hits.p, v.ctr.p, cur);
+            if (s->pool_on()) LMCU_DISPATCH_SMEM(k_pt_extend_p, s->fp32, count, q_blocks, LMCU_TRAV_BLOCK, pool_smem_pt, st, d, q[w][cur], v.hits.p, v.ctr.p, cur, v.arena.p);
+            else LMCU_DISPATCH(k_pt_extend_q, s->tri_kind(), count, q_blocks, LMCU_TRAV_BLOCK, st, d, q[w][cur], v.hits.p, v.ctr.p, cur);
             cudaEventRecord(ev[1], st);
             if (pp[w].light_tracing) {
                 if (s->composite) k_lt_shade<true><<<shade_blocks, LMCU_SHADE_BLOCK, 0, st>>>(d, pp[w], q[w][cur], q[w][cur ^ 1], sq[w], v.hits.p, v.ctr.p, cur);
@@ -2030,8 +2213,8 @@ static int pt_pass(LmcuScene* s, const PtParams& pp_all, bool count, PtAccum& ac
             else if (s->composite) k_pt_shade<true><<<shade_blocks, LMCU_SHADE_BLOCK, 0, st>>>(d, pp[w], q[w][cur], q[w][cur ^ 1], sq[w], v.hits.p, s->film.p, v.ctr.p, cur);
             else k_pt_shade<false><<<shade_blocks, LMCU_SHADE_BLOCK, 0, st>>>(d, pp[w], q[w][cur], q[w][cur ^ 1], sq[w], v.hits.p, s->film.p, v.ctr.p, cur);
             cudaEventRecord(ev[2], st);
-            if (s->pool_mode) LMCU_DISPATCH_SMEM(k_pt_shadow_p, s->fp32, count, q_blocks, LMCU_TRAV_BLOCK, pool_smem_pt, st, d, sq[w], s->film.p, v.ctr.p, v.arena.p);
-            else LMCU_DISPATCH(k_pt_shadow_q, s->fp32, count, q_blocks, LMCU_TRAV_BLOCK, st, d, sq[w], s->film.p, v.ctr.p);
+            if (s->pool_on()) LMCU_DISPATCH_SMEM(k_pt_shadow_p, s->fp32, count, q_blocks, LMCU_TRAV_BLOCK, pool_smem_pt, st, d, sq[w], s->film.p, v.ctr.p, v.arena.p);
+            else LMCU_DISPATCH(k_pt_shadow_q, s->tri_kind(), count, q_blocks, LMCU_TRAV_BLOCK, st, d, sq[w], s->film.p, v.ctr.p);
             cudaEventRecord(ev[3], st);
             v.cur ^= 1;
             acc.launches += 5;
@@ -2295,7 +2478,7 @@ int lmcu_render_bdpt(LmcuScene* s, const LmcuRenderParams* p, float* film_rgb, L
     store.nverts = B.nverts.p; store.eye_pixel = B.eye_pixel.p; store.cap = cap; store.mv = p->max_verts;
     ShadowQueue sq;
     sq.ray_o = B.sq[0].p; sq.ray_d = B.sq[1].p; sq.contrib = B.sq[2].p;
-    const unsigned q_blocks = (unsigned)(s->num_sms * s->ctas_per_sm);
+    const unsigned q_blocks = (unsigned)(s->num_sms * s->trav_ctas());
     auto run_pass = [&](int64_t count) -> int {
         for (int64_t done = 0; done < count;) {
             const int64_t n = std::min<int64_t>(cap, count - done);
@@ -2310,7 +2493,7 @@ int lmcu_render_bdpt(LmcuScene* s, const LmcuRenderParams* p, float* film_rgb, L
             for (int k = 1; k < p->max_verts; k++) {
                 PathQueue q{};
                 q.ray_o = B.q_o[cur].p; q.ray_d = B.q_d[cur].p;
-                LMCU_DISPATCH(k_pt_extend_q, s->fp32, false, q_blocks, LMCU_TRAV_BLOCK, st, d, q, B.hits.p, B.ctr.p, cur);
+                LMCU_DISPATCH(k_pt_extend_q, s->tri_kind(), false, q_blocks, LMCU_TRAV_BLOCK, st, d, q, B.hits.p, B.ctr.p, cur);
                 if (s->composite) k_bdpt_vertex<true><<<vtx_blocks, 128, 0, st>>>(d, pp, store, k, B.q_d[cur].p, B.q_id[cur].p, B.hits.p, B.q_o[cur ^ 1].p, B.q_d[cur ^ 1].p, B.q_id[cur ^ 1].p, B.ctr.p, cur);
                 else k_bdpt_vertex<false><<<vtx_blocks, 128, 0, st>>>(d, pp, store, k, B.q_d[cur].p, B.q_id[cur].p, B.hits.p, B.q_o[cur ^ 1].p, B.q_d[cur ^ 1].p, B.q_id[cur ^ 1].p, B.ctr.p, cur);
                 k_bdpt_flip<<<1, 1, 0, st>>>(B.ctr.p, cur);
@@ -2323,7 +2506,7 @@ int lmcu_render_bdpt(LmcuScene* s, const LmcuRenderParams* p, float* film_rgb, L
             const dim3 cgrid((unsigned)std::min<int64_t>((n + 127) / 128, (int64_t)s->num_sms * 2), (unsigned)pairs.size());
             if (s->composite) k_bdpt_connect<true><<<cgrid, 128, 0, st>>>(d, pp, store, B.pairs.p, B.pair_list.p, B.pair_count.p, sq, s->film.p, B.ctr.p);
             else k_bdpt_connect<false><<<cgrid, 128, 0, st>>>(d, pp, store, B.pairs.p, B.pair_list.p, B.pair_count.p, sq, s->film.p, B.ctr.p);
-            LMCU_DISPATCH(k_pt_shadow_q, s->fp32, false, q_blocks, LMCU_TRAV_BLOCK, st, d, sq, s->film.p, B.ctr.p);
+            LMCU_DISPATCH(k_pt_shadow_q, s->tri_kind(), false, q_blocks, LMCU_TRAV_BLOCK, st, d, sq, s->film.p, B.ctr.p);
             CU(cudaGetLastError());
             k_film_fold<<<fold_blocks, 256, 0, st>>>(s->film.p, s->film_acc.p, s->film.n);
             launches += 7;

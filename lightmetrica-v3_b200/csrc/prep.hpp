@@ -263,4 +263,41 @@ inline int prepare_scene(const LmcuSceneDesc* d, PreparedScene& o, std::string& 
     return LMCU_OK;
 }
 
+// -- two-level layout: host-side pieces shared by lmcu.cu and tests/hostsim ------------------------------------------------
+// The instance record of primitive `prim` whose mesh tree has its root at node `root`.  False when the global transform
+// is not an invertible affine map (then the scene is built flattened).
+inline bool make_inst(const PrimDev& pr, uint32_t prim, uint32_t root, InstDev& o) {
+    const double* M = pr.M;
+    if (M[3] != 0.0 || M[7] != 0.0 || M[11] != 0.0 || M[15] != 1.0) return false;
+    if (!(pr.J > 0.0) || !std::isfinite(pr.J)) return false;
+    for (int c = 0; c < 4; c++) for (int r = 0; r < 3; r++) o.M[3 * c + r] = M[4 * c + r];
+    // inverse of the 3x3 part = transpose of the normal matrix (NM = inverse-transpose, column-major)
+    for (int c = 0; c < 3; c++) for (int r = 0; r < 3; r++) {
+        o.Minv[3 * c + r] = pr.NM[3 * r + c];
+        if (!std::isfinite(o.Minv[3 * c + r])) return false;
+    }
+    for (int r = 0; r < 3; r++) o.Minv[9 + r] = -(o.Minv[r] * M[12] + o.Minv[3 + r] * M[13] + o.Minv[6 + r] * M[14]);
+    o.root = root; o.tri_offset = pr.tri_offset; o.prim = prim; o.pad_ = 0;
+    return true;
+}
+
+// LmcuBuildOptions::two_level resolved against the scene.  The flattened tree is the faster one to walk (C4: 477 against 347
+// Mpaths/s — the two-level walk pays an object-space ray per instance entered and a vertex transform per leaf test), so the
+// automatic choice keeps it while it fits: two-level only for an instanced scene (flattened triangles >= 4 x the unique ones)
+// whose flattened build (~475 bytes per triangle at its peak: 155 resident + the builder's temporaries) would take more than
+// half of `budget_bytes` (the device's free memory).
+inline bool want_two_level(int option, const std::vector<PrimDev>& prims, const std::vector<uint32_t>& face_offset, uint32_t nt,
+                           double budget_bytes = 0.0) {
+    if (option < 0) return false;
+    std::vector<char> used(face_offset.size(), 0);
+    uint64_t unique = 0;
+    InstDev tmp;
+    for (size_t i = 0; i < prims.size(); i++) {
+        if (!make_inst(prims[i], (uint32_t)i, 0u, tmp)) return false;
+        if (!used[prims[i].mesh]) { used[prims[i].mesh] = 1; unique += prims[i].num_faces; }
+    }
+    if (option > 0) return true;
+    return (uint64_t)nt >= 4 * unique && budget_bytes > 0.0 && 475.0 * (double)nt > 0.5 * budget_bytes;
+}
+
 }  // namespace lmcu

@@ -39,7 +39,8 @@ __device__ __forceinline__ double rcp_newton(double d) {
 template <bool ANY, bool COUNT, typename TriT, typename IO>
 __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, const TriT* __restrict__ tris,
                                             uint32_t n, uint32_t* cursor, const IO& io, uint32_t* overflow,
-                                            TraverseCounters* ctr, int fetch_threshold) {
+                                            TraverseCounters* ctr, int fetch_threshold, const InstDev* __restrict__ inst = nullptr) {
+    constexpr bool TWO = TriT::kTwoLevel;   // two-level tree (bvh.cuh): `inst` = the top level's leaf-ordered instance table
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t lt_mask = (1u << lane) - 1u;
     const uint4* nodes4 = reinterpret_cast<const uint4*>(nodes);
@@ -57,6 +58,7 @@ __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, 
     int32_t htri = -1;
     uint2 ngroup = make_uint2(0u, 0u), tgroup = make_uint2(0u, 0u);
     int sp = 0;
+    uint32_t cinst = kNoInst;     // TWO: the instance whose tree the lane is in (f is then the ray in its object space)
 
     while (true) {
         // ---- results of the rays that finished since the last visit here.  A lane keeps its finished ray's (t, u, v, |det|,
@@ -84,6 +86,7 @@ __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, 
                         ngroup = make_uint2(0u, 0x80000000u);   // the root occupies virtual slot 7 of group 0
                         tgroup = make_uint2(0u, 0u);
                         sp = 0;
+                        cinst = kNoInst;
                         active = true;
                     }
                 }
@@ -96,10 +99,42 @@ __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, 
         // ---- traverse until enough lanes are idle to make a re-fetch worth its latency ------------------
         while (true) {
             if (active) {
+                // ---- TWO: a lane in the top level that holds leaf items enters the first of them: what is left of the node is
+                // parked, the ray goes to the instance's object space, and the node step below starts on the mesh tree's root
+                // in this same iteration
+#define LMCU_ENTER_INSTANCE()                                                                                   \
+                {                                                                                               \
+                    const int ei = bfind(tgroup.y);                                                             \
+                    tgroup.y &= ~(1u << ei);                                                                    \
+                    const uint32_t in = tgroup.x + (uint32_t)ei;                                                \
+                    if (sp + 3 > kStackSize) { atomicExch(overflow, 1u); sp = kStackSize - 3; }                 \
+                    if (ngroup.y > 0x00ffffffu) stack[sp++] = ngroup;                                           \
+                    if (tgroup.y != 0u) stack[sp++] = tgroup;                                                   \
+                    stack[sp++] = make_uint2(0u, 0u);                                                           \
+                    cinst = in;                                                                                 \
+                    f = make_rayf_obj(r, inst[in].Minv);                                                        \
+                    ngroup = make_uint2(inst[in].root, 0x80000000u);                                            \
+                    tgroup = make_uint2(0u, 0u);                                                                \
+                }
+                if constexpr (TWO) {
+                    if (cinst == kNoInst && tgroup.y != 0u) LMCU_ENTER_INSTANCE()
+                }
                 if (tgroup.y == 0u) {
-                    if (ngroup.y <= 0x00ffffffu) {
-                        if (sp > 0) ngroup = stack[--sp];
+                    if (ngroup.y <= 0x00ffffffu && sp > 0) {
+                        uint2 e = stack[--sp];
+                        if constexpr (TWO) {
+                            if (e.y == 0u) {                                   // the marker: back in the top level, world-space ray
+                                cinst = kNoInst;
+                                f = make_rayf(r);
+                                if (sp > 0) e = stack[--sp];
+                            }
+                            if (e.y > 0x00ffffffu) ngroup = e;
+                            else if (e.y != 0u) { tgroup = e; LMCU_ENTER_INSTANCE() }      // more instances of a top-level leaf
+                        } else {
+                            ngroup = e;
+                        }
                     }
+#undef LMCU_ENTER_INSTANCE
                     if (ngroup.y > 0x00ffffffu) {
                         // ---- one wide-node step
                         const uint32_t hits = ngroup.y;
@@ -129,12 +164,19 @@ __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, 
                     }
                 }
                 // ---- leaf work: FP64 Möller–Trumbore, reference operation order (accel_sahbvh.cpp:58-75)
-                if (active && tgroup.y != 0u) {
+                if (active && tgroup.y != 0u && (!TWO || cinst != kNoInst)) {
                     const int ti = bfind(tgroup.y);
                     tgroup.y &= ~(1u << ti);
                     const uint32_t tri = tgroup.x + (uint32_t)ti;
                     D3 p1, p2, p3;
+                    int32_t id = (int32_t)tri;
                     load_tri(tris, tri, p1, p2, p3);
+                    if constexpr (TWO) {
+                        // the vertices in world space, by the flattened build's operations: the test below sees the same operands
+                        const double* M = inst[cinst].M;
+                        p1 = transform_point34(M, p1); p2 = transform_point34(M, p2); p3 = transform_point34(M, p3);
+                        id = (int32_t)(inst[cinst].tri_offset + (uint32_t)tris[tri].face);
+                    }
                     if (COUNT) ctr->tris++;
                     const D3 e1 = dsub3(p2, p1), e2 = dsub3(p3, p1);
                     const D3 p = dcross(r.d, e2);
@@ -150,7 +192,7 @@ __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, 
                         // run at the 3-4 lanes whose triangle passed the barycentric test.
                         const double t = IO::kExactT ? divrn(ddot(e2, q), d) : mulrn(ddot(e2, q), rcp_newton(d));
                         if (!(t < r.tmin || ht < t)) {          // inclusive bounds; a later equal-t triangle wins
-                            ht = t; hu = u; hv = v; had = ad; htri = (int32_t)tri;
+                            ht = t; hu = u; hv = v; had = ad; htri = id;
                             tmax_up = f32_up(t);
                             if (ANY) {
                                 pending = true;

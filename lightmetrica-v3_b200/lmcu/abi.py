@@ -94,13 +94,13 @@ class LmcuRenderStats(C.Structure):
 
 
 class LmcuBuildOptions(C.Structure):
-    _fields_ = [("max_leaf_tris", C.c_int32), ("reserved_", C.c_int32 * 7)]
+    _fields_ = [("max_leaf_tris", C.c_int32), ("two_level", C.c_int32), ("reserved_", C.c_int32 * 6)]
 
 
 class LmcuBuildStats(C.Structure):
     _fields_ = [("elapsed", C.c_double), ("num_triangles", C.c_int64), ("num_wide_nodes", C.c_int64),
                 ("node_bytes", C.c_int64), ("triangle_bytes", C.c_int64),
-                ("triangles_fp32", C.c_int32), ("pad_", C.c_int32), ("sah_cost", C.c_double)]
+                ("triangles_fp32", C.c_int32), ("two_level", C.c_int32), ("sah_cost", C.c_double)]
 
 
 def render_params(width, height, spp=1, max_verts=20, seed=42, sampling_mode=SAMPLING_MIS,

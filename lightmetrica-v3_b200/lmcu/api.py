@@ -85,9 +85,10 @@ def enable_peer_access(device, peer_device):
 class Scene:
     """accel::cuda_bvh + renderer::{raycast,ao,pt}_cuda over one uploaded scene on one GPU."""
 
-    def __init__(self, builder=None, device=0, max_leaf_tris=0, accel_blob=None):
+    def __init__(self, builder=None, device=0, max_leaf_tris=0, accel_blob=None, two_level=0):
         """builder: scene description (None = accel-only scene restored from `accel_blob`).  accel_blob: bytes written by
-        save_accel(); when given, the BVH is loaded instead of built (Component::save / load of an Accel)."""
+        save_accel(); when given, the BVH is loaded instead of built (Component::save / load of an Accel).  two_level: 1 = one
+        tree per mesh + one over the primitives (instanced scenes), -1 = one tree over the flattened scene, 0 = automatic."""
         self._builder = builder
         self._h = C.c_void_p()
         _check(lib().lmcu_scene_create(int(device), C.byref(self._h)))
@@ -102,6 +103,7 @@ class Scene:
         else:
             opts = abi.LmcuBuildOptions()
             opts.max_leaf_tris = max_leaf_tris
+            opts.two_level = two_level
             _check(lib().lmcu_accel_build(self._h, C.byref(opts), C.byref(self.build_stats)))
         self.last_stats = None
 

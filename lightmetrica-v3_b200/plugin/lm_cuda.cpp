@@ -555,19 +555,22 @@ struct DeviceScene {
     uint64_t sig = 0;
     int device = 0;
     bool shading = false;
+    int layout = 0;                        // LmcuBuildOptions::two_level the scene was built with
     std::map<int, Transform> transforms;   // SceneNode::index -> Transform for Accel::Hit
     std::mutex render_mu;                  // one render at a time per device scene (film and path pools live in it)
     ~DeviceScene() { if (h) lmcu_scene_destroy(h); }
     DeviceScene() = default;
     DeviceScene(const DeviceScene&) = delete;
-    void upload(SceneExport& ex, int dev) {
+    void upload(SceneExport& ex, int dev, int two_level) {
         ex.gather_triangles();
         if (h) { lmcu_scene_destroy(h); h = nullptr; }
-        device = dev; sig = ex.sig; shading = ex.shading_;
+        device = dev; sig = ex.sig; shading = ex.shading_; layout = two_level;
         transforms = ex.transforms;
         check(lmcu_scene_create(device, &h));
         check(lmcu_scene_upload(h, &ex.desc));
-        check(lmcu_accel_build(h, nullptr, nullptr));
+        LmcuBuildOptions opts{};
+        opts.two_level = two_level;
+        check(lmcu_accel_build(h, &opts, nullptr));
     }
 };
 
@@ -576,11 +579,11 @@ struct SceneCache {
     std::list<std::shared_ptr<DeviceScene>> entries;      // most recently used first
     static constexpr size_t kMax = 4;
     long long hits = 0, misses = 0;
-    std::shared_ptr<DeviceScene> acquire(SceneExport& ex, int device, bool use_cache) {
+    std::shared_ptr<DeviceScene> acquire(SceneExport& ex, int device, bool use_cache, int two_level = 0) {
         if (use_cache) {
             std::unique_lock<std::mutex> lk(mu);
             for (auto it = entries.begin(); it != entries.end(); ++it) {
-                if ((*it)->sig == ex.sig && (*it)->device == device && (*it)->shading == ex.shading_) {
+                if ((*it)->sig == ex.sig && (*it)->device == device && (*it)->shading == ex.shading_ && (*it)->layout == two_level) {
                     auto hit = *it;
                     hits++;
                     entries.erase(it);
@@ -590,7 +593,7 @@ struct SceneCache {
             }
         }
         auto fresh = std::make_shared<DeviceScene>();
-        fresh->upload(ex, device);
+        fresh->upload(ex, device, two_level);
         if (use_cache) {
             std::unique_lock<std::mutex> lk(mu);
             misses++;
@@ -617,6 +620,9 @@ SceneCache& g_scene_cache = *new SceneCache;
 
    :param int device: CUDA device index. Default: 0.
    :param bool cache: Reuse the device scene of an earlier build of the same scene content. Default: true.
+   :param int two_level: 1: instancing-aware layout, one tree per mesh + one over the primitives (as ``accel::embreeinstanced``;
+      memory and build time follow the unique triangles, same hits, slower walk); -1: one tree over the flattened scene;
+      0 (default): flattened while it fits the device. A two-level accel cannot be saved.
 
    ``intersect()`` keeps the scalar contract of :cpp:func:`lm::Accel::intersect` (one ray per call,
    thread-safe and lock-free: every calling thread owns a pinned ray/hit slot and a CUDA stream) for callers
@@ -628,6 +634,7 @@ class Accel_CudaBVH final : public Accel {
 private:
     int device_ = 0;
     bool cache_ = true;
+    int two_level_ = 0;
     std::shared_ptr<DeviceScene> dev_;
     mutable std::mutex mu_;
 
@@ -635,6 +642,7 @@ public:
     virtual void construct(const Json& prop) override {
         device_ = json::value<int>(prop, "device", 0);
         cache_ = json::value<bool>(prop, "cache", true);
+        two_level_ = json::value<int>(prop, "two_level", 0);
     }
 
     // Component::save / load (include/lm/component.h:210-236), the counterpart of accel::sahbvh archiving nodes_, trs_,
@@ -675,7 +683,7 @@ public:
         SceneExport ex;
         ex.gather_description(scene, false);
         LM_INFO("Building");
-        dev_ = g_scene_cache.acquire(ex, device_, cache_);
+        dev_ = g_scene_cache.acquire(ex, device_, cache_, two_level_);
     }
 
     // Batched closest hit: n rays in, n hits out, one kernel launch.  Hit::primitive is the scene node
@@ -828,6 +836,7 @@ protected:
     Film* film_;
     mutable int device_ = 0;
     bool cache_ = true;
+    int two_level_ = 0;                                        // "two_level": LmcuBuildOptions::two_level of the device scene
     mutable std::shared_ptr<DeviceScene> dev_;
 
 public:
@@ -838,13 +847,14 @@ public:
 
 protected:
     // weak references travel as locators and are re-pointed after the whole tree is loaded (include/lm/serial.h:238-300)
-    template <typename Archive> void serialize_base(Archive& ar) { ar(scene_, film_, device_, cache_); }
+    template <typename Archive> void serialize_base(Archive& ar) { ar(scene_, film_, device_, cache_, two_level_); }
 
     void construct_base(const Json& prop) {
         scene_ = json::comp_ref<Scene>(prop, "scene");
         film_ = json::comp_ref<Film>(prop, "output");
         device_ = json::value<int>(prop, "device", 0);
         cache_ = json::value<bool>(prop, "cache", true);      // false: export, upload and build again on every render()
+        two_level_ = json::value<int>(prop, "two_level", 0);   // 1: one tree per mesh + one over the primitives (instanced scenes)
     }
 
     // The device scene for the CURRENT content of scene_: found in the cache when nothing that the export reads has
@@ -852,7 +862,7 @@ protected:
     void upload() const {
         SceneExport ex;
         ex.gather_description(*scene_, true);
-        dev_ = g_scene_cache.acquire(ex, device_, cache_);
+        dev_ = g_scene_cache.acquire(ex, device_, cache_, two_level_);
     }
 
     // Host destination of the device film: film::cuda's own pixel buffer (one copy), else a staging vector
@@ -1095,7 +1105,7 @@ public:
             for (int g = 0; g < G; g++) {
                 threads.emplace_back([&, g] {
                     try {
-                        devs[g] = g_scene_cache.acquire(ex, devices_[g], cache_);
+                        devs[g] = g_scene_cache.acquire(ex, devices_[g], cache_, two_level_);
                         locks[g] = std::unique_lock<std::mutex>(devs[g]->render_mu);
                         LmcuRenderParams q = p;
                         q.rescale = 0;

@@ -29,11 +29,18 @@ struct SimScene {
     std::vector<TriF64> t64;
     std::vector<TriShade> shade;
     std::vector<TriUV> uv;
+    std::vector<TriObj> tobj;            // two-level layout
+    std::vector<InstDev> inst;
+    bool two_level = false;
     bool fp32 = false;
     float bounds[6] = { 0, 0, 0, 0, 0, 0 };
     DevScene dev() const {
         DevScene d{};
-        d.nodes = nodes.data(); d.t32 = fp32 ? t32.data() : nullptr; d.t64 = fp32 ? nullptr : t64.data();
+        d.nodes = nodes.data(); d.t32 = fp32 ? t32.data() : nullptr; d.t64 = fp32 || two_level ? nullptr : t64.data();
+        if (two_level) {
+            d.tobj = tobj.data(); d.inst = inst.data(); d.mesh_p = mesh_p.data(); d.mesh_n = mesh_n.data();
+            d.mesh_t = ps.mesh_t.empty() ? nullptr : ps.mesh_t.data();
+        }
         d.shade = shade.data(); d.prims = ps.prims.data(); d.mats = ps.mats.data(); d.lights = ps.lights.data();
         d.emit = ps.emit.data(); d.cdf = ps.cdf.data(); d.env_tex = ps.env_tex.data();
         d.num_prims = (int)ps.prims.size(); d.num_lights = (int)ps.lights.size(); d.env_light = ps.env_light;
@@ -59,12 +66,12 @@ static int intersect_t(const SimScene& s, const LmcuRay* rays, long long n, Lmcu
         r.tmin = rays[i].tmin; r.tmax = rays[i].tmax;
         HitD h; h.t = r.tmax; h.u = h.v = 0; h.tri = -1;
         TraverseCounters tc; tc.nodes = tc.tris = 0;
-        if (!traverse<false, true, TriT>(d.nodes, scene_tris<TriT>(d), r, h, stack, &tc)) overflow = 1;
+        if (!traverse<false, true, TriT>(d.nodes, scene_tris<TriT>(d), r, h, stack, &tc, d.inst)) overflow = 1;
         cn += tc.nodes; ct += tc.tris;
         int32_t prim = -1, face = -1;
         if (h.tri >= 0) {
-            F3 p1, p2, p3; int32_t pi;
-            tri_fetch(d, (uint32_t)h.tri, p1, p2, p3, pi, face);
+            int32_t pi;
+            tri_ids(d, (uint32_t)h.tri, pi, face);
             prim = d.prims[pi].node_index;
         }
         hits[i] = LmcuHit{ h.t, h.u, h.v, prim, face };
@@ -146,34 +153,14 @@ uint32_t sah_build(SahCtx& c, uint32_t b, uint32_t e) {
 }
 }
 
-extern "C" {
 
-const char* hostsim_last_error() { return g_err.c_str(); }
-
-int hostsim_scene_create(const LmcuSceneDesc* d, int max_leaf, void** out, long long* num_nodes) {
-    auto* s = new SimScene;
-    const int rc = prepare_scene(d, s->ps, g_err);
-    if (rc) { delete s; return rc; }
-    const uint32_t nt = s->ps.nt;
-    const size_t total_faces = s->ps.face_offset.back();
-    s->mesh_p.assign(total_faces * 9, 0.0);
-    s->mesh_n.assign(total_faces * 9, 0.0);
-    for (int i = 0; i < d->num_meshes; i++) {
-        const size_t cnt = (size_t)d->meshes[i].num_faces * 9;
-        memcpy(s->mesh_p.data() + (size_t)s->ps.face_offset[i] * 9, d->meshes[i].p, cnt * sizeof(double));
-        if (d->meshes[i].n) memcpy(s->mesh_n.data() + (size_t)s->ps.face_offset[i] * 9, d->meshes[i].n, cnt * sizeof(double));
-    }
-    // k_flatten
-    std::vector<double> wp((size_t)nt * 9), centre((size_t)nt * 3);
-    std::vector<float> tri_lo((size_t)nt * 3), tri_hi((size_t)nt * 3);
-    bool exact = true;
+// morton -> sort -> hierarchy -> fit -> collapse over n items with float bounds lo / hi and centres (the middle of
+// lmcu_accel_build, shared by the flattened tree, the per-mesh trees and the tree over the instances)
+static bool build_tree_host(uint32_t nt, const std::vector<float>& tri_lo, const std::vector<float>& tri_hi, const std::vector<double>& centre,
+                            int max_leaf, std::vector<WideNode>& wide, std::vector<uint32_t>& tri_order) {
     float slo[3] = { 3e38f, 3e38f, 3e38f }, shi[3] = { -3e38f, -3e38f, -3e38f };
-    for (uint32_t g = 0; g < nt; g++) {
-        exact = flatten_body(g, s->ps.prims.data(), (int)s->ps.prims.size(), s->mesh_p.data(), wp.data(), tri_lo.data(),
-                             tri_hi.data(), centre.data()) && exact;
+    for (uint32_t g = 0; g < nt; g++)
         for (int a = 0; a < 3; a++) { slo[a] = fminf(slo[a], tri_lo[(size_t)g * 3 + a]); shi[a] = fmaxf(shi[a], tri_hi[(size_t)g * 3 + a]); }
-    }
-    for (int a = 0; a < 3; a++) { s->bounds[a] = slo[a]; s->bounds[3 + a] = shi[a]; }
     // k_morton + sort
     const double dlo[3] = { slo[0], slo[1], slo[2] }, dhi[3] = { shi[0], shi[1], shi[2] };
     std::vector<uint64_t> keys(nt);
@@ -218,8 +205,8 @@ int hostsim_scene_create(const LmcuSceneDesc* d, int max_leaf, void** out, long 
         }
     }
     // k_collapse, level by level
-    std::vector<WideNode> wide(nt);
-    std::vector<uint32_t> tri_order(nt);
+    wide.assign(nt, WideNode{});
+    tri_order.assign(nt, 0u);
     std::vector<CollapseItem> queue[2];
     queue[0].resize(nt); queue[1].resize(nt);
     uint32_t counters[3] = { 1u, 0u, 0u };
@@ -237,8 +224,99 @@ int hostsim_scene_create(const LmcuSceneDesc* d, int max_leaf, void** out, long 
         counters[2] = 0;
         cur ^= 1;
     }
-    if (counters[1] != nt) { g_err = "collapse lost triangles"; delete s; return 3; }
     wide.resize(counters[0]);
+    return counters[1] == nt;
+}
+
+extern "C" {
+
+const char* hostsim_last_error() { return g_err.c_str(); }
+
+// The two-level layout (LmcuBuildOptions::two_level), as lmcu_accel_build lays it out: [top-level tree | one tree per mesh in use]
+static int build_two_level(SimScene* s, int max_leaf) {
+    const std::vector<PrimDev>& prims = s->ps.prims;
+    const uint32_t np = (uint32_t)prims.size(), nt = s->ps.nt;
+    // top level: world-space box per primitive
+    std::vector<float> ilo((size_t)np * 3, 3e38f), ihi((size_t)np * 3, -3e38f);
+    for (uint32_t g = 0; g < nt; g++) {
+        float lo[3], hi[3];
+        const uint32_t pi = world_bounds_body(g, prims.data(), (int)np, s->mesh_p.data(), lo, hi);
+        for (int a = 0; a < 3; a++) { ilo[pi * 3 + a] = fminf(ilo[pi * 3 + a], lo[a]); ihi[pi * 3 + a] = fmaxf(ihi[pi * 3 + a], hi[a]); }
+    }
+    std::vector<double> icentre((size_t)np * 3);
+    for (size_t i = 0; i < (size_t)np * 3; i++) icentre[i] = ((double)ilo[i] + (double)ihi[i]) * 0.5;
+    for (int a = 0; a < 3; a++) { s->bounds[a] = 3e38f; s->bounds[3 + a] = -3e38f; }
+    for (uint32_t i = 0; i < np; i++) for (int a = 0; a < 3; a++) {
+        s->bounds[a] = fminf(s->bounds[a], ilo[i * 3 + a]); s->bounds[3 + a] = fmaxf(s->bounds[3 + a], ihi[i * 3 + a]);
+    }
+    std::vector<WideNode> top;
+    std::vector<uint32_t> inst_order;
+    if (!build_tree_host(np, ilo, ihi, icentre, max_leaf, top, inst_order)) return 3;
+    s->nodes = top;
+    // bottom levels
+    const size_t nm = s->ps.face_offset.size() - 1;
+    std::vector<uint32_t> root(nm, 0xffffffffu);
+    for (uint32_t i = 0; i < np; i++) {
+        const int m = prims[i].mesh;
+        if (root[m] != 0xffffffffu) continue;
+        const uint32_t nf = prims[i].num_faces;
+        const double* p = s->mesh_p.data() + (size_t)s->ps.face_offset[m] * 9;
+        std::vector<float> lo((size_t)nf * 3), hi((size_t)nf * 3);
+        std::vector<double> centre((size_t)nf * 3);
+        for (uint32_t k = 0; k < nf; k++) obj_bounds_body(k, p, lo.data(), hi.data(), centre.data());
+        std::vector<WideNode> wide;
+        std::vector<uint32_t> order;
+        if (!build_tree_host(nf, lo, hi, centre, max_leaf, wide, order)) return 3;
+        const uint32_t node_off = (uint32_t)s->nodes.size(), item_off = (uint32_t)s->tobj.size();
+        for (WideNode& w : wide) relocate_body(w, node_off, item_off);
+        s->nodes.insert(s->nodes.end(), wide.begin(), wide.end());
+        s->tobj.resize(item_off + nf);
+        for (uint32_t k = 0; k < nf; k++) emit_obj_body(k, order.data(), p, m, s->tobj.data() + item_off);
+        root[m] = node_off;
+    }
+    s->inst.resize(np);
+    for (uint32_t k = 0; k < np; k++) {
+        const uint32_t pi = inst_order[k];
+        if (!make_inst(prims[pi], pi, root[prims[pi].mesh], s->inst[k])) return 4;
+    }
+    s->two_level = true;
+    return 0;
+}
+
+int hostsim_scene_create2(const LmcuSceneDesc* d, int max_leaf, int two_level, void** out, long long* num_nodes) {
+    auto* s = new SimScene;
+    const int rc = prepare_scene(d, s->ps, g_err);
+    if (rc) { delete s; return rc; }
+    const uint32_t nt = s->ps.nt;
+    const size_t total_faces = s->ps.face_offset.back();
+    s->mesh_p.assign(total_faces * 9, 0.0);
+    s->mesh_n.assign(total_faces * 9, 0.0);
+    for (int i = 0; i < d->num_meshes; i++) {
+        const size_t cnt = (size_t)d->meshes[i].num_faces * 9;
+        memcpy(s->mesh_p.data() + (size_t)s->ps.face_offset[i] * 9, d->meshes[i].p, cnt * sizeof(double));
+        if (d->meshes[i].n) memcpy(s->mesh_n.data() + (size_t)s->ps.face_offset[i] * 9, d->meshes[i].n, cnt * sizeof(double));
+    }
+    if (want_two_level(two_level, s->ps.prims, s->ps.face_offset, nt)) {
+        const int rc2 = build_two_level(s, max_leaf);
+        if (rc2) { g_err = "two-level build failed"; delete s; return rc2; }
+        if (num_nodes) *num_nodes = (long long)s->nodes.size();
+        *out = s;
+        return 0;
+    }
+    // k_flatten
+    std::vector<double> wp((size_t)nt * 9), centre((size_t)nt * 3);
+    std::vector<float> tri_lo((size_t)nt * 3), tri_hi((size_t)nt * 3);
+    bool exact = true;
+    float slo[3] = { 3e38f, 3e38f, 3e38f }, shi[3] = { -3e38f, -3e38f, -3e38f };
+    for (uint32_t g = 0; g < nt; g++) {
+        exact = flatten_body(g, s->ps.prims.data(), (int)s->ps.prims.size(), s->mesh_p.data(), wp.data(), tri_lo.data(),
+                             tri_hi.data(), centre.data()) && exact;
+        for (int a = 0; a < 3; a++) { slo[a] = fminf(slo[a], tri_lo[(size_t)g * 3 + a]); shi[a] = fmaxf(shi[a], tri_hi[(size_t)g * 3 + a]); }
+    }
+    for (int a = 0; a < 3; a++) { s->bounds[a] = slo[a]; s->bounds[3 + a] = shi[a]; }
+    std::vector<WideNode> wide;
+    std::vector<uint32_t> tri_order;
+    if (!build_tree_host(nt, tri_lo, tri_hi, centre, max_leaf, wide, tri_order)) { g_err = "collapse lost triangles"; delete s; return 3; }
     s->nodes = wide;
     s->fp32 = exact;
     if (exact) s->t32.resize(nt); else s->t64.resize(nt);
@@ -254,12 +332,19 @@ int hostsim_scene_create(const LmcuSceneDesc* d, int max_leaf, void** out, long 
     return 0;
 }
 
+int hostsim_scene_create(const LmcuSceneDesc* d, int max_leaf, void** out, long long* num_nodes) {
+    return hostsim_scene_create2(d, max_leaf, -1, out, num_nodes);
+}
+
+int hostsim_two_level(void* p) { return static_cast<SimScene*>(p)->two_level ? 1 : 0; }
+
 void hostsim_scene_destroy(void* p) { delete static_cast<SimScene*>(p); }
 
 int hostsim_fp32(void* p) { return static_cast<SimScene*>(p)->fp32 ? 1 : 0; }
 
 int hostsim_intersect(void* p, const LmcuRay* rays, long long n, LmcuHit* hits, double* npr, double* tpr) {
     const SimScene& s = *static_cast<SimScene*>(p);
+    if (s.two_level) return intersect_t<TriObj>(s, rays, n, hits, npr, tpr);
     return s.fp32 ? intersect_t<TriF32>(s, rays, n, hits, npr, tpr) : intersect_t<TriF64>(s, rays, n, hits, npr, tpr);
 }
 
@@ -273,7 +358,8 @@ int hostsim_raycast(void* p, const LmcuRenderParams* rp_, float* film) {
     uint2 stack[kStackSize];
     for (int y = 0; y < rp.height; y++) {
         for (int x = 0; x < rp.width; x++) {
-            if (s.fp32) raycast_pixel<TriF32>(d, rp, x, y, film, stack); else raycast_pixel<TriF64>(d, rp, x, y, film, stack);
+            if (s.two_level) raycast_pixel<TriObj>(d, rp, x, y, film, stack);
+            else if (s.fp32) raycast_pixel<TriF32>(d, rp, x, y, film, stack); else raycast_pixel<TriF64>(d, rp, x, y, film, stack);
         }
     }
     return 0;
@@ -287,7 +373,8 @@ int hostsim_ao(void* p, const LmcuRenderParams* rp, float* film) {
     memset(film, 0, sizeof(float) * 3 * rp->width * rp->height);
     for (int y = 0; y < rp->height; y++) {
         for (int x = 0; x < rp->width; x++) {
-            if (s.fp32) ao_pixel<TriF32>(d, rp->width, rp->height, x, y, rp->spp, rp->sample_offset, rp->seed, rp->ao_distance, film, stack, &rays);
+            if (s.two_level) ao_pixel<TriObj>(d, rp->width, rp->height, x, y, rp->spp, rp->sample_offset, rp->seed, rp->ao_distance, film, stack, &rays);
+            else if (s.fp32) ao_pixel<TriF32>(d, rp->width, rp->height, x, y, rp->spp, rp->sample_offset, rp->seed, rp->ao_distance, film, stack, &rays);
             else ao_pixel<TriF64>(d, rp->width, rp->height, x, y, rp->spp, rp->sample_offset, rp->seed, rp->ao_distance, film, stack, &rays);
         }
     }
@@ -318,14 +405,14 @@ int hostsim_pt(void* p, const LmcuRenderParams* rp, float* film, long long* rays
         const GenOut go = pt_generate_body(d, pp, g, q, 0);
         if (go.shadow) {        // image mode: NEE connection of the camera vertex
             HitD hs;
-            if (s.fp32) pt_trace<true, false, TriF32>(d, go.sh_o, go.sh_d, hs, stack, nullptr); else pt_trace<true, false, TriF64>(d, go.sh_o, go.sh_d, hs, stack, nullptr);
+            if (s.two_level) pt_trace<true, false, TriObj>(d, go.sh_o, go.sh_d, hs, stack, nullptr); else if (s.fp32) pt_trace<true, false, TriF32>(d, go.sh_o, go.sh_d, hs, stack, nullptr); else pt_trace<true, false, TriF64>(d, go.sh_o, go.sh_d, hs, stack, nullptr);
             rays++;
             const uint32_t px = f2u(go.sh_c.w);
             if (hs.tri < 0) { acc[px * 3 + 0] += go.sh_c.x; acc[px * 3 + 1] += go.sh_c.y; acc[px * 3 + 2] += go.sh_c.z; }
         }
         while (true) {
             HitD h;
-            if (s.fp32) pt_trace<false, false, TriF32>(d, ro, rd, h, stack, nullptr); else pt_trace<false, false, TriF64>(d, ro, rd, h, stack, nullptr);
+            if (s.two_level) pt_trace<false, false, TriObj>(d, ro, rd, h, stack, nullptr); else if (s.fp32) pt_trace<false, false, TriF32>(d, ro, rd, h, stack, nullptr); else pt_trace<false, false, TriF64>(d, ro, rd, h, stack, nullptr);
             rays++;
             const float4 hit = make_float4((float)h.t, (float)h.u, (float)h.v, u2f((uint32_t)h.tri));
             const ShadeOut o = pt_shade_body<true>(d, pp, ro, rd, tp, aux, info, hit);
@@ -333,7 +420,7 @@ int hostsim_pt(void* p, const LmcuRenderParams* rp, float* film, long long* rays
             acc[pixel * 3 + 0] += o.emit.x; acc[pixel * 3 + 1] += o.emit.y; acc[pixel * 3 + 2] += o.emit.z;
             if (o.shadow) {
                 HitD hs;
-                if (s.fp32) pt_trace<true, false, TriF32>(d, o.sh_o, o.sh_d, hs, stack, nullptr); else pt_trace<true, false, TriF64>(d, o.sh_o, o.sh_d, hs, stack, nullptr);
+                if (s.two_level) pt_trace<true, false, TriObj>(d, o.sh_o, o.sh_d, hs, stack, nullptr); else if (s.fp32) pt_trace<true, false, TriF32>(d, o.sh_o, o.sh_d, hs, stack, nullptr); else pt_trace<true, false, TriF64>(d, o.sh_o, o.sh_d, hs, stack, nullptr);
                 rays++;
                 if (hs.tri < 0) { acc[pixel * 3 + 0] += o.sh_c.x; acc[pixel * 3 + 1] += o.sh_c.y; acc[pixel * 3 + 2] += o.sh_c.z; }
             }
@@ -376,13 +463,13 @@ int hostsim_lt(void* p, const LmcuRenderParams* rp, float* film, long long* rays
         lt_generate_body(d, pp, g, q, 0);
         while (true) {
             HitD h;
-            if (s.fp32) pt_trace<false, false, TriF32>(d, ro, rd, h, stack, nullptr); else pt_trace<false, false, TriF64>(d, ro, rd, h, stack, nullptr);
+            if (s.two_level) pt_trace<false, false, TriObj>(d, ro, rd, h, stack, nullptr); else if (s.fp32) pt_trace<false, false, TriF32>(d, ro, rd, h, stack, nullptr); else pt_trace<false, false, TriF64>(d, ro, rd, h, stack, nullptr);
             rays++;
             const float4 hit = make_float4((float)h.t, (float)h.u, (float)h.v, u2f((uint32_t)h.tri));
             const ShadeOut o = lt_shade_body<true>(d, pp, ro, rd, tp, info, hit);
             if (o.shadow) {
                 HitD hs;
-                if (s.fp32) pt_trace<true, false, TriF32>(d, o.sh_o, o.sh_d, hs, stack, nullptr); else pt_trace<true, false, TriF64>(d, o.sh_o, o.sh_d, hs, stack, nullptr);
+                if (s.two_level) pt_trace<true, false, TriObj>(d, o.sh_o, o.sh_d, hs, stack, nullptr); else if (s.fp32) pt_trace<true, false, TriF32>(d, o.sh_o, o.sh_d, hs, stack, nullptr); else pt_trace<true, false, TriF64>(d, o.sh_o, o.sh_d, hs, stack, nullptr);
                 rays++;
                 const uint32_t px = f2u(o.sh_c.w);
                 if (hs.tri < 0) { acc[px * 3 + 0] += o.sh_c.x; acc[px * 3 + 1] += o.sh_c.y; acc[px * 3 + 2] += o.sh_c.z; }
@@ -426,7 +513,8 @@ int hostsim_bdpt(void* p, const LmcuRenderParams* rp, float* film, long long* ra
     long long total_rays = 0;
     for (uint64_t g = 0; g < pp.total_paths; g++) {
         bc.rays = 0;
-        if (s.fp32) bdpt_sample<TriF32, true>(d, pp, min_verts, g, stack, &bc, splat); else bdpt_sample<TriF64, true>(d, pp, min_verts, g, stack, &bc, splat);
+        if (s.two_level) bdpt_sample<TriObj, true>(d, pp, min_verts, g, stack, &bc, splat);
+        else if (s.fp32) bdpt_sample<TriF32, true>(d, pp, min_verts, g, stack, &bc, splat); else bdpt_sample<TriF64, true>(d, pp, min_verts, g, stack, &bc, splat);
         total_rays += bc.rays;
     }
     if (bc.overflow) { g_err = "bvh traversal stack overflow"; return 1; }

@@ -37,16 +37,17 @@ def lib():
 
 
 class SimScene:
-    def __init__(self, builder, max_leaf=3):
+    def __init__(self, builder, max_leaf=3, two_level=-1):
         self._b = builder
         self._desc = builder.desc()
         self._h = C.c_void_p()
         nn = C.c_longlong()
-        rc = lib().hostsim_scene_create(C.byref(self._desc), max_leaf, C.byref(self._h), C.byref(nn))
+        rc = lib().hostsim_scene_create2(C.byref(self._desc), max_leaf, two_level, C.byref(self._h), C.byref(nn))
         if rc:
             raise RuntimeError(lib().hostsim_last_error().decode())
         self.num_nodes = nn.value
         self.fp32 = bool(lib().hostsim_fp32(self._h))
+        self.two_level = bool(lib().hostsim_two_level(self._h))
 
     def intersect(self, rays):
         rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)

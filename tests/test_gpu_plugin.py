@@ -380,3 +380,23 @@ def test_renderer_bdpt_cuda(plugin):
     ft, elapsed, proc = rs.render("renderer::bdpt_cuda", pt)
     assert proc % 100000 == 0 and proc > 0 and abs(ft.mean() - fr.mean()) < 0.03 * fr.mean()
     rs.close()
+
+
+def test_renderers_cuda_two_level_layout(plugin):
+    """'two_level': 1 on the plugin's renderers (one tree per mesh + one over the primitives, as accel::embreeinstanced does
+    for the reference): the raycast image equals the flattened layout's, pt agrees with the reference's renderer::pt."""
+    sb = scenes.instanced_spheres(grid=2, num_theta=24)
+    rs = plugin.RefScene(sb)
+    p = abi.render_params(160, 90, spp=128, max_verts=10)
+    fr, _, _ = rs.render("pt", p)
+    f_flat, _, _ = rs.render("renderer::raycast_cuda", abi.render_params(160, 90))
+    os.environ["LMREF_EXTRA_PROPS"] = '{"two_level": 1}'
+    try:
+        fc, _, pc = rs.render("renderer::pt_cuda", p)
+        f_two, _, _ = rs.render("renderer::raycast_cuda", abi.render_params(160, 90))
+    finally:
+        del os.environ["LMREF_EXTRA_PROPS"]
+    assert pc == 128
+    assert_pt_parity(fr, fc, 128, rel_mean=0.015)
+    assert rmse(f_flat, f_two) <= 1e-6 and f_flat.std() > 0.05
+    rs.close()

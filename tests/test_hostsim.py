@@ -254,3 +254,55 @@ def test_bdpt_statistics(reference, sim, scene):
     al = ss.render("bdpt", abi.render_params(w, h, max_verts=3, min_verts=3, num_samples=w * h * 4, primary_ray_sampling_mode=abi.PRIMARY_IMAGE))
     assert 0 < al.mean() < lo.mean()
     rs.close()
+
+
+@pytest.mark.parametrize("grid,num_theta", [(3, 12), (2, 24)])
+def test_two_level_layout_equals_flattened(sim, grid, num_theta):
+    """LmcuBuildOptions::two_level (one tree per mesh in object space + one over the instances; leaf test on vertices
+    transformed with the flattened build's operations): every hit field, the raycast image and a path-traced image are
+    bit-identical to the flattened tree's (sequential CPU build of the kernel bodies: same sample streams, same order)."""
+    sb = scenes.instanced_spheres(grid=grid, num_theta=num_theta)
+    a, b = sim.SimScene(sb, two_level=-1), sim.SimScene(sb, two_level=1)
+    assert b.two_level and not a.two_level and b.num_nodes < a.num_nodes
+    lo, hi = np.array([-1., -.2, -1.]) * grid, np.array([1., 1.2, 1.]) * grid
+    rays = np.concatenate([scenes.camera_rays(sb.camera, 160, 90), scenes.random_rays(20000, lo, hi)])
+    ha, hb = a.intersect(rays), b.intersect(rays)
+    assert a.overflow == 0 and b.overflow == 0 and (ha["primitive"] >= 0).sum() > 5000
+    for k in ("primitive", "face", "t", "u", "v"):
+        assert (ha[k] == hb[k]).all(), k
+    rays["tmin"], rays["tmax"] = 0.7, 2.9
+    ha, hb = a.intersect(rays), b.intersect(rays)
+    for k in ("primitive", "face", "t", "u", "v"):
+        assert (ha[k] == hb[k]).all(), k
+    p = abi.render_params(64, 36)
+    assert np.array_equal(a.render("raycast", p), b.render("raycast", p))
+    p = abi.render_params(32, 18, spp=4, max_verts=6)
+    fa, fb = a.render("pt", p), b.render("pt", p)
+    assert np.array_equal(fa, fb) and fa.mean() > 0.1
+    p = abi.render_params(32, 18, spp=2, ao_distance=0.5)
+    assert np.array_equal(a.render("ao", p), b.render("ao", p))
+
+
+def test_two_level_vs_reference_and_policy(reference, sim, tmp_path):
+    sb = scenes.instanced_spheres(grid=2, num_theta=12)
+    rs, ss = reference.RefScene(sb), sim.SimScene(sb, two_level=1)
+    rays = np.concatenate([scenes.camera_rays(sb.camera, 160, 90), scenes.random_rays(8000, np.array([-2, 0, -2.]), np.array([2, 3, 2.]))])
+    assert_hit_parity(rs.intersect(rays), ss.intersect(rays), max_special=0)
+    rs.close()
+    assert not sim.SimScene(sb, two_level=0).two_level                      # automatic: a small scene stays flattened
+    # textured meshes (texture coordinates from the mesh arrays) and meshes without vertex normals
+    sb = scenes.textured_scene(tmp_path, 8, "obj")
+    a, b = sim.SimScene(sb, two_level=-1), sim.SimScene(sb, two_level=1)
+    assert b.two_level
+    # the shell's walls share edges that the symmetric camera meets exactly: on those rays (equal t on two primitives) the
+    # reported triangle depends on the order of the walk — 2 of the 2304 pixels here
+    p = abi.render_params(64, 36)
+    fa, fb = a.render("raycast", p), b.render("raycast", p)
+    assert (fa != fb).any(axis=2).sum() <= 2 and fa.std() > 0.02
+    p = abi.render_params(24, 14, spp=4, max_verts=5)
+    fa, fb = a.render("pt", p), b.render("pt", p)
+    assert (fa != fb).any(axis=2).sum() <= 4 and fa.mean() > 0.05
+    # a singular transform cannot be walked in object space: flattened
+    tri = scenes._f32(np.array([[[0, 0, 0], [1, 0, 0], [0, 1, 0]]], dtype=np.float64))
+    sb.add_primitive(sb.add_mesh(tri, scenes.flat_normals(tri)), sb.diffuse((.5, .5, .5)), M=scenes.scale([1.0, 1.0, 0.0]))
+    assert not sim.SimScene(sb, two_level=1).two_level
