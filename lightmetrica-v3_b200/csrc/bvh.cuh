@@ -185,6 +185,10 @@ constexpr float kByteBias = 32768.0f;
 
 // Intersects the 8 quantised child boxes of one node; returns the CWBVH hit mask
 // (bits 31..24: internal children in traversal priority, bits 23..0: triangles).
+// (Measured and dropped: sm_100a's packed fma.rn.f32x2 — one FFMA2 forming the near and the far plane distance of an axis,
+// 24 FFMA2 for the 48 FFMA of a node step, no extra moves in the SASS, 704 -> 680 instructions in k_pt_extend_q — is
+// 0.5 % SLOWER on C2 (1909 against 1919 Mpaths/s, profiles/r02_ab_ffma2.log): an FFMA2 takes the issue port for two cycles,
+// so the kernel's binding resource, issue slots, is not relieved.)
 LMCU_HD uint32_t node_hitmask(const uint4 n0, const uint4 n1, const uint4 n2, const uint4 n3, const uint4 n4,
                               const RayF& f, float tmin_dn, float tmax_up) {
     const float px = u2f(n0.x), py = u2f(n0.y), pz = u2f(n0.z);

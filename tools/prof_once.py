@@ -2,6 +2,7 @@
 
   python tools/prof_once.py c2     C2 pt 1920x1080 @ 8 spp, one wavefront        -> k_pt_extend_q / k_pt_shade / k_pt_shadow_q
   python tools/prof_once.py c4     C4 pt 3840x2160 @ 2 spp, one wavefront        -> k_pt_extend_q on the 49.7 M-triangle scene
+  python tools/prof_once.py c4two  the same on the two-level layout                      -> k_pt_extend_q<TriObj>
   python tools/prof_once.py c3     C3 incoherent bounce batch, device buffers    -> k_intersect_q<TriF32>
 """
 import json
@@ -16,12 +17,12 @@ import lmcu  # noqa: E402
 from lmcu import abi, scenes  # noqa: E402
 
 mode = sys.argv[1]
-if mode in ("c2", "c4"):
+if mode in ("c2", "c4", "c4two"):
     if mode == "c2":
         sb, w, h, spp = scenes.cornell_spheres(64), 1920, 1080, 48
     else:
         sb, w, h, spp = scenes.instanced_spheres(grid=10, num_theta=112), 3840, 2160, 10
-    sc = lmcu.Scene(sb)
+    sc = lmcu.Scene(sb, two_level=1 if mode == "c4two" else 0)
     _, st = sc.render("pt", abi.render_params(w, h, spp=spp, max_verts=20, wavefronts=1), download=False)
     # one wavefront of 16 Mi paths, refilled to capacity every iteration while new paths remain (>= 5 iterations here):
     # launches 1..4 of the extend kernel trace exactly 2^24 rays, a steady-state mix of camera and bounce rays
