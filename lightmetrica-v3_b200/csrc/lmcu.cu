@@ -688,6 +688,8 @@ __global__ void __launch_bounds__(LMCU_SHADE_BLOCK, LMCU_SHADE_MINB) k_pt_shade(
     uint32_t tile = 0;
     for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x, tile ^= 1u) {
         const uint32_t i = base + threadIdx.x;
+        // (Measured and dropped, profiles/r02_ab_shade_pf.log: reading the NEXT tile's hit triangle here and pulling its
+        // geometry + shading records toward L1 after the shading below — shade 27 % -> 37 % of the step, C2 1920 -> 1768.)
         {   // the queues stream from HBM: pull the next grid-stride tile of this CTA into L2 while this one is shaded
             const uint32_t nx = i + gridDim.x * blockDim.x;
             if (nx < n && (threadIdx.x & 7u) == 0u) {          // one prefetch per 128-byte line of float4s
