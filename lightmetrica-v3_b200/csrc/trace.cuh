@@ -99,42 +99,45 @@ __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, 
         // ---- traverse until enough lanes are idle to make a re-fetch worth its latency ------------------
         while (true) {
             if (active) {
-                // ---- TWO: a lane in the top level that holds leaf items enters the first of them: what is left of the node is
-                // parked, the ray goes to the instance's object space, and the node step below starts on the mesh tree's root
-                // in this same iteration
-#define LMCU_ENTER_INSTANCE()                                                                                   \
-                {                                                                                               \
-                    const int ei = bfind(tgroup.y);                                                             \
-                    tgroup.y &= ~(1u << ei);                                                                    \
-                    const uint32_t in = tgroup.x + (uint32_t)ei;                                                \
-                    if (sp + 3 > kStackSize) { atomicExch(overflow, 1u); sp = kStackSize - 3; }                 \
-                    if (ngroup.y > 0x00ffffffu) stack[sp++] = ngroup;                                           \
-                    if (tgroup.y != 0u) stack[sp++] = tgroup;                                                   \
-                    stack[sp++] = make_uint2(0u, 0u);                                                           \
-                    cinst = in;                                                                                 \
-                    f = make_rayf_obj(r, inst[in].Minv);                                                        \
-                    ngroup = make_uint2(inst[in].root, 0x80000000u);                                            \
-                    tgroup = make_uint2(0u, 0u);                                                                \
-                }
                 if constexpr (TWO) {
-                    if (cinst == kNoInst && tgroup.y != 0u) LMCU_ENTER_INSTANCE()
+                    // ---- nothing in hand: pop.  A marker takes the ray back to the top level (world space) and the entry
+                    // under it is popped with it; a top-level leaf's remaining instances come back as a triangle-group entry
+                    bool to_world = false;
+                    if (tgroup.y == 0u && ngroup.y <= 0x00ffffffu && sp > 0) {
+                        uint2 e = stack[--sp];
+                        if (e.y == 0u) {
+                            cinst = kNoInst;
+                            to_world = true;
+                            if (sp > 0) e = stack[--sp];
+                        }
+                        if (e.y > 0x00ffffffu) ngroup = e;
+                        else if (e.y != 0u) tgroup = e;
+                    }
+                    // ---- a lane in the top level that holds leaf items (from the node step of the last iteration, or popped
+                    // just now) enters the first of them: what is left of the node is parked, the ray goes to the instance's
+                    // object space, and the node step below starts on the mesh tree's root in this same iteration
+                    if (cinst == kNoInst && tgroup.y != 0u) {
+                        const int ei = bfind(tgroup.y);
+                        tgroup.y &= ~(1u << ei);
+                        const uint32_t in = tgroup.x + (uint32_t)ei;
+                        if (sp + 3 > kStackSize) { atomicExch(overflow, 1u); sp = kStackSize - 3; }
+                        if (ngroup.y > 0x00ffffffu) stack[sp++] = ngroup;
+                        if (tgroup.y != 0u) stack[sp++] = tgroup;
+                        stack[sp++] = make_uint2(0u, 0u);
+                        cinst = in;
+                        f = make_rayf_obj(r, inst[in].Minv);
+                        ngroup = make_uint2(inst[in].root, 0x80000000u);
+                        tgroup = make_uint2(0u, 0u);
+                        to_world = false;                     // straight into the next instance of the same leaf
+                    }
+                    if (to_world) f = make_rayf(r);
                 }
                 if (tgroup.y == 0u) {
-                    if (ngroup.y <= 0x00ffffffu && sp > 0) {
-                        uint2 e = stack[--sp];
-                        if constexpr (TWO) {
-                            if (e.y == 0u) {                                   // the marker: back in the top level, world-space ray
-                                cinst = kNoInst;
-                                f = make_rayf(r);
-                                if (sp > 0) e = stack[--sp];
-                            }
-                            if (e.y > 0x00ffffffu) ngroup = e;
-                            else if (e.y != 0u) { tgroup = e; LMCU_ENTER_INSTANCE() }      // more instances of a top-level leaf
-                        } else {
-                            ngroup = e;
+                    if constexpr (!TWO) {
+                        if (ngroup.y <= 0x00ffffffu) {
+                            if (sp > 0) ngroup = stack[--sp];
                         }
                     }
-#undef LMCU_ENTER_INSTANCE
                     if (ngroup.y > 0x00ffffffu) {
                         // ---- one wide-node step
                         const uint32_t hits = ngroup.y;
