@@ -318,7 +318,7 @@ def bdpt_rate(sc, abi, sb):
     film, st = sc.render("bdpt", abi.render_params(W, H, num_samples=n, **kw))
     out = {"samples": n, "max_verts": mv, "msamples_per_s": st["paths"] / st["elapsed"] / 1e6,
            "mrays_per_s": st["rays"] / st["elapsed"] / 1e6, "rays_per_sample": st["rays"] / st["paths"],
-           "kernels": "k_bdpt_subpaths (one thread per subpath) -> k_bdpt_connect (one thread per (strategy, sample), strategy-major) -> k_pt_shadow_q"}
+           "kernels": "k_bdpt_gen, then per vertex index k_pt_extend_q -> k_bdpt_vertex (random walks as a wavefront) -> k_bdpt_lists (per-strategy work lists) -> k_bdpt_connect (one thread per (strategy, sample), strategy-major) -> k_pt_shadow_q"}
     try:
         from oracle import ref
         if ref.available():
