@@ -383,6 +383,30 @@ def instanced_spheres(grid=10, num_theta=112, seed=3, env=None):
     return sb
 
 
+def affine_instances(seed=0, n_inst=40, num_theta=10):
+    """Two meshes (a UV sphere, a box) under `n_inst` general affine transforms: rotation + shear (a random 3x3), anisotropic
+    scale 0.02 .. 30 per axis, every third one mirrored (negative determinant).  The stress fixture of the two-level layout:
+    object-space node tests under transforms that are far from rigid."""
+    rng = np.random.RandomState(seed)
+    sb = SceneBuilder()
+    p, n = uv_sphere(num_theta, 2 * num_theta, 0.5)
+    m1 = sb.add_mesh(_f32(p), n)
+    bx = _f32(box((-.5, -.3, -.2), (.5, .3, .2)))
+    m2 = sb.add_mesh(bx, flat_normals(bx))
+    mat = sb.diffuse((.6, .6, .6))
+    for i in range(n_inst):
+        A = rng.randn(3, 3) @ np.diag(np.exp(rng.uniform(np.log(0.02), np.log(30), 3)))
+        if i % 3 == 0:
+            A[:, 0] *= -1
+        M = np.eye(4)
+        M[:3, :3] = A * 0.5
+        M[:3, 3] = rng.uniform(-4, 4, 3)
+        sb.add_primitive(m1 if i % 2 else m2, mat, M=M)
+    sb.set_envconst((1, 1, 1))
+    sb.set_camera(position=(0, 0, 14), center=(0, 0, 0), up=(0, 1, 0), vfov=40, aspect=1)
+    return sb
+
+
 # ------------------------------------------------------------------------------------------------
 # Procedural environment map (C4 variant): sun lobe + sky gradient, stored as Radiance RGBE so that the
 # reference (texture::bitmap -> stb_image) and the device see bit-identical texels

@@ -65,6 +65,26 @@ def test_two_level_hits_equal_flattened_and_reference(reference, grid, num_theta
     rs.close(); flat.close(); two.close()
 
 
+@pytest.mark.parametrize("seed", [0, 1, 2, 3, 4, 5])
+def test_two_level_under_general_affine_transforms(reference, seed):
+    """Shear, anisotropic scale 0.02 .. 30 per axis, mirrored instances (negative determinant): the object-space node tests
+    stay conservative — no hit of the flattened tree is lost, every field bit-equal — through the queue kernel, and the hits
+    are accel::sahbvh's."""
+    sb = scenes.affine_instances(seed)
+    flat, two = lmcu.Scene(sb, two_level=-1), lmcu.Scene(sb, two_level=1)
+    assert two.build_stats.two_level == 1
+    rays = np.concatenate([scenes.camera_rays(sb.camera, 400, 400), scenes.random_rays(200000, np.array([-6, -6, -6.]), np.array([6, 6, 6.]), seed=seed)])
+    hf, ht = flat.intersect(rays), two.intersect(rays)
+    assert _same_hits(hf, ht) <= 2 and (ht["primitive"] >= 0).sum() > 50000
+    rs = reference.RefScene(sb)
+    assert_hit_parity(rs.intersect(rays[:100000]), ht[:100000], max_special=4)
+    p = abi.render_params(256, 256, visualize_normal=True)
+    fa, _ = flat.render("raycast", p)
+    fb, _ = two.render("raycast", p)
+    _same_image(fa, fb, 1e-4)
+    rs.close(); flat.close(); two.close()
+
+
 def test_two_level_tmin_tmax_window_and_any_hit():
     sb = scenes.instanced_spheres(grid=3, num_theta=16)
     flat, two = lmcu.Scene(sb, two_level=-1), lmcu.Scene(sb, two_level=1)

@@ -306,3 +306,20 @@ def test_two_level_vs_reference_and_policy(reference, sim, tmp_path):
     tri = scenes._f32(np.array([[[0, 0, 0], [1, 0, 0], [0, 1, 0]]], dtype=np.float64))
     sb.add_primitive(sb.add_mesh(tri, scenes.flat_normals(tri)), sb.diffuse((.5, .5, .5)), M=scenes.scale([1.0, 1.0, 0.0]))
     assert not sim.SimScene(sb, two_level=1).two_level
+
+
+@pytest.mark.parametrize("seed", [0, 1, 4])
+def test_two_level_under_general_affine_transforms(reference, sim, seed):
+    """Shear, anisotropic scale 0.02 .. 30, mirrored instances: the object-space node tests stay conservative (no hit of the
+    flattened tree is lost, every field bit-equal) and the hits are the reference's."""
+    sb = scenes.affine_instances(seed)
+    a, b = sim.SimScene(sb, two_level=-1), sim.SimScene(sb, two_level=1)
+    assert b.two_level
+    rays = np.concatenate([scenes.camera_rays(sb.camera, 120, 120), scenes.random_rays(30000, np.array([-6, -6, -6.]), np.array([6, 6, 6.]), seed=seed)])
+    ha, hb = a.intersect(rays), b.intersect(rays)
+    assert a.overflow == 0 and b.overflow == 0 and (ha["primitive"] >= 0).sum() > 10000
+    for k in ("primitive", "face", "t", "u", "v"):
+        assert (ha[k] == hb[k]).all(), k
+    rs = reference.RefScene(sb)
+    assert_hit_parity(rs.intersect(rays[:20000]), hb[:20000], max_special=2)
+    rs.close()
