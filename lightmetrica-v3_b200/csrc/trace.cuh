@@ -45,6 +45,11 @@ __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, 
     const uint32_t lt_mask = (1u << lane) - 1u;
     const uint4* nodes4 = reinterpret_cast<const uint4*>(nodes);
     uint2 stack[kStackSize];
+    // (Measured and dropped, profiles/r02_ab_smem_stack.log: the top 4 / 8 entries of every thread's stack in shared memory
+    // ([depth][thread], deeper entries spilling to this array): C2 1915 -> 1921 / 1886 Mpaths/s, the extend kernel alone 0.7 %
+    // slower — the stack is 69 bytes of local-memory traffic per ray, 91-97 % of it served by L1, profiles/r02_ncu_summary.md.)
+#define LMCU_PUSH(E) { stack[sp++] = (E); }
+#define LMCU_POP() (stack[--sp])
 
     // per-lane traversal state
     bool active = false;
@@ -104,11 +109,11 @@ __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, 
                     // under it is popped with it; a top-level leaf's remaining instances come back as a triangle-group entry
                     bool to_world = false;
                     if (tgroup.y == 0u && ngroup.y <= 0x00ffffffu && sp > 0) {
-                        uint2 e = stack[--sp];
+                        uint2 e = LMCU_POP();
                         if (e.y == 0u) {
                             cinst = kNoInst;
                             to_world = true;
-                            if (sp > 0) e = stack[--sp];
+                            if (sp > 0) e = LMCU_POP();
                         }
                         if (e.y > 0x00ffffffu) ngroup = e;
                         else if (e.y != 0u) tgroup = e;
@@ -121,9 +126,9 @@ __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, 
                         tgroup.y &= ~(1u << ei);
                         const uint32_t in = tgroup.x + (uint32_t)ei;
                         if (sp + 3 > kStackSize) { atomicExch(overflow, 1u); sp = kStackSize - 3; }
-                        if (ngroup.y > 0x00ffffffu) stack[sp++] = ngroup;
-                        if (tgroup.y != 0u) stack[sp++] = tgroup;
-                        stack[sp++] = make_uint2(0u, 0u);
+                        if (ngroup.y > 0x00ffffffu) LMCU_PUSH(ngroup)
+                        if (tgroup.y != 0u) LMCU_PUSH(tgroup)
+                        LMCU_PUSH(make_uint2(0u, 0u))
                         cinst = in;
                         f = make_rayf_obj(r, inst[in].Minv);
                         ngroup = make_uint2(inst[in].root, 0x80000000u);
@@ -135,7 +140,7 @@ __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, 
                 if (tgroup.y == 0u) {
                     if constexpr (!TWO) {
                         if (ngroup.y <= 0x00ffffffu) {
-                            if (sp > 0) ngroup = stack[--sp];
+                            if (sp > 0) ngroup = LMCU_POP();
                         }
                     }
                     if (ngroup.y > 0x00ffffffu) {
@@ -147,7 +152,7 @@ __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, 
                         ngroup.y &= ~(1u << child_bit);
                         if (ngroup.y > 0x00ffffffu) {
                             if (sp >= kStackSize) { atomicExch(overflow, 1u); sp = kStackSize - 1; }
-                            stack[sp++] = ngroup;
+                            LMCU_PUSH(ngroup)
                         }
                         const uint32_t slot = (uint32_t)(child_bit - 24) ^ (f.octinv4 & 0xffu);
                         const uint32_t ni = base + popc(imask & ~(0xffffffffu << slot));
@@ -212,6 +217,9 @@ __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, 
     }
 }
 
+
+#undef LMCU_PUSH
+#undef LMCU_POP
 
 #endif  // __CUDACC__
 
