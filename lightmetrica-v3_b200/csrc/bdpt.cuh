@@ -361,7 +361,7 @@ LMCU_HD bool bdpt_hit_vertex(const DevScene& s, const PtParams& p, uint64_t sidx
         v.p = f3s(0.f); v.n = -d; v.gn = f3s(0.f);
         return true;
     }
-    const SurfPoint sp = surface_point(s, (uint32_t)tri, hu, hv);
+    const SurfPoint sp = surface_point<COMP>(s, (uint32_t)tri, hu, hv);
     v.kind = BV_SURFACE; v.p = sp.p; v.n = sp.n; v.gn = sp.gn; v.tu = sp.tu; v.tv = sp.tv; v.mat = sp.material; v.light = sp.light;
     const MaterialDev& m = s.mats[sp.material];
     const R4 uc = rand4(p.seed, light_side ? kLightPathKey : kEyePathKey, sidx, 3u + 2u * (uint32_t)k);

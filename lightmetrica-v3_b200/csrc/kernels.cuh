@@ -95,8 +95,14 @@ LMCU_HD SurfPoint surface_point_inst(const DevScene& s, uint32_t g, float u, flo
     return sp;
 }
 
+// GENERAL = false: the caller's instantiation never sees a two-level scene (the plain-material shade kernels and the one-level
+// pixel loops: their register budget has no room for the second path — with it k_pt_shade<false> spills 92 instead of 68 bytes
+// and C2 loses 0.8 %, profiles/r02_ab_pre_two_level.log)
+template <bool GENERAL = true>
 LMCU_HD SurfPoint surface_point(const DevScene& s, uint32_t tri, float u, float v) {
-    if (s.tobj) return surface_point_inst(s, tri, u, v);
+    if constexpr (GENERAL) {
+        if (s.tobj) return surface_point_inst(s, tri, u, v);
+    }
     SurfPoint sp;
     F3 p1, p2, p3;
     tri_fetch(s, tri, p1, p2, p3, sp.prim, sp.face);
@@ -336,7 +342,7 @@ LMCU_HD void raycast_pixel(const DevScene& s, const RaycastParams& p, int x, int
             c = f3(p.bg[0], p.bg[1], p.bg[2]);
         }
     } else {
-        const SurfPoint sp = surface_point(s, (uint32_t)h.tri, (float)h.u, (float)h.v);
+        const SurfPoint sp = surface_point<TriT::kTwoLevel>(s, (uint32_t)h.tri, (float)h.u, (float)h.v);
         if (p.visualize_normal) {
             c = f3(fabsf(sp.n.x), fabsf(sp.n.y), fabsf(sp.n.z));
         } else {
@@ -362,7 +368,7 @@ LMCU_HD void ao_pixel(const DevScene& s, int width, int height, int x, int y, in
     traverse<false, false, TriT>(s.nodes, scene_tris<TriT>(s), r, h, stack, nullptr, s.inst);
     *ray_count += 1;
     if (h.tri < 0) return;   // the reference leaves the pixel untouched on a miss
-    const SurfPoint sp = surface_point(s, (uint32_t)h.tri, (float)h.u, (float)h.v);
+    const SurfPoint sp = surface_point<TriT::kTwoLevel>(s, (uint32_t)h.tri, (float)h.u, (float)h.v);
     const F3 wi = -f3((float)r.d.x, (float)r.d.y, (float)r.d.z);
     const Frame f = frame_twosided(sp.n, wi);
     float V = 0.f;
@@ -690,7 +696,7 @@ LMCU_HD ShadeOut pt_shade_body(const DevScene& s, const PtParams& p, float4 ro, 
         return out;
     }
 
-    const SurfPoint sp = surface_point(s, (uint32_t)tri, hit.y, hit.z);
+    const SurfPoint sp = surface_point<COMPOSITE>(s, (uint32_t)tri, hit.y, hit.z);
     const MaterialDev& mat = s.mats[sp.material];
 
     // direct hit on an emitter (renderer_pt.cpp:248-270)
@@ -843,7 +849,7 @@ LMCU_HD ShadeOut lt_shade_body(const DevScene& s, const PtParams& p, float4 ro, 
     uint32_t num_verts = info.y & 0xffu;                                    // loop counter of the iteration that traced this ray (1 = primary)
     F3 thr = f3(thr_pix.x, thr_pix.y, thr_pix.z);
     const F3 wi = -f3(rd.x, rd.y, rd.z);
-    const SurfPoint sp = surface_point(s, (uint32_t)tri, hit.y, hit.z);
+    const SurfPoint sp = surface_point<COMPOSITE>(s, (uint32_t)tri, hit.y, hit.z);
     const MaterialDev& mat = s.mats[sp.material];
     const R4 u0 = rand4(p.seed, kLightPathKey, sidx, num_verts * 4u + 4u);  // ud0, ud1, rr, uc0
     if (num_verts > 5u) {                                                   // renderer_lt.cpp:143-149

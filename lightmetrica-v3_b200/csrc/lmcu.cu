@@ -1069,6 +1069,8 @@ struct LmcuScene {
     bool two_level = false;
     int tri_kind() const { return two_level ? 2 : fp32 ? 1 : 0; }      // LMCU_DISPATCH: TriObj / TriF32 / TriF64 instantiations
     int trav_ctas() const { return two_level ? std::min(ctas_per_sm, LMCU_MINB_TWO) : ctas_per_sm; }   // CTAs per SM of the persistent traversal grids
+    bool general() const { return composite || two_level; }            // the <true> instantiations of the shade / bdpt kernels: textured or
+                                                                       // mixture materials, or surface points resolved through instances
     bool pool_on() const { return pool_mode && !two_level; }           // the shared-memory ray pool (trace2.cuh) walks one-level trees only
     std::vector<uint32_t> face_offset;   // per mesh, first face in mesh_p / mesh_n / mesh_t
     bool built = false, fp32 = false;
@@ -2209,10 +2211,10 @@ static int pt_pass(LmcuScene* s, const PtParams& pp_all, bool count, PtAccum& ac
             else LMCU_DISPATCH(k_pt_extend_q, s->tri_kind(), count, q_blocks, LMCU_TRAV_BLOCK, st, d, q[w][cur], v.hits.p, v.ctr.p, cur);
             cudaEventRecord(ev[1], st);
             if (pp[w].light_tracing) {
-                if (s->composite) k_lt_shade<true><<<shade_blocks, LMCU_SHADE_BLOCK, 0, st>>>(d, pp[w], q[w][cur], q[w][cur ^ 1], sq[w], v.hits.p, v.ctr.p, cur);
+                if (s->general()) k_lt_shade<true><<<shade_blocks, LMCU_SHADE_BLOCK, 0, st>>>(d, pp[w], q[w][cur], q[w][cur ^ 1], sq[w], v.hits.p, v.ctr.p, cur);
                 else k_lt_shade<false><<<shade_blocks, LMCU_SHADE_BLOCK, 0, st>>>(d, pp[w], q[w][cur], q[w][cur ^ 1], sq[w], v.hits.p, v.ctr.p, cur);
             }
-            else if (s->composite) k_pt_shade<true><<<shade_blocks, LMCU_SHADE_BLOCK, 0, st>>>(d, pp[w], q[w][cur], q[w][cur ^ 1], sq[w], v.hits.p, s->film.p, v.ctr.p, cur);
+            else if (s->general()) k_pt_shade<true><<<shade_blocks, LMCU_SHADE_BLOCK, 0, st>>>(d, pp[w], q[w][cur], q[w][cur ^ 1], sq[w], v.hits.p, s->film.p, v.ctr.p, cur);
             else k_pt_shade<false><<<shade_blocks, LMCU_SHADE_BLOCK, 0, st>>>(d, pp[w], q[w][cur], q[w][cur ^ 1], sq[w], v.hits.p, s->film.p, v.ctr.p, cur);
             cudaEventRecord(ev[2], st);
             if (s->pool_on()) LMCU_DISPATCH_SMEM(k_pt_shadow_p, s->fp32, count, q_blocks, LMCU_TRAV_BLOCK, pool_smem_pt, st, d, sq[w], s->film.p, v.ctr.p, v.arena.p);
@@ -2496,7 +2498,7 @@ int lmcu_render_bdpt(LmcuScene* s, const LmcuRenderParams* p, float* film_rgb, L
                 PathQueue q{};
                 q.ray_o = B.q_o[cur].p; q.ray_d = B.q_d[cur].p;
                 LMCU_DISPATCH(k_pt_extend_q, s->tri_kind(), false, q_blocks, LMCU_TRAV_BLOCK, st, d, q, B.hits.p, B.ctr.p, cur);
-                if (s->composite) k_bdpt_vertex<true><<<vtx_blocks, 128, 0, st>>>(d, pp, store, k, B.q_d[cur].p, B.q_id[cur].p, B.hits.p, B.q_o[cur ^ 1].p, B.q_d[cur ^ 1].p, B.q_id[cur ^ 1].p, B.ctr.p, cur);
+                if (s->general()) k_bdpt_vertex<true><<<vtx_blocks, 128, 0, st>>>(d, pp, store, k, B.q_d[cur].p, B.q_id[cur].p, B.hits.p, B.q_o[cur ^ 1].p, B.q_d[cur ^ 1].p, B.q_id[cur ^ 1].p, B.ctr.p, cur);
                 else k_bdpt_vertex<false><<<vtx_blocks, 128, 0, st>>>(d, pp, store, k, B.q_d[cur].p, B.q_id[cur].p, B.hits.p, B.q_o[cur ^ 1].p, B.q_d[cur ^ 1].p, B.q_id[cur ^ 1].p, B.ctr.p, cur);
                 k_bdpt_flip<<<1, 1, 0, st>>>(B.ctr.p, cur);
                 cur ^= 1;
@@ -2506,7 +2508,7 @@ int lmcu_render_bdpt(LmcuScene* s, const LmcuRenderParams* p, float* film_rgb, L
             const dim3 lgrid((unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)s->num_sms), (unsigned)pairs.size());
             k_bdpt_lists<<<lgrid, 256, 0, st>>>(pp, store, B.pairs.p, B.pair_list.p, B.pair_count.p);
             const dim3 cgrid((unsigned)std::min<int64_t>((n + 127) / 128, (int64_t)s->num_sms * 2), (unsigned)pairs.size());
-            if (s->composite) k_bdpt_connect<true><<<cgrid, 128, 0, st>>>(d, pp, store, B.pairs.p, B.pair_list.p, B.pair_count.p, sq, s->film.p, B.ctr.p);
+            if (s->general()) k_bdpt_connect<true><<<cgrid, 128, 0, st>>>(d, pp, store, B.pairs.p, B.pair_list.p, B.pair_count.p, sq, s->film.p, B.ctr.p);
             else k_bdpt_connect<false><<<cgrid, 128, 0, st>>>(d, pp, store, B.pairs.p, B.pair_list.p, B.pair_count.p, sq, s->film.p, B.ctr.p);
             LMCU_DISPATCH(k_pt_shadow_q, s->tri_kind(), false, q_blocks, LMCU_TRAV_BLOCK, st, d, sq, s->film.p, B.ctr.p);
             CU(cudaGetLastError());
