@@ -664,7 +664,8 @@ struct ShadeOut {
 // Scene::intersect (renderer_pt.cpp:229-300 for the hit, then :127-209 of the next loop iteration).
 // COMPOSITE = the scene holds a textured or mixture material; the <false> instantiation (every BASELINE config) carries
 // none of that code or its registers.
-template <bool COMPOSITE>
+// INST: surface points may have to be resolved through instances (two-level layout); the composite instantiation always can
+template <bool COMPOSITE, bool INST = COMPOSITE>
 LMCU_HD ShadeOut pt_shade_body(const DevScene& s, const PtParams& p, float4 ro, float4 rd, float4 thr_pix, float4 aux,
                                uint2 info, float4 hit) {
     ShadeOut out;
@@ -696,7 +697,7 @@ LMCU_HD ShadeOut pt_shade_body(const DevScene& s, const PtParams& p, float4 ro, 
         return out;
     }
 
-    const SurfPoint sp = surface_point<COMPOSITE>(s, (uint32_t)tri, hit.y, hit.z);
+    const SurfPoint sp = surface_point<INST>(s, (uint32_t)tri, hit.y, hit.z);
     const MaterialDev& mat = s.mats[sp.material];
 
     // direct hit on an emitter (renderer_pt.cpp:248-270)

@@ -680,7 +680,7 @@ __global__ void __launch_bounds__(LMCU_SHADE_BLOCK, LMCU_SHADE_MINB) k_lt_shade(
     }
 }
 
-template <bool COMPOSITE>
+template <bool COMPOSITE, bool INST = COMPOSITE>
 __global__ void __launch_bounds__(LMCU_SHADE_BLOCK, LMCU_SHADE_MINB) k_pt_shade(DevScene s, PtParams p, PathQueue qin, PathQueue qout, ShadowQueue sq,
                                                   const float4* hits, float* film, PtCounters* ctr, int cur) {
     __shared__ uint32_t smem[2][34];
@@ -702,7 +702,7 @@ __global__ void __launch_bounds__(LMCU_SHADE_BLOCK, LMCU_SHADE_MINB) k_pt_shade(
         o.alive = false; o.shadow = false;
         if (i < n) {
             const float4 tp = Q_LD(qin.thr_pix + i);
-            o = pt_shade_body<COMPOSITE>(s, p, Q_LD(qin.ray_o + i), Q_LD(qin.ray_d + i), tp, Q_LD(qin.aux + i), Q_LD(qin.info + i), Q_LD(hits + i));
+            o = pt_shade_body<COMPOSITE, INST>(s, p, Q_LD(qin.ray_o + i), Q_LD(qin.ray_d + i), tp, Q_LD(qin.aux + i), Q_LD(qin.info + i), Q_LD(hits + i));
             if (!is_zero(o.emit)) {
                 float* px = film + (size_t)f2u(tp.w) * 3;
                 atomicAdd(px + 0, o.emit.x); atomicAdd(px + 1, o.emit.y); atomicAdd(px + 2, o.emit.z);
@@ -1068,7 +1068,9 @@ struct LmcuScene {
     DBuf<InstDev> inst;                  // ... instance records in the top level's leaf order
     bool two_level = false;
     int tri_kind() const { return two_level ? 2 : fp32 ? 1 : 0; }      // LMCU_DISPATCH: TriObj / TriF32 / TriF64 instantiations
-    int trav_ctas() const { return two_level ? std::min(ctas_per_sm, LMCU_MINB_TWO) : ctas_per_sm; }   // CTAs per SM of the persistent traversal grids
+    int trav_ctas(bool wavefront = false) const {
+        return (two_level ? std::min(ctas_per_sm, LMCU_MINB_TWO) : ctas_per_sm) + (wavefront ? spare_ctas : 0);
+    }   // CTAs per SM of the persistent traversal grids
     bool general() const { return composite || two_level; }            // the <true> instantiations of the shade / bdpt kernels: textured or
                                                                        // mixture materials, or surface points resolved through instances
     bool pool_on() const { return pool_mode && !two_level; }           // the shared-memory ray pool (trace2.cuh) walks one-level trees only
@@ -1133,6 +1135,11 @@ struct LmcuScene {
     DBuf<uint2> batch_arena;             // pool mode: traversal stacks of the accel-batch kernel
     int shade_ctas_per_sm = LMCU_SHADE_MINB;     // LMCU_SHADE_GRID: CTAs per SM in the shade kernel's grid-stride grid
     int ctas_per_sm = LMCU_MINB;                 // LMCU_CTAS: resident 128-thread CTAs per SM for the persistent traversal grids
+    int spare_ctas = 2;                          // LMCU_SPARE_CTAS: the wavefront loops launch this many MORE traversal CTAs per SM than are
+                                                 // resident; they start as the first ones run out of rays and fill the tail of a launch
+                                                 // next to the other wavefront's kernels (grids of 6 / 7 / 8 / 10 / 12 per SM: 1930 / 1945 /
+                                                 // 1946 / 1945 / 1944 Mpaths/s on C2; a batch launch on its own loses 1-2 % to them:
+                                                 // profiles/r02_ab_knobs.log)
 
     DevScene dev() const {
         DevScene d{};
@@ -1186,6 +1193,7 @@ int lmcu_scene_create(int device, LmcuScene** out) {
     if (const char* e = getenv("LMCU_POOL_FETCH")) s->pool_refill = std::max(1, atoi(e));
     if (const char* e = getenv("LMCU_CHUNK")) { uint32_t c = 1; while (c * 2 <= (uint32_t)std::max(1, atoi(e)) && c < 4096) c *= 2; s->path_chunk = c; }
     if (const char* e = getenv("LMCU_CTAS")) s->ctas_per_sm = std::max(1, atoi(e));
+    if (const char* e = getenv("LMCU_SPARE_CTAS")) s->spare_ctas = std::max(0, atoi(e));
     if (const char* e = getenv("LMCU_SHADE_GRID")) s->shade_ctas_per_sm = std::max(1, atoi(e));
     if (const char* e = getenv("LMCU_WAVES")) s->default_waves = std::min((int)LmcuScene::kMaxWaves, std::max(1, atoi(e)));
     CU(s->cursor.alloc(8 + LmcuScene::kCursorRing));
@@ -2160,7 +2168,7 @@ static int pt_pass(LmcuScene* s, const PtParams& pp_all, bool count, PtAccum& ac
     // pending, so a kernel's drain tail is filled by the other loop's next kernel (grids cut to 1/K measured worse).
     const int K = s->waves;
     const DevScene d = s->dev();
-    const unsigned q_blocks = (unsigned)(s->num_sms * s->trav_ctas());
+    const unsigned q_blocks = (unsigned)(s->num_sms * s->trav_ctas(true));
     const unsigned shade_blocks = (unsigned)(s->num_sms * s->shade_ctas_per_sm), gen_blocks = (unsigned)s->num_sms * 4;
     const int kGroup = 4;                       // iterations between host checks
     const size_t pool_smem_pt = pool_bytes_per_warp<ExtendIO, kPoolK>() * (LMCU_TRAV_BLOCK / 32);
@@ -2214,7 +2222,8 @@ static int pt_pass(LmcuScene* s, const PtParams& pp_all, bool count, PtAccum& ac
                 if (s->general()) k_lt_shade<true><<<shade_blocks, LMCU_SHADE_BLOCK, 0, st>>>(d, pp[w], q[w][cur], q[w][cur ^ 1], sq[w], v.hits.p, v.ctr.p, cur);
                 else k_lt_shade<false><<<shade_blocks, LMCU_SHADE_BLOCK, 0, st>>>(d, pp[w], q[w][cur], q[w][cur ^ 1], sq[w], v.hits.p, v.ctr.p, cur);
             }
-            else if (s->general()) k_pt_shade<true><<<shade_blocks, LMCU_SHADE_BLOCK, 0, st>>>(d, pp[w], q[w][cur], q[w][cur ^ 1], sq[w], v.hits.p, s->film.p, v.ctr.p, cur);
+            else if (s->composite) k_pt_shade<true><<<shade_blocks, LMCU_SHADE_BLOCK, 0, st>>>(d, pp[w], q[w][cur], q[w][cur ^ 1], sq[w], v.hits.p, s->film.p, v.ctr.p, cur);
+            else if (s->two_level) k_pt_shade<false, true><<<shade_blocks, LMCU_SHADE_BLOCK, 0, st>>>(d, pp[w], q[w][cur], q[w][cur ^ 1], sq[w], v.hits.p, s->film.p, v.ctr.p, cur);
             else k_pt_shade<false><<<shade_blocks, LMCU_SHADE_BLOCK, 0, st>>>(d, pp[w], q[w][cur], q[w][cur ^ 1], sq[w], v.hits.p, s->film.p, v.ctr.p, cur);
             cudaEventRecord(ev[2], st);
             if (s->pool_on()) LMCU_DISPATCH_SMEM(k_pt_shadow_p, s->fp32, count, q_blocks, LMCU_TRAV_BLOCK, pool_smem_pt, st, d, sq[w], s->film.p, v.ctr.p, v.arena.p);
@@ -2482,7 +2491,7 @@ int lmcu_render_bdpt(LmcuScene* s, const LmcuRenderParams* p, float* film_rgb, L
     store.nverts = B.nverts.p; store.eye_pixel = B.eye_pixel.p; store.cap = cap; store.mv = p->max_verts;
     ShadowQueue sq;
     sq.ray_o = B.sq[0].p; sq.ray_d = B.sq[1].p; sq.contrib = B.sq[2].p;
-    const unsigned q_blocks = (unsigned)(s->num_sms * s->trav_ctas());
+    const unsigned q_blocks = (unsigned)(s->num_sms * s->trav_ctas(true));
     auto run_pass = [&](int64_t count) -> int {
         for (int64_t done = 0; done < count;) {
             const int64_t n = std::min<int64_t>(cap, count - done);
