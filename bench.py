@@ -480,7 +480,7 @@ def run_ours(args):
     # wall clock, max over ranks
     desc_bytes = sum(p.nbytes + (n.nbytes if n is not None else 0) for p, n in sb.meshes)
     sync()
-    e2e_steps = max(1, min(args.steps, 2))
+    e2e_steps = max(1, min(args.steps, 5))
     cur = {}
     reduce_e2e, close_e2e = make_reducer(torch, dist, lmcu, D, lambda: cur["sc"], rank, world, local_rank, args.reduce)
 
@@ -502,12 +502,16 @@ def run_ours(args):
     e2e_step()
     sync()
     t0 = time.perf_counter()
+    e2e_times = []
     for _ in range(e2e_steps):
+        ts = time.perf_counter()
         host_film = e2e_step()
+        e2e_times.append(time.perf_counter() - ts)
     t_e2e = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
     close_e2e()
     e2e = {"value": paths_per_step / t_e2e / 1e6, "unit": "Mpaths/s",
            "h2d_bytes_per_step": int(desc_bytes), "d2h_bytes_per_step": int(npix * 3 * 4),
+           "steps": e2e_steps, "step_seconds_rank0": [round(t, 4) for t in e2e_times],
            "what": "lmcu.Scene(host scene description) [H2D + BVH build] + render('pt') + film combine (%s) + film D2H, "
                    "wall clock, max over ranks" % args.reduce}
 

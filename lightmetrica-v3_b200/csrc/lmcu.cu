@@ -960,7 +960,8 @@ __global__ void __launch_bounds__(256) k_film_reduce_slice(FilmSet films, int nu
 // ================================================================================================
 // Scratch allocations (path pools, films) are recycled across scenes of a process: cudaMalloc / cudaFree of
 // the 1.7 GB of path queues cost far more than a BVH build, and a host that re-creates its scene per render
-// (the Lightmetrica plugin does) would pay it every time.  Freed blocks of >= 1 MiB are parked here per
+// (the Lightmetrica plugin does) would pay it every time.  Freed blocks of every size — the builder's small temporaries too: next to gigabytes of live path
+// pools a cudaFree / cudaMalloc pair costs 0.1-0.2 ms and now and then hundreds (tools/build_probe.py) — are parked here per
 // (device, size), at most kCacheBytes per process, and handed out again on the next equal-sized request.
 namespace {
 struct BlockCache {
@@ -968,6 +969,7 @@ struct BlockCache {
     std::multimap<std::pair<int, size_t>, void*> blocks;
     std::map<int, size_t> bytes;           // parked bytes per device
     size_t cap = size_t(24) << 30;         // per DEVICE; LMCU_CACHE_GB overrides it (0 = park nothing)
+    static constexpr size_t kMaxBlocks = 8192;
     BlockCache() { if (const char* e = getenv("LMCU_CACHE_GB")) cap = (size_t)(atof(e) * double(size_t(1) << 30)); }
     void* take(int device, size_t n) {
         std::lock_guard<std::mutex> lk(mu);
@@ -995,7 +997,7 @@ struct BlockCache {
     bool park(int device, size_t n, void* p) {
         std::lock_guard<std::mutex> lk(mu);
         const bool keep = exported.count(p) != 0;
-        if (!keep && (n < (size_t(1) << 20) || bytes[device] + n > cap)) return false;
+        if (!keep && (bytes[device] + n > cap || blocks.size() >= kMaxBlocks)) return false;
         blocks.insert({ { device, n }, p });
         bytes[device] += n;
         return true;
@@ -1437,10 +1439,18 @@ int lmcu_accel_build(LmcuScene* s, const LmcuBuildOptions* opts, LmcuBuildStats*
     cudaStream_t st = s->stream;
     CU(cudaEventRecord(s->ev0, st));
     s->built = false;
-    size_t free_b = 0, total_b = 0;
-    CU(cudaMemGetInfo(&free_b, &total_b));
-    if (const char* e = getenv("LMCU_BUILD_BUDGET_GB")) free_b = (size_t)(atof(e) * double(size_t(1) << 30));   // the memory the automatic layout choice plans with
-    s->two_level = want_two_level(two_level_opt, s->h_prims, s->face_offset, nt, (double)free_b);
+    {
+        // the device is only asked for its free memory when the answer can matter (cudaMemGetInfo costs ~10 ms next to
+        // gigabytes of live allocations, and now and then hundreds: tools/build_probe.py)
+        const int cand = two_level_candidate(two_level_opt, s->h_prims, s->face_offset, nt);
+        s->two_level = cand > 0;
+        if (cand == 0) {
+            size_t free_b = 0, total_b = 0;
+            if (const char* e = getenv("LMCU_BUILD_BUDGET_GB")) free_b = (size_t)(atof(e) * double(size_t(1) << 30));   // the memory the automatic layout choice plans with
+            else CU(cudaMemGetInfo(&free_b, &total_b));
+            s->two_level = two_level_by_budget(nt, (double)free_b);
+        }
+    }
     s->t32.release(); s->t64.release(); s->tobj.release(); s->inst.release(); s->shade.release(); s->uv.release();
 
     if (s->two_level) {

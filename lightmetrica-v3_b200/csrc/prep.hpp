@@ -286,18 +286,26 @@ inline bool make_inst(const PrimDev& pr, uint32_t prim, uint32_t root, InstDev& 
 // automatic choice keeps it while it fits: two-level only for an instanced scene (flattened triangles >= 4 x the unique ones)
 // whose flattened build (~475 bytes per triangle at its peak: 155 resident + the builder's temporaries) would take more than
 // half of `budget_bytes` (the device's free memory).
-inline bool want_two_level(int option, const std::vector<PrimDev>& prims, const std::vector<uint32_t>& face_offset, uint32_t nt,
-                           double budget_bytes = 0.0) {
-    if (option < 0) return false;
+// Step 1 (no device query): -1 = flattened, 1 = two-level, 0 = an instanced scene under the automatic option — the caller then
+// decides with two_level_by_budget().
+inline int two_level_candidate(int option, const std::vector<PrimDev>& prims, const std::vector<uint32_t>& face_offset, uint32_t nt) {
+    if (option < 0) return -1;
     std::vector<char> used(face_offset.size(), 0);
     uint64_t unique = 0;
     InstDev tmp;
     for (size_t i = 0; i < prims.size(); i++) {
-        if (!make_inst(prims[i], (uint32_t)i, 0u, tmp)) return false;
+        if (!make_inst(prims[i], (uint32_t)i, 0u, tmp)) return -1;
         if (!used[prims[i].mesh]) { used[prims[i].mesh] = 1; unique += prims[i].num_faces; }
     }
-    if (option > 0) return true;
-    return (uint64_t)nt >= 4 * unique && budget_bytes > 0.0 && 475.0 * (double)nt > 0.5 * budget_bytes;
+    if (option > 0) return 1;
+    return (uint64_t)nt >= 4 * unique ? 0 : -1;
+}
+inline bool two_level_by_budget(uint32_t nt, double budget_bytes) { return budget_bytes > 0.0 && 475.0 * (double)nt > 0.5 * budget_bytes; }
+
+inline bool want_two_level(int option, const std::vector<PrimDev>& prims, const std::vector<uint32_t>& face_offset, uint32_t nt,
+                           double budget_bytes = 0.0) {
+    const int c = two_level_candidate(option, prims, face_offset, nt);
+    return c > 0 || (c == 0 && two_level_by_budget(nt, budget_bytes));
 }
 
 }  // namespace lmcu

@@ -14,7 +14,7 @@ sb = scenes.cornell_spheres(64)
 keep = lmcu.Scene(sb)                     # the resident scene of bench.py holds its own pools
 keep.render("pt", abi.render_params(1920, 1080, spp=4, max_verts=20), download=False)
 spp = int(sys.argv[1]) if len(sys.argv) > 1 else 256
-for it in range(4):
+for it in range(int(os.environ.get("E2E_ITERS", "4"))):
     t = [time.perf_counter()]
     d = sb.desc(); t.append(time.perf_counter())
     sc = lmcu.Scene(sb); t.append(time.perf_counter())
