@@ -355,11 +355,14 @@ def plugin_e2e(sb, abi, spp, paths):
             os.environ.pop("LMREF_EXTRA_PROPS", None)
         try:
             rs.render("renderer::pt_cuda", abi.render_params(W, H, spp=16, max_verts=MAX_VERTS, seed=SEED))    # warm the path pools
-            t0 = time.perf_counter()
-            film, elapsed, processed = rs.render("renderer::pt_cuda", p)
-            wall = time.perf_counter() - t0
-            out[name] = {"value": paths / wall / 1e6, "unit": "Mpaths/s", "wall_s": wall, "render_json_elapsed_s": elapsed,
-                         "processed": int(processed)}
+            walls = []
+            for _ in range(2):                              # two calls, the faster one quoted, both listed (one-shot wall clock
+                t0 = time.perf_counter()                    # around a host-side export is at the mercy of the host)
+                film, elapsed, processed = rs.render("renderer::pt_cuda", p)
+                walls.append(time.perf_counter() - t0)
+            wall = min(walls)
+            out[name] = {"value": paths / wall / 1e6, "unit": "Mpaths/s", "wall_s": wall, "wall_s_all": [round(w, 4) for w in walls],
+                         "render_json_elapsed_s": elapsed, "processed": int(processed)}
         finally:
             os.environ.pop("LMREF_FILM", None)
             os.environ.pop("LMREF_EXTRA_PROPS", None)
