@@ -259,9 +259,12 @@ const char* lmcu_last_error(void);
 int lmcu_device_count(void);
 const char* lmcu_version(void);
 
-/* Scratch blocks (path pools, films) are recycled per device inside the library, at most LMCU_CACHE_GB (default 24) GiB
- * per device; lmcu_cache_trim() hands the parked blocks of `device` back to the driver (after a device synchronise). */
+/* Device blocks (path pools, films, the builder's temporaries) are recycled per device inside the library: a freed block is
+ * parked and handed out again on the next request of the same size, at most LMCU_CACHE_GB (default 24) GiB per device — over
+ * the cap the blocks parked longest ago go back to the driver.  lmcu_cache_trim() hands every parked block of `device` back
+ * (after a device synchronise); lmcu_cache_stats() reports what is parked. */
 int lmcu_cache_trim(int device);
+int lmcu_cache_stats(int device, int64_t* parked_bytes, int64_t* parked_blocks);
 /* Measured read bandwidth of the L2 (GB/s) over a `bytes`-sized buffer that every CTA streams repeatedly: the roofline
  * denominator for traversal of an L2-resident BVH (bench.py). */
 int lmcu_probe_l2_bandwidth(int device, int64_t bytes, double* gb_per_s);

@@ -965,9 +965,11 @@ __global__ void __launch_bounds__(256) k_film_reduce_slice(FilmSet films, int nu
 // (device, size), at most kCacheBytes per process, and handed out again on the next equal-sized request.
 namespace {
 struct BlockCache {
+    struct Parked { void* p; uint64_t seq; };
     std::mutex mu;
-    std::multimap<std::pair<int, size_t>, void*> blocks;
+    std::multimap<std::pair<int, size_t>, Parked> blocks;
     std::map<int, size_t> bytes;           // parked bytes per device
+    uint64_t clock = 0;
     size_t cap = size_t(24) << 30;         // per DEVICE; LMCU_CACHE_GB overrides it (0 = park nothing)
     static constexpr size_t kMaxBlocks = 8192;
     BlockCache() { if (const char* e = getenv("LMCU_CACHE_GB")) cap = (size_t)(atof(e) * double(size_t(1) << 30)); }
@@ -975,7 +977,7 @@ struct BlockCache {
         std::lock_guard<std::mutex> lk(mu);
         auto it = blocks.find({ device, n });
         if (it == blocks.end()) return nullptr;
-        void* p = it->second;
+        void* p = it->second.p;
         blocks.erase(it);
         bytes[device] -= n;
         return p;
@@ -984,8 +986,8 @@ struct BlockCache {
     void flush(int device) {
         std::lock_guard<std::mutex> lk(mu);
         for (auto it = blocks.begin(); it != blocks.end();) {
-            if (it->first.first == device && !exported.count(it->second)) {
-                cudaFree(it->second); bytes[device] -= it->first.second; it = blocks.erase(it);
+            if (it->first.first == device && !exported.count(it->second.p)) {
+                cudaFree(it->second.p); bytes[device] -= it->first.second; it = blocks.erase(it);
             }
             else ++it;
         }
@@ -994,11 +996,26 @@ struct BlockCache {
     // undefined behaviour — so it is parked whatever its size and the cap, for the life of the process.
     std::set<void*> exported;
     void mark_exported(void* p) { std::lock_guard<std::mutex> lk(mu); exported.insert(p); }
+    // Over the cap the blocks parked LONGEST ago make room (a process that built a 50 M-triangle scene once would otherwise
+    // sit on its temporaries for good while the path pools of every later scene go back and forth to the driver).
     bool park(int device, size_t n, void* p) {
         std::lock_guard<std::mutex> lk(mu);
         const bool keep = exported.count(p) != 0;
-        if (!keep && (bytes[device] + n > cap || blocks.size() >= kMaxBlocks)) return false;
-        blocks.insert({ { device, n }, p });
+        if (!keep) {
+            if (n > cap) return false;
+            while (bytes[device] + n > cap || blocks.size() >= kMaxBlocks) {
+                auto victim = blocks.end();
+                for (auto it = blocks.begin(); it != blocks.end(); ++it) {
+                    if (it->first.first != device || exported.count(it->second.p)) continue;
+                    if (victim == blocks.end() || it->second.seq < victim->second.seq) victim = it;
+                }
+                if (victim == blocks.end()) return false;
+                cudaFree(victim->second.p);
+                bytes[device] -= victim->first.second;
+                blocks.erase(victim);
+            }
+        }
+        blocks.insert({ { device, n }, Parked{ p, ++clock } });
         bytes[device] += n;
         return true;
     }
@@ -1897,6 +1914,16 @@ int lmcu_cache_trim(int device) {
     CU(cudaSetDevice(device));
     CU(cudaDeviceSynchronize());
     g_cache.flush(device);
+    return LMCU_OK;
+}
+
+int lmcu_cache_stats(int device, int64_t* parked_bytes, int64_t* parked_blocks) {
+    if (device < 0 || device >= lmcu_device_count()) return fail(LMCU_ERR_INVALID_ARGUMENT, "bad device index");
+    std::lock_guard<std::mutex> lk(g_cache.mu);
+    int64_t nb = 0;
+    for (const auto& b : g_cache.blocks) if (b.first.first == device) nb++;
+    if (parked_bytes) *parked_bytes = (int64_t)g_cache.bytes[device];
+    if (parked_blocks) *parked_blocks = nb;
     return LMCU_OK;
 }
 

@@ -21,7 +21,7 @@ _LIB = None
 EXPORTS = [
     "lmcu_last_error", "lmcu_device_count", "lmcu_version", "lmcu_scene_create", "lmcu_scene_destroy",
     "lmcu_scene_set_stream", "lmcu_scene_upload", "lmcu_accel_build", "lmcu_accel_intersect", "lmcu_accel_intersect1", "lmcu_accel_intersect_device",
-    "lmcu_cache_trim", "lmcu_probe_l2_bandwidth",
+    "lmcu_cache_trim", "lmcu_cache_stats", "lmcu_probe_l2_bandwidth",
     "lmcu_accel_intersect_counted", "lmcu_accel_save_size", "lmcu_accel_save", "lmcu_accel_load", "lmcu_render_raycast", "lmcu_render_ao", "lmcu_render_pt", "lmcu_render_lt", "lmcu_render_bdpt",
     "lmcu_film_device_ptr", "lmcu_film_rescale", "lmcu_film_download",
     "lmcu_film_ipc_export", "lmcu_ipc_open", "lmcu_ipc_close", "lmcu_enable_peer_access", "lmcu_film_reduce_peers", "lmcu_film_reduce_slice",
@@ -58,6 +58,13 @@ def device_count():
 
 def cache_trim(device=0):
     _check(lib().lmcu_cache_trim(int(device)))
+
+
+def cache_stats(device=0):
+    """(bytes, blocks) parked in the library's device-block cache."""
+    b, n = C.c_int64(), C.c_int64()
+    _check(lib().lmcu_cache_stats(int(device), C.byref(b), C.byref(n)))
+    return b.value, n.value
 
 
 def probe_l2_bandwidth(device=0, nbytes=32 << 20):

@@ -761,3 +761,24 @@ def test_bdpt_kernels_equal_the_one_thread_form(scene, tmp_path):
         assert abs(st["rays"] - ss.rays) <= 1e-3 * ss.rays          # a vertex on a decision boundary may round differently (libm vs CUDA)
         assert np.allclose(fg, fs, rtol=1e-3, atol=1e-4 * float(fs.max()))
     sc.close()
+
+
+@pytest.mark.parametrize("cap_gb", [0.02, 24.0])
+def test_block_cache_cap_and_lru(cap_gb):
+    """The library recycles device blocks (path pools, films, builder temporaries) through a per-device cache: never more than
+    LMCU_CACHE_GB parked (the blocks parked longest ago make room), the most recent sizes stay available, results do not depend
+    on it, lmcu_cache_trim() empties it."""
+    import json
+    import subprocess
+    env = dict(os.environ, LMCU_CACHE_GB=str(cap_gb), PYTHONPATH=os.pathsep.join(sys.path))
+    r = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "cache_child.py"), str(cap_gb)],
+                       capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    for b, n in out["parked"]:
+        assert 0 < b <= out["cap"] and n > 0
+    assert out["reuse"][0] == out["reuse"][1]                 # the second build of the last scene found every block parked
+    assert out["after_trim"] == [0, 0]
+    assert all(0.02 < m < 1.0 for m in out["film_means"])
+    if cap_gb < 1:
+        assert max(b for b, _ in out["parked"]) > 0.5 * out["cap"]          # the small cap was actually reached
