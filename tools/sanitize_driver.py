@@ -21,16 +21,18 @@ import lmcu  # noqa: E402
 from lmcu import abi, scenes  # noqa: E402
 
 
-def run_scene(name, sb, w=48, h=27, spp=2, lt=True, bdpt=True):
-    sc = lmcu.Scene(sb, device=0)
+def run_scene(name, sb, w=48, h=27, spp=2, lt=True, bdpt=True, two_level=-1):
+    sc = lmcu.Scene(sb, device=0, two_level=two_level)
+    assert sc.build_stats.two_level == (1 if two_level > 0 else 0)
     rays = scenes.camera_rays(sb.camera, w, h)
     hits = sc.intersect(rays)
     sc.intersect(rays[:64], counted=True)
     sc.intersect1(rays[len(rays) // 2])
-    blob = sc.save_accel()
-    sc2 = lmcu.Scene(sb, device=0, accel_blob=blob)
-    assert (sc2.intersect(rays)["face"] == hits["face"]).all()
-    sc2.close()
+    if two_level <= 0:                                          # a two-level accel is rebuilt, not serialised
+        blob = sc.save_accel()
+        sc2 = lmcu.Scene(sb, device=0, accel_blob=blob)
+        assert (sc2.intersect(rays)["face"] == hits["face"]).all()
+        sc2.close()
     sc.render("raycast", abi.render_params(w, h))
     sc.render("raycast", abi.render_params(w, h, visualize_normal=True))
     sc.render("ao", abi.render_params(w, h, spp=spp))
@@ -66,6 +68,16 @@ def run_scene(name, sb, w=48, h=27, spp=2, lt=True, bdpt=True):
 
 def main():
     tmp = tempfile.mkdtemp()
+    # the two-level layout: per-mesh trees + tree over the primitives, object-space walk, surface points through instances
+    run_scene("two-level instanced+env", scenes.instanced_spheres(grid=2, num_theta=8, env=scenes.env_light(os.path.join(tmp, "e2.hdr"), 64, 32)),
+              two_level=1)
+    run_scene("two-level textured obj", scenes.textured_scene(tmp, 8, "obj"), two_level=1)
+    run_scene("two-level affine", scenes.affine_instances(1, 12, 6), two_level=1, lt=False, bdpt=False)
+    run_scene("two-level cornell_box", scenes.cornell_box(True), two_level=1)
+    if len(sys.argv) > 1 and sys.argv[1] == "two_level":
+        lmcu.cache_trim(0)
+        print("driver done")
+        return
     run_scene("cornell_box", scenes.cornell_box(True))
     run_scene("cornell_spheres", scenes.cornell_spheres(8))
     run_scene("instanced+envconst", scenes.instanced_spheres(grid=2, num_theta=8))
