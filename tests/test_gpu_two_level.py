@@ -85,6 +85,22 @@ def test_two_level_under_general_affine_transforms(reference, seed):
     rs.close(); flat.close(); two.close()
 
 
+@pytest.mark.parametrize("nf_list", [[1], [1, 1, 1], [2, 1], [3, 7, 1]])
+def test_two_level_ragged_and_tiny_meshes(nf_list):
+    """Meshes of 1, 2, 3 and 7 triangles (mesh trees whose root is a leaf cluster, a top level of 3 .. 9 instances)."""
+    from test_hostsim import _tiny_instanced
+    sb = _tiny_instanced(nf_list)
+    flat, two = lmcu.Scene(sb, two_level=-1), lmcu.Scene(sb, two_level=1)
+    assert two.build_stats.two_level == 1
+    rays = np.concatenate([scenes.camera_rays(sb.camera, 96, 96), scenes.random_rays(20000, np.array([-2, -2, -2.]), np.array([2, 2, 2.]))])
+    hf, ht = flat.intersect(rays), two.intersect(rays)
+    assert _same_hits(hf, ht) == 0 and (ht["primitive"] >= 0).sum() > 300
+    for i in range(0, len(rays), 2503):
+        h1 = two.intersect1(rays[i])
+        assert h1["primitive"] == ht[i]["primitive"] and h1["t"] == ht[i]["t"]
+    flat.close(); two.close()
+
+
 def test_two_level_tmin_tmax_window_and_any_hit():
     sb = scenes.instanced_spheres(grid=3, num_theta=16)
     flat, two = lmcu.Scene(sb, two_level=-1), lmcu.Scene(sb, two_level=1)

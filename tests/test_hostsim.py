@@ -323,3 +323,28 @@ def test_two_level_under_general_affine_transforms(reference, sim, seed):
     rs = reference.RefScene(sb)
     assert_hit_parity(rs.intersect(rays[:20000]), hb[:20000], max_special=2)
     rs.close()
+
+
+def _tiny_instanced(nf_list, seed=0):
+    rng = np.random.RandomState(seed)
+    sb = scenes.SceneBuilder()
+    for nf in nf_list:
+        tri = scenes._f32(rng.rand(nf, 3, 3) * 2 - 1)
+        m = sb.add_mesh(tri, scenes.flat_normals(tri))
+        for _ in range(3):
+            sb.add_primitive(m, sb.diffuse((.5, .5, .5)), M=scenes.translate(rng.uniform(-1, 1, 3)) @ scenes.rotate(rng.rand() * 360, rng.randn(3)))
+    sb.set_camera(position=(0, 0, 6), center=(0, 0, 0), up=(0, 1, 0), vfov=40, aspect=1)
+    return sb
+
+
+@pytest.mark.parametrize("nf_list", [[1], [1, 1, 1], [2, 1], [3, 7, 1]])
+def test_two_level_ragged_and_tiny_meshes(sim, nf_list):
+    """Meshes of 1, 2, 3 and 7 triangles (mesh trees whose root is a leaf cluster, a top level of 3 .. 9 instances)."""
+    sb = _tiny_instanced(nf_list)
+    a, b = sim.SimScene(sb, two_level=-1), sim.SimScene(sb, two_level=1)
+    assert b.two_level
+    rays = np.concatenate([scenes.camera_rays(sb.camera, 96, 96), scenes.random_rays(20000, np.array([-2, -2, -2.]), np.array([2, 2, 2.]))])
+    ha, hb = a.intersect(rays), b.intersect(rays)
+    assert (ha["primitive"] >= 0).sum() > 300
+    for k in ("primitive", "face", "t", "u", "v"):
+        assert (ha[k] == hb[k]).all(), k
