@@ -227,7 +227,7 @@ typedef struct LmcuBuildOptions {
                                                 over the flattened scene.  Same hits (the leaf test transforms the vertices
                                                 with the flattened build's operations); memory and build time follow the
                                                 UNIQUE triangle count (C4: 4.95 MB and 10 ms against 4.75 GB and 40 ms); the
-                                                walk is slower (C4: 0.73 x the flattened tree's paths per second: an
+                                                walk is slower (C4: 0.78 x the flattened tree's paths per second: an
                                                 object-space ray per instance entered, a vertex transform per leaf test).
                                                 1 = on (when every transform is an invertible affine map), -1 = off,
                                                 0 = automatic: flattened while it fits — two-level only when the flattened

@@ -281,7 +281,7 @@ inline bool make_inst(const PrimDev& pr, uint32_t prim, uint32_t root, InstDev& 
     return true;
 }
 
-// LmcuBuildOptions::two_level resolved against the scene.  The flattened tree is the faster one to walk (C4: 477 against 347
+// LmcuBuildOptions::two_level resolved against the scene.  The flattened tree is the faster one to walk (C4: 477 against 370
 // Mpaths/s — the two-level walk pays an object-space ray per instance entered and a vertex transform per leaf test), so the
 // automatic choice keeps it while it fits: two-level only for an instanced scene (flattened triangles >= 4 x the unique ones)
 // whose flattened build (~475 bytes per triangle at its peak: 155 resident + the builder's temporaries) would take more than
