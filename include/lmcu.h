@@ -165,6 +165,13 @@ enum { LMCU_PRIMARY_PIXEL = 0,        /* one pixel per sample index, scheduler::
 /* scheduler (src/scheduler.cpp): "sample" = fixed spp / num_samples (:37-49,131-141), "time" = whole passes until
  * render_time seconds have elapsed (:75-103,162-187) */
 enum { LMCU_SCHED_SAMPLE = 0, LMCU_SCHED_TIME = 1 };
+/* The strategies (s light vertices, t eye vertices) lmcu_render_bdpt evaluates per sample.  ALL is renderer::bdpt: every
+ * connection, power-heuristic weights.  The other three are the reference's single-strategy renderers on the same path
+ * structure (src/renderer/renderer_bdpt.cpp), each connection UNWEIGHTED (Path::eval_sampling_weight_bidir only): */
+enum { LMCU_BDPT_ALL = 0,
+       LMCU_BDPT_PT_NAIVE = 1,        /* renderer::pt_naive_path (:63-124): (0, t), the eye subpath hits a light */
+       LMCU_BDPT_PT_NEE = 2,          /* renderer::pt_nee_path (:129-200): (1, n-1), or (0, n) when eye vertex n-2 is specular */
+       LMCU_BDPT_LT_NEE = 3 };        /* renderer::lt_nee_path (:205-288): (n-1, 1), the light subpath connects to the pinhole */
 
 typedef struct LmcuRenderParams {
     int32_t width, height;                   /* film size */
@@ -198,7 +205,7 @@ typedef struct LmcuRenderParams {
     void (*progress)(void* user, int64_t processed_paths, int64_t total_paths, double elapsed_seconds);
     void* progress_user;
     int32_t min_verts;                       /* bdpt: minimum number of path vertices (0 = 2, renderer_bdpt.cpp:51) */
-    int32_t reserved_;
+    int32_t bdpt_strategies;                 /* bdpt: LMCU_BDPT_* — which connections (s, t) a sample evaluates (default all) */
 } LmcuRenderParams;
 
 typedef struct LmcuRenderStats {
@@ -319,7 +326,9 @@ int lmcu_render_lt(LmcuScene* scene, const LmcuRenderParams* p, float* film_rgb,
  * to max_verts vertices (no Russian roulette), every connection (s, t) with min_verts <= s + t <= max_verts, power-heuristic
  * weights over all strategies of the connected path.  Keys used: max_verts (2..20), min_verts (0 = 2), seed, scheduler (sample:
  * num_samples; time: render_time, samples_per_iter), sample_offset, rescale (film *= w*h/processed, :390-391).  Image-space
- * scheduler only (renderer_bdpt.cpp:54-56). */
+ * scheduler only (renderer_bdpt.cpp:54-56).  bdpt_strategies selects renderer::pt_naive_path / pt_nee_path / lt_nee_path: the
+ * same subpaths and connections restricted to one strategy family, without weights; the subpath no strategy extends is
+ * not walked past its endpoint. */
 int lmcu_render_bdpt(LmcuScene* scene, const LmcuRenderParams* p, float* film_rgb, LmcuRenderStats* stats);
 /* Device film of the last render (width*height*3 floats) for the multi-GPU film reduce
  * (sample split: every rank renders with rescale=0, NCCL-reduces this buffer, then scales). */

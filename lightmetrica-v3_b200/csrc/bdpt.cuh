@@ -386,6 +386,7 @@ LMCU_HD int bdpt_subpath(const DevScene& s, const PtParams& p, uint64_t sidx, bo
     F3 o, d;
     bdpt_first_vertex(s, p, sidx, light_side, vs[0], o, d);
     n = 1;
+    if (max_verts == 1) return n;       // only the endpoint is used (the single-strategy modes)
     while (true) {
         HitD h;
         if (!pt_trace<false, false, TriT>(s, make_float4(o.x, o.y, o.z, (float)kEps), make_float4(d.x, d.y, d.z, (float)kInf), h, stack, nullptr)) ctr->overflow = 1u;
@@ -538,6 +539,10 @@ LMCU_HD bool bdpt_connect(const DevScene& s, const PtParams& p, int sL, int t, c
         out.sh_d = make_float4(w.x, w.y, w.z, dist * (1.0f - (float)kEps));
     }
     if (is_zero(C) || !(C.x == C.x) || !(C.y == C.y) || !(C.z == C.z)) return false;
+    if (p.bdpt_mode != 0u) {            // pt_naive_path / pt_nee_path / lt_nee_path: Path::eval_sampling_weight_bidir alone
+        out.C = C;
+        return true;
+    }
     // -- the densities around the connecting edge; full path x_0 (light) .. x_{n-1} (camera), x_i = Y(i) for i < sL and
     // Z(n-1-i) above.  fL[i] / fE[i] = density of generating x_i from the light / eye side:
     // p_{s'} = prod_{i < s'} fL[i] * prod_{i >= s'} fE[i].
@@ -600,6 +605,24 @@ LMCU_HD bool bdpt_connect(const DevScene& s, const PtParams& p, int sL, int t, c
     return true;
 }
 
+// Which connections (sL, t) a sample evaluates (LmcuRenderParams::bdpt_strategies).  zspec(j) = eye vertex j is a delta
+// interaction; only asked for vertices the strategy's eye subpath length implies.
+//   1  renderer::pt_naive_path (renderer_bdpt.cpp:80-93): the eye subpath alone, (0, t)
+//   2  renderer::pt_nee_path (:150-170): (1, n-1) unless eye vertex n-2 is specular, then (0, n)
+//   3  renderer::lt_nee_path (:228-233): (n-1, 1)
+template <typename ZSpec>
+LMCU_HD bool bdpt_strategy_on(uint32_t mode, int sL, int t, const ZSpec& zspec) {
+    switch (mode) {
+    case 1u: return sL == 0;
+    case 2u: return sL == 1 ? !zspec(t - 1) : (sL == 0 && t >= 2 && zspec(t - 2));
+    case 3u: return t == 1;
+    default: return true;
+    }
+}
+// longest eye / light subpath any active strategy reads
+LMCU_HD int bdpt_eye_max(uint32_t mode, int max_verts) { return mode == 3u ? 1 : max_verts; }
+LMCU_HD int bdpt_light_max(uint32_t mode, int max_verts) { return mode == 1u ? 0 : (mode == 2u ? 1 : max_verts); }
+
 // Subpath data in local arrays (the one-thread-per-sample form below)
 struct BdptLocalAcc {
     const BVert* ys; const BVert* zs;
@@ -640,8 +663,8 @@ LMCU_HD void bdpt_sample(const DevScene& s, const PtParams& p, int min_verts, ui
     float pcE[kBdptMaxVerts], pcL[kBdptMaxVerts];
     float zF[kBdptMaxVerts], zR[kBdptMaxVerts], yF[kBdptMaxVerts], yR[kBdptMaxVerts];
     bool zSpec[kBdptMaxVerts], ySpec[kBdptMaxVerts];
-    const int nE = bdpt_subpath<TriT, COMP>(s, p, sidx, false, p.max_verts, zs, stack, ctr);
-    const int nL = bdpt_subpath<TriT, COMP>(s, p, sidx, true, p.max_verts, ys, stack, ctr);
+    const int nE = bdpt_subpath<TriT, COMP>(s, p, sidx, false, bdpt_eye_max(p.bdpt_mode, p.max_verts), zs, stack, ctr);
+    const int nL = bdpt_subpath<TriT, COMP>(s, p, sidx, true, bdpt_light_max(p.bdpt_mode, p.max_verts), ys, stack, ctr);
     bdpt_alphas<COMP>(s, zs, nE, false, aE, pcE);
     bdpt_alphas<COMP>(s, ys, nL, true, aL, pcL);
     bdpt_subpath_pdfs<COMP>(s, zs, nE, zF, zR, zSpec);
@@ -654,6 +677,7 @@ LMCU_HD void bdpt_sample(const DevScene& s, const PtParams& p, int min_verts, ui
         for (int t = 1; t <= nE; t++) {                     // t = 0: a light subpath never hits the pinhole (bidir.h:600-606,626-629)
             const int n = sL + t;
             if (n < min_verts || n > p.max_verts || n < 2) continue;
+            if (!bdpt_strategy_on(p.bdpt_mode, sL, t, [&](int j) { return zSpec[j]; })) continue;
             BdptConn c;
             if (!bdpt_connect<COMP>(s, p, sL, t, acc, eye_pixel, c)) continue;
             if (c.shadow) {

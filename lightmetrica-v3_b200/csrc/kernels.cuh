@@ -417,6 +417,7 @@ struct PtParams {
     uint32_t image_mode;        // primary_ray_sampling_mode = image: the raster window is the whole film (renderer_pt.cpp:104-106)
     uint32_t light_tracing;     // renderer::lt: paths start on the lights and connect to the camera (renderer_lt.cpp)
     uint32_t chunk;             // pixel mode: consecutive path indices walk `chunk` samples of one pixel before the next pixel
+    uint32_t bdpt_mode;         // bdpt: LMCU_BDPT_* (lmcu.h) — all strategies with MIS weights, or one unweighted strategy family
 };
 
 // RNG counter word 0 of a path's primary sample in image mode (no pixel is known before the raster position is drawn)

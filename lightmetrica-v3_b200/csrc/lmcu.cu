@@ -458,9 +458,12 @@ __global__ void __launch_bounds__(256) k_bdpt_gen(DevScene s, PtParams p, BdptSt
             st.ve[o0] = make_float2(bv_specular<false>(s, v) ? -pa : pa, 0.f);
             if (!side) st.eye_pixel[g] = 0u;
         }
-        ro[i] = make_float4(o.x, o.y, o.z, (float)kEps);
-        rd[i] = make_float4(d.x, d.y, d.z, (float)kInf);
-        id[i] = i;
+        // single-strategy modes walk one side only (bdpt_eye_max / bdpt_light_max): its rays fill the queue from slot 0
+        if (p.bdpt_mode != 0u && (side != 0) != (p.bdpt_mode == 3u)) continue;
+        const uint32_t slot = p.bdpt_mode == 3u ? g : i;
+        ro[slot] = make_float4(o.x, o.y, o.z, (float)kEps);
+        rd[slot] = make_float4(d.x, d.y, d.z, (float)kInf);
+        id[slot] = i;
     }
 }
 
@@ -524,7 +527,8 @@ __global__ void __launch_bounds__(256) k_bdpt_lists(PtParams p, BdptStore st, co
     uint32_t* mine = list + (size_t)blockIdx.y * st.cap;
     for (uint32_t base = blockIdx.x * blockDim.x; base < total; base += gridDim.x * blockDim.x) {
         const uint32_t i = base + threadIdx.x;
-        const bool ok = i < total && pr.y <= st.nverts[i] && pr.x <= st.nverts[(size_t)st.cap + i];
+        bool ok = i < total && pr.y <= st.nverts[i] && pr.x <= st.nverts[(size_t)st.cap + i];
+        if (ok && p.bdpt_mode != 0u) ok = bdpt_strategy_on(p.bdpt_mode, pr.x, pr.y, [&](int j) { return signbit(st.ve[st.at(0, j, i)].x); });
         const uint32_t b = __ballot_sync(0xffffffffu, ok);
         if (b) {
             uint32_t pos = 0;
@@ -1200,7 +1204,8 @@ int lmcu_scene_create(int device, LmcuScene** out) {
     if (n == 0) return fail(LMCU_ERR_NO_DEVICE, "no CUDA device: liblmcu has no CPU fallback");
     if (device < 0 || device >= n) return fail(LMCU_ERR_INVALID_ARGUMENT, "bad device index");
     CU(cudaSetDevice(device));
-    LmcuScene* s = new LmcuScene;
+    struct Guard { LmcuScene* s; ~Guard() { if (s) lmcu_scene_destroy(s); } } guard{ new LmcuScene };   // no leak on an error return
+    LmcuScene* s = guard.s;
     s->device = device;
     CU(cudaDeviceGetAttribute(&s->num_sms, cudaDevAttrMultiProcessorCount, device));
     CU(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking));
@@ -1219,6 +1224,9 @@ int lmcu_scene_create(int device, LmcuScene** out) {
     CU(s->flags.alloc(4));
     CU(cudaMemset(s->cursor.p, 0, (8 + LmcuScene::kCursorRing) * sizeof(unsigned long long)));
     CU(cudaMemset(s->flags.p, 0, 4 * sizeof(uint32_t)));
+    // cudaMemset is asynchronous and runs on the legacy default stream, which the scene's non-blocking streams do not wait for
+    CU(cudaStreamSynchronize(0));
+    guard.s = nullptr;
     *out = s;
     return LMCU_OK;
 }
@@ -1300,6 +1308,9 @@ int lmcu_scene_upload(LmcuScene* s, const LmcuSceneDesc* d) {
     if (!ps.mix.empty()) CU(cudaMemcpy(s->mix.p, ps.mix.data(), ps.mix.size() * sizeof(MixEntry), cudaMemcpyHostToDevice));
     CU(s->prims.alloc(ps.prims.size()));
     CU(cudaMemcpy(s->prims.p, ps.prims.data(), ps.prims.size() * sizeof(PrimDev), cudaMemcpyHostToDevice));
+    // a cudaMemcpy from pageable memory may return once the data is staged, and the memsets above are asynchronous: both sit on
+    // the legacy default stream, which the scene's non-blocking streams do not wait for
+    CU(cudaStreamSynchronize(0));
     s->built = false;
     return LMCU_OK;
 }
@@ -1523,6 +1534,7 @@ int lmcu_accel_build(LmcuScene* s, const LmcuBuildOptions* opts, LmcuBuildStats*
         k_sah_cost<<<grid_for(s->nodes.n, 256), 256, 0, st>>>(s->nodes.p, (uint32_t)s->nodes.n, cost.p);
         CU(cudaGetLastError());
         CU(cudaMemcpyAsync(h_cost, cost.p, sizeof(h_cost), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));      // before `cost` goes back to the block cache
     }
     CU(cudaStreamSynchronize(st));
     s->built = true;
@@ -1740,6 +1752,7 @@ int lmcu_accel_load(LmcuScene* s, const void* buffer, int64_t bytes) {
         s->num_prims = (int)h.num_prims;
         s->blob_desc_digest = h.desc_digest;
     }
+    CU(cudaStreamSynchronize(0));           // the pageable copies above (legacy default stream) have landed
     s->built = true;
     return LMCU_OK;
 }
@@ -1821,6 +1834,7 @@ static int intersect_host(LmcuScene* s, const LmcuRay* rays, int64_t n, LmcuHit*
     CU(cudaSetDevice(s->device));
     DBuf<LmcuRay> d_rays;
     DBuf<LmcuHit> d_hits;
+    SyncOnExit sync_on_exit{ s->stream };   // destroyed before the buffers: an early error return never parks a block a kernel still writes
     CU(d_rays.alloc(n)); CU(d_hits.alloc(n));
     CU(cudaMemcpyAsync(d_rays.p, rays, (size_t)n * sizeof(LmcuRay), cudaMemcpyHostToDevice, s->stream));
     const int rc = launch_intersect(s, d_rays.p, n, d_hits.p, count, s->stream);
@@ -2482,6 +2496,8 @@ int lmcu_render_bdpt(LmcuScene* s, const LmcuRenderParams* p, float* film_rgb, L
     }
     if (p->max_verts < 2 || p->max_verts > kBdptMaxVerts) return fail(LMCU_ERR_INVALID_ARGUMENT, "bdpt: max_verts must be in 2..20");
     const int min_verts = p->min_verts > 0 ? p->min_verts : 2;
+    const int mode = p->bdpt_strategies;
+    if (mode < LMCU_BDPT_ALL || mode > LMCU_BDPT_LT_NEE) return fail(LMCU_ERR_INVALID_ARGUMENT, "bdpt: bad bdpt_strategies");
     CU(cudaSetDevice(s->device));
     rc = ensure_film(s, p->width, p->height, true);
     if (rc) return rc;
@@ -2490,14 +2506,20 @@ int lmcu_render_bdpt(LmcuScene* s, const LmcuRenderParams* p, float* film_rgb, L
     PtParams pp{};
     pp.width = p->width; pp.height = p->height; pp.max_verts = p->max_verts; pp.seed = p->seed;
     pp.image_mode = 1u;
+    pp.bdpt_mode = (uint32_t)mode;
     const DevScene d = s->dev();
     const unsigned fold_blocks = (unsigned)std::min<size_t>((s->film.n + 255) / 256, (size_t)s->num_sms * 8);
     const auto t0 = std::chrono::steady_clock::now();
     int64_t processed = 0, launches = 0;
     // strategies (s, t) with min_verts <= s + t <= max_verts (renderer_bdpt.cpp:350-361); t = 0 never connects to a pinhole
     std::vector<int2> pairs;
+    // the single-strategy renderers (:80-93,150-170,228-233) keep one family; pt_nee_path picks between (1, n-1) and
+    // (0, n) per sample (k_bdpt_lists: bdpt_strategy_on)
     for (int n = std::max(2, min_verts); n <= p->max_verts; n++)
-        for (int sL = 0; sL < n; sL++) pairs.push_back(make_int2(sL, n - sL));
+        for (int sL = 0; sL < n; sL++) {
+            if ((mode == LMCU_BDPT_PT_NAIVE && sL != 0) || (mode == LMCU_BDPT_PT_NEE && sL > 1) || (mode == LMCU_BDPT_LT_NEE && sL != n - 1)) continue;
+            pairs.push_back(make_int2(sL, n - sL));
+        }
     if (pairs.empty()) return fail(LMCU_ERR_INVALID_ARGUMENT, "bdpt: min_verts exceeds max_verts");
     // samples per pass: the shadow queue holds one entry per (strategy, sample), at most 32 Mi (1.5 GB)
     LmcuScene::BdptPools& B = s->bdpt;
@@ -2535,7 +2557,7 @@ int lmcu_render_bdpt(LmcuScene* s, const LmcuRenderParams* p, float* film_rgb, L
             pp.sample_offset = (uint64_t)p->sample_offset + (uint64_t)processed;
             pp.total_paths = (uint64_t)n;
             pp.capacity = cap;
-            k_bdpt_reset<<<1, 1, 0, st>>>(B.ctr.p, (uint32_t)(2 * n));
+            k_bdpt_reset<<<1, 1, 0, st>>>(B.ctr.p, (uint32_t)(mode == LMCU_BDPT_ALL ? 2 * n : n));   // rays k_bdpt_gen enqueues
             const unsigned gen_blocks = (unsigned)std::min<int64_t>((2 * n + 255) / 256, (int64_t)s->num_sms * 8);
             const unsigned vtx_blocks = (unsigned)std::min<int64_t>((2 * n + 127) / 128, (int64_t)s->num_sms * 8);
             k_bdpt_gen<<<gen_blocks, 256, 0, st>>>(d, pp, store, B.q_o[0].p, B.q_d[0].p, B.q_id[0].p);

@@ -33,6 +33,7 @@ LIGHT_AREA, LIGHT_ENVCONST, LIGHT_ENV, LIGHT_POINT, LIGHT_DIRECTIONAL = 0, 1, 2,
 SAMPLING_NAIVE, SAMPLING_NEE, SAMPLING_MIS = 0, 1, 2
 PRIMARY_PIXEL, PRIMARY_IMAGE = 0, 1
 SCHED_SAMPLE, SCHED_TIME = 0, 1
+BDPT_ALL, BDPT_PT_NAIVE, BDPT_PT_NEE, BDPT_LT_NEE = 0, 1, 2, 3      # LmcuRenderParams::bdpt_strategies
 
 
 class LmcuTexture(C.Structure):
@@ -78,7 +79,7 @@ class LmcuRenderParams(C.Structure):
                 ("samples_per_iter", C.c_int64), ("render_time", C.c_double),
                 ("wavefronts", C.c_int32), ("ao_mark_misses", C.c_int32),
                 ("progress", C.c_void_p), ("progress_user", C.c_void_p),
-                ("min_verts", C.c_int32), ("reserved_", C.c_int32)]
+                ("min_verts", C.c_int32), ("bdpt_strategies", C.c_int32)]
 
 
 PROGRESS_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int64, C.c_int64, C.c_double)
@@ -108,7 +109,7 @@ def render_params(width, height, spp=1, max_verts=20, seed=42, sampling_mode=SAM
                   visualize_normal=False, color=None, ao_distance=0.2, count_traversal=False,
                   primary_ray_sampling_mode=PRIMARY_PIXEL, scheduler=SCHED_SAMPLE, num_samples=0,
                   samples_per_iter=0, render_time=0.0, wavefronts=0, ao_mark_misses=False, progress=None,
-                  min_verts=0):
+                  min_verts=0, bdpt_strategies=0):
     """Defaults follow the reference renderers' JSON defaults (renderer_pt.cpp:51-77,
     renderer_raycast.cpp:48-60, functest/renderer_ao.cpp:36-40)."""
     p = LmcuRenderParams()
@@ -125,6 +126,7 @@ def render_params(width, height, spp=1, max_verts=20, seed=42, sampling_mode=SAM
     p.wavefronts = wavefronts
     p.ao_mark_misses = int(ao_mark_misses)
     p.min_verts = min_verts
+    p.bdpt_strategies = bdpt_strategies
     if progress is not None:                      # a PROGRESS_FN instance; the params object keeps it alive
         p._progress_ref = progress
         p.progress = C.cast(progress, C.c_void_p)

@@ -1276,6 +1276,48 @@ class Renderer_BDPT_Cuda final : public Renderer_SPI_CudaBase {
 
 LM_COMP_REG_IMPL(Renderer_BDPT_Cuda, "renderer::bdpt_cuda");
 
+/*
+\rst
+.. function:: renderer::bdptopt_cuda
+
+   ``renderer::bdptopt`` (src/renderer/renderer_bdptopt.cpp) is the estimator of ``renderer::bdpt`` with its MIS weights
+   computed incrementally; on the device there is one implementation, so this key runs ``renderer::bdpt_cuda``.
+
+.. function:: renderer::pt_naive_path_cuda
+.. function:: renderer::pt_nee_path_cuda
+.. function:: renderer::lt_nee_path_cuda
+
+   The reference's single-strategy renderers on the path structure (src/renderer/renderer_bdpt.cpp:63-124, 129-200,
+   205-288): the subpaths and connections of ``renderer::bdpt_cuda`` restricted to one strategy family — the eye subpath
+   alone, (0, t); next-event estimation, (1, n-1), or (0, n) behind a specular vertex; the light subpath connected to the
+   pinhole, (n-1, 1) — each connection unweighted (``LmcuRenderParams::bdpt_strategies``).  Parameters as
+   ``renderer::bdpt_cuda``.
+\endrst
+*/
+class Renderer_BDPTOpt_Cuda final : public Renderer_SPI_CudaBase {
+    virtual int launch(LmcuScene* h, const LmcuRenderParams* p, float* target, LmcuRenderStats* st) const override {
+        return lmcu_render_bdpt(h, p, target, st);
+    }
+};
+
+LM_COMP_REG_IMPL(Renderer_BDPTOpt_Cuda, "renderer::bdptopt_cuda");
+
+template <int Strategies>
+class Renderer_PathStrategy_Cuda final : public Renderer_SPI_CudaBase {
+    virtual int launch(LmcuScene* h, const LmcuRenderParams* p, float* target, LmcuRenderStats* st) const override {
+        LmcuRenderParams q = *p;
+        q.bdpt_strategies = Strategies;
+        return lmcu_render_bdpt(h, &q, target, st);
+    }
+};
+using Renderer_PT_Naive_Path_Cuda = Renderer_PathStrategy_Cuda<LMCU_BDPT_PT_NAIVE>;
+using Renderer_PT_NEE_Path_Cuda = Renderer_PathStrategy_Cuda<LMCU_BDPT_PT_NEE>;
+using Renderer_LT_NEE_Path_Cuda = Renderer_PathStrategy_Cuda<LMCU_BDPT_LT_NEE>;
+
+LM_COMP_REG_IMPL(Renderer_PT_Naive_Path_Cuda, "renderer::pt_naive_path_cuda");
+LM_COMP_REG_IMPL(Renderer_PT_NEE_Path_Cuda, "renderer::pt_nee_path_cuda");
+LM_COMP_REG_IMPL(Renderer_LT_NEE_Path_Cuda, "renderer::lt_nee_path_cuda");
+
 LM_NAMESPACE_END(LM_NAMESPACE)
 
 // Batched rays for hosts that hold numpy / torch buffers (func_accel_consistency-style notebooks): `accel_loc` is the

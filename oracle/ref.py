@@ -39,8 +39,15 @@ def init(num_threads=-0, verbose=False):
     return lib().lmref_num_threads()
 
 
+_PLUGINS = set()
+
+
 def load_plugin(path):
+    """lm::comp::load_plugin, once per path and process (test modules share one reference instance)."""
+    if path in _PLUGINS:
+        return
     _check(lib().lmref_load_plugin(path.encode()))
+    _PLUGINS.add(path)
 
 
 class RefScene:

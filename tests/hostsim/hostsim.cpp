@@ -501,6 +501,7 @@ int hostsim_bdpt(void* p, const LmcuRenderParams* rp, float* film, long long* ra
     pp.width = rp->width; pp.height = rp->height; pp.max_verts = rp->max_verts; pp.seed = rp->seed;
     pp.sample_offset = (uint64_t)rp->sample_offset;
     pp.image_mode = 1u;
+    pp.bdpt_mode = (uint32_t)rp->bdpt_strategies;
     pp.total_paths = (uint64_t)rp->num_samples;
     if (rp->max_verts > kBdptMaxVerts) { g_err = "max_verts too large"; return 1; }
     const int min_verts = rp->min_verts > 0 ? rp->min_verts : 2;

@@ -256,6 +256,30 @@ def test_bdpt_statistics(reference, sim, scene):
     rs.close()
 
 
+@pytest.mark.parametrize("scene", ["spheres", "env"])
+@pytest.mark.parametrize("name,mode", [("pt_naive_path", abi.BDPT_PT_NAIVE), ("pt_nee_path", abi.BDPT_PT_NEE),
+                                       ("lt_nee_path", abi.BDPT_LT_NEE)])
+def test_single_strategy_path_renderers(reference, sim, scene, name, mode):
+    """LmcuRenderParams::bdpt_strategies: the bdpt device code restricted to one unweighted strategy family against the
+    reference's renderer::pt_naive_path / pt_nee_path / lt_nee_path (src/renderer/renderer_bdpt.cpp:63-288).  The glass
+    sphere exercises pt_nee_path's switch to (0, n) behind a specular vertex."""
+    sb = scenes.cornell_spheres(12) if scene == "spheres" else scenes.instanced_spheres(grid=2, num_theta=10)
+    rs, ss = reference.RefScene(sb), sim.SimScene(sb)
+    w, h, spp = 64, 36, 48
+    kw = dict(max_verts=6, num_samples=w * h * spp, primary_ray_sampling_mode=abi.PRIMARY_IMAGE)
+    fr, _, processed = rs.render("renderer::" + name, abi.render_params(w, h, **kw))
+    assert processed == w * h * spp
+    fs = ss.render("bdpt", abi.render_params(w, h, bdpt_strategies=mode, **kw))
+    assert fs.mean() > 0
+    assert_pt_parity(fr, fs, spp, rel_mean=0.02)
+    if scene == "spheres" and mode != abi.BDPT_LT_NEE:
+        # complete estimators of the image renderer::bdpt converges to (lt_nee_path has no strategy for a path whose
+        # vertex before the pinhole is specular, and with a light at infinity (1, n-1) never connects: as in the reference)
+        fb = ss.render("bdpt", abi.render_params(w, h, **kw))
+        assert_pt_parity(fb, fs, spp, rel_mean=0.02)
+    rs.close()
+
+
 @pytest.mark.parametrize("grid,num_theta", [(3, 12), (2, 24)])
 def test_two_level_layout_equals_flattened(sim, grid, num_theta):
     """LmcuBuildOptions::two_level (one tree per mesh in object space + one over the instances; leaf test on vertices
