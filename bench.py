@@ -319,6 +319,14 @@ def bdpt_rate(sc, abi, sb):
     out = {"samples": n, "max_verts": mv, "msamples_per_s": st["paths"] / st["elapsed"] / 1e6,
            "mrays_per_s": st["rays"] / st["elapsed"] / 1e6, "rays_per_sample": st["rays"] / st["paths"],
            "kernels": "k_bdpt_gen, then per vertex index k_pt_extend_q -> k_bdpt_vertex (random walks as a wavefront) -> k_bdpt_lists (per-strategy work lists) -> k_bdpt_connect (one thread per (strategy, sample), strategy-major) -> k_pt_shadow_q"}
+    # the reference's single-strategy renderers on the same path structure (renderer_bdpt.cpp:63-288): bdpt_strategies
+    films = {}
+    try:
+        for name, mode in (("pt_naive_path", abi.BDPT_PT_NAIVE), ("pt_nee_path", abi.BDPT_PT_NEE), ("lt_nee_path", abi.BDPT_LT_NEE)):
+            films[name], ss = sc.render("bdpt", abi.render_params(W, H, num_samples=n, bdpt_strategies=mode, **kw))
+            out[name] = {"msamples_per_s": ss["paths"] / ss["elapsed"] / 1e6, "rays_per_sample": ss["rays"] / ss["paths"]}
+    except Exception as ex:
+        out["single_strategy_failed"] = str(ex)
     try:
         from oracle import ref
         if ref.available():
@@ -328,6 +336,10 @@ def bdpt_rate(sc, abi, sb):
             fr, elapsed, processed = rs.render("renderer::bdpt", abi.render_params(W, H, num_samples=nr, **kw))
             out["cpu_reference"] = {"samples": int(processed), "msamples_per_s": processed / elapsed / 1e6, "threads": threads,
                                     "rel_mean_diff": float(abs(film.mean() - fr.mean()) / fr.mean())}
+            for name, f in films.items():
+                fr, elapsed, processed = rs.render("renderer::" + name, abi.render_params(W, H, num_samples=nr, **kw))
+                out[name]["cpu_reference"] = {"samples": int(processed), "msamples_per_s": processed / elapsed / 1e6, "threads": threads,
+                                              "rel_mean_diff": float(abs(f.mean() - fr.mean()) / fr.mean())}
             rs.close()
     except Exception as ex:
         out["cpu_reference"] = {"failed": str(ex)}
