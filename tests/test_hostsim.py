@@ -256,21 +256,25 @@ def test_bdpt_statistics(reference, sim, scene):
     rs.close()
 
 
-@pytest.mark.parametrize("scene", ["spheres", "env"])
+@pytest.mark.parametrize("scene", ["spheres", "env", "delta", "obj", "mix"])
 @pytest.mark.parametrize("name,mode", [("pt_naive_path", abi.BDPT_PT_NAIVE), ("pt_nee_path", abi.BDPT_PT_NEE),
                                        ("lt_nee_path", abi.BDPT_LT_NEE)])
-def test_single_strategy_path_renderers(reference, sim, scene, name, mode):
+def test_single_strategy_path_renderers(reference, sim, tmp_path, scene, name, mode):
     """LmcuRenderParams::bdpt_strategies: the bdpt device code restricted to one unweighted strategy family against the
     reference's renderer::pt_naive_path / pt_nee_path / lt_nee_path (src/renderer/renderer_bdpt.cpp:63-288).  The glass
-    sphere exercises pt_nee_path's switch to (0, n) behind a specular vertex."""
-    sb = scenes.cornell_spheres(12) if scene == "spheres" else scenes.instanced_spheres(grid=2, num_theta=10)
+    sphere exercises pt_nee_path's switch to (0, n) behind a specular vertex; also: a constant environment (a light at
+    infinity connects through no (1, n-1)), point + directional lights (degenerated endpoints: pt_naive_path stays black
+    in the reference too), the OBJ-import material set and the constant-weight mixtures."""
+    sb = {"spheres": lambda: scenes.cornell_spheres(12), "env": lambda: scenes.instanced_spheres(grid=2, num_theta=10),
+          "delta": lambda: scenes.delta_lights_scene(2, 16), "obj": lambda: scenes.textured_scene(tmp_path, 12, "obj"),
+          "mix": lambda: scenes.textured_scene(tmp_path, 12, "mix")}[scene]()
     rs, ss = reference.RefScene(sb), sim.SimScene(sb)
     w, h, spp = 64, 36, 48
     kw = dict(max_verts=6, num_samples=w * h * spp, primary_ray_sampling_mode=abi.PRIMARY_IMAGE)
     fr, _, processed = rs.render("renderer::" + name, abi.render_params(w, h, **kw))
     assert processed == w * h * spp
     fs = ss.render("bdpt", abi.render_params(w, h, bdpt_strategies=mode, **kw))
-    assert fs.mean() > 0
+    assert fs.mean() > 0 or (scene == "delta" and mode == abi.BDPT_PT_NAIVE and fr.max() == 0)
     assert_pt_parity(fr, fs, spp, rel_mean=0.02)
     if scene == "spheres" and mode != abi.BDPT_LT_NEE:
         # complete estimators of the image renderer::bdpt converges to (lt_nee_path has no strategy for a path whose
