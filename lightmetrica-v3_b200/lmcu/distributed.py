@@ -66,6 +66,18 @@ def render_pt_sample_split(render_sums, total_spp, rank, world, dist=None):
     return reduce_and_rescale(film, total_spp, rank, world, dist)
 
 
+def render_spi_sample_split(render_sums, num_samples, num_pixels, rank, world, dist=None):
+    """The same split for the renderers on the image-space scheduler (scheduler::spi::*: renderer::lt, bdpt, the
+    single-strategy path renderers, pt with primary_ray_sampling_mode = image): a sample is one path whose contributions
+    land on arbitrary pixels, rank r renders the contiguous block of the `num_samples` sample indices that sample_block
+    gives it (LmcuRenderParams: num_samples = count, sample_offset = offset, rescale = 0), the films are summed on rank 0
+    and scaled ONCE by num_pixels / num_samples (renderer_lt.cpp:162, renderer_bdpt.cpp:390-391).
+    render_sums(sample_offset, count) -> torch tensor of per-pixel sums.  A rank whose block is empty contributes zeros."""
+    offset, count = sample_block(num_samples, rank, world)
+    film = render_sums(offset, count)
+    return reduce_and_rescale(film, float(num_samples) / float(num_pixels), rank, world, dist)
+
+
 class SceneFilmOps:
     """The `ops` of PeerFilmReducer for an lmcu.Scene (or, with `scene` a callable, for whichever scene it returns at the
     time of the call: a host that re-creates its scene per render keeps ONE reducer and its cached mappings as long as

@@ -147,6 +147,41 @@ def test_sample_split_reduce(tmp_path, world, total_spp):
     assert torch.allclose(got, want, atol=1e-6)
 
 
+def _spi_worker(rank, world, port, num_samples, npix, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    def render_sums(offset, count):                      # stand-in light tracer: sample i splats onto an arbitrary pixel
+        film = torch.zeros(npix * 3)
+        for i in range(offset, offset + count):
+            px = (i * 7 + 3) % npix
+            film[px * 3:px * 3 + 3] += _fake_sample_image(i, 1)
+        return film
+
+    film = D.render_spi_sample_split(render_sums, num_samples, npix, rank, world, dist)
+    if rank == 0:
+        torch.save(film, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,num_samples", [(2, 50), (3, 2)])
+def test_image_space_sample_split(tmp_path, world, num_samples):
+    """lt / bdpt style split: blocks of path indices, arbitrary-pixel splats, one rescale by pixels / samples on rank 0
+    (with 2 samples on 3 ranks one rank owns an empty block)."""
+    npix = 12
+    out = str(tmp_path / "film.pt")
+    mp.spawn(_spi_worker, args=(world, _free_port(), num_samples, npix, out), nprocs=world, join=True)
+    got = torch.load(out)
+    want = torch.zeros(npix * 3)
+    for i in range(num_samples):
+        px = (i * 7 + 3) % npix
+        want[px * 3:px * 3 + 3] += _fake_sample_image(i, 1)
+    want *= npix / num_samples
+    assert torch.allclose(got, want, atol=1e-6)
+
+
 def test_sample_blocks_tile_the_range():
     for total in (1, 7, 16, 1024, 16384):
         for world in (1, 2, 3, 4, 8):
