@@ -44,6 +44,25 @@ def test_struct_sizes_match_header(tmp_path):
     assert RAY_DTYPE.itemsize == 64 and HIT_DTYPE.itemsize == 32
 
 
+def test_field_offsets_match_header(tmp_path):
+    """... and every field sits at the offset gcc gives it (same names in both; a reordered or retyped field that keeps the
+    struct size would otherwise go unnoticed)."""
+    import subprocess
+    from lmcu import abi
+    names = ["LmcuRay", "LmcuHit", "LmcuMesh", "LmcuPrimitive", "LmcuTexture", "LmcuMaterial", "LmcuLight", "LmcuCamera",
+             "LmcuSceneDesc", "LmcuRenderParams", "LmcuRenderStats", "LmcuBuildOptions", "LmcuBuildStats"]
+    pairs = [(n, f[0]) for n in names for f in getattr(abi, n)._fields_]
+    src = tmp_path / "offsets.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "lmcu.h"\nint main(void) {\n' +
+                   "".join('  printf("%s.%s %%zu\\n", offsetof(%s, %s));\n' % (n, f, n, f) for n, f in pairs) + "  return 0;\n}\n")
+    exe = tmp_path / "offsets"
+    subprocess.check_call(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    got = dict(line.split() for line in subprocess.check_output([str(exe)]).decode().splitlines())
+    assert len(pairs) > 100
+    for n, f in pairs:
+        assert getattr(getattr(abi, n), f).offset == int(got["%s.%s" % (n, f)]), (n, f)
+
+
 def test_no_cpu_fallback_without_device():
     """Without a CUDA device the product must fail loudly (LMCU_ERR_NO_DEVICE), never compute on the CPU."""
     import lmcu
