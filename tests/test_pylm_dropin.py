@@ -72,8 +72,13 @@ def render(lm, renderer_key, film_key="bitmap", w=160, h=90, **kw):
 def test_plugin_registers_its_components_in_the_reference_registry(lm):
     keys = []
     lm.comp.foreach_registered(lambda k: keys.append(k))
-    for k in ("accel::cuda_bvh", "renderer::raycast_cuda", "renderer::ao_cuda", "renderer::pt_cuda", "renderer::lt_cuda", "renderer::bdpt_cuda", "film::cuda"):
+    for k in ("accel::cuda_bvh", "renderer::raycast_cuda", "renderer::ao_cuda", "renderer::pt_cuda", "renderer::lt_cuda", "renderer::bdpt_cuda",
+              "renderer::bdptopt_cuda", "renderer::pt_naive_path_cuda", "renderer::pt_nee_path_cuda", "renderer::lt_nee_path_cuda", "film::cuda"):
         assert k in keys
+    # every renderer the reference registers on this path has a device counterpart under '<key>_cuda'
+    for k in keys:
+        if k.startswith("renderer::") and not k.endswith("_cuda") and k not in ("renderer::blank", "renderer::volpt", "renderer::volpt_naive"):
+            assert k + "_cuda" in keys, k
     # the reference's own pipeline through its Python API (CPU): accel::sahbvh + renderer::raycast
     scene = build_scene(lm, "sahbvh")
     scene.build()
