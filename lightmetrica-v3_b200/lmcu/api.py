@@ -150,9 +150,17 @@ class Scene:
 
     # -- Renderer ---------------------------------------------------------------------------------
     def render(self, renderer, params, download=True):
-        """renderer: 'raycast' | 'ao' | 'pt' | 'lt' | 'bdpt'.  Returns (film[h,w,3] float32 or None, stats dict)."""
+        """renderer: 'raycast' | 'ao' | 'pt' | 'lt' | 'bdpt' | 'bdptopt', or one of the reference's single-strategy renderers
+        'pt_naive_path' | 'pt_nee_path' | 'lt_nee_path' (= 'bdpt' with params.bdpt_strategies set accordingly, on a copy).
+        Returns (film[h,w,3] float32 or None, stats dict)."""
+        strategies = {"pt_naive_path": abi.BDPT_PT_NAIVE, "pt_nee_path": abi.BDPT_PT_NEE, "lt_nee_path": abi.BDPT_LT_NEE}
+        if renderer in strategies:
+            caller_params = params                      # keeps what the copy points at (progress callback) alive
+            params = abi.LmcuRenderParams.from_buffer_copy(caller_params)
+            params.bdpt_strategies = strategies[renderer]
+            renderer = "bdpt"
         fn = {"raycast": lib().lmcu_render_raycast, "ao": lib().lmcu_render_ao, "pt": lib().lmcu_render_pt, "lt": lib().lmcu_render_lt,
-              "bdpt": lib().lmcu_render_bdpt}[renderer]
+              "bdpt": lib().lmcu_render_bdpt, "bdptopt": lib().lmcu_render_bdpt}[renderer]
         film = np.empty((params.height, params.width, 3), dtype=np.float32) if download else None
         st = abi.LmcuRenderStats()
         _check(fn(self._h, C.byref(params), film.ctypes.data_as(C.c_void_p) if download else None, C.byref(st)))
