@@ -76,3 +76,18 @@ def test_plugin_path_strategy_renderers(reference):
         assert pr == pc == w * h * spp, name
         assert_pt_parity(fr, fc, spp, rel_mean=0.02)
     rs.close()
+
+
+def test_python_mirror_takes_the_reference_renderer_names():
+    """lmcu.Scene.render('pt_naive_path' | 'pt_nee_path' | 'lt_nee_path' | 'bdptopt') = 'bdpt' with bdpt_strategies set on a
+    copy of the caller's parameters (same samples, same image)."""
+    sc = lmcu.Scene(scenes.cornell_spheres(12))
+    w, h = 64, 36
+    kw = dict(max_verts=6, num_samples=w * h * 16, primary_ray_sampling_mode=abi.PRIMARY_IMAGE)
+    for name, mode in MODES + [("bdptopt", abi.BDPT_ALL)]:
+        p = abi.render_params(w, h, **kw)
+        a, _ = sc.render(name, p)
+        b, _ = sc.render("bdpt", abi.render_params(w, h, bdpt_strategies=mode, **kw))
+        assert p.bdpt_strategies == 0
+        assert a.mean() > 0 and np.allclose(a, b, rtol=1e-4, atol=1e-6), name
+    sc.close()
