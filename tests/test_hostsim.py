@@ -309,6 +309,13 @@ def test_two_level_layout_equals_flattened(sim, grid, num_theta):
     assert np.array_equal(fa, fb) and fa.mean() > 0.1
     p = abi.render_params(32, 18, spp=2, ao_distance=0.5)
     assert np.array_equal(a.render("ao", p), b.render("ao", p))
+    # the light tracer, the bidirectional path tracer and its single-strategy forms read their vertices through the same
+    # surface-point code: identical images on both layouts
+    for renderer, mode in (("lt", abi.BDPT_ALL), ("bdpt", abi.BDPT_ALL), ("bdpt", abi.BDPT_PT_NAIVE), ("bdpt", abi.BDPT_PT_NEE),
+                           ("bdpt", abi.BDPT_LT_NEE)):
+        p = abi.render_params(32, 18, max_verts=6, num_samples=32 * 18 * 4, bdpt_strategies=mode, primary_ray_sampling_mode=abi.PRIMARY_IMAGE)
+        fa, fb = a.render(renderer, p), b.render(renderer, p)
+        assert np.array_equal(fa, fb) and fa.mean() > 0.01, (renderer, mode)
 
 
 def test_two_level_vs_reference_and_policy(reference, sim, tmp_path):
