@@ -53,6 +53,9 @@ def run_scene(name, sb, w=48, h=27, spp=2, lt=True, bdpt=True, two_level=-1):
                                                            primary_ray_sampling_mode=abi.PRIMARY_IMAGE))
             assert np.isfinite(film).all() and st["rays"] > 0
         sc.render("bdpt", abi.render_params(w, h, max_verts=5, scheduler=abi.SCHED_TIME, render_time=0.02, samples_per_iter=1000))
+        for name in ("pt_naive_path", "pt_nee_path", "lt_nee_path"):      # single-strategy forms: one-sided walks, per-sample strategy choice
+            film, st = sc.render(name, abi.render_params(w, h, max_verts=6, num_samples=w * h * spp, primary_ray_sampling_mode=abi.PRIMARY_IMAGE))
+            assert np.isfinite(film).all() and st["rays"] > 0
     # film combine kernels on one device (the peer pointers are this scene's own film)
     sc.render("pt", abi.render_params(w, h, spp=spp, max_verts=4, rescale=0), download=False)
     ptr = sc.film_device()[0]
